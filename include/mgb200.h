@@ -1,0 +1,225 @@
+/* mgb200.h -- C ABI of libmgb200.so, the B200-native replacement of minigraph's seed-chain-align hot path.
+ *
+ * The library is a drop-in for the mapping entry points of the reference: it keeps the symbol names, argument
+ * meaning and ownership rules of minigraph.h so that the unmodified C host (main.c, gfa-*.c, bseq.c, format.c,
+ * options.c, kthread.c ...) links against it.  Struct layouts below are binary compatible with the reference
+ * headers they cite; they are restated here (not included) so that the library builds without the reference tree.
+ * If the reference headers are included first (MINIGRAPH_H / __GFA_H__ defined), the restated types are skipped.
+ *
+ * Every entry point needs a CUDA device (sm_100a); there is no CPU fallback: without a device mg_index() returns
+ * NULL after printing an error, and mgb_last_error() tells why.
+ */
+#ifndef MGB200_H
+#define MGB200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Types restated from the reference (binary compatible)
+ * ---------------------------------------------------------------------------------------------------------- */
+#ifndef __GFA_H__
+#define __GFA_H__ /* the restated declarations below stand in for gfa.h */
+typedef struct { /* gfa.h:33-39 */
+	uint64_t v_lv;
+	uint32_t w;
+	int32_t rank;
+	int32_t ov, ow;
+	uint64_t link_id:61, strong:1, del:1, comp:1;
+} gfa_arc_t;
+
+typedef struct { uint32_t m_aux, l_aux; uint8_t *aux; } gfa_aux_t; /* gfa.h:50-53 */
+
+typedef struct gfa_utg_s gfa_utg_t; /* gfa.h:55-63, opaque here */
+
+typedef struct { /* gfa.h:65-74 */
+	int32_t len;
+	uint32_t del:16, circ:16;
+	int32_t snid;
+	int32_t soff;
+	int32_t rank;
+	char *name, *seq;
+	gfa_utg_t *utg;
+	gfa_aux_t aux;
+} gfa_seg_t;
+
+typedef struct { char *name; int32_t min, max, rank; } gfa_sseq_t; /* gfa.h:82-85 */
+
+typedef struct { /* gfa.h:89-101 */
+	uint32_t m_seg, n_seg, max_rank;
+	gfa_seg_t *seg;
+	void *h_names;
+	uint32_t m_sseq, n_sseq;
+	gfa_sseq_t *sseq;
+	void *h_snames;
+	uint64_t m_arc, n_arc;
+	gfa_arc_t *arc;
+	gfa_aux_t *link_aux;
+	uint64_t *idx;
+} gfa_t;
+
+typedef struct { const char *seq; int32_t len; } gfa_edseq_t; /* gfa.h:103-106 */
+#endif
+
+#ifndef MINIGRAPH_H
+#define MINIGRAPH_H /* the restated declarations below stand in for minigraph.h */
+#define MG_M_RMQ    0x8000      /* minigraph.h:24 */
+#define MG_M_CIGAR  0x4000000   /* minigraph.h:35 */
+
+typedef struct { uint64_t x, y; } mg128_t; /* minigraph.h:41 */
+
+typedef struct { int w, k; int bucket_bits; } mg_idxopt_t; /* minigraph.h:46-49 */
+
+typedef struct { /* minigraph.h:51-77 */
+	uint64_t flag;
+	int64_t mini_batch_size;
+	int seed;
+	int max_qlen;
+	int pe_ori;
+	int occ_max1, occ_max1_cap;
+	float occ_max1_frac;
+	int bw, bw_long;
+	int rmq_size_cap;
+	int rmq_rescue_size;
+	float rmq_rescue_ratio;
+	int max_gap_pre, max_gap, max_gap_ref, max_frag_len;
+	float div;
+	float chn_pen_gap, chn_pen_skip;
+	int max_lc_skip, max_lc_iter, max_gc_skip;
+	int min_lc_cnt, min_lc_score;
+	int min_gc_cnt, min_gc_score;
+	int gdp_max_ed, lc_max_trim, lc_max_occ;
+	float mask_level;
+	int sub_diff;
+	int best_n;
+	float pri_ratio;
+	int ref_bonus;
+	int64_t cap_kalloc;
+	int min_cov_mapq, min_cov_blen;
+} mg_mapopt_t;
+
+typedef struct { /* minigraph.h:93-98 */
+	const gfa_t *g;
+	gfa_edseq_t *es;
+	int32_t b, w, k, flag, n_seg;
+	struct mg_idx_bucket_s *B; /* hidden: here it points to the engine's model (host copy + device image) */
+} mg_idx_t;
+
+typedef struct { int32_t off, cnt; uint32_t v; int32_t score; int32_t ed; } mg_llchain_t; /* minigraph.h:108-113 */
+
+typedef struct { /* minigraph.h:115-118 */
+	int32_t n_cigar, mlen, blen, aplen, ss, ee;
+	uint64_t cigar[];
+} mg_cigar_t;
+
+typedef struct { int32_t len, n_off, *off; char *ds; } mg_ds_t; /* minigraph.h:120-123 */
+
+typedef struct { /* minigraph.h:125-138 */
+	int32_t id, parent;
+	int32_t off, cnt;
+	int32_t n_anchor, score;
+	int32_t qs, qe;
+	int32_t plen, ps, pe;
+	int32_t blen, mlen;
+	float div;
+	uint32_t hash;
+	int32_t subsc, n_sub;
+	uint32_t mapq:8, flt:1, dummy:23;
+	mg_cigar_t *p;
+	mg_ds_t ds;
+} mg_gchain_t;
+
+typedef struct { /* minigraph.h:140-146 */
+	void *km;
+	int32_t n_gc, n_lc, n_a, rep_len;
+	mg_gchain_t *gc;
+	mg_llchain_t *lc;
+	mg128_t *a;
+} mg_gchains_t;
+
+typedef struct mg_tbuf_s mg_tbuf_t; /* minigraph.h:148, opaque */
+#endif
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Entry points that replace reference symbols one to one
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* replaces index.c:211-230 mg_index(): upper-cases the segments of g (index.c:215-220), returns NULL when the graph
+ * has overlapping links (index.c:192-196), builds the minimizer index, uploads graph+index to the GPU and updates
+ * mo->occ_max1 / lc_max_occ / bw_long exactly like options.c:120-134 mg_opt_update(). n_threads is ignored. */
+mg_idx_t *mg_index(gfa_t *g, const mg_idxopt_t *io, int n_threads, mg_mapopt_t *mo);
+
+/* replaces index.c:30-46 mg_idx_destroy() */
+void mg_idx_destroy(mg_idx_t *gi);
+
+/* replaces index.c:67-72 mg_idx_get(): host view of one occurrence list (ascending seg<<32|pos<<1|strand) */
+const uint64_t *mg_idx_get(const mg_idx_t *gi, uint64_t minier, int *n);
+
+/* replaces index.c:74-93 mg_idx_cal_quantile() */
+void mg_idx_cal_quantile(const mg_idx_t *gi, int32_t m, float f[], int32_t q[]);
+
+/* replace map-algo.c:14-27 mg_tbuf_init()/mg_tbuf_destroy(): the per-thread arena becomes a handle without state */
+mg_tbuf_t *mg_tbuf_init(void);
+void mg_tbuf_destroy(mg_tbuf_t *b);
+
+/* replaces map-algo.c:340-495 mg_map_frag() for n_segs == 1 (the only case the long-read presets produce):
+ * gcs[0] receives a malloc()ed result owned by the caller (free with mg_gchain_free), or NULL when the read is empty
+ * or longer than opt->max_qlen (map-algo.c:359-360). One read per launch: correct but slow -- use mg_map_batch. */
+void mg_map_frag(const mg_idx_t *gi, int n_segs, const int *qlens, const char **seqs, mg_gchains_t **gcs, mg_tbuf_t *b, const mg_mapopt_t *opt, const char *qname);
+
+/* replaces map-algo.c:497-502 mg_map() */
+mg_gchains_t *mg_map(const mg_idx_t *gi, int qlen, const char *seq, mg_tbuf_t *b, const mg_mapopt_t *opt, const char *qname);
+
+/* replaces gchain1.c:522-535 mg_gchain_free() (results are plain malloc/calloc blocks, km == NULL) */
+void mg_gchain_free(mg_gchains_t *gs);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * New entry point: the GPU batch dispatcher that replaces kt_for(worker_for) at gmap.c:99
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Map n_reads single-segment reads in one go. seqs[i] must be upper-case (gmap.c:81) and need not be 0-terminated;
+ * names[i] may be NULL. gcs[i] is filled exactly as worker_for() (gmap.c:29-64) would fill s->gcs[off].
+ * Returns 0, or a negative code after printing the reason (no partial results are left behind). */
+int mg_map_batch(const mg_idx_t *gi, int n_reads, const int *qlens, const char *const *seqs, const char *const *names,
+				 mg_gchains_t **gcs, const mg_mapopt_t *opt);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Engine controls and instrumentation (not part of the reference API)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+typedef struct {
+	double t_h2d_ms, t_seed_ms, t_chain_ms, t_align_ms, t_d2h_ms, t_host_ms; /* last batch, CUDA events / host clock */
+	int64_t n_reads, n_bases;
+	int64_t n_seeds;        /* sum of seeds entering the chaining kernel */
+	int64_t n_anchors_out;  /* sum of anchors kept in linear chains */
+	int64_t n_chains_out;   /* sum of linear chains out of the DP */
+	int64_t n_minimizers;
+	int64_t out_bytes;      /* result bytes copied back */
+	int64_t n_launches;     /* kernels launched for the batch */
+	int64_t n_retry;        /* reads re-run with a larger arena */
+	uint64_t arena_peak;    /* largest per-worker arena use */
+} mgb_stats_t;
+
+const char *mgb_last_error(void);
+void mgb_get_stats(const mg_idx_t *gi, mgb_stats_t *st);
+/* knobs: "arena_mb" (per worker), "workers_per_sm", "device"; returns 0 if the key is known */
+int mgb_set_param(const char *key, int64_t value);
+const char *mgb_version(void);
+
+/* Convenience for callers without a gfa_t (bench, tests): parse GFA/rGFA text the way gfa-io.c:294-337 gfa_read()
+ * does for S/L lines with SN/SO/SR tags and plain FASTA, and finalize arcs like gfa-base.c:421-430. */
+gfa_t *mgb_gfa_read(const char *fn);
+void mgb_gfa_destroy(gfa_t *g);
+
+/* Byte-exact GAF line(s) for one read, restating format.c:121-291 mg_write_gaf() for flag bits used by -c. The text is
+ * appended to *buf (realloc()ed, *len/*cap updated). */
+void mgb_write_gaf(char **buf, size_t *len, size_t *cap, const gfa_t *g, const mg_gchains_t *gs, int32_t qlen, const char *qname, uint64_t flag);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,283 @@
+// mgb_common.cuh -- shared device-side building blocks of the B200 mapping engine.
+//
+// Everything in csrc/*.cuh is written once as warp-cooperative device code.  The functions are
+// marked MG_HD so that the *same* source can also be compiled by g++ into tests/hostsim (a
+// single-lane simulator used only by the CPU-side unit tests to debug control flow in the
+// GPU-less build container).  The shipped library (libmgb200.so) contains only the CUDA build.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define MG_HD __host__ __device__
+#define MG_D __device__
+#else
+#define MG_HD
+#define MG_D
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define MGB_ON_DEVICE 1
+#else
+#define MGB_ON_DEVICE 0
+#endif
+
+namespace mgb {
+
+// ---- error codes (per read) ----
+enum {
+	MGB_OK = 0,
+	MGB_E_ARENA = -1,    // per-worker arena exhausted: the read is retried by the host with a larger arena
+	MGB_E_POOL = -2,     // a global output pool is exhausted: the batch is retried with larger pools
+	MGB_E_INTERNAL = -3, // invariant violated (the reference would assert/abort here)
+	MGB_E_UNSUPPORTED = -4
+};
+
+// ---- the universal 16-byte record (reference: minigraph.h:41 mg128_t) ----
+struct u128 { uint64_t x, y; };
+
+// seed flag bits (reference: mgpriv.h:18-27)
+static const uint64_t SEED_IGNORE = 1ULL << 41;
+static const uint64_t SEED_TANDEM = 1ULL << 42;
+static const uint64_t SEED_FIXED = 1ULL << 43;
+static const int SEED_SEG_SHIFT = 48;
+static const uint64_t SEED_SEG_MASK = 0xffULL << 48;
+static const int SEED_OCC_SHIFT = 56;
+static const int MAX_SHORT_K = 15;
+
+// ---- bump arena: one per worker (warp), stack discipline via mark/release ----
+struct Arena {
+	char *base;
+	uint64_t cap, top, peak;
+};
+
+MG_HD inline void arena_init(Arena &A, void *base, uint64_t cap) { A.base = (char*)base, A.cap = cap, A.top = 0, A.peak = 0; }
+
+MG_HD inline void *arena_alloc(Arena &A, uint64_t n_bytes)
+{
+	uint64_t n = (n_bytes + 15) & ~(uint64_t)15;
+	if (A.top + n > A.cap) return 0;
+	void *p = A.base + A.top;
+	A.top += n;
+	if (A.top > A.peak) A.peak = A.top;
+	return p;
+}
+
+#define MGB_ALLOC(A, ptr, type, n) do { \
+		(ptr) = (type*)mgb::arena_alloc((A), (uint64_t)sizeof(type) * (uint64_t)((n) > 0? (n) : 1)); \
+		if ((ptr) == 0) return mgb::MGB_E_ARENA; \
+	} while (0)
+
+#define MGB_TRY(expr) do { int _mgb_rc = (expr); if (_mgb_rc < 0) return _mgb_rc; } while (0)
+
+// growable vector living in an arena; growth abandons the old block (reclaimed when the caller releases its mark)
+template<typename T>
+struct AVec {
+	T *a;
+	int64_t n, m;
+};
+
+template<typename T>
+MG_HD inline void avec_init(AVec<T> &v) { v.a = 0, v.n = v.m = 0; }
+
+template<typename T>
+MG_HD inline int avec_reserve(Arena &A, AVec<T> &v, int64_t want)
+{
+	if (want <= v.m) return 0;
+	int64_t m = v.m? v.m : 16;
+	while (m < want) m += (m >> 1) + 16;
+	// extend in place when the vector is the topmost allocation of the arena
+	uint64_t old_bytes = ((uint64_t)sizeof(T) * (uint64_t)v.m + 15) & ~(uint64_t)15;
+	if (v.a && (char*)v.a + old_bytes == A.base + A.top) {
+		uint64_t new_bytes = ((uint64_t)sizeof(T) * (uint64_t)m + 15) & ~(uint64_t)15;
+		if ((uint64_t)((char*)v.a - A.base) + new_bytes > A.cap) return MGB_E_ARENA;
+		A.top = (uint64_t)((char*)v.a - A.base) + new_bytes;
+		if (A.top > A.peak) A.peak = A.top;
+		v.m = m;
+		return 0;
+	}
+	T *b = (T*)arena_alloc(A, (uint64_t)sizeof(T) * (uint64_t)m);
+	if (b == 0) return MGB_E_ARENA;
+	for (int64_t i = 0; i < v.n; ++i) b[i] = v.a[i];
+	v.a = b, v.m = m;
+	return 0;
+}
+
+template<typename T>
+MG_HD inline int avec_push(Arena &A, AVec<T> &v, const T &x)
+{
+	if (v.n == v.m) { int rc = avec_reserve(A, v, v.n + 1); if (rc < 0) return rc; }
+	v.a[v.n++] = x;
+	return 0;
+}
+
+// ---- global bump pool shared by all workers of one launch ----
+struct Pool {
+	unsigned long long used; // bytes
+	unsigned long long cap;
+};
+
+MG_HD inline int64_t pool_alloc(Pool *p, uint64_t n_bytes) // returns byte offset or -1
+{
+	unsigned long long n = (n_bytes + 15) & ~15ULL, off;
+#if MGB_ON_DEVICE
+	off = atomicAdd(&p->used, n);
+#else
+	off = p->used, p->used += n;
+#endif
+	if (off + n > p->cap) return -1;
+	return (int64_t)off;
+}
+
+// ---- hash functions that leak into results (reference: khashl.h:321-346, sketch.c:28-38) ----
+MG_HD inline uint32_t hash32(uint32_t key)
+{
+	key += ~(key << 15);
+	key ^= (key >> 10);
+	key += (key << 3);
+	key ^= (key >> 6);
+	key += ~(key << 11);
+	key ^= (key >> 16);
+	return key;
+}
+
+MG_HD inline uint32_t hash_str(const char *s)
+{
+	uint32_t h = (uint32_t)(int32_t)*s; // NB: plain char is signed on x86-64
+	if (h) for (++s; *s; ++s) h = (h << 5) - h + (uint32_t)(int32_t)*s;
+	return h;
+}
+
+MG_HD inline uint64_t hash64_mask(uint64_t key, uint64_t mask) // invertible integer hash restricted to 2k bits
+{
+	key = (~key + (key << 21)) & mask;
+	key = key ^ key >> 24;
+	key = ((key + (key << 3)) + (key << 8)) & mask;
+	key = key ^ key >> 14;
+	key = ((key + (key << 2)) + (key << 4)) & mask;
+	key = key ^ key >> 28;
+	key = (key + (key << 31)) & mask;
+	return key;
+}
+
+// fast log2 approximation used by the chaining penalties (reference: mgpriv.h:63-71); valid for x>=2
+MG_HD inline float fast_log2(float x)
+{
+	uint32_t i;
+#if MGB_ON_DEVICE
+	i = __float_as_uint(x);
+#else
+	memcpy(&i, &x, 4);
+#endif
+	float log_2 = (float)(int)(((i >> 23) & 255) - 128);
+	i &= ~(255u << 23);
+	i += 127u << 23;
+	float f;
+#if MGB_ON_DEVICE
+	f = __uint_as_float(i);
+	// no FMA contraction: the reference is built with -ffp-contract=off
+	log_2 = __fadd_rn(log_2, __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(-0.34484843f, f), 2.02466578f), f), -0.67487759f));
+#else
+	memcpy(&f, &i, 4);
+	log_2 += (-0.34484843f * f + 2.02466578f) * f - 0.67487759f;
+#endif
+	return log_2;
+}
+
+MG_HD inline int nt4(uint8_t c) // reference: sketch.c:9-26 seq_nt4_table
+{
+	switch (c) {
+	case 'A': case 'a': return 0;
+	case 'C': case 'c': return 1;
+	case 'G': case 'g': return 2;
+	case 'T': case 't': case 'U': case 'u': return 3;
+	case 0: return 0; case 1: return 1; case 2: return 2; case 3: return 3;
+	default: return 4;
+	}
+}
+
+// ---- bit-exact emulation of klib's in-place MSD radix sort (reference: ksort.h:112-162) ----
+// The sort is NOT stable; its tie order reaches the output, hence the exact replay of
+// the cycle-leader permutation.  Recursion is turned into an explicit range stack (children are
+// disjoint, so their processing order is irrelevant).  A digit on which all keys agree permutes
+// nothing, so such levels are skipped.
+template<typename T, typename KeyFn>
+MG_HD inline void rs_insertsort(T *beg, T *end, KeyFn key)
+{
+	for (T *i = beg + 1; i < end; ++i) {
+		if (key(*i) < key(*(i - 1))) {
+			T *j, tmp = *i;
+			for (j = i; j > beg && key(tmp) < key(*(j - 1)); --j) *j = *(j - 1);
+			*j = tmp;
+		}
+	}
+}
+
+struct RsRange { int32_t beg, end, s; };
+
+template<typename T, typename KeyFn>
+MG_HD inline int radix_sort_exact(Arena &A, T *a, int64_t n, int sizeof_key, KeyFn key)
+{
+	const int MIN_SIZE = 64;
+	if (n <= MIN_SIZE) { rs_insertsort(a, a + n, key); return 0; }
+	uint64_t mark = A.top;
+	RsRange *stack;
+	int64_t m_stack = n / MIN_SIZE + 272;
+	MGB_ALLOC(A, stack, RsRange, m_stack);
+	int32_t bb[256], be[256];
+	int64_t top = 0;
+	stack[top].beg = 0, stack[top].end = (int32_t)n, stack[top].s = (sizeof_key - 1) * 8, ++top;
+	while (top > 0) {
+		RsRange r = stack[--top];
+		int s = r.s;
+		// which digits vary inside this range?
+		uint64_t k_or = 0, k_and = ~0ULL;
+		for (int32_t i = r.beg; i < r.end; ++i) { uint64_t k = (uint64_t)key(a[i]); k_or |= k, k_and &= k; }
+		uint64_t diff = k_or ^ k_and;
+		while (s > 0 && ((diff >> s) & 0xff) == 0) s -= 8; // identity levels
+		if (s < 0) s = 0;
+		if (((diff >> s) & 0xff) == 0) continue; // s == 0 and nothing varies: all keys equal, order untouched
+		for (int k = 0; k < 256; ++k) bb[k] = 0;
+		for (int32_t i = r.beg; i < r.end; ++i) ++bb[(key(a[i]) >> s) & 0xff];
+		{
+			int32_t acc = r.beg;
+			for (int k = 0; k < 256; ++k) { int32_t c = bb[k]; bb[k] = acc; acc += c; be[k] = acc; }
+		}
+		for (int k = 0; k < 256;) { // cycle-leader permutation
+			if (bb[k] != be[k]) {
+				int l = (int)((key(a[bb[k]]) >> s) & 0xff);
+				if (l != k) {
+					T tmp = a[bb[k]], swap;
+					do {
+						swap = tmp; tmp = a[bb[l]]; a[bb[l]++] = swap;
+						l = (int)((key(tmp) >> s) & 0xff);
+					} while (l != k);
+					a[bb[k]++] = tmp;
+				} else ++bb[k];
+			} else ++k;
+		}
+		if (s) {
+			int s2 = s > 8? s - 8 : 0;
+			int32_t st = r.beg;
+			for (int k = 0; k < 256; ++k) {
+				int32_t en = be[k];
+				if (en - st > MIN_SIZE) {
+					if (top >= m_stack) { A.top = mark; return MGB_E_INTERNAL; }
+					stack[top].beg = st, stack[top].end = en, stack[top].s = s2, ++top;
+				} else if (en - st > 1) rs_insertsort(a + st, a + en, key);
+				st = en;
+			}
+		}
+	}
+	A.top = mark;
+	return 0;
+}
+
+struct KeyX128 { MG_HD uint64_t operator()(const u128 &p) const { return p.x; } };
+struct KeyU64 { MG_HD uint64_t operator()(const uint64_t &p) const { return p; } };
+
+MG_HD inline int radix_sort_128x(Arena &A, u128 *a, int64_t n) { return radix_sort_exact(A, a, n, 8, KeyX128()); }
+MG_HD inline int radix_sort_64(Arena &A, uint64_t *a, int64_t n) { return radix_sort_exact(A, a, n, 8, KeyU64()); }
+
+} // namespace mgb

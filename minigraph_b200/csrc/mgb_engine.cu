@@ -1,0 +1,741 @@
+// mgb_engine.cu -- host side of libmgb200.so: model construction, batch dispatcher and the C ABI (include/mgb200.h).
+//
+// Compiled by nvcc for sm_100a into the product library.  With -DMGB_HOSTSIM the same file is compiled by g++ into
+// tests/hostsim/libmgb_hostsim.so, where "device memory" is host memory and a "launch" is a loop over reads with a
+// single lane: that build exists only so that the CPU-only unit tests can exercise the control flow of the kernels.
+// It is never loaded by the product path; the product library refuses to work without a CUDA device.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+#include <algorithm>
+#include <string>
+#include <chrono>
+
+#include "../../include/mgb200.h"
+#include "mgb_galign.cuh"
+
+#ifndef MGB_HOSTSIM
+#include <cuda_runtime.h>
+#endif
+
+using namespace mgb;
+
+// ---------------------------------------------------------------------------------------------------------------
+// errors, parameters
+// ---------------------------------------------------------------------------------------------------------------
+
+static std::string g_last_error;
+static void set_error(const std::string &s) { g_last_error = s; fprintf(stderr, "[E::mgb200] %s\n", s.c_str()); }
+
+static int64_t p_arena_mb = 8;        // per worker, first pass
+static int64_t p_arena_big_mb = 1024; // per worker, retry pass
+static int64_t p_workers_per_sm = 16;
+static int64_t p_device = 0;
+static int64_t p_block_warps = 4;
+
+extern "C" const char *mgb_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char *mgb_version(void) { return "mgb200-r1"; }
+extern "C" int mgb_set_param(const char *key, int64_t value)
+{
+	if (!strcmp(key, "arena_mb")) p_arena_mb = value;
+	else if (!strcmp(key, "arena_big_mb")) p_arena_big_mb = value;
+	else if (!strcmp(key, "workers_per_sm")) p_workers_per_sm = value;
+	else if (!strcmp(key, "device")) p_device = value;
+	else if (!strcmp(key, "block_warps")) p_block_warps = value;
+	else return -1;
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// device memory shim
+// ---------------------------------------------------------------------------------------------------------------
+
+#ifdef MGB_HOSTSIM
+static bool dev_ok() { return true; }
+static void *dmalloc(size_t n) { void *p = malloc(n? n : 16); return p; }
+static void dfree(void *p) { free(p); }
+static void h2d(void *d, const void *h, size_t n) { if (n) memcpy(d, h, n); }
+static void d2h(void *h, const void *d, size_t n) { if (n) memcpy(h, d, n); }
+static void dzero(void *d, size_t n) { if (n) memset(d, 0, n); }
+static void dsync() {}
+static int dev_sm_count() { return 2; }
+static size_t dev_free_mem() { return (size_t)8 << 30; }
+#else
+#define CUDA_OK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { set_error(std::string(#call) + ": " + cudaGetErrorString(_e)); abort(); } } while (0)
+static bool dev_ok()
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return false;
+	if (cudaSetDevice((int)p_device) != cudaSuccess) return false;
+	return true;
+}
+static void *dmalloc(size_t n) { void *p = 0; CUDA_OK(cudaMalloc(&p, n? n : 16)); return p; }
+static void dfree(void *p) { if (p) cudaFree(p); }
+static void h2d(void *d, const void *h, size_t n) { if (n) CUDA_OK(cudaMemcpy(d, h, n, cudaMemcpyHostToDevice)); }
+static void d2h(void *h, const void *d, size_t n) { if (n) CUDA_OK(cudaMemcpy(h, d, n, cudaMemcpyDeviceToHost)); }
+static void dzero(void *d, size_t n) { if (n) CUDA_OK(cudaMemset(d, 0, n)); }
+static void dsync() { CUDA_OK(cudaDeviceSynchronize()); }
+static int dev_sm_count() { int v = 0; CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, (int)p_device)); return v; }
+static size_t dev_free_mem() { size_t f = 0, t = 0; CUDA_OK(cudaMemGetInfo(&f, &t)); return f; }
+#endif
+
+template<typename T> static T *dalloc_copy(const std::vector<T> &v)
+{
+	T *d = (T*)dmalloc(v.size() * sizeof(T));
+	h2d(d, v.data(), v.size() * sizeof(T));
+	return d;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------------
+
+struct LaunchArgs {
+	PipeCtx c;
+	ReadOut *routs;
+	const int32_t *rid_list; // NULL: reads 0..n-1
+	int32_t n_work;
+	char *arena_base;
+	uint64_t arena_bytes;
+	uint64_t *arena_peak;    // per worker
+	// segment sketch (index build)
+	Pool *pool_mz; u128 *mz;
+};
+
+template<int STAGE>
+MG_HD inline int run_stage(const LaunchArgs &L, int rid, Arena &A)
+{
+	if (STAGE == 0) return stage_seed(L.c, rid, A);
+	if (STAGE == 1) return stage_chain(L.c, rid, A);
+	if (STAGE == 2) return stage_align(L.c, L.routs, rid, A);
+	if (STAGE == 3) { // sketch one graph segment for the index (reference: index.c:200-205)
+		AVec<u128> mv;
+		avec_init(mv);
+		int32_t len = L.c.g.seg_len[rid];
+		if (len <= 0) return 0;
+		MGB_TRY(sketch_seq(A, g_vseq(L.c.g, (uint32_t)rid << 1), len, L.c.ix.w, L.c.ix.k, (uint32_t)rid, mv));
+		int64_t off = pool_alloc(L.pool_mz, (uint64_t)mv.n * sizeof(u128));
+		if (off < 0) return MGB_E_POOL;
+		u128 *dst = L.mz + off / (int64_t)sizeof(u128);
+		for (int64_t i = 0; i < mv.n; ++i) dst[i] = mv.a[i];
+		return 0;
+	}
+	return MGB_E_INTERNAL;
+}
+
+#ifndef MGB_HOSTSIM
+// One warp per work item; items are pulled from a global counter so that long reads do not stall a wave.
+// Round-1 scheme: lane 0 runs the (sequential, bit-exact) stage code, the other lanes idle at the barrier.
+template<int STAGE>
+__global__ void __launch_bounds__(128) k_stage(LaunchArgs L)
+{
+	const int lane = threadIdx.x & 31;
+	const int worker = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+	Arena A;
+	arena_init(A, L.arena_base + (uint64_t)worker * L.arena_bytes, L.arena_bytes);
+	for (;;) {
+		int item = 0;
+		if (lane == 0) item = (int)atomicAdd(L.c.next_read, 1u);
+		item = __shfl_sync(0xffffffffu, item, 0);
+		if (item >= L.n_work) break;
+		if (lane == 0) {
+			int rid = L.rid_list? L.rid_list[item] : item;
+			A.top = 0;
+			int rc = run_stage<STAGE>(L, rid, A);
+			if (rc < 0) {
+				if (STAGE == 3) atomicMin((int*)L.routs, rc); // routs reused as a single status word for the index build
+				else { L.c.meta[rid].status = rc; if (STAGE == 2) L.routs[rid].status = rc; }
+			}
+		}
+		__syncwarp();
+	}
+	if (lane == 0 && L.arena_peak) L.arena_peak[worker] = A.peak > L.arena_peak[worker]? A.peak : L.arena_peak[worker];
+}
+#endif
+
+struct Workers {
+	int n_workers;
+	uint64_t arena_bytes;
+	char *arena;
+	uint64_t *peak;
+};
+
+template<int STAGE>
+static void launch_stage(LaunchArgs &L, const Workers &W)
+{
+	L.arena_base = W.arena, L.arena_bytes = W.arena_bytes, L.arena_peak = W.peak;
+	unsigned int zero = 0;
+	h2d(L.c.next_read, &zero, sizeof(zero));
+#ifdef MGB_HOSTSIM
+	Arena A;
+	arena_init(A, W.arena, W.arena_bytes);
+	for (int item = 0; item < L.n_work; ++item) {
+		int rid = L.rid_list? L.rid_list[item] : item;
+		A.top = 0;
+		int rc = run_stage<STAGE>(L, rid, A);
+		if (rc < 0) {
+			if (STAGE == 3) { if (rc < *(int*)L.routs) *(int*)L.routs = rc; }
+			else { L.c.meta[rid].status = rc; if (STAGE == 2) L.routs[rid].status = rc; }
+		}
+	}
+	if (W.peak && A.peak > W.peak[0]) W.peak[0] = A.peak;
+#else
+	int threads = (int)p_block_warps * 32;
+	int blocks = (W.n_workers + (int)p_block_warps - 1) / (int)p_block_warps;
+	k_stage<STAGE><<<blocks, threads>>>(L);
+	CUDA_OK(cudaGetLastError());
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// model: flattened graph + minimizer index, host copy and device image
+// ---------------------------------------------------------------------------------------------------------------
+
+struct Model {
+	// host copies
+	std::vector<int32_t> seg_len;
+	std::vector<uint64_t> vseq_off;
+	std::vector<char> seq;
+	std::vector<uint64_t> arc_idx;
+	std::vector<DevArc> arc;
+	std::vector<u128> slot;
+	std::vector<uint64_t> pos;
+	std::vector<uint32_t> occ;      // occurrences per distinct minimizer (for the quantiles)
+	uint64_t n_slots_mask;
+	int k, w;
+	// device image
+	GraphDev g;
+	IndexDev ix;
+	std::vector<void*> dev_ptrs;
+	// per-model scratch reused across batches
+	Workers W, Wbig;
+	std::vector<float> logf_tab; float *d_logf; int n_logf;
+	mgb_stats_t stats;
+	gfa_edseq_t *es;
+};
+
+static void model_free(Model *M)
+{
+	for (void *p : M->dev_ptrs) dfree(p);
+	if (M->W.arena) dfree(M->W.arena);
+	if (M->W.peak) dfree(M->W.peak);
+	if (M->Wbig.arena) dfree(M->Wbig.arena);
+	if (M->Wbig.peak) dfree(M->Wbig.peak);
+	if (M->d_logf) dfree(M->d_logf);
+	delete M;
+}
+
+static unsigned char comp_tab[256];
+static void init_comp_tab() // reference: gfa-base.c:509-526 gfa_comp_table
+{
+	static const char *from = "ABCDEFGHIJKLMNOPQRSTUVWXYZ", *to = "TVGHEFCDIJMLKNOPQYSAABWXRZ";
+	for (int i = 0; i < 256; ++i) comp_tab[i] = (unsigned char)i;
+	for (int i = 0; i < 26; ++i) {
+		comp_tab[(unsigned char)from[i]] = (unsigned char)to[i];
+		comp_tab[(unsigned char)(from[i] + 32)] = (unsigned char)(to[i] + 32);
+	}
+}
+
+static void ensure_workers(Workers &W, int n_workers, uint64_t arena_bytes)
+{
+	if (W.arena && W.n_workers == n_workers && W.arena_bytes == arena_bytes) return;
+	if (W.arena) dfree(W.arena);
+	if (W.peak) dfree(W.peak);
+	W.n_workers = n_workers, W.arena_bytes = arena_bytes;
+	W.arena = (char*)dmalloc((size_t)n_workers * arena_bytes);
+	W.peak = (uint64_t*)dmalloc((size_t)n_workers * sizeof(uint64_t));
+	dzero(W.peak, (size_t)n_workers * sizeof(uint64_t));
+}
+
+static int default_workers()
+{
+#ifdef MGB_HOSTSIM
+	return 1;
+#else
+	return dev_sm_count() * (int)p_workers_per_sm;
+#endif
+}
+
+static Model *model_build(gfa_t *g, int k, int w)
+{
+	Model *M = new Model();
+	M->k = k, M->w = w, M->d_logf = 0, M->n_logf = 0, M->es = 0;
+	memset(&M->W, 0, sizeof(Workers)), memset(&M->Wbig, 0, sizeof(Workers));
+	memset(&M->stats, 0, sizeof(M->stats));
+	init_comp_tab();
+	const uint32_t n_seg = g->n_seg, n_vtx = n_seg * 2;
+	M->seg_len.resize(n_seg);
+	M->vseq_off.resize(n_vtx);
+	uint64_t tot = 0;
+	for (uint32_t i = 0; i < n_seg; ++i) {
+		M->seg_len[i] = g->seg[i].len;
+		M->vseq_off[i << 1] = tot, tot += (uint64_t)g->seg[i].len + 8;   // 8 bytes of slack after every copy
+		M->vseq_off[i << 1 | 1] = tot, tot += (uint64_t)g->seg[i].len + 8;
+	}
+	M->seq.assign(tot + 16, 0);
+	for (uint32_t i = 0; i < n_seg; ++i) {
+		const gfa_seg_t *s = &g->seg[i];
+		char *f = &M->seq[M->vseq_off[i << 1]], *r = &M->seq[M->vseq_off[i << 1 | 1]];
+		for (int32_t j = 0; j < s->len; ++j) f[j] = s->seq[j];
+		for (int32_t j = 0; j < s->len; ++j) r[s->len - j - 1] = (char)comp_tab[(uint8_t)s->seq[j]]; // reference: gfa-ed.c:33-36
+	}
+	M->arc_idx.assign(g->idx, g->idx + n_vtx);
+	M->arc.resize(g->n_arc);
+	for (uint64_t i = 0; i < g->n_arc; ++i) { // verbatim order
+		DevArc a;
+		a.w = g->arc[i].w, a.lv = (uint32_t)g->arc[i].v_lv, a.rank = g->arc[i].rank, a.ow = g->arc[i].ow;
+		M->arc[i] = a;
+	}
+	// upload the graph
+	M->g.n_seg = (int32_t)n_seg;
+	M->g.seg_len = dalloc_copy(M->seg_len), M->dev_ptrs.push_back((void*)M->g.seg_len);
+	M->g.vseq_off = dalloc_copy(M->vseq_off), M->dev_ptrs.push_back((void*)M->g.vseq_off);
+	M->g.seq = dalloc_copy(M->seq), M->dev_ptrs.push_back((void*)M->g.seq);
+	M->g.arc_idx = dalloc_copy(M->arc_idx), M->dev_ptrs.push_back((void*)M->g.arc_idx);
+	M->g.arc = dalloc_copy(M->arc), M->dev_ptrs.push_back((void*)M->g.arc);
+	M->ix.k = k, M->ix.w = w, M->ix.slot = 0, M->ix.pos = 0, M->ix.n_slots_mask = 0;
+
+	// sketch every segment on the device (K1 reused), then build the table on the host
+	std::vector<u128> mz;
+	{
+		uint64_t tot_len = 0;
+		int32_t max_len = 1;
+		for (uint32_t i = 0; i < n_seg; ++i) { tot_len += (uint64_t)g->seg[i].len; if (g->seg[i].len > max_len) max_len = g->seg[i].len; }
+		uint64_t cap = (tot_len / 2 + 64 * (uint64_t)n_seg + 1024) * sizeof(u128);
+		// a worker sketches one whole segment inside its arena: ~ (len/w + growth slack) records
+		uint64_t need = (uint64_t)max_len * 16 + ((uint64_t)1 << 20);
+		uint64_t arena_b = std::max<uint64_t>((uint64_t)p_arena_mb << 20, need);
+		int nw = default_workers();
+		while (nw > 1 && (uint64_t)nw * arena_b > dev_free_mem() / 2) nw /= 2;
+		for (;;) {
+			ensure_workers(M->W, nw, arena_b);
+			Pool hp; hp.used = 0, hp.cap = cap;
+			Pool *d_pool = (Pool*)dmalloc(sizeof(Pool));
+			u128 *d_mz = (u128*)dmalloc(cap);
+			int *d_status = (int*)dmalloc(sizeof(int));
+			unsigned int *d_next = (unsigned int*)dmalloc(sizeof(unsigned int));
+			int st0 = 0;
+			h2d(d_pool, &hp, sizeof(Pool));
+			h2d(d_status, &st0, sizeof(int));
+			LaunchArgs L;
+			memset(&L, 0, sizeof(L));
+			L.c.g = M->g, L.c.ix = M->ix, L.c.next_read = d_next;
+			L.routs = (ReadOut*)d_status, L.rid_list = 0, L.n_work = (int32_t)n_seg, L.pool_mz = d_pool, L.mz = d_mz;
+			launch_stage<3>(L, M->W);
+			dsync();
+			d2h(&st0, d_status, sizeof(int));
+			d2h(&hp, d_pool, sizeof(Pool));
+			bool retry = false;
+			if (st0 == MGB_E_POOL) cap *= 2, retry = true;
+			else if (st0 == MGB_E_ARENA) arena_b *= 2, nw = std::max(1, nw / 2), retry = true;
+			else if (st0 < 0) { set_error("segment sketch failed with code " + std::to_string(st0)); abort(); }
+			if (!retry) {
+				mz.resize(hp.used / sizeof(u128));
+				d2h(mz.data(), d_mz, hp.used);
+			}
+			dfree(d_pool), dfree(d_mz), dfree(d_status), dfree(d_next);
+			if (!retry) break;
+		}
+	}
+	// group by minimizer; occurrence lists ascending (reference: index.c:115-165 mg_idx_a2h)
+	std::sort(mz.begin(), mz.end(), [](const u128 &a, const u128 &b) { return (a.x >> 8) != (b.x >> 8)? (a.x >> 8) < (b.x >> 8) : a.y < b.y; });
+	size_t n_keys = 0;
+	for (size_t i = 0; i < mz.size(); ++i) if (i == 0 || (mz[i].x >> 8) != (mz[i-1].x >> 8)) ++n_keys;
+	uint64_t n_slots = 16;
+	while (n_slots < n_keys * 2) n_slots <<= 1;
+	M->n_slots_mask = n_slots - 1;
+	M->slot.assign(n_slots, u128{~0ULL, ~0ULL});
+	M->occ.reserve(n_keys);
+	for (size_t i = 0; i < mz.size();) {
+		size_t j = i;
+		uint64_t key = mz[i].x >> 8;
+		while (j < mz.size() && (mz[j].x >> 8) == key) ++j;
+		uint64_t h = idx_slot_hash(key) & M->n_slots_mask;
+		while (M->slot[h].x != ~0ULL) h = (h + 1) & M->n_slots_mask;
+		if (j - i == 1) {
+			M->slot[h].x = key << 1 | 1, M->slot[h].y = mz[i].y;
+			M->occ.push_back(1);
+		} else {
+			M->slot[h].x = key << 1, M->slot[h].y = (uint64_t)M->pos.size() << 32 | (uint64_t)(j - i);
+			for (size_t t = i; t < j; ++t) M->pos.push_back(mz[t].y);
+			M->occ.push_back((uint32_t)(j - i));
+		}
+		i = j;
+	}
+	M->ix.n_slots_mask = M->n_slots_mask;
+	M->ix.slot = dalloc_copy(M->slot), M->dev_ptrs.push_back((void*)M->ix.slot);
+	M->ix.pos = dalloc_copy(M->pos), M->dev_ptrs.push_back((void*)M->ix.pos);
+	return M;
+}
+
+static const Model *model_of(const mg_idx_t *gi) { return (const Model*)gi->B; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// C ABI: index
+// ---------------------------------------------------------------------------------------------------------------
+
+extern "C" void mg_idx_cal_quantile(const mg_idx_t *gi, int32_t m, float f[], int32_t q[])
+{
+	const Model *M = model_of(gi);
+	std::vector<uint32_t> a(M->occ);
+	uint64_t n = a.size();
+	for (int32_t i = 0; i < m; ++i) {
+		size_t kk = (size_t)((1.0 - (double)f[i]) * (double)n);
+		if (n == 0) { q[i] = 0; continue; }
+		if (kk >= n) kk = n - 1;
+		std::nth_element(a.begin(), a.begin() + kk, a.end());
+		q[i] = (int32_t)a[kk];
+	}
+}
+
+extern "C" const uint64_t *mg_idx_get(const mg_idx_t *gi, uint64_t minier, int *n)
+{
+	const Model *M = model_of(gi);
+	IndexDev ix;
+	ix.k = M->k, ix.w = M->w, ix.n_slots_mask = M->n_slots_mask, ix.slot = M->slot.data(), ix.pos = M->pos.data();
+	return idx_get(ix, minier, n);
+}
+
+extern "C" mg_idx_t *mg_index(gfa_t *g, const mg_idxopt_t *io, int n_threads, mg_mapopt_t *mo)
+{
+	(void)n_threads;
+	if (!dev_ok()) { set_error("no CUDA device available: libmgb200 has no CPU path"); return 0; }
+	for (uint32_t i = 0; i < g->n_seg; ++i) { // reference: index.c:215-220
+		gfa_seg_t *s = &g->seg[i];
+		for (int32_t j = 0; j < s->len; ++j)
+			if (s->seq[j] >= 'a' && s->seq[j] <= 'z') s->seq[j] -= 32;
+	}
+	for (uint64_t i = 0; i < g->n_arc; ++i) // reference: index.c:176-183,192-196
+		if (g->arc[i].ov != 0 || g->arc[i].ow != 0) {
+			fprintf(stderr, "[E::%s] minigraph doesn't work with graphs containing overlapping segments\n", __func__);
+			return 0;
+		}
+	int k = io->k, w = io->w, b = io->bucket_bits;
+	if (k * 2 < b) b = k * 2;
+	if (w < 1) w = 1;
+	Model *M = model_build(g, k, w);
+	mg_idx_t *gi = (mg_idx_t*)calloc(1, sizeof(mg_idx_t));
+	gi->g = g, gi->b = b, gi->w = w, gi->k = k, gi->n_seg = (int32_t)g->n_seg;
+	gi->B = (struct mg_idx_bucket_s*)M;
+	// host view of both strands for callers that read gi->es (reference: gfa-ed.c:24-42)
+	gi->es = (gfa_edseq_t*)malloc(sizeof(gfa_edseq_t) * 2 * (size_t)g->n_seg);
+	for (uint32_t i = 0; i < g->n_seg; ++i) {
+		gi->es[i << 1].seq = g->seg[i].seq, gi->es[i << 1].len = g->seg[i].len;
+		gi->es[i << 1 | 1].seq = &M->seq[M->vseq_off[i << 1 | 1]], gi->es[i << 1 | 1].len = g->seg[i].len;
+	}
+	if (mo) { // reference: options.c:120-134 mg_opt_update
+		float f[2];
+		int32_t q[2];
+		f[0] = 0.1f, f[1] = mo->occ_max1_frac;
+		mg_idx_cal_quantile(gi, 2, f, q);
+		if (q[0] > mo->lc_max_occ) mo->lc_max_occ = q[0];
+		if (mo->lc_max_occ > mo->occ_max1_cap) mo->lc_max_occ = mo->occ_max1_cap;
+		if (q[1] > mo->occ_max1) mo->occ_max1 = q[1];
+		if (mo->occ_max1 > mo->occ_max1_cap) mo->occ_max1 = mo->occ_max1_cap;
+		if (mo->bw_long < mo->bw) mo->bw_long = mo->bw;
+	}
+	return gi;
+}
+
+extern "C" void mg_idx_destroy(mg_idx_t *gi)
+{
+	if (gi == 0) return;
+	if (gi->B) model_free((Model*)gi->B);
+	free(gi->es);
+	free(gi);
+}
+
+struct mg_tbuf_s { int dummy; };
+extern "C" mg_tbuf_t *mg_tbuf_init(void) { return (mg_tbuf_t*)calloc(1, sizeof(mg_tbuf_t)); }
+extern "C" void mg_tbuf_destroy(mg_tbuf_t *b) { free(b); }
+
+extern "C" void mg_gchain_free(mg_gchains_t *gs)
+{
+	if (gs == 0) return;
+	for (int32_t i = 0; i < gs->n_gc; ++i) {
+		free(gs->gc[i].p);
+		free(gs->gc[i].ds.ds);
+		free(gs->gc[i].ds.off);
+	}
+	free(gs->gc); free(gs->a); free(gs->lc);
+	free(gs);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// batch dispatcher
+// ---------------------------------------------------------------------------------------------------------------
+
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+#ifndef MGB_HOSTSIM
+struct EvTimer {
+	cudaEvent_t a, b;
+	EvTimer() { cudaEventCreate(&a); cudaEventCreate(&b); }
+	~EvTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+	void start() { cudaEventRecord(a, 0); }
+	void stop() { cudaEventRecord(b, 0); }
+	double ms() { float t = 0; cudaEventSynchronize(b); cudaEventElapsedTime(&t, a, b); return t; }
+};
+#else
+struct EvTimer { double t0, t1; void start() { t0 = now_ms(); } void stop() { t1 = now_ms(); } double ms() { return t1 - t0; } };
+#endif
+
+static void fill_opt(MapOptDev &o, const mg_mapopt_t *opt, int k)
+{
+	memset(&o, 0, sizeof(o));
+	o.flag = opt->flag, o.seed = opt->seed, o.max_qlen = opt->max_qlen, o.occ_max1 = opt->occ_max1;
+	o.bw = opt->bw, o.bw_long = opt->bw_long, o.rmq_size_cap = opt->rmq_size_cap, o.rmq_rescue_size = opt->rmq_rescue_size;
+	o.rmq_rescue_ratio = opt->rmq_rescue_ratio;
+	o.max_gap_pre = opt->max_gap_pre, o.max_gap = opt->max_gap, o.max_gap_ref = opt->max_gap_ref, o.max_frag_len = opt->max_frag_len;
+	{ // reference: map-algo.c:388-390; expf() must be the host libm
+		float tmp = expf(-opt->div * k);
+		o.chn_pen_gap = opt->chn_pen_gap * tmp;
+		o.chn_pen_skip = opt->chn_pen_skip * tmp;
+	}
+	o.max_lc_skip = opt->max_lc_skip, o.max_lc_iter = opt->max_lc_iter, o.max_gc_skip = opt->max_gc_skip;
+	o.min_lc_cnt = opt->min_lc_cnt, o.min_lc_score = opt->min_lc_score, o.min_gc_cnt = opt->min_gc_cnt, o.min_gc_score = opt->min_gc_score;
+	o.gdp_max_ed = opt->gdp_max_ed, o.lc_max_trim = opt->lc_max_trim, o.lc_max_occ = opt->lc_max_occ;
+	o.mask_level = opt->mask_level, o.sub_diff = opt->sub_diff, o.best_n = opt->best_n, o.pri_ratio = opt->pri_ratio, o.ref_bonus = opt->ref_bonus;
+}
+
+static mg_gchains_t *build_result(const ReadOut &ro, const char *blob)
+{
+	mg_gchains_t *gs = (mg_gchains_t*)calloc(1, sizeof(mg_gchains_t));
+	gs->rep_len = ro.rep_len;
+	if (ro.n_gc == 0) return gs; // reference: gchain1.c:460 returns the bare struct
+	gs->n_gc = ro.n_gc, gs->n_lc = ro.n_lc, gs->n_a = ro.n_a;
+	gs->gc = (mg_gchain_t*)calloc((size_t)ro.n_gc, sizeof(mg_gchain_t));
+	gs->lc = (mg_llchain_t*)malloc((size_t)(ro.n_lc > 0? ro.n_lc : 1) * sizeof(mg_llchain_t));
+	gs->a = (mg128_t*)malloc((size_t)(ro.n_a > 0? ro.n_a : 1) * sizeof(mg128_t));
+	const GChain *d = (const GChain*)blob;
+	uint64_t off_lc = align8((uint64_t)ro.n_gc * sizeof(GChain));
+	uint64_t off_a = off_lc + align8((uint64_t)ro.n_lc * sizeof(LLChain));
+	memcpy(gs->lc, blob + off_lc, (size_t)ro.n_lc * sizeof(mg_llchain_t));
+	memcpy(gs->a, blob + off_a, (size_t)ro.n_a * sizeof(mg128_t));
+	for (int32_t i = 0; i < ro.n_gc; ++i) {
+		mg_gchain_t *p = &gs->gc[i];
+		const GChain *s = &d[i];
+		p->id = s->id, p->parent = s->parent, p->off = s->off, p->cnt = s->cnt, p->n_anchor = s->n_anchor, p->score = s->score;
+		p->qs = s->qs, p->qe = s->qe, p->plen = s->plen, p->ps = s->ps, p->pe = s->pe, p->blen = s->blen, p->mlen = s->mlen;
+		p->hash = s->hash, p->subsc = s->subsc, p->n_sub = s->n_sub, p->mapq = (uint32_t)s->mapq, p->flt = (uint32_t)s->flt;
+		// reference: gchain1.c:295 (host libm log)
+		p->div = s->n_mini >= s->n_anchor? (float)(log((double)s->n_mini / s->n_anchor) / s->q_span) : (float)(log((double)s->n_anchor / s->n_mini) / s->q_span);
+		if (s->has_cigar) {
+			p->p = (mg_cigar_t*)calloc(1, (size_t)s->n_cigar * 8 + sizeof(mg_cigar_t));
+			p->p->n_cigar = s->n_cigar, p->p->mlen = s->c_mlen, p->p->blen = s->c_blen, p->p->aplen = s->c_aplen, p->p->ss = s->c_ss, p->p->ee = s->c_ee;
+			memcpy(p->p->cigar, blob + s->cigar_off, (size_t)s->n_cigar * 8);
+			p->ds.len = s->ds_len, p->ds.n_off = s->n_dsoff;
+			p->ds.ds = (char*)calloc((size_t)s->ds_len + 1, 1);
+			memcpy(p->ds.ds, blob + s->ds_off, (size_t)s->ds_len);
+			p->ds.off = (int32_t*)calloc((size_t)(s->n_dsoff > 0? s->n_dsoff : 1), sizeof(int32_t));
+			memcpy(p->ds.off, blob + s->dsoff_off, (size_t)s->n_dsoff * sizeof(int32_t));
+		}
+	}
+	return gs;
+}
+
+static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, const char *const *seqs, const char *const *names,
+						  mg_gchains_t **gcs, const mg_mapopt_t *opt)
+{
+	Model *M = (Model*)gi->B;
+	mgb_stats_t &S = M->stats;
+	memset(&S, 0, sizeof(S));
+	for (int i = 0; i < n_reads; ++i) gcs[i] = 0;
+	if (n_reads <= 0) return 0;
+	double t_host0 = now_ms();
+	// ---- pack the batch ----
+	std::vector<uint64_t> seq_off(n_reads);
+	std::vector<int32_t> seq_len(n_reads);
+	std::vector<uint32_t> name_hash(n_reads);
+	uint64_t tot = 0;
+	int32_t max_qlen = 0;
+	for (int i = 0; i < n_reads; ++i) {
+		seq_off[i] = tot, seq_len[i] = qlens[i];
+		tot += (uint64_t)(qlens[i] > 0? qlens[i] : 0) + 8;
+		tot = (tot + 15) & ~(uint64_t)15;
+		name_hash[i] = names && names[i]? hash_str(names[i]) : 0;
+		if (qlens[i] > max_qlen) max_qlen = qlens[i];
+		S.n_bases += qlens[i] > 0? qlens[i] : 0;
+	}
+	S.n_reads = n_reads;
+	std::vector<char> hseq(tot + 16, 0);
+	for (int i = 0; i < n_reads; ++i) if (qlens[i] > 0) memcpy(&hseq[seq_off[i]], seqs[i], (size_t)qlens[i]);
+	// glibc logf table for mapq (reference: gcmisc.c:216-217)
+	{
+		int need = std::max(1 << 16, max_qlen + 4096);
+		if (M->n_logf < need) {
+			M->logf_tab.resize(need);
+			for (int i = 0; i < need; ++i) M->logf_tab[i] = logf((float)i);
+			if (M->d_logf) dfree(M->d_logf);
+			M->d_logf = dalloc_copy(M->logf_tab);
+			M->n_logf = need;
+		}
+	}
+	MapOptDev o;
+	fill_opt(o, opt, M->k);
+	o.logf_tab = M->d_logf, o.n_logf_tab = M->n_logf;
+
+	EvTimer tm_h2d, tm_seed, tm_chain, tm_align, tm_d2h;
+	// ---- device buffers ----
+	tm_h2d.start();
+	char *d_seq = (char*)dmalloc(hseq.size());
+	h2d(d_seq, hseq.data(), hseq.size());
+	uint64_t *d_seq_off = dalloc_copy(seq_off);
+	int32_t *d_seq_len = dalloc_copy(seq_len);
+	uint32_t *d_name_hash = dalloc_copy(name_hash);
+	tm_h2d.stop();
+	ReadMeta *d_meta = (ReadMeta*)dmalloc(sizeof(ReadMeta) * (size_t)n_reads);
+	ReadOut *d_routs = (ReadOut*)dmalloc(sizeof(ReadOut) * (size_t)n_reads);
+	dzero(d_meta, sizeof(ReadMeta) * (size_t)n_reads);
+	dzero(d_routs, sizeof(ReadOut) * (size_t)n_reads);
+	unsigned int *d_next = (unsigned int*)dmalloc(sizeof(unsigned int));
+	Pool *d_pools = (Pool*)dmalloc(sizeof(Pool) * 4);
+
+	uint64_t cap_anchor = std::max<uint64_t>((uint64_t)S.n_bases / 4 * sizeof(u128), (uint64_t)1 << 22);
+	uint64_t cap_minipos = std::max<uint64_t>((uint64_t)S.n_bases * sizeof(int32_t) / 2, (uint64_t)1 << 20);
+	uint64_t cap_lchain = std::max<uint64_t>((uint64_t)n_reads * 64 * sizeof(LChain), (uint64_t)1 << 20);
+	uint64_t cap_out = std::max<uint64_t>((uint64_t)S.n_bases * 4, (uint64_t)1 << 22);
+	std::vector<ReadOut> routs(n_reads);
+	std::vector<ReadMeta> meta(n_reads);
+	std::vector<char> hout;
+	int rc_final = 0;
+	const int n_workers = default_workers();
+	ensure_workers(M->W, n_workers, (uint64_t)p_arena_mb << 20);
+
+	for (int attempt = 0; attempt < 8; ++attempt) {
+		u128 *d_anchor = (u128*)dmalloc(cap_anchor);
+		int32_t *d_minipos = (int32_t*)dmalloc(cap_minipos);
+		LChain *d_lchain = (LChain*)dmalloc(cap_lchain);
+		char *d_out = (char*)dmalloc(cap_out);
+		Pool hp[4];
+		hp[0].used = 0, hp[0].cap = cap_anchor;
+		hp[1].used = 0, hp[1].cap = cap_minipos;
+		hp[2].used = 0, hp[2].cap = cap_lchain;
+		hp[3].used = 0, hp[3].cap = cap_out;
+		h2d(d_pools, hp, sizeof(hp));
+		LaunchArgs L;
+		memset(&L, 0, sizeof(L));
+		L.c.g = M->g, L.c.ix = M->ix, L.c.opt = o;
+		L.c.b.n_reads = n_reads, L.c.b.seq = d_seq, L.c.b.seq_off = d_seq_off, L.c.b.seq_len = d_seq_len, L.c.b.name_hash = d_name_hash;
+		L.c.meta = d_meta;
+		L.c.pool_anchor = &d_pools[0], L.c.anchor = d_anchor;
+		L.c.pool_minipos = &d_pools[1], L.c.minipos = d_minipos;
+		L.c.pool_lchain = &d_pools[2], L.c.lchain = d_lchain;
+		L.c.pool_out = &d_pools[3], L.c.out = d_out;
+		L.c.next_read = d_next;
+		L.routs = d_routs, L.rid_list = 0, L.n_work = n_reads;
+
+		tm_seed.start(); launch_stage<0>(L, M->W); tm_seed.stop();
+		tm_chain.start(); launch_stage<1>(L, M->W); tm_chain.stop();
+		tm_align.start(); launch_stage<2>(L, M->W); tm_align.stop();
+		S.n_launches += 3;
+		dsync();
+		d2h(routs.data(), d_routs, sizeof(ReadOut) * (size_t)n_reads);
+		d2h(meta.data(), d_meta, sizeof(ReadMeta) * (size_t)n_reads);
+
+		// reads whose worker arena overflowed: run them again with large arenas and few workers
+		std::vector<int32_t> redo;
+		bool pool_full = false;
+		for (int i = 0; i < n_reads; ++i) {
+			int st = meta[i].status < 0? meta[i].status : routs[i].status;
+			if (st == MGB_E_ARENA) redo.push_back(i);
+			else if (st == MGB_E_POOL) pool_full = true;
+		}
+		if (!pool_full && !redo.empty()) {
+			uint64_t big = (uint64_t)p_arena_big_mb << 20;
+			int nw = (int)std::min<uint64_t>((uint64_t)n_workers, std::max<uint64_t>(1, dev_free_mem() * 3 / 4 / big));
+			nw = std::min<int>(nw, (int)redo.size());
+			ensure_workers(M->Wbig, std::max(1, nw), big);
+			int32_t *d_list = dalloc_copy(redo);
+			L.rid_list = d_list, L.n_work = (int32_t)redo.size();
+			launch_stage<0>(L, M->Wbig);
+			launch_stage<1>(L, M->Wbig);
+			launch_stage<2>(L, M->Wbig);
+			S.n_launches += 3;
+			dsync();
+			dfree(d_list);
+			S.n_retry += (int64_t)redo.size();
+			d2h(routs.data(), d_routs, sizeof(ReadOut) * (size_t)n_reads);
+			d2h(meta.data(), d_meta, sizeof(ReadMeta) * (size_t)n_reads);
+			for (int i = 0; i < n_reads; ++i) {
+				int st = meta[i].status < 0? meta[i].status : routs[i].status;
+				if (st == MGB_E_POOL) pool_full = true;
+			}
+		}
+		d2h(hp, d_pools, sizeof(hp));
+		bool done = !pool_full;
+		if (done) {
+			tm_d2h.start();
+			hout.resize(std::min<uint64_t>(hp[3].used, cap_out));
+			d2h(hout.data(), d_out, hout.size());
+			tm_d2h.stop();
+			S.out_bytes = (int64_t)hout.size();
+		}
+		dfree(d_anchor), dfree(d_minipos), dfree(d_lchain), dfree(d_out);
+		if (done) break;
+		// grow whatever overflowed (used counts keep growing past cap, so they tell how much was wanted)
+		if (hp[0].used > cap_anchor) cap_anchor = hp[0].used * 3 / 2;
+		if (hp[1].used > cap_minipos) cap_minipos = hp[1].used * 3 / 2;
+		if (hp[2].used > cap_lchain) cap_lchain = hp[2].used * 3 / 2;
+		if (hp[3].used > cap_out) cap_out = hp[3].used * 3 / 2;
+		if (attempt == 7) { set_error("output pools kept overflowing"); rc_final = -2; }
+	}
+	S.t_h2d_ms = tm_h2d.ms(), S.t_seed_ms = tm_seed.ms(), S.t_chain_ms = tm_chain.ms(), S.t_align_ms = tm_align.ms();
+	if (rc_final == 0) S.t_d2h_ms = tm_d2h.ms();
+	{
+		std::vector<uint64_t> peak(M->W.n_workers);
+		d2h(peak.data(), M->W.peak, sizeof(uint64_t) * peak.size());
+		for (uint64_t p : peak) if (p > S.arena_peak) S.arena_peak = p;
+	}
+	dfree(d_seq), dfree(d_seq_off), dfree(d_seq_len), dfree(d_name_hash), dfree(d_meta), dfree(d_routs), dfree(d_next), dfree(d_pools);
+	if (rc_final < 0) return rc_final;
+
+	// ---- results ----
+	for (int i = 0; i < n_reads; ++i) {
+		int st = meta[i].status < 0? meta[i].status : routs[i].status;
+		if (st < 0) {
+			char buf[256];
+			snprintf(buf, sizeof(buf), "read %d ('%s', %d bp) failed on the device with code %d%s", i, names && names[i]? names[i] : "", qlens[i], st,
+					 st == MGB_E_ARENA? " (worker arena exhausted even in the retry pass; raise arena_big_mb)" :
+					 st == MGB_E_UNSUPPORTED? " (code path not implemented yet)" : "");
+			set_error(buf);
+			for (int j = 0; j < i; ++j) { mg_gchain_free(gcs[j]); gcs[j] = 0; }
+			return st;
+		}
+		S.n_seeds += meta[i].n_seed0, S.n_anchors_out += meta[i].n_a, S.n_chains_out += meta[i].n_u0, S.n_minimizers += meta[i].n_mz;
+		if (st == 1) { gcs[i] = 0; continue; } // empty or over-long read: reference returns before allocating (map-algo.c:359-360)
+		gcs[i] = build_result(routs[i], hout.data() + routs[i].blob_off);
+	}
+	S.t_host_ms = now_ms() - t_host0;
+	return 0;
+}
+
+extern "C" int mg_map_batch(const mg_idx_t *gi, int n_reads, const int *qlens, const char *const *seqs, const char *const *names,
+							mg_gchains_t **gcs, const mg_mapopt_t *opt)
+{
+	return map_batch_impl(gi, n_reads, qlens, seqs, names, gcs, opt);
+}
+
+extern "C" void mg_map_frag(const mg_idx_t *gi, int n_segs, const int *qlens, const char **seqs, mg_gchains_t **gcs, mg_tbuf_t *b, const mg_mapopt_t *opt, const char *qname)
+{
+	(void)b;
+	for (int i = 0; i < n_segs; ++i) gcs[i] = 0;
+	if (n_segs <= 0) return;
+	if (n_segs != 1) {
+		set_error("mg_map_frag: multi-segment (paired-end) fragments are not supported by the GPU engine yet");
+		abort();
+	}
+	const char *nm = qname;
+	if (mg_map_batch(gi, 1, qlens, seqs, &nm, gcs, opt) < 0) abort(); // the reference aborts on internal errors too
+}
+
+extern "C" mg_gchains_t *mg_map(const mg_idx_t *gi, int qlen, const char *seq, mg_tbuf_t *b, const mg_mapopt_t *opt, const char *qname)
+{
+	mg_gchains_t *gcs;
+	mg_map_frag(gi, 1, &qlen, &seq, &gcs, b, opt, qname);
+	return gcs;
+}
+
+extern "C" void mgb_get_stats(const mg_idx_t *gi, mgb_stats_t *st) { *st = model_of(gi)->stats; }

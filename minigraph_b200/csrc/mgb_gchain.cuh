@@ -1,0 +1,697 @@
+// mgb_gchain.cuh -- graph chaining over linear chains and materialisation of graph chains.
+//   gchain1_dp()   (reference: gchain1.c:62-240 mg_gchain1_dp, :38-60 cal_sc)
+//   gchain_gen()   (reference: gchain1.c:443-520 mg_gchain_gen with resolve_overlap / bridge_* helpers)
+//   gchain_extra() (reference: gchain1.c:242-297 mg_gchain_extra; the log() for `div` is left to the host)
+//   post-filters   (reference: gcmisc.c:56-223)
+#pragma once
+#include "mgb_model.cuh"
+#include "mgb_lchain.cuh"
+#include "mgb_shortk.cuh"
+#include "mgb_gwfa.cuh"
+
+namespace mgb {
+
+// reference: minigraph.h:108-113 mg_llchain_t
+struct LLChain {
+	int32_t off, cnt;
+	uint32_t v;
+	int32_t score, ed;
+};
+
+// device-side graph chain: mg_gchain_t (minigraph.h:125-138) without host pointers, plus what the host needs to
+// finish it (n_mini/q_span for `div`, CIGAR and ds locations inside the result blob)
+struct GChain {
+	int32_t id, parent;
+	int32_t off, cnt;
+	int32_t n_anchor, score;
+	int32_t qs, qe;
+	int32_t plen, ps, pe;
+	int32_t blen, mlen;
+	uint32_t hash;
+	int32_t subsc, n_sub;
+	int32_t mapq, flt;
+	int32_t n_mini, q_span;
+	// base alignment
+	int32_t has_cigar, n_cigar, c_mlen, c_blen, c_aplen, c_ss, c_ee;
+	int32_t ds_len, n_dsoff;
+	int64_t cigar_off, ds_off, dsoff_off; // byte offsets relative to the blob start
+};
+
+struct GcFrag { uint32_t srt; int32_t i; };
+struct KeyGcFrag { MG_HD uint64_t operator()(const GcFrag &p) const { return p.srt; } };
+
+MG_HD inline int32_t gc_find_max(int32_t n, const GcFrag *gf, uint32_t x)
+{
+	int32_t s = 0, e = n;
+	if (n == 0) return -1;
+	if (gf[n-1].srt < x) return n - 1;
+	if (gf[0].srt >= x) return -1;
+	while (e > s) {
+		int32_t m = s + (e - s) / 2;
+		if (gf[m].srt >= x) e = m;
+		else s = m + 1;
+	}
+	return s;
+}
+
+MG_HD inline int32_t gc_target_dist(const GraphDev &g, const LChain *l0, const LChain *l1)
+{
+	return (l1->qs - l0->qe) - (g.seg_len[l0->v >> 1] - l0->re) + (g.seg_len[l1->v >> 1] - l1->rs);
+}
+
+MG_HD inline int32_t gc_cal_sc(const PathDst *dj, const LChain *li, const LChain *lc, const u128 *an, const GcFrag *a, const int32_t *f,
+							   int bw, int ref_bonus, float chn_pen_gap)
+{
+	const LChain *lj;
+	int32_t gap, sc, segi, segj;
+	float lin_pen, log_pen;
+	if (dj->n_path == 0) return SC_NONE;
+	segi = (int32_t)((an[li->off].y & SEED_SEG_MASK) >> SEED_SEG_SHIFT);
+	gap = dj->dist - dj->target_dist;
+	lj = &lc[a[dj->meta].i];
+	segj = (int32_t)((an[lj->off + lj->cnt - 1].y & SEED_SEG_MASK) >> SEED_SEG_SHIFT);
+	if (gap < 0) gap = -gap;
+	if (segi == segj && gap > bw) return SC_NONE;
+	if (lj->qe <= li->qs) sc = li->score;
+	else sc = (int32_t)((double)(li->qe - lj->qe) / (double)(li->qe - li->qs) * (double)li->score + .499);
+	if (dj->is_0) sc += ref_bonus;
+	lin_pen = chn_pen_gap * (float)gap;
+	log_pen = gap >= 2? fast_log2((float)gap) : 0.0f;
+	sc -= (int32_t)(lin_pen + log_pen);
+	sc += f[dj->meta];
+	return sc;
+}
+
+// Graph chaining DP.  lc[] is permuted into chain order; u[] (score<<32|#lchains) is allocated at the caller's mark.
+MG_HD inline int gchain1_dp(Arena &A, const GraphDev &g, int32_t *n_lc_, LChain *lc, int32_t qlen, int32_t max_dist_g, int32_t max_dist_q, int32_t bw,
+							int32_t max_skip, int32_t ref_bonus, float chn_pen_gap, float mask_level, const u128 *an, uint64_t **u_, int32_t *n_u_)
+{
+	int32_t i, j, k, n_dst, n_ext, n_u, n_v, n_lc = *n_lc_;
+	*u_ = 0, *n_u_ = 0;
+	if (n_lc == 0) return 0;
+	uint64_t *u_store;
+	MGB_ALLOC(A, u_store, uint64_t, n_lc);
+	uint64_t mark = A.top;
+	GcFrag *a;
+	MGB_ALLOC(A, a, GcFrag, n_lc);
+	for (i = n_ext = 0; i < n_lc; ++i) {
+		LChain *r = &lc[i];
+		int32_t is_isolated = 0, min_end_dist_g;
+		r->dist_pre = -1;
+		min_end_dist_g = g.seg_len[r->v >> 1] - r->re;
+		if (r->rs < min_end_dist_g) min_end_dist_g = r->rs;
+		if (min_end_dist_g > max_dist_g) is_isolated = 1;
+		else if (min_end_dist_g >> 3 > r->score) is_isolated = 1;
+		a[i].srt = (uint32_t)is_isolated << 31 | (uint32_t)r->qe;
+		a[i].i = i;
+		if (!is_isolated) ++n_ext;
+	}
+	if (n_ext < 2) {
+		for (i = 0; i < n_lc; ++i) u_store[i] = (uint64_t)(int64_t)lc[i].score << 32 | 1;
+		A.top = mark;
+		*u_ = u_store, *n_u_ = n_lc;
+		return 0;
+	}
+	MGB_TRY(radix_sort_exact(A, a, n_lc, 4, KeyGcFrag()));
+	int32_t *v, *f, *p, *t;
+	MGB_ALLOC(A, v, int32_t, n_lc);
+	MGB_ALLOC(A, f, int32_t, n_ext);
+	MGB_ALLOC(A, p, int32_t, n_ext);
+	MGB_ALLOC(A, t, int32_t, n_ext);
+	for (i = 0; i < n_ext; ++i) t[i] = 0;
+	PathDst *dst;
+	MGB_ALLOC(A, dst, PathDst, n_ext); // at most i destinations for frag i
+	for (i = 0; i < n_ext; ++i) {
+		GcFrag *ai = &a[i];
+		LChain *li = &lc[ai->i];
+		int32_t segi = (int32_t)((an[li->off].y & SEED_SEG_MASK) >> SEED_SEG_SHIFT);
+		{ // candidate predecessors
+			int32_t x = li->qs + bw, n_skip = 0;
+			if (x > qlen) x = qlen;
+			x = gc_find_max(i, a, (uint32_t)x);
+			n_dst = 0;
+			for (j = x; j >= 0; --j) {
+				GcFrag *aj = &a[j];
+				LChain *lj = &lc[aj->i];
+				PathDst *q;
+				int32_t target_dist, segj, dq;
+				if (lj->qs >= li->qs) continue;
+				if (lj->qe > li->qs) {
+					int o = lj->qe - li->qs;
+					if ((float)o > (float)(lj->qe - lj->qs) * mask_level || (float)o > (float)(li->qe - li->qs) * mask_level) continue;
+				}
+				dq = li->qs - lj->qe;
+				segj = (int32_t)((an[lj->off + lj->cnt - 1].y & SEED_SEG_MASK) >> SEED_SEG_SHIFT);
+				if (segi == segj) {
+					if (dq > max_dist_q) break;
+				} else {
+					if (dq > max_dist_g && dq > max_dist_q) break;
+				}
+				if (li->v != lj->v) {
+					int32_t min_dist = li->rs + (g.seg_len[lj->v >> 1] - lj->re);
+					if (min_dist > max_dist_g) continue;
+					if (segi == segj && min_dist - bw > li->qs - lj->qe) continue;
+					target_dist = gc_target_dist(g, lj, li);
+					if (target_dist < 0) continue;
+				} else if (lj->rs >= li->rs || lj->re >= li->re) {
+					continue;
+				} else {
+					int32_t dr = li->rs - lj->re, w = dr > dq? dr - dq : dq - dr;
+					if (segi == segj && w > bw) continue;
+					if (dr > max_dist_g || dr < -max_dist_g) continue;
+					if (lj->re > li->rs) {
+						int o = lj->re - li->rs;
+						if ((float)o > (float)(lj->re - lj->rs) * mask_level || (float)o > (float)(li->re - li->rs) * mask_level) continue;
+					}
+					target_dist = gc_target_dist(g, lj, li);
+				}
+				q = &dst[n_dst++];
+				q->inner = (li->v == lj->v);
+				q->v = lj->v ^ 1;
+				q->meta = j;
+				q->qlen = li->qs - lj->qe;
+				q->target_dist = target_dist;
+				q->target_hash = 0;
+				q->check_hash = 0;
+				q->n_path = 0, q->is_0 = 0, q->path_end = 0, q->dist = 0, q->hash = 0;
+				if (t[j] == i) {
+					if (++n_skip > max_skip) break;
+				}
+				if (p[j] >= 0) t[p[j]] = i;
+			}
+		}
+		{ // reachability and distances
+			MGB_TRY(shortest_k(A, g, li->v ^ 1, n_dst, dst, max_dist_g + (g.seg_len[li->v >> 1] - li->rs), MAX_SHORT_K, 0, 0));
+			for (j = k = 0; j < n_dst; ++j) {
+				PathDst *dj = &dst[j];
+				int32_t sc;
+				if (dj->n_path == 0) continue;
+				sc = gc_cal_sc(dj, li, lc, an, a, f, bw, ref_bonus, chn_pen_gap);
+				if (sc == SC_NONE) continue;
+				if (sc + li->score < 0) continue;
+				dst[k++] = dst[j];
+			}
+			n_dst = k;
+		}
+		{ // DP
+			int32_t max_f = li->score, max_j = -1, max_d = -1, max_inner = 0;
+			uint32_t max_hash = 0;
+			for (j = 0; j < n_dst; ++j) {
+				PathDst *dj = &dst[j];
+				int32_t sc = gc_cal_sc(dj, li, lc, an, a, f, bw, ref_bonus, chn_pen_gap);
+				if (sc == SC_NONE) continue;
+				if (sc > max_f) max_f = sc, max_j = dj->meta, max_d = dj->dist, max_hash = dj->hash, max_inner = dj->inner;
+			}
+			f[i] = max_f, p[i] = max_j;
+			li->dist_pre = max_d;
+			li->hash_pre = max_hash;
+			li->inner_pre = max_inner;
+			v[i] = max_j >= 0 && v[max_j] > max_f? v[max_j] : max_f;
+		}
+	}
+	uint64_t *u;
+	MGB_TRY(chain_backtrack(A, n_ext, f, p, v, t, 0, 0, INT32_MAX, n_lc - n_ext, &u, &n_u, &n_v));
+	if (u == 0) { // cannot happen with min_sc == 0 (every f >= 0), kept for safety
+		MGB_ALLOC(A, u, uint64_t, n_lc);
+		n_u = n_v = 0;
+	}
+	for (i = 0; i < n_lc - n_ext; ++i) {
+		u[n_u++] = (uint64_t)(int64_t)lc[a[n_ext + i].i].score << 32 | 1;
+		v[n_v++] = n_ext + i;
+	}
+	LChain *swap;
+	MGB_ALLOC(A, swap, LChain, n_v);
+	for (i = 0, k = 0; i < n_u; ++i) {
+		int32_t k0 = k, ni = (int32_t)u[i];
+		for (j = 0; j < ni; ++j) swap[k++] = lc[a[v[k0 + (ni - j - 1)]].i];
+	}
+	if (k != n_v) return MGB_E_INTERNAL;
+	for (i = 0; i < n_v; ++i) lc[i] = swap[i];
+	for (i = 0; i < n_u; ++i) u_store[i] = u[i];
+	*n_lc_ = n_v;
+	A.top = mark;
+	*u_ = u_store, *n_u_ = n_u;
+	return 0;
+}
+
+// ---- materialise graph chains ----
+
+struct GcSet { // device analogue of mg_gchains_t
+	int32_t n_gc, n_lc, n_a, rep_len;
+	GChain *gc;
+	LLChain *lc;
+	u128 *a;
+};
+
+struct BridgeAux {
+	const GraphDev *g;
+	const char *qseq;
+	AVec<LLChain> llc;
+	int32_t n_a;
+	u128 *a_new;
+};
+
+MG_HD inline void gc_copy_lchain(LLChain *q, const LChain *p, int32_t *n_a, u128 *a_new, const u128 *a_old, int32_t ed)
+{
+	q->cnt = p->cnt, q->v = p->v, q->score = p->score, q->ed = ed;
+	for (int32_t i = 0; i < p->cnt; ++i) a_new[*n_a + i] = a_old[p->off + i];
+	q->off = *n_a;
+	(*n_a) += q->cnt;
+}
+
+MG_HD inline int gc_push_empty(Arena &A, BridgeAux &aux, uint32_t v)
+{
+	LLChain q;
+	q.off = q.cnt = q.score = 0, q.v = v, q.ed = -1;
+	return avec_push(A, aux.llc, q);
+}
+
+// reference: gchain1.c:319-347 bridge_shortk; returns 0, or 1 when no consistent walk exists (the reference's -1)
+MG_HD inline int gc_bridge_shortk(Arena &A, BridgeAux &aux, const LChain *l0, const LChain *l1, int *failed)
+{
+	uint64_t mark = A.top;
+	int32_t n_pathv;
+	PathDst dst;
+	PathV *p;
+	*failed = 0;
+	memset(&dst, 0, sizeof(dst));
+	dst.v = l0->v ^ 1;
+	if (l1->dist_pre < 0) return MGB_E_INTERNAL;
+	dst.target_dist = l1->dist_pre;
+	dst.target_hash = l1->hash_pre;
+	dst.check_hash = 1;
+	MGB_TRY(shortest_k(A, *aux.g, l1->v ^ 1, 1, &dst, dst.target_dist, MAX_SHORT_K, &p, &n_pathv));
+	if (n_pathv == 0 || dst.target_hash != dst.hash) {
+		A.top = mark;
+		*failed = 1;
+		return 0;
+	}
+	// the path was found backwards: reverse it and flip orientations.  llc may grow above p, p stays valid.
+	for (int32_t s = n_pathv - 2; s >= 1; --s) MGB_TRY(gc_push_empty(A, aux, p[s].v ^ 1));
+	return 0; // NB: p[] is not released here when llc grew above it; the caller's mark reclaims it
+}
+
+// reference: gchain1.c:349-381 bridge_gwfa; *ok = 1 when an alignment within gdp_max_ed was found
+MG_HD inline int gc_bridge_gwfa(Arena &A, BridgeAux &aux, int32_t kmer_size, int32_t gdp_max_ed, const LChain *l0, const LChain *l1, int32_t *ed, int *ok)
+{
+	uint32_t v0 = l0->v, v1 = l1->v;
+	int32_t qs = l0->qe - kmer_size, qe = l1->qs + kmer_size, end0, end1;
+	GwfOpt opt;
+	GwfResult r;
+	*ed = -1, *ok = 0;
+	end0 = l0->re - kmer_size;
+	end1 = l1->rs + kmer_size - 1;
+	opt.traceback = 1, opt.max_chk = 1000, opt.bw_dyn = 1000, opt.max_lag = gdp_max_ed / 2, opt.s_term = -1;
+	opt.i_term = 500000000LL;
+	uint64_t mark = A.top;
+	// walk vertices are copied out before llc can grow over them
+	MGB_TRY(gwf_align(A, *aux.g, opt, qe - qs, &aux.qseq[qs], v0, end0, v1, end1, gdp_max_ed, &r));
+	if (r.s < 0) { A.top = mark; return 0; }
+	// r.v sits at `mark`; pushing to llc may allocate above it, which is fine
+	for (int32_t j = 1; j < r.nv - 1; ++j) MGB_TRY(gc_push_empty(A, aux, (uint32_t)r.v[j]));
+	*ed = r.s, *ok = 1;
+	return 0;
+}
+
+// reference: gchain1.c:383-407 bridge_lchains; *failed mirrors the reference's negative return
+MG_HD inline int gc_bridge_lchains(Arena &A, BridgeAux &aux, int32_t n_seg, int32_t kmer_size, int32_t gdp_max_ed, const LChain *l0, const LChain *l1,
+								   const u128 *a, int *failed)
+{
+	*failed = 0;
+	if (l1->v != l0->v) {
+		int32_t ed = -1;
+		int ok = 0, sk_failed = 0;
+		if (n_seg <= 1) MGB_TRY(gc_bridge_gwfa(A, aux, kmer_size, gdp_max_ed, l0, l1, &ed, &ok));
+		if (!ok) MGB_TRY(gc_bridge_shortk(A, aux, l0, l1, &sk_failed));
+		if (sk_failed) { *failed = 1; return 0; }
+		LLChain q;
+		gc_copy_lchain(&q, l1, &aux.n_a, aux.a_new, a, ed);
+		MGB_TRY(avec_push(A, aux.llc, q));
+	} else {
+		int32_t k;
+		LLChain *t = &aux.llc.a[aux.llc.n - 1];
+		for (k = 0; k < l1->cnt; ++k) {
+			const u128 *ak = &a[l1->off + k];
+			if ((int32_t)ak->x > l0->re && (int32_t)ak->y > l0->qe) break;
+		}
+		if (k < l1->cnt) {
+			t->cnt += l1->cnt - k, t->score += l1->score;
+			for (int32_t i = 0; i < l1->cnt - k; ++i) aux.a_new[aux.n_a + i] = a[l1->off + k + i];
+			aux.n_a += l1->cnt - k;
+		}
+	}
+	return 0;
+}
+
+// reference: gchain1.c:409-441 resolve_overlap
+MG_HD inline int gc_resolve_overlap(LChain *l0, LChain *l1, const u128 *a)
+{
+	int32_t j, x, y, shift0, shift1;
+	x = (int32_t)a[l1->off].x;
+	y = (int32_t)a[l1->off].y;
+	for (j = l0->cnt - 1; j >= 0; --j)
+		if ((int32_t)a[l0->off + j].y <= y && (l0->v != l1->v || (int32_t)a[l0->off + j].x <= x)) break;
+	shift0 = l0->cnt - 1 - j;
+	x = (int32_t)a[l0->off + l0->cnt - 1].x;
+	y = (int32_t)a[l0->off + l0->cnt - 1].y;
+	for (j = 0; j < l1->cnt; ++j)
+		if ((int32_t)a[l1->off + j].y >= y && (l0->v != l1->v || (int32_t)a[l1->off + j].x >= x)) break;
+	shift1 = j;
+	if (shift1 >= l1->cnt) return MGB_E_INTERNAL;
+	if (shift0 > 0) {
+		l0->cnt -= shift0;
+		if (l0->cnt) {
+			l0->qe = (int32_t)a[l0->off + l0->cnt - 1].y + 1;
+			l0->re = (int32_t)a[l0->off + l0->cnt - 1].x + 1;
+		}
+	}
+	if (shift1 > 0) {
+		l1->off += shift1, l1->cnt -= shift1;
+		l1->qs = (int32_t)a[l1->off].y + 1 - (int32_t)(a[l1->off].y >> 32 & 0xff);
+		l1->rs = (int32_t)a[l1->off].x + 1 - (int32_t)(a[l1->off].y >> 32 & 0xff);
+	}
+	if (l0->cnt == 0) l0->qs = l0->qe = l1->qs, l0->rs = l0->re = l1->rs;
+	return 0;
+}
+
+// reference: gchain1.c:242-297 mg_gchain_extra (integer part; div = f(n_mini, n_anchor, q_span) is finished on the host)
+MG_HD inline int gchain_extra(const GraphDev &g, GcSet &gs)
+{
+	for (int32_t i = 0; i < gs.n_gc; ++i) {
+		GChain *p = &gs.gc[i];
+		const LLChain *q;
+		const u128 *last_a;
+		int32_t q_span, rest_pl, tmp, n_mini;
+		p->qs = p->qe = p->ps = p->pe = -1, p->plen = p->blen = p->mlen = 0, p->n_mini = 0, p->q_span = 0;
+		if (p->cnt == 0) continue;
+		if (!(gs.lc[p->off].cnt > 0 && gs.lc[p->off + p->cnt - 1].cnt > 0)) return MGB_E_INTERNAL;
+		q = &gs.lc[p->off];
+		q_span = (int32_t)(gs.a[q->off].y >> 32 & 0xff);
+		p->qs = (int32_t)gs.a[q->off].y + 1 - q_span;
+		p->ps = (int32_t)gs.a[q->off].x + 1 - q_span;
+		tmp = (int32_t)(gs.a[q->off].x >> 32);
+		q = &gs.lc[p->off + p->cnt - 1];
+		p->qe = (int32_t)gs.a[q->off + q->cnt - 1].y + 1;
+		p->pe = g.seg_len[q->v >> 1] - (int32_t)gs.a[q->off + q->cnt - 1].x - 1;
+		n_mini = (int32_t)(gs.a[q->off + q->cnt - 1].x >> 32) - tmp + 1;
+		rest_pl = 0;
+		last_a = &gs.a[gs.lc[p->off].off];
+		for (int32_t j = 0; j < p->cnt; ++j) {
+			const LLChain *qq = &gs.lc[p->off + j];
+			int32_t vlen = g.seg_len[qq->v >> 1];
+			p->plen += vlen;
+			for (int32_t k = 0; k < qq->cnt; ++k) {
+				const u128 *r = &gs.a[qq->off + k];
+				int32_t pl, ql = (int32_t)r->y - (int32_t)last_a->y;
+				int32_t span = (int32_t)(r->y >> 32 & 0xff);
+				if (j == 0 && k == 0) pl = ql = span;
+				else if (j > 0 && k == 0) pl = (int32_t)r->x + 1 + rest_pl;
+				else pl = (int32_t)r->x - (int32_t)last_a->x;
+				if (ql < 0) ql = -ql, n_mini += (int32_t)(last_a->x >> 32) - (int32_t)(r->x >> 32);
+				p->blen += pl > ql? pl : ql;
+				p->mlen += pl > span && ql > span? span : pl < ql? pl : ql;
+				last_a = r;
+			}
+			if (qq->cnt == 0) rest_pl += vlen;
+			else rest_pl = vlen - (int32_t)gs.a[qq->off + qq->cnt - 1].x - 1;
+		}
+		p->pe = p->plen - p->pe;
+		if (p->pe < p->ps) return MGB_E_INTERNAL;
+		p->n_mini = n_mini, p->q_span = q_span;
+	}
+	return 0;
+}
+
+// reference: gcmisc.c:8-33 mg_gchain_restore_order
+MG_HD inline int gchain_restore_order(Arena &A, GcSet &gs)
+{
+	uint64_t mark = A.top;
+	int32_t i, n_a, n_lc;
+	LLChain *lc;
+	u128 *a;
+	MGB_ALLOC(A, lc, LLChain, gs.n_lc);
+	MGB_ALLOC(A, a, u128, gs.n_a);
+	for (i = 0, n_a = n_lc = 0; i < gs.n_gc; ++i) {
+		GChain *gc = &gs.gc[i];
+		if (gc->cnt <= 0) return MGB_E_INTERNAL;
+		for (int32_t k = 0; k < gc->cnt; ++k) lc[n_lc + k] = gs.lc[gc->off + k];
+		const u128 *src = &gs.a[gs.lc[gc->off].off];
+		for (int32_t k = 0; k < gc->n_anchor; ++k) a[n_a + k] = src[k];
+		n_lc += gc->cnt, n_a += gc->n_anchor;
+	}
+	for (i = 0; i < gs.n_lc; ++i) gs.lc[i] = lc[i];
+	for (i = 0; i < gs.n_a; ++i) gs.a[i] = a[i];
+	for (i = 0, n_lc = 0; i < gs.n_gc; ++i) {
+		gs.gc[i].off = n_lc;
+		n_lc += gs.gc[i].cnt;
+	}
+	for (i = 0, n_a = 0; i < gs.n_lc; ++i) {
+		gs.lc[i].off = n_a;
+		n_a += gs.lc[i].cnt;
+	}
+	A.top = mark;
+	return 0;
+}
+
+// reference: gcmisc.c:56-71 mg_gchain_sort_by_score
+MG_HD inline int gchain_sort_by_score(Arena &A, GcSet &gs)
+{
+	uint64_t mark = A.top;
+	u128 *z;
+	GChain *gc;
+	MGB_ALLOC(A, z, u128, gs.n_gc);
+	MGB_ALLOC(A, gc, GChain, gs.n_gc);
+	for (int32_t i = 0; i < gs.n_gc; ++i)
+		z[i].x = (uint64_t)(int64_t)gs.gc[i].score << 32 | gs.gc[i].hash, z[i].y = (uint64_t)i;
+	MGB_TRY(radix_sort_128x(A, z, gs.n_gc));
+	for (int32_t i = gs.n_gc - 1; i >= 0; --i) gc[gs.n_gc - 1 - i] = gs.gc[z[i].y];
+	for (int32_t i = 0; i < gs.n_gc; ++i) gs.gc[i] = gc[i];
+	A.top = mark;
+	return gchain_restore_order(A, gs);
+}
+
+// Build graph chains from the DP result.  Output arrays are allocated at the caller's mark (gs.gc, gs.a, gs.lc).
+MG_HD inline int gchain_gen(Arena &A, const GraphDev &g, int32_t n_u, const uint64_t *u, LChain *lc, const u128 *a, uint32_t hash,
+							int32_t min_gc_cnt, int32_t min_gc_score, int32_t gdp_max_ed, int32_t n_seg, const char *qseq, GcSet &gs)
+{
+	int32_t i, j, k, st, kmer_size;
+	gs.n_gc = gs.n_lc = gs.n_a = 0, gs.rep_len = 0, gs.gc = 0, gs.lc = 0, gs.a = 0;
+	int32_t n_lc_in = 0;
+	for (i = 0, st = 0; i < n_u; ++i) {
+		int32_t m = 0, nui = (int32_t)u[i];
+		for (j = 0; j < nui; ++j) m += lc[st + j].cnt;
+		if (m >= min_gc_cnt && (int64_t)(u[i] >> 32) >= (int64_t)min_gc_score) gs.n_gc++, gs.n_a += m;
+		st += nui;
+	}
+	n_lc_in = st;
+	if (gs.n_gc == 0) return 0;
+	MGB_ALLOC(A, gs.gc, GChain, gs.n_gc);
+	memset(gs.gc, 0, sizeof(GChain) * (size_t)gs.n_gc);
+	MGB_ALLOC(A, gs.a, u128, gs.n_a);
+	// llc can hold at most one entry per input lchain plus the bridging vertices: give it head room below the scratch
+	BridgeAux aux;
+	aux.g = &g, aux.qseq = qseq, aux.n_a = 0, aux.a_new = gs.a;
+	avec_init(aux.llc);
+	MGB_TRY(avec_reserve(A, aux.llc, n_lc_in + 64));
+	kmer_size = (int32_t)(a[0].y >> 32 & 0xff);
+	for (i = k = 0, st = 0; i < n_u; ++i) {
+		int32_t n_a0 = aux.n_a, n_llc0 = (int32_t)aux.llc.n, m = 0, nui = (int32_t)u[i];
+		for (j = 0; j < nui; ++j) m += lc[st + j].cnt;
+		if (m >= min_gc_cnt && (int64_t)(u[i] >> 32) >= (int64_t)min_gc_score) {
+			uint32_t h = hash;
+			int32_t j0;
+			gs.gc[k].score = (int32_t)(u[i] >> 32);
+			gs.gc[k].off = n_llc0;
+			for (j = 0; j < nui; ++j) {
+				const LChain *p = &lc[st + j];
+				h += hash32((uint32_t)p->qs) + hash32((uint32_t)p->re) + hash32(p->v);
+			}
+			gs.gc[k].hash = hash32(h);
+			for (j = 1; j < nui; ++j) MGB_TRY(gc_resolve_overlap(&lc[st + j - 1], &lc[st + j], a));
+			{
+				LLChain q;
+				gc_copy_lchain(&q, &lc[st], &aux.n_a, gs.a, a, -1);
+				MGB_TRY(avec_push(A, aux.llc, q));
+			}
+			for (j0 = 0, j = 1; j < nui; ++j) {
+				const LChain *l0 = &lc[st + j0], *l1 = &lc[st + j];
+				if (l1->cnt > 0) {
+					int failed;
+					MGB_TRY(gc_bridge_lchains(A, aux, n_seg, kmer_size, gdp_max_ed, l0, l1, a, &failed));
+					if (failed) {
+						for (int32_t t = j0; t < j; ++t) {
+							MGB_TRY(gc_bridge_lchains(A, aux, n_seg, kmer_size, gdp_max_ed, &lc[st + t], &lc[st + t + 1], a, &failed));
+							if (failed) return MGB_E_INTERNAL;
+						}
+					}
+					j0 = j;
+				}
+			}
+			gs.gc[k].cnt = (int32_t)aux.llc.n - n_llc0;
+			gs.gc[k].n_anchor = aux.n_a - n_a0;
+			++k;
+		}
+		st += nui;
+	}
+	if (aux.n_a > gs.n_a) return MGB_E_INTERNAL;
+	gs.n_a = aux.n_a;
+	gs.n_lc = (int32_t)aux.llc.n;
+	gs.lc = aux.llc.a;
+	MGB_TRY(gchain_extra(g, gs));
+	MGB_TRY(gchain_sort_by_score(A, gs));
+	return 0;
+}
+
+// ---- primary/secondary bookkeeping (reference: gcmisc.c:74-223) ----
+
+MG_HD inline int gchain_set_parent(Arena &A, float mask_level, int n, GChain *r, int sub_diff)
+{
+	uint64_t mark = A.top;
+	int i, j, k, *w;
+	uint64_t *cov;
+	if (n <= 0) return 0;
+	for (i = 0; i < n; ++i) r[i].id = i;
+	MGB_ALLOC(A, cov, uint64_t, n);
+	MGB_ALLOC(A, w, int, n);
+	w[0] = 0, r[0].parent = 0;
+	for (i = 1, k = 1; i < n; ++i) {
+		GChain *ri = &r[i];
+		int si = ri->qs, ei = ri->qe, n_cov = 0, uncov_len = 0;
+		for (j = 0; j < k; ++j) {
+			GChain *rp = &r[w[j]];
+			int sj = rp->qs, ej = rp->qe;
+			if (ej <= si || sj >= ei) continue;
+			if (sj < si) sj = si;
+			if (ej > ei) ej = ei;
+			cov[n_cov++] = (uint64_t)(int64_t)sj << 32 | (uint64_t)(int64_t)ej;
+		}
+		if (n_cov > 0) {
+			int x = si;
+			MGB_TRY(radix_sort_64(A, cov, n_cov));
+			for (j = 0; j < n_cov; ++j) {
+				if ((int)(cov[j] >> 32) > x) uncov_len += (int)((cov[j] >> 32) - (uint64_t)(int64_t)x);
+				x = (int32_t)cov[j] > x? (int32_t)cov[j] : x;
+			}
+			if (ei > x) uncov_len += ei - x;
+			for (j = 0; j < k; ++j) {
+				GChain *rp = &r[w[j]];
+				int sj = rp->qs, ej = rp->qe, mn, mx, ol;
+				if (ej <= si || sj >= ei) continue;
+				mn = ej - sj < ei - si? ej - sj : ei - si;
+				mx = ej - sj > ei - si? ej - sj : ei - si;
+				ol = si < sj? (ei < sj? 0 : ei < ej? ei - sj : ej - sj) : (ej < si? 0 : ej < ei? ej - si : ei - si);
+				if ((float)ol / (float)mn - (float)uncov_len / (float)mx > mask_level) {
+					int cnt_sub = 0;
+					ri->parent = rp->parent;
+					rp->subsc = rp->subsc > ri->score? rp->subsc : ri->score;
+					if (ri->cnt >= rp->cnt) cnt_sub = 1;
+					if (cnt_sub) ++rp->n_sub;
+					break;
+				}
+			}
+		} else j = k;
+		if (j == k) w[k++] = i, ri->parent = i, ri->n_sub = 0;
+	}
+	(void)sub_diff;
+	A.top = mark;
+	return 0;
+}
+
+MG_HD inline void gchain_flt_sub(float pri_ratio, int min_diff, int best_n, int n, GChain *r)
+{
+	if (pri_ratio > 0.0f && n > 0) {
+		int i, n_2nd = 0;
+		for (i = 0; i < n; ++i) {
+			int p = r[i].parent;
+			if (p == i) r[i].flt = 0;
+			else if (((float)r[i].score >= (float)r[p].score * pri_ratio || r[i].score + min_diff >= r[p].score) && n_2nd < best_n) {
+				if (!(r[i].qs == r[p].qs && r[i].qe == r[p].qe && r[i].ps == r[p].ps && r[i].pe == r[p].pe)) r[i].flt = 0, ++n_2nd;
+				else r[i].flt = 1;
+			} else r[i].flt = 1;
+		}
+	}
+}
+
+// reference: gcmisc.c:151-188 mg_gchain_drop_flt (+ restore_offset)
+MG_HD inline int gchain_drop_flt(Arena &A, GcSet &gs)
+{
+	uint64_t mark = A.top;
+	int32_t i, j, n_gc, n_lc, n_a, n_lc0, n_a0, *o2n;
+	if (gs.n_gc == 0) return 0;
+	MGB_ALLOC(A, o2n, int32_t, gs.n_gc);
+	for (i = 0, n_gc = 0; i < gs.n_gc; ++i) {
+		GChain *r = &gs.gc[i];
+		o2n[i] = -1;
+		if (r->flt || r->cnt == 0) continue;
+		o2n[i] = n_gc++;
+	}
+	n_gc = n_lc = n_a = 0;
+	n_lc0 = n_a0 = 0;
+	for (i = 0; i < gs.n_gc; ++i) {
+		GChain *r = &gs.gc[i];
+		if (o2n[i] >= 0) {
+			int32_t r_cnt = r->cnt, r_na = r->n_anchor;
+			for (j = 0; j < r_na; ++j) gs.a[n_a + j] = gs.a[n_a0 + j];
+			for (j = 0; j < r_cnt; ++j) gs.lc[n_lc + j] = gs.lc[n_lc0 + j];
+			gs.gc[n_gc] = *r;
+			gs.gc[n_gc].id = n_gc;
+			gs.gc[n_gc].parent = o2n[gs.gc[n_gc].parent];
+			++n_gc, n_lc += r_cnt, n_a += r_na;
+			n_lc0 += r_cnt, n_a0 += r_na;
+		} else n_lc0 += r->cnt, n_a0 += r->n_anchor;
+	}
+	if (n_lc0 != gs.n_lc || n_a0 != gs.n_a) return MGB_E_INTERNAL;
+	gs.n_gc = n_gc, gs.n_lc = n_lc, gs.n_a = n_a;
+	for (i = 0, n_a = n_lc = 0; i < gs.n_gc; ++i) { // restore_offset
+		GChain *gc = &gs.gc[i];
+		gc->off = n_lc;
+		for (j = 0, gc->n_anchor = 0; j < gc->cnt; ++j) {
+			LLChain *lc = &gs.lc[n_lc + j];
+			lc->off = n_a;
+			n_a += lc->cnt;
+			gc->n_anchor += lc->cnt;
+		}
+		n_lc += gc->cnt;
+	}
+	if (n_lc != gs.n_lc || n_a != gs.n_a) return MGB_E_INTERNAL;
+	A.top = mark;
+	return 0;
+}
+
+// reference: gcmisc.c:191-223 mg_gchain_set_mapq; logf() comes from the host-tabulated glibc values
+MG_HD inline int gchain_set_mapq(const MapOptDev &o, GcSet &gs, int qlen, int max_mini, int min_gc_score)
+{
+	const float q_coef = 40.0f;
+	int64_t sum_sc = 0;
+	float uniq_ratio, r_sc, r_cnt;
+	int i, t_sc, t_cnt;
+	if (gs.n_gc == 0) return 0;
+	t_sc = qlen < 100? qlen : 100;
+	t_cnt = max_mini < 10? max_mini : 10;
+	if (t_cnt < 5) t_cnt = 5;
+	r_sc = (float)(1.0 / (double)t_sc);
+	r_cnt = (float)(1.0 / (double)t_cnt);
+	for (i = 0; i < gs.n_gc; ++i)
+		if (gs.gc[i].parent == gs.gc[i].id) sum_sc += gs.gc[i].score;
+	uniq_ratio = (float)sum_sc / (float)(sum_sc + gs.rep_len);
+	for (i = 0; i < gs.n_gc; ++i) {
+		GChain *r = &gs.gc[i];
+		if (r->parent == r->id) {
+			int mapq, subsc;
+			float pen_s1 = (r->score > t_sc? 1.0f : (float)r->score * r_sc) * uniq_ratio;
+			float x, pen_cm = r->n_anchor > t_cnt? 1.0f : (float)r->n_anchor * r_cnt;
+			pen_cm = pen_s1 < pen_cm? pen_s1 : pen_cm;
+			subsc = r->subsc > min_gc_score? r->subsc : min_gc_score;
+			x = (float)subsc / (float)r->score;
+			if (r->score < 0 || r->score >= o.n_logf_tab || r->n_sub + 1 >= o.n_logf_tab) return MGB_E_UNSUPPORTED;
+			mapq = (int)(pen_cm * q_coef * (1.0f - x) * o.logf_tab[r->score]);
+			mapq -= (int)(4.343f * o.logf_tab[r->n_sub + 1] + .499f);
+			mapq = mapq > 0? mapq : 0;
+			if (r->score > subsc && mapq == 0) mapq = 1;
+			r->mapq = mapq < 60? mapq : 60;
+		} else r->mapq = 0;
+	}
+	return 0;
+}
+
+} // namespace mgb

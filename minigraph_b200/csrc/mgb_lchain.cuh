@@ -1,0 +1,510 @@
+// mgb_lchain.cuh -- stage B: linear chaining of one read's seeds.
+//   chain_dp()      banded DP with skip heuristics          (reference: lchain.c:149-219 mg_lchain_dp)
+//   chain_rmq()     RMQ-tree DP for long gaps               (reference: lchain.c:252-372 mg_lchain_rmq)
+//   chain_backtrack / chain_compact                          (reference: lchain.c:9-112)
+//   lchain_gen, end trimming and bad-seed filters            (reference: lchain.c:374-441, map-algo.c:194-330)
+#pragma once
+#include "mgb_model.cuh"
+#include "mgb_rmq.cuh"
+
+namespace mgb {
+
+static const int32_t SC_NONE = INT32_MIN;
+
+// chaining score between anchors i (later) and j (earlier)  (reference: lchain.c:114-139 comput_sc)
+MG_HD inline int32_t chain_score(const u128 &ai, const u128 &aj, int32_t max_dist_x, int32_t max_dist_y, int32_t bw,
+								 float pen_gap, float pen_skip, int is_cdna, int n_seg)
+{
+	int32_t dq = (int32_t)ai.y - (int32_t)aj.y, dr, dd, dg, q_span, sc;
+	int32_t sidi = (int32_t)((ai.y & SEED_SEG_MASK) >> SEED_SEG_SHIFT);
+	int32_t sidj = (int32_t)((aj.y & SEED_SEG_MASK) >> SEED_SEG_SHIFT);
+	if (dq <= 0 || dq > max_dist_x) return SC_NONE;
+	dr = (int32_t)(ai.x - aj.x);
+	if (sidi == sidj && (dr == 0 || dq > max_dist_y)) return SC_NONE;
+	dd = dr > dq? dr - dq : dq - dr;
+	if (sidi == sidj && dd > bw) return SC_NONE;
+	if (n_seg > 1 && !is_cdna && sidi == sidj && dr > max_dist_y) return SC_NONE;
+	dg = dr < dq? dr : dq;
+	q_span = (int32_t)(aj.y >> 32 & 0xff);
+	sc = q_span < dg? q_span : dg;
+	if (dd || dg > q_span) {
+		float lin_pen = pen_gap * (float)dd + pen_skip * (float)dg;
+		float log_pen = dd >= 1? fast_log2((float)(dd + 1)) : 0.0f;
+		if (is_cdna || sidi != sidj) {
+			if (sidi != sidj && dr == 0) ++sc;
+			else if (dr > dq || sidi != sidj) sc -= (int)(lin_pen < log_pen? lin_pen : log_pen);
+			else sc -= (int)(lin_pen + .5f * log_pen);
+		} else sc -= (int)(lin_pen + .5f * log_pen);
+	}
+	return sc;
+}
+
+// follow one chain backwards from z[k] until the score drops too far (reference: lchain.c:9-25)
+MG_HD inline int64_t chain_bk_end(int32_t max_drop, const u128 *z, const int32_t *f, const int32_t *p, int32_t *t, int64_t k)
+{
+	int64_t i = (int64_t)z[k].y, end_i = -1, max_i = i;
+	int32_t max_s = 0;
+	if (i < 0 || t[i] != 0) return i;
+	do {
+		int32_t s;
+		t[i] = 2;
+		end_i = i = p[i];
+		s = i < 0? (int32_t)z[k].x : (int32_t)z[k].x - f[i];
+		if (s > max_s) max_s = s, max_i = i;
+		else if (max_s - s > max_drop) break;
+	} while (i >= 0 && t[i] == 0);
+	for (i = (int64_t)z[k].y; i >= 0 && i != end_i; i = p[i]) t[i] = 0;
+	return max_i;
+}
+
+// peel chains best-score-first (reference: lchain.c:27-77 mg_chain_backtrack). u[] gets extra_u spare entries.
+MG_HD inline int chain_backtrack(Arena &A, int64_t n, const int32_t *f, const int32_t *p, int32_t *v, int32_t *t, int32_t min_cnt, int32_t min_sc,
+								 int32_t max_drop, int32_t extra_u, uint64_t **u_, int32_t *n_u_, int32_t *n_v_)
+{
+	u128 *z;
+	uint64_t *u;
+	int64_t i, k, n_z = 0, n_v;
+	int32_t n_u;
+	*n_u_ = *n_v_ = 0, *u_ = 0;
+	for (i = 0; i < n; ++i) if (f[i] >= min_sc) ++n_z;
+	if (n_z == 0) return 0;
+	// u[] must outlive z[]: reserve the worst case first (one chain per end point), then z on top
+	MGB_ALLOC(A, u, uint64_t, n_z + extra_u);
+	uint64_t mark = A.top;
+	MGB_ALLOC(A, z, u128, n_z);
+	for (i = 0, k = 0; i < n; ++i)
+		if (f[i] >= min_sc) z[k].x = (uint64_t)(int64_t)f[i], z[k++].y = (uint64_t)i;
+	MGB_TRY(radix_sort_128x(A, z, n_z));
+	for (i = 0; i < n; ++i) t[i] = 0;
+	for (k = n_z - 1, n_v = n_u = 0; k >= 0; --k) {
+		if (t[z[k].y] == 0) {
+			int64_t n_v0 = n_v, end_i;
+			int32_t sc;
+			end_i = chain_bk_end(max_drop, z, f, p, t, k);
+			for (i = (int64_t)z[k].y; i != end_i; i = p[i])
+				v[n_v++] = (int32_t)i, t[i] = 1;
+			sc = i < 0? (int32_t)z[k].x : (int32_t)z[k].x - f[i];
+			if (sc >= min_sc && n_v > n_v0 && n_v - n_v0 >= min_cnt)
+				u[n_u++] = (uint64_t)sc << 32 | (uint64_t)(n_v - n_v0);
+			else n_v = n_v0;
+		}
+	}
+	A.top = mark;
+	*u_ = u, *n_u_ = n_u, *n_v_ = (int32_t)n_v;
+	return 0;
+}
+
+// gather chained anchors and order chains by target position (reference: lchain.c:79-112 compact_a).
+// The result (n_v anchors) is written back to a[0..n_v).
+MG_HD inline int chain_compact(Arena &A, int32_t n_u, uint64_t *u, int32_t n_v, const int32_t *v, u128 *a)
+{
+	uint64_t mark = A.top;
+	u128 *b, *w;
+	uint64_t *u2;
+	int64_t i, j, k;
+	MGB_ALLOC(A, b, u128, n_v);
+	for (i = 0, k = 0; i < n_u; ++i) {
+		int32_t k0 = (int32_t)k, ni = (int32_t)u[i];
+		for (j = 0; j < ni; ++j) b[k++] = a[v[k0 + (ni - j - 1)]];
+	}
+	MGB_ALLOC(A, w, u128, n_u);
+	for (i = k = 0; i < n_u; ++i) {
+		w[i].x = b[k].x, w[i].y = (uint64_t)k << 32 | (uint64_t)i;
+		k += (int32_t)u[i];
+	}
+	MGB_TRY(radix_sort_128x(A, w, n_u));
+	MGB_ALLOC(A, u2, uint64_t, n_u);
+	for (i = k = 0; i < n_u; ++i) {
+		int32_t j2 = (int32_t)w[i].y, n = (int32_t)u[j2];
+		const u128 *src = &b[w[i].y >> 32];
+		u2[i] = u[j2];
+		for (int32_t x = 0; x < n; ++x) a[k + x] = src[x];
+		k += n;
+	}
+	for (i = 0; i < n_u; ++i) u[i] = u2[i];
+	A.top = mark;
+	return 0;
+}
+
+// Banded chaining DP (reference: lchain.c:149-219).  On return a[0..*n_a_) holds the chained anchors
+// and u[0..n_u) = score<<32|cnt per chain (u lives in the arena above the caller's mark).
+MG_HD inline int chain_dp(Arena &A, int max_dist_x, int max_dist_y, int bw, int max_skip, int max_iter, int min_cnt, int min_sc,
+						  float pen_gap, float pen_skip, int is_cdna, int n_seg, int64_t n, u128 *a,
+						  int32_t *n_u_, uint64_t **u_, int32_t *n_a_)
+{
+	int32_t *f, *t, *v, *p, n_u, n_v, max_drop = bw;
+	int64_t i, j, max_ii, st = 0;
+	uint64_t *u;
+	*u_ = 0, *n_u_ = 0, *n_a_ = 0;
+	if (n == 0) return 0;
+	if (max_dist_x < bw) max_dist_x = bw;
+	if (max_dist_y < bw && !is_cdna) max_dist_y = bw;
+	if (is_cdna) max_drop = INT32_MAX;
+	// u is allocated by chain_backtrack below the scratch; to keep stack discipline the scratch is
+	// carved after reserving room for u at the bottom.
+	uint64_t *u_store;
+	MGB_ALLOC(A, u_store, uint64_t, n);
+	uint64_t mark = A.top;
+	MGB_ALLOC(A, p, int32_t, n);
+	MGB_ALLOC(A, f, int32_t, n);
+	MGB_ALLOC(A, v, int32_t, n);
+	MGB_ALLOC(A, t, int32_t, n);
+	for (i = 0; i < n; ++i) t[i] = 0;
+	for (i = 0, max_ii = -1; i < n; ++i) {
+		int64_t max_j = -1, end_j;
+		int32_t max_f = (int32_t)(a[i].y >> 32 & 0xff), n_skip = 0;
+		while (st < i && (a[i].x >> 32 != a[st].x >> 32 || a[i].x > a[st].x + (uint64_t)max_dist_x)) ++st;
+		if (i - st > max_iter) st = i - max_iter;
+		for (j = i - 1; j >= st; --j) {
+			int32_t sc = chain_score(a[i], a[j], max_dist_x, max_dist_y, bw, pen_gap, pen_skip, is_cdna, n_seg);
+			if (sc == SC_NONE) continue;
+			sc += f[j];
+			if (sc > max_f) {
+				max_f = sc, max_j = j;
+				if (n_skip > 0) --n_skip;
+			} else if (t[j] == (int32_t)i) {
+				if (++n_skip > max_skip) break;
+			}
+			if (p[j] >= 0) t[p[j]] = (int32_t)i;
+		}
+		end_j = j;
+		if (max_ii < 0 || (int64_t)(a[i].x - a[max_ii].x) > (int64_t)max_dist_x) {
+			int32_t mx = INT32_MIN;
+			max_ii = -1;
+			for (j = i - 1; j >= st; --j)
+				if (mx < f[j]) mx = f[j], max_ii = j;
+		}
+		if (max_ii >= 0 && max_ii < end_j) {
+			int32_t tmp = chain_score(a[i], a[max_ii], max_dist_x, max_dist_y, bw, pen_gap, pen_skip, is_cdna, n_seg);
+			if (tmp != SC_NONE && max_f < tmp + f[max_ii])
+				max_f = tmp + f[max_ii], max_j = max_ii;
+		}
+		f[i] = max_f, p[i] = (int32_t)max_j;
+		v[i] = max_j >= 0 && v[max_j] > max_f? v[max_j] : max_f;
+		if (max_ii < 0 || ((int64_t)(a[i].x - a[max_ii].x) <= (int64_t)max_dist_x && f[max_ii] < f[i]))
+			max_ii = i;
+	}
+	MGB_TRY(chain_backtrack(A, n, f, p, v, t, min_cnt, min_sc, max_drop, 0, &u, &n_u, &n_v));
+	if (n_u > 0) {
+		MGB_TRY(chain_compact(A, n_u, u, n_v, v, a));
+		for (i = 0; i < n_u; ++i) u_store[i] = u[i];
+	}
+	A.top = mark;
+	*u_ = u_store, *n_u_ = n_u, *n_a_ = n_u > 0? n_v : 0;
+	return 0;
+}
+
+// gap-only score used by the RMQ DP (reference: lchain.c:234-250 comput_sc_simple)
+MG_HD inline int32_t chain_score_simple(const u128 &ai, const u128 &aj, float pen_gap, float pen_skip, int32_t *exact, int32_t *width)
+{
+	int32_t dq = (int32_t)ai.y - (int32_t)aj.y, dr, dd, dg, q_span, sc;
+	dr = (int32_t)(ai.x - aj.x);
+	*width = dd = dr > dq? dr - dq : dq - dr;
+	dg = dr < dq? dr : dq;
+	q_span = (int32_t)(aj.y >> 32 & 0xff);
+	sc = q_span < dg? q_span : dg;
+	if (exact) *exact = (dd == 0 && dg <= q_span);
+	if (dd || dq > q_span) {
+		float lin_pen = pen_gap * (float)dd + pen_skip * (float)dg;
+		float log_pen = dd >= 1? fast_log2((float)(dd + 1)) : 0.0f;
+		sc -= (int)(lin_pen + .5f * log_pen);
+	}
+	return sc;
+}
+
+// RMQ chaining (reference: lchain.c:252-372).  Same output convention as chain_dp().
+MG_HD inline int chain_rmq(Arena &A, int max_dist, int max_dist_inner, int bw, int max_chn_skip, int cap_rmq_size, int min_cnt, int min_sc,
+						   float pen_gap, float pen_skip, int64_t n, u128 *a, int32_t *n_u_, uint64_t **u_, int32_t *n_a_)
+{
+	int32_t *f, *t, *v, *p, n_u, n_v, max_drop = bw;
+	int64_t i, i0, st = 0, st_inner = 0;
+	uint64_t *u;
+	RmqTree root, root_inner;
+	*u_ = 0, *n_u_ = 0, *n_a_ = 0;
+	if (n == 0) return 0;
+	if (max_dist < bw) max_dist = bw;
+	if (max_dist_inner <= 0 || max_dist_inner >= max_dist) max_dist_inner = 0;
+	uint64_t *u_store;
+	MGB_ALLOC(A, u_store, uint64_t, n);
+	uint64_t mark = A.top;
+	MGB_ALLOC(A, p, int32_t, n);
+	MGB_ALLOC(A, f, int32_t, n);
+	MGB_ALLOC(A, t, int32_t, n);
+	MGB_ALLOC(A, v, int32_t, n);
+	for (i = 0; i < n; ++i) t[i] = 0;
+	uint64_t mark_tree = A.top;
+	MGB_TRY(rmq_init(A, root, (int32_t)n));
+	root_inner.nd = 0, root_inner.root = RMQ_NIL, root_inner.n_nd = root_inner.m_nd = 0;
+	if (max_dist_inner > 0) MGB_TRY(rmq_init(A, root_inner, (int32_t)n));
+
+	for (i = i0 = 0; i < n; ++i) {
+		int64_t max_j = -1;
+		int32_t q_span = (int32_t)(a[i].y >> 32 & 0xff), max_f = q_span;
+		int32_t q;
+		// add in-range anchors
+		if (i0 < i && a[i0].x != a[i].x) {
+			for (int64_t j = i0; j < i; ++j) {
+				double pri = -(f[j] + 0.5 * pen_gap * ((int32_t)a[j].x + (int32_t)a[j].y));
+				if (rmq_insert(root, (int32_t)a[j].y, (int32_t)j, pri) < 0) return MGB_E_INTERNAL;
+				if (max_dist_inner > 0)
+					if (rmq_insert(root_inner, (int32_t)a[j].y, (int32_t)j, pri) < 0) return MGB_E_INTERNAL;
+			}
+			i0 = i;
+		}
+		// drop anchors out of range
+		while (st < i && (a[i].x >> 32 != a[st].x >> 32 || a[i].x > a[st].x + (uint64_t)max_dist || rmq_size(root) > (uint32_t)cap_rmq_size)) {
+			rmq_erase(root, (int32_t)a[st].y, (int32_t)st);
+			++st;
+		}
+		if (max_dist_inner > 0) {
+			while (st_inner < i && (a[i].x >> 32 != a[st_inner].x >> 32 || a[i].x > a[st_inner].x + (uint64_t)max_dist_inner || rmq_size(root_inner) > (uint32_t)cap_rmq_size)) {
+				rmq_erase(root_inner, (int32_t)a[st_inner].y, (int32_t)st_inner);
+				++st_inner;
+			}
+		}
+		// RMQ
+		q = rmq_query(root, (int32_t)a[i].y - max_dist, INT32_MAX, (int32_t)a[i].y - 1, 0);
+		if (q != RMQ_NIL) {
+			int32_t sc, exact, width, n_skip = 0;
+			int64_t j = root.nd[q].i;
+			sc = f[j] + chain_score_simple(a[i], a[j], pen_gap, pen_skip, &exact, &width);
+			if (width <= bw && sc > max_f) max_f = sc, max_j = j;
+			if (!exact && root_inner.root != RMQ_NIL && (int32_t)a[i].y > 0) {
+				int32_t lo = rmq_lower(root_inner, (int32_t)a[i].y - 1, (int32_t)n);
+				if (lo != RMQ_NIL) {
+					RmqItr itr;
+					int32_t qi;
+					rmq_itr_find(root_inner, lo, itr);
+					while ((qi = rmq_itr_at(itr)) != RMQ_NIL) {
+						if (root_inner.nd[qi].y < (int32_t)a[i].y - max_dist_inner) break;
+						j = root_inner.nd[qi].i;
+						sc = f[j] + chain_score_simple(a[i], a[j], pen_gap, pen_skip, 0, &width);
+						if (width <= bw) {
+							if (sc > max_f) {
+								max_f = sc, max_j = j;
+								if (n_skip > 0) --n_skip;
+							} else if (t[j] == (int32_t)i) {
+								if (++n_skip > max_chn_skip) break;
+							}
+							if (p[j] >= 0) t[p[j]] = (int32_t)i;
+						}
+						if (!rmq_itr_prev(root_inner, itr)) break;
+					}
+				}
+			}
+		}
+		f[i] = max_f, p[i] = (int32_t)max_j;
+		v[i] = max_j >= 0 && v[max_j] > max_f? v[max_j] : max_f;
+	}
+	A.top = mark_tree;
+	MGB_TRY(chain_backtrack(A, n, f, p, v, t, min_cnt, min_sc, max_drop, 0, &u, &n_u, &n_v));
+	if (n_u > 0) {
+		MGB_TRY(chain_compact(A, n_u, u, n_v, v, a));
+		for (i = 0; i < n_u; ++i) u_store[i] = u[i];
+	}
+	A.top = mark;
+	*u_ = u_store, *n_u_ = n_u, *n_a_ = n_u > 0? n_v : 0;
+	return 0;
+}
+
+// chain descriptors ordered by query start (reference: lchain.c:374-408 mg_lchain_gen)
+MG_HD inline int lchain_gen(Arena &A, int n_u, const uint64_t *u, const u128 *a, LChain *r)
+{
+	uint64_t mark = A.top;
+	u128 *z;
+	int i, k;
+	if (n_u == 0) return 0;
+	MGB_ALLOC(A, z, u128, n_u);
+	for (i = k = 0; i < n_u; ++i) {
+		int32_t qs = (int32_t)a[k].y + 1 - (int32_t)(a[k].y >> 32 & 0xff);
+		z[i].x = (uint64_t)(uint32_t)qs << 32 | u[i] >> 32;
+		z[i].y = (uint64_t)k << 32 | (uint64_t)(uint32_t)(int32_t)u[i];
+		k += (int32_t)u[i];
+	}
+	MGB_TRY(radix_sort_128x(A, z, n_u));
+	for (i = 0; i < n_u; ++i) {
+		LChain *ri = &r[i];
+		int32_t k2 = (int32_t)(z[i].y >> 32), q_span = (int32_t)(a[k2].y >> 32 & 0xff);
+		ri->off = k2;
+		ri->cnt = (int32_t)z[i].y;
+		ri->score = (int32_t)(uint32_t)z[i].x;
+		ri->v = (uint32_t)(a[k2].x >> 32);
+		ri->rs = (int32_t)a[k2].x + 1 > q_span? (int32_t)a[k2].x + 1 - q_span : 0;
+		ri->qs = (int32_t)(z[i].x >> 32);
+		ri->re = (int32_t)a[k2 + ri->cnt - 1].x + 1;
+		ri->qe = (int32_t)a[k2 + ri->cnt - 1].y + 1;
+		ri->dist_pre = 0, ri->hash_pre = 0, ri->inner_pre = 0;
+	}
+	A.top = mark;
+	return 0;
+}
+
+// trim chain ends made of high-occurrence seeds (reference: map-algo.c:194-206 mm_fix_bad_ends)
+MG_HD inline void fix_bad_ends(const u128 *a, int32_t lc_max_occ, int32_t lc_max_trim, int32_t *as, int32_t *cnt)
+{
+	int32_t i, k, as0 = *as, cnt0 = *cnt;
+	for (i = as0 + cnt0 - 1, k = 0; k < lc_max_trim && k < cnt0; ++k, --i)
+		if ((int64_t)(a[i].y >> SEED_OCC_SHIFT) <= (int64_t)lc_max_occ) break;
+	*cnt -= k;
+	for (i = as0, k = 0; k < *cnt && k < lc_max_trim; ++i, ++k)
+		if ((int64_t)(a[i].y >> SEED_OCC_SHIFT) <= (int64_t)lc_max_occ) break;
+	*as += k, *cnt -= k;
+}
+
+// trim ends that hang off through a large indel (reference: map-algo.c:208-242 mm_fix_bad_ends_alt)
+MG_HD inline void fix_bad_ends_alt(const u128 *a, int32_t score, int bw, int min_match, int32_t *as, int32_t *cnt)
+{
+	int32_t i, l, m, as0 = *as, cnt0 = *cnt;
+	if (cnt0 < 3) return;
+	m = l = (int32_t)(a[as0].y >> 32 & 0xff);
+	for (i = as0 + 1; i < as0 + cnt0 - 1; ++i) {
+		int32_t lq, lr, mn, mx;
+		int32_t q_span = (int32_t)(a[i].y >> 32 & 0xff);
+		lr = (int32_t)a[i].x - (int32_t)a[i-1].x;
+		lq = (int32_t)a[i].y - (int32_t)a[i-1].y;
+		mn = lr < lq? lr : lq;
+		mx = lr > lq? lr : lq;
+		if (mx - mn > l >> 1) *as = i;
+		l += mn;
+		m += mn < q_span? mn : q_span;
+		if (l >= bw << 1 || (m >= min_match && m >= bw) || m >= score >> 1) break;
+	}
+	*cnt = as0 + cnt0 - *as;
+	m = l = (int32_t)(a[as0 + cnt0 - 1].y >> 32 & 0xff);
+	for (i = as0 + cnt0 - 2; i > *as; --i) {
+		int32_t lq, lr, mn, mx;
+		int32_t q_span = (int32_t)(a[i+1].y >> 32 & 0xff);
+		lr = (int32_t)a[i+1].x - (int32_t)a[i].x;
+		lq = (int32_t)a[i+1].y - (int32_t)a[i].y;
+		mn = lr < lq? lr : lq;
+		mx = lr > lq? lr : lq;
+		if (mx - mn > l >> 1) *cnt = i + 1 - *as;
+		l += mn;
+		m += mn < q_span? mn : q_span;
+		if (l >= bw << 1 || (m >= min_match && m >= bw) || m >= score >> 1) break;
+	}
+}
+
+MG_HD inline int32_t anchor_gap(const u128 *a, int32_t i) // query advance minus target advance between a[i-1] and a[i]
+{
+	return ((int32_t)a[i].y - (int32_t)a[i-1].y) - ((int32_t)a[i].x - (int32_t)a[i-1].x);
+}
+
+// positions of long gaps inside a chain (reference: map-algo.c:244-263 collect_long_gaps); K=0 when fewer than two
+MG_HD inline int collect_long_gaps(Arena &A, int as1, int cnt1, const u128 *a, int min_gap, int **K_, int *n_)
+{
+	int i, n, *K;
+	*n_ = 0, *K_ = 0;
+	for (i = 1, n = 0; i < cnt1; ++i) {
+		// NB: the reference mixes int32 and uint64 here; the result truncated to int is the same
+		int gap = (int)(((int64_t)(int32_t)a[as1 + i].y - (int64_t)a[as1 + i - 1].y) - ((int64_t)(int32_t)a[as1 + i].x - (int64_t)a[as1 + i - 1].x));
+		if (gap < -min_gap || gap > min_gap) ++n;
+	}
+	if (n <= 1) return 0;
+	MGB_ALLOC(A, K, int, n);
+	for (i = 1, n = 0; i < cnt1; ++i) {
+		int gap = (int)(((int64_t)(int32_t)a[as1 + i].y - (int64_t)a[as1 + i - 1].y) - ((int64_t)(int32_t)a[as1 + i].x - (int64_t)a[as1 + i - 1].x));
+		if (gap < -min_gap || gap > min_gap) K[n++] = i;
+	}
+	*n_ = n, *K_ = K;
+	return 0;
+}
+
+// flag seeds inside clusters of opposite indels (reference: map-algo.c:265-300 mm_filter_bad_seeds)
+MG_HD inline int filter_bad_seeds(Arena &A, int as1, int cnt1, u128 *a, int min_gap, int diff_thres, int max_ext_len, int max_ext_cnt)
+{
+	uint64_t mark = A.top;
+	int max_st, max_en, n, i, k, mx, *K;
+	MGB_TRY(collect_long_gaps(A, as1, cnt1, a, min_gap, &K, &n));
+	if (K == 0) return 0;
+	mx = 0, max_st = max_en = -1;
+	for (k = 0;; ++k) {
+		int gap, l, n_ins = 0, n_del = 0, qs, rs, max_diff = 0, max_diff_l = -1;
+		if (k == n || k >= max_en) {
+			if (max_en > 0)
+				for (i = K[max_st]; i < K[max_en]; ++i)
+					a[as1 + i].y |= SEED_IGNORE;
+			mx = 0, max_st = max_en = -1;
+			if (k == n) break;
+		}
+		i = K[k];
+		gap = ((int32_t)a[as1 + i].y - (int32_t)a[as1 + i - 1].y) - (int32_t)(a[as1 + i].x - a[as1 + i - 1].x);
+		if (gap > 0) n_ins += gap;
+		else n_del += -gap;
+		qs = (int32_t)a[as1 + i - 1].y;
+		rs = (int32_t)a[as1 + i - 1].x;
+		for (l = k + 1; l < n && l <= k + max_ext_cnt; ++l) {
+			int j = K[l], diff;
+			if ((int32_t)a[as1 + j].y - qs > max_ext_len || (int32_t)a[as1 + j].x - rs > max_ext_len) break;
+			gap = ((int32_t)a[as1 + j].y - (int32_t)a[as1 + j - 1].y) - (int32_t)(a[as1 + j].x - a[as1 + j - 1].x);
+			if (gap > 0) n_ins += gap;
+			else n_del += -gap;
+			diff = n_ins + n_del - (n_ins > n_del? n_ins - n_del : n_del - n_ins);
+			if (max_diff < diff) max_diff = diff, max_diff_l = l;
+		}
+		if (max_diff > diff_thres && max_diff > mx)
+			mx = max_diff, max_st = k, max_en = max_diff_l;
+	}
+	A.top = mark;
+	return 0;
+}
+
+// flag seeds between compensating long gaps (reference: map-algo.c:302-338 mm_filter_bad_seeds_alt)
+MG_HD inline int filter_bad_seeds_alt(Arena &A, int as1, int cnt1, u128 *a, int min_gap, int max_ext)
+{
+	uint64_t mark = A.top;
+	int n, k, *K;
+	MGB_TRY(collect_long_gaps(A, as1, cnt1, a, min_gap, &K, &n));
+	if (K == 0) return 0;
+	for (k = 0; k < n;) {
+		int i = K[k], l;
+		int gap1 = ((int32_t)a[as1 + i].y - (int32_t)a[as1 + i - 1].y) - ((int32_t)a[as1 + i].x - (int32_t)a[as1 + i - 1].x);
+		int re1 = (int32_t)a[as1 + i].x;
+		int qe1 = (int32_t)a[as1 + i].y;
+		gap1 = gap1 > 0? gap1 : -gap1;
+		for (l = k + 1; l < n; ++l) {
+			int j = K[l], gap2, q_span_pre, rs2, qs2, m;
+			if ((int32_t)a[as1 + j].y - qe1 > max_ext || (int32_t)a[as1 + j].x - re1 > max_ext) break;
+			gap2 = ((int32_t)a[as1 + j].y - (int32_t)a[as1 + j - 1].y) - (int32_t)(a[as1 + j].x - a[as1 + j - 1].x);
+			q_span_pre = (int)(a[as1 + j - 1].y >> 32 & 0xff);
+			rs2 = (int32_t)a[as1 + j - 1].x + q_span_pre;
+			qs2 = (int32_t)a[as1 + j - 1].y + q_span_pre;
+			m = rs2 - re1 < qs2 - qe1? rs2 - re1 : qs2 - qe1;
+			gap2 = gap2 > 0? gap2 : -gap2;
+			if (m > gap1 + gap2) break;
+			re1 = (int32_t)a[as1 + j].x;
+			qe1 = (int32_t)a[as1 + j].y;
+			gap1 = gap2;
+		}
+		if (l > k + 1) {
+			int j, end = K[l - 1];
+			for (j = K[k]; j < end; ++j) a[as1 + j].y |= SEED_IGNORE;
+			a[as1 + end].y |= SEED_FIXED;
+		}
+		k = l;
+	}
+	A.top = mark;
+	return 0;
+}
+
+// replace the high half of a[].x by the index of the minimizer on the query (reference: lchain.c:410-441)
+MG_HD inline int update_anchors(int32_t n_a, u128 *a, int32_t n, const int32_t *mini_pos)
+{
+	int32_t st = -1, j, k, L = 0, R = n - 1, x;
+	if (n_a <= 0) return 0;
+	x = (int32_t)a[0].y;
+	while (L <= R) {
+		int32_t m = (int32_t)(((uint64_t)L + (uint64_t)R) >> 1);
+		int32_t y = mini_pos[m];
+		if (y < x) L = m + 1;
+		else if (y > x) R = m - 1;
+		else { st = m; break; }
+	}
+	if (st < 0) return MGB_E_INTERNAL;
+	for (k = 0, j = st; j < n && k < n_a; ++j)
+		if ((int32_t)a[k].y == mini_pos[j])
+			a[k].x = (uint64_t)j << 32 | (a[k].x & 0xffffffffULL), ++k;
+	return k == n_a? 0 : MGB_E_INTERNAL;
+}
+
+} // namespace mgb

@@ -1,0 +1,153 @@
+// mgb_pipeline.cuh -- per-read stage functions glued to the global pools.
+//   stage_seed()  : K1 sketch + K2 lookup/expand + K3 seed sort      (reference: map-algo.c:366-368)
+//   stage_chain() : K4/K5 linear chaining, rescue, chain post-filters (reference: map-algo.c:377-449)
+//   stage_align() : K6-K8 graph chaining, bridging, base alignment    (mgb_galign.cuh)
+#pragma once
+#include "mgb_model.cuh"
+#include "mgb_seed.cuh"
+#include "mgb_lchain.cuh"
+
+namespace mgb {
+
+struct PipeCtx {
+	GraphDev g;
+	IndexDev ix;
+	MapOptDev opt;
+	BatchDev b;
+	ReadMeta *meta;        // [n_reads]
+	// global pools (element arrays + bump allocators)
+	Pool *pool_anchor;     u128 *anchor;
+	Pool *pool_minipos;    int32_t *minipos;
+	Pool *pool_lchain;     LChain *lchain;
+	Pool *pool_out;        char *out;
+	// work queue
+	unsigned int *next_read;
+};
+
+// K1-K3 for one read.  Writes sorted seeds to the anchor pool and the query positions of kept minimizers to the
+// mini_pos pool.
+MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A)
+{
+	ReadMeta &m = c.meta[rid];
+	const char *seq = c.b.seq + c.b.seq_off[rid];
+	int32_t qlen = c.b.seq_len[rid];
+	uint64_t mark = A.top;
+	m.status = 0, m.n_mz = 0, m.rep_len = 0, m.n_a = 0, m.a_off = 0, m.n_mp = 0, m.mp_off = 0, m.n_lc = 0, m.lc_off = 0;
+	m.n_seed0 = 0, m.n_u0 = 0;
+	{ // reference: map-algo.c:362-364
+		uint32_t h = c.b.name_hash[rid];
+		h ^= hash32((uint32_t)qlen) + hash32((uint32_t)c.opt.seed);
+		m.hash = hash32(h);
+	}
+	if (qlen <= 0 || (c.opt.max_qlen > 0 && qlen > c.opt.max_qlen)) { m.status = 1; return 0; } // unmapped by definition
+	AVec<u128> mv;
+	avec_init(mv);
+	MGB_TRY(sketch_seq(A, seq, qlen, c.ix.w, c.ix.k, 0, mv));
+	m.n_mz = (int32_t)mv.n;
+	SeedMatch *sm;
+	int n_m, n_mp, rep_len;
+	int64_t n_a;
+	int32_t *mp_tmp;
+	MGB_ALLOC(A, mp_tmp, int32_t, mv.n);
+	MGB_TRY(collect_matches(A, c.ix, c.opt.occ_max1, mv, &sm, &n_m, &n_a, &rep_len, mp_tmp, &n_mp));
+	m.rep_len = rep_len;
+	int64_t a_off = pool_alloc(c.pool_anchor, (uint64_t)n_a * sizeof(u128));
+	int64_t mp_off = pool_alloc(c.pool_minipos, (uint64_t)n_mp * sizeof(int32_t));
+	if (a_off < 0 || mp_off < 0) return MGB_E_POOL;
+	m.a_off = a_off / (int64_t)sizeof(u128), m.mp_off = mp_off / (int64_t)sizeof(int32_t);
+	m.n_a = (int32_t)n_a, m.n_mp = n_mp, m.n_seed0 = (int32_t)n_a;
+	u128 *a = c.anchor + m.a_off;
+	int32_t *mp = c.minipos + m.mp_off;
+	for (int i = 0; i < n_mp; ++i) mp[i] = mp_tmp[i];
+	expand_seeds(c.g, n_m, sm, a);
+	MGB_TRY(radix_sort_128x(A, a, n_a));
+	A.top = mark;
+	return 0;
+}
+
+// K4/K5 for one read: seeds -> linear chains.  Anchors are compacted in place; chains go to the lchain pool.
+MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A)
+{
+	ReadMeta &m = c.meta[rid];
+	const MapOptDev &o = c.opt;
+	if (m.status != 0) return 0;
+	uint64_t mark = A.top;
+	int32_t qlen = c.b.seq_len[rid];
+	u128 *a = c.anchor + m.a_off;
+	int64_t n_a = m.n_a;
+	int32_t n_lc = 0, n_a_new = 0;
+	uint64_t *u = 0;
+	const int is_splice = !!(o.flag & F_SPLICE), is_sr = !!(o.flag & F_SR);
+	int max_gap_qry, max_gap_ref;
+	// reference: map-algo.c:377-386
+	if (is_sr) max_gap_qry = qlen > o.max_gap? qlen : o.max_gap;
+	else max_gap_qry = o.max_gap;
+	if (o.max_gap_ref > 0) max_gap_ref = o.max_gap_ref;
+	else if (o.max_frag_len > 0) {
+		max_gap_ref = o.max_frag_len - qlen;
+		if (max_gap_ref < o.max_gap) max_gap_ref = o.max_gap;
+	} else max_gap_ref = o.max_gap;
+
+	if (n_a > 0) {
+		if (o.flag & F_RMQ)
+			MGB_TRY(chain_rmq(A, o.max_gap, o.max_gap_pre, o.bw, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
+							  o.chn_pen_gap, o.chn_pen_skip, n_a, a, &n_lc, &u, &n_a_new));
+		else
+			MGB_TRY(chain_dp(A, max_gap_ref, max_gap_qry, o.bw, o.max_lc_skip, o.max_lc_iter, o.min_lc_cnt, o.min_lc_score,
+							 o.chn_pen_gap, o.chn_pen_skip, is_splice, 1, n_a, a, &n_lc, &u, &n_a_new));
+	}
+	m.n_u0 = n_lc;
+	// long-join rescue (reference: map-algo.c:407-417)
+	if (o.bw_long > o.bw && (o.flag & (F_SPLICE | F_SR)) == 0 && n_lc > 1) {
+		int32_t st = (int32_t)a[0].y, en = (int32_t)a[(int32_t)u[0] - 1].y;
+		if (qlen - (en - st) > o.rmq_rescue_size || (float)(qlen - (en - st)) > (float)qlen * o.rmq_rescue_ratio) {
+			int64_t n2 = 0;
+			for (int32_t i = 0; i < n_lc; ++i) n2 += (int32_t)u[i];
+			A.top = mark;
+			MGB_TRY(radix_sort_128x(A, a, n2));
+			MGB_TRY(chain_rmq(A, o.max_gap, o.max_gap_pre, o.bw_long, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
+							  o.chn_pen_gap, o.chn_pen_skip, n2, a, &n_lc, &u, &n_a_new));
+		}
+	}
+	m.n_a = n_lc > 0? n_a_new : 0;
+	m.n_lc = 0;
+	if (n_lc > 0) {
+		LChain *lc;
+		MGB_ALLOC(A, lc, LChain, n_lc);
+		MGB_TRY(lchain_gen(A, n_lc, u, a, lc));
+		if (n_lc > 1) { // reference: map-algo.c:425-444
+			int32_t n_new = 0;
+			for (int32_t i = 0; i < n_lc; ++i) {
+				LChain *p = &lc[i];
+				int32_t cnt = p->cnt, off = p->off;
+				fix_bad_ends(a, o.lc_max_occ, o.lc_max_trim, &off, &cnt);
+				fix_bad_ends_alt(a, p->score, o.bw, 100, &off, &cnt);
+				MGB_TRY(filter_bad_seeds(A, off, cnt, a, 10, 40, o.max_gap >> 1, 10));
+				MGB_TRY(filter_bad_seeds_alt(A, off, cnt, a, 30, o.max_gap >> 1));
+				p->off = off, p->cnt = cnt;
+				if (cnt >= o.min_lc_cnt) {
+					int32_t q_span = (int32_t)(a[p->off].y >> 32 & 0xff);
+					p->rs = (int32_t)a[p->off].x + 1 - q_span;
+					p->qs = (int32_t)a[p->off].y + 1 - q_span;
+					p->re = (int32_t)a[p->off + p->cnt - 1].x + 1;
+					p->qe = (int32_t)a[p->off + p->cnt - 1].y + 1;
+					lc[n_new++] = *p;
+				}
+			}
+			n_lc = n_new;
+		}
+		const int32_t *mp = c.minipos + m.mp_off;
+		for (int32_t i = 0; i < n_lc; ++i)
+			MGB_TRY(update_anchors(lc[i].cnt, &a[lc[i].off], m.n_mp, mp));
+		int64_t lc_off = pool_alloc(c.pool_lchain, (uint64_t)n_lc * sizeof(LChain));
+		if (lc_off < 0) return MGB_E_POOL;
+		m.lc_off = lc_off / (int64_t)sizeof(LChain);
+		LChain *dst = c.lchain + m.lc_off;
+		for (int32_t i = 0; i < n_lc; ++i) dst[i] = lc[i];
+		m.n_lc = n_lc;
+	}
+	A.top = mark;
+	return 0;
+}
+
+} // namespace mgb

@@ -1,0 +1,130 @@
+// mgb_seed.cuh -- stage A: minimizer sketch, index lookup, seed expansion and seed sort for one read.
+#pragma once
+#include "mgb_model.cuh"
+
+namespace mgb {
+
+// Symmetric (w,k)-minimizers of one sequence (reference: sketch.c:56-109 mg_sketch()).
+//   out[i].x = hash<<8 | span ;  out[i].y = rid<<32 | lastPos<<1 | strand
+// Quirks kept on purpose: a symmetric k-mer does not advance the window slot, an
+// ambiguous base resets the run but still occupies a slot, ties pick the rightmost, equal-hash
+// duplicates inside one window are all reported, and the last minimum is flushed at the end.
+MG_HD inline int sketch_seq(Arena &A, const char *str, int len, int w, int k, uint32_t rid, AVec<u128> &out)
+{
+	const uint64_t shift1 = 2 * (k - 1), mask = (1ULL << 2 * k) - 1;
+	uint64_t kmer[2] = {0, 0};
+	int l = 0, buf_pos = 0, min_pos = 0, kmer_span = 0;
+	const u128 none = { ~0ULL, ~0ULL };
+	u128 mn = none, *buf;
+	if (!(len > 0 && w > 0 && w < 256 && k > 0 && k <= 28)) return MGB_E_INTERNAL;
+	MGB_TRY(avec_reserve(A, out, out.n + len / w + 16));
+	MGB_ALLOC(A, buf, u128, w);
+	for (int j = 0; j < w; ++j) buf[j] = none;
+	for (int i = 0; i < len; ++i) {
+		int c = nt4((uint8_t)str[i]);
+		u128 info = none;
+		if (c < 4) {
+			kmer_span = l + 1 < k? l + 1 : k;
+			kmer[0] = (kmer[0] << 2 | (uint64_t)c) & mask;
+			kmer[1] = (kmer[1] >> 2) | (3ULL ^ (uint64_t)c) << shift1;
+			if (kmer[0] == kmer[1]) continue; // strand unknown
+			int z = kmer[0] < kmer[1]? 0 : 1;
+			++l;
+			if (l >= k && kmer_span < 256) {
+				info.x = hash64_mask(kmer[z], mask) << 8 | (uint64_t)kmer_span;
+				info.y = (uint64_t)rid << 32 | (uint64_t)((uint32_t)i << 1) | (uint64_t)z;
+			}
+		} else l = 0, kmer_span = 0;
+		buf[buf_pos] = info;
+		if (l == w + k - 1 && mn.x != ~0ULL) { // first full window: report earlier copies of the minimum
+			for (int j = buf_pos + 1; j < w; ++j)
+				if (mn.x == buf[j].x && buf[j].y != mn.y) MGB_TRY(avec_push(A, out, buf[j]));
+			for (int j = 0; j < buf_pos; ++j)
+				if (mn.x == buf[j].x && buf[j].y != mn.y) MGB_TRY(avec_push(A, out, buf[j]));
+		}
+		if (info.x <= mn.x) { // new minimum (rightmost on ties)
+			if (l >= w + k && mn.x != ~0ULL) MGB_TRY(avec_push(A, out, mn));
+			mn = info, min_pos = buf_pos;
+		} else if (buf_pos == min_pos) { // the old minimum slides out
+			if (l >= w + k - 1 && mn.x != ~0ULL) MGB_TRY(avec_push(A, out, mn));
+			mn.x = ~0ULL;
+			for (int j = buf_pos + 1; j < w; ++j)
+				if (mn.x >= buf[j].x) mn = buf[j], min_pos = j;
+			for (int j = 0; j <= buf_pos; ++j)
+				if (mn.x >= buf[j].x) mn = buf[j], min_pos = j;
+			if (l >= w + k - 1 && mn.x != ~0ULL) {
+				for (int j = buf_pos + 1; j < w; ++j)
+					if (mn.x == buf[j].x && mn.y != buf[j].y) MGB_TRY(avec_push(A, out, buf[j]));
+				for (int j = 0; j <= buf_pos; ++j)
+					if (mn.x == buf[j].x && mn.y != buf[j].y) MGB_TRY(avec_push(A, out, buf[j]));
+			}
+		}
+		if (++buf_pos == w) buf_pos = 0;
+	}
+	if (mn.x != ~0ULL) MGB_TRY(avec_push(A, out, mn));
+	return 0;
+}
+
+struct SeedMatch {
+	uint32_t n, q_pos, q_span;
+	uint32_t seg_id, is_tandem;
+	const uint64_t *cr;
+};
+
+// Index probe per minimizer with the high-occurrence filter (reference: map-algo.c:58-91 collect_matches()).
+MG_HD inline int collect_matches(Arena &A, const IndexDev &ix, int max_occ, const AVec<u128> &mv, SeedMatch **m_, int *n_m_,
+								 int64_t *n_a, int *rep_len, int32_t *mini_pos, int *n_mini_pos)
+{
+	int rep_st = 0, rep_en = 0, n_m = 0, n_mp = 0;
+	SeedMatch *m;
+	MGB_ALLOC(A, m, SeedMatch, mv.n);
+	*rep_len = 0, *n_a = 0;
+	for (int64_t i = 0; i < mv.n; ++i) {
+		const u128 *p = &mv.a[i];
+		uint32_t q_pos = (uint32_t)p->y, q_span = (uint32_t)(p->x & 0xff);
+		int t;
+		const uint64_t *cr = idx_get(ix, p->x >> 8, &t);
+		if (t >= max_occ) {
+			int en = (int)(q_pos >> 1) + 1, st = en - (int)q_span;
+			if (st > rep_en) {
+				*rep_len += rep_en - rep_st;
+				rep_st = st, rep_en = en;
+			} else rep_en = en;
+		} else {
+			SeedMatch *q = &m[n_m++];
+			q->q_pos = q_pos, q->q_span = q_span, q->cr = cr, q->n = (uint32_t)t, q->seg_id = (uint32_t)(p->y >> 32);
+			q->is_tandem = 0;
+			if (i > 0 && p->x >> 8 == mv.a[i - 1].x >> 8) q->is_tandem = 1;
+			if (i < mv.n - 1 && p->x >> 8 == mv.a[i + 1].x >> 8) q->is_tandem = 1;
+			*n_a += q->n;
+			mini_pos[n_mp++] = (int32_t)(q_pos >> 1);
+		}
+	}
+	*rep_len += rep_en - rep_st;
+	*m_ = m, *n_m_ = n_m, *n_mini_pos = n_mp;
+	return 0;
+}
+
+// Expand matches to anchors (reference: map-algo.c:152-192 collect_seed_hits(), without the NO_DIAG branch):
+//   a.x = seg<<33 | rev<<32 | tpos ;  a.y = occ<<56 | segid<<48 | tandem | q_span<<32 | qpos
+MG_HD inline void expand_seeds(const GraphDev &g, int n_m, const SeedMatch *m, u128 *a)
+{
+	int64_t n = 0;
+	for (int i = 0; i < n_m; ++i) {
+		const SeedMatch *q = &m[i];
+		const uint64_t *r = q->cr;
+		for (uint32_t k = 0; k < q->n; ++k) {
+			uint64_t rk = r[k];
+			int32_t rpos = (int32_t)((uint32_t)rk >> 1);
+			u128 *p = &a[n++];
+			if ((rk & 1) == (q->q_pos & 1)) p->x = rk >> 32 << 33 | (uint64_t)(uint32_t)rpos;
+			else p->x = rk >> 32 << 33 | 1ULL << 32 | (uint64_t)(uint32_t)(g.seg_len[rk >> 32] - (rpos + 1 - (int32_t)q->q_span) - 1);
+			p->y = (uint64_t)q->q_span << 32 | (uint64_t)(q->q_pos >> 1);
+			p->y |= (uint64_t)q->seg_id << SEED_SEG_SHIFT;
+			if (q->is_tandem) p->y |= SEED_TANDEM;
+			p->y |= (uint64_t)(q->n < 255? q->n : 255) << SEED_OCC_SHIFT;
+		}
+	}
+}
+
+} // namespace mgb

@@ -1,0 +1,333 @@
+// mgb_shortk.cuh -- bounded k-shortest walks from one vertex to a set of destination vertices.
+// (reference: shortk.c:41-242 mg_shortest_k).  Best-first search over the flattened arc CSR; every vertex keeps at
+// most MAX_SHORT_K arrivals.  The frontier key is dist<<32|id with `id` a global insertion counter, so keys are
+// unique and any exact priority queue pops in the reference's order: the AVL tree becomes an indexed
+// binary heap, the visited-vertex hash becomes an open-addressing table in the worker arena.
+#pragma once
+#include "mgb_model.cuh"
+
+namespace mgb {
+
+// reference: mgpriv.h:40-52 mg_path_dst_t
+struct PathDst {
+	uint32_t v;
+	int32_t target_dist;
+	uint32_t target_hash;
+	int32_t meta, check_hash, inner;
+	int32_t qlen;
+	int32_t n_path, is_0;
+	int32_t path_end;
+	int32_t dist;
+	uint32_t hash;
+};
+
+// reference: mgpriv.h:54-57 mg_pathv_t
+struct PathV {
+	uint32_t v, d;
+	int32_t pre;
+};
+
+struct SpNode {
+	uint64_t di;       // dist<<32 | unique id (later: dist<<32 | position in out[])
+	uint32_t v;
+	int32_t pre;
+	uint32_t hash;
+	int32_t is_0;
+	int32_t heap_pos;  // position in the frontier heap, -1 when not in it
+};
+
+struct SpTopK {
+	uint32_t v;
+	int32_t k;
+	int32_t p[MAX_SHORT_K]; // max-heap of node indices by di
+};
+
+struct SpState {
+	AVec<SpNode> nd;
+	AVec<int32_t> heap;     // frontier: min-heap of node indices by di
+	AVec<SpTopK> topk;
+	int32_t *htab;          // vertex -> index into topk (open addressing), -1 empty
+	int32_t htab_bits;
+};
+
+MG_HD inline void sp_heap_swap(SpState &S, int32_t i, int32_t j)
+{
+	int32_t a = S.heap.a[i], b = S.heap.a[j];
+	S.heap.a[i] = b, S.heap.a[j] = a;
+	S.nd.a[b].heap_pos = i, S.nd.a[a].heap_pos = j;
+}
+MG_HD inline void sp_heap_up(SpState &S, int32_t i)
+{
+	while (i > 0) {
+		int32_t par = (i - 1) >> 1;
+		if (S.nd.a[S.heap.a[par]].di <= S.nd.a[S.heap.a[i]].di) break;
+		sp_heap_swap(S, par, i);
+		i = par;
+	}
+}
+MG_HD inline void sp_heap_down(SpState &S, int32_t i)
+{
+	int32_t n = (int32_t)S.heap.n;
+	for (;;) {
+		int32_t l = 2 * i + 1, r = l + 1, m = i;
+		if (l < n && S.nd.a[S.heap.a[l]].di < S.nd.a[S.heap.a[m]].di) m = l;
+		if (r < n && S.nd.a[S.heap.a[r]].di < S.nd.a[S.heap.a[m]].di) m = r;
+		if (m == i) break;
+		sp_heap_swap(S, m, i);
+		i = m;
+	}
+}
+MG_HD inline int sp_heap_push(Arena &A, SpState &S, int32_t node)
+{
+	MGB_TRY(avec_push(A, S.heap, node));
+	S.nd.a[node].heap_pos = (int32_t)S.heap.n - 1;
+	sp_heap_up(S, (int32_t)S.heap.n - 1);
+	return 0;
+}
+MG_HD inline void sp_heap_remove_at(SpState &S, int32_t pos)
+{
+	int32_t last = (int32_t)S.heap.n - 1;
+	int32_t node = S.heap.a[pos];
+	if (pos != last) {
+		int32_t moved = S.heap.a[last];
+		sp_heap_swap(S, pos, last);
+		--S.heap.n;
+		sp_heap_up(S, pos);
+		sp_heap_down(S, S.nd.a[moved].heap_pos);
+	} else --S.heap.n;
+	S.nd.a[node].heap_pos = -1;
+}
+
+MG_HD inline int sp_htab_get(Arena &A, SpState &S, uint32_t v, int *absent, int32_t *idx_)
+{
+	for (;;) {
+		uint32_t mask = (1u << S.htab_bits) - 1, h = hash32(v) & mask;
+		while (S.htab[h] >= 0 && S.topk.a[S.htab[h]].v != v) h = (h + 1) & mask;
+		if (S.htab[h] >= 0) { *absent = 0, *idx_ = S.htab[h]; return 0; }
+		if ((uint64_t)(S.topk.n + 1) * 2 > (1ULL << S.htab_bits)) { // grow and rehash
+			int32_t nb = S.htab_bits + 1, *nt;
+			MGB_ALLOC(A, nt, int32_t, 1LL << nb);
+			uint32_t nmask = (1u << nb) - 1;
+			for (int64_t i = 0; i < (1LL << nb); ++i) nt[i] = -1;
+			for (int64_t i = 0; i < S.topk.n; ++i) {
+				uint32_t g = hash32(S.topk.a[i].v) & nmask;
+				while (nt[g] >= 0) g = (g + 1) & nmask;
+				nt[g] = (int32_t)i;
+			}
+			S.htab = nt, S.htab_bits = nb;
+			continue;
+		}
+		SpTopK t;
+		t.v = v, t.k = 0;
+		MGB_TRY(avec_push(A, S.topk, t));
+		S.htab[h] = (int32_t)S.topk.n - 1;
+		*absent = 1, *idx_ = S.htab[h];
+		return 0;
+	}
+}
+
+// per-vertex top-k max-heap on di (reference: ksort.h:42-65 ks_heapup/ks_heapdown with sp_node_lt)
+MG_HD inline void sp_topk_up(const SpState &S, int32_t n, int32_t *l)
+{
+	int32_t k = n - 1, tmp = l[k];
+	while (k) {
+		int32_t i = (k - 1) >> 1;
+		if (S.nd.a[tmp].di < S.nd.a[l[i]].di) break;
+		l[k] = l[i], k = i;
+	}
+	l[k] = tmp;
+}
+MG_HD inline void sp_topk_down(const SpState &S, int32_t i, int32_t n, int32_t *l)
+{
+	int32_t k = i, tmp = l[i];
+	while ((k = (k << 1) + 1) < n) {
+		if (k != n - 1 && S.nd.a[l[k]].di < S.nd.a[l[k+1]].di) ++k;
+		if (S.nd.a[l[k]].di < S.nd.a[tmp].di) break;
+		l[i] = l[k], i = k;
+	}
+	l[i] = tmp;
+}
+
+// Returns 0 or an error code.  If pathv_/n_pathv_ are non-null the compacted backtrack array is produced in the
+// arena (above the caller's mark); dst[].path_end then indexes it.
+MG_HD inline int shortest_k(Arena &A, const GraphDev &g, uint32_t src, int32_t n_dst, PathDst *dst, int32_t max_dist, int32_t max_k,
+							PathV **pathv_, int32_t *n_pathv_)
+{
+	if (n_pathv_) *n_pathv_ = 0;
+	if (pathv_) *pathv_ = 0;
+	if (n_dst <= 0) return 0;
+	for (int32_t i = 0; i < n_dst; ++i) {
+		PathDst *t = &dst[i];
+		if (t->inner) t->dist = 0, t->n_path = 1, t->path_end = -1;
+		else t->dist = -1, t->n_path = 0, t->path_end = -1;
+	}
+	if (max_k > MAX_SHORT_K) max_k = MAX_SHORT_K;
+	// the result (if requested) must sit below the scratch: reserve it lazily at the end by copying down
+	uint64_t mark = A.top;
+	int8_t *dst_done;
+	uint64_t *dst_group;
+	MGB_ALLOC(A, dst_done, int8_t, n_dst);
+	MGB_ALLOC(A, dst_group, uint64_t, n_dst);
+	for (int32_t i = 0; i < n_dst; ++i) dst_done[i] = 0, dst_group[i] = (uint64_t)dst[i].v << 32 | (uint64_t)i;
+	MGB_TRY(radix_sort_64(A, dst_group, n_dst));
+
+	SpState S;
+	avec_init(S.nd), avec_init(S.heap), avec_init(S.topk);
+	S.htab_bits = 5;
+	MGB_ALLOC(A, S.htab, int32_t, 1 << S.htab_bits);
+	for (int i = 0; i < (1 << S.htab_bits); ++i) S.htab[i] = -1;
+	AVec<int32_t> out;
+	avec_init(out);
+
+	uint32_t id = 0;
+	{
+		SpNode p;
+		int absent; int32_t qi;
+		p.v = src, p.di = (uint64_t)0 << 32 | id++, p.pre = -1, p.is_0 = 1, p.hash = hash32(src), p.heap_pos = -1;
+		MGB_TRY(avec_push(A, S.nd, p));
+		MGB_TRY(sp_heap_push(A, S, 0));
+		MGB_TRY(sp_htab_get(A, S, src, &absent, &qi));
+		S.topk.a[qi].k = 1, S.topk.a[qi].p[0] = 0;
+	}
+	int32_t n_done = 0;
+	while (S.heap.n > 0) {
+		int32_t ri = S.heap.a[0];
+		sp_heap_remove_at(S, 0);
+		int32_t n_out = (int32_t)out.n;
+		S.nd.a[ri].di = S.nd.a[ri].di >> 32 << 32 | (uint64_t)(uint32_t)n_out;
+		MGB_TRY(avec_push(A, out, ri));
+		n_out = (int32_t)out.n;
+		const uint32_t rv = S.nd.a[ri].v, rhash = S.nd.a[ri].hash;
+		const int32_t rdist = (int32_t)(S.nd.a[ri].di >> 32), ris0 = S.nd.a[ri].is_0;
+		{ // is rv a destination?  (binary search the grouped list)
+			int32_t lo = 0, hi = n_dst;
+			while (lo < hi) { int32_t mid = (lo + hi) >> 1; if ((uint32_t)(dst_group[mid] >> 32) < rv) lo = mid + 1; else hi = mid; }
+			if (lo < n_dst && (uint32_t)(dst_group[lo] >> 32) == rv) {
+				int32_t off = lo, cnt = 0;
+				while (off + cnt < n_dst && (uint32_t)(dst_group[off + cnt] >> 32) == rv) ++cnt;
+				for (int32_t j = 0; j < cnt; ++j) {
+					PathDst *t = &dst[(int32_t)dst_group[off + j]];
+					int32_t done = 0;
+					if (t->inner) {
+						done = 1;
+					} else {
+						int32_t copy = 0;
+						if (t->n_path == 0) {
+							copy = 1;
+						} else if (t->target_dist >= 0) {
+							if (rdist == t->target_dist && t->check_hash && rhash == t->target_hash) {
+								copy = 1, done = 1;
+							} else {
+								int32_t d0 = t->dist, d1 = rdist;
+								d0 = d0 > t->target_dist? d0 - t->target_dist : t->target_dist - d0;
+								d1 = d1 > t->target_dist? d1 - t->target_dist : t->target_dist - d1;
+								if (d1 < d0) copy = 1;
+							}
+						}
+						if (copy) {
+							t->path_end = n_out - 1, t->dist = rdist, t->hash = rhash, t->is_0 = ris0;
+							if (t->target_dist >= 0) {
+								if (rdist == t->target_dist && t->check_hash && rhash == t->target_hash) done = 1;
+								else if (rdist > t->target_dist + 1000) done = 1; // MG_SHORT_K_EXT
+							}
+						}
+						++t->n_path;
+						if (t->n_path >= max_k) done = 1;
+					}
+					if (dst_done[off + j] == 0 && done) dst_done[off + j] = 1, ++n_done;
+				}
+				if (n_done == n_dst) break;
+			}
+		}
+		int32_t nv = g_arc_n(g, rv);
+		const DevArc *av = g_arc_a(g, rv);
+		for (int32_t i = 0; i < nv; ++i) {
+			const DevArc *ai = &av[i];
+			int32_t d = (int32_t)((uint32_t)rdist + ai->lv);
+			if (d > max_dist) continue;
+			int absent; int32_t qi;
+			MGB_TRY(sp_htab_get(A, S, ai->w, &absent, &qi));
+			SpTopK *q = &S.topk.a[qi];
+			if (q->k < max_k) {
+				SpNode p;
+				p.v = ai->w, p.di = (uint64_t)(uint32_t)d << 32 | id++, p.pre = n_out - 1;
+				p.hash = rhash + hash32(ai->w);
+				p.is_0 = ris0;
+				if (ai->rank > 0) p.is_0 = 0;
+				p.heap_pos = -1;
+				MGB_TRY(avec_push(A, S.nd, p));
+				int32_t pi = (int32_t)S.nd.n - 1;
+				MGB_TRY(sp_heap_push(A, S, pi));
+				q = &S.topk.a[qi];
+				q->p[q->k++] = pi;
+				sp_topk_up(S, q->k, q->p);
+			} else if ((int64_t)(S.nd.a[q->p[0]].di >> 32) > (int64_t)d) {
+				int32_t pi = q->p[0];
+				if (S.nd.a[pi].heap_pos < 0) { A.top = mark; return MGB_E_INTERNAL; } // "logical bug" branch of the reference
+				sp_heap_remove_at(S, S.nd.a[pi].heap_pos);
+				SpNode *p = &S.nd.a[pi];
+				p->di = (uint64_t)(uint32_t)d << 32 | id++;
+				p->pre = n_out - 1;
+				p->hash = rhash + hash32(ai->w);
+				p->is_0 = ris0;
+				if (ai->rank > 0) p->is_0 = 0;
+				MGB_TRY(sp_heap_push(A, S, pi));
+				sp_topk_down(S, 0, q->k, q->p);
+			}
+		}
+	}
+
+	int32_t n_found = 0;
+	for (int32_t i = 0; i < n_dst; ++i) if (dst[i].n_path > 0) ++n_found;
+	PathV *ret = 0;
+	int32_t n_ret = 0;
+	if (n_found > 0 && n_pathv_) { // backtrack array (reference: shortk.c:198-232)
+		int32_t n_out = (int32_t)out.n, n = 0, *trans;
+		MGB_ALLOC(A, trans, int32_t, n_out);
+		for (int32_t i = 0; i < n_out; ++i) trans[i] = 0;
+		for (int32_t i = 0; i < n_dst; ++i) {
+			PathDst *t = &dst[i];
+			if (t->n_path > 0 && t->target_dist >= 0 && t->path_end >= 0)
+				trans[(int32_t)S.nd.a[out.a[t->path_end]].di] = 1;
+		}
+		for (int32_t i = 0; i < n_out; ++i) {
+			uint32_t ov = S.nd.a[out.a[i]].v;
+			int32_t lo = 0, hi = n_dst;
+			while (lo < hi) { int32_t mid = (lo + hi) >> 1; if ((uint32_t)(dst_group[mid] >> 32) < ov) lo = mid + 1; else hi = mid; }
+			if (lo < n_dst && (uint32_t)(dst_group[lo] >> 32) == ov) {
+				int32_t off = lo, cnt = 0;
+				while (off + cnt < n_dst && (uint32_t)(dst_group[off + cnt] >> 32) == ov) ++cnt;
+				for (int32_t j = off; j < off + cnt; ++j) // NB: the reference indexes dst[] by group position here
+					if (dst[j].target_dist < 0) trans[i] = 1;
+			}
+		}
+		for (int32_t i = n_out - 1; i >= 0; --i)
+			if (trans[i] && S.nd.a[out.a[i]].pre >= 0) trans[S.nd.a[out.a[i]].pre] = 1;
+		for (int32_t i = 0; i < n_out; ++i) {
+			if (trans[i]) trans[i] = n++;
+			else trans[i] = -1;
+		}
+		n_ret = n;
+		PathV *tmp;
+		MGB_ALLOC(A, tmp, PathV, n);
+		for (int32_t i = 0; i < n_out; ++i) {
+			if (trans[i] < 0) continue;
+			PathV *p = &tmp[trans[i]];
+			const SpNode &o = S.nd.a[out.a[i]];
+			p->v = o.v, p->d = (uint32_t)(o.di >> 32);
+			p->pre = o.pre < 0? o.pre : trans[o.pre];
+		}
+		for (int32_t i = 0; i < n_dst; ++i)
+			if (dst[i].path_end >= 0) dst[i].path_end = trans[dst[i].path_end];
+		// move the result down to the caller's mark so that all scratch can be released
+		ret = (PathV*)(A.base + mark);
+		for (int32_t i = 0; i < n; ++i) { PathV x = tmp[i]; ret[i] = x; } // forward copy is safe: destination is below the source
+		A.top = mark + (((uint64_t)n * sizeof(PathV) + 15) & ~(uint64_t)15);
+		if (A.top > A.peak) A.peak = A.top;
+	} else A.top = mark;
+	if (pathv_) *pathv_ = ret;
+	if (n_pathv_) *n_pathv_ = n_ret;
+	return 0;
+}
+
+} // namespace mgb
