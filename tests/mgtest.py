@@ -165,3 +165,65 @@ def map_with_engine(lib, gfa_path, names, seqs, preset="lr", cigar=True, gfa_loa
     lib.mgb_get_stats(gi, C.byref(st))
     lib.mg_idx_destroy(gi)
     return res, mo, st
+
+
+def gaf_with_engine(lib, gfa_path, names, seqs, preset="lr", cigar=True, flag_extra=0):
+    """Map through mg_index + mg_map_batch and format with mgb_write_gaf: the text `minigraph -cx preset` prints."""
+    g = lib.mgb_gfa_read(gfa_path.encode())
+    assert g, "gfa read failed"
+    io, mo = options.opt_set(preset, cigar)
+    mo.flag |= flag_extra
+    gi = lib.mg_index(g, C.byref(io), 1, C.byref(mo))
+    assert gi, lib.mgb_last_error()
+    n = len(seqs)
+    qlens = (C.c_int * n)(*[len(s) for s in seqs])
+    cseqs = (C.c_char_p * n)(*seqs)
+    cnames = (C.c_char_p * n)(*names)
+    gcs = (C.POINTER(capi.mg_gchains_t) * n)()
+    rc = lib.mg_map_batch(gi, n, qlens, cseqs, cnames, gcs, C.byref(mo))
+    assert rc == 0, (rc, lib.mgb_last_error())
+    buf, ln, cap = C.c_void_p(0), C.c_size_t(0), C.c_size_t(0)
+    for i in range(n):
+        lib.mgb_write_gaf(C.byref(buf), C.byref(ln), C.byref(cap), g, gcs[i], len(seqs[i]), names[i], mo.flag)
+        lib.mg_gchain_free(gcs[i])
+    text = C.string_at(buf, ln.value) if buf else b""
+    C.CDLL(None).free(buf)
+    st = capi.mgb_stats_t()
+    lib.mgb_get_stats(gi, C.byref(st))
+    lib.mg_idx_destroy(gi)
+    lib.mgb_gfa_destroy(g)
+    return text, st
+
+
+def gaf_with_ref_binary(gfa_path, fasta_path, preset="lr", threads=1, extra=()):
+    """stdout of the unmodified reference CLI (oracle/_ref/minigraph)."""
+    cmd = [REF_BIN, "-cx", preset, "-t", str(threads)] + list(extra) + [gfa_path, fasta_path]
+    return subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
+
+
+def write_fasta(fn, names, seqs):
+    with open(fn, "wb") as f:
+        for n, s in zip(names, seqs):
+            f.write(b">" + n + b"\n" + s + b"\n")
+
+
+def sim_reads(hap_fa, out_fa, n, length, err="ont", seed=11, circular=False):
+    cmd = [MGSIM, "reads", "-i", hap_fa, "-n", str(n), "-l", str(length), "-e", err, "-s", str(seed), "-o", out_fa]
+    if circular:
+        cmd.append("-c")
+    subprocess.run(cmd, check=True, stderr=subprocess.DEVNULL)
+
+
+def sim_graph(prefix, length, n_hap, seed=7):
+    subprocess.run([MGSIM, "graph", "-l", str(length), "-n", str(n_hap), "-s", str(seed), "-o", prefix], check=True,
+                   stderr=subprocess.DEVNULL)
+
+
+MT_WALKS = [">MTh0>MTh4001>MTh4502>MTh9505>MTh13014>MTh13516", ">MTh0<MTo3426>MTh4502>MTo8961>MTh9505>MTh13516"]
+
+
+def sim_mt_haps(out_fa):
+    cmd = [MGSIM, "walk", "-g", os.path.join(FIX, "MT.gfa"), "-o", out_fa]
+    for w in MT_WALKS:
+        cmd += ["-w", w]
+    subprocess.run(cmd, check=True)
