@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py -- mapped Gbp/s of the seed-chain-align hot path (BASELINE.json metric) on synthetic long reads.
+
+One "step" = one pass of the whole hot path (K1 sketch .. K8 base alignment + ds) over one batch of reads.
+Workload at N=1 (BASELINE.json configs[1]): test/MT.gfa <- 10 000 x 10 kb ONT-error reads, -cx lr -c.
+With N>1 every rank maps its own 10 000-read batch (seed + rank) against a replicated index: weak scaling, no
+data-path collective; the only collective is the all-gather of per-rank GAF byte counts that fixes output offsets.
+
+  value   = bases / device time of the three stage kernels (CUDA events inside libmgb200, inputs resident in HBM)
+  e2e     = bases / wall time of mg_map_batch() from HOST buffers (H2D, kernels, D2H, result assembly) + GAF formatting
+  roofline= chaining kernel (K4/K5, `k_stage<1>`): algorithmic bytes (16 B/seed in + 16 B/anchor out + 8 B/chain) / its
+            event time, against MEASURED_PEAKS.json hbm_gbs
+  --impl reference : the unmodified reference CLI (oracle/_ref/minigraph -t <all cores>) on a bounded sample
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+FIX = os.path.join(REPO, "tests", "golden", "fixtures")
+MGSIM = os.path.join(REPO, "tools", "mgsim")
+REF_BIN = os.path.join(REPO, "oracle", "_ref", "minigraph")
+MT_WALKS = [">MTh0>MTh4001>MTh4502>MTh9505>MTh13014>MTh13516", ">MTh0<MTo3426>MTh4502>MTo8961>MTh9505>MTh13516"]
+
+N_READS, READ_LEN = 10000, 10000
+CPU_SAMPLE_READS = 3000
+
+
+def make_workload(tmp, rank, n_reads=N_READS):
+    hap = os.path.join(tmp, "mt.hap.fa")
+    reads = os.path.join(tmp, "mt.reads.%d.fa" % rank)
+    cmd = [MGSIM, "walk", "-g", os.path.join(FIX, "MT.gfa"), "-o", hap]
+    for w in MT_WALKS:
+        cmd += ["-w", w]
+    subprocess.run(cmd, check=True)
+    subprocess.run([MGSIM, "reads", "-i", hap, "-n", str(n_reads), "-l", str(READ_LEN), "-e", "ont", "-s", str(11 + rank), "-o", reads],
+                   check=True, stderr=subprocess.DEVNULL)
+    return os.path.join(FIX, "MT.gfa"), reads
+
+
+def read_fasta(fn):
+    names, seqs = [], []
+    with open(fn, "rb") as f:
+        data = f.read().split(b"\n")
+    for i in range(0, len(data) - 1, 2):
+        names.append(data[i][1:])
+        seqs.append(data[i + 1])
+    return names, seqs
+
+
+def run_reference_cli(gfa, fasta, threads):
+    """Mapping-phase seconds of the reference (last 'mapped' stamp minus the 'indexed' stamp)."""
+    t0 = time.perf_counter()
+    p = subprocess.run([REF_BIN, "-cx", "lr", "-t", str(threads), gfa, fasta], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, check=True)
+    wall = time.perf_counter() - t0
+    log = p.stderr.decode()
+    t_idx = re.findall(r"\[M::mg_index::([0-9.]+)\*", log)
+    t_map = re.findall(r"\[M::worker_pipeline::([0-9.]+)\*[0-9.]+\] mapped", log)
+    if t_idx and t_map:
+        return float(t_map[-1]) - float(t_idx[-1]), wall
+    return wall, wall
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=5).stdout.decode().strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="mgb200")
+    ap.add_argument("--reads", type=int, default=N_READS)
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    tmp = tempfile.mkdtemp(prefix="mgb_bench_")
+    ncores = os.cpu_count() or 1
+    workload = "test/MT.gfa <- %d x %d bp synthetic ONT-error reads (4%% sub, 3%% del, 3%% ins; mgsim seed 11+rank), -cx lr -c" % (a.reads, READ_LEN)
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        gfa, fa = make_workload(tmp, 0, CPU_SAMPLE_READS)
+        names, seqs = read_fasta(fa)
+        bases = sum(len(s) for s in seqs)
+        for _ in range(min(a.warmup, 1)):
+            run_reference_cli(gfa, fa, ncores)
+        ts = [run_reference_cli(gfa, fa, ncores)[0] for _ in range(a.steps)]
+        t = sum(ts) / len(ts)
+        v = bases / t / 1e9
+        sample = "%d of the %d reads (%.1f Mbp), mapping phase of `minigraph -cx lr -t %d`" % (CPU_SAMPLE_READS, a.reads, bases / 1e6, ncores)
+        print(json.dumps({
+            "impl": "reference", "metric": "mapped Gbp/s (-cx lr)", "value": v, "unit": "Gbp/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/u8 (fp32 chain penalties)",
+            "data": "synthetic", "config": {"workload": workload, "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "Gbp/s", "cores": ncores, "kind": "reference", "sample": sample},
+            "e2e": {"value": v, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from minigraph_b200 import capi, options
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = capi.load_product()
+    lib.mgb_set_param(b"device", local_rank)
+    gfa, fa = make_workload(tmp, rank, a.reads)
+    names, seqs = read_fasta(fa)
+    n = len(seqs)
+    bases = sum(len(s) for s in seqs)
+    g = lib.mgb_gfa_read(gfa.encode())
+    io, mo = options.opt_set("lr", cigar=True)
+    gi = lib.mg_index(g, C.byref(io), 1, C.byref(mo))
+    assert gi, lib.mgb_last_error()
+    qlens = (C.c_int * n)(*[len(s) for s in seqs])
+    cseqs = (C.c_char_p * n)(*seqs)
+    cnames = (C.c_char_p * n)(*names)
+    gcs = (C.POINTER(capi.mg_gchains_t) * n)()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    st = capi.mgb_stats_t()
+    gaf_bytes = [0]
+
+    def step():
+        flush.fill_(1)  # evict L2 (126 MB) between steps
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rc = lib.mg_map_batch(gi, n, qlens, cseqs, cnames, gcs, C.byref(mo))
+        assert rc == 0, lib.mgb_last_error()
+        buf, ln, cap = C.c_void_p(0), C.c_size_t(0), C.c_size_t(0)
+        for i in range(n):
+            lib.mgb_write_gaf(C.byref(buf), C.byref(ln), C.byref(cap), g, gcs[i], qlens[i], cnames[i], mo.flag)
+        t1 = time.perf_counter()
+        gaf_bytes[0] = ln.value
+        C.CDLL(None).free(buf)
+        for i in range(n):
+            lib.mg_gchain_free(gcs[i])
+        lib.mgb_get_stats(gi, C.byref(st))
+        return t1 - t0, (st.t_seed_ms, st.t_chain_ms, st.t_align_ms), st.t_h2d_ms, st.t_d2h_ms
+
+    for _ in range(a.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    walls, kern, stage = [], [], [0.0, 0.0, 0.0]
+    launches = 0
+    for _ in range(a.steps):
+        w, ks, _, _ = step()
+        walls.append(w)
+        kern.append(sum(ks))
+        for i in range(3):
+            stage[i] += ks[i]
+        launches += st.n_launches
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    t_kern = sum(kern) / 1e3
+    t_wall = sum(walls)
+    # the one collective of the path: per-rank GAF byte counts -> output offsets
+    offsets = [0]
+    if world > 1:
+        mine = torch.tensor([gaf_bytes[0]], dtype=torch.int64, device="cuda")
+        allc = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allc, mine)
+        offsets = [0]
+        for c in allc[:-1]:
+            offsets.append(offsets[-1] + int(c.item()))
+        tm = torch.tensor([t_kern, t_wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        t_kern, t_wall = float(tm[0].item()), float(tm[1].item())
+    total_bases = bases * world
+    value = total_bases * a.steps / t_kern / 1e9
+    e2e = total_bases * a.steps / t_wall / 1e9
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = hbm_peak()
+    chain_bytes = 16.0 * st.n_seeds + 16.0 * st.n_anchors_out + 8.0 * st.n_chains_out
+    t_chain_avg = stage[1] / a.steps / 1e3
+    achieved = chain_bytes / t_chain_avg / 1e9 if t_chain_avg > 0 else 0.0
+    # CPU baseline: the unmodified reference on a bounded sample of the same reads, all host cores
+    cpu = None
+    if os.path.exists(REF_BIN):
+        sfa = os.path.join(tmp, "cpu_sample.fa")
+        with open(sfa, "wb") as f:
+            for nm, s in zip(names[:CPU_SAMPLE_READS], seqs[:CPU_SAMPLE_READS]):
+                f.write(b">" + nm + b"\n" + s + b"\n")
+        sb = sum(len(s) for s in seqs[:CPU_SAMPLE_READS])
+        run_reference_cli(gfa, sfa, ncores)
+        tcpu = min(run_reference_cli(gfa, sfa, ncores)[0] for _ in range(2))
+        cpu = {"value": sb / tcpu / 1e9, "unit": "Gbp/s", "cores": ncores, "kind": "reference",
+               "sample": "first %d reads of the batch (%.1f Mbp), mapping phase of `oracle/_ref/minigraph -cx lr -t %d`" % (min(CPU_SAMPLE_READS, n), sb / 1e6, ncores)}
+    out = {
+        "metric": "mapped Gbp/s (-cx lr)", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": t_kern / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int64/u8 (fp32 chain penalties, bit-exact)", "data": "synthetic",
+        "config": {"workload": workload, "reads_per_gpu": n, "bases_per_gpu": bases, "l2": "512 MiB flush buffer written between steps",
+                   "parallelism": "reads sharded one batch per GPU, index replicated; all-gather of GAF byte counts only",
+                   "gaf_offsets": offsets},
+        "stage_ms_per_step": {"seed(K1-K3)": stage[0] / a.steps, "chain(K4-K5)": stage[1] / a.steps, "align(K6-K8)": stage[2] / a.steps},
+        "e2e": {"value": e2e, "unit": "Gbp/s", "ms_per_step": t_wall / a.steps * 1e3,
+                "h2d_bytes_per_step": int(bases + 16 * n + 16 * n), "d2h_bytes_per_step": int(st.out_bytes + 48 * n + 96 * n),
+                "includes": "H2D of reads, 3 stage kernels, D2H of result blobs, mg_gchains_t assembly, GAF text (%d bytes/step)" % gaf_bytes[0]},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "k_stage<1> (linear chaining: mg_lchain_dp/rmq + backtrack + compaction)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "bytes_model": "16 B x %d seeds in + 16 B x %d anchors out + 8 B x %d chains" % (st.n_seeds, st.n_anchors_out, st.n_chains_out)},
+        "cpu_baseline": cpu,
+        "clocks": sampler.summary(),
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
