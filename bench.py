@@ -6,7 +6,7 @@ Workload at N=1 (BASELINE.json configs[1]): test/MT.gfa <- 10 000 x 10 kb ONT-er
 With N>1 every rank maps its own 10 000-read batch (seed + rank) against a replicated index: weak scaling, no
 data-path collective; the only collective is the all-gather of per-rank GAF byte counts that fixes output offsets.
 
-  value   = bases / device time of the three stage kernels (CUDA events inside libmgb200, inputs resident in HBM)
+  value   = bases / device time of the five stage kernels (CUDA events inside libmgb200, inputs resident in HBM)
   e2e     = bases / wall time of mg_map_batch() from HOST buffers (H2D, kernels, D2H, result assembly) + GAF formatting
   roofline= chaining kernel (K4/K5, `k_stage<1>`): algorithmic bytes (16 B/seed in + 16 B/anchor out + 8 B/chain) / its
             event time, against MEASURED_PEAKS.json hbm_gbs
@@ -182,7 +182,7 @@ def main():
         for i in range(n):
             lib.mg_gchain_free(gcs[i])
         lib.mgb_get_stats(gi, C.byref(st))
-        return t1 - t0, (st.t_seed_ms, st.t_chain_ms, st.t_align_ms), st.t_h2d_ms, st.t_d2h_ms
+        return t1 - t0, (st.t_seed_ms, st.t_chain_ms, st.t_align_ms, st.t_wfa_ms, st.t_finish_ms), st.t_h2d_ms, st.t_d2h_ms
 
     for _ in range(a.warmup):
         step()
@@ -191,13 +191,13 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    walls, kern, stage = [], [], [0.0, 0.0, 0.0]
+    walls, kern, stage = [], [], [0.0] * 5
     launches = 0
     for _ in range(a.steps):
         w, ks, _, _ = step()
         walls.append(w)
         kern.append(sum(ks))
-        for i in range(3):
+        for i in range(5):
             stage[i] += ks[i]
         launches += st.n_launches
     torch.cuda.synchronize()
@@ -250,7 +250,8 @@ def main():
         "config": {"workload": workload, "reads_per_gpu": n, "bases_per_gpu": bases, "l2": "512 MiB flush buffer written between steps",
                    "parallelism": "reads sharded one batch per GPU, index replicated; all-gather of GAF byte counts only",
                    "gaf_offsets": offsets},
-        "stage_ms_per_step": {"seed(K1-K3)": stage[0] / a.steps, "chain(K4-K5)": stage[1] / a.steps, "align(K6-K8)": stage[2] / a.steps},
+        "stage_ms_per_step": {"seed(K1-K3)": stage[0] / a.steps, "chain(K4-K5)": stage[1] / a.steps, "gchain+plan(K6-K7)": stage[2] / a.steps,
+                              "wfa_jobs(K8a)": stage[3] / a.steps, "finish(K8b cigar+ds)": stage[4] / a.steps, "wfa_jobs_per_step": int(st.n_jobs)},
         "e2e": {"value": e2e, "unit": "Gbp/s", "ms_per_step": t_wall / a.steps * 1e3,
                 "h2d_bytes_per_step": int(bases + 16 * n + 16 * n), "d2h_bytes_per_step": int(st.out_bytes + 48 * n + 96 * n),
                 "includes": "H2D of reads, 3 stage kernels, D2H of result blobs, mg_gchains_t assembly, GAF text (%d bytes/step)" % gaf_bytes[0]},

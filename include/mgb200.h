@@ -193,6 +193,8 @@ int mg_map_batch(const mg_idx_t *gi, int n_reads, const int *qlens, const char *
 
 typedef struct {
 	double t_h2d_ms, t_seed_ms, t_chain_ms, t_align_ms, t_d2h_ms, t_host_ms; /* last batch, CUDA events / host clock */
+	double t_wfa_ms, t_finish_ms; /* t_align_ms = graph chaining + alignment plan; t_wfa_ms = gap alignment jobs; t_finish_ms = cigar/ds/blob */
+	int64_t n_jobs;         /* WFA jobs of the batch */
 	int64_t n_reads, n_bases;
 	int64_t n_seeds;        /* sum of seeds entering the chaining kernel */
 	int64_t n_anchors_out;  /* sum of anchors kept in linear chains */

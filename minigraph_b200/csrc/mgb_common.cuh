@@ -46,6 +46,30 @@ static const uint64_t SEED_SEG_MASK = 0xffULL << 48;
 static const int SEED_OCC_SHIFT = 56;
 static const int MAX_SHORT_K = 15;
 
+// ---- warp-cooperative helpers ----
+// Warp-uniform functions take `lane` and are entered by all lanes of a warp together: scalar control flow is
+// replicated on every lane (identical values, identical branches), data-parallel loops stride by MGB_W, and
+// phases that exchange data through memory are separated by warp_sync().  The CPU simulator runs with one lane.
+#if MGB_ON_DEVICE
+#define MGB_W 32
+MG_D inline void warp_sync() { __syncwarp(); }
+MG_D inline int warp_any(int pred) { return __any_sync(0xffffffffu, pred); }
+MG_D inline int32_t warp_bcast_i32(int32_t x, int src) { return __shfl_sync(0xffffffffu, x, src); }
+MG_D inline uint64_t warp_bcast_u64(uint64_t x, int src) { return __shfl_sync(0xffffffffu, x, src); }
+MG_D inline int32_t warp_min_i32(int32_t x) { for (int o = 16; o > 0; o >>= 1) { int32_t y = __shfl_xor_sync(0xffffffffu, x, o); x = y < x? y : x; } return x; }
+MG_D inline int32_t warp_max_i32(int32_t x) { for (int o = 16; o > 0; o >>= 1) { int32_t y = __shfl_xor_sync(0xffffffffu, x, o); x = y > x? y : x; } return x; }
+MG_D inline int32_t warp_sum_i32(int32_t x) { for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o); return x; }
+#else
+#define MGB_W 1
+inline void warp_sync() {}
+inline int warp_any(int pred) { return pred; }
+inline int32_t warp_bcast_i32(int32_t x, int) { return x; }
+inline uint64_t warp_bcast_u64(uint64_t x, int) { return x; }
+inline int32_t warp_min_i32(int32_t x) { return x; }
+inline int32_t warp_max_i32(int32_t x) { return x; }
+inline int32_t warp_sum_i32(int32_t x) { return x; }
+#endif
+
 // ---- bump arena: one per worker (warp), stack discipline via mark/release ----
 struct Arena {
 	char *base;
@@ -100,6 +124,30 @@ MG_HD inline int avec_reserve(Arena &A, AVec<T> &v, int64_t want)
 	T *b = (T*)arena_alloc(A, (uint64_t)sizeof(T) * (uint64_t)m);
 	if (b == 0) return MGB_E_ARENA;
 	for (int64_t i = 0; i < v.n; ++i) b[i] = v.a[i];
+	v.a = b, v.m = m;
+	return 0;
+}
+
+// warp-uniform variant: every lane holds an identical copy of A and v; the element copy is split across lanes
+template<typename T>
+MG_HD inline int avec_reserve_w(Arena &A, AVec<T> &v, int64_t want, int lane)
+{
+	if (want <= v.m) return 0;
+	int64_t m = v.m? v.m : 16;
+	while (m < want) m += (m >> 1) + 16;
+	uint64_t old_bytes = ((uint64_t)sizeof(T) * (uint64_t)v.m + 15) & ~(uint64_t)15;
+	if (v.a && (char*)v.a + old_bytes == A.base + A.top) {
+		uint64_t new_bytes = ((uint64_t)sizeof(T) * (uint64_t)m + 15) & ~(uint64_t)15;
+		if ((uint64_t)((char*)v.a - A.base) + new_bytes > A.cap) return MGB_E_ARENA;
+		A.top = (uint64_t)((char*)v.a - A.base) + new_bytes;
+		if (A.top > A.peak) A.peak = A.top;
+		v.m = m;
+		return 0;
+	}
+	T *b = (T*)arena_alloc(A, (uint64_t)sizeof(T) * (uint64_t)m);
+	if (b == 0) return MGB_E_ARENA;
+	for (int64_t i = lane; i < v.n; i += MGB_W) b[i] = v.a[i];
+	warp_sync();
 	v.a = b, v.m = m;
 	return 0;
 }

@@ -100,22 +100,27 @@ struct LaunchArgs {
 	char *arena_base;
 	uint64_t arena_bytes;
 	uint64_t *arena_peak;    // per worker
+	int64_t job_start;       // first job of this launch (stage 4)
 	// segment sketch (index build)
 	Pool *pool_mz; u128 *mz;
 };
 
+// stages: 0 seed (K1-K3), 1 chain (K4/K5), 2 gchain + alignment plan (K6/K7), 3 segment sketch for the index,
+//         4 WFA job (K8a, warp-cooperative), 5 finish: CIGAR stitching + ds + result blob (K8b)
 template<int STAGE>
-MG_HD inline int run_stage(const LaunchArgs &L, int rid, Arena &A)
+MG_HD inline int run_stage(const LaunchArgs &L, int item, Arena &A, int lane)
 {
-	if (STAGE == 0) return stage_seed(L.c, rid, A);
-	if (STAGE == 1) return stage_chain(L.c, rid, A);
-	if (STAGE == 2) return stage_align(L.c, L.routs, rid, A);
+	if (STAGE == 0) return stage_seed(L.c, item, A);
+	if (STAGE == 1) return stage_chain(L.c, item, A);
+	if (STAGE == 2) return stage_gchain(L.c, L.routs, item, A);
+	if (STAGE == 5) return stage_finish(L.c, L.routs, item, A);
+	if (STAGE == 4) return wfa_job_run(A, L.c, L.job_start + item, lane);
 	if (STAGE == 3) { // sketch one graph segment for the index (reference: index.c:200-205)
 		AVec<u128> mv;
 		avec_init(mv);
-		int32_t len = L.c.g.seg_len[rid];
+		int32_t len = L.c.g.seg_len[item];
 		if (len <= 0) return 0;
-		MGB_TRY(sketch_seq(A, g_vseq(L.c.g, (uint32_t)rid << 1), len, L.c.ix.w, L.c.ix.k, (uint32_t)rid, mv));
+		MGB_TRY(sketch_seq(A, g_vseq(L.c.g, (uint32_t)item << 1), len, L.c.ix.w, L.c.ix.k, (uint32_t)item, mv));
 		int64_t off = pool_alloc(L.pool_mz, (uint64_t)mv.n * sizeof(u128));
 		if (off < 0) return MGB_E_POOL;
 		u128 *dst = L.mz + off / (int64_t)sizeof(u128);
@@ -125,9 +130,27 @@ MG_HD inline int run_stage(const LaunchArgs &L, int rid, Arena &A)
 	return MGB_E_INTERNAL;
 }
 
+// record a failure: per read for the mapping stages, a single status word for the index build
+template<int STAGE>
+MG_HD inline void stage_fail(const LaunchArgs &L, int item, int rc)
+{
+	if (STAGE == 3) {
+#if MGB_ON_DEVICE
+		atomicMin((int*)L.routs, rc);
+#else
+		if (rc < *(int*)L.routs) *(int*)L.routs = rc;
+#endif
+		return;
+	}
+	int rid = STAGE == 4? L.c.jobs[L.job_start + item].rid : item;
+	L.c.meta[rid].status = rc; // benign race between jobs of one read: any negative code triggers the redo
+	if (STAGE == 2 || STAGE == 4 || STAGE == 5) L.routs[rid].status = rc;
+}
+
 #ifndef MGB_HOSTSIM
-// One warp per work item; items are pulled from a global counter so that long reads do not stall a wave.
-// Round-1 scheme: lane 0 runs the (sequential, bit-exact) stage code, the other lanes idle at the barrier.
+// One warp per work item; items are pulled from a global counter so that long items do not stall a wave.
+// Stage 4 is warp-cooperative (all lanes enter the stage function); the other stages still run their sequential,
+// bit-exact control flow on lane 0 while the remaining lanes wait at the barrier.
 template<int STAGE>
 __global__ void __launch_bounds__(128) k_stage(LaunchArgs L)
 {
@@ -140,14 +163,15 @@ __global__ void __launch_bounds__(128) k_stage(LaunchArgs L)
 		if (lane == 0) item = (int)atomicAdd(L.c.next_read, 1u);
 		item = __shfl_sync(0xffffffffu, item, 0);
 		if (item >= L.n_work) break;
-		if (lane == 0) {
-			int rid = L.rid_list? L.rid_list[item] : item;
+		if (L.rid_list) item = L.rid_list[item];
+		if (STAGE == 4) {
 			A.top = 0;
-			int rc = run_stage<STAGE>(L, rid, A);
-			if (rc < 0) {
-				if (STAGE == 3) atomicMin((int*)L.routs, rc); // routs reused as a single status word for the index build
-				else { L.c.meta[rid].status = rc; if (STAGE == 2) L.routs[rid].status = rc; }
-			}
+			int rc = run_stage<STAGE>(L, item, A, lane);
+			if (rc < 0 && lane == 0) stage_fail<STAGE>(L, item, rc);
+		} else if (lane == 0) {
+			A.top = 0;
+			int rc = run_stage<STAGE>(L, item, A, 0);
+			if (rc < 0) stage_fail<STAGE>(L, item, rc);
 		}
 		__syncwarp();
 	}
@@ -171,14 +195,11 @@ static void launch_stage(LaunchArgs &L, const Workers &W)
 #ifdef MGB_HOSTSIM
 	Arena A;
 	arena_init(A, W.arena, W.arena_bytes);
-	for (int item = 0; item < L.n_work; ++item) {
-		int rid = L.rid_list? L.rid_list[item] : item;
+	for (int it = 0; it < L.n_work; ++it) {
+		int item = L.rid_list? L.rid_list[it] : it;
 		A.top = 0;
-		int rc = run_stage<STAGE>(L, rid, A);
-		if (rc < 0) {
-			if (STAGE == 3) { if (rc < *(int*)L.routs) *(int*)L.routs = rc; }
-			else { L.c.meta[rid].status = rc; if (STAGE == 2) L.routs[rid].status = rc; }
-		}
+		int rc = run_stage<STAGE>(L, item, A, 0);
+		if (rc < 0) stage_fail<STAGE>(L, item, rc);
 	}
 	if (W.peak && A.peak > W.peak[0]) W.peak[0] = A.peak;
 #else
@@ -500,8 +521,9 @@ static void fill_opt(MapOptDev &o, const mg_mapopt_t *opt, int k)
 	o.mask_level = opt->mask_level, o.sub_diff = opt->sub_diff, o.best_n = opt->best_n, o.pri_ratio = opt->pri_ratio, o.ref_bonus = opt->ref_bonus;
 }
 
-static mg_gchains_t *build_result(const ReadOut &ro, const char *blob)
+static mg_gchains_t *build_result(const ReadOut &ro, const char *pool)
 {
+	const char *blob = pool + ro.blob_off;
 	mg_gchains_t *gs = (mg_gchains_t*)calloc(1, sizeof(mg_gchains_t));
 	gs->rep_len = ro.rep_len;
 	if (ro.n_gc == 0) return gs; // reference: gchain1.c:460 returns the bare struct
@@ -525,12 +547,12 @@ static mg_gchains_t *build_result(const ReadOut &ro, const char *blob)
 		if (s->has_cigar) {
 			p->p = (mg_cigar_t*)calloc(1, (size_t)s->n_cigar * 8 + sizeof(mg_cigar_t));
 			p->p->n_cigar = s->n_cigar, p->p->mlen = s->c_mlen, p->p->blen = s->c_blen, p->p->aplen = s->c_aplen, p->p->ss = s->c_ss, p->p->ee = s->c_ee;
-			memcpy(p->p->cigar, blob + s->cigar_off, (size_t)s->n_cigar * 8);
+			memcpy(p->p->cigar, pool + s->cigar_off, (size_t)s->n_cigar * 8);
 			p->ds.len = s->ds_len, p->ds.n_off = s->n_dsoff;
 			p->ds.ds = (char*)calloc((size_t)s->ds_len + 1, 1);
-			memcpy(p->ds.ds, blob + s->ds_off, (size_t)s->ds_len);
+			memcpy(p->ds.ds, pool + s->ds_off, (size_t)s->ds_len);
 			p->ds.off = (int32_t*)calloc((size_t)(s->n_dsoff > 0? s->n_dsoff : 1), sizeof(int32_t));
-			memcpy(p->ds.off, blob + s->dsoff_off, (size_t)s->n_dsoff * sizeof(int32_t));
+			memcpy(p->ds.off, pool + s->dsoff_off, (size_t)s->n_dsoff * sizeof(int32_t));
 		}
 	}
 	return gs;
@@ -577,7 +599,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 	fill_opt(o, opt, M->k);
 	o.logf_tab = M->d_logf, o.n_logf_tab = M->n_logf;
 
-	EvTimer tm_h2d, tm_seed, tm_chain, tm_align, tm_d2h;
+	EvTimer tm_h2d, tm_seed, tm_chain, tm_align, tm_wfa, tm_fin, tm_d2h;
 	// ---- device buffers ----
 	tm_h2d.start();
 	char *d_seq = (char*)dmalloc(hseq.size());
@@ -591,12 +613,16 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 	dzero(d_meta, sizeof(ReadMeta) * (size_t)n_reads);
 	dzero(d_routs, sizeof(ReadOut) * (size_t)n_reads);
 	unsigned int *d_next = (unsigned int*)dmalloc(sizeof(unsigned int));
-	Pool *d_pools = (Pool*)dmalloc(sizeof(Pool) * 4);
-
-	uint64_t cap_anchor = std::max<uint64_t>((uint64_t)S.n_bases / 4 * sizeof(u128), (uint64_t)1 << 22);
-	uint64_t cap_minipos = std::max<uint64_t>((uint64_t)S.n_bases * sizeof(int32_t) / 2, (uint64_t)1 << 20);
-	uint64_t cap_lchain = std::max<uint64_t>((uint64_t)n_reads * 64 * sizeof(LChain), (uint64_t)1 << 20);
-	uint64_t cap_out = std::max<uint64_t>((uint64_t)S.n_bases * 4, (uint64_t)1 << 22);
+	enum { P_ANCHOR, P_MINIPOS, P_LCHAIN, P_OUT, P_PLAN, P_JOBS, P_CIG, N_POOLS };
+	Pool *d_pools = (Pool*)dmalloc(sizeof(Pool) * N_POOLS);
+	uint64_t cap[N_POOLS];
+	cap[P_ANCHOR] = std::max<uint64_t>((uint64_t)S.n_bases / 4 * sizeof(u128), (uint64_t)1 << 22);
+	cap[P_MINIPOS] = std::max<uint64_t>((uint64_t)S.n_bases * sizeof(int32_t) / 2, (uint64_t)1 << 20);
+	cap[P_LCHAIN] = std::max<uint64_t>((uint64_t)n_reads * 64 * sizeof(LChain), (uint64_t)1 << 20);
+	cap[P_OUT] = std::max<uint64_t>((uint64_t)S.n_bases * 4, (uint64_t)1 << 22);
+	cap[P_PLAN] = std::max<uint64_t>((uint64_t)S.n_bases / 8 * 8, (uint64_t)1 << 20);
+	cap[P_JOBS] = std::max<uint64_t>((uint64_t)S.n_bases / 40 * sizeof(WfaJob), (uint64_t)1 << 20);
+	cap[P_CIG] = std::max<uint64_t>((uint64_t)S.n_bases, (uint64_t)1 << 20);
 	std::vector<ReadOut> routs(n_reads);
 	std::vector<ReadMeta> meta(n_reads);
 	std::vector<char> hout;
@@ -605,33 +631,51 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 	ensure_workers(M->W, n_workers, (uint64_t)p_arena_mb << 20);
 
 	for (int attempt = 0; attempt < 8; ++attempt) {
-		u128 *d_anchor = (u128*)dmalloc(cap_anchor);
-		int32_t *d_minipos = (int32_t*)dmalloc(cap_minipos);
-		LChain *d_lchain = (LChain*)dmalloc(cap_lchain);
-		char *d_out = (char*)dmalloc(cap_out);
-		Pool hp[4];
-		hp[0].used = 0, hp[0].cap = cap_anchor;
-		hp[1].used = 0, hp[1].cap = cap_minipos;
-		hp[2].used = 0, hp[2].cap = cap_lchain;
-		hp[3].used = 0, hp[3].cap = cap_out;
+		void *d_buf[N_POOLS];
+		Pool hp[N_POOLS];
+		for (int i = 0; i < N_POOLS; ++i) d_buf[i] = dmalloc(cap[i]), hp[i].used = 0, hp[i].cap = cap[i];
 		h2d(d_pools, hp, sizeof(hp));
 		LaunchArgs L;
 		memset(&L, 0, sizeof(L));
 		L.c.g = M->g, L.c.ix = M->ix, L.c.opt = o;
 		L.c.b.n_reads = n_reads, L.c.b.seq = d_seq, L.c.b.seq_off = d_seq_off, L.c.b.seq_len = d_seq_len, L.c.b.name_hash = d_name_hash;
 		L.c.meta = d_meta;
-		L.c.pool_anchor = &d_pools[0], L.c.anchor = d_anchor;
-		L.c.pool_minipos = &d_pools[1], L.c.minipos = d_minipos;
-		L.c.pool_lchain = &d_pools[2], L.c.lchain = d_lchain;
-		L.c.pool_out = &d_pools[3], L.c.out = d_out;
+		L.c.pool_anchor = &d_pools[P_ANCHOR], L.c.anchor = (u128*)d_buf[P_ANCHOR];
+		L.c.pool_minipos = &d_pools[P_MINIPOS], L.c.minipos = (int32_t*)d_buf[P_MINIPOS];
+		L.c.pool_lchain = &d_pools[P_LCHAIN], L.c.lchain = (LChain*)d_buf[P_LCHAIN];
+		L.c.pool_out = &d_pools[P_OUT], L.c.out = (char*)d_buf[P_OUT];
+		L.c.pool_plan = &d_pools[P_PLAN], L.c.plan = (uint64_t*)d_buf[P_PLAN];
+		L.c.pool_jobs = &d_pools[P_JOBS], L.c.jobs = (WfaJob*)d_buf[P_JOBS];
+		L.c.pool_cig = &d_pools[P_CIG], L.c.cig = (uint32_t*)d_buf[P_CIG];
 		L.c.next_read = d_next;
-		L.routs = d_routs, L.rid_list = 0, L.n_work = n_reads;
-
-		tm_seed.start(); launch_stage<0>(L, M->W); tm_seed.stop();
-		tm_chain.start(); launch_stage<1>(L, M->W); tm_chain.stop();
-		tm_align.start(); launch_stage<2>(L, M->W); tm_align.stop();
-		S.n_launches += 3;
-		dsync();
+		L.routs = d_routs;
+		int64_t jobs_done = 0;
+		// one pass over a set of reads: 5 launches; the job count is read back between K6/K7 and K8a
+		auto run_pass = [&](const int32_t *d_list, int32_t n_list, const Workers &W, bool timed) {
+			L.rid_list = d_list, L.n_work = n_list;
+			if (timed) tm_seed.start();
+			launch_stage<0>(L, W);
+			if (timed) tm_seed.stop(), tm_chain.start();
+			launch_stage<1>(L, W);
+			if (timed) tm_chain.stop(), tm_align.start();
+			launch_stage<2>(L, W);
+			if (timed) tm_align.stop();
+			Pool pj;
+			d2h(&pj, &d_pools[P_JOBS], sizeof(Pool)); // implicit sync
+			int64_t n_jobs = (int64_t)(std::min<uint64_t>(pj.used, pj.cap) / sizeof(WfaJob));
+			L.rid_list = 0, L.job_start = jobs_done, L.n_work = (int32_t)(n_jobs - jobs_done);
+			if (timed) tm_wfa.start();
+			if (L.n_work > 0) launch_stage<4>(L, W);
+			if (timed) tm_wfa.stop(), tm_fin.start();
+			jobs_done = n_jobs;
+			L.rid_list = d_list, L.n_work = n_list;
+			launch_stage<5>(L, W);
+			if (timed) tm_fin.stop();
+			S.n_launches += 5;
+			dsync();
+		};
+		run_pass(0, n_reads, M->W, true);
+		S.n_jobs = jobs_done;
 		d2h(routs.data(), d_routs, sizeof(ReadOut) * (size_t)n_reads);
 		d2h(meta.data(), d_meta, sizeof(ReadMeta) * (size_t)n_reads);
 
@@ -646,15 +690,9 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 		if (!pool_full && !redo.empty()) {
 			uint64_t big = (uint64_t)p_arena_big_mb << 20;
 			int nw = (int)std::min<uint64_t>((uint64_t)n_workers, std::max<uint64_t>(1, dev_free_mem() * 3 / 4 / big));
-			nw = std::min<int>(nw, (int)redo.size());
 			ensure_workers(M->Wbig, std::max(1, nw), big);
 			int32_t *d_list = dalloc_copy(redo);
-			L.rid_list = d_list, L.n_work = (int32_t)redo.size();
-			launch_stage<0>(L, M->Wbig);
-			launch_stage<1>(L, M->Wbig);
-			launch_stage<2>(L, M->Wbig);
-			S.n_launches += 3;
-			dsync();
+			run_pass(d_list, (int32_t)redo.size(), M->Wbig, false);
 			dfree(d_list);
 			S.n_retry += (int64_t)redo.size();
 			d2h(routs.data(), d_routs, sizeof(ReadOut) * (size_t)n_reads);
@@ -668,21 +706,19 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 		bool done = !pool_full;
 		if (done) {
 			tm_d2h.start();
-			hout.resize(std::min<uint64_t>(hp[3].used, cap_out));
-			d2h(hout.data(), d_out, hout.size());
+			hout.resize(std::min<uint64_t>(hp[P_OUT].used, cap[P_OUT]));
+			d2h(hout.data(), d_buf[P_OUT], hout.size());
 			tm_d2h.stop();
 			S.out_bytes = (int64_t)hout.size();
 		}
-		dfree(d_anchor), dfree(d_minipos), dfree(d_lchain), dfree(d_out);
+		for (int i = 0; i < N_POOLS; ++i) dfree(d_buf[i]);
 		if (done) break;
 		// grow whatever overflowed (used counts keep growing past cap, so they tell how much was wanted)
-		if (hp[0].used > cap_anchor) cap_anchor = hp[0].used * 3 / 2;
-		if (hp[1].used > cap_minipos) cap_minipos = hp[1].used * 3 / 2;
-		if (hp[2].used > cap_lchain) cap_lchain = hp[2].used * 3 / 2;
-		if (hp[3].used > cap_out) cap_out = hp[3].used * 3 / 2;
+		for (int i = 0; i < N_POOLS; ++i) if (hp[i].used > cap[i]) cap[i] = hp[i].used * 3 / 2;
 		if (attempt == 7) { set_error("output pools kept overflowing"); rc_final = -2; }
 	}
 	S.t_h2d_ms = tm_h2d.ms(), S.t_seed_ms = tm_seed.ms(), S.t_chain_ms = tm_chain.ms(), S.t_align_ms = tm_align.ms();
+	S.t_wfa_ms = tm_wfa.ms(), S.t_finish_ms = tm_fin.ms();
 	if (rc_final == 0) S.t_d2h_ms = tm_d2h.ms();
 	{
 		std::vector<uint64_t> peak(M->W.n_workers);
@@ -706,7 +742,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 		}
 		S.n_seeds += meta[i].n_seed0, S.n_anchors_out += meta[i].n_a, S.n_chains_out += meta[i].n_u0, S.n_minimizers += meta[i].n_mz;
 		if (st == 1) { gcs[i] = 0; continue; } // empty or over-long read: reference returns before allocating (map-algo.c:359-360)
-		gcs[i] = build_result(routs[i], hout.data() + routs[i].blob_off);
+		gcs[i] = build_result(routs[i], hout.data());
 	}
 	S.t_host_ms = now_ms() - t_host0;
 	return 0;

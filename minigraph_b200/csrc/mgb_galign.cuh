@@ -31,19 +31,35 @@ MG_HD inline int cigar_append(Arena &A, AVec<uint64_t> &c, int32_t n_cigar, cons
 
 struct CigarOut { uint64_t *cigar; int32_t n; };
 
-// One CIGAR per graph chain: stitch the target across the walk between consecutive kept anchors and align each gap.
-// out[i].cigar is allocated in the arena (kept until the caller releases its mark).
-MG_HD inline int gchain_cigar(Arena &A, const GraphDev &g, const char *qseq, GcSet &gt, CigarOut *out)
+// One gap between two kept anchors that needs a real alignment.  Produced by the planning pass of K6/K7 (one lane
+// per read), consumed by the WFA kernel K8a (one warp per job), stitched back by the finishing pass.
+struct WfaJob {
+	int32_t rid, gc;
+	int32_t l0, l;        // first and last llchain of the gap (indices into the read's LLChain array)
+	int32_t t_beg;        // first target base on lc[l0].v  (= q->x + 1)
+	int32_t t_last;       // last target base on lc[l].v    (= p->x)
+	int32_t tl, ql, q_off;
+	int32_t n_cigar, status;
+	int64_t lc_off;       // byte offset of the read's LLChain array inside the output pool
+	int64_t cig_off;      // byte offset of the job's CIGAR (uint32 len<<4|op) inside the cigar pool
+};
+
+static const uint64_t PLAN_JOB = 1ULL << 63;
+
+// Planning pass of mg_gchain_cigar() (reference: galign.c:39-124): walk the kept anchors of every graph chain, emit
+// literal CIGAR items for the trivial gaps (galign.c:98-100) and a WfaJob for the others.
+MG_HD inline int gchain_cigar_plan(Arena &A, const PipeCtx &c, int rid, const GraphDev &g, GcSet &gt, int64_t lc_off_bytes)
 {
 	for (int32_t i = 0; i < gt.n_gc; ++i) {
 		GChain *gc = &gt.gc[i];
 		int32_t l0 = gc->off;
 		const int32_t off_a0 = gt.lc[l0].off;
 		int32_t j, j0 = 0, k, l, l_seq;
-		AVec<uint64_t> cigar;
-		avec_init(cigar);
-		MGB_TRY(avec_reserve(A, cigar, 64));
-		MGB_TRY(cigar_append1(A, cigar, 7, (int32_t)(gt.a[off_a0].y >> 32 & 0xff)));
+		uint64_t mark = A.top;
+		AVec<uint64_t> plan;
+		avec_init(plan);
+		MGB_TRY(avec_reserve(A, plan, gc->n_anchor + 8));
+		plan.a[plan.n++] = (uint64_t)(gt.a[off_a0].y >> 32 & 0xff) << 4 | 7;
 		for (j = 1; j < gc->n_anchor; ++j) {
 			const u128 *q, *p = &gt.a[off_a0 + j];
 			if ((p->y & SEED_IGNORE) && j != gc->n_anchor - 1) continue;
@@ -53,61 +69,98 @@ MG_HD inline int gchain_cigar(Arena &A, const GraphDev &g, const char *qseq, GcS
 				if (off_a0 + j >= r->off && off_a0 + j < r->off + r->cnt) break;
 			}
 			if (l >= gc->off + gc->cnt) return MGB_E_INTERNAL;
-			uint64_t mark = A.top;
-			const char *tseq;
-			if (l == l0) { // same vertex: the target is a slice of the stored sequence
-				l_seq = (int32_t)p->x - (int32_t)q->x;
-				tseq = g_vseq(g, gt.lc[l0].v) + ((int32_t)q->x + 1);
-			} else {
-				uint32_t v = gt.lc[l0].v;
-				int32_t tot = g.seg_len[v >> 1] - (int32_t)q->x - 1;
-				for (k = l0 + 1; k < l; ++k) tot += g_vlen(g, gt.lc[k].v);
-				tot += (int32_t)p->x + 1;
-				char *seq;
-				MGB_ALLOC(A, seq, char, tot + 1);
-				l_seq = g.seg_len[v >> 1] - (int32_t)q->x - 1;
-				{
-					const char *s = g_vseq(g, v) + ((int32_t)q->x + 1);
-					for (int32_t x = 0; x < l_seq; ++x) seq[x] = s[x];
-				}
-				for (k = l0 + 1; k < l; ++k) {
-					v = gt.lc[k].v;
-					const char *s = g_vseq(g, v);
-					int32_t vl = g_vlen(g, v);
-					for (int32_t x = 0; x < vl; ++x) seq[l_seq + x] = s[x];
-					l_seq += vl;
-				}
-				{
-					const char *s = g_vseq(g, gt.lc[l].v);
-					int32_t n = (int32_t)p->x + 1;
-					for (int32_t x = 0; x < n; ++x) seq[l_seq + x] = s[x];
-					l_seq += n;
-				}
-				tseq = seq;
+			if (l == l0) l_seq = (int32_t)p->x - (int32_t)q->x;
+			else {
+				l_seq = g.seg_len[gt.lc[l0].v >> 1] - (int32_t)q->x - 1;
+				for (k = l0 + 1; k < l; ++k) l_seq += g_vlen(g, gt.lc[k].v);
+				l_seq += (int32_t)p->x + 1;
 			}
-			{
-				int32_t qlen = (int32_t)p->y - (int32_t)q->y;
-				const char *qs = &qseq[(int32_t)q->y + 1];
-				if (!(l_seq > 0 || qlen > 0)) return MGB_E_INTERNAL;
-				if (l_seq == 0) { A.top = mark; MGB_TRY(cigar_append1(A, cigar, 1, qlen)); }
-				else if (qlen == 0) { A.top = mark; MGB_TRY(cigar_append1(A, cigar, 2, l_seq)); }
-				else if (l_seq == qlen && (uint64_t)(int64_t)qlen <= (q->y >> 32 & 0xff)) { A.top = mark; MGB_TRY(cigar_append1(A, cigar, 7, qlen)); }
-				else {
-					WfResult rst;
-					MGB_TRY(wfa_exact(A, l_seq, tseq, qlen, qs, 100000000LL, &rst));
-					if (rst.s < 0) return MGB_E_UNSUPPORTED; // TODO(round 2): chaining heuristic of the reference (miniwfa.c:776-834)
-					// the gap CIGAR sits above `cigar`; when the vector has to grow it moves above the gap CIGAR, and
-					// the hole is reclaimed with the read.  Copy the ops first if growth is impossible in place.
-					if (cigar.n + rst.n_cigar > cigar.m) {
-						// release the gap scratch by moving the ops to a temporary that survives the regrowth
-						MGB_TRY(cigar_append(A, cigar, rst.n_cigar, rst.cigar));
-					} else {
-						MGB_TRY(cigar_append(A, cigar, rst.n_cigar, rst.cigar));
-						A.top = mark;
-					}
-				}
+			int32_t qlen = (int32_t)p->y - (int32_t)q->y;
+			if (!(l_seq > 0 || qlen > 0)) return MGB_E_INTERNAL;
+			if (l_seq == 0) plan.a[plan.n++] = (uint64_t)(int64_t)qlen << 4 | 1;
+			else if (qlen == 0) plan.a[plan.n++] = (uint64_t)(int64_t)l_seq << 4 | 2;
+			else if (l_seq == qlen && (uint64_t)(int64_t)qlen <= (q->y >> 32 & 0xff)) plan.a[plan.n++] = (uint64_t)(int64_t)qlen << 4 | 7;
+			else {
+				int64_t joff = pool_alloc(c.pool_jobs, sizeof(WfaJob));
+				if (joff < 0) return MGB_E_POOL;
+				WfaJob *J = (WfaJob*)((char*)c.jobs + joff);
+				J->rid = rid, J->gc = i, J->l0 = l0, J->l = l, J->t_beg = (int32_t)q->x + 1, J->t_last = (int32_t)p->x;
+				J->tl = l_seq, J->ql = qlen, J->q_off = (int32_t)q->y + 1, J->n_cigar = 0, J->status = 0, J->lc_off = lc_off_bytes, J->cig_off = 0;
+				plan.a[plan.n++] = PLAN_JOB | (uint64_t)(joff / (int64_t)sizeof(WfaJob));
 			}
 			j0 = j, l0 = l;
+		}
+		int64_t poff = pool_alloc(c.pool_plan, (uint64_t)plan.n * 8);
+		if (poff < 0) return MGB_E_POOL;
+		uint64_t *dst = c.plan + poff / 8;
+		for (int64_t t = 0; t < plan.n; ++t) dst[t] = plan.a[t];
+		gc->plan_off = poff / 8, gc->n_plan = (int32_t)plan.n;
+		A.top = mark;
+	}
+	return 0;
+}
+
+// K8a: align one gap.  Warp-uniform (all lanes enter with identical arguments).
+MG_HD inline int wfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int lane)
+{
+	WfaJob *J = &c.jobs[job_idx];
+	const int32_t rid = J->rid, l0 = J->l0, l = J->l, tl = J->tl, ql = J->ql;
+	if (c.meta[rid].status < 0) return 0; // the read already failed elsewhere; it will be redone as a whole
+	const GraphDev &g = c.g;
+	const LLChain *lc = (const LLChain*)(c.out + J->lc_off);
+	const char *qs = c.b.seq + c.b.seq_off[rid] + J->q_off;
+	const char *tseq;
+	if (l == l0) tseq = g_vseq(g, lc[l0].v) + J->t_beg;
+	else { // stitch the target across the walk (reference: galign.c:76-93)
+		char *seq;
+		MGB_ALLOC(A, seq, char, tl + 1);
+		int32_t n = g_vlen(g, lc[l0].v) - J->t_beg, at = 0;
+		const char *s = g_vseq(g, lc[l0].v) + J->t_beg;
+		for (int32_t x = lane; x < n; x += MGB_W) seq[at + x] = s[x];
+		at += n;
+		for (int32_t k = l0 + 1; k < l; ++k) {
+			s = g_vseq(g, lc[k].v), n = g_vlen(g, lc[k].v);
+			for (int32_t x = lane; x < n; x += MGB_W) seq[at + x] = s[x];
+			at += n;
+		}
+		s = g_vseq(g, lc[l].v), n = J->t_last + 1;
+		for (int32_t x = lane; x < n; x += MGB_W) seq[at + x] = s[x];
+		at += n;
+		if (at != tl) return MGB_E_INTERNAL;
+		warp_sync();
+		tseq = seq;
+	}
+	WfResult rst;
+	MGB_TRY(wfa_exact(A, tl, tseq, ql, qs, 100000000LL, &rst, lane));
+	if (rst.s < 0) return MGB_E_UNSUPPORTED; // TODO(round 2): chaining heuristic of the reference (miniwfa.c:776-834)
+	int64_t coff = 0;
+	if (lane == 0) coff = pool_alloc(c.pool_cig, (uint64_t)rst.n_cigar * 4);
+	coff = (int64_t)warp_bcast_u64((uint64_t)coff, 0);
+	if (coff < 0) return MGB_E_POOL;
+	uint32_t *dst = (uint32_t*)((char*)c.cig + coff);
+	for (int32_t x = lane; x < rst.n_cigar; x += MGB_W) dst[x] = rst.cigar[x];
+	if (lane == 0) J->n_cigar = rst.n_cigar, J->cig_off = coff;
+	return 0;
+}
+
+// Finishing pass of mg_gchain_cigar() (reference: galign.c:125-141): concatenate plan items and job CIGARs.
+MG_HD inline int gchain_cigar_finish(Arena &A, const PipeCtx &c, GcSet &gt, CigarOut *out)
+{
+	for (int32_t i = 0; i < gt.n_gc; ++i) {
+		GChain *gc = &gt.gc[i];
+		const int32_t off_a0 = gt.lc[gc->off].off;
+		const uint64_t *plan = c.plan + gc->plan_off;
+		int64_t tot = 0;
+		for (int32_t t = 0; t < gc->n_plan; ++t)
+			tot += (plan[t] & PLAN_JOB)? c.jobs[plan[t] & ~PLAN_JOB].n_cigar : 1;
+		AVec<uint64_t> cigar;
+		avec_init(cigar);
+		MGB_TRY(avec_reserve(A, cigar, tot + 1));
+		for (int32_t t = 0; t < gc->n_plan; ++t) {
+			if (plan[t] & PLAN_JOB) {
+				const WfaJob *J = &c.jobs[plan[t] & ~PLAN_JOB];
+				MGB_TRY(cigar_append(A, cigar, J->n_cigar, (const uint32_t*)((const char*)c.cig + J->cig_off)));
+			} else MGB_TRY(cigar_append1(A, cigar, (int32_t)(plan[t] & 0xf), (int32_t)(plan[t] >> 4)));
 		}
 		out[i].cigar = cigar.a, out[i].n = (int32_t)cigar.n;
 		gc->has_cigar = 1;
@@ -115,7 +168,8 @@ MG_HD inline int gchain_cigar(Arena &A, const GraphDev &g, const char *qseq, GcS
 		gc->c_ss = (int32_t)gt.a[off_a0].x + 1 - (int32_t)(gt.a[off_a0].y >> 32 & 0xff);
 		gc->c_ee = (int32_t)gt.a[off_a0 + gc->n_anchor - 1].x + 1;
 		gc->c_mlen = gc->c_blen = gc->c_aplen = 0;
-		for (j = 0, l = 0; j < gc->n_cigar; ++j) {
+		int32_t l = 0;
+		for (int32_t j = 0; j < gc->n_cigar; ++j) {
 			int32_t op = (int32_t)(cigar.a[j] & 0xf), len = (int32_t)(cigar.a[j] >> 4);
 			if (op == 7) gc->c_mlen += len, gc->c_blen += len;
 			else gc->c_blen += len;
@@ -264,19 +318,20 @@ struct ReadOut {
 	int32_t status;
 	int32_t n_gc, n_lc, n_a, rep_len;
 	int32_t n_mz;
-	uint32_t blob_size;
-	int64_t blob_off;   // byte offset into the output pool; blob = GChain[n_gc] | LLChain[n_lc] | u128 a[n_a] | cigars | ds | ds offsets
+	uint32_t blob_size, blob2_size;
+	int64_t blob_off;   // output pool: GChain[n_gc] | LLChain[n_lc] | u128 a[n_a]          (written by stage_gchain)
+	int64_t blob2_off;  // output pool: per chain CIGAR (u64) | ds text | ds offsets        (written by stage_finish)
 };
 
 MG_HD inline uint64_t align8(uint64_t x) { return (x + 7) & ~(uint64_t)7; }
 
-// K6-K8 for one read.
-MG_HD inline int stage_align(const PipeCtx &c, ReadOut *routs, int rid, Arena &A)
+// K6/K7 for one read: graph chaining, bridging, post filters, alignment planning (one lane).
+MG_HD inline int stage_gchain(const PipeCtx &c, ReadOut *routs, int rid, Arena &A)
 {
 	ReadMeta &m = c.meta[rid];
 	ReadOut &ro = routs[rid];
 	const MapOptDev &o = c.opt;
-	ro.status = 0, ro.n_gc = ro.n_lc = ro.n_a = 0, ro.rep_len = m.rep_len, ro.n_mz = m.n_mz, ro.blob_size = 0, ro.blob_off = 0;
+	ro.status = 0, ro.n_gc = ro.n_lc = ro.n_a = 0, ro.rep_len = m.rep_len, ro.n_mz = m.n_mz, ro.blob_size = ro.blob2_size = 0, ro.blob_off = ro.blob2_off = 0;
 	if (m.status != 0) { ro.status = m.status; return 0; } // status 1: read skipped (empty or too long) -> no result object
 	uint64_t mark = A.top;
 	const char *qseq = c.b.seq + c.b.seq_off[rid];
@@ -295,50 +350,73 @@ MG_HD inline int stage_align(const PipeCtx &c, ReadOut *routs, int rid, Arena &A
 	gchain_flt_sub(o.pri_ratio, c.ix.k * 2, o.best_n, gs.n_gc, gs.gc);
 	MGB_TRY(gchain_drop_flt(A, gs));
 	MGB_TRY(gchain_set_mapq(o, gs, qlen, m.n_mz, o.min_gc_score));
-	CigarOut *cg = 0;
-	DsOut *ds = 0;
-	if ((o.flag & F_CIGAR) && gs.n_gc > 0) {
-		MGB_ALLOC(A, cg, CigarOut, gs.n_gc);
-		MGB_ALLOC(A, ds, DsOut, gs.n_gc);
-		MGB_TRY(gchain_cigar(A, c.g, qseq, gs, cg));
-		MGB_TRY(gchain_ds(A, c.g, qseq, gs, cg, ds));
-	}
-	// ---- serialise ----
-	uint64_t sz = 0;
-	uint64_t off_gc = 0; sz += align8((uint64_t)gs.n_gc * sizeof(GChain));
-	uint64_t off_lc = sz; sz += align8((uint64_t)gs.n_lc * sizeof(LLChain));
-	uint64_t off_a = sz; sz += align8((uint64_t)gs.n_a * sizeof(u128));
-	for (int32_t i = 0; i < gs.n_gc; ++i) {
-		GChain *gc = &gs.gc[i];
-		if (cg) {
-			gc->cigar_off = (int64_t)sz; sz += align8((uint64_t)cg[i].n * 8);
-			gc->ds_off = (int64_t)sz; sz += align8((uint64_t)ds[i].len + 1);
-			gc->dsoff_off = (int64_t)sz; sz += align8((uint64_t)ds[i].n_off * 4);
-		} else gc->has_cigar = 0, gc->n_cigar = 0, gc->cigar_off = gc->ds_off = gc->dsoff_off = 0, gc->ds_len = gc->n_dsoff = 0;
-	}
+	// ---- part 1 of the result ----
+	uint64_t off_lc = align8((uint64_t)gs.n_gc * sizeof(GChain));
+	uint64_t off_a = off_lc + align8((uint64_t)gs.n_lc * sizeof(LLChain));
+	uint64_t sz = off_a + align8((uint64_t)gs.n_a * sizeof(u128));
 	int64_t boff = pool_alloc(c.pool_out, sz);
 	if (boff < 0) return MGB_E_POOL;
 	char *blob = c.out + boff;
+	for (int32_t i = 0; i < gs.n_gc; ++i) {
+		GChain *gc = &gs.gc[i];
+		gc->has_cigar = 0, gc->n_cigar = 0, gc->cigar_off = gc->ds_off = gc->dsoff_off = 0, gc->ds_len = gc->n_dsoff = 0, gc->plan_off = 0, gc->n_plan = 0;
+	}
+	if ((o.flag & F_CIGAR) && gs.n_gc > 0)
+		MGB_TRY(gchain_cigar_plan(A, c, rid, c.g, gs, boff + (int64_t)off_lc));
 	{
-		GChain *d = (GChain*)(blob + off_gc);
+		GChain *d = (GChain*)blob;
 		for (int32_t i = 0; i < gs.n_gc; ++i) d[i] = gs.gc[i];
 		LLChain *dl = (LLChain*)(blob + off_lc);
 		for (int32_t i = 0; i < gs.n_lc; ++i) dl[i] = gs.lc[i];
 		u128 *da = (u128*)(blob + off_a);
 		for (int32_t i = 0; i < gs.n_a; ++i) da[i] = gs.a[i];
-		if (cg) {
-			for (int32_t i = 0; i < gs.n_gc; ++i) {
-				uint64_t *dc = (uint64_t*)(blob + gs.gc[i].cigar_off);
-				for (int32_t k = 0; k < cg[i].n; ++k) dc[k] = cg[i].cigar[k];
-				char *dd = blob + gs.gc[i].ds_off;
-				for (int32_t k = 0; k < ds[i].len; ++k) dd[k] = ds[i].ds[k];
-				dd[ds[i].len] = 0;
-				int32_t *dof = (int32_t*)(blob + gs.gc[i].dsoff_off);
-				for (int32_t k = 0; k < ds[i].n_off; ++k) dof[k] = ds[i].off[k];
-			}
-		}
 	}
 	ro.n_gc = gs.n_gc, ro.n_lc = gs.n_lc, ro.n_a = gs.n_a, ro.blob_size = (uint32_t)sz, ro.blob_off = boff;
+	A.top = mark;
+	return 0;
+}
+
+// K8b for one read: stitch CIGARs, ds strings, part 2 of the result (one lane).
+MG_HD inline int stage_finish(const PipeCtx &c, ReadOut *routs, int rid, Arena &A)
+{
+	ReadMeta &m = c.meta[rid];
+	ReadOut &ro = routs[rid];
+	if (m.status != 0) { ro.status = m.status; return 0; }
+	if (!(c.opt.flag & F_CIGAR) || ro.n_gc == 0) return 0;
+	uint64_t mark = A.top;
+	const char *qseq = c.b.seq + c.b.seq_off[rid];
+	char *blob = c.out + ro.blob_off;
+	GcSet gs;
+	gs.n_gc = ro.n_gc, gs.n_lc = ro.n_lc, gs.n_a = ro.n_a, gs.rep_len = ro.rep_len;
+	gs.gc = (GChain*)blob;
+	gs.lc = (LLChain*)(blob + align8((uint64_t)gs.n_gc * sizeof(GChain)));
+	gs.a = (u128*)((char*)gs.lc + align8((uint64_t)gs.n_lc * sizeof(LLChain)));
+	CigarOut *cg;
+	DsOut *ds;
+	MGB_ALLOC(A, cg, CigarOut, gs.n_gc);
+	MGB_ALLOC(A, ds, DsOut, gs.n_gc);
+	MGB_TRY(gchain_cigar_finish(A, c, gs, cg));
+	MGB_TRY(gchain_ds(A, c.g, qseq, gs, cg, ds));
+	uint64_t sz = 0;
+	for (int32_t i = 0; i < gs.n_gc; ++i)
+		sz += align8((uint64_t)cg[i].n * 8) + align8((uint64_t)ds[i].len + 1) + align8((uint64_t)ds[i].n_off * 4);
+	int64_t boff = pool_alloc(c.pool_out, sz);
+	if (boff < 0) return MGB_E_POOL;
+	uint64_t at = (uint64_t)boff;
+	for (int32_t i = 0; i < gs.n_gc; ++i) {
+		GChain *gc = &gs.gc[i];
+		gc->cigar_off = (int64_t)at; at += align8((uint64_t)cg[i].n * 8);
+		gc->ds_off = (int64_t)at; at += align8((uint64_t)ds[i].len + 1);
+		gc->dsoff_off = (int64_t)at; at += align8((uint64_t)ds[i].n_off * 4);
+		uint64_t *dc = (uint64_t*)(c.out + gc->cigar_off);
+		for (int32_t k = 0; k < cg[i].n; ++k) dc[k] = cg[i].cigar[k];
+		char *dd = c.out + gc->ds_off;
+		for (int32_t k = 0; k < ds[i].len; ++k) dd[k] = ds[i].ds[k];
+		dd[ds[i].len] = 0;
+		int32_t *dof = (int32_t*)(c.out + gc->dsoff_off);
+		for (int32_t k = 0; k < ds[i].n_off; ++k) dof[k] = ds[i].off[k];
+	}
+	ro.blob2_off = boff, ro.blob2_size = (uint32_t)sz;
 	A.top = mark;
 	return 0;
 }

@@ -34,7 +34,9 @@ struct GChain {
 	// base alignment
 	int32_t has_cigar, n_cigar, c_mlen, c_blen, c_aplen, c_ss, c_ee;
 	int32_t ds_len, n_dsoff;
-	int64_t cigar_off, ds_off, dsoff_off; // byte offsets relative to the blob start
+	int64_t cigar_off, ds_off, dsoff_off; // byte offsets into the output pool
+	int64_t plan_off;                     // element offset into the plan pool (alignment plan of this chain)
+	int32_t n_plan, pad_;
 };
 
 struct GcFrag { uint32_t srt; int32_t i; };

@@ -20,6 +20,9 @@ struct PipeCtx {
 	Pool *pool_minipos;    int32_t *minipos;
 	Pool *pool_lchain;     LChain *lchain;
 	Pool *pool_out;        char *out;
+	Pool *pool_plan;       uint64_t *plan;       // alignment plans (literal CIGAR items and job references)
+	Pool *pool_jobs;       struct WfaJob *jobs;  // gap alignment jobs
+	Pool *pool_cig;        uint32_t *cig;        // per-job CIGARs
 	// work queue
 	unsigned int *next_read;
 };

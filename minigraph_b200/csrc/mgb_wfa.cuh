@@ -31,7 +31,7 @@ struct WfState {
 	int32_t s, top, lo, hi;
 };
 
-MG_HD inline void wf_slice_bind(WfState &wf, int slot, int32_t lo, int32_t hi)
+MG_HD inline void wf_slice_bind(WfState &wf, int slot, int32_t lo, int32_t hi, int lane)
 {
 	WfSlice &f = wf.sl[slot];
 	int32_t n = hi - lo + 1;
@@ -42,18 +42,18 @@ MG_HD inline void wf_slice_bind(WfState &wf, int slot, int32_t lo, int32_t hi)
 	f.F1 = f.E1 + wf.lane_stride;
 	f.E2 = f.F1 + wf.lane_stride;
 	f.F2 = f.E2 + wf.lane_stride;
-	for (int32_t i = -WF_PAD; i < 0; ++i) f.H[i] = f.E1[i] = f.E2[i] = f.F1[i] = f.F2[i] = WF_NEG_INF;
-	for (int32_t i = n; i < n + WF_PAD; ++i) f.H[i] = f.E1[i] = f.E2[i] = f.F1[i] = f.F2[i] = WF_NEG_INF;
+	for (int32_t i = -WF_PAD + lane; i < 0; i += MGB_W) f.H[i] = f.E1[i] = f.E2[i] = f.F1[i] = f.F2[i] = WF_NEG_INF;
+	for (int32_t i = n + lane; i < n + WF_PAD; i += MGB_W) f.H[i] = f.E1[i] = f.E2[i] = f.F1[i] = f.F2[i] = WF_NEG_INF;
 	f.H -= lo, f.E1 -= lo, f.E2 -= lo, f.F1 -= lo, f.F2 -= lo;
 }
 
 // reference: miniwfa.c:80-101 wf_stripe_add
-MG_HD inline WfSlice &wf_stripe_add(WfState &wf, int32_t lo, int32_t hi)
+MG_HD inline WfSlice &wf_stripe_add(WfState &wf, int32_t lo, int32_t hi, int lane)
 {
 	++wf.s;
 	++wf.top;
 	if (wf.top == WF_NSLICE) wf.top = 0;
-	wf_slice_bind(wf, wf.top, lo, hi);
+	wf_slice_bind(wf, wf.top, lo, hi, lane);
 	return wf.sl[wf.top];
 }
 
@@ -146,10 +146,63 @@ MG_HD inline int wf_cigar_push1(Arena &A, AVec<uint32_t> &c, int32_t op, int32_t
 	return 0;
 }
 
+// sequential traceback on one lane; writes the CIGAR in input order to cig_store
+MG_HD inline int wf_traceback_lane0(Arena &A, int32_t tl, const char *ts, int32_t ql, const char *qs, const AVec<WfTb1> &tb, const AVec<uint8_t> &tbx,
+									int32_t last_state, uint32_t *cig_store, int64_t max_cigar, int32_t *n_cigar)
+{
+	AVec<uint32_t> cigar;
+	avec_init(cigar);
+	int32_t i = ql - 1, k = tl - 1, s = (int32_t)tb.n - 1, last = last_state;
+	while (i >= 0 && k >= 0) {
+		int32_t k0 = k, j, x, state, ext;
+		if (last == 0) {
+			while (i >= 0 && k >= 0 && qs[i] == ts[k]) --i, --k;
+			if (k0 - k > 0) MGB_TRY(wf_cigar_push1(A, cigar, 7, k0 - k));
+			if (i < 0 || k < 0) break;
+		}
+		if (s < 0) return MGB_E_INTERNAL;
+		j = i - k - tb.a[s].lo;
+		if (j < 0 || j > tb.a[s].hi - tb.a[s].lo) return MGB_E_INTERNAL;
+		x = tbx.a[tb.a[s].off + j];
+		state = last == 0? x & 7 : last;
+		ext = state > 0? x >> (state + 2) & 1 : 0;
+		if (state == 0) {
+			MGB_TRY(wf_cigar_push1(A, cigar, 8, 1));
+			--i, --k, s -= WF_X;
+		} else if (state == 1) {
+			MGB_TRY(wf_cigar_push1(A, cigar, 1, 1));
+			--i, s -= ext? WF_E1 : WF_O1 + WF_E1;
+		} else if (state == 3) {
+			MGB_TRY(wf_cigar_push1(A, cigar, 1, 1));
+			--i, s -= ext? WF_E2 : WF_O2 + WF_E2;
+		} else if (state == 2) {
+			MGB_TRY(wf_cigar_push1(A, cigar, 2, 1));
+			--k, s -= ext? WF_E1 : WF_O1 + WF_E1;
+		} else if (state == 4) {
+			MGB_TRY(wf_cigar_push1(A, cigar, 2, 1));
+			--k, s -= ext? WF_E2 : WF_O2 + WF_E2;
+		} else return MGB_E_INTERNAL;
+		last = state > 0 && ext? state : 0;
+	}
+	if (i >= 0) MGB_TRY(wf_cigar_push1(A, cigar, 1, i + 1));
+	else if (k >= 0) MGB_TRY(wf_cigar_push1(A, cigar, 2, k + 1));
+	if (cigar.n > max_cigar) return MGB_E_INTERNAL;
+	for (int64_t c = 0; c < cigar.n; ++c) cig_store[c] = cigar.a[cigar.n - 1 - c]; // back to input order
+	*n_cigar = (int32_t)cigar.n;
+	return 0;
+}
+
 // Exact WFA with traceback (reference: miniwfa.c:380-435 + :603-615 with opt.step == 0).
 // ts/qs need not be padded: the extension loop checks the sequence ends explicitly, which is what the reference's
 // distinct padding characters achieve (miniwfa.c:182-226).
-MG_HD inline int wfa_exact(Arena &A, int32_t tl, const char *ts, int32_t ql, const char *qs, int64_t max_iter, WfResult *r)
+//
+// Warp-uniform: all lanes enter with identical arguments and identical arena state.  Lanes own diagonals
+// (d = lo + lane, + 32, ...) in the three data-parallel phases of a score step -- pad initialisation, exact-match
+// extension, and the recurrence -- while the scalar bookkeeping (ring of 17 wavefronts, [lo,hi] tracking, the
+// every-256-scores shrink, iteration counting) is replicated.  The traceback is sequential and runs on lane 0.
+// Only one diagonal (d = ql - tl) can reach the end of both sequences, so "first diagonal that finishes" of the
+// sequential reference needs no ordering between lanes.
+MG_HD inline int wfa_exact(Arena &A, int32_t tl, const char *ts, int32_t ql, const char *qs, int64_t max_iter, WfResult *r, int lane)
 {
 	uint64_t mark = A.top;
 	WfState wf;
@@ -171,33 +224,36 @@ MG_HD inline int wfa_exact(Arena &A, int32_t tl, const char *ts, int32_t ql, con
 	// reference: miniwfa.c:103-121 wf_stripe_init
 	wf.s = 0, wf.top = 0, wf.lo = wf.hi = 0;
 	for (int i = 0; i < WF_NSLICE; ++i) {
-		WfSlice &f = wf_stripe_add(wf, 0, 0);
-		f.H[0] = f.E1[0] = f.E2[0] = f.F1[0] = f.F2[0] = WF_NEG_INF;
+		WfSlice &f = wf_stripe_add(wf, 0, 0, lane);
+		if (lane == 0) f.H[0] = f.E1[0] = f.E2[0] = f.F1[0] = f.F2[0] = WF_NEG_INF;
 	}
 	wf.s = 0;
-	wf.sl[wf.top].H[0] = -1;
+	if (lane == 0) wf.sl[wf.top].H[0] = -1;
+	warp_sync();
 
 	for (;;) {
 		WfSlice *p = &wf.sl[wf.top];
-		int32_t d, lo, hi, *H = p->H;
-		for (d = p->lo; d <= p->hi; ++d) {
-			int32_t k = H[d];
+		int32_t lo, hi, *H = p->H;
+		int hit = 0, hit_noext = 0;
+		for (int32_t d = p->lo + lane; d <= p->hi; d += MGB_W) { // extension along exact matches
+			int32_t k = H[d], k0 = k;
 			if (k < -1 || d + k < -1 || k >= tl || d + k >= ql) continue;
 			while (k + 1 < tl && d + k + 1 < ql && ts[k + 1] == qs[d + k + 1]) ++k;
-			if (k == tl - 1 && d + k == ql - 1) {
-				if (k == H[d]) {
-					const WfTb1 &t1 = tb.a[tb.n - 1];
-					last_state = tbx.a[t1.off + (d - t1.lo)] & 7;
-				}
-				break;
-			}
-			H[d] = k;
+			if (k == tl - 1 && d + k == ql - 1) hit = 1, hit_noext = (k == k0);
+			else H[d] = k;
 		}
-		if (d <= p->hi) break;
+		warp_sync();
+		if (warp_any(hit)) {
+			if (warp_any(hit && hit_noext)) {
+				const WfTb1 &t1 = tb.a[tb.n - 1];
+				last_state = tbx.a[t1.off + ((ql - tl) - t1.lo)] & 7;
+			}
+			break;
+		}
 		lo = wf.lo > -tl? wf.lo - 1 : -tl;
 		hi = wf.hi < ql? wf.hi + 1 : ql;
 		{ // reference: miniwfa.c:313-327 wf_next_basic (traceback variant)
-			const WfSlice &ft = wf_stripe_add(wf, lo, hi);
+			const WfSlice &ft = wf_stripe_add(wf, lo, hi, lane);
 			const WfSlice &fx = wf_stripe_get(wf, WF_X);
 			const WfSlice &fo1 = wf_stripe_get(wf, WF_O1 + WF_E1);
 			const WfSlice &fo2 = wf_stripe_get(wf, WF_O2 + WF_E2);
@@ -205,12 +261,15 @@ MG_HD inline int wfa_exact(Arena &A, int32_t tl, const char *ts, int32_t ql, con
 			const WfSlice &fe2 = wf_stripe_get(wf, WF_E2);
 			WfTb1 t1;
 			t1.lo = lo, t1.hi = hi, t1.off = tbx.n;
-			MGB_TRY(avec_push(A, tb, t1));
-			MGB_TRY(avec_reserve(A, tbx, tbx.n + (hi - lo + 1)));
+			MGB_TRY(avec_reserve_w(A, tb, tb.n + 1, lane));
+			if (lane == 0) tb.a[tb.n] = t1;
+			++tb.n;
+			MGB_TRY(avec_reserve_w(A, tbx, tbx.n + (hi - lo + 1), lane));
 			uint8_t *ax = tbx.a + tbx.n - lo;
 			tbx.n += hi - lo + 1;
-			for (int32_t dd = lo; dd <= hi; ++dd)
+			for (int32_t dd = lo + lane; dd <= hi; dd += MGB_W)
 				ax[dd] = wf_cell(dd, ft.H, ft.E1, ft.F1, ft.E2, ft.F2, fx.H, fo1.H, fo2.H, fe1.E1, fe1.F1, fe2.E2, fe2.F2);
+			warp_sync();
 			if (ft.H[lo] >= -1 || ft.E1[lo] >= -1 || ft.F1[lo] >= -1 || ft.E2[lo] >= -1 || ft.F2[lo] >= -1) wf.lo = lo;
 			if (ft.H[hi] >= -1 || ft.E1[hi] >= -1 || ft.F1[hi] >= -1 || ft.E2[hi] >= -1 || ft.F2[hi] >= -1) wf.hi = hi;
 		}
@@ -219,46 +278,16 @@ MG_HD inline int wfa_exact(Arena &A, int32_t tl, const char *ts, int32_t ql, con
 		if (max_iter > 0 && r->n_iter > max_iter) { stopped = 1; break; }
 	}
 	r->s = stopped? -1 : wf.s;
-	if (!stopped) { // reference: miniwfa.c:329-377 wf_traceback
-		AVec<uint32_t> cigar;
-		avec_init(cigar);
-		int32_t i = ql - 1, k = tl - 1, s = (int32_t)tb.n - 1, last = last_state;
-		while (i >= 0 && k >= 0) {
-			int32_t k0 = k, j, x, state, ext;
-			if (last == 0) {
-				while (i >= 0 && k >= 0 && qs[i] == ts[k]) --i, --k;
-				if (k0 - k > 0) MGB_TRY(wf_cigar_push1(A, cigar, 7, k0 - k));
-				if (i < 0 || k < 0) break;
-			}
-			if (s < 0) { A.top = mark; return MGB_E_INTERNAL; }
-			j = i - k - tb.a[s].lo;
-			if (j < 0 || j > tb.a[s].hi - tb.a[s].lo) { A.top = mark; return MGB_E_INTERNAL; }
-			x = tbx.a[tb.a[s].off + j];
-			state = last == 0? x & 7 : last;
-			ext = state > 0? x >> (state + 2) & 1 : 0;
-			if (state == 0) {
-				MGB_TRY(wf_cigar_push1(A, cigar, 8, 1));
-				--i, --k, s -= WF_X;
-			} else if (state == 1) {
-				MGB_TRY(wf_cigar_push1(A, cigar, 1, 1));
-				--i, s -= ext? WF_E1 : WF_O1 + WF_E1;
-			} else if (state == 3) {
-				MGB_TRY(wf_cigar_push1(A, cigar, 1, 1));
-				--i, s -= ext? WF_E2 : WF_O2 + WF_E2;
-			} else if (state == 2) {
-				MGB_TRY(wf_cigar_push1(A, cigar, 2, 1));
-				--k, s -= ext? WF_E1 : WF_O1 + WF_E1;
-			} else if (state == 4) {
-				MGB_TRY(wf_cigar_push1(A, cigar, 2, 1));
-				--k, s -= ext? WF_E2 : WF_O2 + WF_E2;
-			} else { A.top = mark; return MGB_E_INTERNAL; }
-			last = state > 0 && ext? state : 0;
+	if (!stopped) { // reference: miniwfa.c:329-377 wf_traceback (lane 0; the outcome is broadcast)
+		int rc = 0;
+		int32_t n_cig = 0;
+		if (lane == 0) {
+			rc = wf_traceback_lane0(A, tl, ts, ql, qs, tb, tbx, last_state, cig_store, max_cigar, &n_cig);
 		}
-		if (i >= 0) MGB_TRY(wf_cigar_push1(A, cigar, 1, i + 1));
-		else if (k >= 0) MGB_TRY(wf_cigar_push1(A, cigar, 2, k + 1));
-		if (cigar.n > max_cigar) { A.top = mark; return MGB_E_INTERNAL; }
-		for (int64_t c = 0; c < cigar.n; ++c) cig_store[c] = cigar.a[cigar.n - 1 - c]; // back to input order
-		r->n_cigar = (int32_t)cigar.n, r->cigar = cig_store;
+		rc = warp_bcast_i32(rc, 0), n_cig = warp_bcast_i32(n_cig, 0);
+		warp_sync();
+		if (rc < 0) { A.top = mark; return rc; }
+		r->n_cigar = n_cig, r->cigar = cig_store;
 	}
 	A.top = mark_keep;
 	return 0;
