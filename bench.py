@@ -166,6 +166,7 @@ def main():
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
     st = capi.mgb_stats_t()
     gaf_bytes = [0]
+    host = [0.0] * 6
 
     def step():
         flush.fill_(1)  # evict L2 (126 MB) between steps
@@ -173,12 +174,13 @@ def main():
         t0 = time.perf_counter()
         rc = lib.mg_map_batch(gi, n, qlens, cseqs, cnames, gcs, C.byref(mo))
         assert rc == 0, lib.mgb_last_error()
-        buf, ln, cap = C.c_void_p(0), C.c_size_t(0), C.c_size_t(0)
-        for i in range(n):
-            lib.mgb_write_gaf(C.byref(buf), C.byref(ln), C.byref(cap), g, gcs[i], qlens[i], cnames[i], mo.flag)
+        buf, ln = C.c_void_p(0), C.c_size_t(0)
+        lib.mgb_write_gaf_batch(g, n, gcs, qlens, cnames, mo.flag, 0, C.byref(buf), C.byref(ln))
         t1 = time.perf_counter()
         gaf_bytes[0] = ln.value
         C.CDLL(None).free(buf)
+        lib.mgb_get_stats(gi, C.byref(st))
+        host[0] += st.t_pack_ms; host[1] += st.t_h2d_ms; host[2] += st.t_d2h_ms; host[3] += st.t_asm_ms; host[4] += st.t_host_ms; host[5] += (t1 - t0) * 1e3 - st.t_host_ms
         for i in range(n):
             lib.mg_gchain_free(gcs[i])
         lib.mgb_get_stats(gi, C.byref(st))
@@ -186,6 +188,7 @@ def main():
 
     for _ in range(a.warmup):
         step()
+    host[:] = [0.0] * 6
     sampler = ClockSampler(local_rank)
     sampler.start()
     if world > 1:
@@ -251,10 +254,13 @@ def main():
                    "parallelism": "reads sharded one batch per GPU, index replicated; all-gather of GAF byte counts only",
                    "gaf_offsets": offsets},
         "stage_ms_per_step": {"seed(K1-K3)": stage[0] / a.steps, "chain(K4-K5)": stage[1] / a.steps, "gchain+plan(K6-K7)": stage[2] / a.steps,
-                              "wfa_jobs(K8a)": stage[3] / a.steps, "finish(K8b cigar+ds)": stage[4] / a.steps, "wfa_jobs_per_step": int(st.n_jobs)},
+                              "wfa_jobs(K8a)": stage[3] / a.steps, "finish(K8b cigar+ds)": stage[4] / a.steps, "wfa_jobs_per_step": int(st.n_jobs), "wfa_jobs_tier2": int(st.n_jobs_mid), "wfa_jobs_tier3": int(st.n_jobs_big)},
         "e2e": {"value": e2e, "unit": "Gbp/s", "ms_per_step": t_wall / a.steps * 1e3,
                 "h2d_bytes_per_step": int(bases + 16 * n + 16 * n), "d2h_bytes_per_step": int(st.out_bytes + 48 * n + 96 * n),
-                "includes": "H2D of reads, 3 stage kernels, D2H of result blobs, mg_gchains_t assembly, GAF text (%d bytes/step)" % gaf_bytes[0]},
+                "includes": "H2D of reads, 5 stage kernels, D2H of result blobs, mg_gchains_t assembly, GAF text (%d bytes/step)" % gaf_bytes[0]},
+        "host_ms_per_step": {"pack": host[0] / a.steps, "h2d": host[1] / a.steps, "d2h": host[2] / a.steps, "assemble": host[3] / a.steps,
+                             "mg_map_batch_total": host[4] / a.steps, "gaf_text": host[5] / a.steps},
+        "device_cycles_last_step": {k: int(st.prof[i]) for i, k in enumerate(capi.PROF_NAMES)},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "k_stage<1> (linear chaining: mg_lchain_dp/rmq + backtrack + compaction)", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

@@ -194,7 +194,9 @@ int mg_map_batch(const mg_idx_t *gi, int n_reads, const int *qlens, const char *
 typedef struct {
 	double t_h2d_ms, t_seed_ms, t_chain_ms, t_align_ms, t_d2h_ms, t_host_ms; /* last batch, CUDA events / host clock */
 	double t_wfa_ms, t_finish_ms; /* t_align_ms = graph chaining + alignment plan; t_wfa_ms = gap alignment jobs; t_finish_ms = cigar/ds/blob */
+	double t_pack_ms, t_asm_ms; /* host: packing reads into the staging buffer; building mg_gchains_t objects */
 	int64_t n_jobs;         /* WFA jobs of the batch */
+	int64_t n_jobs_mid, n_jobs_big; /* jobs that went to tier 2 / tier 3 */
 	int64_t n_reads, n_bases;
 	int64_t n_seeds;        /* sum of seeds entering the chaining kernel */
 	int64_t n_anchors_out;  /* sum of anchors kept in linear chains */
@@ -204,6 +206,7 @@ typedef struct {
 	int64_t n_launches;     /* kernels launched for the batch */
 	int64_t n_retry;        /* reads re-run with a larger arena */
 	uint64_t arena_peak;    /* largest per-worker arena use */
+	uint64_t prof[32];      /* device cycle counters per phase (see mgb_pipeline.cuh PROF_*) */
 } mgb_stats_t;
 
 const char *mgb_last_error(void);
@@ -220,6 +223,11 @@ void mgb_gfa_destroy(gfa_t *g);
 /* Byte-exact GAF line(s) for one read, restating format.c:121-291 mg_write_gaf() for flag bits used by -c. The text is
  * appended to *buf (realloc()ed, *len/*cap updated). */
 void mgb_write_gaf(char **buf, size_t *len, size_t *cap, const gfa_t *g, const mg_gchains_t *gs, int32_t qlen, const char *qname, uint64_t flag);
+
+/* The same for a whole batch, input order preserved, formatted by n_threads host threads (0: up to 16). *out is
+ * malloc()ed and 0-terminated; the caller frees it. */
+void mgb_write_gaf_batch(const gfa_t *g, int n_reads, mg_gchains_t *const *gcs, const int *qlens, const char *const *names,
+						 uint64_t flag, int n_threads, char **out, size_t *out_len);
 
 #ifdef __cplusplus
 }

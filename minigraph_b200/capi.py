@@ -87,10 +87,16 @@ class gfa_t(C.Structure):  # gfa.h:89-101
 class mgb_stats_t(C.Structure):
     _fields_ = [("t_h2d_ms", C.c_double), ("t_seed_ms", C.c_double), ("t_chain_ms", C.c_double),
                 ("t_align_ms", C.c_double), ("t_d2h_ms", C.c_double), ("t_host_ms", C.c_double),
-                ("t_wfa_ms", C.c_double), ("t_finish_ms", C.c_double), ("n_jobs", C.c_int64),
+                ("t_wfa_ms", C.c_double), ("t_finish_ms", C.c_double), ("t_pack_ms", C.c_double), ("t_asm_ms", C.c_double),
+                ("n_jobs", C.c_int64), ("n_jobs_mid", C.c_int64), ("n_jobs_big", C.c_int64),
                 ("n_reads", C.c_int64), ("n_bases", C.c_int64), ("n_seeds", C.c_int64), ("n_anchors_out", C.c_int64),
                 ("n_chains_out", C.c_int64), ("n_minimizers", C.c_int64), ("out_bytes", C.c_int64),
-                ("n_launches", C.c_int64), ("n_retry", C.c_int64), ("arena_peak", C.c_uint64)]
+                ("n_launches", C.c_int64), ("n_retry", C.c_int64), ("arena_peak", C.c_uint64), ("prof", C.c_uint64 * 32)]
+
+
+PROF_NAMES = ["wfa_fast_cyc", "wfa_fast_n", "wfa_slow_cyc", "wfa_slow_n", "wfa_max_cyc", "wfa_cells", "wfa_tb_cyc", "gc_dp_cyc", "gc_gen_cyc",
+              "gc_post_cyc", "gc_plan_cyc", "fin_cigar_cyc", "fin_ds_cyc", "seed_sketch_cyc", "seed_match_cyc", "seed_sort_cyc", "chain_dp_cyc",
+              "chain_bt_cyc", "chain_rmq_cyc", "chain_post_cyc", "wfa_mid_cyc", "wfa_mid_n"]
 
 
 def bind_mapping_api(lib):
@@ -139,4 +145,7 @@ def bind_engine_api(lib):
     lib.mgb_write_gaf.restype = None
     lib.mgb_write_gaf.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(gfa_t),
                                   C.POINTER(mg_gchains_t), C.c_int32, C.c_char_p, C.c_uint64]
+    lib.mgb_write_gaf_batch.restype = None
+    lib.mgb_write_gaf_batch.argtypes = [C.POINTER(gfa_t), C.c_int, C.POINTER(C.POINTER(mg_gchains_t)), C.POINTER(C.c_int),
+                                        C.POINTER(C.c_char_p), C.c_uint64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     return lib

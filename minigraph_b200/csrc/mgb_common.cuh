@@ -233,6 +233,28 @@ MG_HD inline float fast_log2(float x)
 	return log_2;
 }
 
+// unaligned 32-bit load assembled from two aligned ones (may touch up to 7 bytes behind p: buffers carry slack)
+MG_HD inline uint32_t ld32_unaligned(const char *p)
+{
+	uintptr_t a = (uintptr_t)p;
+	const uint32_t *w = (const uint32_t*)(a & ~(uintptr_t)3);
+	int sh = (int)(a & 3) << 3;
+	uint32_t lo = w[0], hi = w[1];
+#if MGB_ON_DEVICE
+	return __funnelshift_r(lo, hi, sh);
+#else
+	return sh? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+MG_HD inline int ctz32(uint32_t x)
+{
+#if MGB_ON_DEVICE
+	return __ffs((int)x) - 1;
+#else
+	return __builtin_ctz(x);
+#endif
+}
+
 MG_HD inline int nt4(uint8_t c) // reference: sketch.c:9-26 seq_nt4_table
 {
 	switch (c) {

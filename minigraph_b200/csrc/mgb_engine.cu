@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <string>
 #include <chrono>
+#include <thread>
 
 #include "../../include/mgb200.h"
 #include "mgb_galign.cuh"
@@ -29,11 +30,12 @@ using namespace mgb;
 static std::string g_last_error;
 static void set_error(const std::string &s) { g_last_error = s; fprintf(stderr, "[E::mgb200] %s\n", s.c_str()); }
 
-static int64_t p_arena_mb = 8;        // per worker, first pass
+static int64_t p_arena_mb = 6;        // per worker, first pass
 static int64_t p_arena_big_mb = 1024; // per worker, retry pass
-static int64_t p_workers_per_sm = 16;
+static int64_t p_workers_per_sm = 32;
 static int64_t p_device = 0;
 static int64_t p_block_warps = 4;
+static int64_t p_host_threads = 0; // 0: min(16, hardware threads)
 
 extern "C" const char *mgb_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char *mgb_version(void) { return "mgb200-r1"; }
@@ -44,6 +46,7 @@ extern "C" int mgb_set_param(const char *key, int64_t value)
 	else if (!strcmp(key, "workers_per_sm")) p_workers_per_sm = value;
 	else if (!strcmp(key, "device")) p_device = value;
 	else if (!strcmp(key, "block_warps")) p_block_warps = value;
+	else if (!strcmp(key, "host_threads")) p_host_threads = value;
 	else return -1;
 	return 0;
 }
@@ -88,6 +91,52 @@ template<typename T> static T *dalloc_copy(const std::vector<T> &v)
 	return d;
 }
 
+// grow-only buffers kept across batches: device memory, or page-locked host memory for fast H2D/D2H
+struct GrowBuf {
+	void *p; size_t cap; bool host;
+	GrowBuf(bool host_ = false) : p(0), cap(0), host(host_) {}
+	void release()
+	{
+		if (p == 0) return;
+#ifdef MGB_HOSTSIM
+		free(p);
+#else
+		if (host) cudaFreeHost(p); else cudaFree(p);
+#endif
+		p = 0, cap = 0;
+	}
+	void *ensure(size_t n)
+	{
+		if (n <= cap && p) return p;
+		release();
+		size_t c = n + n / 4 + 4096;
+#ifdef MGB_HOSTSIM
+		p = malloc(c);
+#else
+		if (host) CUDA_OK(cudaHostAlloc(&p, c, cudaHostAllocDefault)); else CUDA_OK(cudaMalloc(&p, c));
+#endif
+		cap = c;
+		return p;
+	}
+};
+
+namespace {
+template<typename F> void parallel_for(int64_t n, F fn)
+{
+	int nt = (int)p_host_threads;
+	if (nt <= 0) { nt = (int)std::thread::hardware_concurrency(); if (nt > 16) nt = 16; if (nt < 1) nt = 1; }
+	if (n < 64 || nt == 1) { for (int64_t i = 0; i < n; ++i) fn(i); return; }
+	std::vector<std::thread> th;
+	int64_t chunk = (n + nt - 1) / nt;
+	for (int t = 0; t < nt; ++t) {
+		int64_t b = t * chunk, e = std::min<int64_t>(n, b + chunk);
+		if (b >= e) break;
+		th.emplace_back([=]() { for (int64_t i = b; i < e; ++i) fn(i); });
+	}
+	for (auto &x : th) x.join();
+}
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------------------
@@ -106,15 +155,18 @@ struct LaunchArgs {
 };
 
 // stages: 0 seed (K1-K3), 1 chain (K4/K5), 2 gchain + alignment plan (K6/K7), 3 segment sketch for the index,
-//         4 WFA job (K8a, warp-cooperative), 5 finish: CIGAR stitching + ds + result blob (K8b)
+//         4/6/7 WFA jobs tier 1/2/3 (K8a, warp-cooperative), 5 finish: CIGAR stitching + ds + result blob (K8b)
+#define MGB_IS_WFA(STAGE) ((STAGE) == 4 || (STAGE) == 6 || (STAGE) == 7)
 template<int STAGE>
-MG_HD inline int run_stage(const LaunchArgs &L, int item, Arena &A, int lane)
+MG_HD inline int run_stage(const LaunchArgs &L, int item, Arena &A, int lane, int32_t *smem)
 {
 	if (STAGE == 0) return stage_seed(L.c, item, A);
 	if (STAGE == 1) return stage_chain(L.c, item, A);
 	if (STAGE == 2) return stage_gchain(L.c, L.routs, item, A);
 	if (STAGE == 5) return stage_finish(L.c, L.routs, item, A);
-	if (STAGE == 4) return wfa_job_run(A, L.c, L.job_start + item, lane);
+	if (STAGE == 4) return wfa_job_run(A, L.c, L.job_start + item, lane, smem, 1);
+	if (STAGE == 6) return wfa_job_run(A, L.c, L.c.jobq[0][item], lane, smem, 2);
+	if (STAGE == 7) return wfa_job_run(A, L.c, L.c.jobq[1][item], lane, smem, 3);
 	if (STAGE == 3) { // sketch one graph segment for the index (reference: index.c:200-205)
 		AVec<u128> mv;
 		avec_init(mv);
@@ -142,9 +194,9 @@ MG_HD inline void stage_fail(const LaunchArgs &L, int item, int rc)
 #endif
 		return;
 	}
-	int rid = STAGE == 4? L.c.jobs[L.job_start + item].rid : item;
+	int rid = STAGE == 4? L.c.jobs[L.job_start + item].rid : STAGE == 6? L.c.jobs[L.c.jobq[0][item]].rid : STAGE == 7? L.c.jobs[L.c.jobq[1][item]].rid : item;
 	L.c.meta[rid].status = rc; // benign race between jobs of one read: any negative code triggers the redo
-	if (STAGE == 2 || STAGE == 4 || STAGE == 5) L.routs[rid].status = rc;
+	if (STAGE == 2 || MGB_IS_WFA(STAGE) || STAGE == 5) L.routs[rid].status = rc;
 }
 
 #ifndef MGB_HOSTSIM
@@ -152,31 +204,56 @@ MG_HD inline void stage_fail(const LaunchArgs &L, int item, int rc)
 // Stage 4 is warp-cooperative (all lanes enter the stage function); the other stages still run their sequential,
 // bit-exact control flow on lane 0 while the remaining lanes wait at the barrier.
 template<int STAGE>
-__global__ void __launch_bounds__(128) k_stage(LaunchArgs L)
+__device__ __forceinline__ void stage_loop(const LaunchArgs &L)
 {
 	const int lane = threadIdx.x & 31;
 	const int worker = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
 	Arena A;
 	arena_init(A, L.arena_base + (uint64_t)worker * L.arena_bytes, L.arena_bytes);
+	extern __shared__ int4 dyn_smem[];
+	const int smem_stride = STAGE == 4? WfTier1::STRIDE : STAGE == 6? WfTier2::STRIDE : 0;
+	int32_t *smem = smem_stride? (int32_t*)((char*)dyn_smem + (size_t)(threadIdx.x >> 5) * smem_stride) : 0;
 	for (;;) {
 		int item = 0;
 		if (lane == 0) item = (int)atomicAdd(L.c.next_read, 1u);
 		item = __shfl_sync(0xffffffffu, item, 0);
 		if (item >= L.n_work) break;
 		if (L.rid_list) item = L.rid_list[item];
-		if (STAGE == 4) {
+		if (MGB_IS_WFA(STAGE)) {
 			A.top = 0;
-			int rc = run_stage<STAGE>(L, item, A, lane);
+			int rc = run_stage<STAGE>(L, item, A, lane, smem);
 			if (rc < 0 && lane == 0) stage_fail<STAGE>(L, item, rc);
 		} else if (lane == 0) {
 			A.top = 0;
-			int rc = run_stage<STAGE>(L, item, A, 0);
+			int rc = run_stage<STAGE>(L, item, A, 0, 0);
 			if (rc < 0) stage_fail<STAGE>(L, item, rc);
 		}
 		__syncwarp();
 	}
 	if (lane == 0 && L.arena_peak) L.arena_peak[worker] = A.peak > L.arena_peak[worker]? A.peak : L.arena_peak[worker];
 }
+
+// named entry points (one per stage, so that profiles read well); blocks of 4 warps, MINB blocks per SM wanted
+#define MGB_KERNEL(name, STAGE, MINB) __global__ void __launch_bounds__(128, MINB) name(LaunchArgs L) { stage_loop<STAGE>(L); }
+MGB_KERNEL(k_seed, 0, 8)          // K1-K3: sketch, index lookup, seed sort
+MGB_KERNEL(k_chain, 1, 8)         // K4/K5: linear chaining
+MGB_KERNEL(k_gchain, 2, 4)        // K6/K7: graph chaining, bridging, alignment plan
+MGB_KERNEL(k_index_sketch, 3, 8)  // index build: sketch of graph segments
+MGB_KERNEL(k_wfa_small, 4, 4)     // K8a tier 1: small gaps, wavefronts + traceback bytes in shared memory
+MGB_KERNEL(k_wfa_mid, 6, 3)       // K8a tier 2: mid-size gaps, wavefronts in shared memory (blocks of 2 warps)
+MGB_KERNEL(k_wfa_big, 7, 4)       // K8a tier 3: anything else, wavefronts in the worker arena
+MGB_KERNEL(k_finish, 5, 8)        // K8b: CIGAR stitching, ds strings, result blobs
+static const int STAGE_MINB[8] = { 8, 8, 4, 8, 4, 8, 3, 4 };
+static const int STAGE_WARPS[8] = { 4, 4, 4, 4, 4, 4, 2, 4 };
+template<int STAGE> struct StageKernel;
+template<> struct StageKernel<0> { static void (*get())(LaunchArgs) { return k_seed; } };
+template<> struct StageKernel<1> { static void (*get())(LaunchArgs) { return k_chain; } };
+template<> struct StageKernel<2> { static void (*get())(LaunchArgs) { return k_gchain; } };
+template<> struct StageKernel<3> { static void (*get())(LaunchArgs) { return k_index_sketch; } };
+template<> struct StageKernel<4> { static void (*get())(LaunchArgs) { return k_wfa_small; } };
+template<> struct StageKernel<6> { static void (*get())(LaunchArgs) { return k_wfa_mid; } };
+template<> struct StageKernel<7> { static void (*get())(LaunchArgs) { return k_wfa_big; } };
+template<> struct StageKernel<5> { static void (*get())(LaunchArgs) { return k_finish; } };
 #endif
 
 struct Workers {
@@ -195,17 +272,23 @@ static void launch_stage(LaunchArgs &L, const Workers &W)
 #ifdef MGB_HOSTSIM
 	Arena A;
 	arena_init(A, W.arena, W.arena_bytes);
+	std::vector<int32_t> sim_smem((WfTier1::STRIDE > WfTier2::STRIDE? WfTier1::STRIDE : WfTier2::STRIDE) / 4);
 	for (int it = 0; it < L.n_work; ++it) {
 		int item = L.rid_list? L.rid_list[it] : it;
 		A.top = 0;
-		int rc = run_stage<STAGE>(L, item, A, 0);
+		int rc = run_stage<STAGE>(L, item, A, 0, MGB_IS_WFA(STAGE)? sim_smem.data() : 0);
 		if (rc < 0) stage_fail<STAGE>(L, item, rc);
 	}
 	if (W.peak && A.peak > W.peak[0]) W.peak[0] = A.peak;
 #else
-	int threads = (int)p_block_warps * 32;
-	int blocks = (W.n_workers + (int)p_block_warps - 1) / (int)p_block_warps;
-	k_stage<STAGE><<<blocks, threads>>>(L);
+	const int warps = STAGE_WARPS[STAGE], threads = warps * 32;
+	int want = dev_sm_count() * STAGE_MINB[STAGE] * warps; // resident warps this stage can keep on the chip
+	int n_w = std::min(W.n_workers, want);
+	int blocks = std::max(1, n_w / warps);
+	size_t smem = STAGE == 4? (size_t)warps * WfTier1::STRIDE : STAGE == 6? (size_t)warps * WfTier2::STRIDE : 0;
+	void (*kern)(LaunchArgs) = StageKernel<STAGE>::get();
+	if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	kern<<<blocks, threads, smem>>>(L);
 	CUDA_OK(cudaGetLastError());
 #endif
 }
@@ -235,6 +318,8 @@ struct Model {
 	std::vector<float> logf_tab; float *d_logf; int n_logf;
 	mgb_stats_t stats;
 	gfa_edseq_t *es;
+	// grow-only buffers reused by every batch
+	GrowBuf h_seq{true}, h_out{true}, d_seq, d_meta, d_routs, d_small, d_jobq, d_pool[7];
 };
 
 static void model_free(Model *M)
@@ -245,6 +330,8 @@ static void model_free(Model *M)
 	if (M->Wbig.arena) dfree(M->Wbig.arena);
 	if (M->Wbig.peak) dfree(M->Wbig.peak);
 	if (M->d_logf) dfree(M->d_logf);
+	M->h_seq.release(), M->h_out.release(), M->d_seq.release(), M->d_meta.release(), M->d_routs.release(), M->d_small.release(), M->d_jobq.release();
+	for (int i = 0; i < 7; ++i) M->d_pool[i].release();
 	delete M;
 }
 
@@ -567,6 +654,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 	for (int i = 0; i < n_reads; ++i) gcs[i] = 0;
 	if (n_reads <= 0) return 0;
 	double t_host0 = now_ms();
+	double t_pack0 = t_host0;
 	// ---- pack the batch ----
 	std::vector<uint64_t> seq_off(n_reads);
 	std::vector<int32_t> seq_len(n_reads);
@@ -582,8 +670,9 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 		S.n_bases += qlens[i] > 0? qlens[i] : 0;
 	}
 	S.n_reads = n_reads;
-	std::vector<char> hseq(tot + 16, 0);
-	for (int i = 0; i < n_reads; ++i) if (qlens[i] > 0) memcpy(&hseq[seq_off[i]], seqs[i], (size_t)qlens[i]);
+	const size_t hseq_bytes = tot + 16;
+	char *hseq = (char*)M->h_seq.ensure(hseq_bytes);
+	parallel_for(n_reads, [&](int64_t i) { if (qlens[i] > 0) memcpy(hseq + seq_off[i], seqs[i], (size_t)qlens[i]); });
 	// glibc logf table for mapq (reference: gcmisc.c:216-217)
 	{
 		int need = std::max(1 << 16, max_qlen + 4096);
@@ -595,6 +684,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 			M->n_logf = need;
 		}
 	}
+	S.t_pack_ms = now_ms() - t_pack0;
 	MapOptDev o;
 	fill_opt(o, opt, M->k);
 	o.logf_tab = M->d_logf, o.n_logf_tab = M->n_logf;
@@ -602,17 +692,20 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 	EvTimer tm_h2d, tm_seed, tm_chain, tm_align, tm_wfa, tm_fin, tm_d2h;
 	// ---- device buffers ----
 	tm_h2d.start();
-	char *d_seq = (char*)dmalloc(hseq.size());
-	h2d(d_seq, hseq.data(), hseq.size());
+	char *d_seq = (char*)M->d_seq.ensure(hseq_bytes);
+	h2d(d_seq, hseq, hseq_bytes);
 	uint64_t *d_seq_off = dalloc_copy(seq_off);
 	int32_t *d_seq_len = dalloc_copy(seq_len);
 	uint32_t *d_name_hash = dalloc_copy(name_hash);
 	tm_h2d.stop();
-	ReadMeta *d_meta = (ReadMeta*)dmalloc(sizeof(ReadMeta) * (size_t)n_reads);
-	ReadOut *d_routs = (ReadOut*)dmalloc(sizeof(ReadOut) * (size_t)n_reads);
+	ReadMeta *d_meta = (ReadMeta*)M->d_meta.ensure(sizeof(ReadMeta) * (size_t)n_reads);
+	ReadOut *d_routs = (ReadOut*)M->d_routs.ensure(sizeof(ReadOut) * (size_t)n_reads);
 	dzero(d_meta, sizeof(ReadMeta) * (size_t)n_reads);
 	dzero(d_routs, sizeof(ReadOut) * (size_t)n_reads);
 	unsigned int *d_next = (unsigned int*)dmalloc(sizeof(unsigned int));
+	unsigned int *d_jobq_n = (unsigned int*)dmalloc(sizeof(unsigned int) * 2);
+	unsigned long long *d_prof = (unsigned long long*)dmalloc(sizeof(unsigned long long) * PROF_N);
+	dzero(d_prof, sizeof(unsigned long long) * PROF_N);
 	enum { P_ANCHOR, P_MINIPOS, P_LCHAIN, P_OUT, P_PLAN, P_JOBS, P_CIG, N_POOLS };
 	Pool *d_pools = (Pool*)dmalloc(sizeof(Pool) * N_POOLS);
 	uint64_t cap[N_POOLS];
@@ -625,7 +718,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 	cap[P_CIG] = std::max<uint64_t>((uint64_t)S.n_bases, (uint64_t)1 << 20);
 	std::vector<ReadOut> routs(n_reads);
 	std::vector<ReadMeta> meta(n_reads);
-	std::vector<char> hout;
+	char *hout = 0;
 	int rc_final = 0;
 	const int n_workers = default_workers();
 	ensure_workers(M->W, n_workers, (uint64_t)p_arena_mb << 20);
@@ -633,7 +726,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 	for (int attempt = 0; attempt < 8; ++attempt) {
 		void *d_buf[N_POOLS];
 		Pool hp[N_POOLS];
-		for (int i = 0; i < N_POOLS; ++i) d_buf[i] = dmalloc(cap[i]), hp[i].used = 0, hp[i].cap = cap[i];
+		for (int i = 0; i < N_POOLS; ++i) d_buf[i] = M->d_pool[i].ensure(cap[i]), hp[i].used = 0, hp[i].cap = cap[i];
 		h2d(d_pools, hp, sizeof(hp));
 		LaunchArgs L;
 		memset(&L, 0, sizeof(L));
@@ -648,6 +741,8 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 		L.c.pool_jobs = &d_pools[P_JOBS], L.c.jobs = (WfaJob*)d_buf[P_JOBS];
 		L.c.pool_cig = &d_pools[P_CIG], L.c.cig = (uint32_t*)d_buf[P_CIG];
 		L.c.next_read = d_next;
+		L.c.prof = d_prof;
+		L.c.jobq[0] = 0, L.c.jobq[1] = 0, L.c.jobq_n = d_jobq_n;
 		L.routs = d_routs;
 		int64_t jobs_done = 0;
 		// one pass over a set of reads: 5 launches; the job count is read back between K6/K7 and K8a
@@ -665,13 +760,25 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 			int64_t n_jobs = (int64_t)(std::min<uint64_t>(pj.used, pj.cap) / sizeof(WfaJob));
 			L.rid_list = 0, L.job_start = jobs_done, L.n_work = (int32_t)(n_jobs - jobs_done);
 			if (timed) tm_wfa.start();
-			if (L.n_work > 0) launch_stage<4>(L, W);
+			if (L.n_work > 0) { // three tiers; a job that does not fit one tier is queued for the next
+				int32_t n_new = L.n_work;
+				int32_t *q = (int32_t*)M->d_jobq.ensure(sizeof(int32_t) * 2 * (size_t)n_new);
+				L.c.jobq[0] = q, L.c.jobq[1] = q + n_new;
+				unsigned int qn[2] = {0, 0};
+				h2d(d_jobq_n, qn, sizeof(qn));
+				launch_stage<4>(L, W);
+				d2h(qn, d_jobq_n, sizeof(qn));
+				S.n_launches += 1;
+				if (qn[0] > 0) { L.n_work = (int32_t)qn[0]; launch_stage<6>(L, W); d2h(qn, d_jobq_n, sizeof(qn)); S.n_launches += 1; }
+				if (qn[1] > 0) { L.n_work = (int32_t)qn[1]; launch_stage<7>(L, W); S.n_launches += 1; }
+				if (timed) S.n_jobs_mid = qn[0], S.n_jobs_big = qn[1];
+			}
 			if (timed) tm_wfa.stop(), tm_fin.start();
 			jobs_done = n_jobs;
 			L.rid_list = d_list, L.n_work = n_list;
 			launch_stage<5>(L, W);
 			if (timed) tm_fin.stop();
-			S.n_launches += 5;
+			S.n_launches += 4;
 			dsync();
 		};
 		run_pass(0, n_reads, M->W, true);
@@ -706,12 +813,12 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 		bool done = !pool_full;
 		if (done) {
 			tm_d2h.start();
-			hout.resize(std::min<uint64_t>(hp[P_OUT].used, cap[P_OUT]));
-			d2h(hout.data(), d_buf[P_OUT], hout.size());
+			size_t out_bytes = (size_t)std::min<uint64_t>(hp[P_OUT].used, cap[P_OUT]);
+			hout = (char*)M->h_out.ensure(out_bytes);
+			d2h(hout, d_buf[P_OUT], out_bytes);
 			tm_d2h.stop();
-			S.out_bytes = (int64_t)hout.size();
+			S.out_bytes = (int64_t)out_bytes;
 		}
-		for (int i = 0; i < N_POOLS; ++i) dfree(d_buf[i]);
 		if (done) break;
 		// grow whatever overflowed (used counts keep growing past cap, so they tell how much was wanted)
 		for (int i = 0; i < N_POOLS; ++i) if (hp[i].used > cap[i]) cap[i] = hp[i].used * 3 / 2;
@@ -725,25 +832,33 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 		d2h(peak.data(), M->W.peak, sizeof(uint64_t) * peak.size());
 		for (uint64_t p : peak) if (p > S.arena_peak) S.arena_peak = p;
 	}
-	dfree(d_seq), dfree(d_seq_off), dfree(d_seq_len), dfree(d_name_hash), dfree(d_meta), dfree(d_routs), dfree(d_next), dfree(d_pools);
+	{ unsigned long long hp2[PROF_N]; d2h(hp2, d_prof, sizeof(hp2)); for (int i = 0; i < 32; ++i) S.prof[i] = (uint64_t)hp2[i]; }
+	dfree(d_seq_off), dfree(d_seq_len), dfree(d_name_hash), dfree(d_next), dfree(d_pools), dfree(d_prof), dfree(d_jobq_n);
 	if (rc_final < 0) return rc_final;
 
 	// ---- results ----
+	double t_asm0 = now_ms();
+	int first_bad = -1;
 	for (int i = 0; i < n_reads; ++i) {
 		int st = meta[i].status < 0? meta[i].status : routs[i].status;
-		if (st < 0) {
-			char buf[256];
-			snprintf(buf, sizeof(buf), "read %d ('%s', %d bp) failed on the device with code %d%s", i, names && names[i]? names[i] : "", qlens[i], st,
-					 st == MGB_E_ARENA? " (worker arena exhausted even in the retry pass; raise arena_big_mb)" :
-					 st == MGB_E_UNSUPPORTED? " (code path not implemented yet)" : "");
-			set_error(buf);
-			for (int j = 0; j < i; ++j) { mg_gchain_free(gcs[j]); gcs[j] = 0; }
-			return st;
-		}
+		if (st < 0) { first_bad = i; break; }
 		S.n_seeds += meta[i].n_seed0, S.n_anchors_out += meta[i].n_a, S.n_chains_out += meta[i].n_u0, S.n_minimizers += meta[i].n_mz;
-		if (st == 1) { gcs[i] = 0; continue; } // empty or over-long read: reference returns before allocating (map-algo.c:359-360)
-		gcs[i] = build_result(routs[i], hout.data());
 	}
+	if (first_bad >= 0) {
+		int i = first_bad, st = meta[i].status < 0? meta[i].status : routs[i].status;
+		char buf[256];
+		snprintf(buf, sizeof(buf), "read %d ('%s', %d bp) failed on the device with code %d%s", i, names && names[i]? names[i] : "", qlens[i], st,
+				 st == MGB_E_ARENA? " (worker arena exhausted even in the retry pass; raise arena_big_mb)" :
+				 st == MGB_E_UNSUPPORTED? " (code path not implemented yet)" : "");
+		set_error(buf);
+		return st;
+	}
+	parallel_for(n_reads, [&](int64_t i) {
+		int st = meta[i].status < 0? meta[i].status : routs[i].status;
+		if (st == 1) gcs[i] = 0; // empty or over-long read: reference returns before allocating (map-algo.c:359-360)
+		else gcs[i] = build_result(routs[i], hout);
+	});
+	S.t_asm_ms = now_ms() - t_asm0;
 	S.t_host_ms = now_ms() - t_host0;
 	return 0;
 }

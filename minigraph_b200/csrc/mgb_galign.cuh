@@ -6,6 +6,10 @@
 #include "mgb_pipeline.cuh"
 #include "mgb_gchain.cuh"
 #include "mgb_wfa.cuh"
+#if defined(MGB_HOSTSIM)
+#include <stdio.h>
+#include <stdlib.h>
+#endif
 
 namespace mgb {
 
@@ -101,11 +105,26 @@ MG_HD inline int gchain_cigar_plan(Arena &A, const PipeCtx &c, int rid, const Gr
 }
 
 // K8a: align one gap.  Warp-uniform (all lanes enter with identical arguments).
-MG_HD inline int wfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int lane)
+// tier 1: small gaps, wavefronts + traceback bytes in shared memory; tier 2: mid-size gaps, wavefronts in shared
+// memory; tier 3: anything, wavefronts in the worker arena.  A job that does not fit a tier is appended to the queue
+// of the next one (jobq[tier-1]); the host launches the next tier over that queue.
+MG_HD inline int wfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int lane, int32_t *smem, int tier)
 {
 	WfaJob *J = &c.jobs[job_idx];
 	const int32_t rid = J->rid, l0 = J->l0, l = J->l, tl = J->tl, ql = J->ql;
 	if (c.meta[rid].status < 0) return 0; // the read already failed elsewhere; it will be redone as a whole
+	if ((tier == 1 && (tl > WfTier1::MAXLEN_ || ql > WfTier1::MAXLEN_)) || (tier == 2 && (tl > WfTier2::MAXLEN_ || ql > WfTier2::MAXLEN_))) {
+		if (lane == 0) {
+			unsigned int at;
+#if MGB_ON_DEVICE
+			at = atomicAdd(&c.jobq_n[tier - 1], 1u);
+#else
+			at = c.jobq_n[tier - 1]++;
+#endif
+			c.jobq[tier - 1][at] = (int32_t)job_idx;
+		}
+		return 0;
+	}
 	const GraphDev &g = c.g;
 	const LLChain *lc = (const LLChain*)(c.out + J->lc_off);
 	const char *qs = c.b.seq + c.b.seq_off[rid] + J->q_off;
@@ -131,7 +150,34 @@ MG_HD inline int wfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int la
 		tseq = seq;
 	}
 	WfResult rst;
-	MGB_TRY(wfa_exact(A, tl, tseq, ql, qs, 100000000LL, &rst, lane));
+	unsigned long long pt0 = prof_clock();
+	int rc;
+	if (tier == 1) rc = wfa_smem<WfTier1::W_, WfTier1::MAXLEN_, WfTier1::TBCAP_>(A, smem, tl, tseq, ql, qs, &rst, lane);
+	else if (tier == 2) rc = wfa_smem<WfTier2::W_, WfTier2::MAXLEN_, WfTier2::TBCAP_>(A, smem, tl, tseq, ql, qs, &rst, lane);
+	else rc = wfa_exact(A, tl, tseq, ql, qs, 100000000LL, &rst, lane);
+	if (rc < 0) return rc;
+	if (lane == 0) {
+		unsigned long long dt = prof_clock() - pt0;
+		int slot = tier == 1? PROF_WFA_FAST_CYC : tier == 2? PROF_WFA_MID_CYC : PROF_WFA_SLOW_CYC;
+		prof_add(c, slot, dt), prof_add(c, slot + 1, 1);
+		prof_max(c, PROF_WFA_MAX_CYC, dt);
+		if (rc == 0) prof_add(c, PROF_WFA_CELLS, (unsigned long long)rst.n_iter);
+	}
+	if (rc == 1) { // does not fit this tier
+		if (lane == 0) {
+			unsigned int at;
+#if MGB_ON_DEVICE
+			at = atomicAdd(&c.jobq_n[tier - 1], 1u);
+#else
+			at = c.jobq_n[tier - 1]++;
+#endif
+			c.jobq[tier - 1][at] = (int32_t)job_idx;
+		}
+		return 0;
+	}
+#if !MGB_ON_DEVICE && defined(MGB_HOSTSIM)
+	if (getenv("MGB_DUMP_JOBS")) fprintf(stderr, "JOB\t%d\t%d\t%d\t%ld\t%d\t%d\n", tl, ql, rst.s, (long)rst.n_iter, rst.n_cigar, tier);
+#endif
 	if (rst.s < 0) return MGB_E_UNSUPPORTED; // TODO(round 2): chaining heuristic of the reference (miniwfa.c:776-834)
 	int64_t coff = 0;
 	if (lane == 0) coff = pool_alloc(c.pool_cig, (uint64_t)rst.n_cigar * 4);
@@ -259,7 +305,9 @@ MG_HD inline int gchain_ds(Arena &A, const GraphDev &g, const char *qseq, GcSet 
 			if (op == 0 || op == 7 || op == 8) {
 				int64_t z;
 				int32_t l = 0;
-				for (z = 0; z < len; ++z) {
+				if (op == 7) l = (int32_t)len, z = len; // '=' runs hold identical characters: nothing to look at
+				else z = 0;
+				for (; z < len; ++z) {
 					uint8_t cx = (uint8_t)nt4((uint8_t)seq[x + z]);
 					uint8_t cy = (uint8_t)nt4((uint8_t)qseq[y + z]);
 					if (cx != cy) {
@@ -342,14 +390,21 @@ MG_HD inline int stage_gchain(const PipeCtx &c, ReadOut *routs, int rid, Arena &
 	LChain *lc;
 	MGB_ALLOC(A, lc, LChain, n_lc);
 	for (int32_t i = 0; i < n_lc; ++i) lc[i] = c.lchain[m.lc_off + i];
+	unsigned long long pt0 = prof_clock();
 	MGB_TRY(gchain1_dp(A, c.g, &n_lc, lc, qlen, o.bw_long, o.bw_long, o.bw_long, o.max_gc_skip, o.ref_bonus, o.chn_pen_gap, o.mask_level, a, &u, &n_u));
 	GcSet gs;
+	unsigned long long pt1 = prof_clock();
+	prof_add(c, PROF_GC_DP_CYC, pt1 - pt0);
 	MGB_TRY(gchain_gen(A, c.g, n_u, u, lc, a, m.hash, o.min_gc_cnt, o.min_gc_score, o.gdp_max_ed, 1, qseq, gs));
 	gs.rep_len = m.rep_len;
+	unsigned long long pt2 = prof_clock();
+	prof_add(c, PROF_GC_GEN_CYC, pt2 - pt1);
 	MGB_TRY(gchain_set_parent(A, o.mask_level, gs.n_gc, gs.gc, o.sub_diff));
 	gchain_flt_sub(o.pri_ratio, c.ix.k * 2, o.best_n, gs.n_gc, gs.gc);
 	MGB_TRY(gchain_drop_flt(A, gs));
 	MGB_TRY(gchain_set_mapq(o, gs, qlen, m.n_mz, o.min_gc_score));
+	unsigned long long pt3 = prof_clock();
+	prof_add(c, PROF_GC_POST_CYC, pt3 - pt2);
 	// ---- part 1 of the result ----
 	uint64_t off_lc = align8((uint64_t)gs.n_gc * sizeof(GChain));
 	uint64_t off_a = off_lc + align8((uint64_t)gs.n_lc * sizeof(LLChain));
@@ -372,6 +427,7 @@ MG_HD inline int stage_gchain(const PipeCtx &c, ReadOut *routs, int rid, Arena &
 		for (int32_t i = 0; i < gs.n_a; ++i) da[i] = gs.a[i];
 	}
 	ro.n_gc = gs.n_gc, ro.n_lc = gs.n_lc, ro.n_a = gs.n_a, ro.blob_size = (uint32_t)sz, ro.blob_off = boff;
+	prof_add(c, PROF_GC_PLAN_CYC, prof_clock() - pt3);
 	A.top = mark;
 	return 0;
 }
@@ -395,8 +451,12 @@ MG_HD inline int stage_finish(const PipeCtx &c, ReadOut *routs, int rid, Arena &
 	DsOut *ds;
 	MGB_ALLOC(A, cg, CigarOut, gs.n_gc);
 	MGB_ALLOC(A, ds, DsOut, gs.n_gc);
+	unsigned long long pt0 = prof_clock();
 	MGB_TRY(gchain_cigar_finish(A, c, gs, cg));
+	unsigned long long pt1 = prof_clock();
+	prof_add(c, PROF_FIN_CIGAR_CYC, pt1 - pt0);
 	MGB_TRY(gchain_ds(A, c.g, qseq, gs, cg, ds));
+	prof_add(c, PROF_FIN_DS_CYC, prof_clock() - pt1);
 	uint64_t sz = 0;
 	for (int32_t i = 0; i < gs.n_gc; ++i)
 		sz += align8((uint64_t)cg[i].n * 8) + align8((uint64_t)ds[i].len + 1) + align8((uint64_t)ds[i].n_off * 4);

@@ -573,3 +573,35 @@ extern "C" void mgb_write_gaf(char **buf, size_t *len, size_t *cap, const gfa_t 
 	(*s.buf)[*s.len] = 0;
 	(void)F_FRAG_MERGE;
 }
+
+// GAF text for a whole batch, input order preserved (the reference writes from one thread, gmap.c:101-141; here the
+// records are formatted by several host threads into per-thread buffers that are concatenated in read order).
+#include <thread>
+extern "C" void mgb_write_gaf_batch(const gfa_t *g, int n_reads, mg_gchains_t *const *gcs, const int *qlens, const char *const *names,
+									uint64_t flag, int n_threads, char **out, size_t *out_len)
+{
+	if (n_threads <= 0) { n_threads = (int)std::thread::hardware_concurrency(); if (n_threads > 16) n_threads = 16; if (n_threads < 1) n_threads = 1; }
+	if (n_reads < 256) n_threads = 1;
+	struct Part { char *buf; size_t len, cap; };
+	std::vector<Part> part((size_t)n_threads, Part{0, 0, 0});
+	int64_t chunk = ((int64_t)n_reads + n_threads - 1) / n_threads;
+	auto work = [&](int t) {
+		int64_t b = t * chunk, e = b + chunk < n_reads? b + chunk : n_reads;
+		Part &p = part[(size_t)t];
+		for (int64_t i = b; i < e; ++i)
+			mgb_write_gaf(&p.buf, &p.len, &p.cap, g, gcs[i], qlens[i], names && names[i]? names[i] : "*", flag);
+	};
+	if (n_threads == 1) work(0);
+	else {
+		std::vector<std::thread> th;
+		for (int t = 0; t < n_threads; ++t) th.emplace_back(work, t);
+		for (auto &x : th) x.join();
+	}
+	size_t tot = 0;
+	for (auto &p : part) tot += p.len;
+	char *o = (char*)malloc(tot + 1);
+	size_t at = 0;
+	for (auto &p : part) { if (p.len) memcpy(o + at, p.buf, p.len); at += p.len; free(p.buf); }
+	o[tot] = 0;
+	*out = o, *out_len = tot;
+}

@@ -143,6 +143,11 @@ MG_HD inline int32_t gwf_extend1(int32_t d, int32_t k, int32_t vl, const char *t
 {
 	int32_t max_k = (ql - d < vl? ql - d : vl) - 1;
 	const char *ts_ = ts + 1, *qs_ = qs + d + 1;
+	while (k + 4 <= max_k) { // four bases per step; both buffers carry >= 8 bytes of slack behind their last base
+		uint32_t x = ld32_unaligned(ts_ + k) ^ ld32_unaligned(qs_ + k);
+		if (x) return k + (ctz32(x) >> 3);
+		k += 4;
+	}
 	while (k < max_k && ts_[k] == qs_[k]) ++k;
 	return k;
 }

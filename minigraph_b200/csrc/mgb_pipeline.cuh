@@ -23,9 +23,41 @@ struct PipeCtx {
 	Pool *pool_plan;       uint64_t *plan;       // alignment plans (literal CIGAR items and job references)
 	Pool *pool_jobs;       struct WfaJob *jobs;  // gap alignment jobs
 	Pool *pool_cig;        uint32_t *cig;        // per-job CIGARs
+	int32_t *jobq[2];      unsigned int *jobq_n;   // jobs handed to WFA tier 2 / tier 3
 	// work queue
 	unsigned int *next_read;
+	// instrumentation: 32 counters, see PROF_* below
+	unsigned long long *prof;
 };
+
+enum { PROF_WFA_FAST_CYC = 0, PROF_WFA_FAST_N, PROF_WFA_SLOW_CYC, PROF_WFA_SLOW_N, PROF_WFA_MAX_CYC, PROF_WFA_CELLS, PROF_WFA_TB_CYC,
+	   PROF_GC_DP_CYC, PROF_GC_GEN_CYC, PROF_GC_POST_CYC, PROF_GC_PLAN_CYC, PROF_FIN_CIGAR_CYC, PROF_FIN_DS_CYC, PROF_SEED_SKETCH_CYC,
+	   PROF_SEED_MATCH_CYC, PROF_SEED_SORT_CYC, PROF_CHAIN_DP_CYC, PROF_CHAIN_BT_CYC, PROF_CHAIN_RMQ_CYC, PROF_CHAIN_POST_CYC, PROF_WFA_MID_CYC, PROF_WFA_MID_N, PROF_N = 32 };
+
+MG_HD inline unsigned long long prof_clock()
+{
+#if MGB_ON_DEVICE
+	return (unsigned long long)clock64();
+#else
+	return 0;
+#endif
+}
+MG_HD inline void prof_add(const PipeCtx &c, int slot, unsigned long long v)
+{
+#if MGB_ON_DEVICE
+	if (c.prof) atomicAdd(&c.prof[slot], v);
+#else
+	if (c.prof) c.prof[slot] += v;
+#endif
+}
+MG_HD inline void prof_max(const PipeCtx &c, int slot, unsigned long long v)
+{
+#if MGB_ON_DEVICE
+	if (c.prof) atomicMax(&c.prof[slot], v);
+#else
+	if (c.prof && c.prof[slot] < v) c.prof[slot] = v;
+#endif
+}
 
 // K1-K3 for one read.  Writes sorted seeds to the anchor pool and the query positions of kept minimizers to the
 // mini_pos pool.
@@ -45,8 +77,11 @@ MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A)
 	if (qlen <= 0 || (c.opt.max_qlen > 0 && qlen > c.opt.max_qlen)) { m.status = 1; return 0; } // unmapped by definition
 	AVec<u128> mv;
 	avec_init(mv);
+	unsigned long long t0 = prof_clock();
 	MGB_TRY(sketch_seq(A, seq, qlen, c.ix.w, c.ix.k, 0, mv));
 	m.n_mz = (int32_t)mv.n;
+	unsigned long long t1 = prof_clock();
+	prof_add(c, PROF_SEED_SKETCH_CYC, t1 - t0);
 	SeedMatch *sm;
 	int n_m, n_mp, rep_len;
 	int64_t n_a;
@@ -63,7 +98,10 @@ MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A)
 	int32_t *mp = c.minipos + m.mp_off;
 	for (int i = 0; i < n_mp; ++i) mp[i] = mp_tmp[i];
 	expand_seeds(c.g, n_m, sm, a);
+	unsigned long long t2 = prof_clock();
+	prof_add(c, PROF_SEED_MATCH_CYC, t2 - t1);
 	MGB_TRY(radix_sort_128x(A, a, n_a));
+	prof_add(c, PROF_SEED_SORT_CYC, prof_clock() - t2);
 	A.top = mark;
 	return 0;
 }
@@ -91,6 +129,7 @@ MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A)
 		if (max_gap_ref < o.max_gap) max_gap_ref = o.max_gap;
 	} else max_gap_ref = o.max_gap;
 
+	unsigned long long t0 = prof_clock();
 	if (n_a > 0) {
 		if (o.flag & F_RMQ)
 			MGB_TRY(chain_rmq(A, o.max_gap, o.max_gap_pre, o.bw, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
@@ -100,6 +139,8 @@ MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A)
 							 o.chn_pen_gap, o.chn_pen_skip, is_splice, 1, n_a, a, &n_lc, &u, &n_a_new));
 	}
 	m.n_u0 = n_lc;
+	unsigned long long t1 = prof_clock();
+	prof_add(c, PROF_CHAIN_DP_CYC, t1 - t0);
 	// long-join rescue (reference: map-algo.c:407-417)
 	if (o.bw_long > o.bw && (o.flag & (F_SPLICE | F_SR)) == 0 && n_lc > 1) {
 		int32_t st = (int32_t)a[0].y, en = (int32_t)a[(int32_t)u[0] - 1].y;
@@ -112,6 +153,8 @@ MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A)
 							  o.chn_pen_gap, o.chn_pen_skip, n2, a, &n_lc, &u, &n_a_new));
 		}
 	}
+	unsigned long long t2 = prof_clock();
+	prof_add(c, PROF_CHAIN_RMQ_CYC, t2 - t1);
 	m.n_a = n_lc > 0? n_a_new : 0;
 	m.n_lc = 0;
 	if (n_lc > 0) {
@@ -149,6 +192,7 @@ MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A)
 		for (int32_t i = 0; i < n_lc; ++i) dst[i] = lc[i];
 		m.n_lc = n_lc;
 	}
+	prof_add(c, PROF_CHAIN_POST_CYC, prof_clock() - t2);
 	A.top = mark;
 	return 0;
 }

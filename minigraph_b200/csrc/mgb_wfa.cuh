@@ -1,10 +1,15 @@
-// mgb_wfa.cuh -- global alignment of one inter-anchor gap with the 2-piece affine wavefront algorithm.
+// mgb_wfa.cuh -- global alignment of one inter-anchor gap with the 2-piece affine wavefront algorithm (K8a).
 // (reference: miniwfa.c:380-435 mwf_wfa_core, :281-308 wf_next_tb, :329-377 wf_traceback, :144-171 wf_stripe_shrink)
-// Penalties: mismatch 4, gap1 4+2l, gap2 15+1l.  CIGAR bytes depend on the tie preferences in the recurrence
+// Penalties: mismatch 4, gap1 4+2l, gap2 15+1l.  CIGAR bytes depend on the tie preferences of the recurrence
 // (>= everywhere, E before F, mismatch before gap) and on the traceback state machine; both are kept.
 //
-// Layout: the last max_pen+1 = 17 wavefronts live in fixed slots of the worker arena, five int32 lanes each
-// (H,E1,F1,E2,F2) padded by 17 cells of -inf on both sides; one traceback byte per (score,diagonal).
+// One warp aligns one gap.  Lanes own diagonals in the three data-parallel phases of a score step (exact-match
+// extension, recurrence, traceback-byte store); the scalar bookkeeping ([lo,hi] tracking, iteration counting) is
+// replicated on all lanes; the traceback walk is sequential on lane 0.  Two storage schemes share that skeleton:
+//   wfa_smem<W,..>  wavefront ring in shared memory for windows of at most W diagonals and scores below 255
+//   wfa_exact       ring in the worker arena (global memory), any size, incl. the band re-centring every 256 scores
+// Only one diagonal (d = ql - tl) can reach the end of both sequences, so "the first diagonal that finishes" of the
+// sequential reference needs no ordering between lanes.
 #pragma once
 #include "mgb_common.cuh"
 
@@ -15,17 +20,300 @@ static const int WF_X = 4, WF_O1 = 4, WF_E1 = 2, WF_O2 = 15, WF_E2 = 1;
 static const int WF_MAX_PEN = 16;           // max(x, o1+e1, o2+e2)
 static const int WF_NSLICE = WF_MAX_PEN + 1;
 static const int WF_PAD = WF_MAX_PEN + 1;   // m1 in the reference
+static const int WF_SEQ_PAD = 16;           // sentinel bytes after each staged sequence
+
+#define MGB_WF_MAX(a, b) ((a) >= (b)? (a) : (b))
+
+struct WfResult {
+	int32_t s;        // score, -1 if the iteration cap was hit
+	int32_t n_cigar;
+	int64_t n_iter;
+	uint32_t *cigar;  // len<<4|op  (op: 7 '=', 8 'X', 1 'I', 2 'D'), allocated at the caller's mark
+};
+
+// ---- sequence staging: 4-byte aligned copies followed by sentinel bytes that match nothing ----
+// (the reference pads both strings with two distinct unused characters for the same purpose, miniwfa.c:182-209)
+
+MG_HD inline void wf_stage_seq(char *dst, const char *src, int32_t len, uint8_t sentinel, int lane)
+{
+	for (int32_t i = lane; i < len; i += MGB_W) dst[i] = src[i];
+	for (int32_t i = len + lane; i < len + WF_SEQ_PAD; i += MGB_W) dst[i] = (char)sentinel;
+}
+
+MG_HD inline uint32_t wf_ld32u(const char *base, int32_t pos) // unaligned 32-bit read from an aligned, padded buffer
+{
+	const uint32_t *w = (const uint32_t*)base;
+	uint32_t lo = w[pos >> 2], hi = w[(pos >> 2) + 1];
+	int sh = (pos & 3) << 3;
+#if MGB_ON_DEVICE
+	return __funnelshift_r(lo, hi, sh);
+#else
+	return sh? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+
+// furthest k on diagonal d reachable by exact matches from k (reference: miniwfa.c:212-226 wf_extend1_padded)
+MG_HD inline int32_t wf_extend(const char *ts, const char *qs, int32_t k, int32_t d)
+{
+	for (;;) {
+		uint32_t x = wf_ld32u(ts, k + 1) ^ wf_ld32u(qs, d + k + 1);
+		if (x) {
+#if MGB_ON_DEVICE
+			return k + ((__ffs((int)x) - 1) >> 3);
+#else
+			return k + (__builtin_ctz(x) >> 3);
+#endif
+		}
+		k += 4;
+	}
+}
+
+// ---- traceback (reference: miniwfa.c:329-377 wf_traceback), lane 0 only ----
+// TB::get(s, d) returns the traceback byte of (score s, diagonal d) or -1 if out of range.  Operations are
+// accumulated in registers and written from the back of cig_store, so no reversal pass is needed.
+template<typename TB>
+MG_HD inline int wf_traceback(const TB &tb, int32_t n_scores, int32_t tl, const char *ts, int32_t ql, const char *qs, int32_t last_state,
+							  uint32_t *cig_store, int64_t max_cigar, int32_t *n_cigar, int64_t *first)
+{
+	int32_t i = ql - 1, k = tl - 1, s = n_scores - 1, last = last_state;
+	int64_t w = max_cigar; // next write position is w-1
+	int32_t cur_op = -1, cur_len = 0;
+#define MGB_CIG_PUSH(op_, len_) do { \
+		if (cur_op == (op_)) cur_len += (len_); \
+		else { \
+			if (cur_op >= 0) { if (w <= 0) return MGB_E_INTERNAL; cig_store[--w] = (uint32_t)cur_len << 4 | (uint32_t)cur_op; } \
+			cur_op = (op_), cur_len = (len_); \
+		} \
+	} while (0)
+	while (i >= 0 && k >= 0) {
+		int32_t k0 = k, x, state, ext;
+		if (last == 0) {
+			while (i >= 0 && k >= 0 && qs[i] == ts[k]) --i, --k;
+			if (k0 - k > 0) MGB_CIG_PUSH(7, k0 - k);
+			if (i < 0 || k < 0) break;
+		}
+		if (s < 0) return MGB_E_INTERNAL;
+		x = tb.get(s, i - k);
+		if (x < 0) return MGB_E_INTERNAL;
+		state = last == 0? x & 7 : last;
+		ext = state > 0? x >> (state + 2) & 1 : 0;
+		if (state == 0) { MGB_CIG_PUSH(8, 1); --i, --k, s -= WF_X; }
+		else if (state == 1) { MGB_CIG_PUSH(1, 1); --i, s -= ext? WF_E1 : WF_O1 + WF_E1; }
+		else if (state == 3) { MGB_CIG_PUSH(1, 1); --i, s -= ext? WF_E2 : WF_O2 + WF_E2; }
+		else if (state == 2) { MGB_CIG_PUSH(2, 1); --k, s -= ext? WF_E1 : WF_O1 + WF_E1; }
+		else if (state == 4) { MGB_CIG_PUSH(2, 1); --k, s -= ext? WF_E2 : WF_O2 + WF_E2; }
+		else return MGB_E_INTERNAL;
+		last = state > 0 && ext? state : 0;
+	}
+	if (i >= 0) MGB_CIG_PUSH(1, i + 1);
+	else if (k >= 0) MGB_CIG_PUSH(2, k + 1);
+	if (cur_op >= 0) { if (w <= 0) return MGB_E_INTERNAL; cig_store[--w] = (uint32_t)cur_len << 4 | (uint32_t)cur_op; }
+#undef MGB_CIG_PUSH
+	*n_cigar = (int32_t)(max_cigar - w), *first = w;
+	return 0;
+}
+
+// =================================================================================================================
+// shared-memory scheme
+// =================================================================================================================
+// * H keeps 17 scores, E1/F1 keep 3, E2/F2 keep 2 (the deepest look-backs are o2+e2 = 16, e1 = 2, e2 = 1);
+// * instead of padding every slice with -inf cells, reads are bounds-checked against the per-score [lo,hi]
+//   (warp-uniform scalars), which returns exactly what the reference's padding holds;
+// * diagonals map to columns modulo W, so any window of at most W diagonals fits;
+// * both sequences are staged in shared memory; with TBCAP > 0 the traceback bytes live there too.
+// The scheme gives up (returns 1, nothing written) when the window would exceed W diagonals, the traceback bytes
+// would exceed TBCAP, or the score reaches 255 -- the reference re-centres its band every 256 scores by inspecting
+// all 17 E/F slices (wf_stripe_shrink), which only wfa_exact() keeps -- and the job moves to the next tier.
+
+template<int W, int MAXLEN, int TBCAP>
+struct WfSmemLayout {
+	static const int W_ = W, MAXLEN_ = MAXLEN, TBCAP_ = TBCAP;
+	static const int N_INTS = (17 + 3 + 3 + 2 + 2) * W + 2 * 17 + 2;
+	static const int SEQ_BYTES = (MAXLEN + WF_SEQ_PAD + 3) / 4 * 4;
+	static const int TB_ROW_BYTES = TBCAP > 0? 256 * 8 : 0; // per score: int32 lo, int32 off
+	static const int BYTES = N_INTS * 4 + 2 * SEQ_BYTES + TB_ROW_BYTES + TBCAP;
+	static const int STRIDE = (BYTES + 127) / 128 * 128;
+};
+
+struct WfSrc { const int32_t *p; int32_t lo, hi; }; // one source slice of the recurrence
+
+template<int W>
+MG_HD inline int32_t wfs_col(int32_t d) { return (d + (1 << 20)) & (W - 1); }
+
+template<int W>
+MG_HD inline int32_t wfs_at(const WfSrc &s, int32_t d) { return (d >= s.lo && d <= s.hi)? s.p[wfs_col<W>(d)] : WF_NEG_INF; }
+
+template<int W>
+MG_HD inline WfSrc wfs_src(const int32_t *arr, int nslot, const int32_t *lo, const int32_t *hi, int32_t score)
+{
+	WfSrc s;
+	if (score < 0) { s.p = arr, s.lo = 1, s.hi = 0; return s; }
+	int hs = score % 17;
+	s.p = arr + (score % nslot) * W, s.lo = lo[hs], s.hi = hi[hs];
+	return s;
+}
+
+struct WfTbSmem { // traceback bytes in shared memory: row table {lo, width, off} is packed as lo, off; width from the next row
+	const int32_t *row; const uint8_t *x; int32_t n_rows, used;
+	MG_HD int32_t get(int32_t s, int32_t d) const
+	{
+		int32_t lo = row[2 * s], off = row[2 * s + 1];
+		int32_t end = s + 1 < n_rows? row[2 * s + 3] : used;
+		int32_t j = d - lo;
+		return (j < 0 || off + j >= end)? -1 : (int32_t)x[off + j];
+	}
+};
+
+struct WfTbRow { int32_t lo, hi; uint8_t *x; };
+struct WfTbArena { // traceback rows bump-allocated in the worker arena (reference: miniwfa.c:31-44 wf_tb_add)
+	const WfTbRow *row;
+	MG_HD int32_t get(int32_t s, int32_t d) const
+	{
+		int32_t j = d - row[s].lo;
+		return (j < 0 || j > row[s].hi - row[s].lo)? -1 : (int32_t)row[s].x[j];
+	}
+};
+
+template<int W, int MAXLEN, int TBCAP>
+MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g, int32_t ql, const char *qs_g, WfResult *r, int lane)
+{
+	typedef WfSmemLayout<W, MAXLEN, TBCAP> LY;
+	if (tl > MAXLEN || ql > MAXLEN) return 1;
+	uint64_t mark = A.top;
+	int32_t *H = smem, *E1 = H + 17 * W, *F1 = E1 + 3 * W, *E2 = F1 + 3 * W, *F2 = E2 + 2 * W;
+	int32_t *slo = F2 + 2 * W, *shi = slo + 17;
+	char *ts = (char*)(smem + LY::N_INTS), *qs = ts + LY::SEQ_BYTES;
+	int32_t *tb_row = (int32_t*)(qs + LY::SEQ_BYTES); // TBCAP > 0 only
+	uint8_t *tb_x = (uint8_t*)tb_row + LY::TB_ROW_BYTES;
+	wf_stage_seq(ts, ts_g, tl, 0xfe, lane);
+	wf_stage_seq(qs, qs_g, ql, 0xff, lane);
+	r->s = -1, r->n_cigar = 0, r->n_iter = 0, r->cigar = 0;
+	uint32_t *cig_store;
+	const int64_t max_cigar = (int64_t)tl + ql + 2;
+	MGB_ALLOC(A, cig_store, uint32_t, max_cigar);
+	uint64_t mark_keep = A.top;
+	AVec<WfTbRow> rows; // TBCAP == 0 only
+	avec_init(rows);
+	if (TBCAP == 0) MGB_TRY(avec_reserve_w(A, rows, 256, lane));
+	int32_t n_rows = 0, tb_used = 0;
+	int32_t wlo = 0, whi = 0, last_state = 0, s = 0;
+	if (lane == 0) {
+		slo[0] = 0, shi[0] = 0;
+		H[wfs_col<W>(0)] = -1;
+		E1[wfs_col<W>(0)] = F1[wfs_col<W>(0)] = E2[wfs_col<W>(0)] = F2[wfs_col<W>(0)] = WF_NEG_INF;
+	}
+	warp_sync();
+	for (;;) {
+		const int hs = s % 17;
+		const int32_t plo = slo[hs], phi = shi[hs];
+		int32_t *Hs = H + hs * W;
+		int hit = 0, hit_noext = 0;
+		for (int32_t d = plo + lane; d <= phi; d += MGB_W) {
+			int32_t k0 = Hs[wfs_col<W>(d)];
+			if (k0 < -1 || d + k0 < -1 || k0 >= tl || d + k0 >= ql) continue;
+			int32_t k = wf_extend(ts, qs, k0, d);
+			if (k == tl - 1 && d + k == ql - 1) hit = 1, hit_noext = (k == k0);
+			else Hs[wfs_col<W>(d)] = k;
+		}
+		warp_sync();
+		if (warp_any(hit)) {
+			if (warp_any(hit && hit_noext)) { // no extension on the last diagonal: the state comes from the traceback byte
+				int32_t x;
+				if (TBCAP > 0) { WfTbSmem t; t.row = tb_row, t.x = tb_x, t.n_rows = n_rows, t.used = tb_used; x = t.get(n_rows - 1, ql - tl); }
+				else { WfTbArena t; t.row = rows.a; x = t.get(n_rows - 1, ql - tl); }
+				last_state = x & 7;
+			}
+			break;
+		}
+		const int32_t lo = wlo > -tl? wlo - 1 : -tl;
+		const int32_t hi = whi < ql? whi + 1 : ql;
+		const int32_t width = hi - lo + 1;
+		if (width > W || s + 1 >= 255 || (TBCAP > 0 && tb_used + width > TBCAP)) { A.top = mark; return 1; }
+		const int32_t ns = s + 1, nhs = ns % 17;
+		uint8_t *ax;
+		if (TBCAP > 0) {
+			if (lane == 0) tb_row[2 * n_rows] = lo, tb_row[2 * n_rows + 1] = tb_used;
+			ax = tb_x + tb_used - lo;
+			tb_used += width;
+		} else {
+			MGB_TRY(avec_reserve_w(A, rows, n_rows + 1, lane));
+			uint8_t *x;
+			MGB_ALLOC(A, x, uint8_t, width);
+			if (lane == 0) rows.a[n_rows].lo = lo, rows.a[n_rows].hi = hi, rows.a[n_rows].x = x;
+			rows.n = n_rows + 1;
+			ax = x - lo;
+		}
+		++n_rows;
+		const WfSrc sHx = wfs_src<W>(H, 17, slo, shi, ns - WF_X), sHo1 = wfs_src<W>(H, 17, slo, shi, ns - (WF_O1 + WF_E1)),
+					sHo2 = wfs_src<W>(H, 17, slo, shi, ns - (WF_O2 + WF_E2)), sE1 = wfs_src<W>(E1, 3, slo, shi, ns - WF_E1),
+					sF1 = wfs_src<W>(F1, 3, slo, shi, ns - WF_E1), sE2 = wfs_src<W>(E2, 2, slo, shi, ns - WF_E2), sF2 = wfs_src<W>(F2, 2, slo, shi, ns - WF_E2);
+		int32_t *nH = H + nhs * W, *nE1 = E1 + (ns % 3) * W, *nF1 = F1 + (ns % 3) * W, *nE2 = E2 + (ns % 2) * W, *nF2 = F2 + (ns % 2) * W;
+		for (int32_t d = lo + lane; d <= hi; d += MGB_W) { // reference: miniwfa.c:281-308 wf_next_tb
+			int32_t h, f, e, e1, e2, f1, f2, a0, b0;
+			uint8_t x = 0, ze, zf, z;
+			a0 = wfs_at<W>(sHo1, d - 1), b0 = wfs_at<W>(sE1, d - 1);
+			x |= a0 >= b0? 0 : 0x08; e1 = MGB_WF_MAX(a0, b0);
+			a0 = wfs_at<W>(sHo2, d - 1), b0 = wfs_at<W>(sE2, d - 1);
+			x |= a0 >= b0? 0 : 0x20; e2 = MGB_WF_MAX(a0, b0);
+			ze = e1 >= e2? 1 : 3;
+			e = MGB_WF_MAX(e1, e2);
+			a0 = wfs_at<W>(sHo1, d + 1), b0 = wfs_at<W>(sF1, d + 1);
+			x |= a0 >= b0? 0 : 0x10; f1 = MGB_WF_MAX(a0, b0) + 1;
+			a0 = wfs_at<W>(sHo2, d + 1), b0 = wfs_at<W>(sF2, d + 1);
+			x |= a0 >= b0? 0 : 0x40; f2 = MGB_WF_MAX(a0, b0) + 1;
+			zf = f1 >= f2? 2 : 4;
+			f = MGB_WF_MAX(f1, f2);
+			z = e >= f? ze : zf;
+			h = MGB_WF_MAX(e, f);
+			a0 = wfs_at<W>(sHx, d) + 1;
+			z = a0 >= h? 0 : z;
+			h = MGB_WF_MAX(a0, h);
+			const int32_t c = wfs_col<W>(d);
+			nE1[c] = e1, nF1[c] = f1, nE2[c] = e2, nF2[c] = f2, nH[c] = h; // slots of score ns are not read in this loop
+			ax[d] = x | z;
+		}
+		if (lane == 0) slo[nhs] = lo, shi[nhs] = hi;
+		s = ns;
+		warp_sync();
+		{
+			const int32_t cl = wfs_col<W>(lo), ch = wfs_col<W>(hi);
+			if (nH[cl] >= -1 || nE1[cl] >= -1 || nF1[cl] >= -1 || nE2[cl] >= -1 || nF2[cl] >= -1) wlo = lo;
+			if (nH[ch] >= -1 || nE1[ch] >= -1 || nF1[ch] >= -1 || nE2[ch] >= -1 || nF2[ch] >= -1) whi = hi;
+		}
+		r->n_iter += width;
+	}
+	r->s = s;
+	{
+		int rc = 0;
+		int32_t n_cig = 0;
+		int64_t first = 0;
+		if (lane == 0) {
+			if (TBCAP > 0) { WfTbSmem t; t.row = tb_row, t.x = tb_x, t.n_rows = n_rows, t.used = tb_used; rc = wf_traceback(t, n_rows, tl, ts, ql, qs, last_state, cig_store, max_cigar, &n_cig, &first); }
+			else { WfTbArena t; t.row = rows.a; rc = wf_traceback(t, n_rows, tl, ts, ql, qs, last_state, cig_store, max_cigar, &n_cig, &first); }
+		}
+		rc = warp_bcast_i32(rc, 0), n_cig = warp_bcast_i32(n_cig, 0), first = (int64_t)warp_bcast_u64((uint64_t)first, 0);
+		warp_sync();
+		if (rc < 0) { A.top = mark; return rc; }
+		r->n_cigar = n_cig, r->cigar = cig_store + first;
+	}
+	A.top = mark_keep;
+	return 0;
+}
+
+// =================================================================================================================
+// general scheme: ring in the worker arena, mirrors the reference's memory layout
+// =================================================================================================================
+// The last max_pen+1 = 17 wavefronts live in fixed slots of the arena, five int32 lanes each (H,E1,F1,E2,F2) padded
+// by 17 cells of -inf on both sides.
 
 struct WfSlice {
 	int32_t lo, hi;
 	int32_t *H, *E1, *F1, *E2, *F2; // indexable by diagonal d in [lo-PAD, hi+PAD]
 };
 
-struct WfTb1 { int32_t lo, hi; int64_t off; };
-
 struct WfState {
 	WfSlice sl[WF_NSLICE];
-	int32_t *mem;       // WF_NSLICE slots
+	int32_t *mem;        // WF_NSLICE slots
 	int64_t slot_stride; // int32 elements per slot
 	int64_t lane_stride; // int32 elements per lane inside a slot
 	int32_t s, top, lo, hi;
@@ -100,8 +388,6 @@ MG_HD inline int wf_stripe_shrink(WfState &wf, int32_t tl, int32_t ql)
 	return 0;
 }
 
-#define MGB_WF_MAX(a, b) ((a) >= (b)? (a) : (b))
-
 // one cell of the recurrence with its traceback byte (reference: miniwfa.c:281-308 wf_next_tb)
 MG_HD inline uint8_t wf_cell(int32_t d, int32_t *H, int32_t *E1, int32_t *F1, int32_t *E2, int32_t *F2,
 							 const int32_t *pHx, const int32_t *pHo1, const int32_t *pHo2,
@@ -129,98 +415,31 @@ MG_HD inline uint8_t wf_cell(int32_t d, int32_t *H, int32_t *E1, int32_t *F1, in
 	return x | z;
 }
 
-struct WfResult {
-	int32_t s;        // score, -1 if the iteration cap was hit
-	int32_t n_cigar;
-	int64_t n_iter;
-	uint32_t *cigar;  // len<<4|op  (op: 7 '=', 8 'X', 1 'I', 2 'D'), allocated at the caller's mark
-};
-
-MG_HD inline int wf_cigar_push1(Arena &A, AVec<uint32_t> &c, int32_t op, int32_t len)
-{
-	if (c.n && (uint32_t)op == (c.a[c.n-1] & 0xf)) c.a[c.n-1] += (uint32_t)len << 4;
-	else {
-		uint32_t x = (uint32_t)len << 4 | (uint32_t)op;
-		MGB_TRY(avec_push(A, c, x));
-	}
-	return 0;
-}
-
-// sequential traceback on one lane; writes the CIGAR in input order to cig_store
-MG_HD inline int wf_traceback_lane0(Arena &A, int32_t tl, const char *ts, int32_t ql, const char *qs, const AVec<WfTb1> &tb, const AVec<uint8_t> &tbx,
-									int32_t last_state, uint32_t *cig_store, int64_t max_cigar, int32_t *n_cigar)
-{
-	AVec<uint32_t> cigar;
-	avec_init(cigar);
-	int32_t i = ql - 1, k = tl - 1, s = (int32_t)tb.n - 1, last = last_state;
-	while (i >= 0 && k >= 0) {
-		int32_t k0 = k, j, x, state, ext;
-		if (last == 0) {
-			while (i >= 0 && k >= 0 && qs[i] == ts[k]) --i, --k;
-			if (k0 - k > 0) MGB_TRY(wf_cigar_push1(A, cigar, 7, k0 - k));
-			if (i < 0 || k < 0) break;
-		}
-		if (s < 0) return MGB_E_INTERNAL;
-		j = i - k - tb.a[s].lo;
-		if (j < 0 || j > tb.a[s].hi - tb.a[s].lo) return MGB_E_INTERNAL;
-		x = tbx.a[tb.a[s].off + j];
-		state = last == 0? x & 7 : last;
-		ext = state > 0? x >> (state + 2) & 1 : 0;
-		if (state == 0) {
-			MGB_TRY(wf_cigar_push1(A, cigar, 8, 1));
-			--i, --k, s -= WF_X;
-		} else if (state == 1) {
-			MGB_TRY(wf_cigar_push1(A, cigar, 1, 1));
-			--i, s -= ext? WF_E1 : WF_O1 + WF_E1;
-		} else if (state == 3) {
-			MGB_TRY(wf_cigar_push1(A, cigar, 1, 1));
-			--i, s -= ext? WF_E2 : WF_O2 + WF_E2;
-		} else if (state == 2) {
-			MGB_TRY(wf_cigar_push1(A, cigar, 2, 1));
-			--k, s -= ext? WF_E1 : WF_O1 + WF_E1;
-		} else if (state == 4) {
-			MGB_TRY(wf_cigar_push1(A, cigar, 2, 1));
-			--k, s -= ext? WF_E2 : WF_O2 + WF_E2;
-		} else return MGB_E_INTERNAL;
-		last = state > 0 && ext? state : 0;
-	}
-	if (i >= 0) MGB_TRY(wf_cigar_push1(A, cigar, 1, i + 1));
-	else if (k >= 0) MGB_TRY(wf_cigar_push1(A, cigar, 2, k + 1));
-	if (cigar.n > max_cigar) return MGB_E_INTERNAL;
-	for (int64_t c = 0; c < cigar.n; ++c) cig_store[c] = cigar.a[cigar.n - 1 - c]; // back to input order
-	*n_cigar = (int32_t)cigar.n;
-	return 0;
-}
-
-// Exact WFA with traceback (reference: miniwfa.c:380-435 + :603-615 with opt.step == 0).
-// ts/qs need not be padded: the extension loop checks the sequence ends explicitly, which is what the reference's
-// distinct padding characters achieve (miniwfa.c:182-226).
-//
-// Warp-uniform: all lanes enter with identical arguments and identical arena state.  Lanes own diagonals
-// (d = lo + lane, + 32, ...) in the three data-parallel phases of a score step -- pad initialisation, exact-match
-// extension, and the recurrence -- while the scalar bookkeeping (ring of 17 wavefronts, [lo,hi] tracking, the
-// every-256-scores shrink, iteration counting) is replicated.  The traceback is sequential and runs on lane 0.
-// Only one diagonal (d = ql - tl) can reach the end of both sequences, so "first diagonal that finishes" of the
-// sequential reference needs no ordering between lanes.
-MG_HD inline int wfa_exact(Arena &A, int32_t tl, const char *ts, int32_t ql, const char *qs, int64_t max_iter, WfResult *r, int lane)
+// Exact WFA with traceback for any size (reference: miniwfa.c:380-435 + :603-615 with opt.step == 0).
+MG_HD inline int wfa_exact(Arena &A, int32_t tl, const char *ts_g, int32_t ql, const char *qs_g, int64_t max_iter, WfResult *r, int lane)
 {
 	uint64_t mark = A.top;
 	WfState wf;
 	int32_t last_state = 0, stopped = 0;
 	r->s = -1, r->n_cigar = 0, r->n_iter = 0, r->cigar = 0;
-	// the CIGAR is built bottom-up at the caller's mark after the scratch is released; reserve its worst case first
 	uint32_t *cig_store;
 	const int64_t max_cigar = (int64_t)tl + ql + 2;
 	MGB_ALLOC(A, cig_store, uint32_t, max_cigar);
 	uint64_t mark_keep = A.top;
+	char *ts, *qs;
+	MGB_ALLOC(A, ts, char, tl + WF_SEQ_PAD + 4);
+	MGB_ALLOC(A, qs, char, ql + WF_SEQ_PAD + 4);
+	wf_stage_seq(ts, ts_g, tl, 0xfe, lane);
+	wf_stage_seq(qs, qs_g, ql, 0xff, lane);
 	{
 		int64_t maxw = (int64_t)tl + ql + 1;
 		wf.lane_stride = maxw + 2 * WF_PAD;
 		wf.slot_stride = 5 * wf.lane_stride;
 		MGB_ALLOC(A, wf.mem, int32_t, wf.slot_stride * WF_NSLICE);
 	}
-	AVec<WfTb1> tb; AVec<uint8_t> tbx;
-	avec_init(tb), avec_init(tbx);
+	AVec<WfTbRow> rows;
+	avec_init(rows);
+	MGB_TRY(avec_reserve_w(A, rows, 1024, lane));
 	// reference: miniwfa.c:103-121 wf_stripe_init
 	wf.s = 0, wf.top = 0, wf.lo = wf.hi = 0;
 	for (int i = 0; i < WF_NSLICE; ++i) {
@@ -236,17 +455,17 @@ MG_HD inline int wfa_exact(Arena &A, int32_t tl, const char *ts, int32_t ql, con
 		int32_t lo, hi, *H = p->H;
 		int hit = 0, hit_noext = 0;
 		for (int32_t d = p->lo + lane; d <= p->hi; d += MGB_W) { // extension along exact matches
-			int32_t k = H[d], k0 = k;
-			if (k < -1 || d + k < -1 || k >= tl || d + k >= ql) continue;
-			while (k + 1 < tl && d + k + 1 < ql && ts[k + 1] == qs[d + k + 1]) ++k;
+			int32_t k0 = H[d];
+			if (k0 < -1 || d + k0 < -1 || k0 >= tl || d + k0 >= ql) continue;
+			int32_t k = wf_extend(ts, qs, k0, d);
 			if (k == tl - 1 && d + k == ql - 1) hit = 1, hit_noext = (k == k0);
 			else H[d] = k;
 		}
 		warp_sync();
 		if (warp_any(hit)) {
 			if (warp_any(hit && hit_noext)) {
-				const WfTb1 &t1 = tb.a[tb.n - 1];
-				last_state = tbx.a[t1.off + ((ql - tl) - t1.lo)] & 7;
+				WfTbArena t; t.row = rows.a;
+				last_state = t.get((int32_t)rows.n - 1, ql - tl) & 7;
 			}
 			break;
 		}
@@ -259,14 +478,12 @@ MG_HD inline int wfa_exact(Arena &A, int32_t tl, const char *ts, int32_t ql, con
 			const WfSlice &fo2 = wf_stripe_get(wf, WF_O2 + WF_E2);
 			const WfSlice &fe1 = wf_stripe_get(wf, WF_E1);
 			const WfSlice &fe2 = wf_stripe_get(wf, WF_E2);
-			WfTb1 t1;
-			t1.lo = lo, t1.hi = hi, t1.off = tbx.n;
-			MGB_TRY(avec_reserve_w(A, tb, tb.n + 1, lane));
-			if (lane == 0) tb.a[tb.n] = t1;
-			++tb.n;
-			MGB_TRY(avec_reserve_w(A, tbx, tbx.n + (hi - lo + 1), lane));
-			uint8_t *ax = tbx.a + tbx.n - lo;
-			tbx.n += hi - lo + 1;
+			MGB_TRY(avec_reserve_w(A, rows, rows.n + 1, lane));
+			uint8_t *x;
+			MGB_ALLOC(A, x, uint8_t, hi - lo + 1);
+			if (lane == 0) rows.a[rows.n].lo = lo, rows.a[rows.n].hi = hi, rows.a[rows.n].x = x;
+			++rows.n;
+			uint8_t *ax = x - lo;
 			for (int32_t dd = lo + lane; dd <= hi; dd += MGB_W)
 				ax[dd] = wf_cell(dd, ft.H, ft.E1, ft.F1, ft.E2, ft.F2, fx.H, fo1.H, fo2.H, fe1.E1, fe1.F1, fe2.E2, fe2.F2);
 			warp_sync();
@@ -278,19 +495,25 @@ MG_HD inline int wfa_exact(Arena &A, int32_t tl, const char *ts, int32_t ql, con
 		if (max_iter > 0 && r->n_iter > max_iter) { stopped = 1; break; }
 	}
 	r->s = stopped? -1 : wf.s;
-	if (!stopped) { // reference: miniwfa.c:329-377 wf_traceback (lane 0; the outcome is broadcast)
+	if (!stopped) {
 		int rc = 0;
 		int32_t n_cig = 0;
+		int64_t first = 0;
 		if (lane == 0) {
-			rc = wf_traceback_lane0(A, tl, ts, ql, qs, tb, tbx, last_state, cig_store, max_cigar, &n_cig);
+			WfTbArena t; t.row = rows.a;
+			rc = wf_traceback(t, (int32_t)rows.n, tl, ts, ql, qs, last_state, cig_store, max_cigar, &n_cig, &first);
 		}
-		rc = warp_bcast_i32(rc, 0), n_cig = warp_bcast_i32(n_cig, 0);
+		rc = warp_bcast_i32(rc, 0), n_cig = warp_bcast_i32(n_cig, 0), first = (int64_t)warp_bcast_u64((uint64_t)first, 0);
 		warp_sync();
 		if (rc < 0) { A.top = mark; return rc; }
-		r->n_cigar = n_cig, r->cigar = cig_store;
+		r->n_cigar = n_cig, r->cigar = cig_store + first;
 	}
 	A.top = mark_keep;
 	return 0;
 }
+
+// the tiers of the job kernels (K8a)
+typedef WfSmemLayout<64, 256, 4096> WfTier1;   // small gaps: 4 warps per block, traceback bytes in shared memory
+typedef WfSmemLayout<256, 1024, 0> WfTier2;    // mid-size gaps: 2 warps per block, traceback rows in the arena
 
 } // namespace mgb

@@ -182,9 +182,9 @@ def gaf_with_engine(lib, gfa_path, names, seqs, preset="lr", cigar=True, flag_ex
     gcs = (C.POINTER(capi.mg_gchains_t) * n)()
     rc = lib.mg_map_batch(gi, n, qlens, cseqs, cnames, gcs, C.byref(mo))
     assert rc == 0, (rc, lib.mgb_last_error())
-    buf, ln, cap = C.c_void_p(0), C.c_size_t(0), C.c_size_t(0)
+    buf, ln = C.c_void_p(0), C.c_size_t(0)
+    lib.mgb_write_gaf_batch(g, n, gcs, qlens, cnames, mo.flag, 0, C.byref(buf), C.byref(ln))
     for i in range(n):
-        lib.mgb_write_gaf(C.byref(buf), C.byref(ln), C.byref(cap), g, gcs[i], len(seqs[i]), names[i], mo.flag)
         lib.mg_gchain_free(gcs[i])
     text = C.string_at(buf, ln.value) if buf else b""
     C.CDLL(None).free(buf)
