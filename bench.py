@@ -151,6 +151,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = capi.load_product()
     lib.mgb_set_param(b"device", local_rank)
+    for kv in os.environ.get("MGB_PARAMS", "").split(","):
+        if "=" in kv:
+            lib.mgb_set_param(kv.split("=")[0].encode(), int(kv.split("=")[1], 0))
     gfa, fa = make_workload(tmp, rank, a.reads)
     names, seqs = read_fasta(fa)
     n = len(seqs)

@@ -162,6 +162,14 @@ const uint64_t *mg_idx_get(const mg_idx_t *gi, uint64_t minier, int *n);
 /* replaces index.c:74-93 mg_idx_cal_quantile() */
 void mg_idx_cal_quantile(const mg_idx_t *gi, int32_t m, float f[], int32_t q[]);
 
+/* replaces index.c:108-113 mg_idx_hfree(): the one other index.c symbol the remaining host files reference
+ * (shortk.c:191, always with a NULL handle); a no-op here */
+void mg_idx_hfree(void *h);
+
+/* replaces index.c:108-113 mg_idx_hfree(): the one other index.c symbol the remaining host files reference
+ * (shortk.c:191, always with a NULL handle); a no-op here */
+void mg_idx_hfree(void *h);
+
 /* replace map-algo.c:14-27 mg_tbuf_init()/mg_tbuf_destroy(): the per-thread arena becomes a handle without state */
 mg_tbuf_t *mg_tbuf_init(void);
 void mg_tbuf_destroy(mg_tbuf_t *b);

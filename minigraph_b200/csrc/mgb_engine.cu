@@ -36,6 +36,7 @@ static int64_t p_workers_per_sm = 32;
 static int64_t p_device = 0;
 static int64_t p_block_warps = 4;
 static int64_t p_host_threads = 0; // 0: min(16, hardware threads)
+static int64_t p_thread_mask = 0;      // bit s set: stage s runs one item per thread instead of one per warp
 
 extern "C" const char *mgb_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char *mgb_version(void) { return "mgb200-r1"; }
@@ -47,6 +48,7 @@ extern "C" int mgb_set_param(const char *key, int64_t value)
 	else if (!strcmp(key, "device")) p_device = value;
 	else if (!strcmp(key, "block_warps")) p_block_warps = value;
 	else if (!strcmp(key, "host_threads")) p_host_threads = value;
+	else if (!strcmp(key, "thread_mask")) p_thread_mask = value;
 	else return -1;
 	return 0;
 }
@@ -62,6 +64,7 @@ static void dfree(void *p) { free(p); }
 static void h2d(void *d, const void *h, size_t n) { if (n) memcpy(d, h, n); }
 static void d2h(void *h, const void *d, size_t n) { if (n) memcpy(h, d, n); }
 static void dzero(void *d, size_t n) { if (n) memset(d, 0, n); }
+static void dfill(void *d, int v, size_t n) { if (n) memset(d, v, n); }
 static void dsync() {}
 static int dev_sm_count() { return 2; }
 static size_t dev_free_mem() { return (size_t)8 << 30; }
@@ -79,6 +82,7 @@ static void dfree(void *p) { if (p) cudaFree(p); }
 static void h2d(void *d, const void *h, size_t n) { if (n) CUDA_OK(cudaMemcpy(d, h, n, cudaMemcpyHostToDevice)); }
 static void d2h(void *h, const void *d, size_t n) { if (n) CUDA_OK(cudaMemcpy(h, d, n, cudaMemcpyDeviceToHost)); }
 static void dzero(void *d, size_t n) { if (n) CUDA_OK(cudaMemset(d, 0, n)); }
+static void dfill(void *d, int v, size_t n) { if (n) CUDA_OK(cudaMemset(d, v, n)); }
 static void dsync() { CUDA_OK(cudaDeviceSynchronize()); }
 static int dev_sm_count() { int v = 0; CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, (int)p_device)); return v; }
 static size_t dev_free_mem() { size_t f = 0, t = 0; CUDA_OK(cudaMemGetInfo(&f, &t)); return f; }
@@ -150,6 +154,7 @@ struct LaunchArgs {
 	uint64_t arena_bytes;
 	uint64_t *arena_peak;    // per worker
 	int64_t job_start;       // first job of this launch (stage 4)
+	int thread_mode;         // 1: one item per thread (stage_loop_thread)
 	// segment sketch (index build)
 	Pool *pool_mz; u128 *mz;
 };
@@ -157,6 +162,7 @@ struct LaunchArgs {
 // stages: 0 seed (K1-K3), 1 chain (K4/K5), 2 gchain + alignment plan (K6/K7), 3 segment sketch for the index,
 //         4/6/7 WFA jobs tier 1/2/3 (K8a, warp-cooperative), 5 finish: CIGAR stitching + ds + result blob (K8b)
 #define MGB_IS_WFA(STAGE) ((STAGE) == 4 || (STAGE) == 6 || (STAGE) == 7)
+#define MGB_IS_WARP(STAGE) (MGB_IS_WFA(STAGE) || (STAGE) == 8) // stages entered by all lanes of the warp
 template<int STAGE>
 MG_HD inline int run_stage(const LaunchArgs &L, int item, Arena &A, int lane, int32_t *smem)
 {
@@ -164,6 +170,8 @@ MG_HD inline int run_stage(const LaunchArgs &L, int item, Arena &A, int lane, in
 	if (STAGE == 1) return stage_chain(L.c, item, A);
 	if (STAGE == 2) return stage_gchain(L.c, L.routs, item, A);
 	if (STAGE == 5) return stage_finish(L.c, L.routs, item, A);
+	if (STAGE == 8) return gwfa_job_run(A, L.c, L.job_start + item, lane, smem);
+	if (STAGE == 9) return stage_gchain_gen(L.c, L.routs, item, A);
 	if (STAGE == 4) return wfa_job_run(A, L.c, L.job_start + item, lane, smem, 1);
 	if (STAGE == 6) return wfa_job_run(A, L.c, L.c.jobq[0][item], lane, smem, 2);
 	if (STAGE == 7) return wfa_job_run(A, L.c, L.c.jobq[1][item], lane, smem, 3);
@@ -194,9 +202,9 @@ MG_HD inline void stage_fail(const LaunchArgs &L, int item, int rc)
 #endif
 		return;
 	}
-	int rid = STAGE == 4? L.c.jobs[L.job_start + item].rid : STAGE == 6? L.c.jobs[L.c.jobq[0][item]].rid : STAGE == 7? L.c.jobs[L.c.jobq[1][item]].rid : item;
+	int rid = STAGE == 8? L.c.gjobs[L.job_start + item].rid : STAGE == 4? L.c.jobs[L.job_start + item].rid : STAGE == 6? L.c.jobs[L.c.jobq[0][item]].rid : STAGE == 7? L.c.jobs[L.c.jobq[1][item]].rid : item;
 	L.c.meta[rid].status = rc; // benign race between jobs of one read: any negative code triggers the redo
-	if (STAGE == 2 || MGB_IS_WFA(STAGE) || STAGE == 5) L.routs[rid].status = rc;
+	if (STAGE == 2 || MGB_IS_WARP(STAGE) || STAGE == 5 || STAGE == 9) L.routs[rid].status = rc;
 }
 
 #ifndef MGB_HOSTSIM
@@ -211,7 +219,7 @@ __device__ __forceinline__ void stage_loop(const LaunchArgs &L)
 	Arena A;
 	arena_init(A, L.arena_base + (uint64_t)worker * L.arena_bytes, L.arena_bytes);
 	extern __shared__ int4 dyn_smem[];
-	const int smem_stride = STAGE == 4? WfTier1::STRIDE : STAGE == 6? WfTier2::STRIDE : 0;
+	const int smem_stride = STAGE == 4? WfTier1::STRIDE : STAGE == 6? WfTier2::STRIDE : STAGE == 8? GWFA_SMEM_ARENA : 0;
 	int32_t *smem = smem_stride? (int32_t*)((char*)dyn_smem + (size_t)(threadIdx.x >> 5) * smem_stride) : 0;
 	for (;;) {
 		int item = 0;
@@ -219,7 +227,7 @@ __device__ __forceinline__ void stage_loop(const LaunchArgs &L)
 		item = __shfl_sync(0xffffffffu, item, 0);
 		if (item >= L.n_work) break;
 		if (L.rid_list) item = L.rid_list[item];
-		if (MGB_IS_WFA(STAGE)) {
+		if (MGB_IS_WARP(STAGE)) {
 			A.top = 0;
 			int rc = run_stage<STAGE>(L, item, A, lane, smem);
 			if (rc < 0 && lane == 0) stage_fail<STAGE>(L, item, rc);
@@ -233,18 +241,42 @@ __device__ __forceinline__ void stage_loop(const LaunchArgs &L)
 	if (lane == 0 && L.arena_peak) L.arena_peak[worker] = A.peak > L.arena_peak[worker]? A.peak : L.arena_peak[worker];
 }
 
+// Thread-per-item variant for the stages whose control flow is sequential: every THREAD pulls its own item and owns
+// 1/32 of the warp's arena.  The 32 lanes of a warp diverge completely, but the hardware interleaves the diverged
+// lanes, so 32x more items are in flight per warp and their memory latencies overlap.
+template<int STAGE>
+__device__ __forceinline__ void stage_loop_thread(const LaunchArgs &L)
+{
+	const int lane = threadIdx.x & 31;
+	const int worker = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+	const uint64_t sub = (L.arena_bytes / 32) & ~(uint64_t)15;
+	Arena A;
+	arena_init(A, L.arena_base + (uint64_t)worker * L.arena_bytes + (uint64_t)lane * sub, sub);
+	for (;;) {
+		int item = (int)atomicAdd(L.c.next_read, 1u);
+		if (item >= L.n_work) break;
+		if (L.rid_list) item = L.rid_list[item];
+		A.top = 0;
+		int rc = run_stage<STAGE>(L, item, A, -1, 0);
+		if (rc < 0) stage_fail<STAGE>(L, item, rc);
+	}
+	if (L.arena_peak) atomicMax((unsigned long long*)&L.arena_peak[worker], (unsigned long long)A.peak);
+}
+
 // named entry points (one per stage, so that profiles read well); blocks of 4 warps, MINB blocks per SM wanted
-#define MGB_KERNEL(name, STAGE, MINB) __global__ void __launch_bounds__(128, MINB) name(LaunchArgs L) { stage_loop<STAGE>(L); }
+#define MGB_KERNEL(name, STAGE, MINB) __global__ void __launch_bounds__(128, MINB) name(LaunchArgs L) { if (L.thread_mode) stage_loop_thread<STAGE>(L); else stage_loop<STAGE>(L); }
 MGB_KERNEL(k_seed, 0, 8)          // K1-K3: sketch, index lookup, seed sort
 MGB_KERNEL(k_chain, 1, 8)         // K4/K5: linear chaining
-MGB_KERNEL(k_gchain, 2, 4)        // K6/K7: graph chaining, bridging, alignment plan
+MGB_KERNEL(k_gchain, 2, 4)        // K6: graph chaining DP + k-shortest walks, overlap resolution, bridging plan
+MGB_KERNEL(k_gwfa, 8, 4)          // K7a: bridging alignments (graph wavefront), one warp per bridge
+MGB_KERNEL(k_gchain_gen, 9, 4)    // K7b: graph-chain materialisation, post filters, mapq, alignment plan
 MGB_KERNEL(k_index_sketch, 3, 8)  // index build: sketch of graph segments
 MGB_KERNEL(k_wfa_small, 4, 4)     // K8a tier 1: small gaps, wavefronts + traceback bytes in shared memory
 MGB_KERNEL(k_wfa_mid, 6, 3)       // K8a tier 2: mid-size gaps, wavefronts in shared memory (blocks of 2 warps)
 MGB_KERNEL(k_wfa_big, 7, 4)       // K8a tier 3: anything else, wavefronts in the worker arena
 MGB_KERNEL(k_finish, 5, 8)        // K8b: CIGAR stitching, ds strings, result blobs
-static const int STAGE_MINB[8] = { 8, 8, 4, 8, 4, 8, 3, 4 };
-static const int STAGE_WARPS[8] = { 4, 4, 4, 4, 4, 4, 2, 4 };
+static const int STAGE_MINB[10] = { 8, 8, 4, 8, 4, 8, 3, 4, 4, 4 };
+static const int STAGE_WARPS[10] = { 4, 4, 4, 4, 4, 4, 2, 4, 4, 4 };
 template<int STAGE> struct StageKernel;
 template<> struct StageKernel<0> { static void (*get())(LaunchArgs) { return k_seed; } };
 template<> struct StageKernel<1> { static void (*get())(LaunchArgs) { return k_chain; } };
@@ -253,6 +285,8 @@ template<> struct StageKernel<3> { static void (*get())(LaunchArgs) { return k_i
 template<> struct StageKernel<4> { static void (*get())(LaunchArgs) { return k_wfa_small; } };
 template<> struct StageKernel<6> { static void (*get())(LaunchArgs) { return k_wfa_mid; } };
 template<> struct StageKernel<7> { static void (*get())(LaunchArgs) { return k_wfa_big; } };
+template<> struct StageKernel<8> { static void (*get())(LaunchArgs) { return k_gwfa; } };
+template<> struct StageKernel<9> { static void (*get())(LaunchArgs) { return k_gchain_gen; } };
 template<> struct StageKernel<5> { static void (*get())(LaunchArgs) { return k_finish; } };
 #endif
 
@@ -276,7 +310,7 @@ static void launch_stage(LaunchArgs &L, const Workers &W)
 	for (int it = 0; it < L.n_work; ++it) {
 		int item = L.rid_list? L.rid_list[it] : it;
 		A.top = 0;
-		int rc = run_stage<STAGE>(L, item, A, 0, MGB_IS_WFA(STAGE)? sim_smem.data() : 0);
+		int rc = run_stage<STAGE>(L, item, A, 0, MGB_IS_WARP(STAGE)? sim_smem.data() : 0);
 		if (rc < 0) stage_fail<STAGE>(L, item, rc);
 	}
 	if (W.peak && A.peak > W.peak[0]) W.peak[0] = A.peak;
@@ -285,9 +319,12 @@ static void launch_stage(LaunchArgs &L, const Workers &W)
 	int want = dev_sm_count() * STAGE_MINB[STAGE] * warps; // resident warps this stage can keep on the chip
 	int n_w = std::min(W.n_workers, want);
 	int blocks = std::max(1, n_w / warps);
-	size_t smem = STAGE == 4? (size_t)warps * WfTier1::STRIDE : STAGE == 6? (size_t)warps * WfTier2::STRIDE : 0;
+	size_t smem = STAGE == 4? (size_t)warps * WfTier1::STRIDE : STAGE == 6? (size_t)warps * WfTier2::STRIDE : STAGE == 8? (size_t)warps * GWFA_SMEM_ARENA : 0;
 	void (*kern)(LaunchArgs) = StageKernel<STAGE>::get();
 	if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	L.thread_mode = (p_thread_mask >> STAGE) & 1;
+	if (MGB_IS_WFA(STAGE)) L.thread_mode = 0;
+	if (L.thread_mode) smem = 0;
 	kern<<<blocks, threads, smem>>>(L);
 	CUDA_OK(cudaGetLastError());
 #endif
@@ -319,7 +356,7 @@ struct Model {
 	mgb_stats_t stats;
 	gfa_edseq_t *es;
 	// grow-only buffers reused by every batch
-	GrowBuf h_seq{true}, h_out{true}, d_seq, d_meta, d_routs, d_small, d_jobq, d_pool[7];
+	GrowBuf h_seq{true}, h_out{true}, d_seq, d_meta, d_routs, d_small, d_jobq, d_pool[10];
 };
 
 static void model_free(Model *M)
@@ -331,7 +368,7 @@ static void model_free(Model *M)
 	if (M->Wbig.peak) dfree(M->Wbig.peak);
 	if (M->d_logf) dfree(M->d_logf);
 	M->h_seq.release(), M->h_out.release(), M->d_seq.release(), M->d_meta.release(), M->d_routs.release(), M->d_small.release(), M->d_jobq.release();
-	for (int i = 0; i < 7; ++i) M->d_pool[i].release();
+	for (int i = 0; i < 10; ++i) M->d_pool[i].release();
 	delete M;
 }
 
@@ -555,6 +592,8 @@ extern "C" void mg_idx_destroy(mg_idx_t *gi)
 	free(gi);
 }
 
+extern "C" void mg_idx_hfree(void *h) { (void)h; } // reference callers only pass NULL (shortk.c:191)
+
 struct mg_tbuf_s { int dummy; };
 extern "C" mg_tbuf_t *mg_tbuf_init(void) { return (mg_tbuf_t*)calloc(1, sizeof(mg_tbuf_t)); }
 extern "C" void mg_tbuf_destroy(mg_tbuf_t *b) { free(b); }
@@ -706,7 +745,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 	unsigned int *d_jobq_n = (unsigned int*)dmalloc(sizeof(unsigned int) * 2);
 	unsigned long long *d_prof = (unsigned long long*)dmalloc(sizeof(unsigned long long) * PROF_N);
 	dzero(d_prof, sizeof(unsigned long long) * PROF_N);
-	enum { P_ANCHOR, P_MINIPOS, P_LCHAIN, P_OUT, P_PLAN, P_JOBS, P_CIG, N_POOLS };
+	enum { P_ANCHOR, P_MINIPOS, P_LCHAIN, P_OUT, P_PLAN, P_JOBS, P_CIG, P_GSTATE, P_GJOBS, P_WALK, N_POOLS };
 	Pool *d_pools = (Pool*)dmalloc(sizeof(Pool) * N_POOLS);
 	uint64_t cap[N_POOLS];
 	cap[P_ANCHOR] = std::max<uint64_t>((uint64_t)S.n_bases / 4 * sizeof(u128), (uint64_t)1 << 22);
@@ -716,6 +755,9 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 	cap[P_PLAN] = std::max<uint64_t>((uint64_t)S.n_bases / 8 * 8, (uint64_t)1 << 20);
 	cap[P_JOBS] = std::max<uint64_t>((uint64_t)S.n_bases / 40 * sizeof(WfaJob), (uint64_t)1 << 20);
 	cap[P_CIG] = std::max<uint64_t>((uint64_t)S.n_bases, (uint64_t)1 << 20);
+	cap[P_GSTATE] = std::max<uint64_t>((uint64_t)n_reads * 1024, (uint64_t)1 << 20);
+	cap[P_GJOBS] = std::max<uint64_t>((uint64_t)n_reads * 16 * sizeof(GwfaJob), (uint64_t)1 << 20);
+	cap[P_WALK] = std::max<uint64_t>((uint64_t)n_reads * 256, (uint64_t)1 << 20);
 	std::vector<ReadOut> routs(n_reads);
 	std::vector<ReadMeta> meta(n_reads);
 	char *hout = 0;
@@ -728,6 +770,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 		Pool hp[N_POOLS];
 		for (int i = 0; i < N_POOLS; ++i) d_buf[i] = M->d_pool[i].ensure(cap[i]), hp[i].used = 0, hp[i].cap = cap[i];
 		h2d(d_pools, hp, sizeof(hp));
+		dfill(d_buf[P_GJOBS], 0xff, cap[P_GJOBS]); // reserved-but-unused bridging job slots read as rid == -1
 		LaunchArgs L;
 		memset(&L, 0, sizeof(L));
 		L.c.g = M->g, L.c.ix = M->ix, L.c.opt = o;
@@ -740,11 +783,14 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 		L.c.pool_plan = &d_pools[P_PLAN], L.c.plan = (uint64_t*)d_buf[P_PLAN];
 		L.c.pool_jobs = &d_pools[P_JOBS], L.c.jobs = (WfaJob*)d_buf[P_JOBS];
 		L.c.pool_cig = &d_pools[P_CIG], L.c.cig = (uint32_t*)d_buf[P_CIG];
+		L.c.pool_gstate = &d_pools[P_GSTATE], L.c.gstate = (char*)d_buf[P_GSTATE];
+		L.c.pool_gjobs = &d_pools[P_GJOBS], L.c.gjobs = (GwfaJob*)d_buf[P_GJOBS];
+		L.c.pool_walk = &d_pools[P_WALK], L.c.walk = (int32_t*)d_buf[P_WALK];
 		L.c.next_read = d_next;
 		L.c.prof = d_prof;
 		L.c.jobq[0] = 0, L.c.jobq[1] = 0, L.c.jobq_n = d_jobq_n;
 		L.routs = d_routs;
-		int64_t jobs_done = 0;
+		int64_t jobs_done = 0, gjobs_done = 0;
 		// one pass over a set of reads: 5 launches; the job count is read back between K6/K7 and K8a
 		auto run_pass = [&](const int32_t *d_list, int32_t n_list, const Workers &W, bool timed) {
 			L.rid_list = d_list, L.n_work = n_list;
@@ -754,6 +800,17 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 			launch_stage<1>(L, W);
 			if (timed) tm_chain.stop(), tm_align.start();
 			launch_stage<2>(L, W);
+			{ // bridging jobs planned by k_gchain, then materialisation
+				Pool pg;
+				d2h(&pg, &d_pools[P_GJOBS], sizeof(Pool)); // implicit sync
+				int64_t n_gj = (int64_t)(std::min<uint64_t>(pg.used, pg.cap) / sizeof(GwfaJob));
+				L.rid_list = 0, L.job_start = gjobs_done, L.n_work = (int32_t)(n_gj - gjobs_done);
+				if (L.n_work > 0) { launch_stage<8>(L, W); S.n_launches += 1; }
+				gjobs_done = n_gj;
+				L.rid_list = d_list, L.n_work = n_list;
+				launch_stage<9>(L, W);
+				S.n_launches += 1;
+			}
 			if (timed) tm_align.stop();
 			Pool pj;
 			d2h(&pj, &d_pools[P_JOBS], sizeof(Pool)); // implicit sync
@@ -821,7 +878,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 		}
 		if (done) break;
 		// grow whatever overflowed (used counts keep growing past cap, so they tell how much was wanted)
-		for (int i = 0; i < N_POOLS; ++i) if (hp[i].used > cap[i]) cap[i] = hp[i].used * 3 / 2;
+		for (int i = 0; i < N_POOLS; ++i) if (hp[i].used > cap[i]) cap[i] = (hp[i].used * 3 / 2 + 4095) & ~(uint64_t)4095;
 		if (attempt == 7) { set_error("output pools kept overflowing"); rc_final = -2; }
 	}
 	S.t_h2d_ms = tm_h2d.ms(), S.t_seed_ms = tm_seed.ms(), S.t_chain_ms = tm_chain.ms(), S.t_align_ms = tm_align.ms();

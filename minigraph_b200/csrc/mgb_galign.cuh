@@ -373,7 +373,14 @@ struct ReadOut {
 
 MG_HD inline uint64_t align8(uint64_t x) { return (x + 7) & ~(uint64_t)7; }
 
-// K6/K7 for one read: graph chaining, bridging, post filters, alignment planning (one lane).
+// state handed from the graph-chaining DP pass to the materialisation pass
+struct GState {
+	int32_t n_lc, n_u, n_gc, n_jobs;
+	int64_t job_first;
+	// followed by LChain lc[n_lc] | uint64 u[n_u] | uint32 gc_hash[n_gc]
+};
+
+// K6 for one read: graph chaining DP, overlap resolution, bridging plan (one lane).
 MG_HD inline int stage_gchain(const PipeCtx &c, ReadOut *routs, int rid, Arena &A)
 {
 	ReadMeta &m = c.meta[rid];
@@ -382,23 +389,122 @@ MG_HD inline int stage_gchain(const PipeCtx &c, ReadOut *routs, int rid, Arena &
 	ro.status = 0, ro.n_gc = ro.n_lc = ro.n_a = 0, ro.rep_len = m.rep_len, ro.n_mz = m.n_mz, ro.blob_size = ro.blob2_size = 0, ro.blob_off = ro.blob2_off = 0;
 	if (m.status != 0) { ro.status = m.status; return 0; } // status 1: read skipped (empty or too long) -> no result object
 	uint64_t mark = A.top;
-	const char *qseq = c.b.seq + c.b.seq_off[rid];
 	const int32_t qlen = c.b.seq_len[rid];
 	const u128 *a = c.anchor + m.a_off;
-	int32_t n_lc = m.n_lc, n_u = 0;
+	int32_t n_lc = m.n_lc, n_u = 0, n_gc = 0;
 	uint64_t *u = 0;
 	LChain *lc;
+	uint32_t *gc_hash;
 	MGB_ALLOC(A, lc, LChain, n_lc);
+	MGB_ALLOC(A, gc_hash, uint32_t, n_lc);
 	for (int32_t i = 0; i < n_lc; ++i) lc[i] = c.lchain[m.lc_off + i];
 	unsigned long long pt0 = prof_clock();
 	MGB_TRY(gchain1_dp(A, c.g, &n_lc, lc, qlen, o.bw_long, o.bw_long, o.bw_long, o.max_gc_skip, o.ref_bonus, o.chn_pen_gap, o.mask_level, a, &u, &n_u));
+	prof_add(c, PROF_GC_DP_CYC, prof_clock() - pt0);
+	// a read's jobs must be contiguous in the pool (they are consumed in order): reserve the worst case, one job per
+	// linear chain, up front and mark the unused slots
+	int64_t job_first;
+	{
+		int64_t off = pool_alloc(c.pool_gjobs, (uint64_t)(n_lc > 0? n_lc : 1) * sizeof(GwfaJob));
+		if (off < 0) return MGB_E_POOL;
+		job_first = off / (int64_t)sizeof(GwfaJob);
+	}
+	struct LocalEmit {
+		GwfaJob *dst; int rid; int32_t n, cap;
+		MG_HD int operator()(GwfaJob &J) { if (n >= cap) return MGB_E_INTERNAL; J.rid = rid; dst[n++] = J; return 0; }
+	} le;
+	le.dst = c.gjobs + job_first, le.rid = rid, le.n = 0, le.cap = n_lc > 0? n_lc : 1;
+	MGB_TRY(gchain_prep(c.g, n_u, u, lc, a, m.hash, o.min_gc_cnt, o.min_gc_score, o.gdp_max_ed, gc_hash, &n_gc, le));
+	for (int32_t i = le.n; i < le.cap; ++i) le.dst[i].rid = -1; // unused reserved slots: skipped by the job kernel
+	// persist
+	uint64_t sz = sizeof(GState) + align8((uint64_t)n_lc * sizeof(LChain)) + (uint64_t)n_u * 8 + align8((uint64_t)n_gc * 4);
+	int64_t goff = pool_alloc(c.pool_gstate, sz);
+	if (goff < 0) return MGB_E_POOL;
+	GState *gsb = (GState*)(c.gstate + goff);
+	gsb->n_lc = n_lc, gsb->n_u = n_u, gsb->n_gc = n_gc, gsb->n_jobs = le.n, gsb->job_first = job_first;
+	LChain *dlc = (LChain*)(gsb + 1);
+	for (int32_t i = 0; i < n_lc; ++i) dlc[i] = lc[i];
+	uint64_t *du = (uint64_t*)((char*)dlc + align8((uint64_t)n_lc * sizeof(LChain)));
+	for (int32_t i = 0; i < n_u; ++i) du[i] = u[i];
+	uint32_t *dh = (uint32_t*)(du + n_u);
+	for (int32_t i = 0; i < n_gc; ++i) dh[i] = gc_hash[i];
+	m.gstate_off = goff;
+	A.top = mark;
+	return 0;
+}
+
+// K7a: one bridging alignment (reference: gchain1.c:349-381).  The wavefront containers of a typical bridge (tens of
+// diagonals) fit a small per-warp arena in SHARED memory, which removes the global-memory latency from the sequential
+// control flow; a bridge that outgrows it is redone with the worker's arena in HBM.  Lane 0 runs the alignment.
+static const int GWFA_SMEM_ARENA = 12 * 1024;
+
+MG_HD inline int gwfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int lane, int32_t *smem)
+{
+	GwfaJob *J = &c.gjobs[job_idx];
+	if (J->rid < 0) return 0;
+	if (c.meta[J->rid].status < 0) return 0;
+	int rc = 0;
+	if (lane <= 0) { // lane -1: thread-per-job mode, no warp to talk to
+		GwfOpt opt;
+		GwfResult r;
+		opt.traceback = 1, opt.max_chk = 1000, opt.bw_dyn = 1000, opt.max_lag = J->max_ed / 2, opt.s_term = -1;
+		opt.i_term = 500000000LL;
+		const char *qseq = c.b.seq + c.b.seq_off[J->rid];
+		unsigned long long t0 = prof_clock();
+		Arena S;
+		arena_init(S, smem, smem? GWFA_SMEM_ARENA : 0);
+		rc = smem? gwf_align(S, c.g, opt, J->ql, qseq + J->qs, J->v0, J->end0, J->v1, J->end1, J->max_ed, &r) : MGB_E_ARENA;
+		if (rc == MGB_E_ARENA) rc = gwf_align(A, c.g, opt, J->ql, qseq + J->qs, J->v0, J->end0, J->v1, J->end1, J->max_ed, &r);
+		prof_add(c, PROF_GC_GWFA_CYC, prof_clock() - t0);
+#if !MGB_ON_DEVICE && defined(MGB_HOSTSIM)
+		if (getenv("MGB_DUMP_JOBS")) fprintf(stderr, "GWFA\t%d\t%d\t%ld\t%d\t%lu\t%lu\n", J->ql, r.s, (long)r.n_iter, r.nv, (unsigned long)S.peak, (unsigned long)A.peak);
+#endif
+		if (rc == 0) {
+			J->s = r.s, J->nv = r.s >= 0? r.nv : 0;
+			if (r.s >= 0) {
+				int64_t woff = pool_alloc(c.pool_walk, (uint64_t)r.nv * 4);
+				if (woff < 0) rc = MGB_E_POOL;
+				else {
+					J->walk_off = woff / 4;
+					for (int32_t i = 0; i < r.nv; ++i) c.walk[J->walk_off + i] = r.v[i];
+				}
+			}
+		}
+	}
+	if (lane >= 0) rc = warp_bcast_i32(rc, 0);
+	return rc;
+}
+
+// K7b for one read: materialise graph chains from the DP and the bridging results, post filters, alignment plan.
+MG_HD inline int stage_gchain_gen(const PipeCtx &c, ReadOut *routs, int rid, Arena &A)
+{
+	ReadMeta &m = c.meta[rid];
+	ReadOut &ro = routs[rid];
+	const MapOptDev &o = c.opt;
+	if (m.status != 0) { ro.status = m.status; return 0; }
+	uint64_t mark = A.top;
+	const char *qseq = c.b.seq + c.b.seq_off[rid];
+	const int32_t qlen = c.b.seq_len[rid];
+	const u128 *a = c.anchor + m.a_off;
+	const GState *gsb = (const GState*)(c.gstate + m.gstate_off);
+	const int32_t n_lc = gsb->n_lc, n_u = gsb->n_u;
+	LChain *lc;
+	MGB_ALLOC(A, lc, LChain, n_lc);
+	{
+		const LChain *slc = (const LChain*)(gsb + 1);
+		for (int32_t i = 0; i < n_lc; ++i) lc[i] = slc[i];
+	}
+	const uint64_t *u = (const uint64_t*)((const char*)(gsb + 1) + align8((uint64_t)n_lc * sizeof(LChain)));
+	const uint32_t *gc_hash = (const uint32_t*)(u + n_u);
+	GwfaFeed feed;
+	feed.job = c.gjobs + gsb->job_first, feed.walk_pool = c.walk, feed.next = 0, feed.n = gsb->n_jobs;
 	GcSet gs;
 	unsigned long long pt1 = prof_clock();
-	prof_add(c, PROF_GC_DP_CYC, pt1 - pt0);
-	MGB_TRY(gchain_gen(A, c.g, n_u, u, lc, a, m.hash, o.min_gc_cnt, o.min_gc_score, o.gdp_max_ed, 1, qseq, gs));
+	MGB_TRY(gchain_gen(A, c.g, n_u, u, lc, a, m.hash, o.min_gc_cnt, o.min_gc_score, o.gdp_max_ed, 1, qseq, gs, &feed, gc_hash));
 	gs.rep_len = m.rep_len;
 	unsigned long long pt2 = prof_clock();
 	prof_add(c, PROF_GC_GEN_CYC, pt2 - pt1);
+	prof_add(c, PROF_GC_SHORTK_CYC, gs.cyc_shortk), prof_add(c, PROF_GC_EXTRA_CYC, gs.cyc_extra);
 	MGB_TRY(gchain_set_parent(A, o.mask_level, gs.n_gc, gs.gc, o.sub_diff));
 	gchain_flt_sub(o.pri_ratio, c.ix.k * 2, o.best_n, gs.n_gc, gs.gc);
 	MGB_TRY(gchain_drop_flt(A, gs));

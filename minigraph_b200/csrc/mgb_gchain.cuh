@@ -243,14 +243,36 @@ struct GcSet { // device analogue of mg_gchains_t
 	GChain *gc;
 	LLChain *lc;
 	u128 *a;
+	unsigned long long cyc_gwfa, cyc_shortk, cyc_extra; // instrumentation
+};
+
+// One bridging alignment between two linear chains on different vertices (reference: gchain1.c:349-381 bridge_gwfa).
+// Independent of every other bridge of the read, so the planning pass (gchain_prep) emits them as jobs for the
+// warp-cooperative K7a kernel and gchain_gen() consumes the results in the same order.
+struct GwfaJob {
+	int32_t rid;
+	uint32_t v0, v1;
+	int32_t end0, end1;
+	int32_t qs, ql;
+	int32_t max_ed;
+	int32_t s, nv, status;  // results: edit distance (-1: none within max_ed), walk length
+	int64_t walk_off;       // element offset of the walk (int32 vertices) in the walk pool
+};
+
+struct GwfaFeed { // precomputed bridge results of one read, consumed in order
+	const GwfaJob *job;
+	const int32_t *walk_pool;
+	int32_t next, n;
 };
 
 struct BridgeAux {
 	const GraphDev *g;
+	GwfaFeed *feed;
 	const char *qseq;
 	AVec<LLChain> llc;
 	int32_t n_a;
 	u128 *a_new;
+	unsigned long long cyc_gwfa, cyc_shortk;
 };
 
 MG_HD inline void gc_copy_lchain(LLChain *q, const LChain *p, int32_t *n_a, u128 *a_new, const u128 *a_old, int32_t ed)
@@ -305,6 +327,16 @@ MG_HD inline int gc_bridge_gwfa(Arena &A, BridgeAux &aux, int32_t kmer_size, int
 	end1 = l1->rs + kmer_size - 1;
 	opt.traceback = 1, opt.max_chk = 1000, opt.bw_dyn = 1000, opt.max_lag = gdp_max_ed / 2, opt.s_term = -1;
 	opt.i_term = 500000000LL;
+	if (aux.feed) { // the alignment was done by the job kernel
+		if (aux.feed->next >= aux.feed->n) return MGB_E_INTERNAL;
+		const GwfaJob *J = &aux.feed->job[aux.feed->next++];
+		if (J->v0 != v0 || J->v1 != v1 || J->end0 != end0 || J->end1 != end1 || J->qs != qs || J->ql != qe - qs) return MGB_E_INTERNAL;
+		if (J->s < 0) return 0;
+		const int32_t *w = aux.feed->walk_pool + J->walk_off;
+		for (int32_t j = 1; j < J->nv - 1; ++j) MGB_TRY(gc_push_empty(A, aux, (uint32_t)w[j]));
+		*ed = J->s, *ok = 1;
+		return 0;
+	}
 	uint64_t mark = A.top;
 	// walk vertices are copied out before llc can grow over them
 	MGB_TRY(gwf_align(A, *aux.g, opt, qe - qs, &aux.qseq[qs], v0, end0, v1, end1, gdp_max_ed, &r));
@@ -323,8 +355,12 @@ MG_HD inline int gc_bridge_lchains(Arena &A, BridgeAux &aux, int32_t n_seg, int3
 	if (l1->v != l0->v) {
 		int32_t ed = -1;
 		int ok = 0, sk_failed = 0;
+		unsigned long long t0 = prof_clock();
 		if (n_seg <= 1) MGB_TRY(gc_bridge_gwfa(A, aux, kmer_size, gdp_max_ed, l0, l1, &ed, &ok));
+		unsigned long long t1 = prof_clock();
+		aux.cyc_gwfa += t1 - t0;
 		if (!ok) MGB_TRY(gc_bridge_shortk(A, aux, l0, l1, &sk_failed));
+		aux.cyc_shortk += prof_clock() - t1;
 		if (sk_failed) { *failed = 1; return 0; }
 		LLChain q;
 		gc_copy_lchain(&q, l1, &aux.n_a, aux.a_new, a, ed);
@@ -473,11 +509,57 @@ MG_HD inline int gchain_sort_by_score(Arena &A, GcSet &gs)
 }
 
 // Build graph chains from the DP result.  Output arrays are allocated at the caller's mark (gs.gc, gs.a, gs.lc).
+// Planning pass of gchain_gen(): hash the chains that will be kept, resolve their overlaps (lc[] is modified) and
+// emit one GwfaJob per bridge between different vertices (same pair enumeration as the loop in gchain_gen()).
+template<typename Emit>
+MG_HD inline int gchain_prep(const GraphDev &g, int32_t n_u, const uint64_t *u, LChain *lc, const u128 *a, uint32_t hash, int32_t min_gc_cnt,
+							 int32_t min_gc_score, int32_t gdp_max_ed, uint32_t *gc_hash, int32_t *n_gc_, Emit &emit)
+{
+	int32_t i, j, k, st, kmer_size = 0;
+	*n_gc_ = 0;
+	for (i = k = 0, st = 0; i < n_u; ++i) {
+		int32_t m = 0, nui = (int32_t)u[i];
+		for (j = 0; j < nui; ++j) m += lc[st + j].cnt;
+		if (m >= min_gc_cnt && (int64_t)(u[i] >> 32) >= (int64_t)min_gc_score) {
+			uint32_t h = hash;
+			int32_t j0;
+			if (k == 0) kmer_size = (int32_t)(a[0].y >> 32 & 0xff);
+			for (j = 0; j < nui; ++j) {
+				const LChain *p = &lc[st + j];
+				h += hash32((uint32_t)p->qs) + hash32((uint32_t)p->re) + hash32(p->v);
+			}
+			gc_hash[k] = hash32(h);
+			for (j = 1; j < nui; ++j) MGB_TRY(gc_resolve_overlap(&lc[st + j - 1], &lc[st + j], a));
+			for (j0 = 0, j = 1; j < nui; ++j) {
+				const LChain *l0 = &lc[st + j0], *l1 = &lc[st + j];
+				if (l1->cnt > 0) {
+					if (l1->v != l0->v) {
+						GwfaJob J;
+						J.rid = 0, J.v0 = l0->v, J.v1 = l1->v;
+						J.qs = l0->qe - kmer_size, J.ql = (l1->qs + kmer_size) - J.qs;
+						J.end0 = l0->re - kmer_size, J.end1 = l1->rs + kmer_size - 1;
+						J.max_ed = gdp_max_ed, J.s = -1, J.nv = 0, J.status = 0, J.walk_off = 0;
+						MGB_TRY(emit(J));
+					}
+					j0 = j;
+				}
+			}
+			++k;
+		}
+		st += nui;
+	}
+	*n_gc_ = k;
+	return 0;
+}
+
+// With `feed`, gchain_prep() has already hashed the chains (gc_hash) and resolved overlaps, and the bridging
+// alignments come from the job kernel.
 MG_HD inline int gchain_gen(Arena &A, const GraphDev &g, int32_t n_u, const uint64_t *u, LChain *lc, const u128 *a, uint32_t hash,
-							int32_t min_gc_cnt, int32_t min_gc_score, int32_t gdp_max_ed, int32_t n_seg, const char *qseq, GcSet &gs)
+							int32_t min_gc_cnt, int32_t min_gc_score, int32_t gdp_max_ed, int32_t n_seg, const char *qseq, GcSet &gs,
+							GwfaFeed *feed, const uint32_t *gc_hash)
 {
 	int32_t i, j, k, st, kmer_size;
-	gs.n_gc = gs.n_lc = gs.n_a = 0, gs.rep_len = 0, gs.gc = 0, gs.lc = 0, gs.a = 0;
+	gs.n_gc = gs.n_lc = gs.n_a = 0, gs.rep_len = 0, gs.gc = 0, gs.lc = 0, gs.a = 0, gs.cyc_gwfa = gs.cyc_shortk = gs.cyc_extra = 0;
 	int32_t n_lc_in = 0;
 	for (i = 0, st = 0; i < n_u; ++i) {
 		int32_t m = 0, nui = (int32_t)u[i];
@@ -492,7 +574,7 @@ MG_HD inline int gchain_gen(Arena &A, const GraphDev &g, int32_t n_u, const uint
 	MGB_ALLOC(A, gs.a, u128, gs.n_a);
 	// llc can hold at most one entry per input lchain plus the bridging vertices: give it head room below the scratch
 	BridgeAux aux;
-	aux.g = &g, aux.qseq = qseq, aux.n_a = 0, aux.a_new = gs.a;
+	aux.g = &g, aux.feed = feed, aux.qseq = qseq, aux.n_a = 0, aux.a_new = gs.a, aux.cyc_gwfa = aux.cyc_shortk = 0;
 	avec_init(aux.llc);
 	MGB_TRY(avec_reserve(A, aux.llc, n_lc_in + 64));
 	kmer_size = (int32_t)(a[0].y >> 32 & 0xff);
@@ -504,12 +586,15 @@ MG_HD inline int gchain_gen(Arena &A, const GraphDev &g, int32_t n_u, const uint
 			int32_t j0;
 			gs.gc[k].score = (int32_t)(u[i] >> 32);
 			gs.gc[k].off = n_llc0;
-			for (j = 0; j < nui; ++j) {
-				const LChain *p = &lc[st + j];
-				h += hash32((uint32_t)p->qs) + hash32((uint32_t)p->re) + hash32(p->v);
+			if (feed) gs.gc[k].hash = gc_hash[k];
+			else {
+				for (j = 0; j < nui; ++j) {
+					const LChain *p = &lc[st + j];
+					h += hash32((uint32_t)p->qs) + hash32((uint32_t)p->re) + hash32(p->v);
+				}
+				gs.gc[k].hash = hash32(h);
+				for (j = 1; j < nui; ++j) MGB_TRY(gc_resolve_overlap(&lc[st + j - 1], &lc[st + j], a));
 			}
-			gs.gc[k].hash = hash32(h);
-			for (j = 1; j < nui; ++j) MGB_TRY(gc_resolve_overlap(&lc[st + j - 1], &lc[st + j], a));
 			{
 				LLChain q;
 				gc_copy_lchain(&q, &lc[st], &aux.n_a, gs.a, a, -1);
@@ -521,10 +606,12 @@ MG_HD inline int gchain_gen(Arena &A, const GraphDev &g, int32_t n_u, const uint
 					int failed;
 					MGB_TRY(gc_bridge_lchains(A, aux, n_seg, kmer_size, gdp_max_ed, l0, l1, a, &failed));
 					if (failed) {
+						aux.feed = 0; // the rare re-bridging of consecutive pairs is not planned: align in place
 						for (int32_t t = j0; t < j; ++t) {
 							MGB_TRY(gc_bridge_lchains(A, aux, n_seg, kmer_size, gdp_max_ed, &lc[st + t], &lc[st + t + 1], a, &failed));
 							if (failed) return MGB_E_INTERNAL;
 						}
+						aux.feed = feed;
 					}
 					j0 = j;
 				}
@@ -539,8 +626,11 @@ MG_HD inline int gchain_gen(Arena &A, const GraphDev &g, int32_t n_u, const uint
 	gs.n_a = aux.n_a;
 	gs.n_lc = (int32_t)aux.llc.n;
 	gs.lc = aux.llc.a;
+	gs.cyc_gwfa = aux.cyc_gwfa, gs.cyc_shortk = aux.cyc_shortk;
+	unsigned long long t0 = prof_clock();
 	MGB_TRY(gchain_extra(g, gs));
 	MGB_TRY(gchain_sort_by_score(A, gs));
+	gs.cyc_extra = prof_clock() - t0;
 	return 0;
 }
 

@@ -446,11 +446,7 @@ MG_HD inline int gwf_align(Arena &A, const GraphDev &g, const GwfOpt &opt, int32
 	GwfState z;
 	z.g = &g, z.ql = ql, z.q = q, z.s = 0, z.end_tb = -1, z.q_head = 0;
 	avec_init(z.a), avec_init(z.B), avec_init(z.ooo), avec_init(z.Q), avec_init(z.intv), avec_init(z.tmp), avec_init(z.swap), avec_init(z.t);
-	// the walk buffer sits first so that it survives the release of the scratch
-	int32_t *walk;
-	const int32_t max_walk = 4096;
-	MGB_ALLOC(A, walk, int32_t, max_walk);
-	uint64_t mark_keep = A.top;
+	uint64_t mark_keep = mark;
 	MGB_TRY(u64tab_init(A, z.ha, 6));
 	MGB_TRY(u64tab_init(A, z.ht, 6));
 	MGB_TRY(avec_reserve(A, z.t, 16));
@@ -473,13 +469,16 @@ MG_HD inline int gwf_align(Arena &A, const GraphDev &g, const GwfOpt &opt, int32
 	if (opt.traceback && r->end_off >= 0) { // reference: gfa-ed.c:509-522 gwf_traceback
 		int32_t i = z.end_tb, n = 1;
 		while (i >= 0 && z.t.a[i].v >= 0) ++n, i = z.t.a[i].pre;
-		if (n > max_walk) { A.top = mark; return MGB_E_UNSUPPORTED; }
+		int32_t *tmpw, *walk = (int32_t*)(A.base + mark); // the walk is built above the scratch, then moved down to the mark
+		MGB_ALLOC(A, tmpw, int32_t, n);
 		i = z.end_tb, n = 0;
-		walk[n++] = (int32_t)r->end_v;
-		while (i >= 0 && z.t.a[i].v >= 0) walk[n++] = z.t.a[i].v, i = z.t.a[i].pre;
+		tmpw[n++] = (int32_t)r->end_v;
+		while (i >= 0 && z.t.a[i].v >= 0) tmpw[n++] = z.t.a[i].v, i = z.t.a[i].pre;
 		r->nv = n;
-		for (i = 0; i < n >> 1; ++i) { int32_t tmp = walk[i]; walk[i] = walk[n - 1 - i], walk[n - 1 - i] = tmp; }
+		for (i = 0; i < n >> 1; ++i) { int32_t x = tmpw[i]; tmpw[i] = tmpw[n - 1 - i], tmpw[n - 1 - i] = x; }
+		for (i = 0; i < n; ++i) { int32_t x = tmpw[i]; walk[i] = x; } // forward copy: the destination lies below the source
 		r->v = walk;
+		mark_keep = mark + (((uint64_t)n * 4 + 15) & ~(uint64_t)15);
 	}
 	r->s = r->end_v != (uint32_t)-1? z.s : -1;
 	A.top = mark_keep;

@@ -106,6 +106,7 @@ struct ReadMeta {
 	int32_t n_seed0;     // seeds before chaining (for the byte model)
 	int32_t n_u0;        // chains out of the chaining DP (for the byte model)
 	uint64_t arena_peak;
+	int64_t gstate_off;  // byte offset of the GState blob (between k_gchain and k_gchain_gen)
 };
 
 struct BatchDev {
