@@ -214,14 +214,10 @@ def main():
     t_kern = sum(kern) / 1e3
     t_wall = sum(walls)
     # the one collective of the path: per-rank GAF byte counts -> output offsets
-    offsets = [0]
+    from minigraph_b200 import dist as mdist
+    my_off, counts = mdist.gaf_offsets(gaf_bytes[0], device="cuda")
+    offsets = [sum(counts[:i]) for i in range(len(counts))]
     if world > 1:
-        mine = torch.tensor([gaf_bytes[0]], dtype=torch.int64, device="cuda")
-        allc = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allc, mine)
-        offsets = [0]
-        for c in allc[:-1]:
-            offsets.append(offsets[-1] + int(c.item()))
         tm = torch.tensor([t_kern, t_wall], dtype=torch.float64, device="cuda")
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         t_kern, t_wall = float(tm[0].item()), float(tm[1].item())

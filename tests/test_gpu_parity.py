@@ -37,3 +37,15 @@ def test_edge_reads(lib, workdir):
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not shipped")
 def test_struct_fields_vs_reference(lib, workdir):
     cases.case_struct_random(lib, workdir, n_reads=400)
+
+
+def test_index_matches_oracle_sketch(lib):
+    import subprocess
+    import ctypes as C
+    import os
+    import test_oracle
+    subprocess.check_call(["make", "-s", "-C", os.path.join(T.REPO, "oracle"), "liboracle.so"])
+    orc = C.CDLL(os.path.join(T.REPO, "oracle", "liboracle.so"))
+    orc.orc_sketch.restype = C.c_int64
+    orc.orc_sketch.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int64]
+    test_oracle.check_index(lib, orc)
