@@ -212,25 +212,13 @@ MG_HD inline int32_t chain_score_simple(const u128 &ai, const u128 &aj, float pe
 	return sc;
 }
 
-// RMQ chaining (reference: lchain.c:252-372).  Same output convention as chain_dp().
-MG_HD inline int chain_rmq(Arena &A, int max_dist, int max_dist_inner, int bw, int max_chn_skip, int cap_rmq_size, int min_cnt, int min_sc,
-						   float pen_gap, float pen_skip, int64_t n, u128 *a, int32_t *n_u_, uint64_t **u_, int32_t *n_a_)
+// RMQ chaining, DP fill with the reference's two AVL trees replayed node for node (reference: lchain.c:271-359).
+// Computes f, p, v for all anchors; t is scratch.  Sequential (one lane).
+MG_HD inline int chain_rmq_fill_seq(Arena &A, int max_dist, int max_dist_inner, int bw, int max_chn_skip, int cap_rmq_size,
+									float pen_gap, float pen_skip, int64_t n, const u128 *a, int32_t *f, int32_t *p, int32_t *t, int32_t *v)
 {
-	int32_t *f, *t, *v, *p, n_u, n_v, max_drop = bw;
 	int64_t i, i0, st = 0, st_inner = 0;
-	uint64_t *u;
 	RmqTree root, root_inner;
-	*u_ = 0, *n_u_ = 0, *n_a_ = 0;
-	if (n == 0) return 0;
-	if (max_dist < bw) max_dist = bw;
-	if (max_dist_inner <= 0 || max_dist_inner >= max_dist) max_dist_inner = 0;
-	uint64_t *u_store;
-	MGB_ALLOC(A, u_store, uint64_t, n);
-	uint64_t mark = A.top;
-	MGB_ALLOC(A, p, int32_t, n);
-	MGB_ALLOC(A, f, int32_t, n);
-	MGB_ALLOC(A, t, int32_t, n);
-	MGB_ALLOC(A, v, int32_t, n);
 	for (i = 0; i < n; ++i) t[i] = 0;
 	uint64_t mark_tree = A.top;
 	MGB_TRY(rmq_init(A, root, (int32_t)n));
@@ -297,11 +285,232 @@ MG_HD inline int chain_rmq(Arena &A, int max_dist, int max_dist_inner, int bw, i
 		v[i] = max_j >= 0 && v[max_j] > max_f? v[max_j] : max_f;
 	}
 	A.top = mark_tree;
+	return 0;
+}
+
+// RMQ chaining (reference: lchain.c:252-372).  Same output convention as chain_dp().  Sequential (one lane).
+MG_HD inline int chain_rmq(Arena &A, int max_dist, int max_dist_inner, int bw, int max_chn_skip, int cap_rmq_size, int min_cnt, int min_sc,
+						   float pen_gap, float pen_skip, int64_t n, u128 *a, int32_t *n_u_, uint64_t **u_, int32_t *n_a_)
+{
+	int32_t *f, *t, *v, *p, n_u, n_v, max_drop = bw;
+	uint64_t *u;
+	*u_ = 0, *n_u_ = 0, *n_a_ = 0;
+	if (n == 0) return 0;
+	if (max_dist < bw) max_dist = bw;
+	if (max_dist_inner <= 0 || max_dist_inner >= max_dist) max_dist_inner = 0;
+	uint64_t *u_store;
+	MGB_ALLOC(A, u_store, uint64_t, n);
+	uint64_t mark = A.top;
+	MGB_ALLOC(A, p, int32_t, n);
+	MGB_ALLOC(A, f, int32_t, n);
+	MGB_ALLOC(A, t, int32_t, n);
+	MGB_ALLOC(A, v, int32_t, n);
+	MGB_TRY(chain_rmq_fill_seq(A, max_dist, max_dist_inner, bw, max_chn_skip, cap_rmq_size, pen_gap, pen_skip, n, a, f, p, t, v));
 	MGB_TRY(chain_backtrack(A, n, f, p, v, t, min_cnt, min_sc, max_drop, 0, &u, &n_u, &n_v));
 	if (n_u > 0) {
 		MGB_TRY(chain_compact(A, n_u, u, n_v, v, a));
-		for (i = 0; i < n_u; ++i) u_store[i] = u[i];
+		for (int64_t i = 0; i < n_u; ++i) u_store[i] = u[i];
 	}
+	A.top = mark;
+	*u_ = u_store, *n_u_ = n_u, *n_a_ = n_u > 0? n_v : 0;
+	return 0;
+}
+
+// ---- warp-cooperative RMQ fill ----
+// The two trees of the reference only ever hold index windows of the x-sorted anchor array: outer = [st, i0),
+// inner = [st_inner, i0).  Hence
+//   * the range-minimum query is a lane-parallel scan of the outer window with the (y,idx) interval test of
+//     krmq_rmq() and a min-reduction on pri; the answer is independent of the tree shape unless two candidates tie
+//     on pri, in which case the fill gives up (returns 1) and the caller replays the AVL version;
+//   * the in-order walk over the inner tree is a walk over an array kept sorted by (y,idx); candidates are scored 32
+//     at a time and the order-dependent (max_f, n_skip) state machine is replayed from registers.  The marks
+//     "t[j] == i" only ever come from successors of j inside the same candidate set (p[j'] = j implies y_j < y_j'),
+//     so they are scattered for the whole set first and read afterwards.
+// Exact only while the outer tree never exceeds cap_rmq_size (the caller checks n <= cap).
+MG_HD inline int32_t warp_sum_i32_all(int32_t x) { return warp_sum_i32(x); }
+
+MG_HD inline double warp_min_f64(double x)
+{
+#if MGB_ON_DEVICE
+	for (int o = 16; o > 0; o >>= 1) { double y = __shfl_xor_sync(0xffffffffu, x, o); x = y < x? y : x; }
+#endif
+	return x;
+}
+
+MG_HD inline int chain_rmq_fill_w(Arena &A, int max_dist, int max_dist_inner, int bw, int max_chn_skip, float pen_gap, float pen_skip,
+								  int64_t n, const u128 *a, int32_t *f, int32_t *p, int32_t *t, int32_t *v, int lane)
+{
+	uint64_t mark = A.top;
+	double *pri;
+	uint64_t *K; // inner window, keys y<<32|idx ascending
+	MGB_ALLOC(A, pri, double, n);
+	MGB_ALLOC(A, K, uint64_t, n);
+	int32_t nK = 0;
+	int64_t i, i0 = 0, st = 0, st_inner = 0;
+	for (i = lane; i < n; i += MGB_W) t[i] = 0;
+	warp_sync();
+	for (i = 0; i < n; ++i) {
+		const uint64_t xi = a[i].x, yi64 = a[i].y;
+		const int32_t yi = (int32_t)yi64;
+		int64_t max_j = -1;
+		int32_t max_f = (int32_t)(yi64 >> 32 & 0xff);
+		// (1) anchors with a smaller target position become available
+		if (i0 < i && a[i0].x != xi) {
+			for (int64_t j = i0; j < i; ++j) {
+				const uint64_t xj = a[j].x, yj = a[j].y;
+				if (lane == 0) pri[j] = -(f[j] + 0.5 * pen_gap * ((int32_t)xj + (int32_t)yj));
+				if (max_dist_inner > 0) { // insert (y,idx) into the sorted inner window
+					const uint64_t key = (uint64_t)(uint32_t)(int32_t)yj << 32 | (uint64_t)(uint32_t)j;
+					int32_t cnt = 0;
+					for (int32_t x = lane; x < nK; x += MGB_W) cnt += K[x] < key;
+					const int32_t pos = warp_sum_i32(cnt);
+					for (int32_t e = nK; e > pos; e -= MGB_W) { // shift [pos, nK) up by one, top chunk first
+						int32_t idx = e - 1 - lane;
+						uint64_t val = 0;
+						if (idx >= pos) val = K[idx];
+						warp_sync();
+						if (idx >= pos) K[idx + 1] = val;
+						warp_sync();
+					}
+					if (lane == 0) K[pos] = key;
+					++nK;
+					warp_sync();
+				}
+			}
+			i0 = i;
+			warp_sync();
+		}
+		// (2) retire anchors that fell out of range
+		while (st < i && (xi >> 32 != a[st].x >> 32 || xi > a[st].x + (uint64_t)max_dist)) ++st;
+		if (max_dist_inner > 0) {
+			while (st_inner < i && (xi >> 32 != a[st_inner].x >> 32 || xi > a[st_inner].x + (uint64_t)max_dist_inner)) {
+				if (st_inner < i0) { // it is in the window: remove its key
+					const uint64_t key = (uint64_t)(uint32_t)(int32_t)a[st_inner].y << 32 | (uint64_t)(uint32_t)st_inner;
+					int32_t cnt = 0;
+					for (int32_t x = lane; x < nK; x += MGB_W) cnt += K[x] < key;
+					const int32_t pos = warp_sum_i32(cnt);
+					for (int32_t b = pos; b + 1 < nK; b += MGB_W) { // shift (pos, nK) down by one, bottom chunk first
+						int32_t idx = b + lane;
+						uint64_t val = 0;
+						if (idx + 1 < nK) val = K[idx + 1];
+						warp_sync();
+						if (idx + 1 < nK) K[idx] = val;
+						warp_sync();
+					}
+					--nK;
+				}
+				++st_inner;
+			}
+		}
+		// (3) range-minimum query on the outer window (reference: lchain.c:317-325, interval of krmq_rmq)
+		{
+			const int64_t hi_j = st < i0? i0 : st; // window [st, i0)
+			double best = 1e300;
+			int32_t best_j = -1, n_best = 0;
+			for (int64_t j = st + lane; j < hi_j; j += MGB_W) {
+				const int32_t yj = (int32_t)a[j].y;
+				if (!(yj > yi - max_dist)) continue;
+				if (!(yj < yi - 1 || (yj == yi - 1 && j == 0))) continue;
+				const double pj = pri[j];
+				if (pj < best) best = pj, best_j = (int32_t)j, n_best = 1;
+				else if (pj == best) ++n_best;
+			}
+			const double gbest = warp_min_f64(best);
+			const int32_t n_at_min = warp_sum_i32(best_j >= 0 && best == gbest? n_best : 0);
+			if (n_at_min > 1) { A.top = mark; return 1; } // pri tie: the winner depends on the AVL shape
+			if (n_at_min == 1) {
+				const int32_t j = warp_max_i32(best_j >= 0 && best == gbest? best_j : -1);
+				int32_t exact, width, n_skip = 0;
+				int32_t sc = f[j] + chain_score_simple(a[i], a[j], pen_gap, pen_skip, &exact, &width);
+				if (width <= bw && sc > max_f) max_f = sc, max_j = j;
+				if (!exact && nK > 0 && yi > 0) { // (4) walk the inner window downwards from (yi-1, n)
+					const uint64_t hi_key = (uint64_t)(uint32_t)(yi - 1) << 32 | 0xffffffffULL;
+					const int32_t ylo = yi - max_dist_inner;
+					const uint64_t lo_key = ylo > 0? (uint64_t)(uint32_t)ylo << 32 : 0;
+					int32_t c_hi = 0, c_lo = 0;
+					for (int32_t x = lane; x < nK; x += MGB_W) c_hi += K[x] <= hi_key, c_lo += K[x] < lo_key;
+					const int32_t ub = warp_sum_i32(c_hi), lb = warp_sum_i32(c_lo); // candidates K[lb, ub)
+					// marks: t[p[j]] = i for every in-band candidate
+					for (int32_t x = lb + lane; x < ub; x += MGB_W) {
+						const int32_t jj = (int32_t)(uint32_t)K[x];
+						int32_t w2;
+						chain_score_simple(a[i], a[jj], pen_gap, pen_skip, 0, &w2);
+						if (w2 <= bw && p[jj] >= 0) t[p[jj]] = (int32_t)i;
+					}
+					warp_sync();
+					int stop = 0;
+					for (int32_t top = ub; top > lb && !stop; top -= MGB_W) {
+						const int32_t x = top - 1 - lane;
+						int32_t c_ok = 0, c_sc = 0, c_mk = 0, c_j = -1;
+						if (x >= lb) {
+							int32_t w2;
+							c_j = (int32_t)(uint32_t)K[x];
+							c_sc = f[c_j] + chain_score_simple(a[i], a[c_j], pen_gap, pen_skip, 0, &w2);
+							c_ok = w2 <= bw;
+							c_mk = t[c_j] == (int32_t)i;
+						}
+						const int32_t m = top - lb < MGB_W? top - lb : MGB_W;
+						for (int32_t c = 0; c < m; ++c) { // replay in order; all lanes keep identical state
+							const int32_t ok = warp_bcast_i32(c_ok, c);
+							if (!ok) continue;
+							const int32_t s2 = warp_bcast_i32(c_sc, c);
+							if (s2 > max_f) {
+								max_f = s2, max_j = warp_bcast_i32(c_j, c);
+								if (n_skip > 0) --n_skip;
+							} else if (warp_bcast_i32(c_mk, c)) {
+								if (++n_skip > max_chn_skip) { stop = 1; break; }
+							}
+						}
+					}
+				}
+			}
+		}
+		if (lane == 0) {
+			f[i] = max_f, p[i] = (int32_t)max_j;
+			v[i] = max_j >= 0 && v[max_j] > max_f? v[max_j] : max_f;
+		}
+		warp_sync();
+	}
+	A.top = mark;
+	return 0;
+}
+
+// Warp-uniform RMQ chaining: same contract as chain_rmq(); all lanes enter with identical arguments and leave with
+// identical results (outputs are broadcast from lane 0, which runs the sequential backtrack/compaction).
+MG_HD inline int chain_rmq_w(Arena &A, int max_dist, int max_dist_inner, int bw, int max_chn_skip, int cap_rmq_size, int min_cnt, int min_sc,
+							 float pen_gap, float pen_skip, int64_t n, u128 *a, int32_t *n_u_, uint64_t **u_, int32_t *n_a_, int lane)
+{
+	int32_t *f, *t, *v, *p;
+	*u_ = 0, *n_u_ = 0, *n_a_ = 0;
+	if (n == 0) return 0;
+	const int max_drop = bw;
+	if (max_dist < bw) max_dist = bw;
+	if (max_dist_inner <= 0 || max_dist_inner >= max_dist) max_dist_inner = 0;
+	uint64_t *u_store;
+	MGB_ALLOC(A, u_store, uint64_t, n);
+	uint64_t mark = A.top;
+	MGB_ALLOC(A, p, int32_t, n);
+	MGB_ALLOC(A, f, int32_t, n);
+	MGB_ALLOC(A, t, int32_t, n);
+	MGB_ALLOC(A, v, int32_t, n);
+	int rc = n <= cap_rmq_size? chain_rmq_fill_w(A, max_dist, max_dist_inner, bw, max_chn_skip, pen_gap, pen_skip, n, a, f, p, t, v, lane) : 1;
+	if (rc < 0) return rc;
+	int32_t n_u = 0, n_v = 0;
+	int rc2 = 0;
+	if (lane <= 0) { // sequential tail on one lane
+		Arena B = A;
+		if (rc == 1) rc2 = chain_rmq_fill_seq(B, max_dist, max_dist_inner, bw, max_chn_skip, cap_rmq_size, pen_gap, pen_skip, n, a, f, p, t, v);
+		uint64_t *u = 0;
+		if (rc2 == 0) rc2 = chain_backtrack(B, n, f, p, v, t, min_cnt, min_sc, max_drop, 0, &u, &n_u, &n_v);
+		if (rc2 == 0 && n_u > 0) {
+			rc2 = chain_compact(B, n_u, u, n_v, v, a);
+			for (int64_t i = 0; i < n_u; ++i) u_store[i] = u[i];
+		}
+		if (B.peak > A.peak) A.peak = B.peak;
+	}
+	rc2 = warp_bcast_i32(rc2, 0), n_u = warp_bcast_i32(n_u, 0), n_v = warp_bcast_i32(n_v, 0);
+	warp_sync();
+	if (rc2 < 0) return rc2;
 	A.top = mark;
 	*u_ = u_store, *n_u_ = n_u, *n_a_ = n_u > 0? n_v : 0;
 	return 0;

@@ -109,55 +109,10 @@ MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A)
 	return 0;
 }
 
-// K4/K5 for one read: seeds -> linear chains.  Anchors are compacted in place; chains go to the lchain pool.
-MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A)
+// chain records, end trimming, bad-seed filters, anchor update, pool write (reference: map-algo.c:419-449); one lane
+MG_HD inline int stage_chain_tail(const PipeCtx &c, ReadMeta &m, Arena &A, u128 *a, const uint64_t *u, int32_t n_lc, int32_t n_a_new)
 {
-	ReadMeta &m = c.meta[rid];
 	const MapOptDev &o = c.opt;
-	if (m.status != 0) return 0;
-	uint64_t mark = A.top;
-	int32_t qlen = c.b.seq_len[rid];
-	u128 *a = c.anchor + m.a_off;
-	int64_t n_a = m.n_a;
-	int32_t n_lc = 0, n_a_new = 0;
-	uint64_t *u = 0;
-	const int is_splice = !!(o.flag & F_SPLICE), is_sr = !!(o.flag & F_SR);
-	int max_gap_qry, max_gap_ref;
-	// reference: map-algo.c:377-386
-	if (is_sr) max_gap_qry = qlen > o.max_gap? qlen : o.max_gap;
-	else max_gap_qry = o.max_gap;
-	if (o.max_gap_ref > 0) max_gap_ref = o.max_gap_ref;
-	else if (o.max_frag_len > 0) {
-		max_gap_ref = o.max_frag_len - qlen;
-		if (max_gap_ref < o.max_gap) max_gap_ref = o.max_gap;
-	} else max_gap_ref = o.max_gap;
-
-	unsigned long long t0 = prof_clock();
-	if (n_a > 0) {
-		if (o.flag & F_RMQ)
-			MGB_TRY(chain_rmq(A, o.max_gap, o.max_gap_pre, o.bw, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
-							  o.chn_pen_gap, o.chn_pen_skip, n_a, a, &n_lc, &u, &n_a_new));
-		else
-			MGB_TRY(chain_dp(A, max_gap_ref, max_gap_qry, o.bw, o.max_lc_skip, o.max_lc_iter, o.min_lc_cnt, o.min_lc_score,
-							 o.chn_pen_gap, o.chn_pen_skip, is_splice, 1, n_a, a, &n_lc, &u, &n_a_new));
-	}
-	m.n_u0 = n_lc;
-	unsigned long long t1 = prof_clock();
-	prof_add(c, PROF_CHAIN_DP_CYC, t1 - t0);
-	// long-join rescue (reference: map-algo.c:407-417)
-	if (o.bw_long > o.bw && (o.flag & (F_SPLICE | F_SR)) == 0 && n_lc > 1) {
-		int32_t st = (int32_t)a[0].y, en = (int32_t)a[(int32_t)u[0] - 1].y;
-		if (qlen - (en - st) > o.rmq_rescue_size || (float)(qlen - (en - st)) > (float)qlen * o.rmq_rescue_ratio) {
-			int64_t n2 = 0;
-			for (int32_t i = 0; i < n_lc; ++i) n2 += (int32_t)u[i];
-			A.top = mark;
-			MGB_TRY(radix_sort_128x(A, a, n2));
-			MGB_TRY(chain_rmq(A, o.max_gap, o.max_gap_pre, o.bw_long, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
-							  o.chn_pen_gap, o.chn_pen_skip, n2, a, &n_lc, &u, &n_a_new));
-		}
-	}
-	unsigned long long t2 = prof_clock();
-	prof_add(c, PROF_CHAIN_RMQ_CYC, t2 - t1);
 	m.n_a = n_lc > 0? n_a_new : 0;
 	m.n_lc = 0;
 	if (n_lc > 0) {
@@ -195,9 +150,90 @@ MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A)
 		for (int32_t i = 0; i < n_lc; ++i) dst[i] = lc[i];
 		m.n_lc = n_lc;
 	}
-	prof_add(c, PROF_CHAIN_POST_CYC, prof_clock() - t2);
-	A.top = mark;
 	return 0;
+}
+
+// K4/K5 for one read: seeds -> linear chains.  Anchors are compacted in place; chains go to the lchain pool.
+// Warp-uniform: all lanes enter; the RMQ chaining is warp-cooperative, the rest runs on lane 0 and its few scalar
+// results are broadcast.
+MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A, int lane)
+{
+	ReadMeta &m = c.meta[rid];
+	const MapOptDev &o = c.opt;
+	if (m.status != 0) return 0;
+	uint64_t mark = A.top;
+	int32_t qlen = c.b.seq_len[rid];
+	u128 *a = c.anchor + m.a_off;
+	int64_t n_a = m.n_a;
+	int32_t n_lc = 0, n_a_new = 0;
+	uint64_t *u = 0;
+	const int is_splice = !!(o.flag & F_SPLICE), is_sr = !!(o.flag & F_SR);
+	int max_gap_qry, max_gap_ref;
+	// reference: map-algo.c:377-386
+	if (is_sr) max_gap_qry = qlen > o.max_gap? qlen : o.max_gap;
+	else max_gap_qry = o.max_gap;
+	if (o.max_gap_ref > 0) max_gap_ref = o.max_gap_ref;
+	else if (o.max_frag_len > 0) {
+		max_gap_ref = o.max_frag_len - qlen;
+		if (max_gap_ref < o.max_gap) max_gap_ref = o.max_gap;
+	} else max_gap_ref = o.max_gap;
+
+	unsigned long long t0 = prof_clock();
+	if (n_a > 0) {
+		if (o.flag & F_RMQ) {
+			MGB_TRY(chain_rmq_w(A, o.max_gap, o.max_gap_pre, o.bw, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
+								o.chn_pen_gap, o.chn_pen_skip, n_a, a, &n_lc, &u, &n_a_new, lane));
+		} else {
+			int rc = 0;
+			if (lane == 0) {
+				Arena B = A;
+				rc = chain_dp(B, max_gap_ref, max_gap_qry, o.bw, o.max_lc_skip, o.max_lc_iter, o.min_lc_cnt, o.min_lc_score,
+							  o.chn_pen_gap, o.chn_pen_skip, is_splice, 1, n_a, a, &n_lc, &u, &n_a_new);
+				if (B.peak > A.peak) A.peak = B.peak;
+			}
+			rc = warp_bcast_i32(rc, 0), n_lc = warp_bcast_i32(n_lc, 0), n_a_new = warp_bcast_i32(n_a_new, 0);
+			warp_sync();
+			if (rc < 0) return rc;
+			// chain_dp() leaves u[] in a block of n_a words at the caller's top: same address on every lane
+			u = (uint64_t*)(A.base + A.top);
+			A.top += ((uint64_t)n_a * 8 + 15) & ~(uint64_t)15;
+		}
+	}
+	if (lane == 0) m.n_u0 = n_lc;
+	unsigned long long t1 = prof_clock();
+	if (lane == 0) prof_add(c, PROF_CHAIN_DP_CYC, t1 - t0);
+	// long-join rescue (reference: map-algo.c:407-417)
+	if (o.bw_long > o.bw && (o.flag & (F_SPLICE | F_SR)) == 0 && n_lc > 1) {
+		int32_t st = (int32_t)a[0].y, en = (int32_t)a[(int32_t)u[0] - 1].y;
+		if (qlen - (en - st) > o.rmq_rescue_size || (float)(qlen - (en - st)) > (float)qlen * o.rmq_rescue_ratio) {
+			int64_t n2 = 0;
+			for (int32_t i = 0; i < n_lc; ++i) n2 += (int32_t)u[i];
+			A.top = mark;
+			int rc = 0;
+			if (lane == 0) {
+				Arena B = A;
+				rc = radix_sort_128x(B, a, n2);
+				if (B.peak > A.peak) A.peak = B.peak;
+			}
+			rc = warp_bcast_i32(rc, 0);
+			warp_sync();
+			if (rc < 0) return rc;
+			MGB_TRY(chain_rmq_w(A, o.max_gap, o.max_gap_pre, o.bw_long, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
+								o.chn_pen_gap, o.chn_pen_skip, n2, a, &n_lc, &u, &n_a_new, lane));
+		}
+	}
+	unsigned long long t2 = prof_clock();
+	int rc = 0;
+	if (lane == 0) {
+		Arena B = A;
+		prof_add(c, PROF_CHAIN_RMQ_CYC, t2 - t1);
+		rc = stage_chain_tail(c, m, B, a, u, n_lc, n_a_new);
+		if (B.peak > A.peak) A.peak = B.peak;
+		prof_add(c, PROF_CHAIN_POST_CYC, prof_clock() - t2);
+	}
+	rc = warp_bcast_i32(rc, 0);
+	A.top = mark;
+	return rc;
 }
 
 } // namespace mgb
