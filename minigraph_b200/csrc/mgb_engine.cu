@@ -272,10 +272,10 @@ MGB_KERNEL(k_gwfa, 8, 4)          // K7a: bridging alignments (graph wavefront),
 MGB_KERNEL(k_gchain_gen, 9, 4)    // K7b: graph-chain materialisation, post filters, mapq, alignment plan
 MGB_KERNEL(k_index_sketch, 3, 8)  // index build: sketch of graph segments
 MGB_KERNEL(k_wfa_small, 4, 4)     // K8a tier 1: small gaps, wavefronts + traceback bytes in shared memory
-MGB_KERNEL(k_wfa_mid, 6, 3)       // K8a tier 2: mid-size gaps, wavefronts in shared memory (blocks of 2 warps)
+MGB_KERNEL(k_wfa_mid, 6, 5)       // K8a tier 2: mid-size gaps, wavefronts in shared memory (blocks of 2 warps)
 MGB_KERNEL(k_wfa_big, 7, 4)       // K8a tier 3: anything else, wavefronts in the worker arena
 MGB_KERNEL(k_finish, 5, 8)        // K8b: CIGAR stitching, ds strings, result blobs
-static const int STAGE_MINB[10] = { 8, 8, 4, 8, 4, 8, 3, 4, 4, 4 };
+static const int STAGE_MINB[10] = { 8, 8, 4, 8, 4, 8, 5, 4, 4, 4 };
 static const int STAGE_WARPS[10] = { 4, 4, 4, 4, 4, 4, 2, 4, 4, 4 };
 template<int STAGE> struct StageKernel;
 template<> struct StageKernel<0> { static void (*get())(LaunchArgs) { return k_seed; } };

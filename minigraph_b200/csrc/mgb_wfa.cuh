@@ -125,10 +125,12 @@ MG_HD inline int wf_traceback(const TB &tb, int32_t n_scores, int32_t tl, const 
 // would exceed TBCAP, or the score reaches 255 -- the reference re-centres its band every 256 scores by inspecting
 // all 17 E/F slices (wf_stripe_shrink), which only wfa_exact() keeps -- and the job moves to the next tier.
 
-template<int W, int MAXLEN, int TBCAP>
+// HS = number of H slices kept in shared memory (17 = all).  With HS = 7 the slices older than 6 scores -- only read
+// once more, as H[s-16] -- live in a ring in the worker arena (coalesced global loads), which halves the footprint.
+template<int W, int MAXLEN, int TBCAP, int HS = 17>
 struct WfSmemLayout {
-	static const int W_ = W, MAXLEN_ = MAXLEN, TBCAP_ = TBCAP;
-	static const int N_INTS = (17 + 3 + 3 + 2 + 2) * W + 2 * 17 + 2;
+	static const int W_ = W, MAXLEN_ = MAXLEN, TBCAP_ = TBCAP, HS_ = HS;
+	static const int N_INTS = (HS + 3 + 3 + 2 + 2) * W + 2 * 17 + 2;
 	static const int SEQ_BYTES = (MAXLEN + WF_SEQ_PAD + 3) / 4 * 4;
 	static const int TB_ROW_BYTES = TBCAP > 0? 256 * 8 : 0; // per score: int32 lo, int32 off
 	static const int BYTES = N_INTS * 4 + 2 * SEQ_BYTES + TB_ROW_BYTES + TBCAP;
@@ -174,13 +176,13 @@ struct WfTbArena { // traceback rows bump-allocated in the worker arena (referen
 	}
 };
 
-template<int W, int MAXLEN, int TBCAP>
+template<int W, int MAXLEN, int TBCAP, int HS>
 MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g, int32_t ql, const char *qs_g, WfResult *r, int lane)
 {
-	typedef WfSmemLayout<W, MAXLEN, TBCAP> LY;
+	typedef WfSmemLayout<W, MAXLEN, TBCAP, HS> LY;
 	if (tl > MAXLEN || ql > MAXLEN) return 1;
 	uint64_t mark = A.top;
-	int32_t *H = smem, *E1 = H + 17 * W, *F1 = E1 + 3 * W, *E2 = F1 + 3 * W, *F2 = E2 + 2 * W;
+	int32_t *H = smem, *E1 = H + HS * W, *F1 = E1 + 3 * W, *E2 = F1 + 3 * W, *F2 = E2 + 2 * W;
 	int32_t *slo = F2 + 2 * W, *shi = slo + 17;
 	char *ts = (char*)(smem + LY::N_INTS), *qs = ts + LY::SEQ_BYTES;
 	int32_t *tb_row = (int32_t*)(qs + LY::SEQ_BYTES); // TBCAP > 0 only
@@ -195,6 +197,8 @@ MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g,
 	AVec<WfTbRow> rows; // TBCAP == 0 only
 	avec_init(rows);
 	if (TBCAP == 0) MGB_TRY(avec_reserve_w(A, rows, 256, lane));
+	int32_t *Hg = 0; // HS < 17: all 17 H slices, written back after their extension
+	if (HS < 17) MGB_ALLOC(A, Hg, int32_t, 17 * W);
 	int32_t n_rows = 0, tb_used = 0;
 	int32_t wlo = 0, whi = 0, last_state = 0, s = 0;
 	if (lane == 0) {
@@ -206,7 +210,7 @@ MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g,
 	for (;;) {
 		const int hs = s % 17;
 		const int32_t plo = slo[hs], phi = shi[hs];
-		int32_t *Hs = H + hs * W;
+		int32_t *Hs = H + (s % HS) * W;
 		int hit = 0, hit_noext = 0;
 		for (int32_t d = plo + lane; d <= phi; d += MGB_W) {
 			int32_t k0 = Hs[wfs_col<W>(d)];
@@ -216,6 +220,9 @@ MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g,
 			else Hs[wfs_col<W>(d)] = k;
 		}
 		warp_sync();
+		if (HS < 17) { // final values of this slice go to the global ring (read again 16 scores later)
+			for (int32_t d = plo + lane; d <= phi; d += MGB_W) Hg[hs * W + wfs_col<W>(d)] = Hs[wfs_col<W>(d)];
+		}
 		if (warp_any(hit)) {
 			if (warp_any(hit && hit_noext)) { // no extension on the last diagonal: the state comes from the traceback byte
 				int32_t x;
@@ -244,10 +251,10 @@ MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g,
 			ax = x - lo;
 		}
 		++n_rows;
-		const WfSrc sHx = wfs_src<W>(H, 17, slo, shi, ns - WF_X), sHo1 = wfs_src<W>(H, 17, slo, shi, ns - (WF_O1 + WF_E1)),
-					sHo2 = wfs_src<W>(H, 17, slo, shi, ns - (WF_O2 + WF_E2)), sE1 = wfs_src<W>(E1, 3, slo, shi, ns - WF_E1),
+		const WfSrc sHx = wfs_src<W>(H, HS, slo, shi, ns - WF_X), sHo1 = wfs_src<W>(H, HS, slo, shi, ns - (WF_O1 + WF_E1)),
+					sHo2 = HS < 17? wfs_src<W>(Hg, 17, slo, shi, ns - (WF_O2 + WF_E2)) : wfs_src<W>(H, 17, slo, shi, ns - (WF_O2 + WF_E2)), sE1 = wfs_src<W>(E1, 3, slo, shi, ns - WF_E1),
 					sF1 = wfs_src<W>(F1, 3, slo, shi, ns - WF_E1), sE2 = wfs_src<W>(E2, 2, slo, shi, ns - WF_E2), sF2 = wfs_src<W>(F2, 2, slo, shi, ns - WF_E2);
-		int32_t *nH = H + nhs * W, *nE1 = E1 + (ns % 3) * W, *nF1 = F1 + (ns % 3) * W, *nE2 = E2 + (ns % 2) * W, *nF2 = F2 + (ns % 2) * W;
+		int32_t *nH = H + (ns % HS) * W, *nE1 = E1 + (ns % 3) * W, *nF1 = F1 + (ns % 3) * W, *nE2 = E2 + (ns % 2) * W, *nF2 = F2 + (ns % 2) * W;
 		for (int32_t d = lo + lane; d <= hi; d += MGB_W) { // reference: miniwfa.c:281-308 wf_next_tb
 			int32_t h, f, e, e1, e2, f1, f2, a0, b0;
 			uint8_t x = 0, ze, zf, z;
@@ -513,7 +520,7 @@ MG_HD inline int wfa_exact(Arena &A, int32_t tl, const char *ts_g, int32_t ql, c
 }
 
 // the tiers of the job kernels (K8a)
-typedef WfSmemLayout<64, 256, 4096> WfTier1;   // small gaps: 4 warps per block, traceback bytes in shared memory
-typedef WfSmemLayout<256, 1024, 0> WfTier2;    // mid-size gaps: 2 warps per block, traceback rows in the arena
+typedef WfSmemLayout<64, 256, 4096, 17> WfTier1;  // small gaps: 4 warps per block, traceback bytes in shared memory
+typedef WfSmemLayout<256, 1024, 0, 7> WfTier2;    // mid-size gaps: 2 warps per block, old H slices + traceback rows in the arena
 
 } // namespace mgb
