@@ -148,6 +148,7 @@ def main():
     from minigraph_b200 import capi, options
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there otherwise)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = capi.load_product()
     lib.mgb_set_param(b"device", local_rank)

@@ -217,6 +217,10 @@ typedef struct {
 	uint64_t prof[32];      /* device cycle counters per phase (see mgb_pipeline.cuh PROF_*) */
 } mgb_stats_t;
 
+/* test hook: align one gap through the tier-3 WFA path (exact up to max_iter cells, then the reference's chaining
+ * heuristic, miniwfa.c:824-834, with checkpoints every `step` scores); returns n_cigar (len<<4|op) or a negative code */
+int mgb_test_wfa(const char *ts, int tl, const char *qs, int ql, int64_t max_iter, int step, uint32_t *cigar, int cap, int *score);
+
 const char *mgb_last_error(void);
 void mgb_get_stats(const mg_idx_t *gi, mgb_stats_t *st);
 /* knobs: "arena_mb" (per worker), "workers_per_sm", "device"; returns 0 if the key is known */

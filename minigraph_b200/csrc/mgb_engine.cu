@@ -946,4 +946,47 @@ extern "C" mg_gchains_t *mg_map(const mg_idx_t *gi, int qlen, const char *seq, m
 	return gcs;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// test hook: one gap alignment through the tier-3 path (exact WFA capped at max_iter cells, then the chaining
+// heuristic with low-memory checkpoints every `step` scores), reference: miniwfa.c:824-834 mwf_wfa_auto
+// ---------------------------------------------------------------------------------------------------------------
+struct TestWfaArgs { const char *ts, *qs; int32_t tl, ql, step, cap; int64_t max_iter; uint32_t *cigar; int32_t *out; char *arena; uint64_t arena_bytes; };
+MG_HD inline void test_wfa_body(const TestWfaArgs &t, int lane)
+{
+	Arena A;
+	arena_init(A, t.arena, t.arena_bytes);
+	WfResult r;
+	int rc = wfa_exact(A, t.tl, t.ts, t.ql, t.qs, t.max_iter, &r, lane, t.step);
+	if (rc == 0 && r.n_cigar <= t.cap) for (int32_t i = lane; i < r.n_cigar; i += MGB_W) t.cigar[i] = r.cigar[i];
+	if (lane == 0) t.out[0] = rc, t.out[1] = rc == 0? r.n_cigar : 0, t.out[2] = rc == 0? r.s : 0;
+}
+#ifndef MGB_HOSTSIM
+__global__ void k_test_wfa(TestWfaArgs t) { test_wfa_body(t, threadIdx.x & 31); }
+#endif
+extern "C" int mgb_test_wfa(const char *ts, int tl, const char *qs, int ql, int64_t max_iter, int step, uint32_t *cigar, int cap, int *score)
+{
+	if (!dev_ok()) { set_error("no CUDA device available: libmgb200 has no CPU path"); return -100; }
+	TestWfaArgs t;
+	t.tl = tl, t.ql = ql, t.step = step, t.cap = cap, t.max_iter = max_iter, t.arena_bytes = (uint64_t)1 << 30;
+	char *d_ts = (char*)dmalloc((size_t)tl + 64), *d_qs = (char*)dmalloc((size_t)ql + 64);
+	h2d(d_ts, ts, (size_t)tl), h2d(d_qs, qs, (size_t)ql);
+	t.ts = d_ts, t.qs = d_qs;
+	t.cigar = (uint32_t*)dmalloc(sizeof(uint32_t) * (size_t)cap);
+	t.out = (int32_t*)dmalloc(sizeof(int32_t) * 4);
+	t.arena = (char*)dmalloc(t.arena_bytes);
+#ifdef MGB_HOSTSIM
+	test_wfa_body(t, 0);
+#else
+	k_test_wfa<<<1, 32>>>(t);
+	CUDA_OK(cudaGetLastError());
+	dsync();
+#endif
+	int32_t out[4];
+	d2h(out, t.out, sizeof(out));
+	if (out[0] == 0 && out[1] <= cap) d2h(cigar, t.cigar, sizeof(uint32_t) * (size_t)out[1]);
+	*score = out[2];
+	dfree(d_ts), dfree(d_qs), dfree(t.cigar), dfree(t.out), dfree(t.arena);
+	return out[0] < 0? out[0] : out[1];
+}
+
 extern "C" void mgb_get_stats(const mg_idx_t *gi, mgb_stats_t *st) { *st = model_of(gi)->stats; }

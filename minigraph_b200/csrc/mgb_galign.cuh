@@ -178,7 +178,7 @@ MG_HD inline int wfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int la
 #if !MGB_ON_DEVICE && defined(MGB_HOSTSIM)
 	if (getenv("MGB_DUMP_JOBS")) fprintf(stderr, "JOB\t%d\t%d\t%d\t%ld\t%d\t%d\n", tl, ql, rst.s, (long)rst.n_iter, rst.n_cigar, tier);
 #endif
-	if (rst.s < 0) return MGB_E_UNSUPPORTED; // TODO(round 2): chaining heuristic of the reference (miniwfa.c:776-834)
+	if (rst.s < 0) return MGB_E_INTERNAL;
 	int64_t coff = 0;
 	if (lane == 0) coff = pool_alloc(c.pool_cig, (uint64_t)rst.n_cigar * 4);
 	coff = (int64_t)warp_bcast_u64((uint64_t)coff, 0);

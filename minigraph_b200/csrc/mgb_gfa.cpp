@@ -375,20 +375,20 @@ extern "C" void mgb_gfa_destroy(gfa_t *g)
 
 namespace {
 
-struct Str { char **buf; size_t *len, *cap; };
+struct Str { char *b; size_t l, m; }; // local copy of the caller's buffer: keeps pointer and length in registers
 
 inline void s_reserve(Str &s, size_t extra)
 {
-	if (*s.len + extra + 1 > *s.cap) {
-		size_t c = *s.cap? *s.cap : 256;
-		while (c < *s.len + extra + 1) c <<= 1;
-		*s.buf = (char*)realloc(*s.buf, c);
-		*s.cap = c;
+	if (s.l + extra + 1 > s.m) {
+		size_t c = s.m? s.m : 256;
+		while (c < s.l + extra + 1) c <<= 1;
+		s.b = (char*)realloc(s.b, c);
+		s.m = c;
 	}
 }
-inline void s_putc(Str &s, char c) { s_reserve(s, 1); (*s.buf)[(*s.len)++] = c; }
-inline void s_puts(Str &s, const char *p) { size_t l = strlen(p); s_reserve(s, l); memcpy(*s.buf + *s.len, p, l); *s.len += l; }
-inline void s_putn(Str &s, const char *p, size_t l) { s_reserve(s, l); memcpy(*s.buf + *s.len, p, l); *s.len += l; }
+inline void s_putc(Str &s, char c) { s_reserve(s, 1); s.b[s.l++] = c; }
+inline void s_puts(Str &s, const char *p) { size_t l = strlen(p); s_reserve(s, l); memcpy(s.b + s.l, p, l); s.l += l; }
+inline void s_putn(Str &s, const char *p, size_t l) { s_reserve(s, l); memcpy(s.b + s.l, p, l); s.l += l; }
 inline void s_putd(Str &s, int c)
 {
 	char b[16];
@@ -397,7 +397,15 @@ inline void s_putd(Str &s, int c)
 	do { b[l++] = (char)(x % 10 + '0'); x /= 10; } while (x > 0);
 	if (c < 0) b[l++] = '-';
 	s_reserve(s, (size_t)l);
-	for (int i = l - 1; i >= 0; --i) (*s.buf)[(*s.len)++] = b[i];
+	for (int i = l - 1; i >= 0; --i) s.b[s.l++] = b[i];
+}
+// unchecked variants for the bulk fields (capacity reserved by the caller)
+inline void u_putd(Str &s, unsigned x)
+{
+	char b[12];
+	int l = 0;
+	do { b[l++] = (char)(x % 10 + '0'); x /= 10; } while (x > 0);
+	while (l > 0) s.b[s.l++] = b[--l];
 }
 inline void s_seg(Str &s, char sign, const char *name, int st, int en) { s_putc(s, sign); s_puts(s, name); s_putc(s, ':'); s_putd(s, st); s_putc(s, '-'); s_putd(s, en); }
 
@@ -421,12 +429,13 @@ const uint64_t F_WRITE_LCHAIN = 0x800000, F_WRITE_MZ = 0x1000000;
 
 extern "C" void mgb_write_gaf(char **buf, size_t *len, size_t *cap, const gfa_t *g, const mg_gchains_t *gs, int32_t qlen, const char *qname, uint64_t flag)
 {
-	Str s = { buf, len, cap };
+	Str s = { *buf, *len, *cap };
+	struct Sync { Str &s; char **b; size_t *l, *m; ~Sync() { *b = s.b, *l = s.l, *m = s.m; } } sync_back = { s, buf, len, cap };
 	int32_t rev_sign = 0; // sticky across the records of one read, like the reference (format.c:123)
 	if (!g_comp_init) init_comp();
 	if ((gs == 0 || gs->n_gc == 0) && (flag & F_SHOW_UNMAP)) {
 		s_puts(s, qname); s_putc(s, '\t'); s_putd(s, qlen); s_puts(s, "\t0\t0\t*\t*\t0\t0\t0\t0\t0\t0\n");
-		(*s.buf)[*s.len] = 0;
+		s.b[s.l] = 0;
 		return;
 	}
 	if (gs == 0) return;
@@ -438,7 +447,7 @@ extern "C" void mgb_write_gaf(char **buf, size_t *len, size_t *cap, const gfa_t 
 		if (p->cnt == 0) continue;
 		s_puts(s, qname);
 		s_putc(s, '\t'); s_putd(s, qlen); s_putc(s, '\t'); s_putd(s, p->qs); s_putc(s, '\t'); s_putd(s, p->qe); s_puts(s, "\t+\t");
-		sign_pos = *s.len - 2;
+		sign_pos = s.l - 2;
 		if (flag & F_VERTEX_COOR) {
 			compact = 0;
 			for (int32_t j = 0; j < p->cnt; ++j) {
@@ -484,7 +493,7 @@ extern "C" void mgb_write_gaf(char **buf, size_t *len, size_t *cap, const gfa_t 
 			s_puts(s, ps->name); s_putc(s, '\t'); s_putd(s, ps->max); s_putc(s, '\t');
 			if (rev) {
 				rev_sign = 1;
-				(*s.buf)[sign_pos] = '-';
+				s.b[sign_pos] = '-';
 				s_putd(s, t->soff + (p->plen - p->pe)); s_putc(s, '\t'); s_putd(s, t->soff + (p->plen - p->ps));
 			} else {
 				s_putd(s, t->soff + p->ps); s_putc(s, '\t'); s_putd(s, t->soff + p->pe);
@@ -503,13 +512,15 @@ extern "C" void mgb_write_gaf(char **buf, size_t *len, size_t *cap, const gfa_t 
 		}
 		if (p->p) {
 			s_puts(s, "\tcg:Z:");
+			s_reserve(s, (size_t)p->p->n_cigar * 12 + 16);
 			if (rev_sign)
-				for (int32_t j = p->p->n_cigar - 1; j >= 0; --j) { s_putd(s, (int32_t)(p->p->cigar[j] >> 4)); s_putc(s, "MIDNSHP=XB"[p->p->cigar[j] & 0xf]); }
+				for (int32_t j = p->p->n_cigar - 1; j >= 0; --j) { u_putd(s, (unsigned)(p->p->cigar[j] >> 4)); s.b[s.l++] = "MIDNSHP=XB"[p->p->cigar[j] & 0xf]; }
 			else
-				for (int32_t j = 0; j < p->p->n_cigar; ++j) { s_putd(s, (int32_t)(p->p->cigar[j] >> 4)); s_putc(s, "MIDNSHP=XB"[p->p->cigar[j] & 0xf]); }
+				for (int32_t j = 0; j < p->p->n_cigar; ++j) { u_putd(s, (unsigned)(p->p->cigar[j] >> 4)); s.b[s.l++] = "MIDNSHP=XB"[p->p->cigar[j] & 0xf]; }
 		}
 		if (p->ds.ds) {
 			s_puts(s, "\tds:Z:");
+			s_reserve(s, (size_t)p->ds.len + 16);
 			if (rev_sign) {
 				const char *ds = p->ds.ds;
 				for (int32_t k = p->ds.n_off - 1; k >= 0; --k) {
@@ -528,7 +539,7 @@ extern "C" void mgb_write_gaf(char **buf, size_t *len, size_t *cap, const gfa_t 
 						}
 					}
 				}
-			} else s_putn(s, p->ds.ds, strlen(p->ds.ds));
+			} else s_putn(s, p->ds.ds, (size_t)p->ds.len);
 		}
 		s_putc(s, '\n');
 		if (flag & F_WRITE_LCHAIN) { // -S / --write-mz (format.c:252-289)
@@ -570,7 +581,7 @@ extern "C" void mgb_write_gaf(char **buf, size_t *len, size_t *cap, const gfa_t 
 		}
 	}
 	s_reserve(s, 1);
-	(*s.buf)[*s.len] = 0;
+	s.b[s.l] = 0;
 	(void)F_FRAG_MERGE;
 }
 
@@ -588,6 +599,12 @@ extern "C" void mgb_write_gaf_batch(const gfa_t *g, int n_reads, mg_gchains_t *c
 	auto work = [&](int t) {
 		int64_t b = t * chunk, e = b + chunk < n_reads? b + chunk : n_reads;
 		Part &p = part[(size_t)t];
+		size_t est = 0;
+		for (int64_t i = b; i < e; ++i) {
+			est += 256;
+			if (gcs[i]) for (int32_t k = 0; k < gcs[i]->n_gc; ++k) est += 512 + (gcs[i]->gc[k].p? (size_t)gcs[i]->gc[k].p->n_cigar * 8 : 0) + (size_t)gcs[i]->gc[k].ds.len;
+		}
+		p.buf = (char*)malloc(est), p.cap = est;
 		for (int64_t i = b; i < e; ++i)
 			mgb_write_gaf(&p.buf, &p.len, &p.cap, g, gcs[i], qlens[i], names && names[i]? names[i] : "*", flag);
 	};

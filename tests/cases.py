@@ -90,3 +90,66 @@ def case_struct_random(lib, workdir, n_reads=150, seed=23):
         d = T.diff_results(a, b)
         assert d is None, "read %d (%s): %s" % (i, names[i], d)
     return st
+
+
+def case_wfa_fallback(lib, n_cases=12, seed=5):
+    """gaps whose exact WFA exceeds the cell cap take the reference's chaining heuristic + low-memory checkpoints
+    (miniwfa.c:551-601,776-834): same CIGAR and score as mwf_wfa_exact(max_iter) -> mwf_wfa_chain(step) of the reference"""
+    import ctypes as C
+    import random
+    ref = T.load_ref()
+
+    class mwf_opt_t(C.Structure):
+        _fields_ = [("flag", C.c_int32), ("x", C.c_int32), ("o1", C.c_int32), ("e1", C.c_int32), ("o2", C.c_int32), ("e2", C.c_int32),
+                    ("step", C.c_int32), ("max_s", C.c_int32), ("max_iter", C.c_int64), ("max_occ", C.c_int32), ("kmer", C.c_int32), ("min_len", C.c_int32)]
+
+    class mwf_rst_t(C.Structure):
+        _fields_ = [("s", C.c_int32), ("n_cigar", C.c_int32), ("n_iter", C.c_int64), ("cigar", C.POINTER(C.c_uint32))]
+    for f in (ref.mwf_wfa_exact, ref.mwf_wfa_chain):
+        f.restype = None
+        f.argtypes = [C.c_void_p, C.POINTER(mwf_opt_t), C.c_int32, C.c_char_p, C.c_int32, C.c_char_p, C.POINTER(mwf_rst_t)]
+    ref.mwf_opt_init.argtypes = [C.POINTER(mwf_opt_t)]
+    rng = random.Random(seed)
+
+    def mutate(s, rate):
+        out = []
+        for c in s:
+            u = rng.random()
+            if u < rate * 0.4:
+                out.append(rng.choice("ACGT"))
+            elif u < rate * 0.7:
+                continue
+            elif u < rate:
+                out.append(c)
+                out.append(rng.choice("ACGT"))
+            else:
+                out.append(c)
+        return "".join(out)
+    n_fallback = 0
+    for it in range(n_cases):
+        n = rng.choice([300, 900, 2500])
+        t = "".join(rng.choice("ACGT") for _ in range(n))
+        blocks = [mutate(t[i:i + 200], rng.choice([0.02, 0.1, 0.3])) if rng.random() < 0.8 else "".join(rng.choice("ACGT") for _ in range(rng.choice([50, 300])))
+                  for i in range(0, n, 200)]
+        q = "".join(blocks)
+        ts, qs = t.encode(), q.encode()
+        max_iter, step = rng.choice([(2000, 40), (20000, 25), (50000, 100), (10 ** 8, 5000)])
+        opt = mwf_opt_t()
+        ref.mwf_opt_init(C.byref(opt))
+        opt.flag |= 1
+        opt.step, opt.max_iter = 0, max_iter
+        rst = mwf_rst_t()
+        ref.mwf_wfa_exact(None, C.byref(opt), len(ts), ts, len(qs), qs, C.byref(rst))
+        if rst.s < 0:
+            n_fallback += 1
+            opt.step, opt.max_iter = step, -1
+            ref.mwf_wfa_chain(None, C.byref(opt), len(ts), ts, len(qs), qs, C.byref(rst))
+        want = [rst.cigar[i] for i in range(rst.n_cigar)]
+        cap = len(ts) + len(qs) + 8
+        buf = (C.c_uint32 * cap)()
+        score = C.c_int(0)
+        nc = lib.mgb_test_wfa(ts, len(ts), qs, len(qs), max_iter, step, buf, cap, C.byref(score))
+        assert nc >= 0, (it, nc)
+        got = [buf[i] for i in range(nc)]
+        assert got == want and score.value == rst.s, "case %d (tl=%d ql=%d max_iter=%d step=%d): score %d vs %d" % (it, len(ts), len(qs), max_iter, step, score.value, rst.s)
+    assert n_fallback >= 3

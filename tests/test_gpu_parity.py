@@ -49,3 +49,8 @@ def test_index_matches_oracle_sketch(lib):
     orc.orc_sketch.restype = C.c_int64
     orc.orc_sketch.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int64]
     test_oracle.check_index(lib, orc)
+
+
+@pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not shipped")
+def test_wfa_iteration_cap_fallback(lib):
+    cases.case_wfa_fallback(lib, n_cases=10)

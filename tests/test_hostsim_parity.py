@@ -35,3 +35,8 @@ def test_edge_reads(lib, workdir):
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
 def test_struct_fields_vs_reference(lib, workdir):
     cases.case_struct_random(lib, workdir, n_reads=60)
+
+
+@pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
+def test_wfa_iteration_cap_fallback(lib):
+    cases.case_wfa_fallback(lib)
