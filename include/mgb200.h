@@ -202,6 +202,8 @@ int mg_map_batch(const mg_idx_t *gi, int n_reads, const int *qlens, const char *
 typedef struct {
 	double t_h2d_ms, t_seed_ms, t_chain_ms, t_align_ms, t_d2h_ms, t_host_ms; /* last batch, CUDA events / host clock */
 	double t_wfa_ms, t_finish_ms; /* t_align_ms = graph chaining + alignment plan; t_wfa_ms = gap alignment jobs; t_finish_ms = cigar/ds/blob */
+	double t_dev_span_ms;   /* device time from the first kernel start to the last kernel end over all sub-batches (they overlap) */
+	int64_t n_slots;        /* sub-batches the batch was cut into (each on its own stream and host thread) */
 	double t_pack_ms, t_asm_ms; /* host: packing reads into the staging buffer; building mg_gchains_t objects */
 	int64_t n_jobs;         /* WFA jobs of the batch */
 	int64_t n_jobs_mid, n_jobs_big; /* jobs that went to tier 2 / tier 3 */
@@ -214,6 +216,7 @@ typedef struct {
 	int64_t n_launches;     /* kernels launched for the batch */
 	int64_t n_retry;        /* reads re-run with a larger arena */
 	uint64_t arena_peak;    /* largest per-worker arena use */
+	double t_kernel_ms[10]; /* CUDA-event time of each kernel of the first pass: k_seed, k_chain, k_gchain, (index), k_wfa_small, k_finish, k_wfa_mid, k_wfa_big, k_gwfa, k_gchain_gen */
 	uint64_t prof[32];      /* device cycle counters per phase (see mgb_pipeline.cuh PROF_*) */
 } mgb_stats_t;
 

@@ -59,6 +59,9 @@ MG_D inline uint64_t warp_bcast_u64(uint64_t x, int src) { return __shfl_sync(0x
 MG_D inline int32_t warp_min_i32(int32_t x) { for (int o = 16; o > 0; o >>= 1) { int32_t y = __shfl_xor_sync(0xffffffffu, x, o); x = y < x? y : x; } return x; }
 MG_D inline int32_t warp_max_i32(int32_t x) { for (int o = 16; o > 0; o >>= 1) { int32_t y = __shfl_xor_sync(0xffffffffu, x, o); x = y > x? y : x; } return x; }
 MG_D inline int32_t warp_sum_i32(int32_t x) { for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o); return x; }
+MG_D inline uint32_t warp_ballot(int pred) { return __ballot_sync(0xffffffffu, pred); }
+MG_D inline int mask_rank(uint32_t mask, int lane) { return __popc(mask & ((1u << lane) - 1u)); } // set bits below `lane`
+MG_D inline int mask_count(uint32_t mask) { return __popc(mask); }
 #else
 #define MGB_W 1
 inline void warp_sync() {}
@@ -68,6 +71,9 @@ inline uint64_t warp_bcast_u64(uint64_t x, int) { return x; }
 inline int32_t warp_min_i32(int32_t x) { return x; }
 inline int32_t warp_max_i32(int32_t x) { return x; }
 inline int32_t warp_sum_i32(int32_t x) { return x; }
+inline uint32_t warp_ballot(int pred) { return pred? 1u : 0u; }
+inline int mask_rank(uint32_t, int) { return 0; }
+inline int mask_count(uint32_t mask) { return (int)(mask & 1u); }
 #endif
 
 // ---- bump arena: one per worker (warp), stack discipline via mark/release ----

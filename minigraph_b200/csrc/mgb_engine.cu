@@ -13,6 +13,8 @@
 #include <string>
 #include <chrono>
 #include <thread>
+#include <mutex>
+#include <functional>
 
 #include "../../include/mgb200.h"
 #include "mgb_galign.cuh"
@@ -36,7 +38,9 @@ static int64_t p_workers_per_sm = 32;
 static int64_t p_device = 0;
 static int64_t p_block_warps = 4;
 static int64_t p_host_threads = 0; // 0: min(16, hardware threads)
-static int64_t p_thread_mask = 0;      // bit s set: stage s runs one item per thread instead of one per warp
+static int64_t p_thread_mask = 0;
+extern int p_slots; extern int64_t p_min_slot_reads;
+static int64_t p_slot_workers = 0;      // bit s set: stage s runs one item per thread instead of one per warp
 
 extern "C" const char *mgb_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char *mgb_version(void) { return "mgb200-r1"; }
@@ -49,6 +53,9 @@ extern "C" int mgb_set_param(const char *key, int64_t value)
 	else if (!strcmp(key, "block_warps")) p_block_warps = value;
 	else if (!strcmp(key, "host_threads")) p_host_threads = value;
 	else if (!strcmp(key, "thread_mask")) p_thread_mask = value;
+	else if (!strcmp(key, "slots")) p_slots = (int)value;
+	else if (!strcmp(key, "slot_workers")) p_slot_workers = value;
+	else if (!strcmp(key, "min_slot_reads")) p_min_slot_reads = value;
 	else return -1;
 	return 0;
 }
@@ -70,6 +77,8 @@ static int dev_sm_count() { return 2; }
 static size_t dev_free_mem() { return (size_t)8 << 30; }
 #else
 #define CUDA_OK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { set_error(std::string(#call) + ": " + cudaGetErrorString(_e)); abort(); } } while (0)
+// every host thread that drives a slot of the batch pipeline works on its own stream
+static thread_local cudaStream_t t_stream = 0;
 static bool dev_ok()
 {
 	int n = 0;
@@ -79,12 +88,12 @@ static bool dev_ok()
 }
 static void *dmalloc(size_t n) { void *p = 0; CUDA_OK(cudaMalloc(&p, n? n : 16)); return p; }
 static void dfree(void *p) { if (p) cudaFree(p); }
-static void h2d(void *d, const void *h, size_t n) { if (n) CUDA_OK(cudaMemcpy(d, h, n, cudaMemcpyHostToDevice)); }
-static void d2h(void *h, const void *d, size_t n) { if (n) CUDA_OK(cudaMemcpy(h, d, n, cudaMemcpyDeviceToHost)); }
-static void dzero(void *d, size_t n) { if (n) CUDA_OK(cudaMemset(d, 0, n)); }
-static void dfill(void *d, int v, size_t n) { if (n) CUDA_OK(cudaMemset(d, v, n)); }
-static void dsync() { CUDA_OK(cudaDeviceSynchronize()); }
-static int dev_sm_count() { int v = 0; CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, (int)p_device)); return v; }
+static void dsync() { CUDA_OK(cudaStreamSynchronize(t_stream)); }
+static void h2d(void *d, const void *h, size_t n) { if (n) { CUDA_OK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, t_stream)); dsync(); } }
+static void d2h(void *h, const void *d, size_t n) { if (n) { CUDA_OK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, t_stream)); dsync(); } }
+static void dzero(void *d, size_t n) { if (n) CUDA_OK(cudaMemsetAsync(d, 0, n, t_stream)); }
+static void dfill(void *d, int v, size_t n) { if (n) CUDA_OK(cudaMemsetAsync(d, v, n, t_stream)); }
+static int dev_sm_count() { static int v = 0; if (v == 0) CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, (int)p_device)); return v; }
 static size_t dev_free_mem() { size_t f = 0, t = 0; CUDA_OK(cudaMemGetInfo(&f, &t)); return f; }
 #endif
 
@@ -306,7 +315,7 @@ static void launch_stage(LaunchArgs &L, const Workers &W)
 #ifdef MGB_HOSTSIM
 	Arena A;
 	arena_init(A, W.arena, W.arena_bytes);
-	std::vector<int32_t> sim_smem((WfTier1::STRIDE > WfTier2::STRIDE? WfTier1::STRIDE : WfTier2::STRIDE) / 4);
+	std::vector<int32_t> sim_smem(std::max<size_t>(std::max<size_t>(WfTier1::STRIDE, WfTier2::STRIDE), GWFA_SMEM_ARENA) / 4);
 	for (int it = 0; it < L.n_work; ++it) {
 		int item = L.rid_list? L.rid_list[it] : it;
 		A.top = 0;
@@ -325,7 +334,7 @@ static void launch_stage(LaunchArgs &L, const Workers &W)
 	L.thread_mode = (p_thread_mask >> STAGE) & 1;
 	if (MGB_IS_WARP(STAGE)) L.thread_mode = 0;
 	if (L.thread_mode) smem = 0;
-	kern<<<blocks, threads, smem>>>(L);
+	kern<<<blocks, threads, smem, t_stream>>>(L);
 	CUDA_OK(cudaGetLastError());
 #endif
 }
@@ -355,8 +364,23 @@ struct Model {
 	std::vector<float> logf_tab; float *d_logf; int n_logf;
 	mgb_stats_t stats;
 	gfa_edseq_t *es;
-	// grow-only buffers reused by every batch
-	GrowBuf h_seq{true}, h_out{true}, d_seq, d_meta, d_routs, d_small, d_jobq, d_pool[10];
+	// the batch pipeline: a batch is cut into sub-batches, each driven by its own host thread on its own stream ("slot"),
+	// so that kernels, copies and host-side result assembly of different sub-batches overlap
+	struct Slot {
+		GrowBuf h_seq{true}, h_out{true}, h_small{true}, d_seq, d_meta, d_routs, d_small, d_jobq, d_pool[10];
+		Workers W;
+		mgb_stats_t st;
+		double ev_first_ms, ev_last_ms; // first kernel start / last kernel end relative to the batch reference event
+#ifndef MGB_HOSTSIM
+		cudaStream_t stream;
+		cudaEvent_t ev_first, ev_last;
+#endif
+		bool ready;
+		Slot() : ready(false) { memset(&W, 0, sizeof(W)); }
+	};
+	enum { MAX_SLOTS = 8 };
+	Slot slots[MAX_SLOTS];
+	std::mutex big_mutex; // the large-arena retry pass is shared by the slots
 };
 
 static void model_free(Model *M)
@@ -367,8 +391,16 @@ static void model_free(Model *M)
 	if (M->Wbig.arena) dfree(M->Wbig.arena);
 	if (M->Wbig.peak) dfree(M->Wbig.peak);
 	if (M->d_logf) dfree(M->d_logf);
-	M->h_seq.release(), M->h_out.release(), M->d_seq.release(), M->d_meta.release(), M->d_routs.release(), M->d_small.release(), M->d_jobq.release();
-	for (int i = 0; i < 10; ++i) M->d_pool[i].release();
+	for (int k = 0; k < Model::MAX_SLOTS; ++k) {
+		Model::Slot &sl = M->slots[k];
+		sl.h_seq.release(), sl.h_out.release(), sl.h_small.release(), sl.d_seq.release(), sl.d_meta.release(), sl.d_routs.release(), sl.d_small.release(), sl.d_jobq.release();
+		for (int i = 0; i < 10; ++i) sl.d_pool[i].release();
+		if (sl.W.arena) dfree(sl.W.arena);
+		if (sl.W.peak) dfree(sl.W.peak);
+#ifndef MGB_HOSTSIM
+		if (sl.ready) { cudaStreamDestroy(sl.stream); cudaEventDestroy(sl.ev_first); cudaEventDestroy(sl.ev_last); }
+#endif
+	}
 	delete M;
 }
 
@@ -618,15 +650,15 @@ static double now_ms() { return std::chrono::duration<double, std::milli>(std::c
 
 #ifndef MGB_HOSTSIM
 struct EvTimer {
-	cudaEvent_t a, b;
-	EvTimer() { cudaEventCreate(&a); cudaEventCreate(&b); }
+	cudaEvent_t a, b; bool used;
+	EvTimer() : used(false) { cudaEventCreate(&a); cudaEventCreate(&b); }
 	~EvTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
-	void start() { cudaEventRecord(a, 0); }
-	void stop() { cudaEventRecord(b, 0); }
-	double ms() { float t = 0; cudaEventSynchronize(b); cudaEventElapsedTime(&t, a, b); return t; }
+	void start() { cudaEventRecord(a, t_stream); used = true; }
+	void stop() { cudaEventRecord(b, t_stream); }
+	double ms() { if (!used) return 0; float t = 0; cudaEventSynchronize(b); cudaEventElapsedTime(&t, a, b); return t; }
 };
 #else
-struct EvTimer { double t0, t1; void start() { t0 = now_ms(); } void stop() { t1 = now_ms(); } double ms() { return t1 - t0; } };
+struct EvTimer { double t0 = 0, t1 = 0; void start() { t0 = now_ms(); } void stop() { t1 = now_ms(); } double ms() { return t1 - t0; } };
 #endif
 
 static void fill_opt(MapOptDev &o, const mg_mapopt_t *opt, int k)
@@ -684,69 +716,78 @@ static mg_gchains_t *build_result(const ReadOut &ro, const char *pool)
 	return gs;
 }
 
-static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, const char *const *seqs, const char *const *names,
-						  mg_gchains_t **gcs, const mg_mapopt_t *opt)
+int p_slots = 1;              // sub-batches in flight per batch (measured on B200: the kernels already fill the chip, overlap buys nothing)
+int64_t p_min_slot_reads = 512; // do not cut batches into pieces smaller than this
+
+// Map reads [0, n_reads) of one sub-batch on the calling thread's stream (slot `sl`).
+static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads, const int *qlens, const char *const *seqs, const char *const *names,
+					 mg_gchains_t **gcs, int host_threads)
 {
-	Model *M = (Model*)gi->B;
-	mgb_stats_t &S = M->stats;
+	mgb_stats_t &S = sl.st;
 	memset(&S, 0, sizeof(S));
-	for (int i = 0; i < n_reads; ++i) gcs[i] = 0;
+	sl.ev_first_ms = sl.ev_last_ms = 0;
 	if (n_reads <= 0) return 0;
+	const int64_t saved_threads = p_host_threads;
+	(void)saved_threads;
 	double t_host0 = now_ms();
-	double t_pack0 = t_host0;
-	// ---- pack the batch ----
-	std::vector<uint64_t> seq_off(n_reads);
-	std::vector<int32_t> seq_len(n_reads);
-	std::vector<uint32_t> name_hash(n_reads);
+	// ---- pack the sub-batch into page-locked memory ----
 	uint64_t tot = 0;
-	int32_t max_qlen = 0;
+	uint64_t *seq_off; int32_t *seq_len; uint32_t *name_hash;
+	{
+		size_t small = (size_t)n_reads * (8 + 4 + 4) + 256;
+		char *hs = (char*)sl.h_small.ensure(small);
+		seq_off = (uint64_t*)hs, seq_len = (int32_t*)(seq_off + n_reads), name_hash = (uint32_t*)(seq_len + n_reads);
+	}
 	for (int i = 0; i < n_reads; ++i) {
 		seq_off[i] = tot, seq_len[i] = qlens[i];
 		tot += (uint64_t)(qlens[i] > 0? qlens[i] : 0) + 8;
 		tot = (tot + 15) & ~(uint64_t)15;
 		name_hash[i] = names && names[i]? hash_str(names[i]) : 0;
-		if (qlens[i] > max_qlen) max_qlen = qlens[i];
 		S.n_bases += qlens[i] > 0? qlens[i] : 0;
 	}
 	S.n_reads = n_reads;
 	const size_t hseq_bytes = tot + 16;
-	char *hseq = (char*)M->h_seq.ensure(hseq_bytes);
-	parallel_for(n_reads, [&](int64_t i) { if (qlens[i] > 0) memcpy(hseq + seq_off[i], seqs[i], (size_t)qlens[i]); });
-	// glibc logf table for mapq (reference: gcmisc.c:216-217)
-	{
-		int need = std::max(1 << 16, max_qlen + 4096);
-		if (M->n_logf < need) {
-			M->logf_tab.resize(need);
-			for (int i = 0; i < need; ++i) M->logf_tab[i] = logf((float)i);
-			if (M->d_logf) dfree(M->d_logf);
-			M->d_logf = dalloc_copy(M->logf_tab);
-			M->n_logf = need;
+	char *hseq = (char*)sl.h_seq.ensure(hseq_bytes);
+	auto pfor = [&](int64_t n, const std::function<void(int64_t)> &fn) {
+		int nt = host_threads;
+		if (n < 256 || nt <= 1) { for (int64_t i = 0; i < n; ++i) fn(i); return; }
+		std::vector<std::thread> th;
+		int64_t chunk = (n + nt - 1) / nt;
+		for (int t = 0; t < nt; ++t) {
+			int64_t b = t * chunk, e = std::min<int64_t>(n, b + chunk);
+			if (b >= e) break;
+			th.emplace_back([=, &fn]() { for (int64_t i = b; i < e; ++i) fn(i); });
 		}
-	}
-	S.t_pack_ms = now_ms() - t_pack0;
-	MapOptDev o;
-	fill_opt(o, opt, M->k);
-	o.logf_tab = M->d_logf, o.n_logf_tab = M->n_logf;
+		for (auto &x : th) x.join();
+	};
+	pfor(n_reads, [&](int64_t i) { if (qlens[i] > 0) memcpy(hseq + seq_off[i], seqs[i], (size_t)qlens[i]); });
+	S.t_pack_ms = now_ms() - t_host0;
 
 	EvTimer tm_h2d, tm_seed, tm_chain, tm_align, tm_wfa, tm_fin, tm_d2h;
-	// ---- device buffers ----
+	EvTimer tm_k[10]; // one per kernel (first pass only)
+	// ---- device buffers (all persistent: cudaMalloc/cudaFree would serialise the slots) ----
+	enum { P_ANCHOR, P_MINIPOS, P_LCHAIN, P_OUT, P_PLAN, P_JOBS, P_CIG, P_GSTATE, P_GJOBS, P_WALK, N_POOLS };
 	tm_h2d.start();
-	char *d_seq = (char*)M->d_seq.ensure(hseq_bytes);
+	char *d_seq = (char*)sl.d_seq.ensure(hseq_bytes);
 	h2d(d_seq, hseq, hseq_bytes);
-	uint64_t *d_seq_off = dalloc_copy(seq_off);
-	int32_t *d_seq_len = dalloc_copy(seq_len);
-	uint32_t *d_name_hash = dalloc_copy(name_hash);
+	size_t small_dev = (size_t)n_reads * (8 + 4 + 4 + 4) + 4096;
+	char *ds = (char*)sl.d_small.ensure(small_dev);
+	uint64_t *d_seq_off = (uint64_t*)ds;
+	int32_t *d_seq_len = (int32_t*)(d_seq_off + n_reads);
+	uint32_t *d_name_hash = (uint32_t*)(d_seq_len + n_reads);
+	int32_t *d_list_buf = (int32_t*)(d_name_hash + n_reads); // n_reads entries: read list of the retry pass
+	char *dsm = (char*)(((uintptr_t)(d_list_buf + n_reads) + 255) & ~(uintptr_t)255);
+	unsigned int *d_next = (unsigned int*)dsm;
+	unsigned int *d_jobq_n = d_next + 4;
+	unsigned long long *d_prof = (unsigned long long*)(dsm + 64);
+	Pool *d_pools = (Pool*)(dsm + 64 + sizeof(unsigned long long) * PROF_N);
+	h2d(d_seq_off, seq_off, (size_t)n_reads * 16); // seq_off, seq_len and name_hash are contiguous on both sides
 	tm_h2d.stop();
-	ReadMeta *d_meta = (ReadMeta*)M->d_meta.ensure(sizeof(ReadMeta) * (size_t)n_reads);
-	ReadOut *d_routs = (ReadOut*)M->d_routs.ensure(sizeof(ReadOut) * (size_t)n_reads);
+	ReadMeta *d_meta = (ReadMeta*)sl.d_meta.ensure(sizeof(ReadMeta) * (size_t)n_reads);
+	ReadOut *d_routs = (ReadOut*)sl.d_routs.ensure(sizeof(ReadOut) * (size_t)n_reads);
 	dzero(d_meta, sizeof(ReadMeta) * (size_t)n_reads);
 	dzero(d_routs, sizeof(ReadOut) * (size_t)n_reads);
-	unsigned int *d_next = (unsigned int*)dmalloc(sizeof(unsigned int));
-	unsigned int *d_jobq_n = (unsigned int*)dmalloc(sizeof(unsigned int) * 2);
-	unsigned long long *d_prof = (unsigned long long*)dmalloc(sizeof(unsigned long long) * PROF_N);
 	dzero(d_prof, sizeof(unsigned long long) * PROF_N);
-	enum { P_ANCHOR, P_MINIPOS, P_LCHAIN, P_OUT, P_PLAN, P_JOBS, P_CIG, P_GSTATE, P_GJOBS, P_WALK, N_POOLS };
-	Pool *d_pools = (Pool*)dmalloc(sizeof(Pool) * N_POOLS);
 	uint64_t cap[N_POOLS];
 	cap[P_ANCHOR] = std::max<uint64_t>((uint64_t)S.n_bases / 4 * sizeof(u128), (uint64_t)1 << 22);
 	cap[P_MINIPOS] = std::max<uint64_t>((uint64_t)S.n_bases * sizeof(int32_t) / 2, (uint64_t)1 << 20);
@@ -755,20 +796,20 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 	cap[P_PLAN] = std::max<uint64_t>((uint64_t)S.n_bases / 8 * 8, (uint64_t)1 << 20);
 	cap[P_JOBS] = std::max<uint64_t>((uint64_t)S.n_bases / 40 * sizeof(WfaJob), (uint64_t)1 << 20);
 	cap[P_CIG] = std::max<uint64_t>((uint64_t)S.n_bases, (uint64_t)1 << 20);
-	cap[P_GSTATE] = std::max<uint64_t>((uint64_t)n_reads * 1024, (uint64_t)1 << 20);
-	cap[P_GJOBS] = std::max<uint64_t>((uint64_t)n_reads * 16 * sizeof(GwfaJob), (uint64_t)1 << 20);
+	cap[P_GSTATE] = std::max<uint64_t>((uint64_t)n_reads * 2048, (uint64_t)1 << 20);
+	cap[P_GJOBS] = std::max<uint64_t>((uint64_t)n_reads * 24 * sizeof(GwfaJob), (uint64_t)1 << 20);
 	cap[P_WALK] = std::max<uint64_t>((uint64_t)n_reads * 256, (uint64_t)1 << 20);
+	for (int i = 0; i < N_POOLS; ++i) if (sl.d_pool[i].cap > cap[i]) cap[i] = sl.d_pool[i].cap & ~(size_t)4095; // keep what earlier batches needed
 	std::vector<ReadOut> routs(n_reads);
 	std::vector<ReadMeta> meta(n_reads);
 	char *hout = 0;
 	int rc_final = 0;
-	const int n_workers = default_workers();
-	ensure_workers(M->W, n_workers, (uint64_t)p_arena_mb << 20);
+	bool first_kernel = true;
 
 	for (int attempt = 0; attempt < 8; ++attempt) {
 		void *d_buf[N_POOLS];
 		Pool hp[N_POOLS];
-		for (int i = 0; i < N_POOLS; ++i) d_buf[i] = M->d_pool[i].ensure(cap[i]), hp[i].used = 0, hp[i].cap = cap[i];
+		for (int i = 0; i < N_POOLS; ++i) d_buf[i] = sl.d_pool[i].ensure(cap[i]), hp[i].used = 0, hp[i].cap = cap[i];
 		h2d(d_pools, hp, sizeof(hp));
 		dfill(d_buf[P_GJOBS], 0xff, cap[P_GJOBS]); // reserved-but-unused bridging job slots read as rid == -1
 		LaunchArgs L;
@@ -791,59 +832,65 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 		L.c.jobq[0] = 0, L.c.jobq[1] = 0, L.c.jobq_n = d_jobq_n;
 		L.routs = d_routs;
 		int64_t jobs_done = 0, gjobs_done = 0;
-		// one pass over a set of reads: 5 launches; the job count is read back between K6/K7 and K8a
+		// one pass over a set of reads; job counts are read back between the planning and the job kernels
 		auto run_pass = [&](const int32_t *d_list, int32_t n_list, const Workers &W, bool timed) {
 			L.rid_list = d_list, L.n_work = n_list;
+#ifndef MGB_HOSTSIM
+			if (first_kernel) { CUDA_OK(cudaEventRecord(sl.ev_first, t_stream)); first_kernel = false; }
+#endif
 			if (timed) tm_seed.start();
-			launch_stage<0>(L, W);
+			{ if (timed) tm_k[0].start(); launch_stage<0>(L, W); if (timed) tm_k[0].stop(); }
 			if (timed) tm_seed.stop(), tm_chain.start();
-			launch_stage<1>(L, W);
+			{ if (timed) tm_k[1].start(); launch_stage<1>(L, W); if (timed) tm_k[1].stop(); }
 			if (timed) tm_chain.stop(), tm_align.start();
-			launch_stage<2>(L, W);
+			{ if (timed) tm_k[2].start(); launch_stage<2>(L, W); if (timed) tm_k[2].stop(); }
 			{ // bridging jobs planned by k_gchain, then materialisation
 				Pool pg;
-				d2h(&pg, &d_pools[P_GJOBS], sizeof(Pool)); // implicit sync
+				d2h(&pg, &d_pools[P_GJOBS], sizeof(Pool));
 				int64_t n_gj = (int64_t)(std::min<uint64_t>(pg.used, pg.cap) / sizeof(GwfaJob));
 				L.rid_list = 0, L.job_start = gjobs_done, L.n_work = (int32_t)(n_gj - gjobs_done);
-				if (L.n_work > 0) { launch_stage<8>(L, W); S.n_launches += 1; }
+				if (L.n_work > 0) { { if (timed) tm_k[8].start(); launch_stage<8>(L, W); if (timed) tm_k[8].stop(); } S.n_launches += 1; }
 				gjobs_done = n_gj;
 				L.rid_list = d_list, L.n_work = n_list;
-				launch_stage<9>(L, W);
+				{ if (timed) tm_k[9].start(); launch_stage<9>(L, W); if (timed) tm_k[9].stop(); }
 				S.n_launches += 1;
 			}
 			if (timed) tm_align.stop();
 			Pool pj;
-			d2h(&pj, &d_pools[P_JOBS], sizeof(Pool)); // implicit sync
+			d2h(&pj, &d_pools[P_JOBS], sizeof(Pool));
 			int64_t n_jobs = (int64_t)(std::min<uint64_t>(pj.used, pj.cap) / sizeof(WfaJob));
 			L.rid_list = 0, L.job_start = jobs_done, L.n_work = (int32_t)(n_jobs - jobs_done);
 			if (timed) tm_wfa.start();
 			if (L.n_work > 0) { // three tiers; a job that does not fit one tier is queued for the next
 				int32_t n_new = L.n_work;
-				int32_t *q = (int32_t*)M->d_jobq.ensure(sizeof(int32_t) * 2 * (size_t)n_new);
+				int32_t *q = (int32_t*)sl.d_jobq.ensure(sizeof(int32_t) * 2 * (size_t)n_new);
 				L.c.jobq[0] = q, L.c.jobq[1] = q + n_new;
 				unsigned int qn[2] = {0, 0};
 				h2d(d_jobq_n, qn, sizeof(qn));
-				launch_stage<4>(L, W);
+				{ if (timed) tm_k[4].start(); launch_stage<4>(L, W); if (timed) tm_k[4].stop(); }
 				d2h(qn, d_jobq_n, sizeof(qn));
 				S.n_launches += 1;
-				if (qn[0] > 0) { L.n_work = (int32_t)qn[0]; launch_stage<6>(L, W); d2h(qn, d_jobq_n, sizeof(qn)); S.n_launches += 1; }
-				if (qn[1] > 0) { L.n_work = (int32_t)qn[1]; launch_stage<7>(L, W); S.n_launches += 1; }
+				if (qn[0] > 0) { L.n_work = (int32_t)qn[0]; { if (timed) tm_k[6].start(); launch_stage<6>(L, W); if (timed) tm_k[6].stop(); } d2h(qn, d_jobq_n, sizeof(qn)); S.n_launches += 1; }
+				if (qn[1] > 0) { L.n_work = (int32_t)qn[1]; { if (timed) tm_k[7].start(); launch_stage<7>(L, W); if (timed) tm_k[7].stop(); } S.n_launches += 1; }
 				if (timed) S.n_jobs_mid = qn[0], S.n_jobs_big = qn[1];
 			}
 			if (timed) tm_wfa.stop(), tm_fin.start();
 			jobs_done = n_jobs;
 			L.rid_list = d_list, L.n_work = n_list;
-			launch_stage<5>(L, W);
+			{ if (timed) tm_k[5].start(); launch_stage<5>(L, W); if (timed) tm_k[5].stop(); }
 			if (timed) tm_fin.stop();
 			S.n_launches += 4;
+#ifndef MGB_HOSTSIM
+			CUDA_OK(cudaEventRecord(sl.ev_last, t_stream));
+#endif
 			dsync();
 		};
-		run_pass(0, n_reads, M->W, true);
+		run_pass(0, n_reads, sl.W, true);
 		S.n_jobs = jobs_done;
 		d2h(routs.data(), d_routs, sizeof(ReadOut) * (size_t)n_reads);
 		d2h(meta.data(), d_meta, sizeof(ReadMeta) * (size_t)n_reads);
 
-		// reads whose worker arena overflowed: run them again with large arenas and few workers
+		// reads whose worker arena overflowed: run them again with large arenas and few workers (shared by the slots)
 		std::vector<int32_t> redo;
 		bool pool_full = false;
 		for (int i = 0; i < n_reads; ++i) {
@@ -852,12 +899,12 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 			else if (st == MGB_E_POOL) pool_full = true;
 		}
 		if (!pool_full && !redo.empty()) {
+			std::lock_guard<std::mutex> lock(M->big_mutex);
 			uint64_t big = (uint64_t)p_arena_big_mb << 20;
-			int nw = (int)std::min<uint64_t>((uint64_t)n_workers, std::max<uint64_t>(1, dev_free_mem() * 3 / 4 / big));
-			ensure_workers(M->Wbig, std::max(1, nw), big);
-			int32_t *d_list = dalloc_copy(redo);
-			run_pass(d_list, (int32_t)redo.size(), M->Wbig, false);
-			dfree(d_list);
+			int nw = (int)std::min<uint64_t>((uint64_t)sl.W.n_workers, std::max<uint64_t>(1, dev_free_mem() * 3 / 4 / big));
+			if (M->Wbig.arena == 0 || M->Wbig.arena_bytes != big) ensure_workers(M->Wbig, std::max(1, nw), big);
+			h2d(d_list_buf, redo.data(), redo.size() * sizeof(int32_t));
+			run_pass(d_list_buf, (int32_t)redo.size(), M->Wbig, false);
 			S.n_retry += (int64_t)redo.size();
 			d2h(routs.data(), d_routs, sizeof(ReadOut) * (size_t)n_reads);
 			d2h(meta.data(), d_meta, sizeof(ReadMeta) * (size_t)n_reads);
@@ -871,7 +918,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 		if (done) {
 			tm_d2h.start();
 			size_t out_bytes = (size_t)std::min<uint64_t>(hp[P_OUT].used, cap[P_OUT]);
-			hout = (char*)M->h_out.ensure(out_bytes);
+			hout = (char*)sl.h_out.ensure(out_bytes);
 			d2h(hout, d_buf[P_OUT], out_bytes);
 			tm_d2h.stop();
 			S.out_bytes = (int64_t)out_bytes;
@@ -883,14 +930,14 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 	}
 	S.t_h2d_ms = tm_h2d.ms(), S.t_seed_ms = tm_seed.ms(), S.t_chain_ms = tm_chain.ms(), S.t_align_ms = tm_align.ms();
 	S.t_wfa_ms = tm_wfa.ms(), S.t_finish_ms = tm_fin.ms();
+	for (int i = 0; i < 10; ++i) S.t_kernel_ms[i] = tm_k[i].ms();
 	if (rc_final == 0) S.t_d2h_ms = tm_d2h.ms();
 	{
-		std::vector<uint64_t> peak(M->W.n_workers);
-		d2h(peak.data(), M->W.peak, sizeof(uint64_t) * peak.size());
+		std::vector<uint64_t> peak(sl.W.n_workers);
+		d2h(peak.data(), sl.W.peak, sizeof(uint64_t) * peak.size());
 		for (uint64_t p : peak) if (p > S.arena_peak) S.arena_peak = p;
 	}
 	{ unsigned long long hp2[PROF_N]; d2h(hp2, d_prof, sizeof(hp2)); for (int i = 0; i < 32; ++i) S.prof[i] = (uint64_t)hp2[i]; }
-	dfree(d_seq_off), dfree(d_seq_len), dfree(d_name_hash), dfree(d_next), dfree(d_pools), dfree(d_prof), dfree(d_jobq_n);
 	if (rc_final < 0) return rc_final;
 
 	// ---- results ----
@@ -904,19 +951,141 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 	if (first_bad >= 0) {
 		int i = first_bad, st = meta[i].status < 0? meta[i].status : routs[i].status;
 		char buf[256];
-		snprintf(buf, sizeof(buf), "read %d ('%s', %d bp) failed on the device with code %d%s", i, names && names[i]? names[i] : "", qlens[i], st,
-				 st == MGB_E_ARENA? " (worker arena exhausted even in the retry pass; raise arena_big_mb)" :
-				 st == MGB_E_UNSUPPORTED? " (code path not implemented yet)" : "");
+		snprintf(buf, sizeof(buf), "read '%s' (%d bp) failed on the device with code %d%s", names && names[i]? names[i] : "", qlens[i], st,
+				 st == MGB_E_ARENA? " (worker arena exhausted even in the retry pass; raise arena_big_mb)" : "");
 		set_error(buf);
 		return st;
 	}
-	parallel_for(n_reads, [&](int64_t i) {
+	pfor(n_reads, [&](int64_t i) {
 		int st = meta[i].status < 0? meta[i].status : routs[i].status;
 		if (st == 1) gcs[i] = 0; // empty or over-long read: reference returns before allocating (map-algo.c:359-360)
 		else gcs[i] = build_result(routs[i], hout);
 	});
 	S.t_asm_ms = now_ms() - t_asm0;
 	S.t_host_ms = now_ms() - t_host0;
+	return 0;
+}
+
+static void slot_prepare(Model *M, Model::Slot &sl, int n_workers)
+{
+#ifndef MGB_HOSTSIM
+	if (!sl.ready) {
+		CUDA_OK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+		CUDA_OK(cudaEventCreate(&sl.ev_first));
+		CUDA_OK(cudaEventCreate(&sl.ev_last));
+	}
+#endif
+	sl.ready = true;
+	ensure_workers(sl.W, n_workers, (uint64_t)p_arena_mb << 20);
+	(void)M;
+}
+
+static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, const char *const *seqs, const char *const *names,
+						  mg_gchains_t **gcs, const mg_mapopt_t *opt)
+{
+	Model *M = (Model*)gi->B;
+	mgb_stats_t &S = M->stats;
+	memset(&S, 0, sizeof(S));
+	for (int i = 0; i < n_reads; ++i) gcs[i] = 0;
+	if (n_reads <= 0) return 0;
+	double t0 = now_ms();
+	int32_t max_qlen = 0;
+	int64_t tot_bases = 0;
+	for (int i = 0; i < n_reads; ++i) { if (qlens[i] > max_qlen) max_qlen = qlens[i]; tot_bases += qlens[i] > 0? qlens[i] : 0; }
+	{ // glibc logf table for mapq (reference: gcmisc.c:216-217)
+		int need = std::max(1 << 16, max_qlen + 4096);
+		if (M->n_logf < need) {
+			M->logf_tab.resize(need);
+			for (int i = 0; i < need; ++i) M->logf_tab[i] = logf((float)i);
+			if (M->d_logf) dfree(M->d_logf);
+			M->d_logf = dalloc_copy(M->logf_tab);
+			M->n_logf = need;
+		}
+	}
+	MapOptDev o;
+	fill_opt(o, opt, M->k);
+	o.logf_tab = M->d_logf, o.n_logf_tab = M->n_logf;
+	// ---- cut the batch into sub-batches of similar size (by bases), contiguous in input order ----
+#ifdef MGB_HOSTSIM
+	int n_slots = 1;
+#else
+	int n_slots = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(p_slots, Model::MAX_SLOTS), n_reads / std::max<int64_t>(1, p_min_slot_reads)));
+#endif
+	std::vector<int> bound(n_slots + 1, n_reads);
+	bound[0] = 0;
+	{
+		int64_t acc = 0; int k = 1;
+		for (int i = 0; i < n_reads && k < n_slots; ++i) {
+			acc += qlens[i] > 0? qlens[i] : 0;
+			if (acc >= tot_bases * k / n_slots) bound[k++] = i + 1;
+		}
+	}
+	int nt_all = (int)p_host_threads;
+	if (nt_all <= 0) { nt_all = (int)std::thread::hardware_concurrency(); if (nt_all > 16) nt_all = 16; if (nt_all < 1) nt_all = 1; }
+	const int nt_slot = std::max(1, nt_all / n_slots);
+	// a sub-batch gets enough workers to cover half the chip: two kernels of different sub-batches fill it, more queue behind
+	const int n_workers = p_slot_workers > 0? (int)p_slot_workers : std::min(default_workers(), std::max(128, default_workers() * 2 / n_slots));
+	for (int k = 0; k < n_slots; ++k) slot_prepare(M, M->slots[k], n_workers);
+	std::vector<int> rcs(n_slots, 0);
+#ifndef MGB_HOSTSIM
+	cudaEvent_t ev_ref;
+	CUDA_OK(cudaEventCreate(&ev_ref));
+	CUDA_OK(cudaEventRecord(ev_ref, M->slots[0].stream));
+#endif
+	auto work = [&](int k) {
+#ifndef MGB_HOSTSIM
+		cudaSetDevice((int)p_device);
+		t_stream = M->slots[k].stream;
+#endif
+		int b = bound[k], e = bound[k + 1];
+		rcs[k] = map_range(M, M->slots[k], o, e - b, qlens + b, seqs + b, names? names + b : 0, gcs + b, nt_slot);
+	};
+	if (n_slots == 1) {
+		work(0);
+#ifndef MGB_HOSTSIM
+		t_stream = 0; // the slot's stream dies with the model; later calls on this thread (mg_index of another graph) use the default one
+#endif
+	}
+	else {
+		std::vector<std::thread> th;
+		for (int k = 0; k < n_slots; ++k) th.emplace_back(work, k);
+		for (auto &x : th) x.join();
+	}
+	int rc = 0;
+	for (int k = 0; k < n_slots; ++k) if (rcs[k] < 0 && rc == 0) rc = rcs[k];
+	if (rc < 0) { // no partial results are left behind
+		for (int i = 0; i < n_reads; ++i) if (gcs[i]) { mg_gchain_free(gcs[i]); gcs[i] = 0; }
+		return rc;
+	}
+	// ---- merge the statistics of the slots ----
+	double first = 1e30, last = 0;
+	for (int k = 0; k < n_slots; ++k) {
+		const mgb_stats_t &T = M->slots[k].st;
+		if (bound[k + 1] == bound[k]) continue;
+		S.t_h2d_ms += T.t_h2d_ms, S.t_seed_ms += T.t_seed_ms, S.t_chain_ms += T.t_chain_ms, S.t_align_ms += T.t_align_ms, S.t_d2h_ms += T.t_d2h_ms;
+		S.t_wfa_ms += T.t_wfa_ms, S.t_finish_ms += T.t_finish_ms, S.t_pack_ms += T.t_pack_ms, S.t_asm_ms += T.t_asm_ms;
+		for (int i = 0; i < 10; ++i) S.t_kernel_ms[i] += T.t_kernel_ms[i];
+		S.n_jobs += T.n_jobs, S.n_jobs_mid += T.n_jobs_mid, S.n_jobs_big += T.n_jobs_big, S.n_reads += T.n_reads, S.n_bases += T.n_bases;
+		S.n_seeds += T.n_seeds, S.n_anchors_out += T.n_anchors_out, S.n_chains_out += T.n_chains_out, S.n_minimizers += T.n_minimizers;
+		S.out_bytes += T.out_bytes, S.n_launches += T.n_launches, S.n_retry += T.n_retry;
+		if (T.arena_peak > S.arena_peak) S.arena_peak = T.arena_peak;
+		for (int i = 0; i < 32; ++i) { if (i == PROF_WFA_MAX_CYC) { if (T.prof[i] > S.prof[i]) S.prof[i] = T.prof[i]; } else S.prof[i] += T.prof[i]; }
+#ifndef MGB_HOSTSIM
+		float a = 0, b = 0;
+		cudaEventElapsedTime(&a, ev_ref, M->slots[k].ev_first);
+		cudaEventElapsedTime(&b, ev_ref, M->slots[k].ev_last);
+		if (a < first) first = a;
+		if (b > last) last = b;
+#endif
+	}
+#ifndef MGB_HOSTSIM
+	cudaEventDestroy(ev_ref);
+	S.t_dev_span_ms = last > first? last - first : 0;
+#else
+	S.t_dev_span_ms = S.t_seed_ms + S.t_chain_ms + S.t_align_ms + S.t_wfa_ms + S.t_finish_ms;
+#endif
+	S.n_slots = n_slots;
+	S.t_host_ms = now_ms() - t0;
 	return 0;
 }
 

@@ -443,21 +443,28 @@ MG_HD inline int gwfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int l
 	GwfaJob *J = &c.gjobs[job_idx];
 	if (J->rid < 0) return 0;
 	if (c.meta[J->rid].status < 0) return 0;
-	int rc = 0;
-	if (lane <= 0) { // lane -1: thread-per-job mode, no warp to talk to
-		GwfOpt opt;
-		GwfResult r;
-		opt.traceback = 1, opt.max_chk = 1000, opt.bw_dyn = 1000, opt.max_lag = J->max_ed / 2, opt.s_term = -1;
-		opt.i_term = 500000000LL;
-		const char *qseq = c.b.seq + c.b.seq_off[J->rid];
-		unsigned long long t0 = prof_clock();
-		Arena S;
-		arena_init(S, smem, smem? GWFA_SMEM_ARENA : 0);
-		rc = smem? gwf_align(S, c.g, opt, J->ql, qseq + J->qs, J->v0, J->end0, J->v1, J->end1, J->max_ed, &r) : MGB_E_ARENA;
-		if (rc == MGB_E_ARENA) rc = gwf_align(A, c.g, opt, J->ql, qseq + J->qs, J->v0, J->end0, J->v1, J->end1, J->max_ed, &r);
+	GwfShared *sh = (GwfShared*)smem; // the one copy of the alignment state, seen by all lanes
+	const uint64_t sh_bytes = (sizeof(GwfShared) + 15) & ~(uint64_t)15;
+	GwfOpt opt;
+	opt.traceback = 1, opt.max_chk = 1000, opt.bw_dyn = 1000, opt.max_lag = J->max_ed / 2, opt.s_term = -1;
+	opt.i_term = 500000000LL;
+	const char *qseq = c.b.seq + c.b.seq_off[J->rid];
+	unsigned long long t0 = prof_clock();
+	if (lane == 0) arena_init(sh->A, (char*)smem + sh_bytes, GWFA_SMEM_ARENA - sh_bytes);
+	warp_sync();
+	int rc = gwf_align_w(sh, c.g, opt, J->ql, qseq + J->qs, J->v0, J->end0, J->v1, J->end1, J->max_ed, lane);
+	if (rc == MGB_E_ARENA) { // outgrew shared memory: again in the worker's arena
+		warp_sync();
+		if (lane == 0) sh->A = A;
+		warp_sync();
+		rc = gwf_align_w(sh, c.g, opt, J->ql, qseq + J->qs, J->v0, J->end0, J->v1, J->end1, J->max_ed, lane);
+		if (sh->A.peak > A.peak) A.peak = sh->A.peak;
+	}
+	if (lane == 0) {
+		const GwfResult &r = sh->r;
 		prof_add(c, PROF_GC_GWFA_CYC, prof_clock() - t0);
 #if !MGB_ON_DEVICE && defined(MGB_HOSTSIM)
-		if (getenv("MGB_DUMP_JOBS")) fprintf(stderr, "GWFA\t%d\t%d\t%ld\t%d\t%lu\t%lu\n", J->ql, r.s, (long)r.n_iter, r.nv, (unsigned long)S.peak, (unsigned long)A.peak);
+		if (getenv("MGB_DUMP_JOBS")) fprintf(stderr, "GWFA\t%d\t%d\t%ld\t%d\t%lu\n", J->ql, r.s, (long)r.n_iter, r.nv, (unsigned long)sh->A.peak);
 #endif
 		if (rc == 0) {
 			J->s = r.s, J->nv = r.s >= 0? r.nv : 0;
@@ -471,7 +478,8 @@ MG_HD inline int gwfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int l
 			}
 		}
 	}
-	if (lane >= 0) rc = warp_bcast_i32(rc, 0);
+	warp_sync();
+	rc = warp_bcast_i32(rc, 0);
 	return rc;
 }
 

@@ -485,4 +485,293 @@ MG_HD inline int gwf_align(Arena &A, const GraphDev &g, const GwfOpt &opt, int32
 	return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-cooperative form.  The state lives in one place (shared memory on the device) and is seen by all lanes; the
+// per-diagonal work of a wavefront step (extension, the Landau-Vishkin recurrence, the two order-preserving
+// compactions) is spread over the lanes, while the vertex-crossing queue, the dedup and the pruning stay on lane 0.
+// Results are identical to gwf_align(): every list is written in the order the sequential code writes it.
+// ---------------------------------------------------------------------------------------------------------------
+
+struct GwfShared {
+	Arena A;
+	GwfState z;
+	GwfResult r;
+	int32_t rc, go;
+};
+
+// one run of n consecutive diagonals of one vertex (gwf_extend_batch); all lanes enter
+MG_HD inline int gwf_extend_batch_w(GwfShared *sh, int32_t n, GwfDiag *a, int lane)
+{
+	GwfState &z = sh->z;
+	const GraphDev &g = *z.g;
+	const uint32_t v = (uint32_t)(a->vd >> 32);
+	const int32_t vl = g_vlen(g, v), ql = z.ql;
+	const char *ts = g_vseq(g, v);
+	for (int32_t j = lane; j < n; j += MGB_W) {
+		GwfDiag p = a[j];
+		int32_t k = gwf_extend1((int32_t)p.vd - GWF_DIAG_SHIFT, p.k, vl, ts, ql, z.q);
+		p.len = k - p.k;
+		p.xo += (uint32_t)p.len << 2;
+		p.k = k;
+		a[j] = p;
+	}
+	if (lane == 0) {
+		int rc = avec_reserve(sh->A, z.B, z.B.n + n + 2);
+		if (rc == 0) rc = avec_reserve(sh->A, z.Q, z.Q.n + n);
+		if (rc == 0) rc = avec_reserve(sh->A, z.tmp, z.tmp.n + n + 2);
+		sh->rc = rc;
+	}
+	warp_sync();
+	if (sh->rc < 0) return sh->rc;
+	GwfDiag *b = &z.B.a[z.B.n];
+	GwfDiag *Q = z.Q.a;
+	GwfIntv *T = z.tmp.a;
+	int64_t qn = z.Q.n, tn = z.tmp.n;
+	int32_t m = 0;
+	// next-score candidates b[0..n+1], kept in order when still inside the vertex and the query
+	for (int32_t base = 0; base < n + 2; base += MGB_W) {
+		const int32_t j = base + lane;
+		GwfDiag p;
+		int keep = 0, ends = 0;
+		p.vd = 0, p.k = 0, p.xo = 0, p.t = 0, p.len = 0;
+		if (j < n + 2) {
+			if (j == 0) {
+				p.vd = a[0].vd - 1, p.xo = a[0].xo + 2, p.k = a[0].k + 1, p.t = a[0].t;
+			} else if (j == n + 1) {
+				p.vd = a[n-1].vd + 1, p.xo = a[n-1].xo + 2, p.k = a[n-1].k, p.t = a[n-1].t;
+			} else if (j == 1) {
+				const int first = n == 1 || a[0].k > a[1].k;
+				p.vd = a[0].vd;
+				p.xo = first? a[0].xo + 4 : a[1].xo + 2;
+				p.t = first? a[0].t : a[1].t;
+				p.k = (first? a[0].k : a[1].k) + 1;
+			} else if (j == n) {
+				const int first = a[n-2].k > a[n-1].k + 1;
+				p.vd = a[n-1].vd;
+				p.xo = first? a[n-2].xo + 2 : a[n-1].xo + 4;
+				p.t = first? a[n-2].t : a[n-1].t;
+				p.k = first? a[n-2].k : a[n-1].k + 1;
+			} else {
+				const GwfDiag l = a[j-2], c = a[j-1], rr = a[j];
+				uint32_t x = l.xo + 2;
+				int32_t k = l.k, t = l.t;
+				x = k > c.k + 1? x : c.xo + 4;
+				t = k > c.k + 1? t : c.t;
+				k = k > c.k + 1? k : c.k + 1;
+				x = k > rr.k + 1? x : rr.xo + 2;
+				t = k > rr.k + 1? t : rr.t;
+				k = k > rr.k + 1? k : rr.k + 1;
+				p.vd = c.vd, p.k = k, p.xo = x, p.t = t;
+			}
+			const int32_t d = (int32_t)p.vd - GWF_DIAG_SHIFT;
+			if (d + p.k < ql && p.k < vl) keep = 1;
+			else if (p.k == vl) ends = 1;
+		}
+		const uint32_t mk = warp_ballot(keep), me = warp_ballot(ends);
+		if (keep) b[m + mask_rank(mk, lane)] = p;
+		if (ends) {
+			GwfIntv iv;
+			iv.vd0 = gwf_gen_vd(v, (int32_t)p.vd - GWF_DIAG_SHIFT), iv.vd1 = iv.vd0 + 1;
+			T[tn + mask_rank(me, lane)] = iv;
+		}
+		m += mask_count(mk), tn += mask_count(me);
+	}
+	// diagonals touching the end of the vertex or of the query go to the queue
+	for (int32_t base = 0; base < n; base += MGB_W) {
+		const int32_t j = base + lane;
+		GwfDiag p;
+		int f = 0;
+		p.vd = 0, p.k = 0, p.xo = 0, p.t = 0, p.len = 0;
+		if (j < n) {
+			p = a[j];
+			f = p.k == vl - 1 || (int32_t)p.vd - GWF_DIAG_SHIFT + p.k == ql - 1;
+		}
+		const uint32_t mq = warp_ballot(f);
+		if (f) {
+			p.xo |= 1;
+			a[j].xo = p.xo;
+			Q[qn + mask_rank(mq, lane)] = p;
+		}
+		qn += mask_count(mq);
+	}
+	warp_sync();
+	if (lane == 0) z.B.n += m, z.Q.n = qn, z.tmp.n = tn;
+	warp_sync();
+	return 0;
+}
+
+// lane 0: everything of gwf_ed_extend() behind the batches (vertex-crossing queue, dedup, pruning, swap)
+MG_HD inline int gwf_ed_queue(Arena &A, GwfState &z, const GwfOpt &opt, uint32_t v1, int32_t off1, GwfResult *r)
+{
+	const GraphDev &g = *z.g;
+	const int32_t ql = z.ql;
+	const char *q = z.q;
+	int32_t i, n, do_dedup = z.Q.n != 0;
+	while (z.q_head < z.Q.n) {
+		GwfDiag t = z.Q.a[z.q_head++];
+		uint32_t v, x0;
+		int32_t ooo, d, k, vl;
+		ooo = t.xo & 1, v = (uint32_t)(t.vd >> 32);
+		d = (int32_t)t.vd - GWF_DIAG_SHIFT;
+		k = t.k;
+		vl = g_vlen(g, v);
+		k = gwf_extend1(d, k, vl, g_vseq(g, v), ql, q);
+		i = k + d;
+		x0 = (t.xo >> 1) + ((uint32_t)(k - t.k) << 1);
+		if (k + 1 < vl && i + 1 < ql) { // wavefront in the middle of the vertex
+			int32_t push1 = 1, push2 = 1;
+			if (z.B.n >= 2) push1 = gwf_diag_update(&z.B.a[z.B.n - 2], v, d-1, k+1, x0 + 1, ooo, t.t);
+			if (z.B.n >= 1) push2 = gwf_diag_update(&z.B.a[z.B.n - 1], v, d,   k+1, x0 + 2, ooo, t.t);
+			if (push1)          MGB_TRY(gwf_diag_push(A, z.B, v, d-1, k+1, x0 + 1, 1, t.t));
+			if (push2 || push1) MGB_TRY(gwf_diag_push(A, z.B, v, d,   k+1, x0 + 2, 1, t.t));
+			MGB_TRY(gwf_diag_push(A, z.B, v, d+1, k, x0 + 1, ooo, t.t));
+		} else if (i + 1 < ql) { // end of the vertex, not the end of the query
+			int32_t nv = g_arc_n(g, v), j, n_ext = 0, tw = -1;
+			const DevArc *av = g_arc_a(g, v);
+			GwfIntv iv;
+			iv.vd0 = gwf_gen_vd(v, d), iv.vd1 = iv.vd0 + 1;
+			MGB_TRY(avec_push(A, z.tmp, iv));
+			if (opt.traceback) MGB_TRY(gwf_trace_push(A, z, (int32_t)v, t.t, &tw));
+			for (j = 0; j < nv; ++j) {
+				uint32_t w = av[j].w;
+				int32_t ol = av[j].ow;
+				int absent; int64_t slot;
+				MGB_TRY(u64tab_put(A, z.ha, (uint64_t)w << 32 | (uint64_t)(uint32_t)(i + 1), &absent, &slot));
+				if (q[i + 1] == g_vseq(g, w)[ol]) {
+					++n_ext;
+					if (absent) {
+						GwfDiag p;
+						p.vd = gwf_gen_vd(w, i + 1 - ol), p.k = ol, p.xo = (x0 + 2) << 1 | 1, p.t = tw, p.len = 0;
+						MGB_TRY(avec_push(A, z.Q, p));
+					}
+				} else if (absent) {
+					MGB_TRY(gwf_diag_push(A, z.B, w, i - ol,     ol, x0 + 1, 1, tw));
+					MGB_TRY(gwf_diag_push(A, z.B, w, i + 1 - ol, ol, x0 + 2, 1, tw));
+				}
+			}
+			if (nv == 0 || n_ext != nv)
+				MGB_TRY(gwf_diag_push(A, z.B, v, d+1, k, x0 + 1, 1, t.t));
+		} else if (v1 == (uint32_t)-1 || (v == v1 && k == off1)) { // end of the query at the wanted position
+			r->end_v = v, r->end_off = k, r->wlen = (int32_t)(x0 - (uint32_t)i - 1), z.end_tb = t.t;
+			z.a.n = 0;
+			return 0;
+		} else if (k + 1 < vl) { // end of the query, not the end of the vertex
+			MGB_TRY(gwf_diag_push(A, z.B, v, d-1, k+1, x0 + 1, ooo, t.t));
+		} else if (v != v1) { // end of both, but not on the last vertex
+			int32_t nv = g_arc_n(g, v), j, tw = -1;
+			const DevArc *av = g_arc_a(g, v);
+			if (opt.traceback) MGB_TRY(gwf_trace_push(A, z, (int32_t)v, t.t, &tw));
+			for (j = 0; j < nv; ++j)
+				MGB_TRY(gwf_diag_push(A, z.B, av[j].w, i - av[j].ow, av[j].ow, x0 + 1, 1, tw));
+		}
+	}
+	n = (int32_t)z.B.n;
+	if (do_dedup) MGB_TRY(gwf_dedup(A, z, n, z.B.a, &n));
+	if (opt.max_lag > 0 && n > opt.max_chk && ((z.s + 1) & 0xf) == 0)
+		n = gwf_prune(n, z.B.a, (uint32_t)opt.max_lag, opt.bw_dyn);
+	z.B.n = n;
+	{ AVec<GwfDiag> sw = z.a; z.a = z.B; z.B = sw; }
+	return 0;
+}
+
+// gwf_align() entered by all lanes of a warp.  `sh` is visible to every lane; sh->A is the arena to work in.  On return
+// sh->r holds the result (r.v at the arena's mark, as gwf_align leaves it) and the return code is the same on all lanes.
+MG_HD inline int gwf_align_w(GwfShared *sh, const GraphDev &g, const GwfOpt &opt, int32_t ql, const char *q, uint32_t v0, int32_t off0,
+							 uint32_t v1, int32_t off1, int32_t s_term, int lane)
+{
+	Arena &A = sh->A;
+	GwfState &z = sh->z;
+	GwfResult *r = &sh->r;
+	const uint64_t mark = A.top;
+	if (s_term < 0 && opt.s_term >= 0) s_term = opt.s_term;
+	if (lane == 0) {
+		int rc = 0;
+		z.g = &g, z.ql = ql, z.q = q, z.s = 0, z.end_tb = -1, z.q_head = 0;
+		avec_init(z.a), avec_init(z.B), avec_init(z.ooo), avec_init(z.Q), avec_init(z.intv), avec_init(z.tmp), avec_init(z.swap), avec_init(z.t);
+		rc = u64tab_init(A, z.ha, 6);
+		if (rc == 0) rc = u64tab_init(A, z.ht, 6);
+		if (rc == 0) rc = avec_reserve(A, z.t, 16);
+		if (rc == 0) {
+			GwfDiag d0;
+			d0.vd = gwf_gen_vd(v0, -off0), d0.k = off0 - 1, d0.xo = 0, d0.len = 0, d0.t = 0;
+			if (opt.traceback) rc = gwf_trace_push(A, z, -1, -1, &d0.t);
+			if (rc == 0) rc = avec_push(A, z.a, d0);
+		}
+		r->n_iter = 0, r->nv = 0, r->v = 0, r->end_v = (uint32_t)-1, r->end_off = -1, r->wlen = 0;
+		sh->rc = rc, sh->go = rc == 0 && z.a.n > 0;
+	}
+	warp_sync();
+	while (sh->go) {
+		// ---- one edit-distance step (gwf_ed_extend) ----
+		if (lane == 0) {
+			r->end_v = (uint32_t)-1;
+			r->end_off = z.end_tb = -1;
+			z.tmp.n = 0;
+			u64tab_clear(z.ha);
+			z.Q.n = 0, z.q_head = 0;
+			z.B.n = 0;
+			sh->rc = avec_reserve(A, z.B, z.a.n * 2);
+		}
+		warp_sync();
+		if (sh->rc < 0) break;
+		{
+			const int32_t n = (int32_t)z.a.n;
+			GwfDiag *a = z.a.a;
+			int32_t x = 0, rc = 0;
+			for (int32_t base = 1; base <= n && rc == 0; base += MGB_W) { // runs of consecutive diagonals, in order
+				const int32_t i = base + lane;
+				uint32_t mask = warp_ballot(i <= n && (i == n || a[i].vd != a[i-1].vd + 1));
+				while (mask && rc == 0) {
+					const int32_t e = base + ctz32(mask);
+					mask &= mask - 1;
+					rc = gwf_extend_batch_w(sh, e - x, &a[x], lane);
+					x = e;
+				}
+			}
+			if (rc < 0) break; // sh->rc holds it
+		}
+		if (lane == 0) {
+			int rc = gwf_ed_queue(A, z, opt, v1, off1, r);
+			int go = rc == 0;
+			if (go) {
+				r->n_iter += z.a.n;
+				if (r->end_off >= 0 || z.a.n == 0) go = 0;
+				else if (s_term >= 0 && z.s >= s_term) go = 0;
+				else if (opt.i_term > 0 && r->n_iter > opt.i_term) go = 0;
+				else ++z.s;
+			}
+			sh->rc = rc, sh->go = go;
+		}
+		warp_sync();
+	}
+	warp_sync();
+	if (sh->rc < 0) { const int rc = sh->rc; warp_sync(); if (lane == 0) A.top = mark; warp_sync(); return rc; }
+	if (lane == 0) {
+		uint64_t mark_keep = mark;
+		int rc = 0;
+		if (opt.traceback && r->end_off >= 0) { // reference: gfa-ed.c:509-522 gwf_traceback
+			int32_t i = z.end_tb, n = 1;
+			while (i >= 0 && z.t.a[i].v >= 0) ++n, i = z.t.a[i].pre;
+			int32_t *walk = (int32_t*)(A.base + mark);
+			int32_t *tmpw = (int32_t*)arena_alloc(A, (uint64_t)n * sizeof(int32_t));
+			if (tmpw == 0) rc = MGB_E_ARENA;
+			else {
+				i = z.end_tb, n = 0;
+				tmpw[n++] = (int32_t)r->end_v;
+				while (i >= 0 && z.t.a[i].v >= 0) tmpw[n++] = z.t.a[i].v, i = z.t.a[i].pre;
+				r->nv = n;
+				for (i = 0; i < n >> 1; ++i) { int32_t t = tmpw[i]; tmpw[i] = tmpw[n - 1 - i], tmpw[n - 1 - i] = t; }
+				for (i = 0; i < n; ++i) { int32_t t = tmpw[i]; walk[i] = t; } // forward copy: the destination lies below the source
+				r->v = walk;
+				mark_keep = mark + (((uint64_t)n * 4 + 15) & ~(uint64_t)15);
+			}
+		}
+		r->s = r->end_v != (uint32_t)-1? z.s : -1;
+		A.top = rc == 0? mark_keep : mark;
+		sh->rc = rc;
+	}
+	warp_sync();
+	return sh->rc;
+}
+
 } // namespace mgb
