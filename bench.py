@@ -114,6 +114,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mgb200")
     ap.add_argument("--reads", type=int, default=N_READS)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -243,7 +244,7 @@ def main():
     achieved = chain_bytes / t_chain_avg / 1e9 if t_chain_avg > 0 else 0.0
     # CPU baseline: the unmodified reference on a bounded sample of the same reads, all host cores
     cpu = None
-    if os.path.exists(REF_BIN):
+    if os.path.exists(REF_BIN) and not a.no_cpu:
         sfa = os.path.join(tmp, "cpu_sample.fa")
         with open(sfa, "wb") as f:
             for nm, s in zip(names[:CPU_SAMPLE_READS], seqs[:CPU_SAMPLE_READS]):

@@ -171,11 +171,11 @@ struct LaunchArgs {
 // stages: 0 seed (K1-K3), 1 chain (K4/K5), 2 gchain + alignment plan (K6/K7), 3 segment sketch for the index,
 //         4/6/7 WFA jobs tier 1/2/3 (K8a, warp-cooperative), 5 finish: CIGAR stitching + ds + result blob (K8b)
 #define MGB_IS_WFA(STAGE) ((STAGE) == 4 || (STAGE) == 6 || (STAGE) == 7)
-#define MGB_IS_WARP(STAGE) (MGB_IS_WFA(STAGE) || (STAGE) == 8 || (STAGE) == 1) // stages entered by all lanes of the warp
+#define MGB_IS_WARP(STAGE) (MGB_IS_WFA(STAGE) || (STAGE) == 8 || (STAGE) == 1 || (STAGE) == 0) // stages entered by all lanes of the warp
 template<int STAGE>
 MG_HD inline int run_stage(const LaunchArgs &L, int item, Arena &A, int lane, int32_t *smem)
 {
-	if (STAGE == 0) return stage_seed(L.c, item, A);
+	if (STAGE == 0) return stage_seed(L.c, item, A, lane);
 	if (STAGE == 1) return stage_chain(L.c, item, A, lane);
 	if (STAGE == 2) return stage_gchain(L.c, L.routs, item, A);
 	if (STAGE == 5) return stage_finish(L.c, L.routs, item, A);
@@ -1069,7 +1069,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 		S.n_seeds += T.n_seeds, S.n_anchors_out += T.n_anchors_out, S.n_chains_out += T.n_chains_out, S.n_minimizers += T.n_minimizers;
 		S.out_bytes += T.out_bytes, S.n_launches += T.n_launches, S.n_retry += T.n_retry;
 		if (T.arena_peak > S.arena_peak) S.arena_peak = T.arena_peak;
-		for (int i = 0; i < 32; ++i) { if (i == PROF_WFA_MAX_CYC) { if (T.prof[i] > S.prof[i]) S.prof[i] = T.prof[i]; } else S.prof[i] += T.prof[i]; }
+		for (int i = 0; i < 32; ++i) { if (i == PROF_WFA_MAX_CYC || i == PROF_GWFA_MAX_CYC) { if (T.prof[i] > S.prof[i]) S.prof[i] = T.prof[i]; } else S.prof[i] += T.prof[i]; }
 #ifndef MGB_HOSTSIM
 		float a = 0, b = 0;
 		cudaEventElapsedTime(&a, ev_ref, M->slots[k].ev_first);

@@ -462,7 +462,7 @@ MG_HD inline int gwfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int l
 	}
 	if (lane == 0) {
 		const GwfResult &r = sh->r;
-		prof_add(c, PROF_GC_GWFA_CYC, prof_clock() - t0);
+		{ unsigned long long dt = prof_clock() - t0; prof_add(c, PROF_GC_GWFA_CYC, dt); prof_max(c, PROF_GWFA_MAX_CYC, dt); }
 #if !MGB_ON_DEVICE && defined(MGB_HOSTSIM)
 		if (getenv("MGB_DUMP_JOBS")) fprintf(stderr, "GWFA\t%d\t%d\t%ld\t%d\t%lu\n", J->ql, r.s, (long)r.n_iter, r.nv, (unsigned long)sh->A.peak);
 #endif

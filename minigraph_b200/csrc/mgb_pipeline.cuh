@@ -35,7 +35,7 @@ struct PipeCtx {
 
 enum { PROF_WFA_FAST_CYC = 0, PROF_WFA_FAST_N, PROF_WFA_SLOW_CYC, PROF_WFA_SLOW_N, PROF_WFA_MAX_CYC, PROF_WFA_CELLS, PROF_WFA_TB_CYC,
 	   PROF_GC_DP_CYC, PROF_GC_GEN_CYC, PROF_GC_POST_CYC, PROF_GC_PLAN_CYC, PROF_FIN_CIGAR_CYC, PROF_FIN_DS_CYC, PROF_SEED_SKETCH_CYC,
-	   PROF_SEED_MATCH_CYC, PROF_SEED_SORT_CYC, PROF_CHAIN_DP_CYC, PROF_CHAIN_BT_CYC, PROF_CHAIN_RMQ_CYC, PROF_CHAIN_POST_CYC, PROF_WFA_MID_CYC, PROF_WFA_MID_N, PROF_GC_GWFA_CYC, PROF_GC_SHORTK_CYC, PROF_GC_EXTRA_CYC, PROF_N = 32 };
+	   PROF_SEED_MATCH_CYC, PROF_SEED_SORT_CYC, PROF_CHAIN_DP_CYC, PROF_CHAIN_BT_CYC, PROF_CHAIN_RMQ_CYC, PROF_CHAIN_POST_CYC, PROF_WFA_MID_CYC, PROF_WFA_MID_N, PROF_GC_GWFA_CYC, PROF_GC_SHORTK_CYC, PROF_GC_EXTRA_CYC, PROF_GWFA_MAX_CYC, PROF_N = 32 };
 
 MG_HD inline unsigned long long prof_clock()
 {
@@ -64,26 +64,10 @@ MG_HD inline void prof_max(const PipeCtx &c, int slot, unsigned long long v)
 
 // K1-K3 for one read.  Writes sorted seeds to the anchor pool and the query positions of kept minimizers to the
 // mini_pos pool.
-MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A)
+// index lookup, seed expansion, seed sort (one lane)
+MG_HD inline int stage_seed_tail(const PipeCtx &c, ReadMeta &m, Arena &A, const AVec<u128> &mv, unsigned long long t0, unsigned long long t1)
 {
-	ReadMeta &m = c.meta[rid];
-	const char *seq = c.b.seq + c.b.seq_off[rid];
-	int32_t qlen = c.b.seq_len[rid];
-	uint64_t mark = A.top;
-	m.status = 0, m.n_mz = 0, m.rep_len = 0, m.n_a = 0, m.a_off = 0, m.n_mp = 0, m.mp_off = 0, m.n_lc = 0, m.lc_off = 0;
-	m.n_seed0 = 0, m.n_u0 = 0;
-	{ // reference: map-algo.c:362-364
-		uint32_t h = c.b.name_hash[rid];
-		h ^= hash32((uint32_t)qlen) + hash32((uint32_t)c.opt.seed);
-		m.hash = hash32(h);
-	}
-	if (qlen <= 0 || (c.opt.max_qlen > 0 && qlen > c.opt.max_qlen)) { m.status = 1; return 0; } // unmapped by definition
-	AVec<u128> mv;
-	avec_init(mv);
-	unsigned long long t0 = prof_clock();
-	MGB_TRY(sketch_seq(A, seq, qlen, c.ix.w, c.ix.k, 0, mv));
 	m.n_mz = (int32_t)mv.n;
-	unsigned long long t1 = prof_clock();
 	prof_add(c, PROF_SEED_SKETCH_CYC, t1 - t0);
 	SeedMatch *sm;
 	int n_m, n_mp, rep_len;
@@ -105,8 +89,42 @@ MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A)
 	prof_add(c, PROF_SEED_MATCH_CYC, t2 - t1);
 	MGB_TRY(radix_sort_128x(A, a, n_a));
 	prof_add(c, PROF_SEED_SORT_CYC, prof_clock() - t2);
-	A.top = mark;
 	return 0;
+}
+
+// Warp-uniform: all lanes enter; the sketch is cut into chunks over the lanes, the rest runs on lane 0.
+MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A, int lane)
+{
+	ReadMeta &m = c.meta[rid];
+	const char *seq = c.b.seq + c.b.seq_off[rid];
+	const int32_t qlen = c.b.seq_len[rid];
+	const uint64_t mark = A.top;
+	const int skip = qlen <= 0 || (c.opt.max_qlen > 0 && qlen > c.opt.max_qlen);
+	if (lane == 0) {
+		m.status = 0, m.n_mz = 0, m.rep_len = 0, m.n_a = 0, m.a_off = 0, m.n_mp = 0, m.mp_off = 0, m.n_lc = 0, m.lc_off = 0;
+		m.n_seed0 = 0, m.n_u0 = 0;
+		{ // reference: map-algo.c:362-364
+			uint32_t h = c.b.name_hash[rid];
+			h ^= hash32((uint32_t)qlen) + hash32((uint32_t)c.opt.seed);
+			m.hash = hash32(h);
+		}
+		if (skip) m.status = 1; // unmapped by definition
+	}
+	if (skip) return 0;
+	AVec<u128> mv;
+	avec_init(mv);
+	unsigned long long t0 = prof_clock();
+	MGB_TRY(sketch_seq_w(A, seq, qlen, c.ix.w, c.ix.k, 0, mv, lane));
+	unsigned long long t1 = prof_clock();
+	int rc = 0;
+	if (lane == 0) {
+		Arena B = A;
+		rc = stage_seed_tail(c, m, B, mv, t0, t1);
+		if (B.peak > A.peak) A.peak = B.peak;
+	}
+	rc = warp_bcast_i32(rc, 0);
+	A.top = mark;
+	return rc;
 }
 
 // chain records, end trimming, bad-seed filters, anchor update, pool write (reference: map-algo.c:419-449); one lane

@@ -65,6 +65,144 @@ MG_HD inline int sketch_seq(Arena &A, const char *str, int len, int w, int k, ui
 	return 0;
 }
 
+// ---- the same sketch, cut into chunks that are independent of each other ----
+// A chunk that does not start the sequence replays w slots of warm-up before its first position: with k odd and no
+// ambiguous base every position fills a slot, the window before position p holds exactly the k-mers ending at
+// p-w..p-1, the minimum is a function of the window, and the run length l only matters below w+k (it is beyond that
+// once p >= w+2k-1, whatever happened in the first k-1 bases).  Whatever a chunk reports while processing positions
+// [p, end) is therefore what the sequential scan reports there; the lists are concatenated in chunk order.
+// Returns 1 when the chunk cannot be done this way (ambiguous base in its span, list full): the caller then runs
+// sketch_seq() on the whole sequence.
+static const int SKETCH_CHUNKS = 32;
+
+MG_HD inline int sketch_chunk(const char *str, int w, int k, uint32_t rid, int p, int end, int is_first, int is_last, u128 *buf, u128 *outp, int cap, int *n_out)
+{
+	const uint64_t shift1 = 2 * (k - 1), mask = (1ULL << 2 * k) - 1;
+	uint64_t kmer[2] = {0, 0};
+	int l = 0, buf_pos = 0, min_pos = 0, kmer_span = 0, n = 0, i0 = 0;
+	const u128 none = { ~0ULL, ~0ULL };
+	u128 mn = none;
+	for (int j = 0; j < w; ++j) buf[j] = none;
+	if (!is_first) {
+		i0 = p - w;
+		for (int i = i0 - k + 1; i < i0; ++i) { // the k-1 bases in front of the first warm-up slot
+			int c = nt4((uint8_t)str[i]);
+			if (c >= 4) return 1;
+			kmer[0] = (kmer[0] << 2 | (uint64_t)c) & mask;
+			kmer[1] = (kmer[1] >> 2) | (3ULL ^ (uint64_t)c) << shift1;
+		}
+		l = w + k + 1; // any value the thresholds below cannot tell from the true one
+	}
+#define MGB_SK_PUSH(v) do { if (i >= p) { if (n >= cap) return 1; outp[n++] = (v); } } while (0)
+	for (int i = i0; i < end; ++i) {
+		int c = nt4((uint8_t)str[i]);
+		u128 info = none;
+		if (c >= 4) return 1;
+		kmer_span = l + 1 < k? l + 1 : k;
+		kmer[0] = (kmer[0] << 2 | (uint64_t)c) & mask;
+		kmer[1] = (kmer[1] >> 2) | (3ULL ^ (uint64_t)c) << shift1;
+		if (kmer[0] == kmer[1]) { if (is_first) continue; return 1; }
+		int z = kmer[0] < kmer[1]? 0 : 1;
+		if (l < w + k + 1) ++l;
+		if (l >= k && kmer_span < 256) {
+			info.x = hash64_mask(kmer[z], mask) << 8 | (uint64_t)kmer_span;
+			info.y = (uint64_t)rid << 32 | (uint64_t)((uint32_t)i << 1) | (uint64_t)z;
+		}
+		buf[buf_pos] = info;
+		if (l == w + k - 1 && mn.x != ~0ULL) {
+			for (int j = buf_pos + 1; j < w; ++j)
+				if (mn.x == buf[j].x && buf[j].y != mn.y) MGB_SK_PUSH(buf[j]);
+			for (int j = 0; j < buf_pos; ++j)
+				if (mn.x == buf[j].x && buf[j].y != mn.y) MGB_SK_PUSH(buf[j]);
+		}
+		if (info.x <= mn.x) {
+			if (l >= w + k && mn.x != ~0ULL) MGB_SK_PUSH(mn);
+			mn = info, min_pos = buf_pos;
+		} else if (buf_pos == min_pos) {
+			if (l >= w + k - 1 && mn.x != ~0ULL) MGB_SK_PUSH(mn);
+			mn.x = ~0ULL;
+			for (int j = buf_pos + 1; j < w; ++j)
+				if (mn.x >= buf[j].x) mn = buf[j], min_pos = j;
+			for (int j = 0; j <= buf_pos; ++j)
+				if (mn.x >= buf[j].x) mn = buf[j], min_pos = j;
+			if (l >= w + k - 1 && mn.x != ~0ULL) {
+				for (int j = buf_pos + 1; j < w; ++j)
+					if (mn.x == buf[j].x && mn.y != buf[j].y) MGB_SK_PUSH(buf[j]);
+				for (int j = 0; j <= buf_pos; ++j)
+					if (mn.x == buf[j].x && mn.y != buf[j].y) MGB_SK_PUSH(buf[j]);
+			}
+		}
+		if (++buf_pos == w) buf_pos = 0;
+	}
+	if (is_last && mn.x != ~0ULL) { const int i = end; MGB_SK_PUSH(mn); }
+#undef MGB_SK_PUSH
+	*n_out = n;
+	return 0;
+}
+
+// sketch_seq() entered by all lanes of a warp; `out` (replicated on every lane) must be empty.
+MG_HD inline int sketch_seq_w(Arena &A, const char *str, int len, int w, int k, uint32_t rid, AVec<u128> &out, int lane)
+{
+	if (!(len > 0 && w > 0 && w < 256 && k > 0 && k <= 28)) return MGB_E_INTERNAL;
+	const int min_chunk = w + 2 * k > 64? w + 2 * k : 64;
+	const int n_ch = len / min_chunk < SKETCH_CHUNKS? len / min_chunk : SKETCH_CHUNKS;
+	int fail = (k & 1) == 0 || n_ch < 2;
+	if (!fail) {
+		const uint64_t mark = A.top;
+		const int chunk = (len + n_ch - 1) / n_ch, cap = chunk + w + 2;
+		u128 *tmp, *ring;
+		int32_t *cnt;
+		MGB_ALLOC(A, tmp, u128, (int64_t)n_ch * cap);
+		MGB_ALLOC(A, ring, u128, (int64_t)n_ch * w);
+		MGB_ALLOC(A, cnt, int32_t, SKETCH_CHUNKS);
+		for (int c = lane; c < n_ch; c += MGB_W) {
+			const int p = c * chunk, e = p + chunk < len? p + chunk : len;
+			int n = 0;
+			if (p < e) fail |= sketch_chunk(str, w, k, rid, p, e, c == 0, e == len, ring + (int64_t)c * w, tmp + (int64_t)c * cap, cap, &n);
+			cnt[c] = n;
+		}
+		fail = warp_any(fail);
+		warp_sync();
+		if (!fail) {
+			int64_t tot = 0, my_off = 0;
+			for (int c = 0; c < n_ch; ++c) tot += cnt[c];
+			// the result goes above the scratch; it is moved down to the mark afterwards so that the scratch can be released
+			u128 *res;
+			MGB_ALLOC(A, res, u128, tot + 16);
+			for (int c = 0; c < n_ch; ++c) {
+				if (c % MGB_W == lane) {
+					const u128 *src = tmp + (int64_t)c * cap;
+					for (int j = 0; j < cnt[c]; ++j) res[my_off + j] = src[j];
+				}
+				my_off += cnt[c];
+			}
+			warp_sync();
+			u128 *dst = (u128*)(A.base + mark);
+			for (int64_t j = lane; j < tot; j += MGB_W) dst[j] = res[j]; // dst lies inside the consumed per-chunk lists, below res
+			warp_sync();
+			A.top = mark + ((((uint64_t)tot + 16) * sizeof(u128) + 15) & ~(uint64_t)15);
+			if (A.top > A.peak) A.peak = A.top;
+			out.a = dst, out.n = tot, out.m = tot + 16;
+			return 0;
+		}
+		A.top = mark;
+	}
+	// sequential scan on lane 0; its few scalar results are broadcast
+	{
+		Arena B = A;
+		int rc = 0;
+		if (lane == 0) rc = sketch_seq(B, str, len, w, k, rid, out);
+		rc = warp_bcast_i32(rc, 0);
+		out.a = (u128*)warp_bcast_u64((uint64_t)out.a, 0);
+		out.n = (int64_t)warp_bcast_u64((uint64_t)out.n, 0);
+		out.m = (int64_t)warp_bcast_u64((uint64_t)out.m, 0);
+		A.top = warp_bcast_u64(B.top, 0);
+		A.peak = warp_bcast_u64(B.peak, 0);
+		warp_sync();
+		return rc;
+	}
+}
+
 struct SeedMatch {
 	uint32_t n, q_pos, q_span;
 	uint32_t seg_id, is_tandem;
