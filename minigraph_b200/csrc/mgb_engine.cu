@@ -42,6 +42,9 @@ static int64_t p_thread_mask = 0;
 extern int p_slots; extern int64_t p_min_slot_reads;
 static int64_t p_slot_workers = 0;      // bit s set: stage s runs one item per thread instead of one per warp
 
+// launch shape per stage: warps per block and blocks per SM wanted (tunable for experiments: "sw<stage>", "mb<stage>")
+static int STAGE_MINB[10] = { 8, 8, 4, 8, 4, 8, 5, 4, 4, 4 };
+static int STAGE_WARPS[10] = { 4, 4, 4, 4, 4, 4, 2, 4, 4, 4 };
 extern "C" const char *mgb_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char *mgb_version(void) { return "mgb200-r1"; }
 extern "C" int mgb_set_param(const char *key, int64_t value)
@@ -56,6 +59,8 @@ extern "C" int mgb_set_param(const char *key, int64_t value)
 	else if (!strcmp(key, "slots")) p_slots = (int)value;
 	else if (!strcmp(key, "slot_workers")) p_slot_workers = value;
 	else if (!strcmp(key, "min_slot_reads")) p_min_slot_reads = value;
+	else if (!strncmp(key, "sw", 2) && key[2] >= '0' && key[2] <= '9' && !key[3] && value >= 1 && value <= 4) STAGE_WARPS[key[2] - '0'] = (int)value;
+	else if (!strncmp(key, "mb", 2) && key[2] >= '0' && key[2] <= '9' && !key[3] && value >= 1 && value <= 32) STAGE_MINB[key[2] - '0'] = (int)value;
 	else return -1;
 	return 0;
 }
@@ -284,8 +289,6 @@ MGB_KERNEL(k_wfa_small, 4, 4)     // K8a tier 1: small gaps, wavefronts + traceb
 MGB_KERNEL(k_wfa_mid, 6, 5)       // K8a tier 2: mid-size gaps, wavefronts in shared memory (blocks of 2 warps)
 MGB_KERNEL(k_wfa_big, 7, 4)       // K8a tier 3: anything else, wavefronts in the worker arena
 MGB_KERNEL(k_finish, 5, 8)        // K8b: CIGAR stitching, ds strings, result blobs
-static const int STAGE_MINB[10] = { 8, 8, 4, 8, 4, 8, 5, 4, 4, 4 };
-static const int STAGE_WARPS[10] = { 4, 4, 4, 4, 4, 4, 2, 4, 4, 4 };
 template<int STAGE> struct StageKernel;
 template<> struct StageKernel<0> { static void (*get())(LaunchArgs) { return k_seed; } };
 template<> struct StageKernel<1> { static void (*get())(LaunchArgs) { return k_chain; } };
@@ -298,6 +301,49 @@ template<> struct StageKernel<8> { static void (*get())(LaunchArgs) { return k_g
 template<> struct StageKernel<9> { static void (*get())(LaunchArgs) { return k_gchain_gen; } };
 template<> struct StageKernel<5> { static void (*get())(LaunchArgs) { return k_finish; } };
 #endif
+
+// Longest-first order of a job list (a tail of a few long jobs otherwise decides the kernel time).  Jobs are binned by
+// size, four bins per octave, largest first; the order inside a bin does not matter (results do not depend on it).
+MG_HD inline int order_bin(uint32_t key)
+{
+	uint32_t x = key + 1, lz = 0;
+	while ((x >> lz) > 1) ++lz; // floor(log2(x))
+	int b = (int)(lz * 4 + (lz >= 2? ((x >> (lz - 2)) & 3) : 0));
+	return 63 - (b > 63? 63 : b);
+}
+// kind 0: bridging jobs [job_start, job_start+n), key = query length; kind 1: alignment jobs listed in q[0..n), key = tl + ql
+MG_HD inline uint32_t order_key(const LaunchArgs &L, int kind, const int32_t *q, int i)
+{
+	if (kind == 0) return (uint32_t)L.c.gjobs[L.job_start + i].ql;
+	const WfaJob &J = L.c.jobs[q[i]];
+	return (uint32_t)(J.tl + J.ql);
+}
+#ifndef MGB_HOSTSIM
+__global__ void __launch_bounds__(1024) k_job_order(LaunchArgs L, int kind, const int32_t *q, int n, int32_t *order)
+{
+	__shared__ unsigned int cnt[64];
+	const int tid = threadIdx.x;
+	if (tid < 64) cnt[tid] = 0;
+	__syncthreads();
+	for (int i = tid; i < n; i += 1024) atomicAdd(&cnt[order_bin(order_key(L, kind, q, i))], 1u);
+	__syncthreads();
+	if (tid == 0) { unsigned int acc = 0; for (int b = 0; b < 64; ++b) { unsigned int c = cnt[b]; cnt[b] = acc; acc += c; } }
+	__syncthreads();
+	for (int i = tid; i < n; i += 1024) order[atomicAdd(&cnt[order_bin(order_key(L, kind, q, i))], 1u)] = i;
+}
+#endif
+static void make_job_order(const LaunchArgs &L, int kind, const int32_t *q, int n, int32_t *order)
+{
+#ifndef MGB_HOSTSIM
+	k_job_order<<<1, 1024, 0, t_stream>>>(L, kind, q, n, order);
+	CUDA_OK(cudaGetLastError());
+#else
+	unsigned int cnt[65] = {0};
+	for (int i = 0; i < n; ++i) ++cnt[order_bin(order_key(L, kind, q, i)) + 1];
+	for (int b = 0; b < 64; ++b) cnt[b + 1] += cnt[b];
+	for (int i = 0; i < n; ++i) order[cnt[order_bin(order_key(L, kind, q, i))]++] = i;
+#endif
+}
 
 struct Workers {
 	int n_workers;
@@ -367,7 +413,7 @@ struct Model {
 	// the batch pipeline: a batch is cut into sub-batches, each driven by its own host thread on its own stream ("slot"),
 	// so that kernels, copies and host-side result assembly of different sub-batches overlap
 	struct Slot {
-		GrowBuf h_seq{true}, h_out{true}, h_small{true}, d_seq, d_meta, d_routs, d_small, d_jobq, d_pool[10];
+		GrowBuf h_seq{true}, h_out{true}, h_small{true}, d_seq, d_meta, d_routs, d_small, d_jobq, d_order, d_pool[10];
 		Workers W;
 		mgb_stats_t st;
 		double ev_first_ms, ev_last_ms; // first kernel start / last kernel end relative to the batch reference event
@@ -393,7 +439,7 @@ static void model_free(Model *M)
 	if (M->d_logf) dfree(M->d_logf);
 	for (int k = 0; k < Model::MAX_SLOTS; ++k) {
 		Model::Slot &sl = M->slots[k];
-		sl.h_seq.release(), sl.h_out.release(), sl.h_small.release(), sl.d_seq.release(), sl.d_meta.release(), sl.d_routs.release(), sl.d_small.release(), sl.d_jobq.release();
+		sl.h_seq.release(), sl.h_out.release(), sl.h_small.release(), sl.d_seq.release(), sl.d_meta.release(), sl.d_routs.release(), sl.d_small.release(), sl.d_jobq.release(), sl.d_order.release();
 		for (int i = 0; i < 10; ++i) sl.d_pool[i].release();
 		if (sl.W.arena) dfree(sl.W.arena);
 		if (sl.W.peak) dfree(sl.W.peak);
@@ -805,6 +851,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	char *hout = 0;
 	int rc_final = 0;
 	bool first_kernel = true;
+	(void)first_kernel;
 
 	for (int attempt = 0; attempt < 8; ++attempt) {
 		void *d_buf[N_POOLS];
@@ -849,7 +896,16 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 				d2h(&pg, &d_pools[P_GJOBS], sizeof(Pool));
 				int64_t n_gj = (int64_t)(std::min<uint64_t>(pg.used, pg.cap) / sizeof(GwfaJob));
 				L.rid_list = 0, L.job_start = gjobs_done, L.n_work = (int32_t)(n_gj - gjobs_done);
-				if (L.n_work > 0) { { if (timed) tm_k[8].start(); launch_stage<8>(L, W); if (timed) tm_k[8].stop(); } S.n_launches += 1; }
+				if (L.n_work > 0) {
+					int32_t *order = (int32_t*)sl.d_order.ensure(sizeof(int32_t) * (size_t)L.n_work);
+					if (timed) tm_k[8].start();
+					make_job_order(L, 0, 0, L.n_work, order);
+					L.rid_list = order;
+					launch_stage<8>(L, W);
+					L.rid_list = 0;
+					if (timed) tm_k[8].stop();
+					S.n_launches += 2;
+				}
 				gjobs_done = n_gj;
 				L.rid_list = d_list, L.n_work = n_list;
 				{ if (timed) tm_k[9].start(); launch_stage<9>(L, W); if (timed) tm_k[9].stop(); }
@@ -871,7 +927,17 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 				d2h(qn, d_jobq_n, sizeof(qn));
 				S.n_launches += 1;
 				if (qn[0] > 0) { L.n_work = (int32_t)qn[0]; { if (timed) tm_k[6].start(); launch_stage<6>(L, W); if (timed) tm_k[6].stop(); } d2h(qn, d_jobq_n, sizeof(qn)); S.n_launches += 1; }
-				if (qn[1] > 0) { L.n_work = (int32_t)qn[1]; { if (timed) tm_k[7].start(); launch_stage<7>(L, W); if (timed) tm_k[7].stop(); } S.n_launches += 1; }
+				if (qn[1] > 0) {
+					L.n_work = (int32_t)qn[1];
+					int32_t *order = (int32_t*)sl.d_order.ensure(sizeof(int32_t) * (size_t)L.n_work);
+					if (timed) tm_k[7].start();
+					make_job_order(L, 1, L.c.jobq[1], L.n_work, order);
+					L.rid_list = order;
+					launch_stage<7>(L, W);
+					L.rid_list = 0;
+					if (timed) tm_k[7].stop();
+					S.n_launches += 2;
+				}
 				if (timed) S.n_jobs_mid = qn[0], S.n_jobs_big = qn[1];
 			}
 			if (timed) tm_wfa.stop(), tm_fin.start();
@@ -1059,6 +1125,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 	}
 	// ---- merge the statistics of the slots ----
 	double first = 1e30, last = 0;
+	(void)first, (void)last;
 	for (int k = 0; k < n_slots; ++k) {
 		const mgb_stats_t &T = M->slots[k].st;
 		if (bound[k + 1] == bound[k]) continue;

@@ -437,6 +437,7 @@ MG_HD inline int stage_gchain(const PipeCtx &c, ReadOut *routs, int rid, Arena &
 // diagonals) fit a small per-warp arena in SHARED memory, which removes the global-memory latency from the sequential
 // control flow; a bridge that outgrows it is redone with the worker's arena in HBM.  Lane 0 runs the alignment.
 static const int GWFA_SMEM_ARENA = 12 * 1024;
+static const int GWFA_SMEM_MAX_QL = 128;
 
 MG_HD inline int gwfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int lane, int32_t *smem)
 {
@@ -450,9 +451,15 @@ MG_HD inline int gwfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int l
 	opt.i_term = 500000000LL;
 	const char *qseq = c.b.seq + c.b.seq_off[J->rid];
 	unsigned long long t0 = prof_clock();
-	if (lane == 0) arena_init(sh->A, (char*)smem + sh_bytes, GWFA_SMEM_ARENA - sh_bytes);
-	warp_sync();
-	int rc = gwf_align_w(sh, c.g, opt, J->ql, qseq + J->qs, J->v0, J->end0, J->v1, J->end1, J->max_ed, lane);
+	int rc = MGB_E_ARENA;
+	if (J->ql < GWFA_SMEM_MAX_QL) { // longer bridges nearly always outgrow the shared-memory arena: do not try
+		if (lane == 0) arena_init(sh->A, (char*)smem + sh_bytes, GWFA_SMEM_ARENA - sh_bytes);
+		warp_sync();
+		rc = gwf_align_w(sh, c.g, opt, J->ql, qseq + J->qs, J->v0, J->end0, J->v1, J->end1, J->max_ed, lane);
+	}
+	const int in_smem = rc != MGB_E_ARENA;
+	const uint64_t smem_peak = in_smem? sh->A.peak : 0;
+	(void)smem_peak, (void)in_smem;
 	if (rc == MGB_E_ARENA) { // outgrew shared memory: again in the worker's arena
 		warp_sync();
 		if (lane == 0) sh->A = A;
@@ -464,7 +471,7 @@ MG_HD inline int gwfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int l
 		const GwfResult &r = sh->r;
 		{ unsigned long long dt = prof_clock() - t0; prof_add(c, PROF_GC_GWFA_CYC, dt); prof_max(c, PROF_GWFA_MAX_CYC, dt); }
 #if !MGB_ON_DEVICE && defined(MGB_HOSTSIM)
-		if (getenv("MGB_DUMP_JOBS")) fprintf(stderr, "GWFA\t%d\t%d\t%ld\t%d\t%lu\n", J->ql, r.s, (long)r.n_iter, r.nv, (unsigned long)sh->A.peak);
+		if (getenv("MGB_DUMP_JOBS")) fprintf(stderr, "GWFA\t%d\t%d\t%ld\t%d\t%lu\t%d\n", J->ql, r.s, (long)r.n_iter, r.nv, (unsigned long)smem_peak, in_smem);
 #endif
 		if (rc == 0) {
 			J->s = r.s, J->nv = r.s >= 0? r.nv : 0;

@@ -496,7 +496,7 @@ struct GwfShared {
 	Arena A;
 	GwfState z;
 	GwfResult r;
-	int32_t rc, go;
+	int32_t rc, go, dedup;
 };
 
 // one run of n consecutive diagonals of one vertex (gwf_extend_batch); all lanes enter
@@ -600,8 +600,8 @@ MG_HD inline int gwf_extend_batch_w(GwfShared *sh, int32_t n, GwfDiag *a, int la
 	return 0;
 }
 
-// lane 0: everything of gwf_ed_extend() behind the batches (vertex-crossing queue, dedup, pruning, swap)
-MG_HD inline int gwf_ed_queue(Arena &A, GwfState &z, const GwfOpt &opt, uint32_t v1, int32_t off1, GwfResult *r)
+// lane 0: the vertex-crossing queue of gwf_ed_extend()
+MG_HD inline int gwf_ed_queue(Arena &A, GwfState &z, const GwfOpt &opt, uint32_t v1, int32_t off1, GwfResult *r, int *want_dedup)
 {
 	const GraphDev &g = *z.g;
 	const int32_t ql = z.ql;
@@ -654,6 +654,7 @@ MG_HD inline int gwf_ed_queue(Arena &A, GwfState &z, const GwfOpt &opt, uint32_t
 		} else if (v1 == (uint32_t)-1 || (v == v1 && k == off1)) { // end of the query at the wanted position
 			r->end_v = v, r->end_off = k, r->wlen = (int32_t)(x0 - (uint32_t)i - 1), z.end_tb = t.t;
 			z.a.n = 0;
+			*want_dedup = -1; // done
 			return 0;
 		} else if (k + 1 < vl) { // end of the query, not the end of the vertex
 			MGB_TRY(gwf_diag_push(A, z.B, v, d-1, k+1, x0 + 1, ooo, t.t));
@@ -665,12 +666,155 @@ MG_HD inline int gwf_ed_queue(Arena &A, GwfState &z, const GwfOpt &opt, uint32_t
 				MGB_TRY(gwf_diag_push(A, z.B, av[j].w, i - av[j].ow, av[j].ow, x0 + 1, 1, tw));
 		}
 	}
-	n = (int32_t)z.B.n;
-	if (do_dedup) MGB_TRY(gwf_dedup(A, z, n, z.B.a, &n));
+	(void)n;
+	*want_dedup = do_dedup;
+	return 0;
+}
+
+// lane 0: what follows the dedup in gwf_ed_extend()
+MG_HD inline void gwf_ed_finish(GwfState &z, const GwfOpt &opt)
+{
+	int32_t n = (int32_t)z.B.n;
 	if (opt.max_lag > 0 && n > opt.max_chk && ((z.s + 1) & 0xf) == 0)
 		n = gwf_prune(n, z.B.a, (uint32_t)opt.max_lag, opt.bw_dyn);
 	z.B.n = n;
 	{ AVec<GwfDiag> sw = z.a; z.a = z.B; z.B = sw; }
+}
+
+MG_HD inline int64_t gwf_lower_bound_vd(const GwfDiag *a, int64_t n, uint64_t key) // number of elements with vd < key
+{
+	int64_t lo = 0, hi = n;
+	while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (a[mid].vd < key) lo = mid + 1; else hi = mid; }
+	return lo;
+}
+MG_HD inline int64_t gwf_upper_bound_vd(const GwfDiag *a, int64_t n, uint64_t key) // number of elements with vd <= key
+{
+	int64_t lo = 0, hi = n;
+	while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (a[mid].vd <= key) lo = mid + 1; else hi = mid; }
+	return lo;
+}
+
+// gwf_dedup() on z.B entered by all lanes: same lists, same order
+MG_HD inline int gwf_dedup_w(GwfShared *sh, int lane)
+{
+	GwfState &z = sh->z;
+	Arena &A = sh->A;
+	// forbidden intervals: fold the new ones in (lane 0; nothing changes when there are no new ones)
+	if (lane == 0) {
+		int rc = 0;
+		if (z.tmp.n > 0) {
+			int64_t i;
+			for (i = 1; i < z.tmp.n; ++i) if (z.tmp.a[i-1].vd0 > z.tmp.a[i].vd0) break;
+			if (i < z.tmp.n) rc = radix_sort_exact(A, z.tmp.a, z.tmp.n, 8, KeyIntvVd0());
+			if (rc == 0) rc = avec_reserve(A, z.swap, z.intv.n);
+			if (rc == 0) {
+				for (i = 0; i < z.intv.n; ++i) z.swap.a[i] = z.intv.a[i];
+				z.swap.n = z.intv.n;
+				rc = avec_reserve(A, z.intv, z.intv.n + z.tmp.n);
+			}
+			if (rc == 0) {
+				int64_t x = 0, y = 0, k = 0;
+				const GwfIntv *b = z.swap.a, *c = z.tmp.a;
+				GwfIntv *o = z.intv.a;
+				while (x < z.swap.n && y < z.tmp.n) {
+					if (b[x].vd0 <= c[y].vd0) o[k++] = b[x++];
+					else o[k++] = c[y++];
+				}
+				while (x < z.swap.n) o[k++] = b[x++];
+				while (y < z.tmp.n) o[k++] = c[y++];
+				z.intv.n = gwf_intv_merge_adj(k, o);
+			}
+		}
+		if (rc == 0) rc = avec_reserve(A, z.ooo, z.B.n);
+		sh->rc = rc;
+	}
+	warp_sync();
+	if (sh->rc < 0) return sh->rc;
+	GwfDiag *a = z.B.a;
+	const int32_t n_a = (int32_t)z.B.n;
+	// ---- gwf_diag_dedup: sort if needed ----
+	int unsorted = 0;
+	for (int32_t i = 1 + lane; i < n_a; i += MGB_W) if (a[i-1].vd > a[i].vd) unsorted = 1;
+	unsorted = warp_any(unsorted);
+	if (unsorted) { // gwf_diag_sort: in-order part and out-of-order part, the latter sorted, then a stable merge
+		GwfDiag *b = z.ooo.a;
+		int32_t n_c = 0;
+		for (int32_t base = 0; base < n_a; base += MGB_W) {
+			const int32_t i = base + lane;
+			n_c += mask_count(warp_ballot(i < n_a && (a[i].xo & 1)));
+		}
+		const int32_t n_b = n_a - n_c;
+		GwfDiag *c = b + n_b;
+		int32_t jb = 0, jc = 0;
+		for (int32_t base = 0; base < n_a; base += MGB_W) {
+			const int32_t i = base + lane;
+			GwfDiag p;
+			p.vd = 0, p.k = 0, p.xo = 0, p.t = 0, p.len = 0;
+			if (i < n_a) p = a[i];
+			const uint32_t mc = warp_ballot(i < n_a && (p.xo & 1)), mb = warp_ballot(i < n_a && !(p.xo & 1));
+			if (i < n_a) {
+				if (p.xo & 1) c[jc + mask_rank(mc, lane)] = p;
+				else b[jb + mask_rank(mb, lane)] = p;
+			}
+			jc += mask_count(mc), jb += mask_count(mb);
+		}
+		warp_sync();
+		if (lane == 0) sh->rc = radix_sort_exact(A, c, n_c, 8, KeyDiagVd());
+		warp_sync();
+		if (sh->rc < 0) return sh->rc;
+		for (int32_t j = lane; j < n_c; j += MGB_W) c[j].xo &= 0xfffffffeU;
+		warp_sync();
+		for (int32_t i = lane; i < n_b; i += MGB_W) a[i + gwf_lower_bound_vd(c, n_c, b[i].vd)] = b[i];
+		for (int32_t j = lane; j < n_c; j += MGB_W) a[j + gwf_upper_bound_vd(b, n_b, c[j].vd)] = c[j];
+		warp_sync();
+	}
+	// ---- one diagonal per (vertex,diag): the first one reaching furthest ----
+	int32_t n = 0;
+	for (int32_t base = 0; base < n_a; base += MGB_W) {
+		const int32_t i = base + lane;
+		GwfDiag best;
+		int head = 0;
+		best.vd = 0, best.k = 0, best.xo = 0, best.t = 0, best.len = 0;
+		if (i < n_a) {
+			best = a[i];
+			head = i == 0 || a[i-1].vd != best.vd;
+			if (head)
+				for (int32_t j = i + 1; j < n_a && a[j].vd == best.vd; ++j)
+					if (best.k < a[j].k) best = a[j];
+		}
+		const uint32_t mh = warp_ballot(head);
+		warp_sync();
+		if (head) a[n + mask_rank(mh, lane)] = best;
+		n += mask_count(mh);
+		warp_sync();
+	}
+	// ---- drop diagonals inside forbidden bands ----
+	if (z.intv.n > 0) {
+		const GwfIntv *iv = z.intv.a;
+		const int64_t n_iv = z.intv.n;
+		int32_t k = 0;
+		for (int32_t base = 0; base < n; base += MGB_W) {
+			const int32_t i = base + lane;
+			GwfDiag p;
+			int keep = 0;
+			p.vd = 0, p.k = 0, p.xo = 0, p.t = 0, p.len = 0;
+			if (i < n) {
+				p = a[i];
+				int64_t lo = 0, hi = n_iv; // intervals are disjoint and sorted: the last one starting at or before vd decides
+				while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (iv[mid].vd0 <= p.vd) lo = mid + 1; else hi = mid; }
+				keep = !(lo > 0 && p.vd < iv[lo - 1].vd1);
+			}
+			const uint32_t mk = warp_ballot(keep);
+			warp_sync();
+			if (keep) a[k + mask_rank(mk, lane)] = p;
+			k += mask_count(mk);
+			warp_sync();
+		}
+		n = k;
+	}
+	warp_sync();
+	if (lane == 0) z.B.n = n;
+	warp_sync();
 	return 0;
 }
 
@@ -731,7 +875,16 @@ MG_HD inline int gwf_align_w(GwfShared *sh, const GraphDev &g, const GwfOpt &opt
 			if (rc < 0) break; // sh->rc holds it
 		}
 		if (lane == 0) {
-			int rc = gwf_ed_queue(A, z, opt, v1, off1, r);
+			int dd = 0;
+			sh->rc = gwf_ed_queue(A, z, opt, v1, off1, r, &dd);
+			sh->dedup = dd;
+		}
+		warp_sync();
+		if (sh->rc < 0) break;
+		if (sh->dedup > 0 && gwf_dedup_w(sh, lane) < 0) break;
+		if (lane == 0) {
+			int rc = 0;
+			if (sh->dedup >= 0) gwf_ed_finish(z, opt);
 			int go = rc == 0;
 			if (go) {
 				r->n_iter += z.a.n;

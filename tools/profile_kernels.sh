@@ -17,5 +17,6 @@ for k in "$@"; do
 	mangled=$(grep -o "_Z[0-9]*${k}10LaunchArgs" gpurun_out/dis.txt | head -1)
 	python tools/ncu_lines.py $out.sass.csv gpurun_out/dis.txt $mangled 45 > $out.lines.txt 2>&1
 	rm -f $out.sass.csv
+	[ -n "${KEEP_REP:-}" ] || rm -f $out.ncu-rep   # gpurun brings back at most 64 MiB
 done
 rm -f *.cubin gpurun_out/dis.txt
