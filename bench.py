@@ -167,48 +167,75 @@ def main():
     qlens = (C.c_int * n)(*[len(s) for s in seqs])
     cseqs = (C.c_char_p * n)(*seqs)
     cnames = (C.c_char_p * n)(*names)
-    gcs = (C.POINTER(capi.mg_gchains_t) * n)()
+    # two result sets: the GAF text of batch i is written by a second host thread while batch i+1 is being mapped, the
+    # way the reference's kt_pipeline overlaps its output step with the mapping step of the next mini-batch (gmap.c:176-177)
+    gcs2 = [(C.POINTER(capi.mg_gchains_t) * n)(), (C.POINTER(capi.mg_gchains_t) * n)()]
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
     st = capi.mgb_stats_t()
     gaf_bytes = [0]
     host = [0.0] * 6
+    import queue
+    out_q, done_q = queue.Queue(), queue.Queue()
+
+    def output_worker():
+        while True:
+            k = out_q.get()
+            if k is None:
+                return
+            t0 = time.perf_counter()
+            buf, ln = C.c_void_p(0), C.c_size_t(0)
+            lib.mgb_write_gaf_batch(g, n, gcs2[k], qlens, cnames, mo.flag, 0, C.byref(buf), C.byref(ln))
+            gaf_bytes[0] = ln.value
+            C.CDLL(None).free(buf)
+            for i in range(n):
+                lib.mg_gchain_free(gcs2[k][i])
+            host[5] += (time.perf_counter() - t0) * 1e3
+            done_q.put(k)
+
+    worker = threading.Thread(target=output_worker, daemon=True)
+    worker.start()
+    free_sets = [0, 1]
+    step_no = [0]
 
     def step():
         flush.fill_(1)  # evict L2 (126 MB) between steps
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        rc = lib.mg_map_batch(gi, n, qlens, cseqs, cnames, gcs, C.byref(mo))
+        while not free_sets:
+            free_sets.append(done_q.get())
+        k = free_sets.pop(0)
+        rc = lib.mg_map_batch(gi, n, qlens, cseqs, cnames, gcs2[k], C.byref(mo))
         assert rc == 0, lib.mgb_last_error()
-        buf, ln = C.c_void_p(0), C.c_size_t(0)
-        lib.mgb_write_gaf_batch(g, n, gcs, qlens, cnames, mo.flag, 0, C.byref(buf), C.byref(ln))
-        t1 = time.perf_counter()
-        gaf_bytes[0] = ln.value
-        C.CDLL(None).free(buf)
         lib.mgb_get_stats(gi, C.byref(st))
-        host[0] += st.t_pack_ms; host[1] += st.t_h2d_ms; host[2] += st.t_d2h_ms; host[3] += st.t_asm_ms; host[4] += st.t_host_ms; host[5] += (t1 - t0) * 1e3 - st.t_host_ms
-        for i in range(n):
-            lib.mg_gchain_free(gcs[i])
-        lib.mgb_get_stats(gi, C.byref(st))
-        return t1 - t0, (st.t_seed_ms, st.t_chain_ms, st.t_align_ms, st.t_wfa_ms, st.t_finish_ms), st.t_dev_span_ms, int(st.n_slots)
+        host[0] += st.t_pack_ms; host[1] += st.t_h2d_ms; host[2] += st.t_d2h_ms; host[3] += st.t_asm_ms; host[4] += st.t_host_ms
+        out_q.put(k)
+        step_no[0] += 1
+        return (st.t_seed_ms, st.t_chain_ms, st.t_align_ms, st.t_wfa_ms, st.t_finish_ms), st.t_dev_span_ms, int(st.n_slots)
+
+    def drain():
+        while len(free_sets) < 2:
+            free_sets.append(done_q.get())
 
     for _ in range(a.warmup):
         step()
+    drain()
     host[:] = [0.0] * 6
     sampler = ClockSampler(local_rank)
     sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    walls, kern, stage = [], [], [0.0] * 5
+    kern, stage = [], [0.0] * 5
     launches = 0
+    t_begin = time.perf_counter()
     for _ in range(a.steps):
-        w, ks, span, n_slots = step()
-        walls.append(w)
+        ks, span, n_slots = step()
         kern.append(span)
         for i in range(5):
             stage[i] += ks[i]
         launches += st.n_launches
+    drain()  # the last batch's GAF text is part of the job
     torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_begin
     if world > 1:
         dist.barrier()
     sampler.stop_flag = True
@@ -216,12 +243,13 @@ def main():
     # one extra, untimed-for-the-metric step with a single sub-batch: kernels run back to back on one stream, so the CUDA-event
     # times of the stages are per-kernel durations (in the timed steps the sub-batches overlap and share the SMs)
     overlapped_stage = [x / a.steps for x in stage]
+    host_timed = list(host)  # the host-side sums of the timed steps
     lib.mgb_set_param(b"slots", 1)
-    _, serial_stage, serial_span, _ = step()
+    serial_stage, serial_span, _ = step()
+    drain()
     stage = [x * a.steps for x in serial_stage]
     kernel_ms = {k: round(st.t_kernel_ms[i], 3) for i, k in enumerate(capi.KERNEL_NAMES) if k != "k_index_sketch"}
     t_kern = sum(kern) / 1e3
-    t_wall = sum(walls)
     # the one collective of the path: per-rank GAF byte counts -> output offsets
     from minigraph_b200 import dist as mdist
     my_off, counts = mdist.gaf_offsets(gaf_bytes[0], device="cuda")
@@ -268,9 +296,9 @@ def main():
                               "wfa_jobs(K8a)": stage[3] / a.steps, "finish(K8b cigar+ds)": stage[4] / a.steps, "wfa_jobs_per_step": int(st.n_jobs), "wfa_jobs_tier2": int(st.n_jobs_mid), "wfa_jobs_tier3": int(st.n_jobs_big)},
         "e2e": {"value": e2e, "unit": "Gbp/s", "ms_per_step": t_wall / a.steps * 1e3,
                 "h2d_bytes_per_step": int(bases + 16 * n + 16 * n), "d2h_bytes_per_step": int(st.out_bytes + 48 * n + 96 * n),
-                "includes": "H2D of reads, all stage kernels, D2H of result blobs, mg_gchains_t assembly, GAF text (%d bytes/step)" % gaf_bytes[0]},
-        "host_ms_per_step": {"pack": host[0] / a.steps, "h2d": host[1] / a.steps, "d2h": host[2] / a.steps, "assemble": host[3] / a.steps,
-                             "mg_map_batch_total": host[4] / a.steps, "gaf_text": host[5] / a.steps},
+                "includes": "wall clock of K x (pack + H2D of reads, all kernels, D2H of result blobs, mg_gchains_t assembly) with the GAF text (%d bytes/step) of batch i written by a second host thread during batch i+1 (the reference's kt_pipeline does the same, gmap.c:176), plus the last batch's GAF; L2 flush between steps included" % gaf_bytes[0]},
+        "host_ms_per_step": {"pack": host_timed[0] / a.steps, "h2d": host_timed[1] / a.steps, "d2h": host_timed[2] / a.steps, "assemble": host_timed[3] / a.steps,
+                             "mg_map_batch_total": host_timed[4] / a.steps, "gaf_text(second thread)": host_timed[5] / a.steps},
         "device_cycles_last_step": {k: int(st.prof[i]) for i, k in enumerate(capi.PROF_NAMES)},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "k_stage<1> (linear chaining: mg_lchain_dp/rmq + backtrack + compaction)", "bound": "hbm", "achieved": achieved, "peak": peak,

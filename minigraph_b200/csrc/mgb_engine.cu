@@ -43,7 +43,7 @@ extern int p_slots; extern int64_t p_min_slot_reads;
 static int64_t p_slot_workers = 0;      // bit s set: stage s runs one item per thread instead of one per warp
 
 // launch shape per stage: warps per block and blocks per SM wanted (tunable for experiments: "sw<stage>", "mb<stage>")
-static int STAGE_MINB[10] = { 8, 8, 4, 8, 4, 8, 5, 4, 4, 4 };
+static int STAGE_MINB[10] = { 8, 8, 4, 8, 5, 8, 7, 4, 4, 4 };
 static int STAGE_WARPS[10] = { 4, 4, 4, 4, 4, 4, 2, 4, 4, 4 };
 extern "C" const char *mgb_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char *mgb_version(void) { return "mgb200-r1"; }
@@ -285,7 +285,7 @@ MGB_KERNEL(k_gchain, 2, 4)        // K6: graph chaining DP + k-shortest walks, o
 MGB_KERNEL(k_gwfa, 8, 4)          // K7a: bridging alignments (graph wavefront), one warp per bridge
 MGB_KERNEL(k_gchain_gen, 9, 4)    // K7b: graph-chain materialisation, post filters, mapq, alignment plan
 MGB_KERNEL(k_index_sketch, 3, 8)  // index build: sketch of graph segments
-MGB_KERNEL(k_wfa_small, 4, 4)     // K8a tier 1: small gaps, wavefronts + traceback bytes in shared memory
+MGB_KERNEL(k_wfa_small, 4, 5)     // K8a tier 1: small gaps, wavefronts + traceback bytes in shared memory
 MGB_KERNEL(k_wfa_mid, 6, 5)       // K8a tier 2: mid-size gaps, wavefronts in shared memory (blocks of 2 warps)
 MGB_KERNEL(k_wfa_big, 7, 4)       // K8a tier 3: anything else, wavefronts in the worker arena
 MGB_KERNEL(k_finish, 5, 8)        // K8b: CIGAR stitching, ds strings, result blobs

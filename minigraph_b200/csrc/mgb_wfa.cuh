@@ -127,26 +127,32 @@ MG_HD inline int wf_traceback(const TB &tb, int32_t n_scores, int32_t tl, const 
 
 // HS = number of H slices kept in shared memory (17 = all).  With HS = 7 the slices older than 6 scores -- only read
 // once more, as H[s-16] -- live in a ring in the worker arena (coalesced global loads), which halves the footprint.
+// Cells are 16-bit: a valid offset is in [-1, MAXLEN], an invalid one is the sentinel plus the at most 255 increments the
+// recurrence can add, so every comparison and maximum orders the cells exactly as the reference's 32-bit ones do.
+typedef int16_t wf_cell_t;
+static const int32_t WF_NEG_INF16 = -30000;
+
 template<int W, int MAXLEN, int TBCAP, int HS = 17>
 struct WfSmemLayout {
 	static const int W_ = W, MAXLEN_ = MAXLEN, TBCAP_ = TBCAP, HS_ = HS;
-	static const int N_INTS = (HS + 3 + 3 + 2 + 2) * W + 2 * 17 + 2;
+	static const int N_CELLS = (HS + 3 + 3 + 2 + 2) * W;
+	static const int N_INTS = N_CELLS / 2 + 2 * 17 + 2; // cells, then lo[17], hi[17]
 	static const int SEQ_BYTES = (MAXLEN + WF_SEQ_PAD + 3) / 4 * 4;
 	static const int TB_ROW_BYTES = TBCAP > 0? 256 * 8 : 0; // per score: int32 lo, int32 off
 	static const int BYTES = N_INTS * 4 + 2 * SEQ_BYTES + TB_ROW_BYTES + TBCAP;
 	static const int STRIDE = (BYTES + 127) / 128 * 128;
 };
 
-struct WfSrc { const int32_t *p; int32_t lo, hi; }; // one source slice of the recurrence
+struct WfSrc { const wf_cell_t *p; int32_t lo, hi; }; // one source slice of the recurrence
 
 template<int W>
 MG_HD inline int32_t wfs_col(int32_t d) { return (d + (1 << 20)) & (W - 1); }
 
 template<int W>
-MG_HD inline int32_t wfs_at(const WfSrc &s, int32_t d) { return (d >= s.lo && d <= s.hi)? s.p[wfs_col<W>(d)] : WF_NEG_INF; }
+MG_HD inline int32_t wfs_at(const WfSrc &s, int32_t d) { return (d >= s.lo && d <= s.hi)? (int32_t)s.p[wfs_col<W>(d)] : WF_NEG_INF16; }
 
 template<int W>
-MG_HD inline WfSrc wfs_src(const int32_t *arr, int nslot, const int32_t *lo, const int32_t *hi, int32_t score)
+MG_HD inline WfSrc wfs_src(const wf_cell_t *arr, int nslot, const int32_t *lo, const int32_t *hi, int32_t score)
 {
 	WfSrc s;
 	if (score < 0) { s.p = arr, s.lo = 1, s.hi = 0; return s; }
@@ -182,8 +188,9 @@ MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g,
 	typedef WfSmemLayout<W, MAXLEN, TBCAP, HS> LY;
 	if (tl > MAXLEN || ql > MAXLEN) return 1;
 	uint64_t mark = A.top;
-	int32_t *H = smem, *E1 = H + HS * W, *F1 = E1 + 3 * W, *E2 = F1 + 3 * W, *F2 = E2 + 2 * W;
-	int32_t *slo = F2 + 2 * W, *shi = slo + 17;
+	if (MAXLEN > 16000) return 1; // cells are 16-bit
+	wf_cell_t *H = (wf_cell_t*)smem, *E1 = H + HS * W, *F1 = E1 + 3 * W, *E2 = F1 + 3 * W, *F2 = E2 + 2 * W;
+	int32_t *slo = smem + LY::N_CELLS / 2, *shi = slo + 17;
 	char *ts = (char*)(smem + LY::N_INTS), *qs = ts + LY::SEQ_BYTES;
 	int32_t *tb_row = (int32_t*)(qs + LY::SEQ_BYTES); // TBCAP > 0 only
 	uint8_t *tb_x = (uint8_t*)tb_row + LY::TB_ROW_BYTES;
@@ -197,27 +204,27 @@ MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g,
 	AVec<WfTbRow> rows; // TBCAP == 0 only
 	avec_init(rows);
 	if (TBCAP == 0) MGB_TRY(avec_reserve_w(A, rows, 256, lane));
-	int32_t *Hg = 0; // HS < 17: all 17 H slices, written back after their extension
-	if (HS < 17) MGB_ALLOC(A, Hg, int32_t, 17 * W);
+	wf_cell_t *Hg = 0; // HS < 17: all 17 H slices, written back after their extension
+	if (HS < 17) MGB_ALLOC(A, Hg, wf_cell_t, 17 * W);
 	int32_t n_rows = 0, tb_used = 0;
 	int32_t wlo = 0, whi = 0, last_state = 0, s = 0;
 	if (lane == 0) {
 		slo[0] = 0, shi[0] = 0;
 		H[wfs_col<W>(0)] = -1;
-		E1[wfs_col<W>(0)] = F1[wfs_col<W>(0)] = E2[wfs_col<W>(0)] = F2[wfs_col<W>(0)] = WF_NEG_INF;
+		E1[wfs_col<W>(0)] = F1[wfs_col<W>(0)] = E2[wfs_col<W>(0)] = F2[wfs_col<W>(0)] = (wf_cell_t)WF_NEG_INF16;
 	}
 	warp_sync();
 	for (;;) {
 		const int hs = s % 17;
 		const int32_t plo = slo[hs], phi = shi[hs];
-		int32_t *Hs = H + (s % HS) * W;
+		wf_cell_t *Hs = H + (s % HS) * W;
 		int hit = 0, hit_noext = 0;
 		for (int32_t d = plo + lane; d <= phi; d += MGB_W) {
 			int32_t k0 = Hs[wfs_col<W>(d)];
 			if (k0 < -1 || d + k0 < -1 || k0 >= tl || d + k0 >= ql) continue;
 			int32_t k = wf_extend(ts, qs, k0, d);
 			if (k == tl - 1 && d + k == ql - 1) hit = 1, hit_noext = (k == k0);
-			else Hs[wfs_col<W>(d)] = k;
+			else Hs[wfs_col<W>(d)] = (wf_cell_t)k;
 		}
 		warp_sync();
 		if (HS < 17) { // final values of this slice go to the global ring (read again 16 scores later)
@@ -254,7 +261,7 @@ MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g,
 		const WfSrc sHx = wfs_src<W>(H, HS, slo, shi, ns - WF_X), sHo1 = wfs_src<W>(H, HS, slo, shi, ns - (WF_O1 + WF_E1)),
 					sHo2 = HS < 17? wfs_src<W>(Hg, 17, slo, shi, ns - (WF_O2 + WF_E2)) : wfs_src<W>(H, 17, slo, shi, ns - (WF_O2 + WF_E2)), sE1 = wfs_src<W>(E1, 3, slo, shi, ns - WF_E1),
 					sF1 = wfs_src<W>(F1, 3, slo, shi, ns - WF_E1), sE2 = wfs_src<W>(E2, 2, slo, shi, ns - WF_E2), sF2 = wfs_src<W>(F2, 2, slo, shi, ns - WF_E2);
-		int32_t *nH = H + (ns % HS) * W, *nE1 = E1 + (ns % 3) * W, *nF1 = F1 + (ns % 3) * W, *nE2 = E2 + (ns % 2) * W, *nF2 = F2 + (ns % 2) * W;
+		wf_cell_t *nH = H + (ns % HS) * W, *nE1 = E1 + (ns % 3) * W, *nF1 = F1 + (ns % 3) * W, *nE2 = E2 + (ns % 2) * W, *nF2 = F2 + (ns % 2) * W;
 		for (int32_t d = lo + lane; d <= hi; d += MGB_W) { // reference: miniwfa.c:281-308 wf_next_tb
 			int32_t h, f, e, e1, e2, f1, f2, a0, b0;
 			uint8_t x = 0, ze, zf, z;
@@ -276,7 +283,7 @@ MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g,
 			z = a0 >= h? 0 : z;
 			h = MGB_WF_MAX(a0, h);
 			const int32_t c = wfs_col<W>(d);
-			nE1[c] = e1, nF1[c] = f1, nE2[c] = e2, nF2[c] = f2, nH[c] = h; // slots of score ns are not read in this loop
+			nE1[c] = (wf_cell_t)e1, nF1[c] = (wf_cell_t)f1, nE2[c] = (wf_cell_t)e2, nF2[c] = (wf_cell_t)f2, nH[c] = (wf_cell_t)h; // slots of score ns are not read in this loop
 			ax[d] = x | z;
 		}
 		if (lane == 0) slo[nhs] = lo, shi[nhs] = hi;
@@ -905,6 +912,6 @@ MG_HD inline int wfa_exact(Arena &A, int32_t tl, const char *ts_g, int32_t ql, c
 
 // the tiers of the job kernels (K8a)
 typedef WfSmemLayout<64, 256, 4096, 17> WfTier1;  // small gaps: 4 warps per block, traceback bytes in shared memory
-typedef WfSmemLayout<256, 1024, 0, 7> WfTier2;    // mid-size gaps: 2 warps per block, old H slices + traceback rows in the arena
+typedef WfSmemLayout<256, 1024, 0, 17> WfTier2;   // mid-size gaps: 2 warps per block, traceback rows in the arena
 
 } // namespace mgb
