@@ -60,6 +60,13 @@ MG_D inline int32_t warp_min_i32(int32_t x) { for (int o = 16; o > 0; o >>= 1) {
 MG_D inline int32_t warp_max_i32(int32_t x) { for (int o = 16; o > 0; o >>= 1) { int32_t y = __shfl_xor_sync(0xffffffffu, x, o); x = y > x? y : x; } return x; }
 MG_D inline int32_t warp_sum_i32(int32_t x) { for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o); return x; }
 MG_D inline uint32_t warp_ballot(int pred) { return __ballot_sync(0xffffffffu, pred); }
+// maximum over the lanes below this one (INT32_MIN on lane 0)
+MG_D inline int32_t warp_excl_prefix_max_i32(int32_t x, int lane)
+{
+	for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o && y > x) x = y; }
+	x = __shfl_up_sync(0xffffffffu, x, 1);
+	return lane == 0? INT32_MIN : x;
+}
 MG_D inline int mask_rank(uint32_t mask, int lane) { return __popc(mask & ((1u << lane) - 1u)); } // set bits below `lane`
 MG_D inline int mask_count(uint32_t mask) { return __popc(mask); }
 #else
@@ -72,6 +79,7 @@ inline int32_t warp_min_i32(int32_t x) { return x; }
 inline int32_t warp_max_i32(int32_t x) { return x; }
 inline int32_t warp_sum_i32(int32_t x) { return x; }
 inline uint32_t warp_ballot(int pred) { return pred? 1u : 0u; }
+inline int32_t warp_excl_prefix_max_i32(int32_t, int) { return INT32_MIN; }
 inline int mask_rank(uint32_t, int) { return 0; }
 inline int mask_count(uint32_t mask) { return (int)(mask & 1u); }
 #endif

@@ -176,14 +176,14 @@ struct LaunchArgs {
 // stages: 0 seed (K1-K3), 1 chain (K4/K5), 2 gchain + alignment plan (K6/K7), 3 segment sketch for the index,
 //         4/6/7 WFA jobs tier 1/2/3 (K8a, warp-cooperative), 5 finish: CIGAR stitching + ds + result blob (K8b)
 #define MGB_IS_WFA(STAGE) ((STAGE) == 4 || (STAGE) == 6 || (STAGE) == 7)
-#define MGB_IS_WARP(STAGE) (MGB_IS_WFA(STAGE) || (STAGE) == 8 || (STAGE) == 1 || (STAGE) == 0) // stages entered by all lanes of the warp
+#define MGB_IS_WARP(STAGE) (MGB_IS_WFA(STAGE) || (STAGE) == 8 || (STAGE) == 1 || (STAGE) == 0 || (STAGE) == 5) // stages entered by all lanes of the warp
 template<int STAGE>
 MG_HD inline int run_stage(const LaunchArgs &L, int item, Arena &A, int lane, int32_t *smem)
 {
 	if (STAGE == 0) return stage_seed(L.c, item, A, lane);
 	if (STAGE == 1) return stage_chain(L.c, item, A, lane);
 	if (STAGE == 2) return stage_gchain(L.c, L.routs, item, A);
-	if (STAGE == 5) return stage_finish(L.c, L.routs, item, A);
+	if (STAGE == 5) return stage_finish(L.c, L.routs, item, A, lane);
 	if (STAGE == 8) return gwfa_job_run(A, L.c, L.job_start + item, lane, smem);
 	if (STAGE == 9) return stage_gchain_gen(L.c, L.routs, item, A);
 	if (STAGE == 4) return wfa_job_run(A, L.c, L.job_start + item, lane, smem, 1);

@@ -233,130 +233,177 @@ struct DsOut { char *ds; int32_t len; int32_t *off; int32_t n_off; };
 
 MG_HD inline char ds_nt(const char *s, int64_t i) { return "acgtn"[nt4((uint8_t)s[i])]; }
 
-MG_HD inline int ds_putc(Arena &A, AVec<char> &s, char c) { return avec_push(A, s, c); }
-
-MG_HD inline int ds_putint(Arena &A, AVec<char> &s, int32_t c)
+// ---- raw writers for the chunked ds generation: the caller has sized the buffers from per-operation upper bounds ----
+MG_HD inline char *ds_w_int(char *w, int32_t c)
 {
 	char buf[16];
 	int l = 0;
 	uint32_t x = c >= 0? (uint32_t)c : (uint32_t)(-c);
 	do { buf[l++] = (char)(x % 10 + '0'); x /= 10; } while (x > 0);
 	if (c < 0) buf[l++] = '-';
-	for (int i = l - 1; i >= 0; --i) MGB_TRY(avec_push(A, s, buf[i]));
-	return 0;
+	for (int i = l - 1; i >= 0; --i) *w++ = buf[i];
+	return w;
 }
 
 // reference: galign.c:153-180 write_indel
-MG_HD inline int ds_write_indel(Arena &A, AVec<char> &str, int64_t len, const char *seq, int64_t ll, int64_t lr)
+MG_HD inline char *ds_w_indel(char *w, int64_t len, const char *seq, int64_t ll, int64_t lr)
 {
 	int64_t i;
 	if (ll + lr >= len) {
-		MGB_TRY(ds_putc(A, str, '['));
-		for (i = 0; i < len; ++i) MGB_TRY(ds_putc(A, str, ds_nt(seq, i)));
-		MGB_TRY(ds_putc(A, str, ']'));
+		*w++ = '[';
+		for (i = 0; i < len; ++i) *w++ = ds_nt(seq, i);
+		*w++ = ']';
 	} else {
 		int64_t k = 0;
 		if (ll > 0) {
-			MGB_TRY(ds_putc(A, str, '['));
-			for (i = 0; i < ll; ++i) MGB_TRY(ds_putc(A, str, ds_nt(seq, k + i)));
-			MGB_TRY(ds_putc(A, str, ']'));
+			*w++ = '[';
+			for (i = 0; i < ll; ++i) *w++ = ds_nt(seq, k + i);
+			*w++ = ']';
 			k += ll;
 		}
-		for (i = 0; i < len - lr - ll; ++i) MGB_TRY(ds_putc(A, str, ds_nt(seq, k + i)));
+		for (i = 0; i < len - lr - ll; ++i) *w++ = ds_nt(seq, k + i);
 		k += len - lr - ll;
 		if (lr > 0) {
-			MGB_TRY(ds_putc(A, str, '['));
-			for (i = 0; i < lr; ++i) MGB_TRY(ds_putc(A, str, ds_nt(seq, k + i)));
-			MGB_TRY(ds_putc(A, str, ']'));
+			*w++ = '[';
+			for (i = 0; i < lr; ++i) *w++ = ds_nt(seq, k + i);
+			*w++ = ']';
 		}
 	}
-	return 0;
+	return w;
 }
 
-MG_HD inline int gchain_ds(Arena &A, const GraphDev &g, const char *qseq, GcSet &gt, const CigarOut *cg, DsOut *out)
+static const int DS_CHUNKS = 32;
+struct DsChunk { int64_t dx, dy; int32_t cap_b, cap_o, n_b, n_o; };
+
+// The ds:Z string of every chain (reference: galign.c:182-262 mg_gchain_gen_ds).  What one CIGAR operation contributes
+// depends only on the operation and on where it starts on the walk and on the read, so the operations are cut into
+// DS_CHUNKS runs that are written independently (by different lanes on the device) and then joined in order.
+// Warp-uniform: all lanes enter; out[] is filled identically on every lane.
+MG_HD inline int gchain_ds_w(Arena &A, const GraphDev &g, const char *qseq, GcSet &gt, const CigarOut *cg, DsOut *out, int lane)
 {
 	for (int32_t i = 0; i < gt.n_gc; ++i) {
 		GChain *gc = &gt.gc[i];
-		int32_t j;
-		int64_t x, y;
-		AVec<char> str;
-		AVec<int32_t> off;
+		const uint64_t *cigar = cg[i].cigar;
+		const int32_t n_cigar = gc->n_cigar, aplen = gc->c_aplen;
 		char *seq;
 		int64_t seq_l = 0;
-		avec_init(str), avec_init(off);
-		MGB_ALLOC(A, seq, char, gc->c_aplen + 1);
-		for (j = 0; j < gc->cnt; ++j) { // the aligned part of the walk
-			int32_t k = gc->off + j;
-			uint32_t v = gt.lc[k].v;
-			int32_t slen = g_vlen(g, v);
-			int32_t st = j > 0? 0 : gc->c_ss;
-			int32_t en = j < gc->cnt - 1? slen : gc->c_ee;
-			if (seq_l + (en - st) > gc->c_aplen) return MGB_E_INTERNAL;
+		MGB_ALLOC(A, seq, char, aplen + 1);
+		for (int32_t j = 0; j < gc->cnt; ++j) { // the aligned part of the walk
+			const int32_t k = gc->off + j;
+			const uint32_t v = gt.lc[k].v;
+			const int32_t slen = g_vlen(g, v);
+			const int32_t st = j > 0? 0 : gc->c_ss;
+			const int32_t en = j < gc->cnt - 1? slen : gc->c_ee;
+			if (seq_l + (en - st) > aplen) return MGB_E_INTERNAL;
 			const char *s = g_vseq(g, v) + st;
-			for (int32_t t = 0; t < en - st; ++t) seq[seq_l + t] = s[t];
+			for (int32_t t = lane; t < en - st; t += MGB_W) seq[seq_l + t] = s[t];
 			seq_l += en - st;
 		}
-		if (seq_l != gc->c_aplen) return MGB_E_INTERNAL;
-		// both vectors grow; interleaved growth wastes arena but stays correct
-		MGB_TRY(avec_reserve(A, off, 64));
-		MGB_TRY(avec_reserve(A, str, 256));
-		for (j = 0, x = 0, y = gc->qs; j < gc->n_cigar; ++j) {
-			int64_t op = (int64_t)(cg[i].cigar[j] & 0xf), len = (int64_t)(cg[i].cigar[j] >> 4);
-			if (op == 0 || op == 7 || op == 8) {
-				int64_t z;
-				int32_t l = 0;
-				if (op == 7) l = (int32_t)len, z = len; // '=' runs hold identical characters: nothing to look at
-				else z = 0;
-				for (; z < len; ++z) {
-					uint8_t cx = (uint8_t)nt4((uint8_t)seq[x + z]);
-					uint8_t cy = (uint8_t)nt4((uint8_t)qseq[y + z]);
-					if (cx != cy) {
-						if (l > 0) {
-							MGB_TRY(avec_push(A, off, (int32_t)str.n));
-							MGB_TRY(ds_putc(A, str, ':'));
-							MGB_TRY(ds_putint(A, str, l));
-						}
-						MGB_TRY(avec_push(A, off, (int32_t)str.n));
-						MGB_TRY(ds_putc(A, str, '*'));
-						MGB_TRY(ds_putc(A, str, "acgtn"[cx]));
-						MGB_TRY(ds_putc(A, str, "acgtn"[cy]));
-						l = 0;
-					} else ++l;
+		if (seq_l != aplen) return MGB_E_INTERNAL;
+		DsChunk *ch;
+		MGB_ALLOC(A, ch, DsChunk, DS_CHUNKS);
+		const int32_t per = (n_cigar + DS_CHUNKS - 1) / DS_CHUNKS;
+		// pass 0: how far each run advances, and how much it can write at most
+		for (int c = lane; c < DS_CHUNKS; c += MGB_W) {
+			const int32_t j0 = c * per < n_cigar? c * per : n_cigar, j1 = j0 + per < n_cigar? j0 + per : n_cigar;
+			DsChunk d;
+			d.dx = d.dy = 0, d.cap_b = d.cap_o = d.n_b = d.n_o = 0;
+			for (int32_t j = j0; j < j1; ++j) {
+				const int64_t op = (int64_t)(cigar[j] & 0xf), len = (int64_t)(cigar[j] >> 4);
+				if (op == 7) d.dx += len, d.dy += len, d.cap_b += 12, d.cap_o += 1;
+				else if (op == 0 || op == 8) d.dx += len, d.dy += len, d.cap_b += (int32_t)(14 * len + 12), d.cap_o += (int32_t)(2 * len + 1);
+				else if (op == 1) d.dy += len, d.cap_b += (int32_t)(len + 6), d.cap_o += 1;
+				else if (op == 2) d.dx += len, d.cap_b += (int32_t)(len + 6), d.cap_o += 1;
+			}
+			ch[c] = d;
+		}
+		warp_sync();
+		int64_t tot_cb = 0, tot_co = 0;
+		for (int c = 0; c < DS_CHUNKS; ++c) tot_cb += ch[c].cap_b, tot_co += ch[c].cap_o;
+		char *tmp_b;
+		int32_t *tmp_o;
+		MGB_ALLOC(A, tmp_b, char, tot_cb);
+		MGB_ALLOC(A, tmp_o, int32_t, tot_co);
+		// pass 1: every run writes its text and its (run-relative) offsets
+		int bad = 0;
+		for (int c = lane; c < DS_CHUNKS; c += MGB_W) {
+			const int32_t j0 = c * per < n_cigar? c * per : n_cigar, j1 = j0 + per < n_cigar? j0 + per : n_cigar;
+			int64_t x = 0, y = gc->qs, cb = 0, co = 0;
+			for (int q = 0; q < c; ++q) x += ch[q].dx, y += ch[q].dy, cb += ch[q].cap_b, co += ch[q].cap_o;
+			char *const w0 = tmp_b + cb;
+			char *w = w0;
+			int32_t *const o0 = tmp_o + co;
+			int32_t *o = o0;
+			for (int32_t j = j0; j < j1; ++j) {
+				const int64_t op = (int64_t)(cigar[j] & 0xf), len = (int64_t)(cigar[j] >> 4);
+				if (op == 0 || op == 7 || op == 8) {
+					int64_t z;
+					int32_t l = 0;
+					if (op == 7) l = (int32_t)len, z = len; // '=' runs hold identical characters: nothing to look at
+					else z = 0;
+					for (; z < len; ++z) {
+						const uint8_t cx = (uint8_t)nt4((uint8_t)seq[x + z]);
+						const uint8_t cy = (uint8_t)nt4((uint8_t)qseq[y + z]);
+						if (cx != cy) {
+							if (l > 0) { *o++ = (int32_t)(w - w0); *w++ = ':'; w = ds_w_int(w, l); }
+							*o++ = (int32_t)(w - w0);
+							*w++ = '*', *w++ = "acgtn"[cx], *w++ = "acgtn"[cy];
+							l = 0;
+						} else ++l;
+					}
+					if (l > 0) { *o++ = (int32_t)(w - w0); *w++ = ':'; w = ds_w_int(w, l); }
+					x += len, y += len;
+				} else if (op == 1) {
+					int64_t z, ll, lr;
+					for (z = 1; z <= len; ++z)
+						if (y - z < gc->qs || qseq[y + len - z] != qseq[y - z]) break;
+					lr = z - 1;
+					for (z = 0; z < len; ++z)
+						if (y + len + z >= gc->qe || qseq[y + len + z] != qseq[y + z]) break;
+					ll = z;
+					*o++ = (int32_t)(w - w0);
+					*w++ = '+';
+					w = ds_w_indel(w, len, &qseq[y], ll, lr);
+					y += len;
+				} else if (op == 2) {
+					int64_t z, ll, lr;
+					for (z = 1; z <= len; ++z)
+						if (x - z < 0 || seq[x + len - z] != seq[x - z]) break;
+					lr = z - 1;
+					for (z = 0; z < len; ++z)
+						if (x + len + z >= aplen || seq[x + z] != seq[x + len + z]) break;
+					ll = z;
+					*o++ = (int32_t)(w - w0);
+					*w++ = '-';
+					w = ds_w_indel(w, len, &seq[x], ll, lr);
+					x += len;
 				}
-				if (l > 0) {
-					MGB_TRY(avec_push(A, off, (int32_t)str.n));
-					MGB_TRY(ds_putc(A, str, ':'));
-					MGB_TRY(ds_putint(A, str, l));
-				}
-				x += len, y += len;
-			} else if (op == 1) {
-				int64_t z, ll, lr;
-				for (z = 1; z <= len; ++z)
-					if (y - z < gc->qs || qseq[y + len - z] != qseq[y - z]) break;
-				lr = z - 1;
-				for (z = 0; z < len; ++z)
-					if (y + len + z >= gc->qe || qseq[y + len + z] != qseq[y + z]) break;
-				ll = z;
-				MGB_TRY(avec_push(A, off, (int32_t)str.n));
-				MGB_TRY(ds_putc(A, str, '+'));
-				MGB_TRY(ds_write_indel(A, str, len, &qseq[y], ll, lr));
-				y += len;
-			} else if (op == 2) {
-				int64_t z, ll, lr;
-				for (z = 1; z <= len; ++z)
-					if (x - z < 0 || seq[x + len - z] != seq[x - z]) break;
-				lr = z - 1;
-				for (z = 0; z < len; ++z)
-					if (x + len + z >= gc->c_aplen || seq[x + z] != seq[x + len + z]) break;
-				ll = z;
-				MGB_TRY(avec_push(A, off, (int32_t)str.n));
-				MGB_TRY(ds_putc(A, str, '-'));
-				MGB_TRY(ds_write_indel(A, str, len, &seq[x], ll, lr));
-				x += len;
+			}
+			ch[c].n_b = (int32_t)(w - w0), ch[c].n_o = (int32_t)(o - o0);
+			if (ch[c].n_b > ch[c].cap_b || ch[c].n_o > ch[c].cap_o) bad = 1; // cannot happen: the bounds are per operation
+		}
+		if (warp_any(bad)) return MGB_E_INTERNAL;
+		warp_sync();
+		// join
+		int64_t tot_b = 0, tot_o = 0;
+		for (int c = 0; c < DS_CHUNKS; ++c) tot_b += ch[c].n_b, tot_o += ch[c].n_o;
+		char *str;
+		int32_t *off;
+		MGB_ALLOC(A, str, char, tot_b + 1);
+		MGB_ALLOC(A, off, int32_t, tot_o);
+		{
+			int64_t cb = 0, co = 0, ab = 0, ao = 0;
+			for (int c = 0; c < DS_CHUNKS; ++c) {
+				const char *sb = tmp_b + cb;
+				const int32_t *so = tmp_o + co;
+				for (int32_t t = lane; t < ch[c].n_b; t += MGB_W) str[ab + t] = sb[t];
+				for (int32_t t = lane; t < ch[c].n_o; t += MGB_W) off[ao + t] = so[t] + (int32_t)ab;
+				cb += ch[c].cap_b, co += ch[c].cap_o, ab += ch[c].n_b, ao += ch[c].n_o;
 			}
 		}
-		out[i].ds = str.a, out[i].len = (int32_t)str.n, out[i].off = off.a, out[i].n_off = (int32_t)off.n;
-		gc->ds_len = (int32_t)str.n, gc->n_dsoff = (int32_t)off.n;
+		warp_sync();
+		out[i].ds = str, out[i].len = (int32_t)tot_b, out[i].off = off, out[i].n_off = (int32_t)tot_o;
+		if (lane == 0) gc->ds_len = (int32_t)tot_b, gc->n_dsoff = (int32_t)tot_o;
 	}
 	return 0;
 }
@@ -554,11 +601,12 @@ MG_HD inline int stage_gchain_gen(const PipeCtx &c, ReadOut *routs, int rid, Are
 }
 
 // K8b for one read: stitch CIGARs, ds strings, part 2 of the result (one lane).
-MG_HD inline int stage_finish(const PipeCtx &c, ReadOut *routs, int rid, Arena &A)
+// Warp-uniform: all lanes enter.  The CIGAR stitching runs on lane 0, the ds strings and the copies on all lanes.
+MG_HD inline int stage_finish(const PipeCtx &c, ReadOut *routs, int rid, Arena &A, int lane)
 {
 	ReadMeta &m = c.meta[rid];
 	ReadOut &ro = routs[rid];
-	if (m.status != 0) { ro.status = m.status; return 0; }
+	if (m.status != 0) { if (lane == 0) ro.status = m.status; return 0; }
 	if (!(c.opt.flag & F_CIGAR) || ro.n_gc == 0) return 0;
 	uint64_t mark = A.top;
 	const char *qseq = c.b.seq + c.b.seq_off[rid];
@@ -573,31 +621,42 @@ MG_HD inline int stage_finish(const PipeCtx &c, ReadOut *routs, int rid, Arena &
 	MGB_ALLOC(A, cg, CigarOut, gs.n_gc);
 	MGB_ALLOC(A, ds, DsOut, gs.n_gc);
 	unsigned long long pt0 = prof_clock();
-	MGB_TRY(gchain_cigar_finish(A, c, gs, cg));
+	{
+		Arena B = A;
+		int rc = 0;
+		if (lane == 0) rc = gchain_cigar_finish(B, c, gs, cg); // cg[] and the chain headers live in memory: visible to all lanes after the sync
+		rc = warp_bcast_i32(rc, 0);
+		A.top = warp_bcast_u64(B.top, 0);
+		A.peak = warp_bcast_u64(B.peak, 0);
+		warp_sync();
+		if (rc < 0) return rc;
+	}
 	unsigned long long pt1 = prof_clock();
-	prof_add(c, PROF_FIN_CIGAR_CYC, pt1 - pt0);
-	MGB_TRY(gchain_ds(A, c.g, qseq, gs, cg, ds));
-	prof_add(c, PROF_FIN_DS_CYC, prof_clock() - pt1);
+	MGB_TRY(gchain_ds_w(A, c.g, qseq, gs, cg, ds, lane));
+	if (lane == 0) prof_add(c, PROF_FIN_CIGAR_CYC, pt1 - pt0), prof_add(c, PROF_FIN_DS_CYC, prof_clock() - pt1);
 	uint64_t sz = 0;
 	for (int32_t i = 0; i < gs.n_gc; ++i)
 		sz += align8((uint64_t)cg[i].n * 8) + align8((uint64_t)ds[i].len + 1) + align8((uint64_t)ds[i].n_off * 4);
-	int64_t boff = pool_alloc(c.pool_out, sz);
+	int64_t boff = 0;
+	if (lane == 0) boff = pool_alloc(c.pool_out, sz);
+	boff = (int64_t)warp_bcast_u64((uint64_t)boff, 0);
 	if (boff < 0) return MGB_E_POOL;
 	uint64_t at = (uint64_t)boff;
 	for (int32_t i = 0; i < gs.n_gc; ++i) {
 		GChain *gc = &gs.gc[i];
-		gc->cigar_off = (int64_t)at; at += align8((uint64_t)cg[i].n * 8);
-		gc->ds_off = (int64_t)at; at += align8((uint64_t)ds[i].len + 1);
-		gc->dsoff_off = (int64_t)at; at += align8((uint64_t)ds[i].n_off * 4);
-		uint64_t *dc = (uint64_t*)(c.out + gc->cigar_off);
-		for (int32_t k = 0; k < cg[i].n; ++k) dc[k] = cg[i].cigar[k];
-		char *dd = c.out + gc->ds_off;
-		for (int32_t k = 0; k < ds[i].len; ++k) dd[k] = ds[i].ds[k];
-		dd[ds[i].len] = 0;
-		int32_t *dof = (int32_t*)(c.out + gc->dsoff_off);
-		for (int32_t k = 0; k < ds[i].n_off; ++k) dof[k] = ds[i].off[k];
+		const int64_t cigar_off = (int64_t)at; at += align8((uint64_t)cg[i].n * 8);
+		const int64_t ds_off = (int64_t)at; at += align8((uint64_t)ds[i].len + 1);
+		const int64_t dsoff_off = (int64_t)at; at += align8((uint64_t)ds[i].n_off * 4);
+		if (lane == 0) gc->cigar_off = cigar_off, gc->ds_off = ds_off, gc->dsoff_off = dsoff_off;
+		uint64_t *dc = (uint64_t*)(c.out + cigar_off);
+		for (int32_t k = lane; k < cg[i].n; k += MGB_W) dc[k] = cg[i].cigar[k];
+		char *dd = c.out + ds_off;
+		for (int32_t k = lane; k < ds[i].len; k += MGB_W) dd[k] = ds[i].ds[k];
+		if (lane == 0) dd[ds[i].len] = 0;
+		int32_t *dof = (int32_t*)(c.out + dsoff_off);
+		for (int32_t k = lane; k < ds[i].n_off; k += MGB_W) dof[k] = ds[i].off[k];
 	}
-	ro.blob2_off = boff, ro.blob2_size = (uint32_t)sz;
+	if (lane == 0) ro.blob2_off = boff, ro.blob2_size = (uint32_t)sz;
 	A.top = mark;
 	return 0;
 }

@@ -194,6 +194,104 @@ MG_HD inline int chain_dp(Arena &A, int max_dist_x, int max_dist_y, int bw, int 
 	return 0;
 }
 
+// chain_dp() entered by all lanes of a warp.  The predecessors of anchor i are scored 32 at a time; the sequential
+// rules (strict improvement keeps the first maximum, the skip counter with its early exit, the t[] marks left by
+// visited predecessors) are then replayed on the ballots of the chunk, in visiting order.
+MG_HD inline int chain_dp_w(Arena &A, int max_dist_x, int max_dist_y, int bw, int max_skip, int max_iter, int min_cnt, int min_sc,
+							float pen_gap, float pen_skip, int is_cdna, int n_seg, int64_t n, u128 *a,
+							int32_t *n_u_, uint64_t **u_, int32_t *n_a_, int lane)
+{
+	int32_t *f, *t, *v, *p, max_drop = bw;
+	int64_t i, max_ii, st = 0;
+	*u_ = 0, *n_u_ = 0, *n_a_ = 0;
+	if (n == 0) return 0;
+	if (max_dist_x < bw) max_dist_x = bw;
+	if (max_dist_y < bw && !is_cdna) max_dist_y = bw;
+	if (is_cdna) max_drop = INT32_MAX;
+	uint64_t *u_store;
+	MGB_ALLOC(A, u_store, uint64_t, n);
+	uint64_t mark = A.top;
+	MGB_ALLOC(A, p, int32_t, n);
+	MGB_ALLOC(A, f, int32_t, n);
+	MGB_ALLOC(A, v, int32_t, n);
+	MGB_ALLOC(A, t, int32_t, n);
+	for (i = lane; i < n; i += MGB_W) t[i] = 0;
+	warp_sync();
+	for (i = 0, max_ii = -1; i < n; ++i) {
+		const u128 ai = a[i];
+		int64_t max_j = -1, end_j;
+		int32_t max_f = (int32_t)(ai.y >> 32 & 0xff), n_skip = 0;
+		while (st < i && (ai.x >> 32 != a[st].x >> 32 || ai.x > a[st].x + (uint64_t)max_dist_x)) ++st;
+		if (i - st > max_iter) st = i - max_iter;
+		end_j = st - 1;
+		for (int64_t base = i - 1; base >= st; base -= MGB_W) {
+			const int64_t j = base - lane;
+			int32_t sc = SC_NONE, pj = -1;
+			if (j >= st) {
+				sc = chain_score(ai, a[j], max_dist_x, max_dist_y, bw, pen_gap, pen_skip, is_cdna, n_seg);
+				if (sc != SC_NONE) sc += f[j], pj = p[j];
+			}
+			const int active = sc != SC_NONE;
+			if (pj >= 0) t[pj] = (int32_t)i; // marks of lanes past an early exit only touch anchors that are not visited either
+			warp_sync();
+			const int marked = active && t[j] == (int32_t)i;
+			const int32_t before = warp_excl_prefix_max_i32(sc, lane);
+			const int improves = active && sc > (before > max_f? before : max_f);
+			const uint32_t m_imp = warp_ballot(improves), m_mk = warp_ballot(marked && !improves);
+			uint32_t events = m_imp | m_mk;
+			int brk = -1;
+			while (events) {
+				const int l = ctz32(events);
+				events &= events - 1;
+				if (m_imp >> l & 1) { if (n_skip > 0) --n_skip; }
+				else if (++n_skip > max_skip) { brk = l; break; }
+			}
+			const int eligible = active && (brk < 0 || lane < brk);
+			const int32_t best = warp_max_i32(eligible? sc : SC_NONE);
+			if (best > max_f) {
+				max_f = best;
+				max_j = base - ctz32(warp_ballot(eligible && sc == best));
+			}
+			if (brk >= 0) { end_j = base - brk; break; }
+		}
+		if (max_ii < 0 || (int64_t)(ai.x - a[max_ii].x) > (int64_t)max_dist_x) {
+			int32_t mx = INT32_MIN, bj = -1;
+			for (int64_t j = i - 1 - lane; j >= st; j -= MGB_W)
+				if (mx < f[j]) mx = f[j], bj = (int32_t)j;
+			const int32_t m = warp_max_i32(mx);
+			max_ii = warp_max_i32(bj >= 0 && mx == m? bj : -1); // first in visiting order = the largest index among equals
+		}
+		if (max_ii >= 0 && max_ii < end_j) {
+			int32_t tmp = chain_score(ai, a[max_ii], max_dist_x, max_dist_y, bw, pen_gap, pen_skip, is_cdna, n_seg);
+			if (tmp != SC_NONE && max_f < tmp + f[max_ii])
+				max_f = tmp + f[max_ii], max_j = max_ii;
+		}
+		const int32_t vi = max_j >= 0 && v[max_j] > max_f? v[max_j] : max_f;
+		if (max_ii < 0 || ((int64_t)(ai.x - a[max_ii].x) <= (int64_t)max_dist_x && f[max_ii] < max_f))
+			max_ii = i;
+		if (lane == 0) f[i] = max_f, p[i] = (int32_t)max_j, v[i] = vi;
+		warp_sync();
+	}
+	// backtrack and compaction on one lane; u[] ends up in the block reserved at the caller's top
+	int rc = 0, n_u = 0, n_v = 0;
+	if (lane == 0) {
+		Arena B = A;
+		uint64_t *u;
+		rc = chain_backtrack(B, n, f, p, v, t, min_cnt, min_sc, max_drop, 0, &u, &n_u, &n_v);
+		if (rc == 0 && n_u > 0) {
+			rc = chain_compact(B, n_u, u, n_v, v, a);
+			for (i = 0; i < n_u; ++i) u_store[i] = u[i];
+		}
+		if (B.peak > A.peak) A.peak = B.peak;
+	}
+	rc = warp_bcast_i32(rc, 0), n_u = warp_bcast_i32(n_u, 0), n_v = warp_bcast_i32(n_v, 0);
+	warp_sync();
+	if (rc < 0) return rc;
+	A.top = mark;
+	*u_ = u_store, *n_u_ = n_u, *n_a_ = n_u > 0? n_v : 0;
+	return 0;
+}
+
 // gap-only score used by the RMQ DP (reference: lchain.c:234-250 comput_sc_simple)
 MG_HD inline int32_t chain_score_simple(const u128 &ai, const u128 &aj, float pen_gap, float pen_skip, int32_t *exact, int32_t *width)
 {

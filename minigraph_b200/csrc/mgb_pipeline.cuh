@@ -202,19 +202,8 @@ MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A, int lane)
 			MGB_TRY(chain_rmq_w(A, o.max_gap, o.max_gap_pre, o.bw, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
 								o.chn_pen_gap, o.chn_pen_skip, n_a, a, &n_lc, &u, &n_a_new, lane));
 		} else {
-			int rc = 0;
-			if (lane == 0) {
-				Arena B = A;
-				rc = chain_dp(B, max_gap_ref, max_gap_qry, o.bw, o.max_lc_skip, o.max_lc_iter, o.min_lc_cnt, o.min_lc_score,
-							  o.chn_pen_gap, o.chn_pen_skip, is_splice, 1, n_a, a, &n_lc, &u, &n_a_new);
-				if (B.peak > A.peak) A.peak = B.peak;
-			}
-			rc = warp_bcast_i32(rc, 0), n_lc = warp_bcast_i32(n_lc, 0), n_a_new = warp_bcast_i32(n_a_new, 0);
-			warp_sync();
-			if (rc < 0) return rc;
-			// chain_dp() leaves u[] in a block of n_a words at the caller's top: same address on every lane
-			u = (uint64_t*)(A.base + A.top);
-			A.top += ((uint64_t)n_a * 8 + 15) & ~(uint64_t)15;
+			MGB_TRY(chain_dp_w(A, max_gap_ref, max_gap_qry, o.bw, o.max_lc_skip, o.max_lc_iter, o.min_lc_cnt, o.min_lc_score,
+							   o.chn_pen_gap, o.chn_pen_skip, is_splice, 1, n_a, a, &n_lc, &u, &n_a_new, lane));
 		}
 	}
 	if (lane == 0) m.n_u0 = n_lc;
