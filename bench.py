@@ -153,6 +153,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = capi.load_product()
     lib.mgb_set_param(b"device", local_rank)
+    # host threads for packing, result assembly and GAF text: this rank's share of the box (two pools run at once)
+    host_threads = max(4, min(48, ncores // (2 * world)))
+    lib.mgb_set_param(b"host_threads", host_threads)
     for kv in os.environ.get("MGB_PARAMS", "").split(","):
         if "=" in kv:
             lib.mgb_set_param(kv.split("=")[0].encode(), int(kv.split("=")[1], 0))
@@ -184,11 +187,10 @@ def main():
                 return
             t0 = time.perf_counter()
             buf, ln = C.c_void_p(0), C.c_size_t(0)
-            lib.mgb_write_gaf_batch(g, n, gcs2[k], qlens, cnames, mo.flag, 0, C.byref(buf), C.byref(ln))
+            lib.mgb_write_gaf_batch(g, n, gcs2[k], qlens, cnames, mo.flag, host_threads, C.byref(buf), C.byref(ln))
             gaf_bytes[0] = ln.value
             C.CDLL(None).free(buf)
-            for i in range(n):
-                lib.mg_gchain_free(gcs2[k][i])
+            lib.mgb_free_batch(n, gcs2[k])
             host[5] += (time.perf_counter() - t0) * 1e3
             done_q.put(k)
 
@@ -289,7 +291,7 @@ def main():
         "config": {"workload": workload, "reads_per_gpu": n, "bases_per_gpu": bases, "l2": "512 MiB flush buffer written between steps",
                    "parallelism": "reads sharded one batch per GPU, index replicated; all-gather of GAF byte counts only",
                    "gaf_offsets": offsets},
-        "sub_batches": n_slots,
+        "sub_batches": n_slots, "host_threads": host_threads, "host_cores": ncores,
         "stage_ms_note": "stage_ms_per_step comes from one extra step run as a single sub-batch (kernels serialised on one stream, %.1f ms device span); in the timed steps %d sub-batches overlap and the summed per-stream stage times were %s" % (serial_span, n_slots, ["%.1f" % x for x in overlapped_stage]),
         "kernel_ms": kernel_ms,
         "stage_ms_per_step": {"seed(K1-K3)": stage[0] / a.steps, "chain(K4-K5)": stage[1] / a.steps, "gchain+plan(K6-K7)": stage[2] / a.steps,

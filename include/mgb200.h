@@ -195,6 +195,9 @@ void mg_gchain_free(mg_gchains_t *gs);
 int mg_map_batch(const mg_idx_t *gi, int n_reads, const int *qlens, const char *const *seqs, const char *const *names,
 				 mg_gchains_t **gcs, const mg_mapopt_t *opt);
 
+/* mg_gchain_free() over a whole batch (what step 2 of the reference pipeline does read by read, gmap.c:130); entries are set to NULL */
+void mgb_free_batch(int n_reads, mg_gchains_t **gcs);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Engine controls and instrumentation (not part of the reference API)
  * ---------------------------------------------------------------------------------------------------------- */

@@ -60,6 +60,15 @@ MG_D inline int32_t warp_min_i32(int32_t x) { for (int o = 16; o > 0; o >>= 1) {
 MG_D inline int32_t warp_max_i32(int32_t x) { for (int o = 16; o > 0; o >>= 1) { int32_t y = __shfl_xor_sync(0xffffffffu, x, o); x = y > x? y : x; } return x; }
 MG_D inline int32_t warp_sum_i32(int32_t x) { for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o); return x; }
 MG_D inline uint32_t warp_ballot(int pred) { return __ballot_sync(0xffffffffu, pred); }
+MG_D inline uint64_t warp_or_u64(uint64_t x) { for (int o = 16; o > 0; o >>= 1) x |= __shfl_xor_sync(0xffffffffu, x, o); return x; }
+MG_D inline uint64_t warp_and_u64(uint64_t x) { for (int o = 16; o > 0; o >>= 1) x &= __shfl_xor_sync(0xffffffffu, x, o); return x; }
+MG_D inline void lane_atomic_inc(int32_t *p) { atomicAdd(p, 1); }
+// sum over this lane and the lanes below it
+MG_D inline int32_t warp_incl_scan_i32(int32_t x, int lane)
+{
+	for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+	return x;
+}
 // maximum over the lanes below this one (INT32_MIN on lane 0)
 MG_D inline int32_t warp_excl_prefix_max_i32(int32_t x, int lane)
 {
@@ -80,6 +89,10 @@ inline int32_t warp_max_i32(int32_t x) { return x; }
 inline int32_t warp_sum_i32(int32_t x) { return x; }
 inline uint32_t warp_ballot(int pred) { return pred? 1u : 0u; }
 inline int32_t warp_excl_prefix_max_i32(int32_t, int) { return INT32_MIN; }
+inline int32_t warp_incl_scan_i32(int32_t x, int) { return x; }
+inline uint64_t warp_or_u64(uint64_t x) { return x; }
+inline uint64_t warp_and_u64(uint64_t x) { return x; }
+inline void lane_atomic_inc(int32_t *p) { ++*p; }
 inline int mask_rank(uint32_t, int) { return 0; }
 inline int mask_count(uint32_t mask) { return (int)(mask & 1u); }
 #endif
@@ -363,5 +376,90 @@ struct KeyU64 { MG_HD uint64_t operator()(const uint64_t &p) const { return p; }
 
 MG_HD inline int radix_sort_128x(Arena &A, u128 *a, int64_t n) { return radix_sort_exact(A, a, n, 8, KeyX128()); }
 MG_HD inline int radix_sort_64(Arena &A, uint64_t *a, int64_t n) { return radix_sort_exact(A, a, n, 8, KeyU64()); }
+
+// radix_sort_exact() entered by all lanes of a warp.  Only the cycle-leader permutation is inherently sequential (its
+// tie order is what has to be reproduced); it runs on lane 0 over the non-empty bins.  The digit census, the bin
+// offsets, the child ranges and the insertion sorts of the small bins are spread over the lanes.
+template<typename T, typename KeyFn>
+MG_HD inline int radix_sort_exact_w(Arena &A, T *a, int64_t n, int sizeof_key, KeyFn key, int lane)
+{
+	const int MIN_SIZE = 64;
+	if (n <= MIN_SIZE) { if (lane == 0) rs_insertsort(a, a + n, key); warp_sync(); return 0; }
+	uint64_t mark = A.top;
+	RsRange *stack;
+	int64_t m_stack = n / MIN_SIZE + 272;
+	MGB_ALLOC(A, stack, RsRange, m_stack);
+	int32_t *bb, *be, *nz;
+	MGB_ALLOC(A, bb, int32_t, 256);
+	MGB_ALLOC(A, be, int32_t, 256);
+	MGB_ALLOC(A, nz, int32_t, 256);
+	int64_t top = 0;
+	if (lane == 0) stack[0].beg = 0, stack[0].end = (int32_t)n, stack[0].s = (sizeof_key - 1) * 8;
+	top = 1;
+	warp_sync();
+	while (top > 0) {
+		const RsRange r = stack[--top];
+		int s = r.s;
+		uint64_t k_or = 0, k_and = ~0ULL;
+		for (int32_t i = r.beg + lane; i < r.end; i += MGB_W) { uint64_t k = (uint64_t)key(a[i]); k_or |= k, k_and &= k; }
+		k_or = warp_or_u64(k_or), k_and = warp_and_u64(k_and);
+		const uint64_t diff = k_or ^ k_and;
+		while (s > 0 && ((diff >> s) & 0xff) == 0) s -= 8;
+		if (s < 0) s = 0;
+		if (((diff >> s) & 0xff) == 0) continue;
+		for (int k = lane; k < 256; k += MGB_W) bb[k] = 0;
+		warp_sync();
+		for (int32_t i = r.beg + lane; i < r.end; i += MGB_W) lane_atomic_inc(&bb[(key(a[i]) >> s) & 0xff]);
+		warp_sync();
+		int32_t acc = r.beg, n_nz = 0;
+		for (int k0 = 0; k0 < 256; k0 += MGB_W) {
+			const int k = k0 + lane;
+			const int32_t c = bb[k];
+			const int32_t incl = warp_incl_scan_i32(c, lane);
+			const uint32_t mz = warp_ballot(c > 0);
+			warp_sync();
+			bb[k] = acc + incl - c, be[k] = acc + incl;
+			if (c > 0) nz[n_nz + mask_rank(mz, lane)] = k;
+			n_nz += mask_count(mz);
+			acc += warp_bcast_i32(incl, MGB_W - 1);
+		}
+		warp_sync();
+		if (lane == 0) {
+			for (int z = 0; z < n_nz;) { // cycle-leader permutation (empty bins have nothing to do)
+				const int k = nz[z];
+				if (bb[k] != be[k]) {
+					int l = (int)((key(a[bb[k]]) >> s) & 0xff);
+					if (l != k) {
+						T tmp = a[bb[k]], swap;
+						do {
+							swap = tmp; tmp = a[bb[l]]; a[bb[l]++] = swap;
+							l = (int)((key(tmp) >> s) & 0xff);
+						} while (l != k);
+						a[bb[k]++] = tmp;
+					} else ++bb[k];
+				} else ++z;
+			}
+		}
+		warp_sync();
+		if (s) {
+			const int s2 = s > 8? s - 8 : 0;
+			for (int k0 = 0; k0 < 256; k0 += MGB_W) {
+				const int k = k0 + lane;
+				const int32_t st = k == 0? r.beg : be[k - 1], en = be[k];
+				const int big = en - st > MIN_SIZE;
+				const uint32_t mb = warp_ballot(big);
+				if (top + mask_count(mb) > m_stack) { A.top = mark; return MGB_E_INTERNAL; }
+				if (big) { RsRange c; c.beg = st, c.end = en, c.s = s2; stack[top + mask_rank(mb, lane)] = c; }
+				else if (en - st > 1) rs_insertsort(a + st, a + en, key); // bins are disjoint: one lane each
+				top += mask_count(mb);
+			}
+		}
+		warp_sync();
+	}
+	A.top = mark;
+	return 0;
+}
+
+MG_HD inline int radix_sort_128x_w(Arena &A, u128 *a, int64_t n, int lane) { return radix_sort_exact_w(A, a, n, 8, KeyX128(), lane); }
 
 } // namespace mgb

@@ -688,6 +688,11 @@ extern "C" void mg_gchain_free(mg_gchains_t *gs)
 	free(gs);
 }
 
+extern "C" void mgb_free_batch(int n_reads, mg_gchains_t **gcs)
+{
+	for (int i = 0; i < n_reads; ++i) { mg_gchain_free(gcs[i]); gcs[i] = 0; }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // batch dispatcher
 // ---------------------------------------------------------------------------------------------------------------

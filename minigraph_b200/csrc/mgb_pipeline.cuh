@@ -64,35 +64,8 @@ MG_HD inline void prof_max(const PipeCtx &c, int slot, unsigned long long v)
 
 // K1-K3 for one read.  Writes sorted seeds to the anchor pool and the query positions of kept minimizers to the
 // mini_pos pool.
-// index lookup, seed expansion, seed sort (one lane)
-MG_HD inline int stage_seed_tail(const PipeCtx &c, ReadMeta &m, Arena &A, const AVec<u128> &mv, unsigned long long t0, unsigned long long t1)
-{
-	m.n_mz = (int32_t)mv.n;
-	prof_add(c, PROF_SEED_SKETCH_CYC, t1 - t0);
-	SeedMatch *sm;
-	int n_m, n_mp, rep_len;
-	int64_t n_a;
-	int32_t *mp_tmp;
-	MGB_ALLOC(A, mp_tmp, int32_t, mv.n);
-	MGB_TRY(collect_matches(A, c.ix, c.opt.occ_max1, mv, &sm, &n_m, &n_a, &rep_len, mp_tmp, &n_mp));
-	m.rep_len = rep_len;
-	int64_t a_off = pool_alloc(c.pool_anchor, (uint64_t)n_a * sizeof(u128));
-	int64_t mp_off = pool_alloc(c.pool_minipos, (uint64_t)n_mp * sizeof(int32_t));
-	if (a_off < 0 || mp_off < 0) return MGB_E_POOL;
-	m.a_off = a_off / (int64_t)sizeof(u128), m.mp_off = mp_off / (int64_t)sizeof(int32_t);
-	m.n_a = (int32_t)n_a, m.n_mp = n_mp, m.n_seed0 = (int32_t)n_a;
-	u128 *a = c.anchor + m.a_off;
-	int32_t *mp = c.minipos + m.mp_off;
-	for (int i = 0; i < n_mp; ++i) mp[i] = mp_tmp[i];
-	expand_seeds(c.g, n_m, sm, a);
-	unsigned long long t2 = prof_clock();
-	prof_add(c, PROF_SEED_MATCH_CYC, t2 - t1);
-	MGB_TRY(radix_sort_128x(A, a, n_a));
-	prof_add(c, PROF_SEED_SORT_CYC, prof_clock() - t2);
-	return 0;
-}
-
-// Warp-uniform: all lanes enter; the sketch is cut into chunks over the lanes, the rest runs on lane 0.
+// Warp-uniform: all lanes enter; the sketch is cut into chunks over the lanes, the index probes and the seed expansion
+// are spread over the lanes, the (order-sensitive, unstable) seed sort runs on lane 0.
 MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A, int lane)
 {
 	ReadMeta &m = c.meta[rid];
@@ -116,15 +89,34 @@ MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A, int lane)
 	unsigned long long t0 = prof_clock();
 	MGB_TRY(sketch_seq_w(A, seq, qlen, c.ix.w, c.ix.k, 0, mv, lane));
 	unsigned long long t1 = prof_clock();
-	int rc = 0;
+	SeedMatch *sm;
+	int n_m, n_mp, rep_len;
+	int64_t n_a;
+	int32_t *mp_tmp, *a_off;
+	MGB_ALLOC(A, mp_tmp, int32_t, mv.n);
+	MGB_TRY(collect_matches_w(A, c.ix, c.opt.occ_max1, mv, &sm, &n_m, &n_a, &rep_len, mp_tmp, &n_mp, &a_off, lane));
+	int64_t off_a = 0, off_mp = 0;
 	if (lane == 0) {
-		Arena B = A;
-		rc = stage_seed_tail(c, m, B, mv, t0, t1);
-		if (B.peak > A.peak) A.peak = B.peak;
+		off_a = pool_alloc(c.pool_anchor, (uint64_t)n_a * sizeof(u128));
+		off_mp = pool_alloc(c.pool_minipos, (uint64_t)n_mp * sizeof(int32_t));
 	}
-	rc = warp_bcast_i32(rc, 0);
+	off_a = (int64_t)warp_bcast_u64((uint64_t)off_a, 0), off_mp = (int64_t)warp_bcast_u64((uint64_t)off_mp, 0);
+	if (off_a < 0 || off_mp < 0) return MGB_E_POOL;
+	u128 *a = c.anchor + off_a / (int64_t)sizeof(u128);
+	int32_t *mp = c.minipos + off_mp / (int64_t)sizeof(int32_t);
+	if (lane == 0) {
+		m.n_mz = (int32_t)mv.n, m.rep_len = rep_len;
+		m.a_off = off_a / (int64_t)sizeof(u128), m.mp_off = off_mp / (int64_t)sizeof(int32_t);
+		m.n_a = (int32_t)n_a, m.n_mp = n_mp, m.n_seed0 = (int32_t)n_a;
+	}
+	for (int i = lane; i < n_mp; i += MGB_W) mp[i] = mp_tmp[i];
+	expand_seeds_w(c.g, n_m, sm, a_off, a, lane);
+	warp_sync();
+	unsigned long long t2 = prof_clock();
+	MGB_TRY(radix_sort_128x_w(A, a, n_a, lane));
+	if (lane == 0) prof_add(c, PROF_SEED_SKETCH_CYC, t1 - t0), prof_add(c, PROF_SEED_MATCH_CYC, t2 - t1), prof_add(c, PROF_SEED_SORT_CYC, prof_clock() - t2);
 	A.top = mark;
-	return rc;
+	return 0;
 }
 
 // chain records, end trimming, bad-seed filters, anchor update, pool write (reference: map-algo.c:419-449); one lane
@@ -216,15 +208,7 @@ MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A, int lane)
 			int64_t n2 = 0;
 			for (int32_t i = 0; i < n_lc; ++i) n2 += (int32_t)u[i];
 			A.top = mark;
-			int rc = 0;
-			if (lane == 0) {
-				Arena B = A;
-				rc = radix_sort_128x(B, a, n2);
-				if (B.peak > A.peak) A.peak = B.peak;
-			}
-			rc = warp_bcast_i32(rc, 0);
-			warp_sync();
-			if (rc < 0) return rc;
+			MGB_TRY(radix_sort_128x_w(A, a, n2, lane));
 			MGB_TRY(chain_rmq_w(A, o.max_gap, o.max_gap_pre, o.bw_long, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
 								o.chn_pen_gap, o.chn_pen_skip, n2, a, &n_lc, &u, &n_a_new, lane));
 		}

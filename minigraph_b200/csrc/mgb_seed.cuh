@@ -265,4 +265,87 @@ MG_HD inline void expand_seeds(const GraphDev &g, int n_m, const SeedMatch *m, u
 	}
 }
 
+// collect_matches() + the anchor offsets of expand_seeds(), entered by all lanes of a warp: the index probes (one random
+// HBM access chain each) run 32 at a time; the lists are then compacted in order and the repeat-length rule, which is
+// sequential over the rare high-occurrence minimizers, is replayed on their ballot.
+MG_HD inline int collect_matches_w(Arena &A, const IndexDev &ix, int max_occ, const AVec<u128> &mv, SeedMatch **m_, int *n_m_,
+								   int64_t *n_a, int *rep_len, int32_t *mini_pos, int *n_mini_pos, int32_t **a_off_, int lane)
+{
+	int rep_st = 0, rep_en = 0, rl = 0, n_m = 0;
+	int32_t tot = 0;
+	SeedMatch *m, *tm;
+	int32_t *a_off;
+	MGB_ALLOC(A, m, SeedMatch, mv.n);
+	MGB_ALLOC(A, a_off, int32_t, mv.n);
+	MGB_ALLOC(A, tm, SeedMatch, mv.n);
+	for (int64_t i = lane; i < mv.n; i += MGB_W) {
+		const u128 p = mv.a[i];
+		int t;
+		SeedMatch q;
+		q.cr = idx_get(ix, p.x >> 8, &t);
+		q.q_pos = (uint32_t)p.y, q.q_span = (uint32_t)(p.x & 0xff), q.n = (uint32_t)t, q.seg_id = (uint32_t)(p.y >> 32);
+		q.is_tandem = 0;
+		if (i > 0 && p.x >> 8 == mv.a[i - 1].x >> 8) q.is_tandem = 1;
+		if (i < mv.n - 1 && p.x >> 8 == mv.a[i + 1].x >> 8) q.is_tandem = 1;
+		tm[i] = q;
+	}
+	warp_sync();
+	for (int64_t base = 0; base < mv.n; base += MGB_W) {
+		const int64_t i = base + lane;
+		SeedMatch q;
+		q.n = 0, q.q_pos = q.q_span = q.seg_id = q.is_tandem = 0, q.cr = 0;
+		if (i < mv.n) q = tm[i];
+		const int high = i < mv.n && (int)q.n >= max_occ, keep = i < mv.n && !high;
+		uint32_t mh = warp_ballot(high);
+		const uint32_t mk = warp_ballot(keep);
+		while (mh) { // reference: map-algo.c:73-80
+			const int l = ctz32(mh);
+			mh &= mh - 1;
+			const SeedMatch h = tm[base + l];
+			const int en = (int)(h.q_pos >> 1) + 1, st = en - (int)h.q_span;
+			if (st > rep_en) {
+				rl += rep_en - rep_st;
+				rep_st = st, rep_en = en;
+			} else rep_en = en;
+		}
+		const int32_t cnt = keep? (int32_t)q.n : 0;
+		const int32_t incl = warp_incl_scan_i32(cnt, lane);
+		if (keep) {
+			const int at = n_m + mask_rank(mk, lane);
+			m[at] = q;
+			a_off[at] = tot + incl - cnt;
+			mini_pos[at] = (int32_t)(q.q_pos >> 1);
+		}
+		n_m += mask_count(mk);
+		tot += warp_bcast_i32(incl, MGB_W - 1);
+	}
+	rl += rep_en - rep_st;
+	warp_sync();
+	*rep_len = rl, *n_a = tot;
+	*m_ = m, *n_m_ = n_m, *n_mini_pos = n_m, *a_off_ = a_off;
+	return 0;
+}
+
+// expand_seeds() with the matches spread over the lanes; a_off[i] = number of anchors of the matches before i
+MG_HD inline void expand_seeds_w(const GraphDev &g, int n_m, const SeedMatch *m, const int32_t *a_off, u128 *a, int lane)
+{
+	for (int i = lane; i < n_m; i += MGB_W) {
+		const SeedMatch q = m[i];
+		const uint64_t *r = q.cr;
+		u128 *p = a + a_off[i];
+		for (uint32_t k = 0; k < q.n; ++k, ++p) {
+			uint64_t rk = r[k];
+			int32_t rpos = (int32_t)((uint32_t)rk >> 1);
+			u128 v;
+			if ((rk & 1) == (q.q_pos & 1)) v.x = rk >> 32 << 33 | (uint64_t)(uint32_t)rpos;
+			else v.x = rk >> 32 << 33 | 1ULL << 32 | (uint64_t)(uint32_t)(g.seg_len[rk >> 32] - (rpos + 1 - (int32_t)q.q_span) - 1);
+			v.y = (uint64_t)q.q_span << 32 | (uint64_t)(q.q_pos >> 1);
+			v.y |= (uint64_t)q.seg_id << SEED_SEG_SHIFT;
+			if (q.is_tandem) v.y |= SEED_TANDEM;
+			v.y |= (uint64_t)(q.n < 255? q.n : 255) << SEED_OCC_SHIFT;
+			*p = v;
+		}
+	}
+}
+
 } // namespace mgb
