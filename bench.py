@@ -179,6 +179,7 @@ def main():
     host = [0.0] * 6
     import queue
     out_q, done_q = queue.Queue(), queue.Queue()
+    gaf_buf, gaf_cap = C.c_void_p(0), C.c_size_t(0)  # the output buffer is handed back to the writer every batch
 
     def output_worker():
         while True:
@@ -186,10 +187,9 @@ def main():
             if k is None:
                 return
             t0 = time.perf_counter()
-            buf, ln = C.c_void_p(0), C.c_size_t(0)
-            lib.mgb_write_gaf_batch(g, n, gcs2[k], qlens, cnames, mo.flag, host_threads, C.byref(buf), C.byref(ln))
+            ln = C.c_size_t(0)
+            lib.mgb_write_gaf_batch(g, n, gcs2[k], qlens, cnames, mo.flag, host_threads, C.byref(gaf_buf), C.byref(ln), C.byref(gaf_cap))
             gaf_bytes[0] = ln.value
-            C.CDLL(None).free(buf)
             lib.mgb_free_batch(n, gcs2[k])
             host[5] += (time.perf_counter() - t0) * 1e3
             done_q.put(k)

@@ -242,10 +242,12 @@ void mgb_gfa_destroy(gfa_t *g);
  * appended to *buf (realloc()ed, *len/*cap updated). */
 void mgb_write_gaf(char **buf, size_t *len, size_t *cap, const gfa_t *g, const mg_gchains_t *gs, int32_t qlen, const char *qname, uint64_t flag);
 
-/* The same for a whole batch, input order preserved, formatted by n_threads host threads (0: up to 16). *out is
- * malloc()ed and 0-terminated; the caller frees it. */
+/* The same for a whole batch, input order preserved, formatted by n_threads host threads (0: up to 16). The text is
+ * 0-terminated and *out_len receives its length. out_cap == NULL: *out is a fresh malloc() block the caller frees.
+ * out_cap != NULL: (*out, *out_cap) is a buffer owned by the caller (NULL/0 the first time) that is reused and grown
+ * with realloc semantics, like mgb_write_gaf() does with (buf, cap). */
 void mgb_write_gaf_batch(const gfa_t *g, int n_reads, mg_gchains_t *const *gcs, const int *qlens, const char *const *names,
-						 uint64_t flag, int n_threads, char **out, size_t *out_len);
+						 uint64_t flag, int n_threads, char **out, size_t *out_len, size_t *out_cap);
 
 #ifdef __cplusplus
 }

@@ -586,39 +586,49 @@ extern "C" void mgb_write_gaf(char **buf, size_t *len, size_t *cap, const gfa_t 
 }
 
 // GAF text for a whole batch, input order preserved (the reference writes from one thread, gmap.c:101-141; here the
-// records are formatted by several host threads into per-thread buffers that are concatenated in read order).
+// records are formatted by several host threads into per-thread buffers, which the same threads then copy to their
+// place in the output).  The per-thread buffers are kept between calls, and a caller that hands back the previous
+// output buffer (*out with its *out_cap) gets it reused: in steady state no page is touched for the
+// first time, which is what the formatting of ~100 MB of text otherwise mostly waits for.
 #include <thread>
+#include <mutex>
+#include <functional>
 extern "C" void mgb_write_gaf_batch(const gfa_t *g, int n_reads, mg_gchains_t *const *gcs, const int *qlens, const char *const *names,
-									uint64_t flag, int n_threads, char **out, size_t *out_len)
+									uint64_t flag, int n_threads, char **out, size_t *out_len, size_t *out_cap)
 {
+	struct Part { char *buf; size_t len, cap; };
+	static std::mutex mtx;
+	static std::vector<Part> pool;
+	std::lock_guard<std::mutex> lock(mtx);
 	if (n_threads <= 0) { n_threads = (int)std::thread::hardware_concurrency(); if (n_threads > 16) n_threads = 16; if (n_threads < 1) n_threads = 1; }
 	if (n_reads < 256) n_threads = 1;
-	struct Part { char *buf; size_t len, cap; };
-	std::vector<Part> part((size_t)n_threads, Part{0, 0, 0});
-	int64_t chunk = ((int64_t)n_reads + n_threads - 1) / n_threads;
-	auto work = [&](int t) {
+	if ((int)pool.size() < n_threads) pool.resize((size_t)n_threads, Part{0, 0, 0});
+	const int64_t chunk = ((int64_t)n_reads + n_threads - 1) / n_threads;
+	auto run = [&](const std::function<void(int)> &fn) {
+		if (n_threads == 1) { fn(0); return; }
+		std::vector<std::thread> th;
+		for (int t = 0; t < n_threads; ++t) th.emplace_back(fn, t);
+		for (auto &x : th) x.join();
+	};
+	run([&](int t) {
 		int64_t b = t * chunk, e = b + chunk < n_reads? b + chunk : n_reads;
-		Part &p = part[(size_t)t];
-		size_t est = 0;
-		for (int64_t i = b; i < e; ++i) {
-			est += 256;
-			if (gcs[i]) for (int32_t k = 0; k < gcs[i]->n_gc; ++k) est += 512 + (gcs[i]->gc[k].p? (size_t)gcs[i]->gc[k].p->n_cigar * 8 : 0) + (size_t)gcs[i]->gc[k].ds.len;
-		}
-		p.buf = (char*)malloc(est), p.cap = est;
+		Part &p = pool[(size_t)t];
+		p.len = 0;
 		for (int64_t i = b; i < e; ++i)
 			mgb_write_gaf(&p.buf, &p.len, &p.cap, g, gcs[i], qlens[i], names && names[i]? names[i] : "*", flag);
-	};
-	if (n_threads == 1) work(0);
-	else {
-		std::vector<std::thread> th;
-		for (int t = 0; t < n_threads; ++t) th.emplace_back(work, t);
-		for (auto &x : th) x.join();
-	}
+	});
 	size_t tot = 0;
-	for (auto &p : part) tot += p.len;
-	char *o = (char*)malloc(tot + 1);
-	size_t at = 0;
-	for (auto &p : part) { if (p.len) memcpy(o + at, p.buf, p.len); at += p.len; free(p.buf); }
+	std::vector<size_t> at((size_t)n_threads, 0);
+	for (int t = 0; t < n_threads; ++t) at[(size_t)t] = tot, tot += pool[(size_t)t].len;
+	char *o = out_cap? *out : 0;
+	size_t cap = o? *out_cap : 0;
+	if (cap < tot + 1) {
+		free(o);
+		cap = tot + tot / 8 + 1;
+		o = (char*)malloc(cap);
+	}
+	run([&](int t) { const Part &p = pool[(size_t)t]; if (p.len) memcpy(o + at[(size_t)t], p.buf, p.len); });
 	o[tot] = 0;
 	*out = o, *out_len = tot;
+	if (out_cap) *out_cap = cap;
 }

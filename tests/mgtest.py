@@ -183,7 +183,7 @@ def gaf_with_engine(lib, gfa_path, names, seqs, preset="lr", cigar=True, flag_ex
     rc = lib.mg_map_batch(gi, n, qlens, cseqs, cnames, gcs, C.byref(mo))
     assert rc == 0, (rc, lib.mgb_last_error())
     buf, ln = C.c_void_p(0), C.c_size_t(0)
-    lib.mgb_write_gaf_batch(g, n, gcs, qlens, cnames, mo.flag, 0, C.byref(buf), C.byref(ln))
+    lib.mgb_write_gaf_batch(g, n, gcs, qlens, cnames, mo.flag, 0, C.byref(buf), C.byref(ln), None)
     for i in range(n):
         lib.mg_gchain_free(gcs[i])
     text = C.string_at(buf, ln.value) if buf else b""
