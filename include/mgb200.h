@@ -239,7 +239,7 @@ gfa_t *mgb_gfa_read(const char *fn);
 void mgb_gfa_destroy(gfa_t *g);
 
 /* Byte-exact GAF line(s) for one read, restating format.c:121-291 mg_write_gaf() for flag bits used by -c. The text is
- * appended to *buf (realloc()ed, *len/*cap updated). */
+ * appended to *buf (realloc()ed; *len and *cap updated). */
 void mgb_write_gaf(char **buf, size_t *len, size_t *cap, const gfa_t *g, const mg_gchains_t *gs, int32_t qlen, const char *qname, uint64_t flag);
 
 /* The same for a whole batch, input order preserved, formatted by n_threads host threads (0: up to 16). The text is

@@ -118,7 +118,9 @@ MG_HD inline int wf_traceback(const TB &tb, int32_t n_scores, int32_t tl, const 
 // =================================================================================================================
 // * H keeps 17 scores, E1/F1 keep 3, E2/F2 keep 2 (the deepest look-backs are o2+e2 = 16, e1 = 2, e2 = 1);
 // * instead of padding every slice with -inf cells, reads are bounds-checked against the per-score [lo,hi]
-//   (warp-uniform scalars), which returns exactly what the reference's padding holds;
+//   (warp-uniform, the last 16 of them held in registers), which returns exactly what the reference's padding holds;
+// * a new cell is extended along its exact matches right after it is computed (the reference extends the whole
+//   wavefront at the top of the next iteration: same cells, same values, one pass over shared memory less);
 // * diagonals map to columns modulo W, so any window of at most W diagonals fits;
 // * both sequences are staged in shared memory; with TBCAP > 0 the traceback bytes live there too.
 // The scheme gives up (returns 1, nothing written) when the window would exceed W diagonals, the traceback bytes
@@ -136,7 +138,7 @@ template<int W, int MAXLEN, int TBCAP, int HS = 17>
 struct WfSmemLayout {
 	static const int W_ = W, MAXLEN_ = MAXLEN, TBCAP_ = TBCAP, HS_ = HS;
 	static const int N_CELLS = (HS + 3 + 3 + 2 + 2) * W;
-	static const int N_INTS = N_CELLS / 2 + 2 * 17 + 2; // cells, then lo[17], hi[17]
+	static const int N_INTS = N_CELLS / 2;
 	static const int SEQ_BYTES = (MAXLEN + WF_SEQ_PAD + 3) / 4 * 4;
 	static const int TB_ROW_BYTES = TBCAP > 0? 256 * 8 : 0; // per score: int32 lo, int32 off
 	static const int BYTES = N_INTS * 4 + 2 * SEQ_BYTES + TB_ROW_BYTES + TBCAP;
@@ -150,16 +152,6 @@ MG_HD inline int32_t wfs_col(int32_t d) { return (d + (1 << 20)) & (W - 1); }
 
 template<int W>
 MG_HD inline int32_t wfs_at(const WfSrc &s, int32_t d) { return (d >= s.lo && d <= s.hi)? (int32_t)s.p[wfs_col<W>(d)] : WF_NEG_INF16; }
-
-template<int W>
-MG_HD inline WfSrc wfs_src(const wf_cell_t *arr, int nslot, const int32_t *lo, const int32_t *hi, int32_t score)
-{
-	WfSrc s;
-	if (score < 0) { s.p = arr, s.lo = 1, s.hi = 0; return s; }
-	int hs = score % 17;
-	s.p = arr + (score % nslot) * W, s.lo = lo[hs], s.hi = hi[hs];
-	return s;
-}
 
 struct WfTbSmem { // traceback bytes in shared memory: row table {lo, width, off} is packed as lo, off; width from the next row
 	const int32_t *row; const uint8_t *x; int32_t n_rows, used;
@@ -187,10 +179,9 @@ MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g,
 {
 	typedef WfSmemLayout<W, MAXLEN, TBCAP, HS> LY;
 	if (tl > MAXLEN || ql > MAXLEN) return 1;
+	if (MAXLEN > 16000 || HS != 17) return 1; // cells are 16-bit; all 17 H slices are kept on chip
 	uint64_t mark = A.top;
-	if (MAXLEN > 16000) return 1; // cells are 16-bit
 	wf_cell_t *H = (wf_cell_t*)smem, *E1 = H + HS * W, *F1 = E1 + 3 * W, *E2 = F1 + 3 * W, *F2 = E2 + 2 * W;
-	int32_t *slo = smem + LY::N_CELLS / 2, *shi = slo + 17;
 	char *ts = (char*)(smem + LY::N_INTS), *qs = ts + LY::SEQ_BYTES;
 	int32_t *tb_row = (int32_t*)(qs + LY::SEQ_BYTES); // TBCAP > 0 only
 	uint8_t *tb_x = (uint8_t*)tb_row + LY::TB_ROW_BYTES;
@@ -204,34 +195,29 @@ MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g,
 	AVec<WfTbRow> rows; // TBCAP == 0 only
 	avec_init(rows);
 	if (TBCAP == 0) MGB_TRY(avec_reserve_w(A, rows, 256, lane));
-	wf_cell_t *Hg = 0; // HS < 17: all 17 H slices, written back after their extension
-	if (HS < 17) MGB_ALLOC(A, Hg, wf_cell_t, 17 * W);
 	int32_t n_rows = 0, tb_used = 0;
 	int32_t wlo = 0, whi = 0, last_state = 0, s = 0;
-	if (lane == 0) {
-		slo[0] = 0, shi[0] = 0;
-		H[wfs_col<W>(0)] = -1;
+	int64_t n_iter = 0;
+	int hs = 0, m3 = 0, m2 = 0; // s % 17, s % 3, s % 2, kept incrementally
+	// [lo,hi] of the last 16 scores in registers, newest first: g0 = score s, g1 = s-1, ... (hi<<16 | lo+0x8000; 0x8001 = empty)
+#define MGB_WF_RG(lo_, hi_) ((uint32_t)((hi_) + 0x8000) << 16 | (uint32_t)((lo_) + 0x8000))
+	uint32_t g0 = MGB_WF_RG(0, 0), g1 = MGB_WF_RG(1, 0), g2 = g1, g3 = g1, g4 = g1, g5 = g1, g6 = g1, g7 = g1, g8 = g1, g9 = g1, g10 = g1, g11 = g1, g12 = g1, g13 = g1, g14 = g1, g15 = g1;
+	int hit = 0, hit_noext = 0;
+	if (lane == 0) { // score 0: the main diagonal, extended from the corner
 		E1[wfs_col<W>(0)] = F1[wfs_col<W>(0)] = E2[wfs_col<W>(0)] = F2[wfs_col<W>(0)] = (wf_cell_t)WF_NEG_INF16;
+		int32_t k0 = -1, k = -1;
+		if (!(k0 >= tl || k0 >= ql)) {
+			k = wf_extend(ts, qs, k0, 0);
+			if (k == tl - 1 && k == ql - 1) hit = 1, hit_noext = (k == k0), k = k0;
+		}
+		H[wfs_col<W>(0)] = (wf_cell_t)k;
 	}
+	hit = warp_any(hit), hit_noext = warp_any(hit_noext);
 	warp_sync();
 	for (;;) {
-		const int hs = s % 17;
-		const int32_t plo = slo[hs], phi = shi[hs];
-		wf_cell_t *Hs = H + (s % HS) * W;
-		int hit = 0, hit_noext = 0;
-		for (int32_t d = plo + lane; d <= phi; d += MGB_W) {
-			int32_t k0 = Hs[wfs_col<W>(d)];
-			if (k0 < -1 || d + k0 < -1 || k0 >= tl || d + k0 >= ql) continue;
-			int32_t k = wf_extend(ts, qs, k0, d);
-			if (k == tl - 1 && d + k == ql - 1) hit = 1, hit_noext = (k == k0);
-			else Hs[wfs_col<W>(d)] = (wf_cell_t)k;
-		}
-		warp_sync();
-		if (HS < 17) { // final values of this slice go to the global ring (read again 16 scores later)
-			for (int32_t d = plo + lane; d <= phi; d += MGB_W) Hg[hs * W + wfs_col<W>(d)] = Hs[wfs_col<W>(d)];
-		}
-		if (warp_any(hit)) {
-			if (warp_any(hit && hit_noext)) { // no extension on the last diagonal: the state comes from the traceback byte
+		// invariant: the wavefront of score s is computed, extended along exact matches and visible to all lanes
+		if (hit) {
+			if (hit_noext) { // no extension on the last diagonal: the state comes from the traceback byte
 				int32_t x;
 				if (TBCAP > 0) { WfTbSmem t; t.row = tb_row, t.x = tb_x, t.n_rows = n_rows, t.used = tb_used; x = t.get(n_rows - 1, ql - tl); }
 				else { WfTbArena t; t.row = rows.a; x = t.get(n_rows - 1, ql - tl); }
@@ -243,7 +229,8 @@ MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g,
 		const int32_t hi = whi < ql? whi + 1 : ql;
 		const int32_t width = hi - lo + 1;
 		if (width > W || s + 1 >= 255 || (TBCAP > 0 && tb_used + width > TBCAP)) { A.top = mark; return 1; }
-		const int32_t ns = s + 1, nhs = ns % 17;
+		const int32_t ns = s + 1;
+		const int nhs = hs + 1 == 17? 0 : hs + 1, n3 = m3 + 1 == 3? 0 : m3 + 1, n2 = m2 ^ 1;
 		uint8_t *ax;
 		if (TBCAP > 0) {
 			if (lane == 0) tb_row[2 * n_rows] = lo, tb_row[2 * n_rows + 1] = tb_used;
@@ -258,11 +245,18 @@ MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g,
 			ax = x - lo;
 		}
 		++n_rows;
-		const WfSrc sHx = wfs_src<W>(H, HS, slo, shi, ns - WF_X), sHo1 = wfs_src<W>(H, HS, slo, shi, ns - (WF_O1 + WF_E1)),
-					sHo2 = HS < 17? wfs_src<W>(Hg, 17, slo, shi, ns - (WF_O2 + WF_E2)) : wfs_src<W>(H, 17, slo, shi, ns - (WF_O2 + WF_E2)), sE1 = wfs_src<W>(E1, 3, slo, shi, ns - WF_E1),
-					sF1 = wfs_src<W>(F1, 3, slo, shi, ns - WF_E1), sE2 = wfs_src<W>(E2, 2, slo, shi, ns - WF_E2), sF2 = wfs_src<W>(F2, 2, slo, shi, ns - WF_E2);
-		wf_cell_t *nH = H + (ns % HS) * W, *nE1 = E1 + (ns % 3) * W, *nF1 = F1 + (ns % 3) * W, *nE2 = E2 + (ns % 2) * W, *nF2 = F2 + (ns % 2) * W;
-		for (int32_t d = lo + lane; d <= hi; d += MGB_W) { // reference: miniwfa.c:281-308 wf_next_tb
+		// source slices: score ns-4 (mismatch), ns-6 and ns-16 (gap opens), ns-2 and ns-1 (gap extensions)
+		const int r4 = nhs >= WF_X? nhs - WF_X : nhs - WF_X + 17, r6 = nhs >= WF_O1 + WF_E1? nhs - (WF_O1 + WF_E1) : nhs - (WF_O1 + WF_E1) + 17;
+		const int r16 = nhs >= WF_O2 + WF_E2? nhs - (WF_O2 + WF_E2) : nhs - (WF_O2 + WF_E2) + 17;
+		const int e1slot = n3 >= 2? n3 - 2 : n3 + 1; // (ns-2) % 3
+		WfSrc sHx, sHo1, sHo2, sE1, sF1, sE2, sF2;
+#define MGB_WF_SRC(dst, arr, slot, g) (dst).p = (arr) + (slot) * W, (dst).lo = (int32_t)((g) & 0xffffu) - 0x8000, (dst).hi = (int32_t)((g) >> 16) - 0x8000
+		MGB_WF_SRC(sHx, H, r4, g3); MGB_WF_SRC(sHo1, H, r6, g5); MGB_WF_SRC(sHo2, H, r16, g15);
+		MGB_WF_SRC(sE1, E1, e1slot, g1); MGB_WF_SRC(sF1, F1, e1slot, g1); MGB_WF_SRC(sE2, E2, m2, g0); MGB_WF_SRC(sF2, F2, m2, g0);
+#undef MGB_WF_SRC
+		wf_cell_t *nH = H + nhs * W, *nE1 = E1 + n3 * W, *nF1 = F1 + n3 * W, *nE2 = E2 + n2 * W, *nF2 = F2 + n2 * W;
+		int grow_lo = 0, grow_hi = 0;
+		for (int32_t d = lo + lane; d <= hi; d += MGB_W) { // reference: miniwfa.c:281-308 wf_next_tb, then :212-226 on the new cell
 			int32_t h, f, e, e1, e2, f1, f2, a0, b0;
 			uint8_t x = 0, ze, zf, z;
 			a0 = wfs_at<W>(sHo1, d - 1), b0 = wfs_at<W>(sE1, d - 1);
@@ -282,20 +276,31 @@ MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g,
 			a0 = wfs_at<W>(sHx, d) + 1;
 			z = a0 >= h? 0 : z;
 			h = MGB_WF_MAX(a0, h);
+			ax[d] = x | z;
+			if (h >= -1 || e1 >= -1 || f1 >= -1 || e2 >= -1 || f2 >= -1) { // does the window still grow on this side?
+				if (d == lo) grow_lo = 1;
+				if (d == hi) grow_hi = 1;
+			}
+			if (!(h < -1 || d + h < -1 || h >= tl || d + h >= ql)) { // extend the new cell right away
+				const int32_t k = wf_extend(ts, qs, h, d);
+				if (k == tl - 1 && d + k == ql - 1) hit = 1, hit_noext = (k == h);
+				else h = k;
+			}
 			const int32_t c = wfs_col<W>(d);
 			nE1[c] = (wf_cell_t)e1, nF1[c] = (wf_cell_t)f1, nE2[c] = (wf_cell_t)e2, nF2[c] = (wf_cell_t)f2, nH[c] = (wf_cell_t)h; // slots of score ns are not read in this loop
-			ax[d] = x | z;
 		}
-		if (lane == 0) slo[nhs] = lo, shi[nhs] = hi;
-		s = ns;
+		if (warp_any(grow_lo)) wlo = lo;
+		if (warp_any(grow_hi)) whi = hi;
+		hit = warp_any(hit);
+		hit_noext = warp_any(hit && hit_noext);
+		g15 = g14, g14 = g13, g13 = g12, g12 = g11, g11 = g10, g10 = g9, g9 = g8, g8 = g7, g7 = g6, g6 = g5, g5 = g4, g4 = g3, g3 = g2, g2 = g1, g1 = g0;
+		g0 = MGB_WF_RG(lo, hi);
+		s = ns, hs = nhs, m3 = n3, m2 = n2;
+		n_iter += width;
 		warp_sync();
-		{
-			const int32_t cl = wfs_col<W>(lo), ch = wfs_col<W>(hi);
-			if (nH[cl] >= -1 || nE1[cl] >= -1 || nF1[cl] >= -1 || nE2[cl] >= -1 || nF2[cl] >= -1) wlo = lo;
-			if (nH[ch] >= -1 || nE1[ch] >= -1 || nF1[ch] >= -1 || nE2[ch] >= -1 || nF2[ch] >= -1) whi = hi;
-		}
-		r->n_iter += width;
 	}
+#undef MGB_WF_RG
+	r->n_iter = n_iter;
 	r->s = s;
 	{
 		int rc = 0;
