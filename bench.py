@@ -99,6 +99,24 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+def chain_traffic():
+    """DRAM bytes of one k_chain launch from the committed `ncu --set full` digest (profiles/r01_ncu_k_chain.txt), or None."""
+    try:
+        rd = wr = None
+        with open(os.path.join(REPO, "profiles", "r01_ncu_k_chain.txt")) as f:
+            for ln in f:
+                t = ln.rstrip("\n").split("\t")
+                if len(t) == 3 and t[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    v = float(t[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[t[2]]
+                    if t[0].startswith("dram__bytes_read"):
+                        rd = v
+                    else:
+                        wr = v
+        return rd + wr if rd is not None and wr is not None else None
+    except Exception:
+        return None
+
+
 def hbm_peak():
     try:
         with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
@@ -303,8 +321,10 @@ def main():
                              "mg_map_batch_total": host_timed[4] / a.steps, "gaf_text(second thread)": host_timed[5] / a.steps},
         "device_cycles_last_step": {k: int(st.prof[i]) for i, k in enumerate(capi.PROF_NAMES)},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "k_stage<1> (linear chaining: mg_lchain_dp/rmq + backtrack + compaction)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "roofline": {"kernel": "k_chain (linear chaining: mg_lchain_dp/rmq + backtrack + compaction)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": chain_traffic(), "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_chain launch on this workload, profiles/r01_ncu_k_chain.txt",
+                     "algorithmic_bytes_per_launch": chain_bytes, "launch_ms": t_chain_avg * 1e3, "peak_source": peak_src,
+                     "note": "the chaining kernel is bound by dependent-access latency and instruction issue, not by HBM bandwidth (DESIGN.md section 4)",
                      "bytes_model": "16 B x %d seeds in + 16 B x %d anchors out + 8 B x %d chains" % (st.n_seeds, st.n_anchors_out, st.n_chains_out)},
         "cpu_baseline": cpu,
         "clocks": sampler.summary(),
