@@ -63,6 +63,13 @@ MG_D inline uint32_t warp_ballot(int pred) { return __ballot_sync(0xffffffffu, p
 MG_D inline uint64_t warp_or_u64(uint64_t x) { for (int o = 16; o > 0; o >>= 1) x |= __shfl_xor_sync(0xffffffffu, x, o); return x; }
 MG_D inline uint64_t warp_and_u64(uint64_t x) { for (int o = 16; o > 0; o >>= 1) x &= __shfl_xor_sync(0xffffffffu, x, o); return x; }
 MG_D inline void lane_atomic_inc(int32_t *p) { atomicAdd(p, 1); }
+// maximum over this lane and the lanes below it
+MG_D inline uint64_t warp_incl_scan_max_u64(uint64_t x, int lane)
+{
+	for (int o = 1; o < 32; o <<= 1) { uint64_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o && y > x) x = y; }
+	return x;
+}
+MG_D inline uint64_t warp_shfl_up1_u64(uint64_t x) { return __shfl_up_sync(0xffffffffu, x, 1); } // value of the lane below (own value on lane 0)
 // sum over this lane and the lanes below it
 MG_D inline int32_t warp_incl_scan_i32(int32_t x, int lane)
 {
@@ -90,6 +97,8 @@ inline int32_t warp_sum_i32(int32_t x) { return x; }
 inline uint32_t warp_ballot(int pred) { return pred? 1u : 0u; }
 inline int32_t warp_excl_prefix_max_i32(int32_t, int) { return INT32_MIN; }
 inline int32_t warp_incl_scan_i32(int32_t x, int) { return x; }
+inline uint64_t warp_incl_scan_max_u64(uint64_t x, int) { return x; }
+inline uint64_t warp_shfl_up1_u64(uint64_t x) { return x; }
 inline uint64_t warp_or_u64(uint64_t x) { return x; }
 inline uint64_t warp_and_u64(uint64_t x) { return x; }
 inline void lane_atomic_inc(int32_t *p) { ++*p; }

@@ -38,9 +38,11 @@ static int64_t p_workers_per_sm = 32;
 static int64_t p_device = 0;
 static int64_t p_block_warps = 4;
 static int64_t p_host_threads = 0; // 0: min(16, hardware threads)
-static int64_t p_thread_mask = 0;
+static int64_t p_thread_mask = 0;      // bit s set: stage s runs one item per thread instead of one per warp (experiments)
 extern int p_slots; extern int64_t p_min_slot_reads;
-static int64_t p_slot_workers = 0;      // bit s set: stage s runs one item per thread instead of one per warp
+static int64_t p_slot_workers = 0;
+static int64_t p_big_len = 0;          // > 0: gaps with tl or ql at or above this go to a tier-3 launch on a second stream beside tiers 1/2
+                                       // (measured on B200 with 384: tier 3 -3 ms, tier 1 +7 ms from the shared SMs -- off)
 
 // launch shape per stage: warps per block and blocks per SM wanted (tunable for experiments: "sw<stage>", "mb<stage>")
 static int STAGE_MINB[10] = { 8, 8, 4, 8, 5, 8, 7, 4, 4, 4 };
@@ -58,6 +60,7 @@ extern "C" int mgb_set_param(const char *key, int64_t value)
 	else if (!strcmp(key, "thread_mask")) p_thread_mask = value;
 	else if (!strcmp(key, "slots")) p_slots = (int)value;
 	else if (!strcmp(key, "slot_workers")) p_slot_workers = value;
+	else if (!strcmp(key, "big_len")) p_big_len = value;
 	else if (!strcmp(key, "min_slot_reads")) p_min_slot_reads = value;
 	else if (!strncmp(key, "sw", 2) && key[2] >= '0' && key[2] <= '9' && !key[3] && value >= 1 && value <= 4) STAGE_WARPS[key[2] - '0'] = (int)value;
 	else if (!strncmp(key, "mb", 2) && key[2] >= '0' && key[2] <= '9' && !key[3] && value >= 1 && value <= 32) STAGE_MINB[key[2] - '0'] = (int)value;
@@ -332,6 +335,29 @@ __global__ void __launch_bounds__(1024) k_job_order(LaunchArgs L, int kind, cons
 	for (int i = tid; i < n; i += 1024) order[atomicAdd(&cnt[order_bin(order_key(L, kind, q, i))], 1u)] = i;
 }
 #endif
+// gaps that no on-chip tier can take (tl or ql >= big_len): listed up front, so that their tier-3 launch can run beside tiers 1/2
+#ifndef MGB_HOSTSIM
+__global__ void __launch_bounds__(1024) k_job_split(LaunchArgs L, int n, int32_t *bigq, unsigned int *n_big)
+{
+	for (int i = threadIdx.x; i < n; i += 1024) {
+		const WfaJob &J = L.c.jobs[L.job_start + i];
+		if (J.tl >= L.c.big_len || J.ql >= L.c.big_len) bigq[atomicAdd(n_big, 1u)] = (int32_t)(L.job_start + i);
+	}
+}
+#endif
+static void make_job_split(const LaunchArgs &L, int n, int32_t *bigq, unsigned int *n_big)
+{
+#ifndef MGB_HOSTSIM
+	k_job_split<<<1, 1024, 0, t_stream>>>(L, n, bigq, n_big);
+	CUDA_OK(cudaGetLastError());
+#else
+	for (int i = 0; i < n; ++i) {
+		const WfaJob &J = L.c.jobs[L.job_start + i];
+		if (J.tl >= L.c.big_len || J.ql >= L.c.big_len) bigq[(*n_big)++] = (int32_t)(L.job_start + i);
+	}
+#endif
+}
+
 static void make_job_order(const LaunchArgs &L, int kind, const int32_t *q, int n, int32_t *order)
 {
 #ifndef MGB_HOSTSIM
@@ -413,12 +439,12 @@ struct Model {
 	// the batch pipeline: a batch is cut into sub-batches, each driven by its own host thread on its own stream ("slot"),
 	// so that kernels, copies and host-side result assembly of different sub-batches overlap
 	struct Slot {
-		GrowBuf h_seq{true}, h_out{true}, h_small{true}, d_seq, d_meta, d_routs, d_small, d_jobq, d_order, d_pool[10];
-		Workers W;
+		GrowBuf h_seq{true}, h_out{true}, h_small{true}, d_seq, d_meta, d_routs, d_small, d_jobq, d_order, d_bigq, d_pool[10];
+		Workers W, W2; // W2: the few workers of the tier-3 launch that runs beside tiers 1/2
 		mgb_stats_t st;
 		double ev_first_ms, ev_last_ms; // first kernel start / last kernel end relative to the batch reference event
 #ifndef MGB_HOSTSIM
-		cudaStream_t stream;
+		cudaStream_t stream, stream2;
 		cudaEvent_t ev_first, ev_last;
 #endif
 		bool ready;
@@ -439,7 +465,9 @@ static void model_free(Model *M)
 	if (M->d_logf) dfree(M->d_logf);
 	for (int k = 0; k < Model::MAX_SLOTS; ++k) {
 		Model::Slot &sl = M->slots[k];
-		sl.h_seq.release(), sl.h_out.release(), sl.h_small.release(), sl.d_seq.release(), sl.d_meta.release(), sl.d_routs.release(), sl.d_small.release(), sl.d_jobq.release(), sl.d_order.release();
+		sl.h_seq.release(), sl.h_out.release(), sl.h_small.release(), sl.d_seq.release(), sl.d_meta.release(), sl.d_routs.release(), sl.d_small.release(), sl.d_jobq.release(), sl.d_order.release(), sl.d_bigq.release();
+		if (sl.W2.arena) dfree(sl.W2.arena);
+		if (sl.W2.peak) dfree(sl.W2.peak);
 		for (int i = 0; i < 10; ++i) sl.d_pool[i].release();
 		if (sl.W.arena) dfree(sl.W.arena);
 		if (sl.W.peak) dfree(sl.W.peak);
@@ -830,6 +858,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	char *dsm = (char*)(((uintptr_t)(d_list_buf + n_reads) + 255) & ~(uintptr_t)255);
 	unsigned int *d_next = (unsigned int*)dsm;
 	unsigned int *d_jobq_n = d_next + 4;
+	unsigned int *d_next2 = d_next + 8, *d_nbig = d_next + 9;
 	unsigned long long *d_prof = (unsigned long long*)(dsm + 64);
 	Pool *d_pools = (Pool*)(dsm + 64 + sizeof(unsigned long long) * PROF_N);
 	h2d(d_seq_off, seq_off, (size_t)n_reads * 16); // seq_off, seq_len and name_hash are contiguous on both sides
@@ -928,6 +957,36 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 				L.c.jobq[0] = q, L.c.jobq[1] = q + n_new;
 				unsigned int qn[2] = {0, 0};
 				h2d(d_jobq_n, qn, sizeof(qn));
+				// gaps too long for the on-chip tiers are known up front: their tier-3 launch goes to a second stream with its own few
+				// workers and runs beside tiers 1/2 (its time is set by the longest gap, which would otherwise be an idle tail)
+				bool side = false;
+				L.c.big_len = 0;
+				if (&W == &sl.W && p_big_len > 0) {
+					L.c.big_len = (int32_t)p_big_len;
+					int32_t *bigq = (int32_t*)sl.d_bigq.ensure(sizeof(int32_t) * 2 * (size_t)n_new);
+					unsigned int n_big = 0;
+					h2d(d_nbig, &n_big, sizeof(n_big));
+					make_job_split(L, n_new, bigq, d_nbig);
+					d2h(&n_big, d_nbig, sizeof(n_big));
+					if (n_big > 0) {
+						LaunchArgs L2 = L;
+						L2.c.jobq[1] = bigq, L2.c.next_read = d_next2, L2.n_work = (int32_t)n_big;
+						make_job_order(L2, 1, bigq, (int)n_big, bigq + n_new);
+						L2.rid_list = bigq + n_new;
+						dsync();
+#ifndef MGB_HOSTSIM
+						cudaStream_t main_stream = t_stream;
+						t_stream = sl.stream2;
+						launch_stage<7>(L2, sl.W2);
+						t_stream = main_stream;
+#else
+						launch_stage<7>(L2, sl.W2);
+#endif
+						side = true;
+						S.n_launches += 3;
+						if (timed) S.n_jobs_side = n_big;
+					}
+				}
 				{ if (timed) tm_k[4].start(); launch_stage<4>(L, W); if (timed) tm_k[4].stop(); }
 				d2h(qn, d_jobq_n, sizeof(qn));
 				S.n_launches += 1;
@@ -944,6 +1003,11 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 					S.n_launches += 2;
 				}
 				if (timed) S.n_jobs_mid = qn[0], S.n_jobs_big = qn[1];
+#ifndef MGB_HOSTSIM
+				if (side) CUDA_OK(cudaStreamSynchronize(sl.stream2));
+#endif
+				(void)side;
+				L.c.big_len = 0;
 			}
 			if (timed) tm_wfa.stop(), tm_fin.start();
 			jobs_done = n_jobs;
@@ -1042,12 +1106,14 @@ static void slot_prepare(Model *M, Model::Slot &sl, int n_workers)
 #ifndef MGB_HOSTSIM
 	if (!sl.ready) {
 		CUDA_OK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+		CUDA_OK(cudaStreamCreateWithFlags(&sl.stream2, cudaStreamNonBlocking));
 		CUDA_OK(cudaEventCreate(&sl.ev_first));
 		CUDA_OK(cudaEventCreate(&sl.ev_last));
 	}
 #endif
 	sl.ready = true;
 	ensure_workers(sl.W, n_workers, (uint64_t)p_arena_mb << 20);
+	ensure_workers(sl.W2, dev_sm_count() * 2, (uint64_t)p_arena_mb << 20);
 	(void)M;
 }
 
@@ -1137,7 +1203,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 		S.t_h2d_ms += T.t_h2d_ms, S.t_seed_ms += T.t_seed_ms, S.t_chain_ms += T.t_chain_ms, S.t_align_ms += T.t_align_ms, S.t_d2h_ms += T.t_d2h_ms;
 		S.t_wfa_ms += T.t_wfa_ms, S.t_finish_ms += T.t_finish_ms, S.t_pack_ms += T.t_pack_ms, S.t_asm_ms += T.t_asm_ms;
 		for (int i = 0; i < 10; ++i) S.t_kernel_ms[i] += T.t_kernel_ms[i];
-		S.n_jobs += T.n_jobs, S.n_jobs_mid += T.n_jobs_mid, S.n_jobs_big += T.n_jobs_big, S.n_reads += T.n_reads, S.n_bases += T.n_bases;
+		S.n_jobs += T.n_jobs, S.n_jobs_mid += T.n_jobs_mid, S.n_jobs_big += T.n_jobs_big, S.n_jobs_side += T.n_jobs_side, S.n_reads += T.n_reads, S.n_bases += T.n_bases;
 		S.n_seeds += T.n_seeds, S.n_anchors_out += T.n_anchors_out, S.n_chains_out += T.n_chains_out, S.n_minimizers += T.n_minimizers;
 		S.out_bytes += T.out_bytes, S.n_launches += T.n_launches, S.n_retry += T.n_retry;
 		if (T.arena_peak > S.arena_peak) S.arena_peak = T.arena_peak;

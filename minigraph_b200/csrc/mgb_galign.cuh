@@ -113,6 +113,7 @@ MG_HD inline int wfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int la
 	WfaJob *J = &c.jobs[job_idx];
 	const int32_t rid = J->rid, l0 = J->l0, l = J->l, tl = J->tl, ql = J->ql;
 	if (c.meta[rid].status < 0) return 0; // the read already failed elsewhere; it will be redone as a whole
+	if (tier < 3 && c.big_len > 0 && (tl >= c.big_len || ql >= c.big_len)) return 0; // taken by the concurrent tier-3 launch
 	if ((tier == 1 && (tl > WfTier1::MAXLEN_ || ql > WfTier1::MAXLEN_)) || (tier == 2 && (tl > WfTier2::MAXLEN_ || ql > WfTier2::MAXLEN_))) {
 		if (lane == 0) {
 			unsigned int at;

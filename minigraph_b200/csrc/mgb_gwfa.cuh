@@ -699,37 +699,67 @@ MG_HD inline int gwf_dedup_w(GwfShared *sh, int lane)
 {
 	GwfState &z = sh->z;
 	Arena &A = sh->A;
-	// forbidden intervals: fold the new ones in (lane 0; nothing changes when there are no new ones)
+	// forbidden intervals: fold the new ones in (nothing changes when there are no new ones)
+	const int64_t n_old = z.intv.n, n_new = z.tmp.n;
 	if (lane == 0) {
 		int rc = 0;
-		if (z.tmp.n > 0) {
+		if (n_new > 0) {
 			int64_t i;
-			for (i = 1; i < z.tmp.n; ++i) if (z.tmp.a[i-1].vd0 > z.tmp.a[i].vd0) break;
-			if (i < z.tmp.n) rc = radix_sort_exact(A, z.tmp.a, z.tmp.n, 8, KeyIntvVd0());
-			if (rc == 0) rc = avec_reserve(A, z.swap, z.intv.n);
-			if (rc == 0) {
-				for (i = 0; i < z.intv.n; ++i) z.swap.a[i] = z.intv.a[i];
-				z.swap.n = z.intv.n;
-				rc = avec_reserve(A, z.intv, z.intv.n + z.tmp.n);
-			}
-			if (rc == 0) {
-				int64_t x = 0, y = 0, k = 0;
-				const GwfIntv *b = z.swap.a, *c = z.tmp.a;
-				GwfIntv *o = z.intv.a;
-				while (x < z.swap.n && y < z.tmp.n) {
-					if (b[x].vd0 <= c[y].vd0) o[k++] = b[x++];
-					else o[k++] = c[y++];
-				}
-				while (x < z.swap.n) o[k++] = b[x++];
-				while (y < z.tmp.n) o[k++] = c[y++];
-				z.intv.n = gwf_intv_merge_adj(k, o);
-			}
+			for (i = 1; i < n_new; ++i) if (z.tmp.a[i-1].vd0 > z.tmp.a[i].vd0) break;
+			if (i < n_new) rc = radix_sort_exact(A, z.tmp.a, n_new, 8, KeyIntvVd0());
+			if (rc == 0) rc = avec_reserve(A, z.swap, n_old);
+			if (rc == 0) z.swap.n = n_old, rc = avec_reserve(A, z.intv, n_old + n_new);
 		}
 		if (rc == 0) rc = avec_reserve(A, z.ooo, z.B.n);
 		sh->rc = rc;
 	}
 	warp_sync();
 	if (sh->rc < 0) return sh->rc;
+	if (n_new > 0) {
+		GwfIntv *b = z.swap.a, *c = z.tmp.a, *o = z.intv.a;
+		for (int64_t i = lane; i < n_old; i += MGB_W) b[i] = o[i]; // o may have moved: avec_reserve copied the old content
+		warp_sync();
+		// stable merge of two sorted lists (the old one first on ties), every element finds its place by bisection
+		for (int64_t x = lane; x < n_old; x += MGB_W) {
+			const uint64_t key = b[x].vd0;
+			int64_t lo = 0, hi = n_new;
+			while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (c[mid].vd0 < key) lo = mid + 1; else hi = mid; }
+			o[x + lo] = b[x];
+		}
+		for (int64_t y = lane; y < n_new; y += MGB_W) {
+			const uint64_t key = c[y].vd0;
+			int64_t lo = 0, hi = n_old;
+			while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (b[mid].vd0 <= key) lo = mid + 1; else hi = mid; }
+			o[y + lo] = c[y];
+		}
+		warp_sync();
+		// gwf_intv_merge_adj: an interval opens a new run when it starts beyond everything seen so far
+		const int64_t n_m = n_old + n_new;
+		int64_t k = 0;
+		uint64_t carry = 0; // running maximum of vd1 over the elements of the earlier rounds
+		for (int64_t base = 0; base < n_m; base += MGB_W) {
+			const int64_t i = base + lane;
+			GwfIntv e;
+			e.vd0 = e.vd1 = 0;
+			if (i < n_m) e = o[i];
+			uint64_t pm = warp_incl_scan_max_u64(i < n_m? e.vd1 : 0, lane);
+			if (pm < carry) pm = carry;
+			uint64_t before = warp_shfl_up1_u64(pm);
+			if (lane == 0) before = carry;
+			const int head = i < n_m && (i == 0 || e.vd0 > before);
+			const uint32_t mh = warp_ballot(head);
+			if (head) {
+				const int64_t g = k + mask_rank(mh, lane);
+				o[g].vd0 = e.vd0;
+				if (g > 0) o[g - 1].vd1 = before;
+			}
+			k += mask_count(mh);
+			carry = warp_bcast_u64(pm, MGB_W - 1);
+			warp_sync();
+		}
+		if (lane == 0) o[k - 1].vd1 = carry, z.intv.n = k;
+		warp_sync();
+	}
 	GwfDiag *a = z.B.a;
 	const int32_t n_a = (int32_t)z.B.n;
 	// ---- gwf_diag_dedup: sort if needed ----

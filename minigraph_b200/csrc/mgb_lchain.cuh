@@ -126,6 +126,84 @@ MG_HD inline int chain_compact(Arena &A, int32_t n_u, uint64_t *u, int32_t n_v, 
 	return 0;
 }
 
+// chain_backtrack() + chain_compact() entered by all lanes of a warp: the end-point list, the sorts and the copies are
+// spread over the lanes, the peeling itself (a walk over p[] with the visit marks) stays on lane 0.  u_store receives
+// the chain descriptors; a[0..n_v) the chained anchors.
+MG_HD inline int chain_finish_w(Arena &A, int64_t n, const int32_t *f, const int32_t *p, int32_t *v, int32_t *t, int32_t min_cnt, int32_t min_sc,
+								int32_t max_drop, u128 *a, uint64_t *u_store, int32_t *n_u_, int32_t *n_v_, int lane)
+{
+	const uint64_t mark = A.top;
+	*n_u_ = *n_v_ = 0;
+	int32_t n_z = 0;
+	for (int64_t i = lane; i < n; i += MGB_W) n_z += f[i] >= min_sc;
+	n_z = warp_sum_i32(n_z);
+	if (n_z == 0) return 0;
+	uint64_t *u;
+	u128 *z;
+	MGB_ALLOC(A, u, uint64_t, n_z);
+	MGB_ALLOC(A, z, u128, n_z);
+	{
+		int32_t k = 0;
+		for (int64_t base = 0; base < n; base += MGB_W) {
+			const int64_t i = base + lane;
+			const int keep = i < n && f[i] >= min_sc;
+			const uint32_t m = warp_ballot(keep);
+			if (keep) { u128 e; e.x = (uint64_t)(int64_t)f[i], e.y = (uint64_t)i; z[k + mask_rank(m, lane)] = e; }
+			k += mask_count(m);
+		}
+	}
+	for (int64_t i = lane; i < n; i += MGB_W) t[i] = 0;
+	warp_sync();
+	MGB_TRY(radix_sort_128x_w(A, z, n_z, lane));
+	int32_t n_u = 0, n_v = 0;
+	if (lane == 0) { // reference: lchain.c:27-77
+		for (int64_t k = n_z - 1; k >= 0; --k) {
+			if (t[z[k].y] == 0) {
+				int64_t n_v0 = n_v, end_i, i;
+				int32_t sc;
+				end_i = chain_bk_end(max_drop, z, f, p, t, k);
+				for (i = (int64_t)z[k].y; i != end_i; i = p[i])
+					v[n_v++] = (int32_t)i, t[i] = 1;
+				sc = i < 0? (int32_t)z[k].x : (int32_t)z[k].x - f[i];
+				if (sc >= min_sc && n_v > n_v0 && n_v - n_v0 >= min_cnt)
+					u[n_u++] = (uint64_t)sc << 32 | (uint64_t)(n_v - n_v0);
+				else n_v = (int32_t)n_v0;
+			}
+		}
+	}
+	n_u = warp_bcast_i32(n_u, 0), n_v = warp_bcast_i32(n_v, 0);
+	warp_sync();
+	if (n_u > 0) { // reference: lchain.c:79-112 compact_a
+		u128 *b, *w;
+		int32_t *koff;
+		MGB_ALLOC(A, b, u128, n_v);
+		MGB_ALLOC(A, w, u128, n_u);
+		MGB_ALLOC(A, koff, int32_t, n_u + 1);
+		if (lane == 0) { int32_t k = 0; for (int32_t i = 0; i < n_u; ++i) koff[i] = k, k += (int32_t)u[i]; koff[n_u] = k; }
+		warp_sync();
+		for (int32_t i = 0; i < n_u; ++i) {
+			const int32_t k0 = koff[i], ni = (int32_t)u[i];
+			for (int32_t j = lane; j < ni; j += MGB_W) b[k0 + j] = a[v[k0 + (ni - j - 1)]];
+		}
+		warp_sync();
+		for (int32_t i = lane; i < n_u; i += MGB_W) w[i].x = b[koff[i]].x, w[i].y = (uint64_t)koff[i] << 32 | (uint64_t)i;
+		warp_sync();
+		MGB_TRY(radix_sort_128x_w(A, w, n_u, lane));
+		int32_t k = 0;
+		for (int32_t i = 0; i < n_u; ++i) {
+			const int32_t j2 = (int32_t)w[i].y, cnt = (int32_t)u[j2];
+			const u128 *src = &b[w[i].y >> 32];
+			for (int32_t x = lane; x < cnt; x += MGB_W) a[k + x] = src[x];
+			if (lane == 0) u_store[i] = u[j2];
+			k += cnt;
+		}
+		warp_sync();
+	}
+	A.top = mark;
+	*n_u_ = n_u, *n_v_ = n_v;
+	return 0;
+}
+
 // Banded chaining DP (reference: lchain.c:149-219).  On return a[0..*n_a_) holds the chained anchors
 // and u[0..n_u) = score<<32|cnt per chain (u lives in the arena above the caller's mark).
 MG_HD inline int chain_dp(Arena &A, int max_dist_x, int max_dist_y, int bw, int max_skip, int max_iter, int min_cnt, int min_sc,
@@ -272,21 +350,8 @@ MG_HD inline int chain_dp_w(Arena &A, int max_dist_x, int max_dist_y, int bw, in
 		if (lane == 0) f[i] = max_f, p[i] = (int32_t)max_j, v[i] = vi;
 		warp_sync();
 	}
-	// backtrack and compaction on one lane; u[] ends up in the block reserved at the caller's top
-	int rc = 0, n_u = 0, n_v = 0;
-	if (lane == 0) {
-		Arena B = A;
-		uint64_t *u;
-		rc = chain_backtrack(B, n, f, p, v, t, min_cnt, min_sc, max_drop, 0, &u, &n_u, &n_v);
-		if (rc == 0 && n_u > 0) {
-			rc = chain_compact(B, n_u, u, n_v, v, a);
-			for (i = 0; i < n_u; ++i) u_store[i] = u[i];
-		}
-		if (B.peak > A.peak) A.peak = B.peak;
-	}
-	rc = warp_bcast_i32(rc, 0), n_u = warp_bcast_i32(n_u, 0), n_v = warp_bcast_i32(n_v, 0);
-	warp_sync();
-	if (rc < 0) return rc;
+	int32_t n_u = 0, n_v = 0;
+	MGB_TRY(chain_finish_w(A, n, f, p, v, t, min_cnt, min_sc, max_drop, a, u_store, &n_u, &n_v, lane));
 	A.top = mark;
 	*u_ = u_store, *n_u_ = n_u, *n_a_ = n_u > 0? n_v : 0;
 	return 0;
@@ -594,21 +659,18 @@ MG_HD inline int chain_rmq_w(Arena &A, int max_dist, int max_dist_inner, int bw,
 	int rc = n <= cap_rmq_size? chain_rmq_fill_w(A, max_dist, max_dist_inner, bw, max_chn_skip, pen_gap, pen_skip, n, a, f, p, t, v, lane) : 1;
 	if (rc < 0) return rc;
 	int32_t n_u = 0, n_v = 0;
-	int rc2 = 0;
-	if (lane <= 0) { // sequential tail on one lane
-		Arena B = A;
-		if (rc == 1) rc2 = chain_rmq_fill_seq(B, max_dist, max_dist_inner, bw, max_chn_skip, cap_rmq_size, pen_gap, pen_skip, n, a, f, p, t, v);
-		uint64_t *u = 0;
-		if (rc2 == 0) rc2 = chain_backtrack(B, n, f, p, v, t, min_cnt, min_sc, max_drop, 0, &u, &n_u, &n_v);
-		if (rc2 == 0 && n_u > 0) {
-			rc2 = chain_compact(B, n_u, u, n_v, v, a);
-			for (int64_t i = 0; i < n_u; ++i) u_store[i] = u[i];
+	if (rc == 1) { // too many anchors for the cooperative fill: sequential replay on one lane
+		int rc2 = 0;
+		if (lane == 0) {
+			Arena B = A;
+			rc2 = chain_rmq_fill_seq(B, max_dist, max_dist_inner, bw, max_chn_skip, cap_rmq_size, pen_gap, pen_skip, n, a, f, p, t, v);
+			if (B.peak > A.peak) A.peak = B.peak;
 		}
-		if (B.peak > A.peak) A.peak = B.peak;
+		rc2 = warp_bcast_i32(rc2, 0);
+		warp_sync();
+		if (rc2 < 0) return rc2;
 	}
-	rc2 = warp_bcast_i32(rc2, 0), n_u = warp_bcast_i32(n_u, 0), n_v = warp_bcast_i32(n_v, 0);
-	warp_sync();
-	if (rc2 < 0) return rc2;
+	MGB_TRY(chain_finish_w(A, n, f, p, v, t, min_cnt, min_sc, max_drop, a, u_store, &n_u, &n_v, lane));
 	A.top = mark;
 	*u_ = u_store, *n_u_ = n_u, *n_a_ = n_u > 0? n_v : 0;
 	return 0;

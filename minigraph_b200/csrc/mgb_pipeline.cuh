@@ -24,6 +24,7 @@ struct PipeCtx {
 	Pool *pool_jobs;       struct WfaJob *jobs;  // gap alignment jobs
 	Pool *pool_cig;        uint32_t *cig;        // per-job CIGARs
 	int32_t *jobq[2];      unsigned int *jobq_n;   // jobs handed to WFA tier 2 / tier 3
+	int32_t big_len;       // > 0: gaps with tl or ql >= big_len are not touched by tiers 1/2 (a tier-3 launch on a second stream has them)
 	Pool *pool_gstate;     char *gstate;         // per-read state between the two graph-chaining passes
 	Pool *pool_gjobs;      struct GwfaJob *gjobs; // bridging alignment jobs (K7a)
 	Pool *pool_walk;       int32_t *walk;        // walks found by the bridging jobs
