@@ -184,7 +184,7 @@ template<int STAGE>
 MG_HD inline int run_stage(const LaunchArgs &L, int item, Arena &A, int lane, int32_t *smem)
 {
 	if (STAGE == 0) return stage_seed(L.c, item, A, lane);
-	if (STAGE == 1) return stage_chain(L.c, item, A, lane);
+	if (STAGE == 1) return stage_chain(L.c, item, A, lane, smem);
 	if (STAGE == 2) return stage_gchain(L.c, L.routs, item, A);
 	if (STAGE == 5) return stage_finish(L.c, L.routs, item, A, lane);
 	if (STAGE == 8) return gwfa_job_run(A, L.c, L.job_start + item, lane, smem);
@@ -387,7 +387,7 @@ static void launch_stage(LaunchArgs &L, const Workers &W)
 #ifdef MGB_HOSTSIM
 	Arena A;
 	arena_init(A, W.arena, W.arena_bytes);
-	std::vector<int32_t> sim_smem(std::max<size_t>(std::max<size_t>(WfTier1::STRIDE, WfTier2::STRIDE), GWFA_SMEM_ARENA) / 4);
+	std::vector<int32_t> sim_smem(std::max<size_t>(std::max<size_t>(WfTier1::STRIDE, WfTier2::STRIDE), std::max<size_t>(GWFA_SMEM_ARENA, CHAIN_SMEM)) / 4);
 	for (int it = 0; it < L.n_work; ++it) {
 		int item = L.rid_list? L.rid_list[it] : it;
 		A.top = 0;

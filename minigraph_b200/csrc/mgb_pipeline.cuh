@@ -167,7 +167,11 @@ MG_HD inline int stage_chain_tail(const PipeCtx &c, ReadMeta &m, Arena &A, u128 
 // K4/K5 for one read: seeds -> linear chains.  Anchors are compacted in place; chains go to the lchain pool.
 // Warp-uniform: all lanes enter; the RMQ chaining is warp-cooperative, the rest runs on lane 0 and its few scalar
 // results are broadcast.
-MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A, int lane)
+// Shared memory for the DP state was tried (7 and 14 KiB per warp): the DP itself got ~25 % faster, but the smaller L1 and the
+// lower occupancy cost the rest of the kernel more (k_chain 11.0 -> 14.6 / 16.0 ms on B200), so the kernel asks for none.
+static const int CHAIN_SMEM = 7 * 1024;
+
+MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A, int lane, int32_t *smem = 0)
 {
 	ReadMeta &m = c.meta[rid];
 	const MapOptDev &o = c.opt;
@@ -196,7 +200,7 @@ MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A, int lane)
 								o.chn_pen_gap, o.chn_pen_skip, n_a, a, &n_lc, &u, &n_a_new, lane));
 		} else {
 			MGB_TRY(chain_dp_w(A, max_gap_ref, max_gap_qry, o.bw, o.max_lc_skip, o.max_lc_iter, o.min_lc_cnt, o.min_lc_score,
-							   o.chn_pen_gap, o.chn_pen_skip, is_splice, 1, n_a, a, &n_lc, &u, &n_a_new, lane));
+							   o.chn_pen_gap, o.chn_pen_skip, is_splice, 1, n_a, a, &n_lc, &u, &n_a_new, lane, smem, smem? CHAIN_SMEM : 0));
 		}
 	}
 	if (lane == 0) m.n_u0 = n_lc;
