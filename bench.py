@@ -36,6 +36,17 @@ N_READS, READ_LEN = 10000, 10000
 CPU_SAMPLE_READS = 3000
 
 
+def make_workload_c3(tmp, rank, n_reads, graph_len=5000000, n_hap=8, read_len=15000):
+    """synthetic MHC-scale rGFA (5 Mb backbone, 8 haplotypes with SVs, seed 7) and ONT-error reads (seed 5+rank)."""
+    prefix = os.path.join(tmp, "mhc")
+    if not os.path.exists(prefix + ".gfa"):
+        subprocess.run([MGSIM, "graph", "-l", str(graph_len), "-n", str(n_hap), "-s", "7", "-o", prefix], check=True, stderr=subprocess.DEVNULL)
+    reads = os.path.join(tmp, "mhc.reads.%d.fa" % rank)
+    subprocess.run([MGSIM, "reads", "-i", prefix + ".hap.fa", "-n", str(n_reads), "-l", str(read_len), "-e", "ont", "-s", str(5 + rank), "-o", reads],
+                   check=True, stderr=subprocess.DEVNULL)
+    return prefix + ".gfa", reads
+
+
 def make_workload(tmp, rank, n_reads=N_READS):
     hap = os.path.join(tmp, "mt.hap.fa")
     reads = os.path.join(tmp, "mt.reads.%d.fa" % rank)
@@ -133,6 +144,8 @@ def main():
     ap.add_argument("--impl", default="mgb200")
     ap.add_argument("--reads", type=int, default=N_READS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"], help="c2: test/MT.gfa <- 10 kb reads (the metric's configuration, default); c3: synthetic MHC-scale rGFA <- 15 kb reads")
+    ap.add_argument("--check", type=int, default=0, help="also compare the GAF text of the first N reads with the reference binary (oracle/_ref/minigraph), byte for byte")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -140,11 +153,13 @@ def main():
     tmp = tempfile.mkdtemp(prefix="mgb_bench_")
     ncores = os.cpu_count() or 1
     workload = "test/MT.gfa <- %d x %d bp synthetic ONT-error reads (4%% sub, 3%% del, 3%% ins; mgsim seed 11+rank), -cx lr -c" % (a.reads, READ_LEN)
+    if a.workload == "c3":
+        workload = "synthetic MHC-scale rGFA (5 Mb backbone, 8 haplotypes with SVs, mgsim seed 7) <- %d x 15000 bp ONT-error reads (seed 5+rank), -cx lr -c" % a.reads
 
     if a.impl == "reference":
         if rank != 0:
             return
-        gfa, fa = make_workload(tmp, 0, CPU_SAMPLE_READS)
+        gfa, fa = make_workload_c3(tmp, 0, CPU_SAMPLE_READS) if a.workload == "c3" else make_workload(tmp, 0, CPU_SAMPLE_READS)
         names, seqs = read_fasta(fa)
         bases = sum(len(s) for s in seqs)
         for _ in range(min(a.warmup, 1)):
@@ -177,7 +192,7 @@ def main():
     for kv in os.environ.get("MGB_PARAMS", "").split(","):
         if "=" in kv:
             lib.mgb_set_param(kv.split("=")[0].encode(), int(kv.split("=")[1], 0))
-    gfa, fa = make_workload(tmp, rank, a.reads)
+    gfa, fa = make_workload_c3(tmp, rank, a.reads) if a.workload == "c3" else make_workload(tmp, rank, a.reads)
     names, seqs = read_fasta(fa)
     n = len(seqs)
     bases = sum(len(s) for s in seqs)
@@ -286,6 +301,24 @@ def main():
             dist.destroy_process_group()
         return
 
+    check = None
+    if a.check > 0 and os.path.exists(REF_BIN):  # untimed: the first reads once more, GAF text against the reference binary
+        m = min(a.check, n)
+        cfa = os.path.join(tmp, "check.fa")
+        with open(cfa, "wb") as f:
+            for nm, sq in zip(names[:m], seqs[:m]):
+                f.write(b">" + nm + b"\n" + sq + b"\n")
+        want = subprocess.run([REF_BIN, "-cx", "lr", "-t", str(ncores), gfa, cfa], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+        gcs_c = (C.POINTER(capi.mg_gchains_t) * m)()
+        rc = lib.mg_map_batch(gi, m, qlens, cseqs, cnames, gcs_c, C.byref(mo))
+        assert rc == 0, lib.mgb_last_error()
+        buf, ln = C.c_void_p(0), C.c_size_t(0)
+        lib.mgb_write_gaf_batch(g, m, gcs_c, qlens, cnames, mo.flag, host_threads, C.byref(buf), C.byref(ln), None)
+        got = C.string_at(buf, ln.value)
+        C.CDLL(None).free(buf)
+        lib.mgb_free_batch(m, gcs_c)
+        check = {"reads": m, "gaf_bytes": len(want), "identical": got == want}
+
     peak, peak_src = hbm_peak()
     chain_bytes = 16.0 * st.n_seeds + 16.0 * st.n_anchors_out + 8.0 * st.n_chains_out
     t_chain_avg = stage[1] / a.steps / 1e3
@@ -326,7 +359,7 @@ def main():
                      "algorithmic_bytes_per_launch": chain_bytes, "launch_ms": t_chain_avg * 1e3, "peak_source": peak_src,
                      "note": "the chaining kernel is bound by dependent-access latency and instruction issue, not by HBM bandwidth (DESIGN.md section 4)",
                      "bytes_model": "16 B x %d seeds in + 16 B x %d anchors out + 8 B x %d chains" % (st.n_seeds, st.n_anchors_out, st.n_chains_out)},
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu, "parity_check": check,
         "clocks": sampler.summary(),
     }
     print(json.dumps(out))

@@ -291,16 +291,13 @@ MG_HD inline int ctz32(uint32_t x)
 #endif
 }
 
-MG_HD inline int nt4(uint8_t c) // reference: sketch.c:9-26 seq_nt4_table
+MG_HD inline int nt4(uint8_t c) // reference: sketch.c:9-26 seq_nt4_table (A/C/G/T/U in either case and the raw codes 0..3; 4 otherwise)
 {
-	switch (c) {
-	case 'A': case 'a': return 0;
-	case 'C': case 'c': return 1;
-	case 'G': case 'g': return 2;
-	case 'T': case 't': case 'U': case 'u': return 3;
-	case 0: return 0; case 1: return 1; case 2: return 2; case 3: return 3;
-	default: return 4;
-	}
+	const uint32_t idx = c & 0x1fu; // position in the alphabet for 0x40..0x7f
+	const uint64_t code = (1ULL << 2 * 3) | (2ULL << 2 * 7) | (3ULL << 2 * 20) | (3ULL << 2 * 21); // C, G, T, U (A is 0)
+	const uint32_t letters = (1u << 1) | (1u << 3) | (1u << 7) | (1u << 20) | (1u << 21);
+	if ((c & 0xc0u) == 0x40u && (letters >> idx & 1u)) return (int)(code >> 2 * idx & 3u);
+	return c < 4? (int)c : 4;
 }
 
 // ---- bit-exact emulation of klib's in-place MSD radix sort (reference: ksort.h:112-162) ----

@@ -164,22 +164,23 @@ MG_HD inline int sketch_seq_w(Arena &A, const char *str, int len, int w, int k, 
 		fail = warp_any(fail);
 		warp_sync();
 		if (!fail) {
-			int64_t tot = 0, my_off = 0;
+			int64_t tot = 0;
 			for (int c = 0; c < n_ch; ++c) tot += cnt[c];
-			// the result goes above the scratch; it is moved down to the mark afterwards so that the scratch can be released
-			u128 *res;
-			MGB_ALLOC(A, res, u128, tot + 16);
-			for (int c = 0; c < n_ch; ++c) {
-				if (c % MGB_W == lane) {
-					const u128 *src = tmp + (int64_t)c * cap;
-					for (int j = 0; j < cnt[c]; ++j) res[my_off + j] = src[j];
+			// the per-chunk lists are closed up in place (the first one already sits at the mark); a list only ever moves down
+			u128 *dst = tmp;
+			int64_t off = cnt[0];
+			for (int c = 1; c < n_ch; ++c) {
+				const u128 *src = tmp + (int64_t)c * cap;
+				for (int j0 = 0; j0 < cnt[c]; j0 += MGB_W) {
+					const int j = j0 + lane;
+					u128 e = {0, 0};
+					if (j < cnt[c]) e = src[j];
+					warp_sync();
+					if (j < cnt[c]) dst[off + j] = e;
+					warp_sync();
 				}
-				my_off += cnt[c];
+				off += cnt[c];
 			}
-			warp_sync();
-			u128 *dst = (u128*)(A.base + mark);
-			for (int64_t j = lane; j < tot; j += MGB_W) dst[j] = res[j]; // dst lies inside the consumed per-chunk lists, below res
-			warp_sync();
 			A.top = mark + ((((uint64_t)tot + 16) * sizeof(u128) + 15) & ~(uint64_t)15);
 			if (A.top > A.peak) A.peak = A.top;
 			out.a = dst, out.n = tot, out.m = tot + 16;
