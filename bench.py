@@ -147,6 +147,10 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3"], help="c2: test/MT.gfa <- 10 kb reads (the metric's configuration, default); c3: synthetic MHC-scale rGFA <- 15 kb reads")
     ap.add_argument("--check", type=int, default=0, help="also compare the GAF text of the first N reads with the reference binary (oracle/_ref/minigraph), byte for byte")
     a = ap.parse_args()
+    # stdout carries exactly one JSON line: everything libraries print to fd 1 (NCCL's version banner, ...) goes to stderr instead
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -168,13 +172,14 @@ def main():
         t = sum(ts) / len(ts)
         v = bases / t / 1e9
         sample = "%d of the %d reads (%.1f Mbp), mapping phase of `minigraph -cx lr -t %d`" % (CPU_SAMPLE_READS, a.reads, bases / 1e6, ncores)
-        print(json.dumps({
+        json_out.write(json.dumps({
             "impl": "reference", "metric": "mapped Gbp/s (-cx lr)", "value": v, "unit": "Gbp/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/u8 (fp32 chain penalties)",
             "data": "synthetic", "config": {"workload": workload, "sample": sample},
             "cpu_baseline": {"value": v, "unit": "Gbp/s", "cores": ncores, "kind": "reference", "sample": sample},
             "e2e": {"value": v, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }))
+        }) + "\n")
+        json_out.flush()
         return
 
     import torch
@@ -182,7 +187,7 @@ def main():
     from minigraph_b200 import capi, options
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there otherwise)
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = capi.load_product()
     lib.mgb_set_param(b"device", local_rank)
@@ -362,7 +367,8 @@ def main():
         "cpu_baseline": cpu, "parity_check": check,
         "clocks": sampler.summary(),
     }
-    print(json.dumps(out))
+    json_out.write(json.dumps(out) + "\n")
+    json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 

@@ -45,7 +45,7 @@ static int64_t p_big_len = 0;          // > 0: gaps with tl or ql at or above th
                                        // (measured on B200 with 384: tier 3 -3 ms, tier 1 +7 ms from the shared SMs -- off)
 
 // launch shape per stage: warps per block and blocks per SM wanted (tunable for experiments: "sw<stage>", "mb<stage>")
-static int STAGE_MINB[10] = { 8, 8, 4, 8, 5, 8, 7, 4, 4, 4 };
+static int STAGE_MINB[10] = { 8, 8, 8, 8, 5, 8, 7, 4, 4, 4 };
 static int STAGE_WARPS[10] = { 4, 4, 4, 4, 4, 4, 2, 4, 4, 4 };
 extern "C" const char *mgb_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char *mgb_version(void) { return "mgb200-r1"; }
@@ -284,7 +284,7 @@ __device__ __forceinline__ void stage_loop_thread(const LaunchArgs &L)
 #define MGB_KERNEL(name, STAGE, MINB) __global__ void __launch_bounds__(128, MINB) name(LaunchArgs L) { if (L.thread_mode) stage_loop_thread<STAGE>(L); else stage_loop<STAGE>(L); }
 MGB_KERNEL(k_seed, 0, 8)          // K1-K3: sketch, index lookup, seed sort
 MGB_KERNEL(k_chain, 1, 8)         // K4/K5: linear chaining
-MGB_KERNEL(k_gchain, 2, 4)        // K6: graph chaining DP + k-shortest walks, overlap resolution, bridging plan
+MGB_KERNEL(k_gchain, 2, 8)        // K6: graph chaining DP + k-shortest walks, overlap resolution, bridging plan
 MGB_KERNEL(k_gwfa, 8, 4)          // K7a: bridging alignments (graph wavefront), one warp per bridge
 MGB_KERNEL(k_gchain_gen, 9, 4)    // K7b: graph-chain materialisation, post filters, mapq, alignment plan
 MGB_KERNEL(k_index_sketch, 3, 8)  // index build: sketch of graph segments
@@ -314,10 +314,12 @@ MG_HD inline int order_bin(uint32_t key)
 	int b = (int)(lz * 4 + (lz >= 2? ((x >> (lz - 2)) & 3) : 0));
 	return 63 - (b > 63? 63 : b);
 }
-// kind 0: bridging jobs [job_start, job_start+n), key = query length; kind 1: alignment jobs listed in q[0..n), key = tl + ql
+// kind 0: bridging jobs [job_start, job_start+n), key = query length; kind 1: alignment jobs listed in q[0..n), key = tl + ql;
+// kind 2: reads 0..n-1, key = number of linear chains
 MG_HD inline uint32_t order_key(const LaunchArgs &L, int kind, const int32_t *q, int i)
 {
 	if (kind == 0) return (uint32_t)L.c.gjobs[L.job_start + i].ql;
+	if (kind == 2) return (uint32_t)L.c.meta[i].n_lc; // reads by their number of linear chains (graph chaining is roughly quadratic in it)
 	const WfaJob &J = L.c.jobs[q[i]];
 	return (uint32_t)(J.tl + J.ql);
 }
@@ -924,7 +926,16 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 			if (timed) tm_seed.stop(), tm_chain.start();
 			{ if (timed) tm_k[1].start(); launch_stage<1>(L, W); if (timed) tm_k[1].stop(); }
 			if (timed) tm_chain.stop(), tm_align.start();
-			{ if (timed) tm_k[2].start(); launch_stage<2>(L, W); if (timed) tm_k[2].stop(); }
+			if (d_list == 0 && n_list >= 1024) { // whole batch: reads with many linear chains first (a few of them set the time of this kernel)
+				int32_t *order = (int32_t*)sl.d_order.ensure(sizeof(int32_t) * (size_t)n_list);
+				if (timed) tm_k[2].start();
+				make_job_order(L, 2, 0, n_list, order);
+				L.rid_list = order;
+				launch_stage<2>(L, W);
+				L.rid_list = d_list;
+				if (timed) tm_k[2].stop();
+				S.n_launches += 1;
+			} else { if (timed) tm_k[2].start(); launch_stage<2>(L, W); if (timed) tm_k[2].stop(); }
 			{ // bridging jobs planned by k_gchain, then materialisation
 				Pool pg;
 				d2h(&pg, &d_pools[P_GJOBS], sizeof(Pool));
@@ -1207,7 +1218,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 		S.n_seeds += T.n_seeds, S.n_anchors_out += T.n_anchors_out, S.n_chains_out += T.n_chains_out, S.n_minimizers += T.n_minimizers;
 		S.out_bytes += T.out_bytes, S.n_launches += T.n_launches, S.n_retry += T.n_retry;
 		if (T.arena_peak > S.arena_peak) S.arena_peak = T.arena_peak;
-		for (int i = 0; i < 32; ++i) { if (i == PROF_WFA_MAX_CYC || i == PROF_GWFA_MAX_CYC) { if (T.prof[i] > S.prof[i]) S.prof[i] = T.prof[i]; } else S.prof[i] += T.prof[i]; }
+		for (int i = 0; i < 32; ++i) { if (i == PROF_WFA_MAX_CYC || i == PROF_GWFA_MAX_CYC || i == PROF_GC_DP_MAX_CYC) { if (T.prof[i] > S.prof[i]) S.prof[i] = T.prof[i]; } else S.prof[i] += T.prof[i]; }
 #ifndef MGB_HOSTSIM
 		float a = 0, b = 0;
 		cudaEventElapsedTime(&a, ev_ref, M->slots[k].ev_first);

@@ -448,7 +448,7 @@ MG_HD inline int stage_gchain(const PipeCtx &c, ReadOut *routs, int rid, Arena &
 	for (int32_t i = 0; i < n_lc; ++i) lc[i] = c.lchain[m.lc_off + i];
 	unsigned long long pt0 = prof_clock();
 	MGB_TRY(gchain1_dp(A, c.g, &n_lc, lc, qlen, o.bw_long, o.bw_long, o.bw_long, o.max_gc_skip, o.ref_bonus, o.chn_pen_gap, o.mask_level, a, &u, &n_u));
-	prof_add(c, PROF_GC_DP_CYC, prof_clock() - pt0);
+	{ unsigned long long dt = prof_clock() - pt0; prof_add(c, PROF_GC_DP_CYC, dt); prof_max(c, PROF_GC_DP_MAX_CYC, dt); }
 	// a read's jobs must be contiguous in the pool (they are consumed in order): reserve the worst case, one job per
 	// linear chain, up front and mark the unused slots
 	int64_t job_first;
