@@ -39,62 +39,68 @@ struct SpNode {
 struct SpTopK {
 	uint32_t v;
 	int32_t k;
-	int32_t p[MAX_SHORT_K]; // max-heap of node indices by di
+	int32_t p[MAX_SHORT_K];  // max-heap of node indices by di ...
+	uint64_t d[MAX_SHORT_K]; // ... with the keys beside them (a comparison then stays inside this record)
 };
+
+struct SpHeapEnt { uint64_t di; int32_t node, pad; }; // frontier entry: the key travels with the node index
 
 struct SpState {
 	AVec<SpNode> nd;
-	AVec<int32_t> heap;     // frontier: min-heap of node indices by di
+	AVec<SpHeapEnt> heap;   // frontier: min-heap by di (keys are unique, so any exact heap pops in the reference's order)
 	AVec<SpTopK> topk;
 	int32_t *htab;          // vertex -> index into topk (open addressing), -1 empty
 	int32_t htab_bits;
 };
 
-MG_HD inline void sp_heap_swap(SpState &S, int32_t i, int32_t j)
-{
-	int32_t a = S.heap.a[i], b = S.heap.a[j];
-	S.heap.a[i] = b, S.heap.a[j] = a;
-	S.nd.a[b].heap_pos = i, S.nd.a[a].heap_pos = j;
-}
+MG_HD inline void sp_heap_set(SpState &S, int32_t i, const SpHeapEnt &e) { S.heap.a[i] = e; S.nd.a[e.node].heap_pos = i; }
 MG_HD inline void sp_heap_up(SpState &S, int32_t i)
 {
+	const SpHeapEnt e = S.heap.a[i];
 	while (i > 0) {
-		int32_t par = (i - 1) >> 1;
-		if (S.nd.a[S.heap.a[par]].di <= S.nd.a[S.heap.a[i]].di) break;
-		sp_heap_swap(S, par, i);
+		const int32_t par = (i - 1) >> 1;
+		const SpHeapEnt pe = S.heap.a[par];
+		if (pe.di <= e.di) break;
+		sp_heap_set(S, i, pe);
 		i = par;
 	}
+	sp_heap_set(S, i, e);
 }
 MG_HD inline void sp_heap_down(SpState &S, int32_t i)
 {
-	int32_t n = (int32_t)S.heap.n;
+	const int32_t n = (int32_t)S.heap.n;
+	const SpHeapEnt e = S.heap.a[i];
 	for (;;) {
-		int32_t l = 2 * i + 1, r = l + 1, m = i;
-		if (l < n && S.nd.a[S.heap.a[l]].di < S.nd.a[S.heap.a[m]].di) m = l;
-		if (r < n && S.nd.a[S.heap.a[r]].di < S.nd.a[S.heap.a[m]].di) m = r;
-		if (m == i) break;
-		sp_heap_swap(S, m, i);
+		const int32_t l = 2 * i + 1, r = l + 1;
+		if (l >= n) break;
+		SpHeapEnt c = S.heap.a[l];
+		int32_t m = l;
+		if (r < n) { const SpHeapEnt cr = S.heap.a[r]; if (cr.di < c.di) c = cr, m = r; }
+		if (e.di <= c.di) break;
+		sp_heap_set(S, i, c);
 		i = m;
 	}
+	sp_heap_set(S, i, e);
 }
 MG_HD inline int sp_heap_push(Arena &A, SpState &S, int32_t node)
 {
-	MGB_TRY(avec_push(A, S.heap, node));
+	SpHeapEnt e;
+	e.di = S.nd.a[node].di, e.node = node, e.pad = 0;
+	MGB_TRY(avec_push(A, S.heap, e));
 	S.nd.a[node].heap_pos = (int32_t)S.heap.n - 1;
 	sp_heap_up(S, (int32_t)S.heap.n - 1);
 	return 0;
 }
 MG_HD inline void sp_heap_remove_at(SpState &S, int32_t pos)
 {
-	int32_t last = (int32_t)S.heap.n - 1;
-	int32_t node = S.heap.a[pos];
+	const int32_t last = (int32_t)S.heap.n - 1;
+	const int32_t node = S.heap.a[pos].node;
+	--S.heap.n;
 	if (pos != last) {
-		int32_t moved = S.heap.a[last];
-		sp_heap_swap(S, pos, last);
-		--S.heap.n;
+		sp_heap_set(S, pos, S.heap.a[last]);
 		sp_heap_up(S, pos);
-		sp_heap_down(S, S.nd.a[moved].heap_pos);
-	} else --S.heap.n;
+		sp_heap_down(S, S.nd.a[S.heap.a[last].node].heap_pos); // a[last] still holds the moved entry's node
+	}
 	S.nd.a[node].heap_pos = -1;
 }
 
@@ -126,26 +132,29 @@ MG_HD inline int sp_htab_get(Arena &A, SpState &S, uint32_t v, int *absent, int3
 	}
 }
 
-// per-vertex top-k max-heap on di (reference: ksort.h:42-65 ks_heapup/ks_heapdown with sp_node_lt)
-MG_HD inline void sp_topk_up(const SpState &S, int32_t n, int32_t *l)
+// per-vertex top-k max-heap on di (reference: ksort.h:42-65 ks_heapup/ks_heapdown with sp_node_lt); only its root, the
+// longest of the kept arrivals, is ever consulted, and keys are unique
+MG_HD inline void sp_topk_up(int32_t n, int32_t *l, uint64_t *d)
 {
 	int32_t k = n - 1, tmp = l[k];
+	const uint64_t td = d[k];
 	while (k) {
 		int32_t i = (k - 1) >> 1;
-		if (S.nd.a[tmp].di < S.nd.a[l[i]].di) break;
-		l[k] = l[i], k = i;
+		if (td < d[i]) break;
+		l[k] = l[i], d[k] = d[i], k = i;
 	}
-	l[k] = tmp;
+	l[k] = tmp, d[k] = td;
 }
-MG_HD inline void sp_topk_down(const SpState &S, int32_t i, int32_t n, int32_t *l)
+MG_HD inline void sp_topk_down(int32_t i, int32_t n, int32_t *l, uint64_t *d)
 {
 	int32_t k = i, tmp = l[i];
+	const uint64_t td = d[i];
 	while ((k = (k << 1) + 1) < n) {
-		if (k != n - 1 && S.nd.a[l[k]].di < S.nd.a[l[k+1]].di) ++k;
-		if (S.nd.a[l[k]].di < S.nd.a[tmp].di) break;
-		l[i] = l[k], i = k;
+		if (k != n - 1 && d[k] < d[k+1]) ++k;
+		if (d[k] < td) break;
+		l[i] = l[k], d[i] = d[k], i = k;
 	}
-	l[i] = tmp;
+	l[i] = tmp, d[i] = td;
 }
 
 // Returns 0 or an error code.  If pathv_/n_pathv_ are non-null the compacted backtrack array is produced in the
@@ -173,11 +182,15 @@ MG_HD inline int shortest_k(Arena &A, const GraphDev &g, uint32_t src, int32_t n
 
 	SpState S;
 	avec_init(S.nd), avec_init(S.heap), avec_init(S.topk);
-	S.htab_bits = 5;
+	MGB_TRY(avec_reserve(A, S.nd, 256)); // growth abandons the old block and copies: start where most searches end
+	MGB_TRY(avec_reserve(A, S.heap, 128));
+	MGB_TRY(avec_reserve(A, S.topk, 32));
+	S.htab_bits = 6;
 	MGB_ALLOC(A, S.htab, int32_t, 1 << S.htab_bits);
 	for (int i = 0; i < (1 << S.htab_bits); ++i) S.htab[i] = -1;
 	AVec<int32_t> out;
 	avec_init(out);
+	MGB_TRY(avec_reserve(A, out, 256));
 
 	uint32_t id = 0;
 	{
@@ -187,11 +200,11 @@ MG_HD inline int shortest_k(Arena &A, const GraphDev &g, uint32_t src, int32_t n
 		MGB_TRY(avec_push(A, S.nd, p));
 		MGB_TRY(sp_heap_push(A, S, 0));
 		MGB_TRY(sp_htab_get(A, S, src, &absent, &qi));
-		S.topk.a[qi].k = 1, S.topk.a[qi].p[0] = 0;
+		S.topk.a[qi].k = 1, S.topk.a[qi].p[0] = 0, S.topk.a[qi].d[0] = S.nd.a[0].di;
 	}
 	int32_t n_done = 0;
 	while (S.heap.n > 0) {
-		int32_t ri = S.heap.a[0];
+		int32_t ri = S.heap.a[0].node;
 		sp_heap_remove_at(S, 0);
 		int32_t n_out = (int32_t)out.n;
 		S.nd.a[ri].di = S.nd.a[ri].di >> 32 << 32 | (uint64_t)(uint32_t)n_out;
@@ -259,9 +272,9 @@ MG_HD inline int shortest_k(Arena &A, const GraphDev &g, uint32_t src, int32_t n
 				int32_t pi = (int32_t)S.nd.n - 1;
 				MGB_TRY(sp_heap_push(A, S, pi));
 				q = &S.topk.a[qi];
-				q->p[q->k++] = pi;
-				sp_topk_up(S, q->k, q->p);
-			} else if ((int64_t)(S.nd.a[q->p[0]].di >> 32) > (int64_t)d) {
+				q->p[q->k] = pi, q->d[q->k] = p.di, ++q->k;
+				sp_topk_up(q->k, q->p, q->d);
+			} else if ((int64_t)(q->d[0] >> 32) > (int64_t)d) {
 				int32_t pi = q->p[0];
 				if (S.nd.a[pi].heap_pos < 0) { A.top = mark; return MGB_E_INTERNAL; } // "logical bug" branch of the reference
 				sp_heap_remove_at(S, S.nd.a[pi].heap_pos);
@@ -272,7 +285,8 @@ MG_HD inline int shortest_k(Arena &A, const GraphDev &g, uint32_t src, int32_t n
 				p->is_0 = ris0;
 				if (ai->rank > 0) p->is_0 = 0;
 				MGB_TRY(sp_heap_push(A, S, pi));
-				sp_topk_down(S, 0, q->k, q->p);
+				q->d[0] = p->di;
+				sp_topk_down(0, q->k, q->p, q->d);
 			}
 		}
 	}
