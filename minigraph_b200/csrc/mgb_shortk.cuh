@@ -49,16 +49,17 @@ struct SpState {
 	AVec<SpNode> nd;
 	AVec<SpHeapEnt> heap;   // frontier: min-heap by di (keys are unique, so any exact heap pops in the reference's order)
 	AVec<SpTopK> topk;
-	int32_t *htab;          // vertex -> index into topk (open addressing), -1 empty
+	int64_t *htab;          // vertex -> index into topk (open addressing): vertex<<32 | index, -1 empty
 	int32_t htab_bits;
 };
 
 MG_HD inline void sp_heap_set(SpState &S, int32_t i, const SpHeapEnt &e) { S.heap.a[i] = e; S.nd.a[e.node].heap_pos = i; }
+// 4-ary heap: half the levels of a binary one, and the four children of a node are 64 contiguous bytes
 MG_HD inline void sp_heap_up(SpState &S, int32_t i)
 {
 	const SpHeapEnt e = S.heap.a[i];
 	while (i > 0) {
-		const int32_t par = (i - 1) >> 1;
+		const int32_t par = (i - 1) >> 2;
 		const SpHeapEnt pe = S.heap.a[par];
 		if (pe.di <= e.di) break;
 		sp_heap_set(S, i, pe);
@@ -71,11 +72,12 @@ MG_HD inline void sp_heap_down(SpState &S, int32_t i)
 	const int32_t n = (int32_t)S.heap.n;
 	const SpHeapEnt e = S.heap.a[i];
 	for (;;) {
-		const int32_t l = 2 * i + 1, r = l + 1;
-		if (l >= n) break;
-		SpHeapEnt c = S.heap.a[l];
-		int32_t m = l;
-		if (r < n) { const SpHeapEnt cr = S.heap.a[r]; if (cr.di < c.di) c = cr, m = r; }
+		const int32_t c0 = 4 * i + 1;
+		if (c0 >= n) break;
+		const int32_t nc = n - c0 < 4? n - c0 : 4;
+		SpHeapEnt c = S.heap.a[c0];
+		int32_t m = c0;
+		for (int32_t j = 1; j < nc; ++j) { const SpHeapEnt x = S.heap.a[c0 + j]; if (x.di < c.di) c = x, m = c0 + j; }
 		if (e.di <= c.di) break;
 		sp_heap_set(S, i, c);
 		i = m;
@@ -108,17 +110,19 @@ MG_HD inline int sp_htab_get(Arena &A, SpState &S, uint32_t v, int *absent, int3
 {
 	for (;;) {
 		uint32_t mask = (1u << S.htab_bits) - 1, h = hash32(v) & mask;
-		while (S.htab[h] >= 0 && S.topk.a[S.htab[h]].v != v) h = (h + 1) & mask;
-		if (S.htab[h] >= 0) { *absent = 0, *idx_ = S.htab[h]; return 0; }
+		int64_t e;
+		while ((e = S.htab[h]) >= 0 && (uint32_t)(e >> 32) != v) h = (h + 1) & mask;
+		if (e >= 0) { *absent = 0, *idx_ = (int32_t)e; return 0; }
 		if ((uint64_t)(S.topk.n + 1) * 2 > (1ULL << S.htab_bits)) { // grow and rehash
-			int32_t nb = S.htab_bits + 1, *nt;
-			MGB_ALLOC(A, nt, int32_t, 1LL << nb);
+			int32_t nb = S.htab_bits + 1;
+			int64_t *nt;
+			MGB_ALLOC(A, nt, int64_t, 1LL << nb);
 			uint32_t nmask = (1u << nb) - 1;
 			for (int64_t i = 0; i < (1LL << nb); ++i) nt[i] = -1;
 			for (int64_t i = 0; i < S.topk.n; ++i) {
 				uint32_t g = hash32(S.topk.a[i].v) & nmask;
 				while (nt[g] >= 0) g = (g + 1) & nmask;
-				nt[g] = (int32_t)i;
+				nt[g] = (int64_t)S.topk.a[i].v << 32 | i;
 			}
 			S.htab = nt, S.htab_bits = nb;
 			continue;
@@ -126,8 +130,8 @@ MG_HD inline int sp_htab_get(Arena &A, SpState &S, uint32_t v, int *absent, int3
 		SpTopK t;
 		t.v = v, t.k = 0;
 		MGB_TRY(avec_push(A, S.topk, t));
-		S.htab[h] = (int32_t)S.topk.n - 1;
-		*absent = 1, *idx_ = S.htab[h];
+		S.htab[h] = (int64_t)v << 32 | (S.topk.n - 1);
+		*absent = 1, *idx_ = (int32_t)S.topk.n - 1;
 		return 0;
 	}
 }
@@ -182,15 +186,15 @@ MG_HD inline int shortest_k(Arena &A, const GraphDev &g, uint32_t src, int32_t n
 
 	SpState S;
 	avec_init(S.nd), avec_init(S.heap), avec_init(S.topk);
-	MGB_TRY(avec_reserve(A, S.nd, 256)); // growth abandons the old block and copies: start where most searches end
-	MGB_TRY(avec_reserve(A, S.heap, 128));
-	MGB_TRY(avec_reserve(A, S.topk, 32));
-	S.htab_bits = 6;
-	MGB_ALLOC(A, S.htab, int32_t, 1 << S.htab_bits);
+	MGB_TRY(avec_reserve(A, S.nd, 1024)); // growth abandons the old block and copies: start where most searches end
+	MGB_TRY(avec_reserve(A, S.heap, 256));
+	MGB_TRY(avec_reserve(A, S.topk, 64));
+	S.htab_bits = 7;
+	MGB_ALLOC(A, S.htab, int64_t, 1 << S.htab_bits);
 	for (int i = 0; i < (1 << S.htab_bits); ++i) S.htab[i] = -1;
 	AVec<int32_t> out;
 	avec_init(out);
-	MGB_TRY(avec_reserve(A, out, 256));
+	MGB_TRY(avec_reserve(A, out, 1024));
 
 	uint32_t id = 0;
 	{
