@@ -128,12 +128,16 @@ def case_wfa_fallback(lib, n_cases=12, seed=5):
     n_fallback = 0
     for it in range(n_cases):
         n = rng.choice([300, 900, 2500])
+        if it == 0:
+            n = 9000  # tl + ql > 16000: beyond the 16-bit ring of tier 3, takes the 32-bit one
         t = "".join(rng.choice("ACGT") for _ in range(n))
-        blocks = [mutate(t[i:i + 200], rng.choice([0.02, 0.1, 0.3])) if rng.random() < 0.8 else "".join(rng.choice("ACGT") for _ in range(rng.choice([50, 300])))
+        blocks = [mutate(t[i:i + 200], rng.choice([0.02, 0.1, 0.3]) if it else 0.02) if rng.random() < 0.8 or it == 0 else "".join(rng.choice("ACGT") for _ in range(rng.choice([50, 300])))
                   for i in range(0, n, 200)]
         q = "".join(blocks)
         ts, qs = t.encode(), q.encode()
         max_iter, step = rng.choice([(2000, 40), (20000, 25), (50000, 100), (10 ** 8, 5000)])
+        if it == 0:
+            max_iter, step = 10 ** 8, 5000
         opt = mwf_opt_t()
         ref.mwf_opt_init(C.byref(opt))
         opt.flag |= 1
@@ -153,3 +157,21 @@ def case_wfa_fallback(lib, n_cases=12, seed=5):
         got = [buf[i] for i in range(nc)]
         assert got == want and score.value == rst.s, "case %d (tl=%d ql=%d max_iter=%d step=%d): score %d vs %d" % (it, len(ts), len(qs), max_iter, step, score.value, rst.s)
     assert n_fallback >= 3
+
+
+def case_switches(lib, workdir, device):
+    """the engine's experiment switches change the schedule, never the result: the same golden GAF with each of them on"""
+    settings = [{b"big_len": 384}]  # long gaps to a tier-3 launch of their own
+    if device:
+        settings += [{b"slots": 2, b"min_slot_reads": 8},          # two sub-batches on private streams
+                     {b"thread_mask": (1 << 2) | (1 << 9)},        # graph chaining stages: one read per thread
+                     {b"sw8": 1, b"mb8": 16, b"sw7": 1, b"mb7": 16}]  # one-warp blocks for the tail-bound job kernels
+    defaults = {b"big_len": 0, b"slots": 1, b"min_slot_reads": 512, b"thread_mask": 0, b"sw8": 4, b"mb8": 4, b"sw7": 4, b"mb7": 4}
+    for st in settings:
+        try:
+            for k, v in st.items():
+                assert lib.mgb_set_param(k, v) == 0
+            case_c3(lib, workdir)
+        finally:
+            for k in st:
+                lib.mgb_set_param(k, defaults[k])

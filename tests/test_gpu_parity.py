@@ -34,6 +34,10 @@ def test_edge_reads(lib, workdir):
     cases.case_edge(lib, workdir)
 
 
+def test_engine_switches_keep_results(lib, workdir):
+    cases.case_switches(lib, workdir, device=True)
+
+
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not shipped")
 def test_struct_fields_vs_reference(lib, workdir):
     cases.case_struct_random(lib, workdir, n_reads=400)
