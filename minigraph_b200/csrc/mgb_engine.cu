@@ -15,6 +15,7 @@
 #include <thread>
 #include <mutex>
 #include <functional>
+#include "mgb_hostpool.h"
 
 #include "../../include/mgb200.h"
 #include "mgb_galign.cuh"
@@ -41,6 +42,7 @@ static int64_t p_host_threads = 0; // 0: min(16, hardware threads)
 static int64_t p_thread_mask = 0;      // bit s set: stage s runs one item per thread instead of one per warp (experiments)
 extern int p_slots; extern int64_t p_min_slot_reads;
 static int64_t p_slot_workers = 0;
+static int64_t p_side_warps = 1;       // warps per SM of that side launch
 static int64_t p_big_len = 0;          // > 0: gaps with tl or ql at or above this go to a tier-3 launch on a second stream beside tiers 1/2
                                        // (measured on B200 with 384: tier 3 -3 ms, tier 1 +7 ms from the shared SMs -- off)
 
@@ -61,6 +63,7 @@ extern "C" int mgb_set_param(const char *key, int64_t value)
 	else if (!strcmp(key, "slots")) p_slots = (int)value;
 	else if (!strcmp(key, "slot_workers")) p_slot_workers = value;
 	else if (!strcmp(key, "big_len")) p_big_len = value;
+	else if (!strcmp(key, "side_warps")) p_side_warps = value;
 	else if (!strcmp(key, "min_slot_reads")) p_min_slot_reads = value;
 	else if (!strncmp(key, "sw", 2) && key[2] >= '0' && key[2] <= '9' && !key[3] && value >= 1 && value <= 4) STAGE_WARPS[key[2] - '0'] = (int)value;
 	else if (!strncmp(key, "mb", 2) && key[2] >= '0' && key[2] <= '9' && !key[3] && value >= 1 && value <= 32) STAGE_MINB[key[2] - '0'] = (int)value;
@@ -142,19 +145,14 @@ struct GrowBuf {
 };
 
 namespace {
+static mgb::HostPool g_host_pool; // packing, result assembly, index build (one caller at a time)
 template<typename F> void parallel_for(int64_t n, F fn)
 {
 	int nt = (int)p_host_threads;
 	if (nt <= 0) { nt = (int)std::thread::hardware_concurrency(); if (nt > 16) nt = 16; if (nt < 1) nt = 1; }
 	if (n < 64 || nt == 1) { for (int64_t i = 0; i < n; ++i) fn(i); return; }
-	std::vector<std::thread> th;
-	int64_t chunk = (n + nt - 1) / nt;
-	for (int t = 0; t < nt; ++t) {
-		int64_t b = t * chunk, e = std::min<int64_t>(n, b + chunk);
-		if (b >= e) break;
-		th.emplace_back([=]() { for (int64_t i = b; i < e; ++i) fn(i); });
-	}
-	for (auto &x : th) x.join();
+	const std::function<void(int64_t)> f = fn;
+	g_host_pool.run(n, nt, f);
 }
 }
 
@@ -381,7 +379,7 @@ struct Workers {
 };
 
 template<int STAGE>
-static void launch_stage(LaunchArgs &L, const Workers &W)
+static void launch_stage(LaunchArgs &L, const Workers &W, int warps_override = 0)
 {
 	L.arena_base = W.arena, L.arena_bytes = W.arena_bytes, L.arena_peak = W.peak;
 	unsigned int zero = 0;
@@ -398,8 +396,8 @@ static void launch_stage(LaunchArgs &L, const Workers &W)
 	}
 	if (W.peak && A.peak > W.peak[0]) W.peak[0] = A.peak;
 #else
-	const int warps = STAGE_WARPS[STAGE], threads = warps * 32;
-	int want = dev_sm_count() * STAGE_MINB[STAGE] * warps; // resident warps this stage can keep on the chip
+	const int warps = warps_override > 0? warps_override : STAGE_WARPS[STAGE], threads = warps * 32;
+	int want = dev_sm_count() * STAGE_MINB[STAGE] * STAGE_WARPS[STAGE]; // resident warps this stage can keep on the chip
 	int n_w = std::min(W.n_workers, want);
 	int blocks = std::max(1, n_w / warps);
 	size_t smem = STAGE == 4? (size_t)warps * WfTier1::STRIDE : STAGE == 6? (size_t)warps * WfTier2::STRIDE : STAGE == 8? (size_t)warps * GWFA_SMEM_ARENA : 0;
@@ -830,16 +828,8 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	const size_t hseq_bytes = tot + 16;
 	char *hseq = (char*)sl.h_seq.ensure(hseq_bytes);
 	auto pfor = [&](int64_t n, const std::function<void(int64_t)> &fn) {
-		int nt = host_threads;
-		if (n < 256 || nt <= 1) { for (int64_t i = 0; i < n; ++i) fn(i); return; }
-		std::vector<std::thread> th;
-		int64_t chunk = (n + nt - 1) / nt;
-		for (int t = 0; t < nt; ++t) {
-			int64_t b = t * chunk, e = std::min<int64_t>(n, b + chunk);
-			if (b >= e) break;
-			th.emplace_back([=, &fn]() { for (int64_t i = b; i < e; ++i) fn(i); });
-		}
-		for (auto &x : th) x.join();
+		if (n < 256 || host_threads <= 1 || p_slots > 1) { for (int64_t i = 0; i < n; ++i) fn(i); return; } // sub-batch threads do not share the pool
+		g_host_pool.run(n, host_threads, fn);
 	};
 	pfor(n_reads, [&](int64_t i) { if (qlens[i] > 0) memcpy(hseq + seq_off[i], seqs[i], (size_t)qlens[i]); });
 	S.t_pack_ms = now_ms() - t_host0;
@@ -988,7 +978,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 #ifndef MGB_HOSTSIM
 						cudaStream_t main_stream = t_stream;
 						t_stream = sl.stream2;
-						launch_stage<7>(L2, sl.W2);
+						launch_stage<7>(L2, sl.W2, 1); // one-warp blocks, one per SM: the long gaps ride along without taking much from tiers 1/2
 						t_stream = main_stream;
 #else
 						launch_stage<7>(L2, sl.W2);
@@ -1124,7 +1114,7 @@ static void slot_prepare(Model *M, Model::Slot &sl, int n_workers)
 #endif
 	sl.ready = true;
 	ensure_workers(sl.W, n_workers, (uint64_t)p_arena_mb << 20);
-	ensure_workers(sl.W2, dev_sm_count() * 2, (uint64_t)p_arena_mb << 20);
+	ensure_workers(sl.W2, dev_sm_count() * (int)p_side_warps, (uint64_t)p_arena_mb << 20);
 	(void)M;
 }
 

@@ -593,6 +593,7 @@ extern "C" void mgb_write_gaf(char **buf, size_t *len, size_t *cap, const gfa_t 
 #include <thread>
 #include <mutex>
 #include <functional>
+#include "mgb_hostpool.h"
 extern "C" void mgb_write_gaf_batch(const gfa_t *g, int n_reads, mg_gchains_t *const *gcs, const int *qlens, const char *const *names,
 									uint64_t flag, int n_threads, char **out, size_t *out_len, size_t *out_cap)
 {
@@ -604,11 +605,10 @@ extern "C" void mgb_write_gaf_batch(const gfa_t *g, int n_reads, mg_gchains_t *c
 	if (n_reads < 256) n_threads = 1;
 	if ((int)pool.size() < n_threads) pool.resize((size_t)n_threads, Part{0, 0, 0});
 	const int64_t chunk = ((int64_t)n_reads + n_threads - 1) / n_threads;
+	static mgb::HostPool workers; // the writer's own workers (the engine may be mapping the next batch on its pool meanwhile)
 	auto run = [&](const std::function<void(int)> &fn) {
 		if (n_threads == 1) { fn(0); return; }
-		std::vector<std::thread> th;
-		for (int t = 0; t < n_threads; ++t) th.emplace_back(fn, t);
-		for (auto &x : th) x.join();
+		workers.run(n_threads, n_threads, [&](int64_t t) { fn((int)t); });
 	};
 	run([&](int t) {
 		int64_t b = t * chunk, e = b + chunk < n_reads? b + chunk : n_reads;

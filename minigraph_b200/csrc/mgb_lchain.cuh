@@ -328,6 +328,11 @@ MG_HD inline int chain_dp_w(Arena &A, int max_dist_x, int max_dist_y, int bw, in
 			const uint32_t m_imp = warp_ballot(improves), m_mk = warp_ballot(marked && !improves);
 			uint32_t events = m_imp | m_mk;
 			int brk = -1;
+			if (m_mk == 0) { // only improvements in this chunk: the counter just drains
+				n_skip -= mask_count(m_imp);
+				if (n_skip < 0) n_skip = 0;
+				events = 0;
+			}
 			while (events) {
 				const int l = ctz32(events);
 				events &= events - 1;
