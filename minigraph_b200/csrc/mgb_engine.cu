@@ -371,6 +371,71 @@ static void make_job_order(const LaunchArgs &L, int kind, const int32_t *q, int 
 #endif
 }
 
+// ---- result blobs in read order ----
+// The kernels allocate a read's two result blobs from the output pool in completion order.  Before the copy to the host they are
+// closed up in read order, so that the copy can go in a few pieces and the host threads can build the mg_gchains_t of one piece
+// while the next one is still on the wire.
+struct PackArgs { ReadOut *routs; const ReadMeta *meta; int n; const char *pool; char *packed; uint64_t *off; };
+MG_HD inline uint64_t pack_size(const PackArgs &P, int r)
+{
+	const ReadOut &ro = P.routs[r];
+	if (P.meta[r].status != 0 || ro.status != 0 || ro.n_gc <= 0) return 0;
+	return (((uint64_t)ro.blob_size + 15) & ~(uint64_t)15) + (((uint64_t)ro.blob2_size + 15) & ~(uint64_t)15);
+}
+MG_HD inline void pack_read(const PackArgs &P, int r, int lane, int nl)
+{
+	ReadOut &ro = P.routs[r];
+	const uint64_t sz = P.off[r + 1] - P.off[r];
+	if (sz == 0) return;
+	const uint64_t n1 = ((uint64_t)ro.blob_size + 15) & ~(uint64_t)15, n2 = sz - n1;
+	const uint64_t *s1 = (const uint64_t*)(P.pool + ro.blob_off), *s2 = (const uint64_t*)(P.pool + ro.blob2_off);
+	uint64_t *d1 = (uint64_t*)(P.packed + P.off[r]), *d2 = d1 + n1 / 8;
+	for (uint64_t i = lane; i < n1 / 8; i += nl) d1[i] = s1[i];
+	for (uint64_t i = lane; i < n2 / 8; i += nl) d2[i] = s2[i];
+#if MGB_ON_DEVICE
+	__syncwarp();
+#endif
+	const int64_t delta = (int64_t)(P.off[r] + n1) - ro.blob2_off;
+	GChain *gc = (GChain*)d1;
+	for (int i = lane; i < ro.n_gc; i += nl)
+		if (gc[i].has_cigar) gc[i].cigar_off += delta, gc[i].ds_off += delta, gc[i].dsoff_off += delta;
+	if (lane == 0) ro.blob_off = (int64_t)P.off[r], ro.blob2_off = (int64_t)(P.off[r] + n1);
+}
+#ifndef MGB_HOSTSIM
+__global__ void __launch_bounds__(1024) k_out_scan(PackArgs P)
+{
+	__shared__ uint64_t part[1024];
+	const int tid = threadIdx.x, per = (P.n + 1023) / 1024;
+	const int r0 = tid * per < P.n? tid * per : P.n, r1 = r0 + per < P.n? r0 + per : P.n;
+	uint64_t sum = 0;
+	for (int r = r0; r < r1; ++r) sum += pack_size(P, r);
+	part[tid] = sum;
+	__syncthreads();
+	if (tid == 0) { uint64_t acc = 0; for (int i = 0; i < 1024; ++i) { uint64_t c = part[i]; part[i] = acc; acc += c; } P.off[P.n] = acc; }
+	__syncthreads();
+	uint64_t acc = part[tid];
+	for (int r = r0; r < r1; ++r) { P.off[r] = acc; acc += pack_size(P, r); }
+}
+__global__ void __launch_bounds__(256) k_out_pack(PackArgs P)
+{
+	const int lane = threadIdx.x & 31, warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), n_warp = (int)((gridDim.x * blockDim.x) >> 5);
+	for (int r = warp; r < P.n; r += n_warp) pack_read(P, r, lane, 32);
+}
+#endif
+static void pack_results(const PackArgs &P)
+{
+#ifndef MGB_HOSTSIM
+	k_out_scan<<<1, 1024, 0, t_stream>>>(P);
+	k_out_pack<<<dev_sm_count() * 8, 256, 0, t_stream>>>(P);
+	CUDA_OK(cudaGetLastError());
+#else
+	uint64_t acc = 0;
+	for (int r = 0; r < P.n; ++r) { P.off[r] = acc; acc += pack_size(P, r); }
+	P.off[P.n] = acc;
+	for (int r = 0; r < P.n; ++r) pack_read(P, r, 0, 1);
+#endif
+}
+
 struct Workers {
 	int n_workers;
 	uint64_t arena_bytes;
@@ -439,13 +504,13 @@ struct Model {
 	// the batch pipeline: a batch is cut into sub-batches, each driven by its own host thread on its own stream ("slot"),
 	// so that kernels, copies and host-side result assembly of different sub-batches overlap
 	struct Slot {
-		GrowBuf h_seq{true}, h_out{true}, h_small{true}, d_seq, d_meta, d_routs, d_small, d_jobq, d_order, d_bigq, d_pool[10];
+		GrowBuf h_seq{true}, h_out{true}, h_small{true}, d_seq, d_meta, d_routs, d_small, d_jobq, d_order, d_bigq, d_packed, d_packoff, d_pool[10];
 		Workers W, W2; // W2: the few workers of the tier-3 launch that runs beside tiers 1/2
 		mgb_stats_t st;
 		double ev_first_ms, ev_last_ms; // first kernel start / last kernel end relative to the batch reference event
 #ifndef MGB_HOSTSIM
 		cudaStream_t stream, stream2;
-		cudaEvent_t ev_first, ev_last;
+		cudaEvent_t ev_first, ev_last, ev_piece[4];
 #endif
 		bool ready;
 		Slot() : ready(false) { memset(&W, 0, sizeof(W)); }
@@ -465,7 +530,7 @@ static void model_free(Model *M)
 	if (M->d_logf) dfree(M->d_logf);
 	for (int k = 0; k < Model::MAX_SLOTS; ++k) {
 		Model::Slot &sl = M->slots[k];
-		sl.h_seq.release(), sl.h_out.release(), sl.h_small.release(), sl.d_seq.release(), sl.d_meta.release(), sl.d_routs.release(), sl.d_small.release(), sl.d_jobq.release(), sl.d_order.release(), sl.d_bigq.release();
+		sl.h_seq.release(), sl.h_out.release(), sl.h_small.release(), sl.d_seq.release(), sl.d_meta.release(), sl.d_routs.release(), sl.d_small.release(), sl.d_jobq.release(), sl.d_order.release(), sl.d_bigq.release(), sl.d_packed.release(), sl.d_packoff.release();
 		if (sl.W2.arena) dfree(sl.W2.arena);
 		if (sl.W2.peak) dfree(sl.W2.peak);
 		for (int i = 0; i < 10; ++i) sl.d_pool[i].release();
@@ -831,16 +896,31 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 		if (n < 256 || host_threads <= 1 || p_slots > 1) { for (int64_t i = 0; i < n; ++i) fn(i); return; } // sub-batch threads do not share the pool
 		g_host_pool.run(n, host_threads, fn);
 	};
-	pfor(n_reads, [&](int64_t i) { if (qlens[i] > 0) memcpy(hseq + seq_off[i], seqs[i], (size_t)qlens[i]); });
-	S.t_pack_ms = now_ms() - t_host0;
-
 	EvTimer tm_h2d, tm_seed, tm_chain, tm_align, tm_wfa, tm_fin, tm_d2h;
 	EvTimer tm_k[10]; // one per kernel (first pass only)
 	// ---- device buffers (all persistent: cudaMalloc/cudaFree would serialise the slots) ----
 	enum { P_ANCHOR, P_MINIPOS, P_LCHAIN, P_OUT, P_PLAN, P_JOBS, P_CIG, P_GSTATE, P_GJOBS, P_WALK, N_POOLS };
-	tm_h2d.start();
 	char *d_seq = (char*)sl.d_seq.ensure(hseq_bytes);
-	h2d(d_seq, hseq, hseq_bytes);
+	tm_h2d.start();
+	{ // pack and upload in a few pieces: the copy of one piece runs while the host threads pack the next
+		const int n_piece = n_reads >= 2048? 4 : 1;
+		double t_pack = 0;
+		for (int pc = 0; pc < n_piece; ++pc) {
+			const int64_t r0 = (int64_t)n_reads * pc / n_piece, r1 = (int64_t)n_reads * (pc + 1) / n_piece;
+			if (r0 >= r1) continue;
+			const double tp0 = now_ms();
+			pfor(r1 - r0, [&](int64_t i) { if (qlens[r0 + i] > 0) memcpy(hseq + seq_off[r0 + i], seqs[r0 + i], (size_t)qlens[r0 + i]); });
+			t_pack += now_ms() - tp0;
+			const uint64_t b0 = seq_off[r0], b1 = r1 < n_reads? seq_off[r1] : (uint64_t)hseq_bytes;
+#ifndef MGB_HOSTSIM
+			CUDA_OK(cudaMemcpyAsync(d_seq + b0, hseq + b0, b1 - b0, cudaMemcpyHostToDevice, t_stream));
+#else
+			memcpy(d_seq + b0, hseq + b0, b1 - b0);
+#endif
+		}
+		dsync();
+		S.t_pack_ms = t_pack;
+	}
 	size_t small_dev = (size_t)n_reads * (8 + 4 + 4 + 4) + 4096;
 	char *ds = (char*)sl.d_small.ensure(small_dev);
 	uint64_t *d_seq_off = (uint64_t*)ds;
@@ -875,7 +955,8 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	std::vector<ReadOut> routs(n_reads);
 	std::vector<ReadMeta> meta(n_reads);
 	char *hout = 0;
-	int rc_final = 0;
+	int rc_final = 0, n_piece = 1;
+	std::vector<uint64_t> pack_off;
 	bool first_kernel = true;
 	(void)first_kernel;
 
@@ -1051,11 +1132,29 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 		}
 		d2h(hp, d_pools, sizeof(hp));
 		bool done = !pool_full;
-		if (done) {
+		if (done) { // blobs into read order, then to the host in pieces (the assembly below follows piece by piece)
 			tm_d2h.start();
-			size_t out_bytes = (size_t)std::min<uint64_t>(hp[P_OUT].used, cap[P_OUT]);
-			hout = (char*)sl.h_out.ensure(out_bytes);
-			d2h(hout, d_buf[P_OUT], out_bytes);
+			const size_t pool_bytes = (size_t)std::min<uint64_t>(hp[P_OUT].used, cap[P_OUT]);
+			PackArgs P;
+			P.routs = d_routs, P.meta = d_meta, P.n = n_reads, P.pool = (const char*)d_buf[P_OUT];
+			P.packed = (char*)sl.d_packed.ensure(pool_bytes + 64), P.off = (uint64_t*)sl.d_packoff.ensure(sizeof(uint64_t) * ((size_t)n_reads + 1));
+			pack_results(P);
+			d2h(routs.data(), d_routs, sizeof(ReadOut) * (size_t)n_reads);
+			pack_off.resize((size_t)n_reads + 1);
+			d2h(pack_off.data(), P.off, sizeof(uint64_t) * ((size_t)n_reads + 1));
+			const size_t out_bytes = (size_t)pack_off[n_reads];
+			hout = (char*)sl.h_out.ensure(out_bytes + 64);
+			n_piece = n_reads >= 2048? 4 : 1;
+			for (int pc = 0; pc < n_piece; ++pc) {
+				const int64_t r0 = (int64_t)n_reads * pc / n_piece, r1 = (int64_t)n_reads * (pc + 1) / n_piece;
+				const uint64_t b0 = pack_off[r0], b1 = pack_off[r1];
+#ifndef MGB_HOSTSIM
+				if (b1 > b0) CUDA_OK(cudaMemcpyAsync(hout + b0, P.packed + b0, b1 - b0, cudaMemcpyDeviceToHost, t_stream));
+				CUDA_OK(cudaEventRecord(sl.ev_piece[pc], t_stream));
+#else
+				if (b1 > b0) memcpy(hout + b0, P.packed + b0, b1 - b0);
+#endif
+			}
 			tm_d2h.stop();
 			S.out_bytes = (int64_t)out_bytes;
 		}
@@ -1067,7 +1166,6 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	S.t_h2d_ms = tm_h2d.ms(), S.t_seed_ms = tm_seed.ms(), S.t_chain_ms = tm_chain.ms(), S.t_align_ms = tm_align.ms();
 	S.t_wfa_ms = tm_wfa.ms(), S.t_finish_ms = tm_fin.ms();
 	for (int i = 0; i < 10; ++i) S.t_kernel_ms[i] = tm_k[i].ms();
-	if (rc_final == 0) S.t_d2h_ms = tm_d2h.ms();
 	{
 		std::vector<uint64_t> peak(sl.W.n_workers);
 		d2h(peak.data(), sl.W.peak, sizeof(uint64_t) * peak.size());
@@ -1092,12 +1190,20 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 		set_error(buf);
 		return st;
 	}
-	pfor(n_reads, [&](int64_t i) {
-		int st = meta[i].status < 0? meta[i].status : routs[i].status;
-		if (st == 1) gcs[i] = 0; // empty or over-long read: reference returns before allocating (map-algo.c:359-360)
-		else gcs[i] = build_result(routs[i], hout);
-	});
+	for (int pc = 0; pc < n_piece; ++pc) {
+		const int64_t r0 = (int64_t)n_reads * pc / n_piece, r1 = (int64_t)n_reads * (pc + 1) / n_piece;
+#ifndef MGB_HOSTSIM
+		CUDA_OK(cudaEventSynchronize(sl.ev_piece[pc]));
+#endif
+		pfor(r1 - r0, [&](int64_t k) {
+			const int64_t i = r0 + k;
+			int st = meta[i].status < 0? meta[i].status : routs[i].status;
+			if (st == 1) gcs[i] = 0; // empty or over-long read: reference returns before allocating (map-algo.c:359-360)
+			else gcs[i] = build_result(routs[i], hout);
+		});
+	}
 	S.t_asm_ms = now_ms() - t_asm0;
+	S.t_d2h_ms = tm_d2h.ms(); // pack kernels + the pieces of the copy (they overlap the assembly above)
 	S.t_host_ms = now_ms() - t_host0;
 	return 0;
 }
@@ -1110,6 +1216,7 @@ static void slot_prepare(Model *M, Model::Slot &sl, int n_workers)
 		CUDA_OK(cudaStreamCreateWithFlags(&sl.stream2, cudaStreamNonBlocking));
 		CUDA_OK(cudaEventCreate(&sl.ev_first));
 		CUDA_OK(cudaEventCreate(&sl.ev_last));
+		for (int i = 0; i < 4; ++i) CUDA_OK(cudaEventCreateWithFlags(&sl.ev_piece[i], cudaEventDisableTiming));
 	}
 #endif
 	sl.ready = true;
