@@ -87,7 +87,7 @@ class gfa_t(C.Structure):  # gfa.h:89-101
 class mgb_stats_t(C.Structure):
     _fields_ = [("t_h2d_ms", C.c_double), ("t_seed_ms", C.c_double), ("t_chain_ms", C.c_double),
                 ("t_align_ms", C.c_double), ("t_d2h_ms", C.c_double), ("t_host_ms", C.c_double),
-                ("t_wfa_ms", C.c_double), ("t_finish_ms", C.c_double), ("t_dev_span_ms", C.c_double), ("n_jobs_side", C.c_int64), ("n_slots", C.c_int64), ("t_pack_ms", C.c_double), ("t_asm_ms", C.c_double),
+                ("t_wfa_ms", C.c_double), ("t_finish_ms", C.c_double), ("t_dev_span_ms", C.c_double), ("skip1_len", C.c_int64), ("skip2_len", C.c_int64), ("n_jobs_side", C.c_int64), ("n_slots", C.c_int64), ("t_pack_ms", C.c_double), ("t_asm_ms", C.c_double),
                 ("n_jobs", C.c_int64), ("n_jobs_mid", C.c_int64), ("n_jobs_big", C.c_int64),
                 ("n_reads", C.c_int64), ("n_bases", C.c_int64), ("n_seeds", C.c_int64), ("n_anchors_out", C.c_int64),
                 ("n_chains_out", C.c_int64), ("n_minimizers", C.c_int64), ("out_bytes", C.c_int64),

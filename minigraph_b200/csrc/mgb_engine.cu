@@ -42,6 +42,7 @@ static int64_t p_host_threads = 0; // 0: min(16, hardware threads)
 static int64_t p_thread_mask = 0;      // bit s set: stage s runs one item per thread instead of one per warp (experiments)
 extern int p_slots; extern int64_t p_min_slot_reads;
 static int64_t p_slot_workers = 0;
+static int64_t p_tier_learn = 1;       // 0: every gap tries every tier (no routing)
 static int64_t p_side_warps = 1;       // warps per SM of that side launch
 static int64_t p_big_len = 0;          // > 0: gaps with tl or ql at or above this go to a tier-3 launch on a second stream beside tiers 1/2
                                        // (measured on B200 with 384: tier 3 -3 ms, tier 1 +7 ms from the shared SMs -- off)
@@ -64,6 +65,7 @@ extern "C" int mgb_set_param(const char *key, int64_t value)
 	else if (!strcmp(key, "slot_workers")) p_slot_workers = value;
 	else if (!strcmp(key, "big_len")) p_big_len = value;
 	else if (!strcmp(key, "side_warps")) p_side_warps = value;
+	else if (!strcmp(key, "tier_learn")) p_tier_learn = value;
 	else if (!strcmp(key, "min_slot_reads")) p_min_slot_reads = value;
 	else if (!strncmp(key, "sw", 2) && key[2] >= '0' && key[2] <= '9' && !key[3] && value >= 1 && value <= 4) STAGE_WARPS[key[2] - '0'] = (int)value;
 	else if (!strncmp(key, "mb", 2) && key[2] >= '0' && key[2] <= '9' && !key[3] && value >= 1 && value <= 32) STAGE_MINB[key[2] - '0'] = (int)value;
@@ -498,6 +500,7 @@ struct Model {
 	std::vector<void*> dev_ptrs;
 	// per-model scratch reused across batches
 	Workers W, Wbig;
+	int32_t skip1_len = INT32_MAX, skip2_len = INT32_MAX; // WFA tier routing learned from earlier batches (wfa_job_run)
 	std::vector<float> logf_tab; float *d_logf; int n_logf;
 	mgb_stats_t stats;
 	gfa_edseq_t *es;
@@ -871,6 +874,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	memset(&S, 0, sizeof(S));
 	sl.ev_first_ms = sl.ev_last_ms = 0;
 	if (n_reads <= 0) return 0;
+	const int32_t L_skip1 = M->skip1_len, L_skip2 = M->skip2_len; // thresholds this batch runs with
 	const int64_t saved_threads = p_host_threads;
 	(void)saved_threads;
 	double t_host0 = now_ms();
@@ -921,7 +925,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 		dsync();
 		S.t_pack_ms = t_pack;
 	}
-	size_t small_dev = (size_t)n_reads * (8 + 4 + 4 + 4) + 4096;
+	size_t small_dev = (size_t)n_reads * (8 + 4 + 4 + 4) + 4096 + 1024;
 	char *ds = (char*)sl.d_small.ensure(small_dev);
 	uint64_t *d_seq_off = (uint64_t*)ds;
 	int32_t *d_seq_len = (int32_t*)(d_seq_off + n_reads);
@@ -933,6 +937,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	unsigned int *d_next2 = d_next + 8, *d_nbig = d_next + 9;
 	unsigned long long *d_prof = (unsigned long long*)(dsm + 64);
 	Pool *d_pools = (Pool*)(dsm + 64 + sizeof(unsigned long long) * PROF_N);
+	unsigned int *d_tier_hist = (unsigned int*)((char*)(d_pools + 16) + 64); // 32 x 4 counters behind the pool headers
 	h2d(d_seq_off, seq_off, (size_t)n_reads * 16); // seq_off, seq_len and name_hash are contiguous on both sides
 	tm_h2d.stop();
 	ReadMeta *d_meta = (ReadMeta*)sl.d_meta.ensure(sizeof(ReadMeta) * (size_t)n_reads);
@@ -940,6 +945,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	dzero(d_meta, sizeof(ReadMeta) * (size_t)n_reads);
 	dzero(d_routs, sizeof(ReadOut) * (size_t)n_reads);
 	dzero(d_prof, sizeof(unsigned long long) * PROF_N);
+	dzero(d_tier_hist, sizeof(unsigned int) * 128);
 	uint64_t cap[N_POOLS];
 	cap[P_ANCHOR] = std::max<uint64_t>((uint64_t)S.n_bases / 4 * sizeof(u128), (uint64_t)1 << 22);
 	cap[P_MINIPOS] = std::max<uint64_t>((uint64_t)S.n_bases * sizeof(int32_t) / 2, (uint64_t)1 << 20);
@@ -983,6 +989,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 		L.c.pool_walk = &d_pools[P_WALK], L.c.walk = (int32_t*)d_buf[P_WALK];
 		L.c.next_read = d_next;
 		L.c.prof = d_prof;
+		L.c.tier_hist = d_tier_hist, L.c.skip1_len = L_skip1, L.c.skip2_len = L_skip2;
 		L.c.jobq[0] = 0, L.c.jobq[1] = 0, L.c.jobq_n = d_jobq_n;
 		L.routs = d_routs;
 		int64_t jobs_done = 0, gjobs_done = 0;
@@ -1172,6 +1179,17 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 		for (uint64_t p : peak) if (p > S.arena_peak) S.arena_peak = p;
 	}
 	{ unsigned long long hp2[PROF_N]; d2h(hp2, d_prof, sizeof(hp2)); for (int i = 0; i < 32; ++i) S.prof[i] = (uint64_t)hp2[i]; }
+	{ // tier routing for the next batch: the first length bucket in which the sampled gaps mostly ended beyond a tier
+		unsigned int h[128];
+		d2h(h, d_tier_hist, sizeof(h));
+		int32_t t1 = INT32_MAX, t2 = INT32_MAX;
+		for (int b = 0; b < 32 && t1 == INT32_MAX; ++b) { unsigned int in = h[b * 4 + 1], out = h[b * 4 + 2] + h[b * 4 + 3]; if (in + out >= 8 && in < out) t1 = b * 16; }
+		for (int b = 0; b < 32 && t2 == INT32_MAX; ++b) { unsigned int in = h[b * 4 + 1] + h[b * 4 + 2], out = h[b * 4 + 3]; if (in + out >= 8 && in < out) t2 = b * 16; }
+		unsigned int tot = 0;
+		for (int i = 0; i < 128; ++i) tot += h[i];
+		if (tot >= 256 && p_tier_learn) { std::lock_guard<std::mutex> lock(M->big_mutex); M->skip1_len = t1, M->skip2_len = t2 < t1? t1 : t2; }
+		S.skip1_len = L_skip1, S.skip2_len = L_skip2;
+	}
 	if (rc_final < 0) return rc_final;
 
 	// ---- results ----
@@ -1311,7 +1329,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 		S.t_h2d_ms += T.t_h2d_ms, S.t_seed_ms += T.t_seed_ms, S.t_chain_ms += T.t_chain_ms, S.t_align_ms += T.t_align_ms, S.t_d2h_ms += T.t_d2h_ms;
 		S.t_wfa_ms += T.t_wfa_ms, S.t_finish_ms += T.t_finish_ms, S.t_pack_ms += T.t_pack_ms, S.t_asm_ms += T.t_asm_ms;
 		for (int i = 0; i < 10; ++i) S.t_kernel_ms[i] += T.t_kernel_ms[i];
-		S.n_jobs += T.n_jobs, S.n_jobs_mid += T.n_jobs_mid, S.n_jobs_big += T.n_jobs_big, S.n_jobs_side += T.n_jobs_side, S.n_reads += T.n_reads, S.n_bases += T.n_bases;
+		S.n_jobs += T.n_jobs, S.n_jobs_mid += T.n_jobs_mid, S.n_jobs_big += T.n_jobs_big, S.n_jobs_side += T.n_jobs_side, S.skip1_len = T.skip1_len, S.skip2_len = T.skip2_len, S.n_reads += T.n_reads, S.n_bases += T.n_bases;
 		S.n_seeds += T.n_seeds, S.n_anchors_out += T.n_anchors_out, S.n_chains_out += T.n_chains_out, S.n_minimizers += T.n_minimizers;
 		S.out_bytes += T.out_bytes, S.n_launches += T.n_launches, S.n_retry += T.n_retry;
 		if (T.arena_peak > S.arena_peak) S.arena_peak = T.arena_peak;

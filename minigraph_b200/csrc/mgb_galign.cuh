@@ -114,6 +114,24 @@ MG_HD inline int wfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int la
 	const int32_t rid = J->rid, l0 = J->l0, l = J->l, tl = J->tl, ql = J->ql;
 	if (c.meta[rid].status < 0) return 0; // the read already failed elsewhere; it will be redone as a whole
 	if (tier < 3 && c.big_len > 0 && (tl >= c.big_len || ql >= c.big_len)) return 0; // taken by the concurrent tier-3 launch
+	// Routing: a gap that cannot finish in an on-chip tier costs that tier up to a full window of cells before it gives up.
+	// Which lengths fail depends on the error rate of the reads, so it is learned: one gap in 16 tries every tier and
+	// reports where it finished; the host turns the counts of one batch into the two thresholds of the next.  The
+	// result of a gap does not depend on the tier that computes it.
+	const int32_t mlen = tl > ql? tl : ql;
+	const int explore = (job_idx & 15) == 0;
+	if (!explore && ((tier == 1 && mlen >= c.skip1_len) || (tier == 2 && mlen >= c.skip2_len))) {
+		if (lane == 0) {
+			unsigned int at;
+#if MGB_ON_DEVICE
+			at = atomicAdd(&c.jobq_n[tier - 1], 1u);
+#else
+			at = c.jobq_n[tier - 1]++;
+#endif
+			c.jobq[tier - 1][at] = (int32_t)job_idx;
+		}
+		return 0;
+	}
 	if ((tier == 1 && (tl > WfTier1::MAXLEN_ || ql > WfTier1::MAXLEN_)) || (tier == 2 && (tl > WfTier2::MAXLEN_ || ql > WfTier2::MAXLEN_))) {
 		if (lane == 0) {
 			unsigned int at;
@@ -163,6 +181,14 @@ MG_HD inline int wfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int la
 		prof_add(c, slot, dt), prof_add(c, slot + 1, 1);
 		prof_max(c, PROF_WFA_MAX_CYC, dt);
 		if (rc == 0) prof_add(c, PROF_WFA_CELLS, (unsigned long long)rst.n_iter);
+		if (rc == 0 && explore && c.tier_hist) {
+			unsigned int *h = &c.tier_hist[(mlen >> 4 < 31? mlen >> 4 : 31) * 4 + tier];
+#if MGB_ON_DEVICE
+			atomicAdd(h, 1u);
+#else
+			++*h;
+#endif
+		}
 	}
 	if (rc == 1) { // does not fit this tier
 		if (lane == 0) {

@@ -32,6 +32,9 @@ struct PipeCtx {
 	unsigned int *next_read;
 	// instrumentation: 32 counters, see PROF_* below
 	unsigned long long *prof;
+	// tier routing of the gap alignments, learned from the batches before (see wfa_job_run)
+	int32_t skip1_len, skip2_len; // gaps with max(tl,ql) at or above these go past tier 1 / tier 2 without trying them
+	unsigned int *tier_hist;      // [32 length buckets of 16 bases][4]: final tier of the gaps that tried every tier
 };
 
 enum { PROF_WFA_FAST_CYC = 0, PROF_WFA_FAST_N, PROF_WFA_SLOW_CYC, PROF_WFA_SLOW_N, PROF_WFA_MAX_CYC, PROF_WFA_CELLS, PROF_WFA_TB_CYC,

@@ -175,3 +175,34 @@ def case_switches(lib, workdir, device):
         finally:
             for k in st:
                 lib.mgb_set_param(k, defaults[k])
+
+
+def case_tier_routing(lib, workdir, n_reads=60):
+    """the WFA tier thresholds learned from one batch route the gaps of the next: same results, and the routing did engage"""
+    import ctypes as C
+    from minigraph_b200 import capi, options
+    hap, reads = os.path.join(workdir, "mt.hap.fa"), os.path.join(workdir, "mt.route.fa")
+    T.sim_mt_haps(hap)
+    T.sim_reads(hap, reads, n_reads, 10000, "ont", 29)
+    names, seqs = T.read_fasta(reads)
+    g = lib.mgb_gfa_read(os.path.join(T.FIX, "MT.gfa").encode())
+    io, mo = options.opt_set("lr", True)
+    gi = lib.mg_index(g, C.byref(io), 1, C.byref(mo))
+    assert gi, lib.mgb_last_error()
+    n = len(seqs)
+    qlens = (C.c_int * n)(*[len(s) for s in seqs])
+    cseqs, cnames = (C.c_char_p * n)(*seqs), (C.c_char_p * n)(*names)
+    runs, st = [], capi.mgb_stats_t()
+    for it in range(2):
+        gcs = (C.POINTER(capi.mg_gchains_t) * n)()
+        assert lib.mg_map_batch(gi, n, qlens, cseqs, cnames, gcs, C.byref(mo)) == 0, lib.mgb_last_error()
+        runs.append([T.gchains_to_py(gcs[i]) for i in range(n)])
+        lib.mgb_free_batch(n, gcs)
+        lib.mgb_get_stats(gi, C.byref(st))
+        if it == 0:
+            assert st.skip1_len > 1 << 30  # nothing learned yet: every gap tries every tier
+    assert st.skip1_len < 400 and st.skip2_len >= st.skip1_len, (st.skip1_len, st.skip2_len)
+    for i, (a, b) in enumerate(zip(*runs)):
+        d = T.diff_results(a, b)
+        assert d is None, "read %d differs between the unrouted and the routed batch: %s" % (i, d)
+    lib.mg_idx_destroy(gi)

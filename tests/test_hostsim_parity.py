@@ -32,6 +32,10 @@ def test_edge_reads(lib, workdir):
     cases.case_edge(lib, workdir)
 
 
+def test_learned_tier_routing_keeps_results(lib, workdir):
+    cases.case_tier_routing(lib, workdir)
+
+
 def test_engine_switches_keep_results(lib, workdir):
     cases.case_switches(lib, workdir, device=False)
 
