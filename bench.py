@@ -357,7 +357,9 @@ def main():
                 "includes": "wall clock of K x (pack + H2D of reads, all kernels, D2H of result blobs, mg_gchains_t assembly) with the GAF text (%d bytes/step) of batch i written by a second host thread during batch i+1 (the reference's kt_pipeline does the same, gmap.c:176), plus the last batch's GAF; L2 flush between steps included" % gaf_bytes[0]},
         "host_ms_per_step": {"pack": host_timed[0] / a.steps, "h2d": host_timed[1] / a.steps, "d2h": host_timed[2] / a.steps, "assemble": host_timed[3] / a.steps,
                              "mg_map_batch_total": host_timed[4] / a.steps, "gaf_text(second thread)": host_timed[5] / a.steps},
-        "device_cycles_last_step": {k: int(st.prof[i]) for i, k in enumerate(capi.PROF_NAMES)},
+        "device_cycles_last_step": {k: (int(st.prof[i]) >> 16 if k in ("wfa_max_cyc", "gwfa_max_cyc") else int(st.prof[i])) for i, k in enumerate(capi.PROF_NAMES)},
+        "slowest_units": {"gap_len": int(st.prof[capi.PROF_NAMES.index("wfa_max_cyc")]) & 0xffff, "bridge_len": int(st.prof[capi.PROF_NAMES.index("gwfa_max_cyc")]) & 0xffff},
+        "wfa_tier_routing": {"skip_tier1_at": int(st.skip1_len), "skip_tier2_at": int(st.skip2_len)},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "k_chain (linear chaining: mg_lchain_dp/rmq + backtrack + compaction)", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": chain_traffic(), "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_chain launch on this workload, profiles/r01_ncu_k_chain.txt",

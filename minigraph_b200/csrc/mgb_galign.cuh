@@ -179,7 +179,7 @@ MG_HD inline int wfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int la
 		unsigned long long dt = prof_clock() - pt0;
 		int slot = tier == 1? PROF_WFA_FAST_CYC : tier == 2? PROF_WFA_MID_CYC : PROF_WFA_SLOW_CYC;
 		prof_add(c, slot, dt), prof_add(c, slot + 1, 1);
-		prof_max(c, PROF_WFA_MAX_CYC, dt);
+		prof_max(c, PROF_WFA_MAX_CYC, dt << 16 | (unsigned long long)(mlen < 65535? mlen : 65535)); // cycles of the slowest gap, its length in the low 16 bits
 		if (rc == 0) prof_add(c, PROF_WFA_CELLS, (unsigned long long)rst.n_iter);
 		if (rc == 0 && explore && c.tier_hist) {
 			unsigned int *h = &c.tier_hist[(mlen >> 4 < 31? mlen >> 4 : 31) * 4 + tier];
@@ -543,7 +543,7 @@ MG_HD inline int gwfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int l
 	}
 	if (lane == 0) {
 		const GwfResult &r = sh->r;
-		{ unsigned long long dt = prof_clock() - t0; prof_add(c, PROF_GC_GWFA_CYC, dt); prof_max(c, PROF_GWFA_MAX_CYC, dt); }
+		{ unsigned long long dt = prof_clock() - t0; prof_add(c, PROF_GC_GWFA_CYC, dt); prof_max(c, PROF_GWFA_MAX_CYC, dt << 16 | (unsigned long long)(J->ql < 65535? J->ql : 65535)); }
 #if !MGB_ON_DEVICE && defined(MGB_HOSTSIM)
 		if (getenv("MGB_DUMP_JOBS")) fprintf(stderr, "GWFA\t%d\t%d\t%ld\t%d\t%lu\t%d\n", J->ql, r.s, (long)r.n_iter, r.nv, (unsigned long)smem_peak, in_smem);
 #endif
