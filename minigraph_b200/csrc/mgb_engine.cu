@@ -1187,7 +1187,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 		for (int b = 0; b < 32 && t2 == INT32_MAX; ++b) { unsigned int in = h[b * 4 + 1] + h[b * 4 + 2], out = h[b * 4 + 3]; if (in + out >= 8 && in < out) t2 = b * 16; }
 		unsigned int tot = 0;
 		for (int i = 0; i < 128; ++i) tot += h[i];
-		if (tot >= 256 && p_tier_learn) { std::lock_guard<std::mutex> lock(M->big_mutex); M->skip1_len = t1, M->skip2_len = t2 < t1? t1 : t2; }
+		if (tot >= 64 && p_tier_learn) { std::lock_guard<std::mutex> lock(M->big_mutex); M->skip1_len = t1, M->skip2_len = t2 < t1? t1 : t2; }
 		S.skip1_len = L_skip1, S.skip2_len = L_skip2;
 	}
 	if (rc_final < 0) return rc_final;

@@ -115,11 +115,11 @@ MG_HD inline int wfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int la
 	if (c.meta[rid].status < 0) return 0; // the read already failed elsewhere; it will be redone as a whole
 	if (tier < 3 && c.big_len > 0 && (tl >= c.big_len || ql >= c.big_len)) return 0; // taken by the concurrent tier-3 launch
 	// Routing: a gap that cannot finish in an on-chip tier costs that tier up to a full window of cells before it gives up.
-	// Which lengths fail depends on the error rate of the reads, so it is learned: one gap in 16 tries every tier and
+	// Which lengths fail depends on the error rate of the reads, so it is learned: one gap in 64 tries every tier and
 	// reports where it finished; the host turns the counts of one batch into the two thresholds of the next.  The
 	// result of a gap does not depend on the tier that computes it.
 	const int32_t mlen = tl > ql? tl : ql;
-	const int explore = (job_idx & 15) == 0;
+	const int explore = (job_idx & 63) == 0;
 	if (!explore && ((tier == 1 && mlen >= c.skip1_len) || (tier == 2 && mlen >= c.skip2_len))) {
 		if (lane == 0) {
 			unsigned int at;
@@ -511,7 +511,7 @@ MG_HD inline int stage_gchain(const PipeCtx &c, ReadOut *routs, int rid, Arena &
 // diagonals) fit a small per-warp arena in SHARED memory, which removes the global-memory latency from the sequential
 // control flow; a bridge that outgrows it is redone with the worker's arena in HBM.  Lane 0 runs the alignment.
 static const int GWFA_SMEM_ARENA = 12 * 1024;
-static const int GWFA_SMEM_MAX_QL = 128;
+static const int GWFA_SMEM_MAX_QL = 96;
 
 MG_HD inline int gwfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int lane, int32_t *smem)
 {

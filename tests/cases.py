@@ -177,7 +177,7 @@ def case_switches(lib, workdir, device):
                 lib.mgb_set_param(k, defaults[k])
 
 
-def case_tier_routing(lib, workdir, n_reads=60):
+def case_tier_routing(lib, workdir, n_reads=120):
     """the WFA tier thresholds learned from one batch route the gaps of the next: same results, and the routing did engage"""
     import ctypes as C
     from minigraph_b200 import capi, options
