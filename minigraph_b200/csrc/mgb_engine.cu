@@ -176,8 +176,9 @@ struct LaunchArgs {
 	Pool *pool_mz; u128 *mz;
 };
 
-// stages: 0 seed (K1-K3), 1 chain (K4/K5), 2 gchain + alignment plan (K6/K7), 3 segment sketch for the index,
-//         4/6/7 WFA jobs tier 1/2/3 (K8a, warp-cooperative), 5 finish: CIGAR stitching + ds + result blob (K8b)
+// stages: 0 seed (K1-K3), 1 chain (K4/K5), 2 graph chaining DP + bridge plan (K6), 8 bridging jobs (K7a), 9 graph-chain
+//         materialisation + alignment plan (K7b), 4/6/7 WFA jobs tier 1/2/3 (K8a), 5 finish: CIGAR stitching + ds + result
+//         blob (K8b), 3 segment sketch for the index
 #define MGB_IS_WFA(STAGE) ((STAGE) == 4 || (STAGE) == 6 || (STAGE) == 7)
 #define MGB_IS_WARP(STAGE) (MGB_IS_WFA(STAGE) || (STAGE) == 8 || (STAGE) == 1 || (STAGE) == 0 || (STAGE) == 5) // stages entered by all lanes of the warp
 template<int STAGE>
@@ -226,8 +227,8 @@ MG_HD inline void stage_fail(const LaunchArgs &L, int item, int rc)
 
 #ifndef MGB_HOSTSIM
 // One warp per work item; items are pulled from a global counter so that long items do not stall a wave.
-// Stage 4 is warp-cooperative (all lanes enter the stage function); the other stages still run their sequential,
-// bit-exact control flow on lane 0 while the remaining lanes wait at the barrier.
+// The stages listed in MGB_IS_WARP are warp-uniform (all lanes enter the stage function, see mgb_common.cuh); the two
+// graph-chaining stages (2 and 9) run their sequential control flow on lane 0 while the other lanes wait at the barrier.
 template<int STAGE>
 __device__ __forceinline__ void stage_loop(const LaunchArgs &L)
 {
@@ -875,8 +876,6 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	sl.ev_first_ms = sl.ev_last_ms = 0;
 	if (n_reads <= 0) return 0;
 	const int32_t L_skip1 = M->skip1_len, L_skip2 = M->skip2_len; // thresholds this batch runs with
-	const int64_t saved_threads = p_host_threads;
-	(void)saved_threads;
 	double t_host0 = now_ms();
 	// ---- pack the sub-batch into page-locked memory ----
 	uint64_t tot = 0;
