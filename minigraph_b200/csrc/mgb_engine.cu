@@ -1145,6 +1145,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 			P.routs = d_routs, P.meta = d_meta, P.n = n_reads, P.pool = (const char*)d_buf[P_OUT];
 			P.packed = (char*)sl.d_packed.ensure(pool_bytes + 64), P.off = (uint64_t*)sl.d_packoff.ensure(sizeof(uint64_t) * ((size_t)n_reads + 1));
 			pack_results(P);
+			S.n_launches += 2;
 			d2h(routs.data(), d_routs, sizeof(ReadOut) * (size_t)n_reads);
 			pack_off.resize((size_t)n_reads + 1);
 			d2h(pack_off.data(), P.off, sizeof(uint64_t) * ((size_t)n_reads + 1));
