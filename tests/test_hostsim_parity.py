@@ -48,3 +48,41 @@ def test_struct_fields_vs_reference(lib, workdir):
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
 def test_wfa_iteration_cap_fallback(lib):
     cases.case_wfa_fallback(lib)
+
+
+def test_gaf_batch_writer_reuses_buffer(lib, workdir):
+    """mgb_write_gaf_batch(): several threads, the caller's buffer handed back and reused, same bytes as the one-read writer"""
+    import ctypes as C
+    import os
+    from minigraph_b200 import capi, options
+    hap, reads = os.path.join(workdir, "mt.hap.fa"), os.path.join(workdir, "mt.gafw.fa")
+    T.sim_mt_haps(hap)
+    T.sim_reads(hap, reads, 300, 2000, "ont", 41)
+    names, seqs = T.read_fasta(reads)
+    g = lib.mgb_gfa_read(os.path.join(T.FIX, "MT.gfa").encode())
+    io, mo = options.opt_set("lr", True)
+    gi = lib.mg_index(g, C.byref(io), 1, C.byref(mo))
+    n = len(seqs)
+    qlens = (C.c_int * n)(*[len(s) for s in seqs])
+    cseqs, cnames = (C.c_char_p * n)(*seqs), (C.c_char_p * n)(*names)
+    gcs = (C.POINTER(capi.mg_gchains_t) * n)()
+    assert lib.mg_map_batch(gi, n, qlens, cseqs, cnames, gcs, C.byref(mo)) == 0, lib.mgb_last_error()
+    one, ln1, cap1 = C.c_void_p(0), C.c_size_t(0), C.c_size_t(0)
+    for i in range(n):
+        lib.mgb_write_gaf(C.byref(one), C.byref(ln1), C.byref(cap1), g, gcs[i], qlens[i], cnames[i], mo.flag)
+    want = C.string_at(one, ln1.value)
+    buf, ln, cap = C.c_void_p(0), C.c_size_t(0), C.c_size_t(0)
+    seen = set()
+    for threads in (4, 7, 1, 4):
+        lib.mgb_write_gaf_batch(g, n, gcs, qlens, cnames, mo.flag, threads, C.byref(buf), C.byref(ln), C.byref(cap))
+        assert C.string_at(buf, ln.value) == want
+        assert cap.value > ln.value
+        seen.add(buf.value)
+    assert len(seen) == 1  # the buffer of the first call served all of them
+    fresh, lnf = C.c_void_p(0), C.c_size_t(0)
+    lib.mgb_write_gaf_batch(g, n, gcs, qlens, cnames, mo.flag, 3, C.byref(fresh), C.byref(lnf), None)
+    assert C.string_at(fresh, lnf.value) == want
+    C.CDLL(None).free(fresh)
+    lib.mgb_free_batch(n, gcs)
+    assert all(not gcs[i] for i in range(n))
+    lib.mg_idx_destroy(gi)
