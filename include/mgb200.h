@@ -174,9 +174,10 @@ void mg_idx_hfree(void *h);
 mg_tbuf_t *mg_tbuf_init(void);
 void mg_tbuf_destroy(mg_tbuf_t *b);
 
-/* replaces map-algo.c:340-495 mg_map_frag() for n_segs == 1 (the only case the long-read presets produce):
- * gcs[0] receives a malloc()ed result owned by the caller (free with mg_gchain_free), or NULL when the read is empty
- * or longer than opt->max_qlen (map-algo.c:359-360). One read per launch: correct but slow -- use mg_map_batch. */
+/* replaces map-algo.c:340-495 mg_map_frag(): gcs[0] receives a malloc()ed result owned by the caller (free with
+ * mg_gchain_free), or NULL when the fragment is empty, has more than 255 segments or is longer than opt->max_qlen
+ * (map-algo.c:359-360); gcs[i>0] = NULL. With n_segs > 1 the concatenated fragment is mapped and no CIGAR is produced
+ * (map-algo.c:34-45,464,475). One fragment per launch: correct but slow -- use mg_map_batch for single-segment reads. */
 void mg_map_frag(const mg_idx_t *gi, int n_segs, const int *qlens, const char **seqs, mg_gchains_t **gcs, mg_tbuf_t *b, const mg_mapopt_t *opt, const char *qname);
 
 /* replaces map-algo.c:497-502 mg_map() */

@@ -508,7 +508,7 @@ struct Model {
 	// the batch pipeline: a batch is cut into sub-batches, each driven by its own host thread on its own stream ("slot"),
 	// so that kernels, copies and host-side result assembly of different sub-batches overlap
 	struct Slot {
-		GrowBuf h_seq{true}, h_out{true}, h_small{true}, d_seq, d_meta, d_routs, d_small, d_jobq, d_order, d_bigq, d_packed, d_packoff, d_pool[10];
+		GrowBuf h_seq{true}, h_out{true}, h_small{true}, d_seq, d_meta, d_routs, d_small, d_jobq, d_order, d_bigq, d_packed, d_packoff, d_segs, d_pool[10];
 		Workers W, W2; // W2: the few workers of the tier-3 launch that runs beside tiers 1/2
 		mgb_stats_t st;
 		double ev_first_ms, ev_last_ms; // first kernel start / last kernel end relative to the batch reference event
@@ -534,7 +534,7 @@ static void model_free(Model *M)
 	if (M->d_logf) dfree(M->d_logf);
 	for (int k = 0; k < Model::MAX_SLOTS; ++k) {
 		Model::Slot &sl = M->slots[k];
-		sl.h_seq.release(), sl.h_out.release(), sl.h_small.release(), sl.d_seq.release(), sl.d_meta.release(), sl.d_routs.release(), sl.d_small.release(), sl.d_jobq.release(), sl.d_order.release(), sl.d_bigq.release(), sl.d_packed.release(), sl.d_packoff.release();
+		sl.h_seq.release(), sl.h_out.release(), sl.h_small.release(), sl.d_seq.release(), sl.d_meta.release(), sl.d_routs.release(), sl.d_small.release(), sl.d_jobq.release(), sl.d_order.release(), sl.d_bigq.release(), sl.d_packed.release(), sl.d_packoff.release(), sl.d_segs.release();
 		if (sl.W2.arena) dfree(sl.W2.arena);
 		if (sl.W2.peak) dfree(sl.W2.peak);
 		for (int i = 0; i < 10; ++i) sl.d_pool[i].release();
@@ -869,7 +869,7 @@ int64_t p_min_slot_reads = 512; // do not cut batches into pieces smaller than t
 
 // Map reads [0, n_reads) of one sub-batch on the calling thread's stream (slot `sl`).
 static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads, const int *qlens, const char *const *seqs, const char *const *names,
-					 mg_gchains_t **gcs, int host_threads)
+					 mg_gchains_t **gcs, int host_threads, const std::vector<int32_t> *seg_off = 0, const std::vector<int32_t> *seg_len = 0)
 {
 	mgb_stats_t &S = sl.st;
 	memset(&S, 0, sizeof(S));
@@ -939,6 +939,13 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	unsigned int *d_tier_hist = (unsigned int*)((char*)(d_pools + 16) + 64); // 32 x 4 counters behind the pool headers
 	h2d(d_seq_off, seq_off, (size_t)n_reads * 16); // seq_off, seq_len and name_hash are contiguous on both sides
 	tm_h2d.stop();
+	int32_t *d_seg_off = 0, *d_seg_len = 0; // multi-segment fragments only (mg_map_frag with n_segs > 1)
+	if (seg_off && seg_len) {
+		d_seg_off = (int32_t*)sl.d_segs.ensure(sizeof(int32_t) * (seg_off->size() + seg_len->size()));
+		d_seg_len = d_seg_off + seg_off->size();
+		h2d(d_seg_off, seg_off->data(), sizeof(int32_t) * seg_off->size());
+		h2d(d_seg_len, seg_len->data(), sizeof(int32_t) * seg_len->size());
+	}
 	ReadMeta *d_meta = (ReadMeta*)sl.d_meta.ensure(sizeof(ReadMeta) * (size_t)n_reads);
 	ReadOut *d_routs = (ReadOut*)sl.d_routs.ensure(sizeof(ReadOut) * (size_t)n_reads);
 	dzero(d_meta, sizeof(ReadMeta) * (size_t)n_reads);
@@ -975,6 +982,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 		memset(&L, 0, sizeof(L));
 		L.c.g = M->g, L.c.ix = M->ix, L.c.opt = o;
 		L.c.b.n_reads = n_reads, L.c.b.seq = d_seq, L.c.b.seq_off = d_seq_off, L.c.b.seq_len = d_seq_len, L.c.b.name_hash = d_name_hash;
+		L.c.b.seg_off = d_seg_off, L.c.b.seg_len = d_seg_len;
 		L.c.meta = d_meta;
 		L.c.pool_anchor = &d_pools[P_ANCHOR], L.c.anchor = (u128*)d_buf[P_ANCHOR];
 		L.c.pool_minipos = &d_pools[P_MINIPOS], L.c.minipos = (int32_t*)d_buf[P_MINIPOS];
@@ -1244,7 +1252,7 @@ static void slot_prepare(Model *M, Model::Slot &sl, int n_workers)
 }
 
 static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, const char *const *seqs, const char *const *names,
-						  mg_gchains_t **gcs, const mg_mapopt_t *opt)
+						  mg_gchains_t **gcs, const mg_mapopt_t *opt, const std::vector<int32_t> *seg_off = 0, const std::vector<int32_t> *seg_len = 0)
 {
 	Model *M = (Model*)gi->B;
 	mgb_stats_t &S = M->stats;
@@ -1301,7 +1309,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 		t_stream = M->slots[k].stream;
 #endif
 		int b = bound[k], e = bound[k + 1];
-		rcs[k] = map_range(M, M->slots[k], o, e - b, qlens + b, seqs + b, names? names + b : 0, gcs + b, nt_slot);
+		rcs[k] = map_range(M, M->slots[k], o, e - b, qlens + b, seqs + b, names? names + b : 0, gcs + b, nt_slot, seg_off, seg_len); // segments only come with one-read batches
 	};
 	if (n_slots == 1) {
 		work(0);
@@ -1364,9 +1372,17 @@ extern "C" void mg_map_frag(const mg_idx_t *gi, int n_segs, const int *qlens, co
 	(void)b;
 	for (int i = 0; i < n_segs; ++i) gcs[i] = 0;
 	if (n_segs <= 0) return;
-	if (n_segs != 1) {
-		set_error("mg_map_frag: multi-segment (paired-end) fragments are not supported by the GPU engine yet");
-		abort();
+	if (n_segs != 1) { // reference: map-algo.c:356-360,366,457-464: one result for the concatenated fragment, no CIGAR
+		if (n_segs > 255) return; // MG_MAX_SEG
+		std::string cat;
+		std::vector<int32_t> seg_off(2), seg_len((size_t)n_segs);
+		for (int i = 0; i < n_segs; ++i) { seg_len[(size_t)i] = qlens[i] > 0? qlens[i] : 0; if (qlens[i] > 0) cat.append(seqs[i], (size_t)qlens[i]); }
+		seg_off[0] = 0, seg_off[1] = n_segs;
+		if (cat.empty()) return;
+		const int qlen_sum = (int)cat.size();
+		const char *sq = cat.data(), *nm1 = qname;
+		if (map_batch_impl(gi, 1, &qlen_sum, &sq, &nm1, gcs, opt, &seg_off, &seg_len) < 0) abort();
+		return;
 	}
 	const char *nm = qname;
 	if (mg_map_batch(gi, 1, qlens, seqs, &nm, gcs, opt) < 0) abort(); // the reference aborts on internal errors too

@@ -488,7 +488,7 @@ MG_HD inline int stage_gchain(const PipeCtx &c, ReadOut *routs, int rid, Arena &
 		MG_HD int operator()(GwfaJob &J) { if (n >= cap) return MGB_E_INTERNAL; J.rid = rid; dst[n++] = J; return 0; }
 	} le;
 	le.dst = c.gjobs + job_first, le.rid = rid, le.n = 0, le.cap = n_lc > 0? n_lc : 1;
-	MGB_TRY(gchain_prep(c.g, n_u, u, lc, a, m.hash, o.min_gc_cnt, o.min_gc_score, o.gdp_max_ed, gc_hash, &n_gc, le));
+	MGB_TRY(gchain_prep(c.g, n_u, u, lc, a, m.hash, o.min_gc_cnt, o.min_gc_score, o.gdp_max_ed, batch_n_seg(c.b, rid), gc_hash, &n_gc, le));
 	for (int32_t i = le.n; i < le.cap; ++i) le.dst[i].rid = -1; // unused reserved slots: skipped by the job kernel
 	// persist
 	uint64_t sz = sizeof(GState) + align8((uint64_t)n_lc * sizeof(LChain)) + (uint64_t)n_u * 8 + align8((uint64_t)n_gc * 4);
@@ -589,7 +589,7 @@ MG_HD inline int stage_gchain_gen(const PipeCtx &c, ReadOut *routs, int rid, Are
 	feed.job = c.gjobs + gsb->job_first, feed.walk_pool = c.walk, feed.next = 0, feed.n = gsb->n_jobs;
 	GcSet gs;
 	unsigned long long pt1 = prof_clock();
-	MGB_TRY(gchain_gen(A, c.g, n_u, u, lc, a, m.hash, o.min_gc_cnt, o.min_gc_score, o.gdp_max_ed, 1, qseq, gs, &feed, gc_hash));
+	MGB_TRY(gchain_gen(A, c.g, n_u, u, lc, a, m.hash, o.min_gc_cnt, o.min_gc_score, o.gdp_max_ed, batch_n_seg(c.b, rid), qseq, gs, &feed, gc_hash));
 	gs.rep_len = m.rep_len;
 	unsigned long long pt2 = prof_clock();
 	prof_add(c, PROF_GC_GEN_CYC, pt2 - pt1);
@@ -611,7 +611,7 @@ MG_HD inline int stage_gchain_gen(const PipeCtx &c, ReadOut *routs, int rid, Are
 		GChain *gc = &gs.gc[i];
 		gc->has_cigar = 0, gc->n_cigar = 0, gc->cigar_off = gc->ds_off = gc->dsoff_off = 0, gc->ds_len = gc->n_dsoff = 0, gc->plan_off = 0, gc->n_plan = 0;
 	}
-	if ((o.flag & F_CIGAR) && gs.n_gc > 0)
+	if ((o.flag & F_CIGAR) && gs.n_gc > 0 && batch_n_seg(c.b, rid) == 1) // reference: map-algo.c:475
 		MGB_TRY(gchain_cigar_plan(A, c, rid, c.g, gs, boff + (int64_t)off_lc));
 	{
 		GChain *d = (GChain*)blob;
@@ -634,7 +634,7 @@ MG_HD inline int stage_finish(const PipeCtx &c, ReadOut *routs, int rid, Arena &
 	ReadMeta &m = c.meta[rid];
 	ReadOut &ro = routs[rid];
 	if (m.status != 0) { if (lane == 0) ro.status = m.status; return 0; }
-	if (!(c.opt.flag & F_CIGAR) || ro.n_gc == 0) return 0;
+	if (!(c.opt.flag & F_CIGAR) || ro.n_gc == 0 || batch_n_seg(c.b, rid) != 1) return 0;
 	uint64_t mark = A.top;
 	const char *qseq = c.b.seq + c.b.seq_off[rid];
 	char *blob = c.out + ro.blob_off;

@@ -513,7 +513,7 @@ MG_HD inline int gchain_sort_by_score(Arena &A, GcSet &gs)
 // emit one GwfaJob per bridge between different vertices (same pair enumeration as the loop in gchain_gen()).
 template<typename Emit>
 MG_HD inline int gchain_prep(const GraphDev &g, int32_t n_u, const uint64_t *u, LChain *lc, const u128 *a, uint32_t hash, int32_t min_gc_cnt,
-							 int32_t min_gc_score, int32_t gdp_max_ed, uint32_t *gc_hash, int32_t *n_gc_, Emit &emit)
+							 int32_t min_gc_score, int32_t gdp_max_ed, int32_t n_seg, uint32_t *gc_hash, int32_t *n_gc_, Emit &emit)
 {
 	int32_t i, j, k, st, kmer_size = 0;
 	*n_gc_ = 0;
@@ -533,7 +533,7 @@ MG_HD inline int gchain_prep(const GraphDev &g, int32_t n_u, const uint64_t *u, 
 			for (j0 = 0, j = 1; j < nui; ++j) {
 				const LChain *l0 = &lc[st + j0], *l1 = &lc[st + j];
 				if (l1->cnt > 0) {
-					if (l1->v != l0->v) {
+					if (l1->v != l0->v && n_seg <= 1) { // multi-segment fragments are bridged by shortest walks only (gchain1.c:387)
 						GwfaJob J;
 						J.rid = 0, J.v0 = l0->v, J.v1 = l1->v;
 						J.qs = l0->qe - kmer_size, J.ql = (l1->qs + kmer_size) - J.qs;

@@ -115,6 +115,11 @@ struct BatchDev {
 	const uint64_t *seq_off;    // [n_reads]
 	const int32_t *seq_len;     // [n_reads]
 	const uint32_t *name_hash;  // [n_reads] kh_hash_str(qname) computed by the host, 0 if no name
+	// multi-segment fragments (paired reads; reference: map-algo.c:34-45,356-360): a read's sequence is the concatenation of its
+	// segments, seg_len[seg_off[r] .. seg_off[r+1]) their lengths.  NULL for the usual batch of single-segment reads.
+	const int32_t *seg_off;     // [n_reads + 1]
+	const int32_t *seg_len;
 };
+MG_HD inline int32_t batch_n_seg(const BatchDev &b, int rid) { return b.seg_off? b.seg_off[rid + 1] - b.seg_off[rid] : 1; }
 
 } // namespace mgb

@@ -91,7 +91,26 @@ MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A, int lane)
 	AVec<u128> mv;
 	avec_init(mv);
 	unsigned long long t0 = prof_clock();
-	MGB_TRY(sketch_seq_w(A, seq, qlen, c.ix.w, c.ix.k, 0, mv, lane));
+	const int32_t n_seg = batch_n_seg(c.b, rid);
+	if (n_seg == 1) {
+		MGB_TRY(sketch_seq_w(A, seq, qlen, c.ix.w, c.ix.k, 0, mv, lane));
+	} else { // reference: map-algo.c:34-45 collect_minimizers: every segment on its own, positions shifted by the lengths before it
+		const int32_t *sl = c.b.seg_len + c.b.seg_off[rid];
+		MGB_ALLOC(A, mv.a, u128, (int64_t)qlen + 16 * (int64_t)n_seg);
+		mv.m = (int64_t)qlen + 16 * (int64_t)n_seg;
+		const uint64_t keep = A.top;
+		int32_t sum = 0;
+		for (int32_t i = 0; i < n_seg; ++i) {
+			AVec<u128> one;
+			avec_init(one);
+			if (sl[i] > 0) MGB_TRY(sketch_seq_w(A, seq + sum, sl[i], c.ix.w, c.ix.k, (uint32_t)i, one, lane));
+			if (mv.n + one.n > mv.m) return MGB_E_INTERNAL;
+			for (int64_t j = lane; j < one.n; j += MGB_W) { u128 e = one.a[j]; e.y += (uint64_t)sum << 1; mv.a[mv.n + j] = e; }
+			warp_sync();
+			mv.n += one.n, sum += sl[i];
+			A.top = keep;
+		}
+	}
 	unsigned long long t1 = prof_clock();
 	SeedMatch *sm;
 	int n_m, n_mp, rep_len;
@@ -203,14 +222,14 @@ MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A, int lane, int3
 								o.chn_pen_gap, o.chn_pen_skip, n_a, a, &n_lc, &u, &n_a_new, lane));
 		} else {
 			MGB_TRY(chain_dp_w(A, max_gap_ref, max_gap_qry, o.bw, o.max_lc_skip, o.max_lc_iter, o.min_lc_cnt, o.min_lc_score,
-							   o.chn_pen_gap, o.chn_pen_skip, is_splice, 1, n_a, a, &n_lc, &u, &n_a_new, lane, smem, smem? CHAIN_SMEM : 0));
+							   o.chn_pen_gap, o.chn_pen_skip, is_splice, batch_n_seg(c.b, rid), n_a, a, &n_lc, &u, &n_a_new, lane, smem, smem? CHAIN_SMEM : 0));
 		}
 	}
 	if (lane == 0) m.n_u0 = n_lc;
 	unsigned long long t1 = prof_clock();
 	if (lane == 0) prof_add(c, PROF_CHAIN_DP_CYC, t1 - t0);
 	// long-join rescue (reference: map-algo.c:407-417)
-	if (o.bw_long > o.bw && (o.flag & (F_SPLICE | F_SR)) == 0 && n_lc > 1) {
+	if (o.bw_long > o.bw && (o.flag & (F_SPLICE | F_SR)) == 0 && batch_n_seg(c.b, rid) == 1 && n_lc > 1) {
 		int32_t st = (int32_t)a[0].y, en = (int32_t)a[(int32_t)u[0] - 1].y;
 		if (qlen - (en - st) > o.rmq_rescue_size || (float)(qlen - (en - st)) > (float)qlen * o.rmq_rescue_ratio) {
 			int64_t n2 = 0;

@@ -206,3 +206,52 @@ def case_tier_routing(lib, workdir, n_reads=120):
         d = T.diff_results(a, b)
         assert d is None, "read %d differs between the unrouted and the routed batch: %s" % (i, d)
     lib.mg_idx_destroy(gi)
+
+
+def case_multi_segment(lib, workdir, n_frag=40):
+    """fragments of 2-3 segments through mg_map_frag (paired reads): one result for the concatenated fragment, no CIGAR, same
+    fields as the reference (map-algo.c:34-45,356-360,402,407,464,475)"""
+    import ctypes as C
+    import random
+    from minigraph_b200 import capi, options
+    ref = T.load_ref()
+    hap, reads = os.path.join(workdir, "mt.hap.fa"), os.path.join(workdir, "mt.seg.fa")
+    T.sim_mt_haps(hap)
+    T.sim_reads(hap, reads, n_frag, 9000, "ont", 53)
+    names, seqs = T.read_fasta(reads)
+    rng = random.Random(7)
+    gfa = os.path.join(T.FIX, "MT.gfa")
+    io, mo = options.opt_set("lr", True)
+    g_e = lib.mgb_gfa_read(gfa.encode())
+    gi_e = lib.mg_index(g_e, C.byref(io), 1, C.byref(mo))
+    assert gi_e, lib.mgb_last_error()
+    io_r, mo_r = options.opt_set("lr", True)
+    g_r = ref.gfa_read(gfa.encode())
+    gi_r = ref.mg_index(g_r, C.byref(io_r), 1, C.byref(mo_r))
+    b_r, b_e = ref.mg_tbuf_init(), lib.mg_tbuf_init()
+    for f in (lib.mg_map_frag, ref.mg_map_frag):
+        f.restype = None
+        f.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_char_p), C.POINTER(C.POINTER(capi.mg_gchains_t)), C.c_void_p, C.c_void_p, C.c_char_p]
+    n_mapped = 0
+    for nm, s in zip(names, seqs):
+        n_seg = rng.choice([2, 2, 3])
+        cut = sorted(rng.sample(range(1500, len(s) - 1500), n_seg - 1))
+        parts = [s[a:b] for a, b in zip([0] + cut, cut + [len(s)])]
+        if rng.random() < 0.3:
+            parts[-1] = parts[-1][:40]  # a segment too short to be sketched in chunks
+        ql = (C.c_int * n_seg)(*[len(x) for x in parts])
+        sq = (C.c_char_p * n_seg)(*parts)
+        res = []
+        for lb, gi, mo_x, tb in ((ref, gi_r, mo_r, b_r), (lib, gi_e, mo, b_e)):
+            gcs = (C.POINTER(capi.mg_gchains_t) * n_seg)()
+            lb.mg_map_frag(C.cast(gi, C.c_void_p), n_seg, ql, sq, gcs, tb, C.cast(C.pointer(mo_x), C.c_void_p), nm)
+            assert all(not gcs[i] for i in range(1, n_seg))
+            res.append(T.gchains_to_py(gcs[0]))
+            lb.mg_gchain_free(gcs[0])
+        d = T.diff_results(res[0], res[1])
+        assert d is None, (nm, [len(x) for x in parts], d)
+        if res[0] and res[0]["n_gc"] > 0:
+            n_mapped += 1
+    assert n_mapped >= n_frag // 2
+    ref.mg_tbuf_destroy(b_r), lib.mg_tbuf_destroy(b_e)
+    lib.mg_idx_destroy(gi_e), ref.mg_idx_destroy(gi_r)
