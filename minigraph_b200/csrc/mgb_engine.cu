@@ -1258,6 +1258,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 	mgb_stats_t &S = M->stats;
 	memset(&S, 0, sizeof(S));
 	for (int i = 0; i < n_reads; ++i) gcs[i] = 0;
+	if (opt->flag & F_NO_DIAG) { set_error("MG_M_NO_DIAG (-D, skip self diagonal seeds by sequence name) is not supported by the GPU engine"); return MGB_E_UNSUPPORTED; }
 	if (n_reads <= 0) return 0;
 	double t0 = now_ms();
 	int32_t max_qlen = 0;

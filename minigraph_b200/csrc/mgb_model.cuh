@@ -79,7 +79,7 @@ struct MapOptDev {
 	int32_t n_logf_tab;
 };
 
-static const uint64_t F_SPLICE = 0x10, F_SR = 0x20, F_RMQ = 0x8000, F_CIGAR = 0x4000000;
+static const uint64_t F_SPLICE = 0x10, F_SR = 0x20, F_HEAP_SORT = 0x400, F_RMQ = 0x8000, F_NO_DIAG = 0x400000, F_CIGAR = 0x4000000;
 
 // linear chain (reference: minigraph.h:100-106 mg_lchain_t)
 struct LChain {

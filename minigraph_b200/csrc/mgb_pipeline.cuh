@@ -133,10 +133,20 @@ MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A, int lane)
 		m.n_a = (int32_t)n_a, m.n_mp = n_mp, m.n_seed0 = (int32_t)n_a;
 	}
 	for (int i = lane; i < n_mp; i += MGB_W) mp[i] = mp_tmp[i];
-	expand_seeds_w(c.g, n_m, sm, a_off, a, lane);
-	warp_sync();
-	unsigned long long t2 = prof_clock();
-	MGB_TRY(radix_sort_128x_w(A, a, n_a, lane));
+	unsigned long long t2;
+	if (c.opt.flag & F_HEAP_SORT) { // reference: map-algo.c:367
+		int rc = 0;
+		if (lane == 0) { Arena B = A; rc = expand_seeds_heap(B, c.g, n_m, sm, n_a, a); if (B.peak > A.peak) A.peak = B.peak; }
+		rc = warp_bcast_i32(rc, 0);
+		warp_sync();
+		if (rc < 0) return rc;
+		t2 = prof_clock();
+	} else {
+		expand_seeds_w(c.g, n_m, sm, a_off, a, lane);
+		warp_sync();
+		t2 = prof_clock();
+		MGB_TRY(radix_sort_128x_w(A, a, n_a, lane));
+	}
 	if (lane == 0) prof_add(c, PROF_SEED_SKETCH_CYC, t1 - t0), prof_add(c, PROF_SEED_MATCH_CYC, t2 - t1), prof_add(c, PROF_SEED_SORT_CYC, prof_clock() - t2);
 	A.top = mark;
 	return 0;

@@ -349,4 +349,57 @@ MG_HD inline void expand_seeds_w(const GraphDev &g, int n_m, const SeedMatch *m,
 	}
 }
 
+// Seeds by k-way merge of the occurrence lists (reference: map-algo.c:93-150 collect_seed_hits_heap, the `sr` preset).  The
+// heap is klib's (ksort.h:43-70 with heap_lt = a.x > b.x): its sift order decides the order among equal target positions, so
+// it is replayed as is.  Forward-strand anchors fill a[] from the front in pop order, reverse-strand ones from the back.
+// One lane; no sort follows.
+MG_HD inline void seed_heap_down(int64_t i, int64_t n, u128 *l)
+{
+	int64_t k = i;
+	u128 tmp = l[i];
+	while ((k = (k << 1) + 1) < n) {
+		if (k != n - 1 && l[k].x > l[k+1].x) ++k;
+		if (l[k].x > tmp.x) break;
+		l[i] = l[k], i = k;
+	}
+	l[i] = tmp;
+}
+MG_HD inline int expand_seeds_heap(Arena &A, const GraphDev &g, int n_m, const SeedMatch *m, int64_t n_a, u128 *a)
+{
+	uint64_t mark = A.top;
+	u128 *heap;
+	MGB_ALLOC(A, heap, u128, n_m);
+	int64_t heap_size = 0, n_for = 0, n_rev = 0;
+	for (int i = 0; i < n_m; ++i)
+		if (m[i].n > 0) heap[heap_size].x = m[i].cr[0], heap[heap_size].y = (uint64_t)i << 32, ++heap_size;
+	for (int64_t i = (heap_size >> 1) - 1; i >= 0; --i) seed_heap_down(i, heap_size, heap);
+	while (heap_size > 0) {
+		const SeedMatch *q = &m[heap[0].y >> 32];
+		const uint64_t r = heap[0].x;
+		const int32_t rpos = (int32_t)((uint32_t)r >> 1);
+		u128 *p;
+		if ((r & 1) == (q->q_pos & 1)) {
+			p = &a[n_for++];
+			p->x = r >> 32 << 33 | (uint64_t)(uint32_t)rpos;
+		} else {
+			p = &a[n_a - (++n_rev)];
+			p->x = r >> 32 << 33 | 1ULL << 32 | (uint64_t)(uint32_t)(g.seg_len[r >> 32] - (rpos + 1 - (int32_t)q->q_span) - 1);
+		}
+		p->y = (uint64_t)q->q_span << 32 | (uint64_t)(q->q_pos >> 1);
+		p->y |= (uint64_t)q->seg_id << SEED_SEG_SHIFT;
+		if (q->is_tandem) p->y |= SEED_TANDEM;
+		p->y |= (uint64_t)(q->n < 255? q->n : 255) << SEED_OCC_SHIFT;
+		if ((uint32_t)heap[0].y < q->n - 1) {
+			++heap[0].y;
+			heap[0].x = m[heap[0].y >> 32].cr[(uint32_t)heap[0].y];
+		} else {
+			heap[0] = heap[heap_size - 1];
+			--heap_size;
+		}
+		seed_heap_down(0, heap_size, heap);
+	}
+	A.top = mark;
+	return n_for + n_rev == n_a? 0 : MGB_E_INTERNAL;
+}
+
 } // namespace mgb

@@ -4,6 +4,8 @@ Only the presets of the mapping path are provided (lr = default, asm); the graph
 scope. Values are kept in the C structs of the ABI so that they can be handed to mg_index()/mg_map_batch()."""
 from .capi import mg_idxopt_t, mg_mapopt_t, MG_M_RMQ, MG_M_CIGAR
 
+MG_M_SR, MG_M_FRAG_MODE, MG_M_FRAG_MERGE, MG_M_HEAP_SORT, MG_M_2_IO_THREADS = 0x20, 0x40, 0x80, 0x400, 0x80000  # minigraph.h:10-24
+
 
 def idxopt_init():
     io = mg_idxopt_t()
@@ -52,8 +54,25 @@ def opt_set(preset=None, cigar=True):
         mo.max_lc_skip = mo.max_gc_skip = 50
         mo.div = 0.01
         mo.mini_batch_size = 4000000000
+    elif preset in ("se", "sr"):  # options.c:87-104
+        io.k, io.w = 21, 10
+        mo.flag |= MG_M_SR | MG_M_HEAP_SORT | MG_M_2_IO_THREADS
+        mo.occ_max1, mo.occ_max1_cap = 1000, 2500
+        mo.max_gap = 100
+        mo.bw = mo.bw_long = 100
+        mo.max_frag_len = 800
+        mo.pri_ratio = 0.5
+        mo.min_lc_cnt, mo.min_lc_score = 2, 25
+        mo.min_gc_cnt, mo.min_gc_score = 3, 40
+        mo.mini_batch_size = 50000000
+        mo.min_cov_blen = 50
+        mo.chn_pen_gap = 0.2
+        mo.ref_bonus = 1
+        if preset == "sr":
+            mo.flag |= MG_M_FRAG_MODE | MG_M_FRAG_MERGE
+            mo.pe_ori = 0 << 1 | 1
     else:
-        raise ValueError("unsupported preset %r (mapping presets: lr, asm)" % (preset,))
+        raise ValueError("unsupported preset %r (mapping presets: lr, asm, sr, se)" % (preset,))
     if cigar:
         mo.flag |= MG_M_CIGAR
     return io, mo

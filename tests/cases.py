@@ -255,3 +255,52 @@ def case_multi_segment(lib, workdir, n_frag=40):
     assert n_mapped >= n_frag // 2
     ref.mg_tbuf_destroy(b_r), lib.mg_tbuf_destroy(b_e)
     lib.mg_idx_destroy(gi_e), ref.mg_idx_destroy(gi_r)
+
+
+def case_short_reads(lib, workdir, n_pairs=60):
+    """the `sr` preset: seeds by heap merge instead of the radix sort (map-algo.c:93-150), short-read chaining gaps, read
+    pairs as two-segment fragments -- every field against the reference's mg_map_frag"""
+    import ctypes as C
+    import random
+    from minigraph_b200 import capi, options
+    ref = T.load_ref()
+    hap, reads = os.path.join(workdir, "mt.hap.fa"), os.path.join(workdir, "mt.sr.fa")
+    T.sim_mt_haps(hap)
+    T.sim_reads(hap, reads, n_pairs, 500, "hifi", 61)
+    names, seqs = T.read_fasta(reads)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    rng = random.Random(3)
+    gfa = os.path.join(T.FIX, "MT.gfa")
+    io, mo = options.opt_set("sr", False)
+    g_e = lib.mgb_gfa_read(gfa.encode())
+    gi_e = lib.mg_index(g_e, C.byref(io), 1, C.byref(mo))
+    assert gi_e, lib.mgb_last_error()
+    io_r, mo_r = options.opt_set("sr", False)
+    g_r = ref.gfa_read(gfa.encode())
+    gi_r = ref.mg_index(g_r, C.byref(io_r), 1, C.byref(mo_r))
+    b_r, b_e = ref.mg_tbuf_init(), lib.mg_tbuf_init()
+    for f in (lib.mg_map_frag, ref.mg_map_frag):
+        f.restype = None
+        f.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_char_p), C.POINTER(C.POINTER(capi.mg_gchains_t)), C.c_void_p, C.c_void_p, C.c_char_p]
+    n_mapped = 0
+    for nm, s in zip(names, seqs):
+        if rng.random() < 0.7:  # a pair: 150 bases from each end, the mate reverse-complemented
+            parts = [s[:150], s[-150:].translate(comp)[::-1]]
+        else:
+            parts = [s[:rng.choice([100, 150, 250])]]
+        n_seg = len(parts)
+        ql = (C.c_int * n_seg)(*[len(x) for x in parts])
+        sq = (C.c_char_p * n_seg)(*parts)
+        res = []
+        for lb, gi, mo_x, tb in ((ref, gi_r, mo_r, b_r), (lib, gi_e, mo, b_e)):
+            gcs = (C.POINTER(capi.mg_gchains_t) * n_seg)()
+            lb.mg_map_frag(C.cast(gi, C.c_void_p), n_seg, ql, sq, gcs, tb, C.cast(C.pointer(mo_x), C.c_void_p), nm)
+            res.append(T.gchains_to_py(gcs[0]))
+            lb.mg_gchain_free(gcs[0])
+        d = T.diff_results(res[0], res[1])
+        assert d is None, (nm, [len(x) for x in parts], d)
+        if res[0] and res[0]["n_gc"] > 0:
+            n_mapped += 1
+    assert n_mapped >= n_pairs // 2, n_mapped
+    ref.mg_tbuf_destroy(b_r), lib.mg_tbuf_destroy(b_e)
+    lib.mg_idx_destroy(gi_e), ref.mg_idx_destroy(gi_r)
