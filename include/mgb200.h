@@ -196,6 +196,13 @@ void mg_gchain_free(mg_gchains_t *gs);
 int mg_map_batch(const mg_idx_t *gi, int n_reads, const int *qlens, const char *const *seqs, const char *const *names,
 				 mg_gchains_t **gcs, const mg_mapopt_t *opt);
 
+/* The same for fragments of several segments (read pairs, the `sr` preset): fragment f owns n_seg[f] consecutive entries of
+ * qlens/seqs/gcs; the result of the concatenated fragment goes to its first gcs entry, the others are NULL -- what
+ * worker_for() leaves without MG_M_INDEPEND_SEG (gmap.c:46-48). names[] is per fragment. The caller reverse-complements
+ * mates beforehand as gmap.c:38-40 does. */
+int mg_map_batch_frag(const mg_idx_t *gi, int n_frag, const int *n_seg, const int *qlens, const char *const *seqs, const char *const *names,
+					  mg_gchains_t **gcs, const mg_mapopt_t *opt);
+
 /* mg_gchain_free() over a whole batch (what step 2 of the reference pipeline does read by read, gmap.c:130); entries are set to NULL */
 void mgb_free_batch(int n_reads, mg_gchains_t **gcs);
 

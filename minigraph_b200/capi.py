@@ -148,6 +148,9 @@ def bind_engine_api(lib):
                                   C.POINTER(mg_gchains_t), C.c_int32, C.c_char_p, C.c_uint64]
     lib.mgb_test_wfa.restype = C.c_int
     lib.mgb_test_wfa.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_int)]
+    lib.mg_map_batch_frag.restype = C.c_int
+    lib.mg_map_batch_frag.argtypes = [C.POINTER(mg_idx_t), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_char_p), C.POINTER(C.c_char_p),
+                                      C.POINTER(C.POINTER(mg_gchains_t)), C.POINTER(mg_mapopt_t)]
     lib.mgb_free_batch.restype = None
     lib.mgb_free_batch.argtypes = [C.c_int, C.POINTER(C.POINTER(mg_gchains_t))]
     lib.mgb_write_gaf_batch.restype = None

@@ -1282,6 +1282,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 	int n_slots = 1;
 #else
 	int n_slots = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(p_slots, Model::MAX_SLOTS), n_reads / std::max<int64_t>(1, p_min_slot_reads)));
+	if (seg_off) n_slots = 1; // the segment table indexes the reads of the whole batch
 #endif
 	std::vector<int> bound(n_slots + 1, n_reads);
 	bound[0] = 0;
@@ -1310,7 +1311,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 		t_stream = M->slots[k].stream;
 #endif
 		int b = bound[k], e = bound[k + 1];
-		rcs[k] = map_range(M, M->slots[k], o, e - b, qlens + b, seqs + b, names? names + b : 0, gcs + b, nt_slot, seg_off, seg_len); // segments only come with one-read batches
+		rcs[k] = map_range(M, M->slots[k], o, e - b, qlens + b, seqs + b, names? names + b : 0, gcs + b, nt_slot, seg_off, seg_len);
 	};
 	if (n_slots == 1) {
 		work(0);
@@ -1366,6 +1367,44 @@ extern "C" int mg_map_batch(const mg_idx_t *gi, int n_reads, const int *qlens, c
 							mg_gchains_t **gcs, const mg_mapopt_t *opt)
 {
 	return map_batch_impl(gi, n_reads, qlens, seqs, names, gcs, opt);
+}
+
+// Fragments of several segments (read pairs) in one go: fragment f has n_seg[f] consecutive entries of qlens/seqs/gcs starting at
+// seg_off[f] = n_seg[0] + ... + n_seg[f-1]; gcs[seg_off[f]] receives the result of the concatenated fragment and the other
+// entries NULL, exactly what worker_for() leaves behind without MG_M_INDEPEND_SEG (gmap.c:46-48).  names[f] is per fragment.
+extern "C" int mg_map_batch_frag(const mg_idx_t *gi, int n_frag, const int *n_seg, const int *qlens, const char *const *seqs, const char *const *names,
+								 mg_gchains_t **gcs, const mg_mapopt_t *opt)
+{
+	if (n_frag <= 0) return 0;
+	bool single = true;
+	int64_t n_tot = 0;
+	for (int f = 0; f < n_frag; ++f) { if (n_seg[f] != 1) single = false; n_tot += n_seg[f] > 0? n_seg[f] : 0; }
+	if (single) return map_batch_impl(gi, n_frag, qlens, seqs, names, gcs, opt);
+	for (int64_t i = 0; i < n_tot; ++i) gcs[i] = 0;
+	std::vector<std::string> cat((size_t)n_frag);
+	std::vector<int> qsum((size_t)n_frag);
+	std::vector<const char*> sq((size_t)n_frag);
+	std::vector<int32_t> seg_off((size_t)n_frag + 1), seg_len;
+	std::vector<mg_gchains_t*> res((size_t)n_frag, (mg_gchains_t*)0);
+	seg_len.reserve((size_t)n_tot);
+	int64_t off = 0;
+	for (int f = 0; f < n_frag; ++f) {
+		seg_off[(size_t)f] = (int32_t)seg_len.size();
+		const int ns = n_seg[f] > 0 && n_seg[f] <= 255? n_seg[f] : 0; // more than MG_MAX_SEG segments: no result (map-algo.c:359)
+		for (int j = 0; j < ns; ++j) {
+			const int l = qlens[off + j] > 0? qlens[off + j] : 0;
+			seg_len.push_back(l);
+			if (l > 0) cat[(size_t)f].append(seqs[off + j], (size_t)l);
+		}
+		qsum[(size_t)f] = (int)cat[(size_t)f].size(), sq[(size_t)f] = cat[(size_t)f].data();
+		off += n_seg[f] > 0? n_seg[f] : 0;
+	}
+	seg_off[(size_t)n_frag] = (int32_t)seg_len.size();
+	int rc = map_batch_impl(gi, n_frag, qsum.data(), sq.data(), names, res.data(), opt, &seg_off, &seg_len);
+	if (rc < 0) return rc;
+	off = 0;
+	for (int f = 0; f < n_frag; ++f) { if (n_seg[f] > 0) gcs[off] = res[(size_t)f]; off += n_seg[f] > 0? n_seg[f] : 0; }
+	return 0;
 }
 
 extern "C" void mg_map_frag(const mg_idx_t *gi, int n_segs, const int *qlens, const char **seqs, mg_gchains_t **gcs, mg_tbuf_t *b, const mg_mapopt_t *opt, const char *qname)

@@ -283,11 +283,13 @@ def case_short_reads(lib, workdir, n_pairs=60):
         f.restype = None
         f.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_char_p), C.POINTER(C.POINTER(capi.mg_gchains_t)), C.c_void_p, C.c_void_p, C.c_char_p]
     n_mapped = 0
+    frags, per_frag = [], []
     for nm, s in zip(names, seqs):
         if rng.random() < 0.7:  # a pair: 150 bases from each end, the mate reverse-complemented
             parts = [s[:150], s[-150:].translate(comp)[::-1]]
         else:
             parts = [s[:rng.choice([100, 150, 250])]]
+        frags.append((nm, parts))
         n_seg = len(parts)
         ql = (C.c_int * n_seg)(*[len(x) for x in parts])
         sq = (C.c_char_p * n_seg)(*parts)
@@ -299,8 +301,25 @@ def case_short_reads(lib, workdir, n_pairs=60):
             lb.mg_gchain_free(gcs[0])
         d = T.diff_results(res[0], res[1])
         assert d is None, (nm, [len(x) for x in parts], d)
+        per_frag.append(res[0])
         if res[0] and res[0]["n_gc"] > 0:
             n_mapped += 1
     assert n_mapped >= n_pairs // 2, n_mapped
+    # the same fragments in one call of the batch entry point
+    flat = [x for _, parts in frags for x in parts]
+    n_tot = len(flat)
+    nseg = (C.c_int * len(frags))(*[len(parts) for _, parts in frags])
+    ql = (C.c_int * n_tot)(*[len(x) for x in flat])
+    sq = (C.c_char_p * n_tot)(*flat)
+    nms = (C.c_char_p * len(frags))(*[nm for nm, _ in frags])
+    gcs = (C.POINTER(capi.mg_gchains_t) * n_tot)()
+    assert lib.mg_map_batch_frag(gi_e, len(frags), nseg, ql, sq, nms, gcs, C.byref(mo)) == 0, lib.mgb_last_error()
+    off = 0
+    for f, (nm, parts) in enumerate(frags):
+        assert all(not gcs[off + j] for j in range(1, len(parts)))
+        d = T.diff_results(per_frag[f], T.gchains_to_py(gcs[off]))
+        assert d is None, (nm, d)
+        off += len(parts)
+    lib.mgb_free_batch(n_tot, gcs)
     ref.mg_tbuf_destroy(b_r), lib.mg_tbuf_destroy(b_e)
     lib.mg_idx_destroy(gi_e), ref.mg_idx_destroy(gi_r)

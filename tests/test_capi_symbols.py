@@ -16,7 +16,7 @@ def declared_symbols():
 
 def test_header_lists_the_reference_entry_points():
     syms = declared_symbols()
-    for s in ("mg_index", "mg_idx_destroy", "mg_tbuf_init", "mg_tbuf_destroy", "mg_map", "mg_map_frag", "mg_map_batch", "mg_gchain_free"):
+    for s in ("mg_index", "mg_idx_destroy", "mg_tbuf_init", "mg_tbuf_destroy", "mg_map", "mg_map_frag", "mg_map_batch", "mg_map_batch_frag", "mg_gchain_free"):
         assert s in syms
 
 

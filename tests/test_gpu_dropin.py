@@ -23,3 +23,27 @@ def test_dropin_binary_matches_reference(workdir):
     assert got == want, cases.first_diff(got, want)
     got = subprocess.run([DROPIN, "-cx", "lr", gfa, os.path.join(T.FIX, "MT-orangA.fa")], check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
     assert got == cases.golden("c1_MT_orangA.lr.gaf")
+
+
+REF_BIN = os.path.join(T.REPO, "oracle", "_ref", "minigraph")
+
+
+@pytest.mark.skipif(not (os.path.exists(DROPIN) and os.path.exists(REF_BIN)), reason="oracle/_ref binaries not built")
+def test_dropin_binary_paired_short_reads(workdir):
+    """-x sr with two query files: read pairs become two-segment fragments (gmap.c:70-97) and reach the GPU through
+    mg_map_batch_frag(); same bytes as the reference binary"""
+    hap, frags = os.path.join(workdir, "mt.hap.fa"), os.path.join(workdir, "mt.frag.fa")
+    T.sim_mt_haps(hap)
+    T.sim_reads(hap, frags, 300, 500, "hifi", 67)
+    names, seqs = T.read_fasta(frags)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    r1, r2 = os.path.join(workdir, "sr_1.fa"), os.path.join(workdir, "sr_2.fa")
+    with open(r1, "wb") as f1, open(r2, "wb") as f2:
+        for nm, s in zip(names, seqs):
+            f1.write(b">" + nm + b"/1\n" + s[:150] + b"\n")
+            f2.write(b">" + nm + b"/2\n" + s[-150:].translate(comp)[::-1] + b"\n")
+    gfa = os.path.join(T.FIX, "MT.gfa")
+    want = subprocess.run([REF_BIN, "-x", "sr", "-t", "4", gfa, r1, r2], check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
+    got = subprocess.run([DROPIN, "-x", "sr", "-t", "4", gfa, r1, r2], check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
+    assert len(want) > 1000
+    assert got == want, cases.first_diff(got, want)
