@@ -15,6 +15,7 @@
 #include <thread>
 #include <mutex>
 #include <functional>
+#include <unordered_map>
 #include "mgb_hostpool.h"
 
 #include "../../include/mgb200.h"
@@ -500,6 +501,8 @@ struct Model {
 	IndexDev ix;
 	std::vector<void*> dev_ptrs;
 	// per-model scratch reused across batches
+	std::vector<int32_t> seg_name_id, seg_soff; // MG_M_NO_DIAG: the name a segment goes by (id into name_ids) and its offset there
+	std::unordered_map<std::string, int32_t> name_ids;
 	Workers W, Wbig;
 	int32_t skip1_len = INT32_MAX, skip2_len = INT32_MAX; // WFA tier routing learned from earlier batches (wfa_job_run)
 	std::vector<float> logf_tab; float *d_logf; int n_logf;
@@ -608,8 +611,18 @@ static Model *model_build(gfa_t *g, int k, int w)
 		a.w = g->arc[i].w, a.lv = (uint32_t)g->arc[i].v_lv, a.rank = g->arc[i].rank, a.ow = g->arc[i].ow;
 		M->arc[i] = a;
 	}
+	M->seg_name_id.resize(n_seg), M->seg_soff.resize(n_seg);
+	for (uint32_t i = 0; i < n_seg; ++i) { // reference: map-algo.c:168-174
+		const gfa_seg_t *s = &g->seg[i];
+		const bool stable = s->snid >= 0 && g->sseq;
+		const char *gname = stable? g->sseq[s->snid].name : s->name;
+		auto it = M->name_ids.emplace(std::string(gname? gname : ""), (int32_t)M->name_ids.size()).first;
+		M->seg_name_id[i] = it->second, M->seg_soff[i] = stable? s->soff : 0;
+	}
 	// upload the graph
 	M->g.n_seg = (int32_t)n_seg;
+	M->g.seg_name_id = dalloc_copy(M->seg_name_id), M->dev_ptrs.push_back((void*)M->g.seg_name_id);
+	M->g.seg_soff = dalloc_copy(M->seg_soff), M->dev_ptrs.push_back((void*)M->g.seg_soff);
 	M->g.seg_len = dalloc_copy(M->seg_len), M->dev_ptrs.push_back((void*)M->g.seg_len);
 	M->g.vseq_off = dalloc_copy(M->vseq_off), M->dev_ptrs.push_back((void*)M->g.vseq_off);
 	M->g.seq = dalloc_copy(M->seq), M->dev_ptrs.push_back((void*)M->g.seq);
@@ -924,13 +937,14 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 		dsync();
 		S.t_pack_ms = t_pack;
 	}
-	size_t small_dev = (size_t)n_reads * (8 + 4 + 4 + 4) + 4096 + 1024;
+	size_t small_dev = (size_t)n_reads * (8 + 4 + 4 + 4 + 4) + 4096 + 1024;
 	char *ds = (char*)sl.d_small.ensure(small_dev);
 	uint64_t *d_seq_off = (uint64_t*)ds;
 	int32_t *d_seq_len = (int32_t*)(d_seq_off + n_reads);
 	uint32_t *d_name_hash = (uint32_t*)(d_seq_len + n_reads);
 	int32_t *d_list_buf = (int32_t*)(d_name_hash + n_reads); // n_reads entries: read list of the retry pass
-	char *dsm = (char*)(((uintptr_t)(d_list_buf + n_reads) + 255) & ~(uintptr_t)255);
+	int32_t *d_self_id = d_list_buf + n_reads; // n_reads entries, MG_M_NO_DIAG only
+	char *dsm = (char*)(((uintptr_t)(d_self_id + n_reads) + 255) & ~(uintptr_t)255);
 	unsigned int *d_next = (unsigned int*)dsm;
 	unsigned int *d_jobq_n = d_next + 4;
 	unsigned int *d_next2 = d_next + 8, *d_nbig = d_next + 9;
@@ -939,6 +953,13 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	unsigned int *d_tier_hist = (unsigned int*)((char*)(d_pools + 16) + 64); // 32 x 4 counters behind the pool headers
 	h2d(d_seq_off, seq_off, (size_t)n_reads * 16); // seq_off, seq_len and name_hash are contiguous on both sides
 	tm_h2d.stop();
+	const bool no_diag = (o.flag & F_NO_DIAG) != 0;
+	if (no_diag) { // which segment name, if any, is the read's own (exact string match on the host)
+		std::vector<int32_t> self((size_t)n_reads, -1);
+		for (int i = 0; i < n_reads; ++i)
+			if (names && names[i]) { auto it = M->name_ids.find(names[i]); if (it != M->name_ids.end()) self[(size_t)i] = it->second; }
+		h2d(d_self_id, self.data(), sizeof(int32_t) * (size_t)n_reads);
+	}
 	int32_t *d_seg_off = 0, *d_seg_len = 0; // multi-segment fragments only (mg_map_frag with n_segs > 1)
 	if (seg_off && seg_len) {
 		d_seg_off = (int32_t*)sl.d_segs.ensure(sizeof(int32_t) * (seg_off->size() + seg_len->size()));
@@ -982,7 +1003,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 		memset(&L, 0, sizeof(L));
 		L.c.g = M->g, L.c.ix = M->ix, L.c.opt = o;
 		L.c.b.n_reads = n_reads, L.c.b.seq = d_seq, L.c.b.seq_off = d_seq_off, L.c.b.seq_len = d_seq_len, L.c.b.name_hash = d_name_hash;
-		L.c.b.seg_off = d_seg_off, L.c.b.seg_len = d_seg_len;
+		L.c.b.seg_off = d_seg_off, L.c.b.seg_len = d_seg_len, L.c.b.self_id = no_diag? d_self_id : 0;
 		L.c.meta = d_meta;
 		L.c.pool_anchor = &d_pools[P_ANCHOR], L.c.anchor = (u128*)d_buf[P_ANCHOR];
 		L.c.pool_minipos = &d_pools[P_MINIPOS], L.c.minipos = (int32_t*)d_buf[P_MINIPOS];
@@ -1258,7 +1279,6 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 	mgb_stats_t &S = M->stats;
 	memset(&S, 0, sizeof(S));
 	for (int i = 0; i < n_reads; ++i) gcs[i] = 0;
-	if (opt->flag & F_NO_DIAG) { set_error("MG_M_NO_DIAG (-D, skip self diagonal seeds by sequence name) is not supported by the GPU engine"); return MGB_E_UNSUPPORTED; }
 	if (n_reads <= 0) return 0;
 	double t0 = now_ms();
 	int32_t max_qlen = 0;

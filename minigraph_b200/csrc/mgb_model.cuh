@@ -19,6 +19,9 @@ struct GraphDev {
 	const char *seq;           // upper-case ASCII; every segment stored on both strands (reference: gfa-ed.c:24-42)
 	const uint64_t *arc_idx;   // [2*n_seg] start<<32 | n   (reference: gfa_t::idx)
 	const DevArc *arc;
+	// for MG_M_NO_DIAG (map-algo.c:167-178): the id of the name a segment goes by (its stable sequence if it has one) and its offset there
+	const int32_t *seg_name_id; // [n_seg]
+	const int32_t *seg_soff;    // [n_seg], 0 when the segment is named by itself
 };
 
 MG_HD inline int32_t g_vlen(const GraphDev &g, uint32_t v) { return g.seg_len[v >> 1]; }
@@ -115,6 +118,7 @@ struct BatchDev {
 	const uint64_t *seq_off;    // [n_reads]
 	const int32_t *seq_len;     // [n_reads]
 	const uint32_t *name_hash;  // [n_reads] kh_hash_str(qname) computed by the host, 0 if no name
+	const int32_t *self_id;     // [n_reads] MG_M_NO_DIAG only: GraphDev::seg_name_id value the read's name equals, or -1 (NULL otherwise)
 	// multi-segment fragments (paired reads; reference: map-algo.c:34-45,356-360): a read's sequence is the concatenation of its
 	// segments, seg_len[seg_off[r] .. seg_off[r+1]) their lengths.  NULL for the usual batch of single-segment reads.
 	const int32_t *seg_off;     // [n_reads + 1]

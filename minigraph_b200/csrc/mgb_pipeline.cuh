@@ -142,7 +142,12 @@ MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A, int lane)
 		if (rc < 0) return rc;
 		t2 = prof_clock();
 	} else {
-		expand_seeds_w(c.g, n_m, sm, a_off, a, lane);
+		if ((c.opt.flag & F_NO_DIAG) && c.b.self_id) { // reference: map-algo.c:167 (the heap variant above has no such filter)
+			int32_t kept = 0;
+			if (lane == 0) kept = (int32_t)expand_seeds_nodiag(c.g, n_m, sm, c.b.self_id[rid], a);
+			n_a = warp_bcast_i32(kept, 0);
+			if (lane == 0) m.n_a = (int32_t)n_a, m.n_seed0 = (int32_t)n_a;
+		} else expand_seeds_w(c.g, n_m, sm, a_off, a, lane);
 		warp_sync();
 		t2 = prof_clock();
 		MGB_TRY(radix_sort_128x_w(A, a, n_a, lane));

@@ -402,4 +402,28 @@ MG_HD inline int expand_seeds_heap(Arena &A, const GraphDev &g, int n_m, const S
 	return n_for + n_rev == n_a? 0 : MGB_E_INTERNAL;
 }
 
+// expand_seeds() with the self-diagonal filter of MG_M_NO_DIAG (reference: map-algo.c:160-188): a seed is dropped when the
+// read carries the name its segment goes by and sits at its own position there.  One lane; returns the number of seeds kept.
+MG_HD inline int64_t expand_seeds_nodiag(const GraphDev &g, int n_m, const SeedMatch *m, int32_t self_id, u128 *a)
+{
+	int64_t n = 0;
+	for (int i = 0; i < n_m; ++i) {
+		const SeedMatch *q = &m[i];
+		const uint64_t *r = q->cr;
+		for (uint32_t k = 0; k < q->n; ++k) {
+			uint64_t rk = r[k];
+			int32_t rpos = (int32_t)((uint32_t)rk >> 1);
+			if (self_id >= 0 && g.seg_name_id[rk >> 32] == self_id && (uint32_t)(g.seg_soff[rk >> 32] + (int32_t)(uint32_t)rk) == q->q_pos) continue;
+			u128 *p = &a[n++];
+			if ((rk & 1) == (q->q_pos & 1)) p->x = rk >> 32 << 33 | (uint64_t)(uint32_t)rpos;
+			else p->x = rk >> 32 << 33 | 1ULL << 32 | (uint64_t)(uint32_t)(g.seg_len[rk >> 32] - (rpos + 1 - (int32_t)q->q_span) - 1);
+			p->y = (uint64_t)q->q_span << 32 | (uint64_t)(q->q_pos >> 1);
+			p->y |= (uint64_t)q->seg_id << SEED_SEG_SHIFT;
+			if (q->is_tandem) p->y |= SEED_TANDEM;
+			p->y |= (uint64_t)(q->n < 255? q->n : 255) << SEED_OCC_SHIFT;
+		}
+	}
+	return n;
+}
+
 } // namespace mgb

@@ -323,3 +323,33 @@ def case_short_reads(lib, workdir, n_pairs=60):
     lib.mgb_free_batch(n_tot, gcs)
     ref.mg_tbuf_destroy(b_r), lib.mg_tbuf_destroy(b_e)
     lib.mg_idx_destroy(gi_e), ref.mg_idx_destroy(gi_r)
+
+
+def case_no_diag(lib, workdir):
+    """MG_M_NO_DIAG (-D): a read that carries the name of the sequence it comes from loses the seeds on its own diagonal
+    (map-algo.c:167-178): same result fields as the reference, for a full self copy, a prefix, an inner piece and a stranger"""
+    fa = os.path.join(T.FIX, "MT-human.fa")
+    gname, hs = T.read_fasta(fa)
+    full = hs[0]
+    names = [gname[0], gname[0], gname[0], b"someone_else", gname[0] + b"x"]
+    seqs = [full, full[:6000], full[3000:9000], full[:6000], full[:6000]]
+    import minigraph_b200.options as options_mod
+    orig = options_mod.opt_set
+
+    def with_flag(preset=None, cigar=True):
+        io, mo = orig(preset, cigar)
+        mo.flag |= 0x400000  # MG_M_NO_DIAG (minigraph.h:27)
+        return io, mo
+    options_mod.opt_set = with_flag
+    T.options.opt_set = with_flag
+    try:
+        got, _, _ = T.map_with_engine(lib, fa, names, seqs, "asm")
+        want, _ = T.map_with_ref(fa, names, seqs, "asm")
+    finally:
+        options_mod.opt_set = orig
+        T.options.opt_set = orig
+    for i, (a, b) in enumerate(zip(want, got)):
+        d = T.diff_results(a, b)
+        assert d is None, (i, d)
+    plain, _ = T.map_with_ref(fa, names[:2], seqs[:2], "asm")
+    assert T.diff_results(plain[1], want[1]) is not None  # the flag did change something for the self-named prefix

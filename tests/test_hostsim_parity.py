@@ -42,6 +42,11 @@ def test_short_read_preset(lib, workdir):
     cases.case_short_reads(lib, workdir)
 
 
+@pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
+def test_no_diag_flag(lib, workdir):
+    cases.case_no_diag(lib, workdir)
+
+
 def test_learned_tier_routing_keeps_results(lib, workdir):
     cases.case_tier_routing(lib, workdir)
 
