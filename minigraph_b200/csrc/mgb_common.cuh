@@ -85,6 +85,29 @@ MG_D inline int32_t warp_excl_prefix_max_i32(int32_t x, int lane)
 }
 MG_D inline int mask_rank(uint32_t mask, int lane) { return __popc(mask & ((1u << lane) - 1u)); } // set bits below `lane`
 MG_D inline int mask_count(uint32_t mask) { return __popc(mask); }
+#elif defined(MGB_SIM_LANES)
+// test infrastructure: the lanes of a warp as fibres on one CPU thread (mgb_simlanes.h)
+} // namespace mgb
+#include "mgb_simlanes.h"
+namespace mgb {
+#define MGB_W MGB_SIM_LANES
+inline void warp_sync() { uint64_t o[32]; sim::exchange(0, o, 1); }
+inline int warp_any(int pred) { uint64_t o[32]; sim::exchange(pred != 0, o, 2); for (int i = 0; i < MGB_W; ++i) if (o[i]) return 1; return 0; }
+inline int32_t warp_bcast_i32(int32_t x, int src) { uint64_t o[32]; sim::exchange((uint64_t)(uint32_t)x, o, 3); return (int32_t)(uint32_t)o[src]; }
+inline uint64_t warp_bcast_u64(uint64_t x, int src) { uint64_t o[32]; sim::exchange(x, o, 4); return o[src]; }
+inline int32_t warp_min_i32(int32_t x) { uint64_t o[32]; sim::exchange((uint64_t)(uint32_t)x, o, 5); int32_t r = x; for (int i = 0; i < MGB_W; ++i) if ((int32_t)(uint32_t)o[i] < r) r = (int32_t)(uint32_t)o[i]; return r; }
+inline int32_t warp_max_i32(int32_t x) { uint64_t o[32]; sim::exchange((uint64_t)(uint32_t)x, o, 6); int32_t r = x; for (int i = 0; i < MGB_W; ++i) if ((int32_t)(uint32_t)o[i] > r) r = (int32_t)(uint32_t)o[i]; return r; }
+inline int32_t warp_sum_i32(int32_t x) { uint64_t o[32]; sim::exchange((uint64_t)(uint32_t)x, o, 7); uint32_t r = 0; for (int i = 0; i < MGB_W; ++i) r += (uint32_t)o[i]; return (int32_t)r; }
+inline uint32_t warp_ballot(int pred) { uint64_t o[32]; sim::exchange(pred != 0, o, 8); uint32_t m = 0; for (int i = 0; i < MGB_W; ++i) if (o[i]) m |= 1u << i; return m; }
+inline uint64_t warp_or_u64(uint64_t x) { uint64_t o[32]; sim::exchange(x, o, 9); uint64_t r = 0; for (int i = 0; i < MGB_W; ++i) r |= o[i]; return r; }
+inline uint64_t warp_and_u64(uint64_t x) { uint64_t o[32]; sim::exchange(x, o, 10); uint64_t r = ~0ULL; for (int i = 0; i < MGB_W; ++i) r &= o[i]; return r; }
+inline void lane_atomic_inc(int32_t *p) { ++*p; }
+inline uint64_t warp_incl_scan_max_u64(uint64_t x, int lane) { uint64_t o[32]; sim::exchange(x, o, 11); uint64_t r = o[0]; for (int i = 1; i <= lane; ++i) if (o[i] > r) r = o[i]; return r; }
+inline uint64_t warp_shfl_up1_u64(uint64_t x) { uint64_t o[32]; sim::exchange(x, o, 12); const int l = sim::lane(); return l > 0? o[l - 1] : x; }
+inline int32_t warp_incl_scan_i32(int32_t x, int lane) { uint64_t o[32]; sim::exchange((uint64_t)(uint32_t)x, o, 13); uint32_t r = 0; for (int i = 0; i <= lane; ++i) r += (uint32_t)o[i]; return (int32_t)r; }
+inline int32_t warp_excl_prefix_max_i32(int32_t x, int lane) { uint64_t o[32]; sim::exchange((uint64_t)(uint32_t)x, o, 14); int32_t r = INT32_MIN; for (int i = 0; i < lane; ++i) if ((int32_t)(uint32_t)o[i] > r) r = (int32_t)(uint32_t)o[i]; return r; }
+inline int mask_rank(uint32_t mask, int lane) { return __builtin_popcount(mask & ((1u << lane) - 1u)); }
+inline int mask_count(uint32_t mask) { return __builtin_popcount(mask); }
 #else
 #define MGB_W 1
 inline void warp_sync() {}

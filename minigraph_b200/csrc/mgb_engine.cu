@@ -460,7 +460,24 @@ static void launch_stage(LaunchArgs &L, const Workers &W, int warps_override = 0
 	for (int it = 0; it < L.n_work; ++it) {
 		int item = L.rid_list? L.rid_list[it] : it;
 		A.top = 0;
-		int rc = run_stage<STAGE>(L, item, A, 0, MGB_IS_WARP(STAGE)? sim_smem.data() : 0);
+		int rc;
+#if MGB_W > 1
+		if (MGB_IS_WARP(STAGE)) { // all lanes of the simulated warp enter, each with its own copy of the arena header (as in registers on the device)
+			int rcs[MGB_W];
+			uint64_t peaks[MGB_W];
+			sim::tag()[0] = STAGE, sim::tag()[1] = item;
+			sim::run_warp(MGB_W, [&](int lane) {
+				Arena Al = A;
+				rcs[lane] = run_stage<STAGE>(L, item, Al, lane, sim_smem.data());
+				peaks[lane] = Al.peak;
+			});
+			rc = rcs[0];
+			for (int l = 1; l < MGB_W; ++l) if (rcs[l] != rc) { set_error("simulated warp: lanes returned different codes from one stage"); abort(); }
+			for (int l = 0; l < MGB_W; ++l) if (peaks[l] > A.peak) A.peak = peaks[l];
+		} else
+#endif
+		rc = run_stage<STAGE>(L, item, A, 0, MGB_IS_WARP(STAGE)? sim_smem.data() : 0);
+		if (rc < 0 && getenv("MGB_HOSTSIM_TRACE")) fprintf(stderr, "[hostsim] stage %d item %d failed with %d\n", STAGE, item, rc);
 		if (rc < 0) stage_fail<STAGE>(L, item, rc);
 	}
 	if (W.peak && A.peak > W.peak[0]) W.peak[0] = A.peak;
@@ -1484,7 +1501,11 @@ extern "C" int mgb_test_wfa(const char *ts, int tl, const char *qs, int ql, int6
 	t.out = (int32_t*)dmalloc(sizeof(int32_t) * 4);
 	t.arena = (char*)dmalloc(t.arena_bytes);
 #ifdef MGB_HOSTSIM
+#if MGB_W > 1
+	sim::run_warp(MGB_W, [&](int lane) { test_wfa_body(t, lane); });
+#else
 	test_wfa_body(t, 0);
+#endif
 #else
 	k_test_wfa<<<1, 32>>>(t);
 	CUDA_OK(cudaGetLastError());

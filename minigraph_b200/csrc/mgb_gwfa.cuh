@@ -496,7 +496,6 @@ struct GwfShared {
 	Arena A;
 	GwfState z;
 	GwfResult r;
-	int32_t rc, go, dedup;
 };
 
 // one run of n consecutive diagonals of one vertex (gwf_extend_batch); all lanes enter
@@ -515,14 +514,15 @@ MG_HD inline int gwf_extend_batch_w(GwfShared *sh, int32_t n, GwfDiag *a, int la
 		p.k = k;
 		a[j] = p;
 	}
+	int rc = 0; // codes travel by shuffle, not through shared memory: a flag there could be rewritten before a slow lane has read it
 	if (lane == 0) {
-		int rc = avec_reserve(sh->A, z.B, z.B.n + n + 2);
+		rc = avec_reserve(sh->A, z.B, z.B.n + n + 2);
 		if (rc == 0) rc = avec_reserve(sh->A, z.Q, z.Q.n + n);
 		if (rc == 0) rc = avec_reserve(sh->A, z.tmp, z.tmp.n + n + 2);
-		sh->rc = rc;
 	}
 	warp_sync();
-	if (sh->rc < 0) return sh->rc;
+	rc = warp_bcast_i32(rc, 0);
+	if (rc < 0) return rc;
 	GwfDiag *b = &z.B.a[z.B.n];
 	GwfDiag *Q = z.Q.a;
 	GwfIntv *T = z.tmp.a;
@@ -701,6 +701,7 @@ MG_HD inline int gwf_dedup_w(GwfShared *sh, int lane)
 	Arena &A = sh->A;
 	// forbidden intervals: fold the new ones in (nothing changes when there are no new ones)
 	const int64_t n_old = z.intv.n, n_new = z.tmp.n;
+	int rc0 = 0;
 	if (lane == 0) {
 		int rc = 0;
 		if (n_new > 0) {
@@ -711,10 +712,11 @@ MG_HD inline int gwf_dedup_w(GwfShared *sh, int lane)
 			if (rc == 0) z.swap.n = n_old, rc = avec_reserve(A, z.intv, n_old + n_new);
 		}
 		if (rc == 0) rc = avec_reserve(A, z.ooo, z.B.n);
-		sh->rc = rc;
+		rc0 = rc;
 	}
 	warp_sync();
-	if (sh->rc < 0) return sh->rc;
+	rc0 = warp_bcast_i32(rc0, 0);
+	if (rc0 < 0) return rc0;
 	if (n_new > 0) {
 		GwfIntv *b = z.swap.a, *c = z.tmp.a, *o = z.intv.a;
 		for (int64_t i = lane; i < n_old; i += MGB_W) b[i] = o[i]; // o may have moved: avec_reserve copied the old content
@@ -789,9 +791,10 @@ MG_HD inline int gwf_dedup_w(GwfShared *sh, int lane)
 			jc += mask_count(mc), jb += mask_count(mb);
 		}
 		warp_sync();
-		if (lane == 0) sh->rc = radix_sort_exact(A, c, n_c, 8, KeyDiagVd());
+		if (lane == 0) rc0 = radix_sort_exact(A, c, n_c, 8, KeyDiagVd());
 		warp_sync();
-		if (sh->rc < 0) return sh->rc;
+		rc0 = warp_bcast_i32(rc0, 0);
+		if (rc0 < 0) return rc0;
 		for (int32_t j = lane; j < n_c; j += MGB_W) c[j].xo &= 0xfffffffeU;
 		warp_sync();
 		for (int32_t i = lane; i < n_b; i += MGB_W) a[i + gwf_lower_bound_vd(c, n_c, b[i].vd)] = b[i];
@@ -858,6 +861,7 @@ MG_HD inline int gwf_align_w(GwfShared *sh, const GraphDev &g, const GwfOpt &opt
 	GwfResult *r = &sh->r;
 	const uint64_t mark = A.top;
 	if (s_term < 0 && opt.s_term >= 0) s_term = opt.s_term;
+	int code = 0, go = 0; // replicated on every lane, set by lane 0 and spread by shuffle
 	if (lane == 0) {
 		int rc = 0;
 		z.g = &g, z.ql = ql, z.q = q, z.s = 0, z.end_tb = -1, z.q_head = 0;
@@ -872,10 +876,11 @@ MG_HD inline int gwf_align_w(GwfShared *sh, const GraphDev &g, const GwfOpt &opt
 			if (rc == 0) rc = avec_push(A, z.a, d0);
 		}
 		r->n_iter = 0, r->nv = 0, r->v = 0, r->end_v = (uint32_t)-1, r->end_off = -1, r->wlen = 0;
-		sh->rc = rc, sh->go = rc == 0 && z.a.n > 0;
+		code = rc, go = rc == 0 && z.a.n > 0;
 	}
 	warp_sync();
-	while (sh->go) {
+	code = warp_bcast_i32(code, 0), go = warp_bcast_i32(go, 0);
+	while (go) {
 		// ---- one edit-distance step (gwf_ed_extend) ----
 		if (lane == 0) {
 			r->end_v = (uint32_t)-1;
@@ -884,10 +889,11 @@ MG_HD inline int gwf_align_w(GwfShared *sh, const GraphDev &g, const GwfOpt &opt
 			u64tab_clear(z.ha);
 			z.Q.n = 0, z.q_head = 0;
 			z.B.n = 0;
-			sh->rc = avec_reserve(A, z.B, z.a.n * 2);
+			code = avec_reserve(A, z.B, z.a.n * 2);
 		}
 		warp_sync();
-		if (sh->rc < 0) break;
+		code = warp_bcast_i32(code, 0);
+		if (code < 0) break;
 		{
 			const int32_t n = (int32_t)z.a.n;
 			GwfDiag *a = z.a.a;
@@ -902,33 +908,28 @@ MG_HD inline int gwf_align_w(GwfShared *sh, const GraphDev &g, const GwfOpt &opt
 					x = e;
 				}
 			}
-			if (rc < 0) break; // sh->rc holds it
+			if (rc < 0) { code = rc; break; }
 		}
+		int dd = 0;
+		if (lane == 0) code = gwf_ed_queue(A, z, opt, v1, off1, r, &dd);
+		warp_sync();
+		code = warp_bcast_i32(code, 0), dd = warp_bcast_i32(dd, 0);
+		if (code < 0) break;
+		if (dd > 0 && (code = gwf_dedup_w(sh, lane)) < 0) break;
 		if (lane == 0) {
-			int dd = 0;
-			sh->rc = gwf_ed_queue(A, z, opt, v1, off1, r, &dd);
-			sh->dedup = dd;
+			if (dd >= 0) gwf_ed_finish(z, opt);
+			go = 1;
+			r->n_iter += z.a.n;
+			if (r->end_off >= 0 || z.a.n == 0) go = 0;
+			else if (s_term >= 0 && z.s >= s_term) go = 0;
+			else if (opt.i_term > 0 && r->n_iter > opt.i_term) go = 0;
+			else ++z.s;
 		}
 		warp_sync();
-		if (sh->rc < 0) break;
-		if (sh->dedup > 0 && gwf_dedup_w(sh, lane) < 0) break;
-		if (lane == 0) {
-			int rc = 0;
-			if (sh->dedup >= 0) gwf_ed_finish(z, opt);
-			int go = rc == 0;
-			if (go) {
-				r->n_iter += z.a.n;
-				if (r->end_off >= 0 || z.a.n == 0) go = 0;
-				else if (s_term >= 0 && z.s >= s_term) go = 0;
-				else if (opt.i_term > 0 && r->n_iter > opt.i_term) go = 0;
-				else ++z.s;
-			}
-			sh->rc = rc, sh->go = go;
-		}
-		warp_sync();
+		go = warp_bcast_i32(go, 0);
 	}
 	warp_sync();
-	if (sh->rc < 0) { const int rc = sh->rc; warp_sync(); if (lane == 0) A.top = mark; warp_sync(); return rc; }
+	if (code < 0) { if (lane == 0) A.top = mark; warp_sync(); return code; }
 	if (lane == 0) {
 		uint64_t mark_keep = mark;
 		int rc = 0;
@@ -951,10 +952,10 @@ MG_HD inline int gwf_align_w(GwfShared *sh, const GraphDev &g, const GwfOpt &opt
 		}
 		r->s = r->end_v != (uint32_t)-1? z.s : -1;
 		A.top = rc == 0? mark_keep : mark;
-		sh->rc = rc;
+		code = rc;
 	}
 	warp_sync();
-	return sh->rc;
+	return warp_bcast_i32(code, 0);
 }
 
 } // namespace mgb

@@ -511,6 +511,8 @@ MG_HD inline double warp_min_f64(double x)
 {
 #if MGB_ON_DEVICE
 	for (int o = 16; o > 0; o >>= 1) { double y = __shfl_xor_sync(0xffffffffu, x, o); x = y < x? y : x; }
+#elif defined(MGB_SIM_LANES)
+	{ uint64_t o[32], b; memcpy(&b, &x, 8); sim::exchange(b, o, 15); for (int i = 0; i < MGB_W; ++i) { double y; memcpy(&y, &o[i], 8); if (y < x) x = y; } }
 #endif
 	return x;
 }

@@ -249,6 +249,7 @@ MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A, int lane, int3
 		if (qlen - (en - st) > o.rmq_rescue_size || (float)(qlen - (en - st)) > (float)qlen * o.rmq_rescue_ratio) {
 			int64_t n2 = 0;
 			for (int32_t i = 0; i < n_lc; ++i) n2 += (int32_t)u[i];
+			warp_sync(); // u[] sits at the mark: every lane must have read it before the sort below reuses that memory
 			A.top = mark;
 			MGB_TRY(radix_sort_128x_w(A, a, n2, lane));
 			MGB_TRY(chain_rmq_w(A, o.max_gap, o.max_gap_pre, o.bw_long, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,

@@ -1,0 +1,146 @@
+// mgb_simlanes.h -- TEST INFRASTRUCTURE ONLY: a 32-lane warp on the CPU, for tests/hostsim/libmgb_hostsim32.so.
+//
+// The device code is written as warp-uniform functions (mgb_common.cuh): all lanes enter together, exchange values only
+// through the warp_* helpers and separate memory phases with warp_sync().  That makes a warp easy to run on one CPU
+// thread: every lane is a fibre (ucontext), a lane runs until it reaches a helper, parks its contribution and yields, and
+// the last lane to arrive completes the exchange.  The simulator therefore executes the very ballots, prefix scans and
+// order-preserving compactions the GPU executes, with 32 lanes, and it stops loudly when lanes do not meet at the same
+// helper (a divergence bug that would hang or corrupt on the device).  It says nothing about memory races between two
+// synchronisation points: lanes never run concurrently here.
+#pragma once
+#include <ucontext.h>
+#include <execinfo.h>
+#include <signal.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <unistd.h>
+#include <string.h>
+#include <functional>
+#include <vector>
+
+namespace mgb { namespace sim {
+
+enum { MAX_LANES = 32, STACK_BYTES = 1 << 20 };
+
+struct Warp {
+	int n = 0, cur = 0;
+	ucontext_t sched, ctx[MAX_LANES];
+	std::vector<char> stack[MAX_LANES];
+	bool done[MAX_LANES];
+	uint64_t slot[2][MAX_LANES];
+	int kind[2][MAX_LANES];       // which helper each lane entered the exchange from: lanes of a warp-uniform program use the same one
+	long gen[MAX_LANES];          // exchanges entered so far, per lane
+	long slot_gen[2] = {-1, -1};  // the exchange a buffer currently belongs to
+	int count[2] = {0, 0};        // lanes that have contributed to it
+	long ready[2] = {-1, -1};     // set to the exchange number once every lane has contributed
+	unsigned long progress = 0;
+	int dumper = -1;              // lane that asked for the dump (resumes after each printing lane), -1: the scheduler
+	bool dump = false;            // set when the warp is stuck: the waiting lanes print where they are
+	const std::function<void(int)> *fn = 0;
+};
+
+inline Warp *&current() { static thread_local Warp *w = 0; return w; }
+inline int *tag() { static thread_local int t[2] = {-1, -1}; return t; } // what the warp is working on (stage, item), for the messages
+inline int lane() { Warp *w = current(); return w? w->cur : 0; }
+
+inline void trampoline()
+{
+	Warp *w = current();
+	const int me = w->cur;
+	(*w->fn)(me);
+	w->done[me] = true, ++w->progress;
+	swapcontext(&w->ctx[me], &w->sched); // never resumed
+}
+
+inline void on_segv(int)
+{
+	Warp *w = current();
+	void *bt[32];
+	int nb = backtrace(bt, 32);
+	fprintf(stderr, "[mgb::sim] SIGSEGV in stage %d item %d lane %d\n", tag()[0], tag()[1], w? w->cur : -1);
+	backtrace_symbols_fd(bt, nb, 2);
+	_exit(139);
+}
+inline void install_segv_handler()
+{
+	static bool done = false;
+	if (done) return;
+	done = true;
+	static char alt[1 << 16];
+	stack_t ss;
+	ss.ss_sp = alt, ss.ss_size = sizeof(alt), ss.ss_flags = 0;
+	sigaltstack(&ss, 0);
+	struct sigaction sa;
+	memset(&sa, 0, sizeof(sa));
+	sa.sa_handler = on_segv, sa.sa_flags = SA_ONSTACK;
+	sigaction(SIGSEGV, &sa, 0);
+}
+
+// Run fn(lane) for lanes 0..n-1 as one warp.
+inline void run_warp(int n, const std::function<void(int)> &fn)
+{
+	if (getenv("MGB_SIM_SEGV_TRACE")) install_segv_handler();
+	Warp w;
+	w.n = n, w.fn = &fn;
+	Warp *outer = current();
+	current() = &w;
+	for (int l = 0; l < n; ++l) {
+		w.done[l] = false, w.gen[l] = 0;
+		w.stack[l].resize(STACK_BYTES);
+		getcontext(&w.ctx[l]);
+		w.ctx[l].uc_stack.ss_sp = w.stack[l].data(), w.ctx[l].uc_stack.ss_size = STACK_BYTES, w.ctx[l].uc_link = &w.sched;
+		makecontext(&w.ctx[l], (void (*)())trampoline, 0);
+	}
+	for (;;) { // round robin; a full round without any lane moving on means the lanes wait for different things
+		int alive = 0;
+		const unsigned long before = w.progress;
+		for (int l = 0; l < n; ++l) {
+			if (w.done[l]) continue;
+			++alive, w.cur = l;
+			swapcontext(&w.sched, &w.ctx[l]);
+		}
+		if (alive == 0) break;
+		if (w.progress == before) {
+			fprintf(stderr, "[mgb::sim] stage %d item %d: warp stuck, lanes did not meet at the same warp_* helper (exchange counts:", tag()[0], tag()[1]);
+			for (int l = 0; l < n; ++l) fprintf(stderr, " %ld%s", w.gen[l], w.done[l]? "x" : "");
+			fprintf(stderr, ")\n");
+			w.dump = true;
+			for (int l = 0; l < n; ++l) if (!w.done[l]) { w.cur = l; swapcontext(&w.sched, &w.ctx[l]); }
+			abort();
+		}
+	}
+	current() = outer;
+}
+
+// Every lane contributes v and receives the contributions of all lanes.
+inline void exchange(uint64_t v, uint64_t out[MAX_LANES], int kind)
+{
+	Warp *w = current();
+	if (w == 0) { fprintf(stderr, "[mgb::sim] a warp helper was called outside run_warp()\n"); abort(); }
+	const int me = w->cur;
+	const long g = w->gen[me]++;
+	const int b = (int)(g & 1);
+	if (w->slot_gen[b] != g) w->slot_gen[b] = g, w->count[b] = 0;
+	w->slot[b][me] = v;
+	w->kind[b][me] = kind;
+	++w->progress;
+	if (++w->count[b] == w->n) {
+		for (int l = 1; l < w->n; ++l)
+			if (w->kind[b][l] != w->kind[b][0]) {
+				fprintf(stderr, "[mgb::sim] stage %d item %d: lanes 0 and %d meet in different warp_* helpers (kinds %d and %d, exchange %ld)\n", tag()[0], tag()[1], l, w->kind[b][0], w->kind[b][l], g);
+				{ void *bt[24]; int nb = backtrace(bt, 24); fprintf(stderr, "[mgb::sim] lane %d is at:\n", me); backtrace_symbols_fd(bt, nb, 2); }
+				w->dump = true, w->dumper = me;
+				for (int k = 0; k < w->n; ++k) if (k != me && (k == 0 || k == l)) { w->cur = k; swapcontext(&w->ctx[me], &w->ctx[k]); }
+				abort();
+			}
+		w->ready[b] = g;
+	}
+	while (w->ready[b] != g) {
+		swapcontext(&w->ctx[me], &w->sched);
+		if (w->dump) { void *bt[24]; int nb = backtrace(bt, 24); fprintf(stderr, "[mgb::sim] lane %d waits at:\n", me); backtrace_symbols_fd(bt, nb, 2); swapcontext(&w->ctx[me], w->dumper >= 0? &w->ctx[w->dumper] : &w->sched); }
+	}
+	memcpy(out, w->slot[b], sizeof(uint64_t) * (size_t)w->n);
+}
+
+} } // namespace mgb::sim

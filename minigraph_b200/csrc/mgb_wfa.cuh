@@ -203,6 +203,7 @@ MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g,
 #define MGB_WF_RG(lo_, hi_) ((uint32_t)((hi_) + 0x8000) << 16 | (uint32_t)((lo_) + 0x8000))
 	uint32_t g0 = MGB_WF_RG(0, 0), g1 = MGB_WF_RG(1, 0), g2 = g1, g3 = g1, g4 = g1, g5 = g1, g6 = g1, g7 = g1, g8 = g1, g9 = g1, g10 = g1, g11 = g1, g12 = g1, g13 = g1, g14 = g1, g15 = g1;
 	int hit = 0, hit_noext = 0;
+	warp_sync(); // the staged sequences are complete before lane 0 reads them
 	if (lane == 0) { // score 0: the main diagonal, extended from the corner
 		E1[wfs_col<W>(0)] = F1[wfs_col<W>(0)] = E2[wfs_col<W>(0)] = F2[wfs_col<W>(0)] = (wf_cell_t)WF_NEG_INF16;
 		int32_t k0 = -1, k = -1;
@@ -675,9 +676,7 @@ MG_HD inline int wfa_exact_seq(Arena &A, int32_t step, int32_t tl, const char *t
 	MGB_ALLOC(A, qs, char, ql + WF_SEQ_PAD + 4);
 	wf_stage_seq(ts, ts_g, tl, 0xfe, 0);
 	wf_stage_seq(qs, qs_g, ql, 0xff, 0);
-#if MGB_ON_DEVICE
 	for (int32_t i = 1; i < MGB_W; ++i) { wf_stage_seq(ts, ts_g, tl, 0xfe, i); wf_stage_seq(qs, qs_g, ql, 0xff, i); } // single lane covers all strides
-#endif
 	if (step > 0) MGB_TRY(wfa_seg(A, step, tl, ts, ql, qs, &seg, &n_seg));
 	r->s = -1, r->n_cigar = 0, r->n_iter = 0, r->cigar = 0;
 	MGB_TRY(wfa_core(A, tl, ts, ql, qs, max_iter, n_seg, seg, r, cig_store, max_cigar, 0, 1));

@@ -50,6 +50,19 @@ def load_hostsim():
     return _hostsim
 
 
+_hostsim32 = None
+
+
+def load_hostsim32():
+    """the CPU build of the device code with a 32-lane warp simulated by fibres (tests/hostsim/Makefile, mgb_simlanes.h)"""
+    global _hostsim32
+    if _hostsim32 is None:
+        subprocess.check_call(["make", "-s", "-C", os.path.join(REPO, "tests", "hostsim"), "libmgb_hostsim32.so"])
+        lib = C.CDLL(os.path.join(REPO, "tests", "hostsim", "libmgb_hostsim32.so"))
+        _hostsim32 = capi.bind_engine_api(capi.bind_mapping_api(lib))
+    return _hostsim32
+
+
 def read_fasta(fn, upper=True):
     names, seqs = [], []
     cur = []
