@@ -115,6 +115,7 @@ inline void install_segv_handler()
 inline void run_warp(int n, const std::function<void(int)> &fn)
 {
 	if (getenv("MGB_SIM_SEGV_TRACE")) install_segv_handler();
+	static thread_local unsigned long long seed = getenv("MGB_SIM_SEED")? strtoull(getenv("MGB_SIM_SEED"), 0, 10) : 0;
 	Warp w;
 	w.n = n, w.fn = &fn;
 	Warp *outer = current();
@@ -127,7 +128,12 @@ inline void run_warp(int n, const std::function<void(int)> &fn)
 	for (;;) { // round robin; a full round without any lane moving on means the lanes wait for different things
 		int alive = 0;
 		const unsigned long before = w.progress;
-		for (int l = 0; l < n; ++l) {
+		int order[MAX_LANES];
+		for (int l = 0; l < n; ++l) order[l] = l;
+		if (seed) // MGB_SIM_SEED=<n>: lanes are resumed in a different random order every round (other interleavings, same results expected)
+			for (int l = n - 1; l > 0; --l) { seed = seed * 6364136223846793005ULL + 1442695040888963407ULL; int r = (int)((seed >> 33) % (unsigned)(l + 1)); int t = order[l]; order[l] = order[r], order[r] = t; }
+		for (int q = 0; q < n; ++q) {
+			const int l = order[q];
 			if (w.done[l]) continue;
 			++alive;
 			if (w.wait_gen[l] >= 0 && w.ready[w.wait_gen[l] & 1] != w.wait_gen[l]) continue; // still waiting for the others
