@@ -3,7 +3,9 @@
 The one-lane simulator (test_hostsim_parity.py) checks control flow; this build executes the ballots, prefix scans,
 order-preserving compactions and lane-0 hand-overs exactly as a warp does -- with the most adversarial schedule there is
 (a lane runs alone until it needs the others) -- and stops when lanes do not meet at the same helper.  Small inputs:
-a simulated exchange costs 32 context switches."""
+a simulated exchange costs 32 context switches, and every lane repeats the scalar work.  MGB_SIM_SEED=<n> in the environment
+resumes the lanes in a different random order every round (other interleavings, the same results);
+MGB_SIM_SEGV_TRACE=1 prints stage, item, lane and a backtrace on a crash."""
 import os
 
 import pytest
