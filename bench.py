@@ -145,7 +145,7 @@ def main():
     ap.add_argument("--reads", type=int, default=N_READS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c3"], help="c2: test/MT.gfa <- 10 kb reads (the metric's configuration, default); c3: synthetic MHC-scale rGFA <- 15 kb reads")
-    ap.add_argument("--check", type=int, default=0, help="also compare the GAF text of the first N reads with the reference binary (oracle/_ref/minigraph), byte for byte")
+    ap.add_argument("--check", type=int, default=1000, help="after the timed region, compare the GAF text of the first N reads with the reference binary (oracle/_ref/minigraph), byte for byte; 0 to skip")
     a = ap.parse_args()
     # stdout carries exactly one JSON line: everything libraries print to fd 1 (NCCL's version banner, ...) goes to stderr instead
     sys.stdout.flush()
