@@ -20,6 +20,7 @@
 
 #include "../../include/mgb200.h"
 #include "mgb_galign.cuh"
+#include "mgb_wfa_cta.cuh"
 
 #ifndef MGB_HOSTSIM
 #include <cuda_runtime.h>
@@ -45,6 +46,8 @@ extern int p_slots; extern int64_t p_min_slot_reads;
 static int64_t p_slot_workers = 0;
 static int64_t p_tier_learn = 1;       // 0: every gap tries every tier (no routing)
 static int64_t p_side_warps = 1;       // warps per SM of that side launch
+static int g_test_wfa_cta_taken = 0;   // gaps of mgb_test_wfa() answered by the block function so far (mgb_set_param("cta_taken", v) returns it and sets it to v)
+static int64_t p_cta_len = 0;          // > 0: tier-3 gaps with tl + ql at or above this are first offered to a block-per-gap kernel (k_wfa_cta); not yet measured
 static int64_t p_big_len = 0;          // > 0: gaps with tl or ql at or above this go to a tier-3 launch on a second stream beside tiers 1/2
                                        // (measured on B200 with 384: tier 3 -3 ms, tier 1 +7 ms from the shared SMs -- off)
 
@@ -65,6 +68,8 @@ extern "C" int mgb_set_param(const char *key, int64_t value)
 	else if (!strcmp(key, "slots")) p_slots = (int)value;
 	else if (!strcmp(key, "slot_workers")) p_slot_workers = value;
 	else if (!strcmp(key, "big_len")) p_big_len = value;
+	else if (!strcmp(key, "cta_len")) p_cta_len = value;
+	else if (!strcmp(key, "cta_taken")) { int n = g_test_wfa_cta_taken; g_test_wfa_cta_taken = (int)value; return n; } // test hook counter: returns it, then sets it
 	else if (!strcmp(key, "side_warps")) p_side_warps = value;
 	else if (!strcmp(key, "tier_learn")) p_tier_learn = value;
 	else if (!strcmp(key, "min_slot_reads")) p_min_slot_reads = value;
@@ -193,7 +198,7 @@ MG_HD inline int run_stage(const LaunchArgs &L, int item, Arena &A, int lane, in
 	if (STAGE == 9) return stage_gchain_gen(L.c, L.routs, item, A);
 	if (STAGE == 4) return wfa_job_run(A, L.c, L.job_start + item, lane, smem, 1);
 	if (STAGE == 6) return wfa_job_run(A, L.c, L.c.jobq[0][item], lane, smem, 2);
-	if (STAGE == 7) return wfa_job_run(A, L.c, L.c.jobq[1][item], lane, smem, 3);
+	if (STAGE == 7) return L.c.jobq[1][item] < 0? 0 : wfa_job_run(A, L.c, L.c.jobq[1][item], lane, smem, 3); // < 0: struck by k_wfa_cta
 	if (STAGE == 3) { // sketch one graph segment for the index (reference: index.c:200-205)
 		AVec<u128> mv;
 		avec_init(mv);
@@ -493,6 +498,71 @@ static void launch_stage(LaunchArgs &L, const Workers &W, int warps_override = 0
 	if (MGB_IS_WARP(STAGE)) L.thread_mode = 0;
 	if (L.thread_mode) smem = 0;
 	kern<<<blocks, threads, smem, t_stream>>>(L);
+	CUDA_OK(cudaGetLastError());
+#endif
+}
+
+// Block-per-gap pass over the tier-3 queue (mgb_wfa_cta.cuh): every block pulls queue entries, aligns the long ones with all
+// its threads and strikes them from the queue; the warp kernel (stage 7) that follows does the rest.
+#ifndef MGB_HOSTSIM
+__global__ void __launch_bounds__(MGB_CTA_THREADS) k_wfa_cta(LaunchArgs L)
+{
+	__shared__ CtaScratch scr;
+	__shared__ int s_item;
+	const int tid = threadIdx.x, warps = MGB_CTA_THREADS / 32;
+	Arena A;
+	arena_init(A, L.arena_base + (uint64_t)blockIdx.x * warps * L.arena_bytes, (uint64_t)warps * L.arena_bytes); // the arenas of its warps, as one
+	CtaCtx cx;
+	cta_init(cx, &scr, tid);
+	for (;;) {
+		if (tid == 0) s_item = (int)atomicAdd(L.c.next_read, 1u);
+		__syncthreads();
+		int item = s_item;
+		__syncthreads();
+		if (item >= L.n_work) break;
+		if (L.rid_list) item = L.rid_list[item];
+		A.top = 0;
+		wfa_job_cta(A, cx, L.c, item, tid);
+		__syncthreads();
+	}
+	if (tid == 0 && L.arena_peak && A.peak > L.arena_peak[blockIdx.x * warps]) L.arena_peak[blockIdx.x * warps] = A.peak;
+}
+#endif
+static void launch_wfa_cta(LaunchArgs &L, const Workers &W)
+{
+	L.arena_base = W.arena, L.arena_bytes = W.arena_bytes, L.arena_peak = W.peak;
+	unsigned int zero = 0;
+	h2d(L.c.next_read, &zero, sizeof(zero));
+#ifdef MGB_HOSTSIM
+	Arena A;
+	arena_init(A, W.arena, W.arena_bytes);
+	CtaScratch scr;
+	for (int it = 0; it < L.n_work; ++it) {
+		const int item = L.rid_list? L.rid_list[it] : it;
+		A.top = 0;
+#if MGB_W > 1
+		uint64_t peaks[MGB_CTA_T];
+		sim::tag()[0] = 10, sim::tag()[1] = item;
+		sim::run_warp(MGB_CTA_T, [&](int tid) {
+			Arena Al = A;
+			CtaCtx cx;
+			cta_init(cx, &scr, tid);
+			wfa_job_cta(Al, cx, L.c, item, tid);
+			peaks[tid] = Al.peak;
+		});
+		for (int l = 0; l < MGB_CTA_T; ++l) if (peaks[l] > A.peak) A.peak = peaks[l];
+#else
+		CtaCtx cx;
+		cta_init(cx, &scr, 0);
+		wfa_job_cta(A, cx, L.c, item, 0);
+#endif
+	}
+	if (W.peak && A.peak > W.peak[0]) W.peak[0] = A.peak;
+#else
+	const int warps = MGB_CTA_THREADS / 32;
+	if (W.n_workers < warps) return; // a block works in the arenas of its warps
+	const int blocks = std::min(W.n_workers / warps, dev_sm_count() * 4);
+	k_wfa_cta<<<blocks, MGB_CTA_THREADS, 0, t_stream>>>(L);
 	CUDA_OK(cudaGetLastError());
 #endif
 }
@@ -1131,6 +1201,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 					if (timed) tm_k[7].start();
 					make_job_order(L, 1, L.c.jobq[1], L.n_work, order);
 					L.rid_list = order;
+					if (p_cta_len > 0) { L.c.cta_len = (int32_t)p_cta_len; launch_wfa_cta(L, W); S.n_launches += 1; }
 					launch_stage<7>(L, W);
 					L.rid_list = 0;
 					if (timed) tm_k[7].stop();
@@ -1486,8 +1557,32 @@ MG_HD inline void test_wfa_body(const TestWfaArgs &t, int lane)
 	if (rc == 0 && r.n_cigar <= t.cap) for (int32_t i = lane; i < r.n_cigar; i += MGB_W) t.cigar[i] = r.cigar[i];
 	if (lane == 0) t.out[0] = rc, t.out[1] = rc == 0? r.n_cigar : 0, t.out[2] = rc == 0? r.s : 0;
 }
+// the same gap offered to the block-per-gap function first (parameter "cta_len"); out[3] = 1 when it produced the result
+MG_HD inline void test_wfa_cta_body(const TestWfaArgs &t, CtaCtx &cx, int tid)
+{
+	Arena A;
+	arena_init(A, t.arena, t.arena_bytes);
+	WfResult r;
+	r.s = -1, r.n_cigar = 0, r.n_iter = 0, r.cigar = 0;
+	char *ts = (char*)arena_alloc(A, (uint64_t)(t.tl + WF_SEQ_PAD + 4)), *qs = (char*)arena_alloc(A, (uint64_t)(t.ql + WF_SEQ_PAD + 4));
+	uint32_t *cig_store = (uint32_t*)arena_alloc(A, (uint64_t)(t.tl + t.ql + 2) * 4);
+	wf_stage_seq_cta(ts, t.ts, t.tl, 0xfe, tid);
+	wf_stage_seq_cta(qs, t.qs, t.ql, 0xff, tid);
+	cta_sync();
+	int rc = wfa_ring_cta(A, cx, t.tl, ts, t.ql, qs, t.max_iter, &r, cig_store, (int64_t)t.tl + t.ql + 2, tid);
+	const int taken = rc == 0 && r.s >= 0 && r.n_cigar <= t.cap;
+	if (taken) for (int32_t i = tid; i < r.n_cigar; i += MGB_CTA_T) t.cigar[i] = r.cigar[i];
+	if (tid == 0) t.out[0] = 0, t.out[1] = taken? r.n_cigar : 0, t.out[2] = taken? r.s : 0, t.out[3] = taken;
+}
 #ifndef MGB_HOSTSIM
 __global__ void k_test_wfa(TestWfaArgs t) { test_wfa_body(t, threadIdx.x & 31); }
+__global__ void __launch_bounds__(MGB_CTA_THREADS) k_test_wfa_cta(TestWfaArgs t)
+{
+	__shared__ CtaScratch scr;
+	CtaCtx cx;
+	cta_init(cx, &scr, threadIdx.x);
+	test_wfa_cta_body(t, cx, threadIdx.x);
+}
 #endif
 extern "C" int mgb_test_wfa(const char *ts, int tl, const char *qs, int ql, int64_t max_iter, int step, uint32_t *cigar, int cap, int *score)
 {
@@ -1500,6 +1595,24 @@ extern "C" int mgb_test_wfa(const char *ts, int tl, const char *qs, int ql, int6
 	t.cigar = (uint32_t*)dmalloc(sizeof(uint32_t) * (size_t)cap);
 	t.out = (int32_t*)dmalloc(sizeof(int32_t) * 4);
 	t.arena = (char*)dmalloc(t.arena_bytes);
+	int32_t out[4] = {0, 0, 0, 0};
+	if (p_cta_len > 0 && tl + ql >= p_cta_len && tl + ql <= 16000 && tl > 0 && ql > 0) {
+		h2d(t.out, out, sizeof(out));
+#ifdef MGB_HOSTSIM
+		CtaScratch scr;
+#if MGB_W > 1
+		sim::run_warp(MGB_CTA_T, [&](int tid) { CtaCtx cx; cta_init(cx, &scr, tid); test_wfa_cta_body(t, cx, tid); });
+#else
+		{ CtaCtx cx; cta_init(cx, &scr, 0); test_wfa_cta_body(t, cx, 0); }
+#endif
+#else
+		k_test_wfa_cta<<<1, MGB_CTA_THREADS>>>(t);
+		CUDA_OK(cudaGetLastError());
+		dsync();
+#endif
+		d2h(out, t.out, sizeof(out));
+	}
+	if (!out[3]) {
 #ifdef MGB_HOSTSIM
 #if MGB_W > 1
 	sim::run_warp(MGB_W, [&](int lane) { test_wfa_body(t, lane); });
@@ -1511,8 +1624,10 @@ extern "C" int mgb_test_wfa(const char *ts, int tl, const char *qs, int ql, int6
 	CUDA_OK(cudaGetLastError());
 	dsync();
 #endif
-	int32_t out[4];
 	d2h(out, t.out, sizeof(out));
+	out[3] = 0;
+	}
+	g_test_wfa_cta_taken += out[3];
 	if (out[0] == 0 && out[1] <= cap) d2h(cigar, t.cigar, sizeof(uint32_t) * (size_t)out[1]);
 	*score = out[2];
 	dfree(d_ts), dfree(d_qs), dfree(t.cigar), dfree(t.out), dfree(t.arena);

@@ -24,6 +24,7 @@ struct PipeCtx {
 	Pool *pool_jobs;       struct WfaJob *jobs;  // gap alignment jobs
 	Pool *pool_cig;        uint32_t *cig;        // per-job CIGARs
 	int32_t *jobq[2];      unsigned int *jobq_n;   // jobs handed to WFA tier 2 / tier 3
+	int32_t cta_len;       // > 0: tier-3 gaps with tl + ql >= cta_len are first offered to the block-per-gap kernel (mgb_wfa_cta.cuh)
 	int32_t big_len;       // > 0: gaps with tl or ql >= big_len are not touched by tiers 1/2 (a tier-3 launch on a second stream has them)
 	Pool *pool_gstate;     char *gstate;         // per-read state between the two graph-chaining passes
 	Pool *pool_gjobs;      struct GwfaJob *gjobs; // bridging alignment jobs (K7a)
@@ -39,7 +40,7 @@ struct PipeCtx {
 
 enum { PROF_WFA_FAST_CYC = 0, PROF_WFA_FAST_N, PROF_WFA_SLOW_CYC, PROF_WFA_SLOW_N, PROF_WFA_MAX_CYC, PROF_WFA_CELLS, PROF_WFA_TB_CYC,
 	   PROF_GC_DP_CYC, PROF_GC_GEN_CYC, PROF_GC_POST_CYC, PROF_GC_PLAN_CYC, PROF_FIN_CIGAR_CYC, PROF_FIN_DS_CYC, PROF_SEED_SKETCH_CYC,
-	   PROF_SEED_MATCH_CYC, PROF_SEED_SORT_CYC, PROF_CHAIN_DP_CYC, PROF_CHAIN_BT_CYC, PROF_CHAIN_RMQ_CYC, PROF_CHAIN_POST_CYC, PROF_WFA_MID_CYC, PROF_WFA_MID_N, PROF_GC_GWFA_CYC, PROF_GC_SHORTK_CYC, PROF_GC_EXTRA_CYC, PROF_GWFA_MAX_CYC, PROF_GC_DP_MAX_CYC, PROF_N = 32 };
+	   PROF_SEED_MATCH_CYC, PROF_SEED_SORT_CYC, PROF_CHAIN_DP_CYC, PROF_CHAIN_BT_CYC, PROF_CHAIN_RMQ_CYC, PROF_CHAIN_POST_CYC, PROF_WFA_MID_CYC, PROF_WFA_MID_N, PROF_GC_GWFA_CYC, PROF_GC_SHORTK_CYC, PROF_GC_EXTRA_CYC, PROF_GWFA_MAX_CYC, PROF_GC_DP_MAX_CYC, PROF_WFA_CTA_CYC, PROF_WFA_CTA_N, PROF_N = 32 };
 
 MG_HD inline unsigned long long prof_clock()
 {

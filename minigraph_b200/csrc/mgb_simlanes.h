@@ -21,7 +21,7 @@
 
 namespace mgb { namespace sim {
 
-enum { MAX_LANES = 32, STACK_BYTES = 1 << 20 };
+enum { MAX_LANES = 128, STACK_BYTES = 1 << 20 }; // 32 lanes for a warp, 128 for the block-uniform code (mgb_cta.cuh)
 
 // A fibre context.  glibc's swapcontext() makes a system call per switch (it saves the signal mask); on x86-64 a lane switch
 // is instead six pushes, a stack swap and six pops -- the callee-saved registers of the SysV ABI -- about fifty times cheaper.
@@ -59,7 +59,7 @@ inline void ctx_make(Ctx &c, Ctx &back, char *stack, size_t bytes, void (*entry)
 struct Warp {
 	int n = 0, cur = 0;
 	Ctx sched, ctx[MAX_LANES];
-	std::vector<char> stack[MAX_LANES];
+	char *stack[MAX_LANES];
 	bool done[MAX_LANES];
 	uint64_t slot[2][MAX_LANES];
 	int kind[2][MAX_LANES];       // which helper each lane entered the exchange from: lanes of a warp-uniform program use the same one
@@ -122,8 +122,8 @@ inline void run_warp(int n, const std::function<void(int)> &fn)
 	current() = &w;
 	for (int l = 0; l < n; ++l) {
 		w.done[l] = false, w.gen[l] = 0, w.wait_gen[l] = -1;
-		w.stack[l].resize(STACK_BYTES);
-		ctx_make(w.ctx[l], w.sched, w.stack[l].data(), STACK_BYTES, trampoline);
+		w.stack[l] = (char*)malloc(STACK_BYTES); // not cleared: only the pages a lane touches are ever mapped
+		ctx_make(w.ctx[l], w.sched, w.stack[l], STACK_BYTES, trampoline);
 	}
 	for (;;) { // round robin; a full round without any lane moving on means the lanes wait for different things
 		int alive = 0;
@@ -150,14 +150,16 @@ inline void run_warp(int n, const std::function<void(int)> &fn)
 			abort();
 		}
 	}
+	for (int l = 0; l < n; ++l) free(w.stack[l]);
 	current() = outer;
 }
 
-// Every lane contributes v and receives the contributions of all lanes.
-inline void exchange(uint64_t v, uint64_t out[MAX_LANES], int kind)
+// Every lane contributes v and receives the contributions of all lanes; out[] has room for `cap` of them.
+inline void exchange(uint64_t v, uint64_t *out, int kind, int cap = 32)
 {
 	Warp *w = current();
 	if (w == 0) { fprintf(stderr, "[mgb::sim] a warp helper was called outside run_warp()\n"); abort(); }
+	if (w->n > cap) { fprintf(stderr, "[mgb::sim] a %d-lane helper (kind %d) was called by a group of %d lanes\n", cap, kind, w->n); abort(); }
 	const int me = w->cur;
 	const long g = w->gen[me]++;
 	const int b = (int)(g & 1);

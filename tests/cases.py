@@ -159,6 +159,23 @@ def case_wfa_fallback(lib, n_cases=12, seed=5):
     assert n_fallback >= 3
 
 
+def case_cta(lib, workdir, n_cases=12):
+    """the block-per-gap tier ("cta_len", off by default): gaps it takes come out the same -- through the job queue (golden
+    GAF of c3, every tier-3 gap taken by a block) and one gap at a time against miniwfa (scores past 256, so the band of
+    the ring is re-centred by block-wide votes; capped runs fall through to the warp path)"""
+    from minigraph_b200 import capi
+    try:
+        assert lib.mgb_set_param(b"cta_len", 64) == 0
+        st = case_c3(lib, workdir)
+        prof = {n: st.prof[i] for i, n in enumerate(capi.PROF_NAMES)}
+        assert prof["wfa_cta_n"] > 50 and prof["wfa_slow_n"] == 0, prof
+        lib.mgb_set_param(b"cta_taken", 0)
+        case_wfa_fallback(lib, n_cases=n_cases)
+        assert lib.mgb_set_param(b"cta_taken", 0) >= 3
+    finally:
+        lib.mgb_set_param(b"cta_len", 0)
+
+
 def case_switches(lib, workdir, device):
     """the engine's experiment switches change the schedule, never the result: the same golden GAF with each of them on"""
     settings = [{b"big_len": 384}]  # long gaps to a tier-3 launch of their own

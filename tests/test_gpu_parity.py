@@ -1,4 +1,6 @@
 """GPU parity tests: libmgb200.so (CUDA, sm_100a) through the C ABI against the golden GAF and oracle/_ref."""
+import os
+
 import pytest
 
 import cases
@@ -72,6 +74,11 @@ def test_index_matches_oracle_sketch(lib):
     orc.orc_sketch.restype = C.c_int64
     orc.orc_sketch.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int64]
     test_oracle.check_index(lib, orc)
+
+
+@pytest.mark.skipif(not (T.have_ref() and os.environ.get("MGB_TEST_CTA")), reason="block-per-gap tier is opt-in (MGB_TEST_CTA=1): off by default in the engine")
+def test_block_per_gap_tier(lib, workdir):
+    cases.case_cta(lib, workdir, n_cases=10)
 
 
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not shipped")

@@ -65,6 +65,11 @@ def test_wfa_iteration_cap_fallback(lib):
     cases.case_wfa_fallback(lib)
 
 
+@pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
+def test_block_per_gap_tier(lib, workdir):
+    cases.case_cta(lib, workdir)
+
+
 def test_gaf_batch_writer_reuses_buffer(lib, workdir):
     """mgb_write_gaf_batch(): several threads, the caller's buffer handed back and reused, same bytes as the one-read writer"""
     import ctypes as C
