@@ -159,6 +159,73 @@ def case_wfa_fallback(lib, n_cases=12, seed=5):
     assert n_fallback >= 3
 
 
+def check_cigar_invariants(r, qlen):
+    """what holds for every mg_gchains_t the reference produces with -c (checked against the reference itself in
+    test_hostsim_parity.py): the CIGAR of a chain spans exactly its query and path intervals and sums to its mlen/blen"""
+    for g in r["gc"]:
+        assert 0 <= g["qs"] < g["qe"] <= qlen and 0 <= g["ps"] < g["pe"] <= g["plen"], g
+        if g["cigar"] is None:
+            continue
+        n_cigar, mlen, blen, aplen, ss, ee = g["cigar_hdr"]
+        assert n_cigar == len(g["cigar"]) and all((c & 15) in (1, 2, 7, 8) and (c >> 4) > 0 for c in g["cigar"])
+        assert sum(c >> 4 for c in g["cigar"] if (c & 15) in (7, 8, 1)) == g["qe"] - g["qs"]
+        assert sum(c >> 4 for c in g["cigar"] if (c & 15) in (7, 8, 2)) == g["pe"] - g["ps"] == aplen
+        assert sum(c >> 4 for c in g["cigar"] if (c & 15) == 7) == mlen and sum(c >> 4 for c in g["cigar"]) == blen
+        assert all((a & 15) != (b & 15) for a, b in zip(g["cigar"], g["cigar"][1:]))  # adjacent operations are merged
+
+
+def case_full_size(lib, workdir, n_reads=10000, n_sub=300, n_ref=100, seed=11):
+    """BASELINE config 2 at its full size (10 000 x 10 kb ONT-like reads on test/MT.gfa), through properties that do not
+    need the reference on every read: (1) reads sampled from the graph map (all but a stray one) and a CIGAR is
+    consistent with its intervals; (2) a result does not depend on the batch a read travels in (mg_map_frag is a pure function of the read,
+    map-algo.c:340-495): a shuffled sample mapped as its own batch gives the same objects; (3) a smaller sample against
+    the reference library itself."""
+    import ctypes as C
+    import random
+    from minigraph_b200 import capi, options
+    hap, reads = os.path.join(workdir, "mt.hap.fa"), os.path.join(workdir, "mt.full.fa")
+    T.sim_mt_haps(hap)
+    T.sim_reads(hap, reads, n_reads, 10000, "ont", seed)
+    names, seqs = T.read_fasta(reads)
+    n = len(seqs)
+    assert n == n_reads
+    gfa = os.path.join(T.FIX, "MT.gfa")
+    g = lib.mgb_gfa_read(gfa.encode())
+    io, mo = options.opt_set("lr", True)
+    gi = lib.mg_index(g, C.byref(io), 1, C.byref(mo))
+    assert gi, lib.mgb_last_error()
+    qlens = (C.c_int * n)(*[len(s) for s in seqs])
+    cseqs, cnames = (C.c_char_p * n)(*seqs), (C.c_char_p * n)(*names)
+    gcs = (C.POINTER(capi.mg_gchains_t) * n)()
+    assert lib.mg_map_batch(gi, n, qlens, cseqs, cnames, gcs, C.byref(mo)) == 0, lib.mgb_last_error()
+    n_mapped = sum(1 for i in range(n) if gcs[i] and gcs[i].contents.n_gc > 0)
+    assert n_mapped >= 0.999 * n, "%d of %d reads sampled from the graph did not map" % (n - n_mapped, n)
+    rng = random.Random(seed)
+    sub = rng.sample(range(n), min(n_sub, n))
+    full = {i: T.gchains_to_py(gcs[i]) for i in sub}
+    lib.mgb_free_batch(n, gcs)
+    for i in sub:
+        check_cigar_invariants(full[i], len(seqs[i]))
+    m = len(sub)
+    qlens2 = (C.c_int * m)(*[len(seqs[i]) for i in sub])
+    cseqs2, cnames2 = (C.c_char_p * m)(*[seqs[i] for i in sub]), (C.c_char_p * m)(*[names[i] for i in sub])
+    gcs2 = (C.POINTER(capi.mg_gchains_t) * m)()
+    assert lib.mg_map_batch(gi, m, qlens2, cseqs2, cnames2, gcs2, C.byref(mo)) == 0, lib.mgb_last_error()
+    for j, i in enumerate(sub):
+        d = T.diff_results(T.gchains_to_py(gcs2[j]), full[i])
+        assert d is None, "read %d: alone vs in the full batch: %s" % (i, d)
+    lib.mgb_free_batch(m, gcs2)
+    lib.mg_idx_destroy(gi)
+    lib.mgb_gfa_destroy(g)
+    if T.have_ref() and n_ref > 0:
+        pick = sub[:n_ref]
+        want, _ = T.map_with_ref(gfa, [names[i] for i in pick], [seqs[i] for i in pick], "lr")
+        for i, w in zip(pick, want):
+            check_cigar_invariants(w, len(seqs[i]))  # the invariants are the reference's, not ours
+            d = T.diff_results(full[i], w)
+            assert d is None, "read %d vs reference: %s" % (i, d)
+
+
 def case_cta(lib, workdir, n_cases=12):
     """the block-per-gap tier ("cta_len", off by default): gaps it takes come out the same -- through the job queue (golden
     GAF of c3, every tier-3 gap taken by a block) and one gap at a time against miniwfa (scores past 256, so the band of

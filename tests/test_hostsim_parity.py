@@ -66,6 +66,12 @@ def test_wfa_iteration_cap_fallback(lib):
 
 
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
+def test_full_size_properties_small(lib, workdir):
+    """the logic of the GPU suite's full-size test (tests/test_gpu_zz_full_size.py) at a size the simulator finishes"""
+    cases.case_full_size(lib, workdir, n_reads=120, n_sub=40, n_ref=20)
+
+
+@pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
 def test_block_per_gap_tier(lib, workdir):
     cases.case_cta(lib, workdir)
 
