@@ -21,6 +21,7 @@
 #include "../../include/mgb200.h"
 #include "mgb_galign.cuh"
 #include "mgb_wfa_cta.cuh"
+#include "mgb_wfa2.cuh"
 
 #ifndef MGB_HOSTSIM
 #include <cuda_runtime.h>
@@ -47,13 +48,14 @@ static int64_t p_slot_workers = 0;
 static int64_t p_tier_learn = 1;       // 0: every gap tries every tier (no routing)
 static int64_t p_side_warps = 1;       // warps per SM of that side launch
 static int g_test_wfa_cta_taken = 0;   // gaps of mgb_test_wfa() answered by the block function so far (mgb_set_param("cta_taken", v) returns it and sets it to v)
+static int64_t p_wfa_v2 = 0;           // 1: tiers 1/2 run the padded-slice version of the on-chip alignment (mgb_wfa2.cuh); not yet measured
 static int64_t p_cta_len = 0;          // > 0: tier-3 gaps with tl + ql at or above this are first offered to a block-per-gap kernel (k_wfa_cta); not yet measured
 static int64_t p_big_len = 0;          // > 0: gaps with tl or ql at or above this go to a tier-3 launch on a second stream beside tiers 1/2
                                        // (measured on B200 with 384: tier 3 -3 ms, tier 1 +7 ms from the shared SMs -- off)
 
 // launch shape per stage: warps per block and blocks per SM wanted (tunable for experiments: "sw<stage>", "mb<stage>")
-static int STAGE_MINB[10] = { 8, 8, 8, 8, 5, 8, 7, 4, 4, 4 };
-static int STAGE_WARPS[10] = { 4, 4, 4, 4, 4, 4, 2, 4, 4, 4 };
+static int STAGE_MINB[12] = { 8, 8, 8, 8, 5, 8, 7, 4, 4, 4, 5, 7 };  // 10, 11: second version of tiers 1 and 2 ("wfa_v2")
+static int STAGE_WARPS[12] = { 4, 4, 4, 4, 4, 4, 2, 4, 4, 4, 4, 2 };
 extern "C" const char *mgb_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char *mgb_version(void) { return "mgb200-r1"; }
 extern "C" int mgb_set_param(const char *key, int64_t value)
@@ -69,6 +71,7 @@ extern "C" int mgb_set_param(const char *key, int64_t value)
 	else if (!strcmp(key, "slot_workers")) p_slot_workers = value;
 	else if (!strcmp(key, "big_len")) p_big_len = value;
 	else if (!strcmp(key, "cta_len")) p_cta_len = value;
+	else if (!strcmp(key, "wfa_v2")) p_wfa_v2 = value;
 	else if (!strcmp(key, "cta_taken")) { int n = g_test_wfa_cta_taken; g_test_wfa_cta_taken = (int)value; return n; } // test hook counter: returns it, then sets it
 	else if (!strcmp(key, "side_warps")) p_side_warps = value;
 	else if (!strcmp(key, "tier_learn")) p_tier_learn = value;
@@ -185,7 +188,7 @@ struct LaunchArgs {
 // stages: 0 seed (K1-K3), 1 chain (K4/K5), 2 graph chaining DP + bridge plan (K6), 8 bridging jobs (K7a), 9 graph-chain
 //         materialisation + alignment plan (K7b), 4/6/7 WFA jobs tier 1/2/3 (K8a), 5 finish: CIGAR stitching + ds + result
 //         blob (K8b), 3 segment sketch for the index
-#define MGB_IS_WFA(STAGE) ((STAGE) == 4 || (STAGE) == 6 || (STAGE) == 7)
+#define MGB_IS_WFA(STAGE) ((STAGE) == 4 || (STAGE) == 6 || (STAGE) == 7 || (STAGE) == 10 || (STAGE) == 11)
 #define MGB_IS_WARP(STAGE) (MGB_IS_WFA(STAGE) || (STAGE) == 8 || (STAGE) == 1 || (STAGE) == 0 || (STAGE) == 5) // stages entered by all lanes of the warp
 template<int STAGE>
 MG_HD inline int run_stage(const LaunchArgs &L, int item, Arena &A, int lane, int32_t *smem)
@@ -198,6 +201,8 @@ MG_HD inline int run_stage(const LaunchArgs &L, int item, Arena &A, int lane, in
 	if (STAGE == 9) return stage_gchain_gen(L.c, L.routs, item, A);
 	if (STAGE == 4) return wfa_job_run(A, L.c, L.job_start + item, lane, smem, 1);
 	if (STAGE == 6) return wfa_job_run(A, L.c, L.c.jobq[0][item], lane, smem, 2);
+	if (STAGE == 10) return wfa_job_run<1>(A, L.c, L.job_start + item, lane, smem, 1);
+	if (STAGE == 11) return wfa_job_run<1>(A, L.c, L.c.jobq[0][item], lane, smem, 2);
 	if (STAGE == 7) return L.c.jobq[1][item] < 0? 0 : wfa_job_run(A, L.c, L.c.jobq[1][item], lane, smem, 3); // < 0: struck by k_wfa_cta
 	if (STAGE == 3) { // sketch one graph segment for the index (reference: index.c:200-205)
 		AVec<u128> mv;
@@ -226,7 +231,7 @@ MG_HD inline void stage_fail(const LaunchArgs &L, int item, int rc)
 #endif
 		return;
 	}
-	int rid = STAGE == 8? L.c.gjobs[L.job_start + item].rid : STAGE == 4? L.c.jobs[L.job_start + item].rid : STAGE == 6? L.c.jobs[L.c.jobq[0][item]].rid : STAGE == 7? L.c.jobs[L.c.jobq[1][item]].rid : item;
+	int rid = STAGE == 8? L.c.gjobs[L.job_start + item].rid : (STAGE == 4 || STAGE == 10)? L.c.jobs[L.job_start + item].rid : (STAGE == 6 || STAGE == 11)? L.c.jobs[L.c.jobq[0][item]].rid : STAGE == 7? L.c.jobs[L.c.jobq[1][item]].rid : item;
 	L.c.meta[rid].status = rc; // benign race between jobs of one read: any negative code triggers the redo
 	if (STAGE == 2 || MGB_IS_WARP(STAGE) || STAGE == 5 || STAGE == 9) L.routs[rid].status = rc;
 }
@@ -243,7 +248,7 @@ __device__ __forceinline__ void stage_loop(const LaunchArgs &L)
 	Arena A;
 	arena_init(A, L.arena_base + (uint64_t)worker * L.arena_bytes, L.arena_bytes);
 	extern __shared__ int4 dyn_smem[];
-	const int smem_stride = STAGE == 4? WfTier1::STRIDE : STAGE == 6? WfTier2::STRIDE : STAGE == 8? GWFA_SMEM_ARENA : 0;
+	const int smem_stride = STAGE == 4? WfTier1::STRIDE : STAGE == 6? WfTier2::STRIDE : STAGE == 10? WfTier1v2::STRIDE : STAGE == 11? WfTier2v2::STRIDE : STAGE == 8? GWFA_SMEM_ARENA : 0;
 	int32_t *smem = smem_stride? (int32_t*)((char*)dyn_smem + (size_t)(threadIdx.x >> 5) * smem_stride) : 0;
 	for (;;) {
 		int item = 0;
@@ -299,6 +304,8 @@ MGB_KERNEL(k_wfa_small, 4, 5)     // K8a tier 1: small gaps, wavefronts + traceb
 MGB_KERNEL(k_wfa_mid, 6, 5)       // K8a tier 2: mid-size gaps, wavefronts in shared memory (blocks of 2 warps)
 MGB_KERNEL(k_wfa_big, 7, 4)       // K8a tier 3: anything else, wavefronts in the worker arena
 MGB_KERNEL(k_finish, 5, 8)        // K8b: CIGAR stitching, ds strings, result blobs
+MGB_KERNEL(k_wfa_small2, 10, 5)   // tier 1, second version (mgb_wfa2.cuh; parameter "wfa_v2")
+MGB_KERNEL(k_wfa_mid2, 11, 5)     // tier 2, second version
 template<int STAGE> struct StageKernel;
 template<> struct StageKernel<0> { static void (*get())(LaunchArgs) { return k_seed; } };
 template<> struct StageKernel<1> { static void (*get())(LaunchArgs) { return k_chain; } };
@@ -310,6 +317,8 @@ template<> struct StageKernel<7> { static void (*get())(LaunchArgs) { return k_w
 template<> struct StageKernel<8> { static void (*get())(LaunchArgs) { return k_gwfa; } };
 template<> struct StageKernel<9> { static void (*get())(LaunchArgs) { return k_gchain_gen; } };
 template<> struct StageKernel<5> { static void (*get())(LaunchArgs) { return k_finish; } };
+template<> struct StageKernel<10> { static void (*get())(LaunchArgs) { return k_wfa_small2; } };
+template<> struct StageKernel<11> { static void (*get())(LaunchArgs) { return k_wfa_mid2; } };
 #endif
 
 // Longest-first order of a job list (a tail of a few long jobs otherwise decides the kernel time).  Jobs are binned by
@@ -461,7 +470,7 @@ static void launch_stage(LaunchArgs &L, const Workers &W, int warps_override = 0
 #ifdef MGB_HOSTSIM
 	Arena A;
 	arena_init(A, W.arena, W.arena_bytes);
-	std::vector<int32_t> sim_smem(std::max<size_t>(std::max<size_t>(WfTier1::STRIDE, WfTier2::STRIDE), std::max<size_t>(GWFA_SMEM_ARENA, CHAIN_SMEM)) / 4);
+	std::vector<int32_t> sim_smem(std::max<size_t>(std::max<size_t>(WfTier1v2::STRIDE, WfTier2v2::STRIDE), std::max<size_t>(GWFA_SMEM_ARENA, CHAIN_SMEM)) / 4);
 	for (int it = 0; it < L.n_work; ++it) {
 		int item = L.rid_list? L.rid_list[it] : it;
 		A.top = 0;
@@ -491,7 +500,7 @@ static void launch_stage(LaunchArgs &L, const Workers &W, int warps_override = 0
 	int want = dev_sm_count() * STAGE_MINB[STAGE] * STAGE_WARPS[STAGE]; // resident warps this stage can keep on the chip
 	int n_w = std::min(W.n_workers, want);
 	int blocks = std::max(1, n_w / warps);
-	size_t smem = STAGE == 4? (size_t)warps * WfTier1::STRIDE : STAGE == 6? (size_t)warps * WfTier2::STRIDE : STAGE == 8? (size_t)warps * GWFA_SMEM_ARENA : 0;
+	size_t smem = STAGE == 4? (size_t)warps * WfTier1::STRIDE : STAGE == 6? (size_t)warps * WfTier2::STRIDE : STAGE == 10? (size_t)warps * WfTier1v2::STRIDE : STAGE == 11? (size_t)warps * WfTier2v2::STRIDE : STAGE == 8? (size_t)warps * GWFA_SMEM_ARENA : 0;
 	void (*kern)(LaunchArgs) = StageKernel<STAGE>::get();
 	if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	L.thread_mode = (p_thread_mask >> STAGE) & 1;
@@ -1191,10 +1200,10 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 						if (timed) S.n_jobs_side = n_big;
 					}
 				}
-				{ if (timed) tm_k[4].start(); launch_stage<4>(L, W); if (timed) tm_k[4].stop(); }
+				{ if (timed) tm_k[4].start(); if (p_wfa_v2) launch_stage<10>(L, W); else launch_stage<4>(L, W); if (timed) tm_k[4].stop(); }
 				d2h(qn, d_jobq_n, sizeof(qn));
 				S.n_launches += 1;
-				if (qn[0] > 0) { L.n_work = (int32_t)qn[0]; { if (timed) tm_k[6].start(); launch_stage<6>(L, W); if (timed) tm_k[6].stop(); } d2h(qn, d_jobq_n, sizeof(qn)); S.n_launches += 1; }
+				if (qn[0] > 0) { L.n_work = (int32_t)qn[0]; { if (timed) tm_k[6].start(); if (p_wfa_v2) launch_stage<11>(L, W); else launch_stage<6>(L, W); if (timed) tm_k[6].stop(); } d2h(qn, d_jobq_n, sizeof(qn)); S.n_launches += 1; }
 				if (qn[1] > 0) {
 					L.n_work = (int32_t)qn[1];
 					int32_t *order = (int32_t*)sl.d_order.ensure(sizeof(int32_t) * (size_t)L.n_work);

@@ -6,6 +6,7 @@
 #include "mgb_pipeline.cuh"
 #include "mgb_gchain.cuh"
 #include "mgb_wfa.cuh"
+#include "mgb_wfa2.cuh"
 #if defined(MGB_HOSTSIM)
 #include <stdio.h>
 #include <stdlib.h>
@@ -108,6 +109,7 @@ MG_HD inline int gchain_cigar_plan(Arena &A, const PipeCtx &c, int rid, const Gr
 // tier 1: small gaps, wavefronts + traceback bytes in shared memory; tier 2: mid-size gaps, wavefronts in shared
 // memory; tier 3: anything, wavefronts in the worker arena.  A job that does not fit a tier is appended to the queue
 // of the next one (jobq[tier-1]); the host launches the next tier over that queue.
+template<int V2 = 0> // V2: tiers 1/2 use wfa_smem2() (mgb_wfa2.cuh) instead of wfa_smem()
 MG_HD inline int wfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int lane, int32_t *smem, int tier)
 {
 	WfaJob *J = &c.jobs[job_idx];
@@ -171,8 +173,8 @@ MG_HD inline int wfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int la
 	WfResult rst;
 	unsigned long long pt0 = prof_clock();
 	int rc;
-	if (tier == 1) rc = wfa_smem<WfTier1::W_, WfTier1::MAXLEN_, WfTier1::TBCAP_, WfTier1::HS_>(A, smem, tl, tseq, ql, qs, &rst, lane);
-	else if (tier == 2) rc = wfa_smem<WfTier2::W_, WfTier2::MAXLEN_, WfTier2::TBCAP_, WfTier2::HS_>(A, smem, tl, tseq, ql, qs, &rst, lane);
+	if (tier == 1) rc = V2? wfa_smem2<WfTier1::W_, WfTier1::MAXLEN_, WfTier1::TBCAP_>(A, smem, tl, tseq, ql, qs, &rst, lane) : wfa_smem<WfTier1::W_, WfTier1::MAXLEN_, WfTier1::TBCAP_, WfTier1::HS_>(A, smem, tl, tseq, ql, qs, &rst, lane);
+	else if (tier == 2) rc = V2? wfa_smem2<WfTier2::W_, WfTier2::MAXLEN_, WfTier2::TBCAP_>(A, smem, tl, tseq, ql, qs, &rst, lane) : wfa_smem<WfTier2::W_, WfTier2::MAXLEN_, WfTier2::TBCAP_, WfTier2::HS_>(A, smem, tl, tseq, ql, qs, &rst, lane);
 	else rc = wfa_exact(A, tl, tseq, ql, qs, 100000000LL, &rst, lane);
 	if (rc < 0) return rc;
 	if (lane == 0) {

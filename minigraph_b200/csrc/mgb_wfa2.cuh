@@ -1,0 +1,193 @@
+// mgb_wfa2.cuh -- second version of the shared-memory gap alignment (wfa_smem, mgb_wfa.cuh): same recurrence, same
+// results, fewer instructions per cell.  Off by default (engine parameter "wfa_v2"): written after the last GPU run of
+// round 1 from the SASS of the first version, whose inner loop spends half of its ~190 instructions per cell on the nine
+// bounds-checked neighbour reads (the per-score [lo,hi] pairs are unpacked again for every cell).
+//
+// What changes:
+// * no bounds checks.  In these tiers the window never shrinks (lo only falls, hi only rises; the reference's band
+//   re-centring needs score 256, which is tier 3), and a slot of the ring is reused by a later score, whose range contains
+//   the old one.  So when all slices start filled with -inf, every cell outside the range a slice was last written with
+//   still holds -inf: exactly what the reference's padding holds (miniwfa.c:182-209) and what the bounds checks of
+//   the first version return.  The nine reads become plain shared-memory loads at columns (d-1, d, d+1) mod W, and the
+//   sixteen rotating [lo,hi] registers go away.  The window may hold W - 2 diagonals (column lo-1 must not alias hi+1);
+// * the four votes of a wavefront are one OR-reduction of four bits; the corner test runs on the one diagonal that can
+//   reach the corner; the "does the window still grow" test runs on the two edge cells only.
+#pragma once
+#include "mgb_wfa.cuh"
+
+namespace mgb {
+
+#if MGB_ON_DEVICE
+MG_D inline uint32_t warp_or_u32(uint32_t x) { return __reduce_or_sync(0xffffffffu, x); }
+#elif defined(MGB_SIM_LANES)
+inline uint32_t warp_or_u32(uint32_t x) { uint64_t o[32]; sim::exchange(x, o, 15); uint32_t r = 0; for (int i = 0; i < MGB_W; ++i) r |= (uint32_t)o[i]; return r; }
+#else
+inline uint32_t warp_or_u32(uint32_t x) { return x; }
+#endif
+
+// keeps a value in a register: the compiler may not look through it (no code is generated)
+#define MGB_OPAQUE(x) asm("" : "+r"(x))
+
+// one cell as a 32-bit value (opaque, so that the arithmetic on it stays 32-bit: left alone, the compiler narrows the maxima to
+// packed 16-bit operations and spends more on moving halves around than it saves)
+MG_HD inline int32_t wf2_ld(const void *base, int32_t off)
+{
+	int32_t v = *(const wf_cell_t*)((const char*)base + off);
+	MGB_OPAQUE(v);
+	return v;
+}
+
+template<int W, int MAXLEN, int TBCAP>
+MG_HD inline int wfa_smem2(Arena &A, int32_t *smem, int32_t tl, const char *ts_g, int32_t ql, const char *qs_g, WfResult *r, int lane)
+{
+	typedef WfSmemLayout<W, MAXLEN, TBCAP, 17> LY;
+	const int HS = 17;
+	if (tl > MAXLEN || ql > MAXLEN) return 1;
+	if (MAXLEN > 16000) return 1; // cells are 16-bit
+	uint64_t mark = A.top;
+	wf_cell_t *H = (wf_cell_t*)smem, *E1 = H + HS * W, *F1 = E1 + 3 * W, *E2 = F1 + 3 * W, *F2 = E2 + 2 * W;
+	char *ts = (char*)(smem + LY::N_INTS), *qs = ts + LY::SEQ_BYTES;
+	int32_t *tb_row = (int32_t*)(qs + LY::SEQ_BYTES); // TBCAP > 0 only
+	uint8_t *tb_x = (uint8_t*)tb_row + LY::TB_ROW_BYTES;
+	{ // every slice starts as -inf
+		const uint32_t two = (uint32_t)(uint16_t)(wf_cell_t)WF_NEG_INF16 * 0x10001u;
+		uint32_t *cells = (uint32_t*)smem;
+		for (int32_t i = lane; i < LY::N_INTS; i += MGB_W) cells[i] = two;
+	}
+	wf_stage_seq(ts, ts_g, tl, 0xfe, lane);
+	wf_stage_seq(qs, qs_g, ql, 0xff, lane);
+	r->s = -1, r->n_cigar = 0, r->n_iter = 0, r->cigar = 0;
+	uint32_t *cig_store;
+	const int64_t max_cigar = (int64_t)tl + ql + 2;
+	MGB_ALLOC(A, cig_store, uint32_t, max_cigar);
+	uint64_t mark_keep = A.top;
+	AVec<WfTbRow> rows; // TBCAP == 0 only
+	avec_init(rows);
+	if (TBCAP == 0) MGB_TRY(avec_reserve_w(A, rows, 256, lane)); // a row per score, and the score stays below 255
+	int32_t n_rows = 0, tb_used = 0;
+	int32_t wlo = 0, whi = 0, last_state = 0, s = 0;
+	int64_t n_iter = 0;
+	int hs = 0, m3 = 0, m2 = 0; // s % 17, s % 3, s % 2, kept incrementally
+	const int32_t d_corner = ql - tl; // the diagonal of the last cell of the matrix
+	int hit = 0, hit_noext = 0;
+	warp_sync(); // the staged sequences and the cleared slices are complete
+	if (lane == 0) { // score 0: the main diagonal, extended from the corner (E/F of score 0 stay -inf)
+		int32_t k0 = -1, k = -1;
+		if (!(k0 >= tl || k0 >= ql)) {
+			k = wf_extend(ts, qs, k0, 0);
+			if (k == tl - 1 && k == ql - 1) hit = 1, hit_noext = (k == k0), k = k0;
+		}
+		H[wfs_col<W>(0)] = (wf_cell_t)k;
+	}
+	{
+		const uint32_t vb = warp_or_u32((hit? 1u : 0u) | (hit_noext? 2u : 0u));
+		hit = vb & 1, hit_noext = vb >> 1 & 1;
+	}
+	warp_sync();
+	for (;;) {
+		// invariant: the wavefront of score s is computed, extended along exact matches and visible to all lanes;
+		// a slice holds -inf everywhere outside the range it was last written with
+		if (hit) {
+			if (hit_noext) { // no extension on the last diagonal: the state comes from the traceback byte
+				int32_t x;
+				if (TBCAP > 0) { WfTbSmem t; t.row = tb_row, t.x = tb_x, t.n_rows = n_rows, t.used = tb_used; x = t.get(n_rows - 1, ql - tl); }
+				else { WfTbArena t; t.row = rows.a; x = t.get(n_rows - 1, ql - tl); }
+				last_state = x & 7;
+			}
+			break;
+		}
+		const int32_t lo = wlo > -tl? wlo - 1 : -tl;
+		const int32_t hi = whi < ql? whi + 1 : ql;
+		const int32_t width = hi - lo + 1;
+		if (width + 2 > W || s + 1 >= 255 || (TBCAP > 0 && tb_used + width > TBCAP)) { A.top = mark; return 1; }
+		const int32_t ns = s + 1;
+		const int nhs = hs + 1 == 17? 0 : hs + 1, n3 = m3 + 1 == 3? 0 : m3 + 1, n2 = m2 ^ 1;
+		uint8_t *ax;
+		if (TBCAP > 0) {
+			if (lane == 0) tb_row[2 * n_rows] = lo, tb_row[2 * n_rows + 1] = tb_used;
+			ax = tb_x + tb_used - lo;
+			tb_used += width;
+		} else {
+			uint8_t *x;
+			MGB_ALLOC(A, x, uint8_t, width);
+			if (lane == 0) rows.a[n_rows].lo = lo, rows.a[n_rows].hi = hi, rows.a[n_rows].x = x;
+			rows.n = n_rows + 1;
+			ax = x - lo;
+		}
+		++n_rows;
+		// source slices: score ns-4 (mismatch), ns-6 and ns-16 (gap opens), ns-2 and ns-1 (gap extensions)
+		const int r4 = nhs >= WF_X? nhs - WF_X : nhs - WF_X + 17, r6 = nhs >= WF_O1 + WF_E1? nhs - (WF_O1 + WF_E1) : nhs - (WF_O1 + WF_E1) + 17;
+		const int r16 = nhs >= WF_O2 + WF_E2? nhs - (WF_O2 + WF_E2) : nhs - (WF_O2 + WF_E2) + 17;
+		const int e1slot = n3 >= 2? n3 - 2 : n3 + 1; // (ns-2) % 3
+		// byte offsets of the slices inside their arrays, held in registers through the cell loop (MGB_OPAQUE: the compiler would
+		// otherwise re-derive each of them from the slot numbers for every cell)
+		int32_t bHx = r4 * W * 2, bHo1 = r6 * W * 2, bHo2 = r16 * W * 2, bE1 = e1slot * W * 2, bE2 = m2 * W * 2, bnH = nhs * W * 2, bn3 = n3 * W * 2, bn2 = n2 * W * 2;
+		MGB_OPAQUE(bHx); MGB_OPAQUE(bHo1); MGB_OPAQUE(bHo2); MGB_OPAQUE(bE1); MGB_OPAQUE(bE2); MGB_OPAQUE(bnH); MGB_OPAQUE(bn3); MGB_OPAQUE(bn2);
+#define MGB_WF_LD(base, off) wf2_ld(base, off)
+#define MGB_WF_ST(base, off, v) (*(wf_cell_t*)((char*)(base) + (off)) = (wf_cell_t)(v))
+		uint32_t vote = 0; // 1: window grows on the low side, 2: on the high side, 4: corner reached, 8: ... without extension
+		for (int32_t d = lo + lane; d <= hi; d += MGB_W) { // reference: miniwfa.c:281-308 wf_next_tb, then :212-226 on the new cell
+			int32_t h, f, e, e1, e2, f1, f2, a0, b0;
+			uint8_t x = 0, ze, zf, z;
+			const int32_t c = wfs_col<W>(d) * 2, cm = (c - 2) & (2 * W - 1), cp = (c + 2) & (2 * W - 1); // byte columns
+			a0 = MGB_WF_LD(H, bHo1 + cm), b0 = MGB_WF_LD(E1, bE1 + cm);
+			x |= a0 >= b0? 0 : 0x08; e1 = MGB_WF_MAX(a0, b0);
+			a0 = MGB_WF_LD(H, bHo2 + cm), b0 = MGB_WF_LD(E2, bE2 + cm);
+			x |= a0 >= b0? 0 : 0x20; e2 = MGB_WF_MAX(a0, b0);
+			ze = e1 >= e2? 1 : 3;
+			e = MGB_WF_MAX(e1, e2);
+			a0 = MGB_WF_LD(H, bHo1 + cp), b0 = MGB_WF_LD(F1, bE1 + cp);
+			x |= a0 >= b0? 0 : 0x10; f1 = MGB_WF_MAX(a0, b0) + 1;
+			a0 = MGB_WF_LD(H, bHo2 + cp), b0 = MGB_WF_LD(F2, bE2 + cp);
+			x |= a0 >= b0? 0 : 0x40; f2 = MGB_WF_MAX(a0, b0) + 1;
+			zf = f1 >= f2? 2 : 4;
+			f = MGB_WF_MAX(f1, f2);
+			z = e >= f? ze : zf;
+			h = MGB_WF_MAX(e, f);
+			a0 = MGB_WF_LD(H, bHx + c) + 1;
+			z = a0 >= h? 0 : z;
+			h = MGB_WF_MAX(a0, h);
+			ax[d] = x | z;
+			if (d == lo || d == hi) { // does the window still grow on this side?
+				if (h >= -1 || e1 >= -1 || f1 >= -1 || e2 >= -1 || f2 >= -1) vote |= (d == lo? 1u : 0u) | (d == hi? 2u : 0u);
+			}
+			if (!(h < -1 || d + h < -1 || h >= tl || d + h >= ql)) { // extend the new cell right away
+				const int32_t k = wf_extend(ts, qs, h, d);
+				if (d == d_corner && k == tl - 1) vote |= 4u | (k == h? 8u : 0u);
+				else h = k;
+			}
+			MGB_WF_ST(E1, bn3 + c, e1), MGB_WF_ST(F1, bn3 + c, f1), MGB_WF_ST(E2, bn2 + c, e2), MGB_WF_ST(F2, bn2 + c, f2), MGB_WF_ST(H, bnH + c, h); // slots of score ns are not read in this loop
+		}
+#undef MGB_WF_LD
+#undef MGB_WF_ST
+		vote = warp_or_u32(vote);
+		if (vote & 1) wlo = lo;
+		if (vote & 2) whi = hi;
+		hit = vote >> 2 & 1, hit_noext = vote >> 3 & 1;
+		s = ns, hs = nhs, m3 = n3, m2 = n2;
+		n_iter += width;
+		warp_sync();
+	}
+	r->n_iter = n_iter;
+	r->s = s;
+	{
+		int rc = 0;
+		int32_t n_cig = 0;
+		int64_t first = 0;
+		if (lane == 0) {
+			if (TBCAP > 0) { WfTbSmem t; t.row = tb_row, t.x = tb_x, t.n_rows = n_rows, t.used = tb_used; rc = wf_traceback(t, n_rows, tl, ts, ql, qs, last_state, cig_store, max_cigar, &n_cig, &first); }
+			else { WfTbArena t; t.row = rows.a; rc = wf_traceback(t, n_rows, tl, ts, ql, qs, last_state, cig_store, max_cigar, &n_cig, &first); }
+		}
+		rc = warp_bcast_i32(rc, 0), n_cig = warp_bcast_i32(n_cig, 0), first = (int64_t)warp_bcast_u64((uint64_t)first, 0);
+		warp_sync();
+		if (rc < 0) { A.top = mark; return rc; }
+		r->n_cigar = n_cig, r->cigar = cig_store + first;
+	}
+	A.top = mark_keep;
+	return 0;
+}
+
+typedef WfSmemLayout<64, 256, 4096, 17> WfTier1v2; // the layouts of the first version
+typedef WfSmemLayout<256, 1024, 0, 17> WfTier2v2;
+
+} // namespace mgb

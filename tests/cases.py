@@ -226,6 +226,25 @@ def case_full_size(lib, workdir, n_reads=10000, n_sub=300, n_ref=100, seed=11):
             assert d is None, "read %d vs reference: %s" % (i, d)
 
 
+def case_wfa_v2(lib, workdir, n_struct=60):
+    """the second version of the on-chip gap alignment ("wfa_v2", off by default; mgb_wfa2.cuh): slices that hold -inf
+    outside their range instead of bounds checks.  Same GAF for the golden cases (lr and asm presets, both on-chip tiers
+    busy), same mg_gchains_t fields as the reference on an SV graph, also with the learned tier routing of a second batch"""
+    from minigraph_b200 import capi
+    try:
+        assert lib.mgb_set_param(b"wfa_v2", 1) == 0
+        for fn in (case_c2, case_c3, case_c4):
+            st = fn(lib, workdir)
+            prof = {n: st.prof[i] for i, n in enumerate(capi.PROF_NAMES)}
+            assert prof["wfa_fast_n"] > 500, prof
+            assert fn is case_c4 or prof["wfa_mid_n"] > 500, prof
+        if T.have_ref():
+            case_struct_random(lib, workdir, n_reads=n_struct, seed=37)
+            case_tier_routing(lib, workdir)
+    finally:
+        lib.mgb_set_param(b"wfa_v2", 0)
+
+
 def case_cta(lib, workdir, n_cases=12):
     """the block-per-gap tier ("cta_len", off by default): gaps it takes come out the same -- through the job queue (golden
     GAF of c3, every tier-3 gap taken by a block) and one gap at a time against miniwfa (scores past 256, so the band of

@@ -76,6 +76,11 @@ def test_index_matches_oracle_sketch(lib):
     test_oracle.check_index(lib, orc)
 
 
+@pytest.mark.skipif(not os.environ.get("MGB_TEST_WFA_V2"), reason="second version of the on-chip alignment is opt-in (MGB_TEST_WFA_V2=1): off by default in the engine")
+def test_wfa_second_version(lib, workdir):
+    cases.case_wfa_v2(lib, workdir, n_struct=150)
+
+
 @pytest.mark.skipif(not (T.have_ref() and os.environ.get("MGB_TEST_CTA")), reason="block-per-gap tier is opt-in (MGB_TEST_CTA=1): off by default in the engine")
 def test_block_per_gap_tier(lib, workdir):
     cases.case_cta(lib, workdir, n_cases=10)

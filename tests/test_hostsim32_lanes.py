@@ -71,6 +71,10 @@ def test_no_diag_flag(lib, workdir):
     cases.case_no_diag(lib, workdir)
 
 
+def test_wfa_second_version(lib, workdir):
+    cases.case_wfa_v2(lib, workdir)
+
+
 def test_block_per_gap_tier(lib, workdir):
     """the block-uniform code with 128 simulated threads: block-wide votes, barriers and broadcasts really exchanged"""
     cases.case_cta(lib, workdir)

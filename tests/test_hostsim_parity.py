@@ -72,6 +72,10 @@ def test_full_size_properties_small(lib, workdir):
 
 
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
+def test_wfa_second_version(lib, workdir):
+    cases.case_wfa_v2(lib, workdir)
+
+
 def test_block_per_gap_tier(lib, workdir):
     cases.case_cta(lib, workdir)
 
