@@ -54,8 +54,8 @@ static int64_t p_big_len = 0;          // > 0: gaps with tl or ql at or above th
                                        // (measured on B200 with 384: tier 3 -3 ms, tier 1 +7 ms from the shared SMs -- off)
 
 // launch shape per stage: warps per block and blocks per SM wanted (tunable for experiments: "sw<stage>", "mb<stage>")
-static int STAGE_MINB[12] = { 8, 8, 8, 8, 5, 8, 7, 4, 4, 4, 5, 7 };  // 10, 11: second version of tiers 1 and 2 ("wfa_v2")
-static int STAGE_WARPS[12] = { 4, 4, 4, 4, 4, 4, 2, 4, 4, 4, 4, 2 };
+static int STAGE_MINB[13] = { 8, 8, 8, 8, 5, 8, 7, 4, 4, 4, 5, 7, 4 };  // 10, 11, 12: second version of tiers 1, 2 and 3 ("wfa_v2")
+static int STAGE_WARPS[13] = { 4, 4, 4, 4, 4, 4, 2, 4, 4, 4, 4, 2, 4 };
 extern "C" const char *mgb_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char *mgb_version(void) { return "mgb200-r1"; }
 extern "C" int mgb_set_param(const char *key, int64_t value)
@@ -188,7 +188,7 @@ struct LaunchArgs {
 // stages: 0 seed (K1-K3), 1 chain (K4/K5), 2 graph chaining DP + bridge plan (K6), 8 bridging jobs (K7a), 9 graph-chain
 //         materialisation + alignment plan (K7b), 4/6/7 WFA jobs tier 1/2/3 (K8a), 5 finish: CIGAR stitching + ds + result
 //         blob (K8b), 3 segment sketch for the index
-#define MGB_IS_WFA(STAGE) ((STAGE) == 4 || (STAGE) == 6 || (STAGE) == 7 || (STAGE) == 10 || (STAGE) == 11)
+#define MGB_IS_WFA(STAGE) ((STAGE) == 4 || (STAGE) == 6 || (STAGE) == 7 || (STAGE) == 10 || (STAGE) == 11 || (STAGE) == 12)
 #define MGB_IS_WARP(STAGE) (MGB_IS_WFA(STAGE) || (STAGE) == 8 || (STAGE) == 1 || (STAGE) == 0 || (STAGE) == 5) // stages entered by all lanes of the warp
 template<int STAGE>
 MG_HD inline int run_stage(const LaunchArgs &L, int item, Arena &A, int lane, int32_t *smem)
@@ -203,6 +203,7 @@ MG_HD inline int run_stage(const LaunchArgs &L, int item, Arena &A, int lane, in
 	if (STAGE == 6) return wfa_job_run(A, L.c, L.c.jobq[0][item], lane, smem, 2);
 	if (STAGE == 10) return wfa_job_run<1>(A, L.c, L.job_start + item, lane, smem, 1);
 	if (STAGE == 11) return wfa_job_run<1>(A, L.c, L.c.jobq[0][item], lane, smem, 2);
+	if (STAGE == 12) return L.c.jobq[1][item] < 0? 0 : wfa_job_run<1>(A, L.c, L.c.jobq[1][item], lane, smem, 3);
 	if (STAGE == 7) return L.c.jobq[1][item] < 0? 0 : wfa_job_run(A, L.c, L.c.jobq[1][item], lane, smem, 3); // < 0: struck by k_wfa_cta
 	if (STAGE == 3) { // sketch one graph segment for the index (reference: index.c:200-205)
 		AVec<u128> mv;
@@ -231,7 +232,7 @@ MG_HD inline void stage_fail(const LaunchArgs &L, int item, int rc)
 #endif
 		return;
 	}
-	int rid = STAGE == 8? L.c.gjobs[L.job_start + item].rid : (STAGE == 4 || STAGE == 10)? L.c.jobs[L.job_start + item].rid : (STAGE == 6 || STAGE == 11)? L.c.jobs[L.c.jobq[0][item]].rid : STAGE == 7? L.c.jobs[L.c.jobq[1][item]].rid : item;
+	int rid = STAGE == 8? L.c.gjobs[L.job_start + item].rid : (STAGE == 4 || STAGE == 10)? L.c.jobs[L.job_start + item].rid : (STAGE == 6 || STAGE == 11)? L.c.jobs[L.c.jobq[0][item]].rid : (STAGE == 7 || STAGE == 12)? L.c.jobs[L.c.jobq[1][item]].rid : item;
 	L.c.meta[rid].status = rc; // benign race between jobs of one read: any negative code triggers the redo
 	if (STAGE == 2 || MGB_IS_WARP(STAGE) || STAGE == 5 || STAGE == 9) L.routs[rid].status = rc;
 }
@@ -306,6 +307,7 @@ MGB_KERNEL(k_wfa_big, 7, 4)       // K8a tier 3: anything else, wavefronts in th
 MGB_KERNEL(k_finish, 5, 8)        // K8b: CIGAR stitching, ds strings, result blobs
 MGB_KERNEL(k_wfa_small2, 10, 5)   // tier 1, second version (mgb_wfa2.cuh; parameter "wfa_v2")
 MGB_KERNEL(k_wfa_mid2, 11, 5)     // tier 2, second version
+MGB_KERNEL(k_wfa_big2, 12, 4)     // tier 3, second version
 template<int STAGE> struct StageKernel;
 template<> struct StageKernel<0> { static void (*get())(LaunchArgs) { return k_seed; } };
 template<> struct StageKernel<1> { static void (*get())(LaunchArgs) { return k_chain; } };
@@ -319,6 +321,7 @@ template<> struct StageKernel<9> { static void (*get())(LaunchArgs) { return k_g
 template<> struct StageKernel<5> { static void (*get())(LaunchArgs) { return k_finish; } };
 template<> struct StageKernel<10> { static void (*get())(LaunchArgs) { return k_wfa_small2; } };
 template<> struct StageKernel<11> { static void (*get())(LaunchArgs) { return k_wfa_mid2; } };
+template<> struct StageKernel<12> { static void (*get())(LaunchArgs) { return k_wfa_big2; } };
 #endif
 
 // Longest-first order of a job list (a tail of a few long jobs otherwise decides the kernel time).  Jobs are binned by
@@ -1211,7 +1214,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 					make_job_order(L, 1, L.c.jobq[1], L.n_work, order);
 					L.rid_list = order;
 					if (p_cta_len > 0) { L.c.cta_len = (int32_t)p_cta_len; launch_wfa_cta(L, W); S.n_launches += 1; }
-					launch_stage<7>(L, W);
+					if (p_wfa_v2) launch_stage<12>(L, W); else launch_stage<7>(L, W);
 					L.rid_list = 0;
 					if (timed) tm_k[7].stop();
 					S.n_launches += 2;
@@ -1556,13 +1559,13 @@ extern "C" mg_gchains_t *mg_map(const mg_idx_t *gi, int qlen, const char *seq, m
 // test hook: one gap alignment through the tier-3 path (exact WFA capped at max_iter cells, then the chaining
 // heuristic with low-memory checkpoints every `step` scores), reference: miniwfa.c:824-834 mwf_wfa_auto
 // ---------------------------------------------------------------------------------------------------------------
-struct TestWfaArgs { const char *ts, *qs; int32_t tl, ql, step, cap; int64_t max_iter; uint32_t *cigar; int32_t *out; char *arena; uint64_t arena_bytes; };
+struct TestWfaArgs { const char *ts, *qs; int32_t tl, ql, step, cap, v2; int64_t max_iter; uint32_t *cigar; int32_t *out; char *arena; uint64_t arena_bytes; };
 MG_HD inline void test_wfa_body(const TestWfaArgs &t, int lane)
 {
 	Arena A;
 	arena_init(A, t.arena, t.arena_bytes);
 	WfResult r;
-	int rc = wfa_exact(A, t.tl, t.ts, t.ql, t.qs, t.max_iter, &r, lane, t.step);
+	int rc = t.v2? wfa_exact<1>(A, t.tl, t.ts, t.ql, t.qs, t.max_iter, &r, lane, t.step) : wfa_exact<0>(A, t.tl, t.ts, t.ql, t.qs, t.max_iter, &r, lane, t.step);
 	if (rc == 0 && r.n_cigar <= t.cap) for (int32_t i = lane; i < r.n_cigar; i += MGB_W) t.cigar[i] = r.cigar[i];
 	if (lane == 0) t.out[0] = rc, t.out[1] = rc == 0? r.n_cigar : 0, t.out[2] = rc == 0? r.s : 0;
 }
@@ -1597,7 +1600,7 @@ extern "C" int mgb_test_wfa(const char *ts, int tl, const char *qs, int ql, int6
 {
 	if (!dev_ok()) { set_error("no CUDA device available: libmgb200 has no CPU path"); return -100; }
 	TestWfaArgs t;
-	t.tl = tl, t.ql = ql, t.step = step, t.cap = cap, t.max_iter = max_iter, t.arena_bytes = (uint64_t)1 << 30;
+	t.tl = tl, t.ql = ql, t.step = step, t.cap = cap, t.v2 = p_wfa_v2? 1 : 0, t.max_iter = max_iter, t.arena_bytes = (uint64_t)1 << 30;
 	char *d_ts = (char*)dmalloc((size_t)tl + 64), *d_qs = (char*)dmalloc((size_t)ql + 64);
 	h2d(d_ts, ts, (size_t)tl), h2d(d_qs, qs, (size_t)ql);
 	t.ts = d_ts, t.qs = d_qs;

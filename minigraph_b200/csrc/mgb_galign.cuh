@@ -175,7 +175,7 @@ MG_HD inline int wfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int la
 	int rc;
 	if (tier == 1) rc = V2? wfa_smem2<WfTier1::W_, WfTier1::MAXLEN_, WfTier1::TBCAP_>(A, smem, tl, tseq, ql, qs, &rst, lane) : wfa_smem<WfTier1::W_, WfTier1::MAXLEN_, WfTier1::TBCAP_, WfTier1::HS_>(A, smem, tl, tseq, ql, qs, &rst, lane);
 	else if (tier == 2) rc = V2? wfa_smem2<WfTier2::W_, WfTier2::MAXLEN_, WfTier2::TBCAP_>(A, smem, tl, tseq, ql, qs, &rst, lane) : wfa_smem<WfTier2::W_, WfTier2::MAXLEN_, WfTier2::TBCAP_, WfTier2::HS_>(A, smem, tl, tseq, ql, qs, &rst, lane);
-	else rc = wfa_exact(A, tl, tseq, ql, qs, 100000000LL, &rst, lane);
+	else rc = wfa_exact<V2>(A, tl, tseq, ql, qs, 100000000LL, &rst, lane);
 	if (rc < 0) return rc;
 	if (lane == 0) {
 		unsigned long long dt = prof_clock() - pt0;

@@ -1040,6 +1040,9 @@ MG_HD inline int wfa_ring_g(Arena &A, int32_t tl, const char *ts, int32_t ql, co
 
 // Tier 3 entry (reference: miniwfa.c:824-834 mwf_wfa_auto): exact alignment capped at max_iter cells by the whole warp;
 // beyond the cap the chaining heuristic takes over on lane 0.
+MG_HD inline int wfa_ring_g2(Arena &A, int32_t tl, const char *ts, int32_t ql, const char *qs, int64_t max_iter, WfResult *r,
+							 uint32_t *cig_store, int64_t max_cigar, int lane); // second version of the ring (mgb_wfa2.cuh), used when V2
+template<int V2 = 0>
 MG_HD inline int wfa_exact(Arena &A, int32_t tl, const char *ts_g, int32_t ql, const char *qs_g, int64_t max_iter, WfResult *r, int lane, int32_t step = 5000)
 {
 	uint64_t mark = A.top;
@@ -1055,7 +1058,7 @@ MG_HD inline int wfa_exact(Arena &A, int32_t tl, const char *ts_g, int32_t ql, c
 	wf_stage_seq(qs, qs_g, ql, 0xff, lane);
 	warp_sync();
 	{
-		int rc = wfa_ring_g(A, tl, ts, ql, qs, max_iter, r, cig_store, max_cigar, lane);
+		int rc = V2? wfa_ring_g2(A, tl, ts, ql, qs, max_iter, r, cig_store, max_cigar, lane) : wfa_ring_g(A, tl, ts, ql, qs, max_iter, r, cig_store, max_cigar, lane);
 		if (rc < 0) return rc;
 		if (rc == 1) MGB_TRY(wfa_core(A, tl, ts, ql, qs, max_iter, 0, 0, r, cig_store, max_cigar, lane, MGB_W));
 	}

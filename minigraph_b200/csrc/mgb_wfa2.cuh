@@ -187,6 +187,193 @@ MG_HD inline int wfa_smem2(Arena &A, int32_t *smem, int32_t tl, const char *ts_g
 	return 0;
 }
 
+// =================================================================================================================
+// tier 3, second version: the arena ring of wfa_ring_g() (mgb_wfa.cuh) with clean slices
+// =================================================================================================================
+// Same idea as above, with two additions the long runs need.  (1) The ring covers every diagonal of the matrix, far more
+// than a gap ever touches, so the slices are initialised lazily: [flo,fhi] is the span of columns on which all 85
+// slices hold -inf or real cells, and it is extended ahead of the window, 128 columns at a time.  (2) Every 256 scores
+// the band is re-centred and can shrink (miniwfa.c:144-171); a slot then still holds cells of the wider wavefront of 17
+// scores ago outside the new range, which the bounds checks of the first version hide.  Here the part of the old range
+// that sticks out is set back to -inf when the slot is rewritten, which keeps the invariant "a slice holds -inf outside
+// the range it was last written with" and with it every value the recurrence and the band shrink read.
+#define MGB_WF2_FILL(need_lo_, need_hi_) do { \
+		const int32_t nl_ = (need_lo_), nh_ = (need_hi_); \
+		if (fhi < flo || nl_ < flo || nh_ > fhi) { \
+			int32_t tlo_ = nl_ - 128 > -tl - 1? nl_ - 128 : -tl - 1, thi_ = nh_ + 128 < ql + 1? nh_ + 128 : ql + 1; \
+			if (fhi >= flo) { if (nl_ >= flo) tlo_ = flo; if (nh_ <= fhi) thi_ = fhi; } \
+			const int32_t a0_ = tlo_, a1_ = fhi >= flo? flo - 1 : thi_, b0_ = fhi >= flo? fhi + 1 : thi_ + 1, b1_ = thi_; \
+			for (int sl_ = 0; sl_ < 85; ++sl_) { \
+				wf_cell_t *p_ = cells + (int64_t)sl_ * W; \
+				for (int32_t d_ = a0_ + lane; d_ <= a1_; d_ += MGB_W) p_[(d_ + (1 << 20)) & mask] = (wf_cell_t)WF_NEG_INF16; \
+				for (int32_t d_ = b0_ + lane; d_ <= b1_; d_ += MGB_W) p_[(d_ + (1 << 20)) & mask] = (wf_cell_t)WF_NEG_INF16; \
+			} \
+			flo = tlo_, fhi = thi_; \
+			warp_sync(); \
+		} \
+	} while (0)
+
+MG_HD inline int wfa_ring_g2(Arena &A, int32_t tl, const char *ts, int32_t ql, const char *qs, int64_t max_iter, WfResult *r,
+							uint32_t *cig_store, int64_t max_cigar, int lane)
+{
+	if (tl + ql > 16000 || tl <= 0 || ql <= 0) return 1;
+	uint64_t mark = A.top;
+	int32_t W = 64;
+	while (W < tl + ql + 2) W <<= 1;
+	const int32_t mask = W - 1;
+	wf_cell_t *cells;
+	MGB_ALLOC(A, cells, wf_cell_t, (int64_t)5 * 17 * W);
+	wf_cell_t *H = cells, *E1 = H + 17 * W, *F1 = E1 + 17 * W, *E2 = F1 + 17 * W, *F2 = E2 + 17 * W;
+	int32_t flo = 0, fhi = -1; // columns on which all 85 slices have been initialised with -inf (empty so far)
+	const int32_t d_corner = ql - tl;
+	AVec<WfTbRow> rows;
+	avec_init(rows);
+	MGB_TRY(avec_reserve_w(A, rows, 1024, lane));
+	int32_t n_rows = 0;
+	int32_t wlo = 0, whi = 0, last_state = 0, s = 0, stopped = 0;
+	int64_t n_iter = 0;
+	int hs = 0;
+#define MGB_WF_RG(lo_, hi_) ((uint32_t)((hi_) + 0x8000) << 16 | (uint32_t)((lo_) + 0x8000))
+	uint32_t g0 = MGB_WF_RG(0, 0), g1 = MGB_WF_RG(1, 0), g2 = g1, g3 = g1, g4 = g1, g5 = g1, g6 = g1, g7 = g1, g8 = g1, g9 = g1, g10 = g1, g11 = g1, g12 = g1, g13 = g1, g14 = g1, g15 = g1, g16 = g1;
+	int hit = 0, hit_noext = 0;
+	MGB_WF2_FILL(-1, 1);
+	if (lane == 0) { // score 0: the main diagonal, extended from the corner
+		const int32_t c0 = (1 << 20) & mask;
+		int32_t k0 = -1, k = -1;
+		k = wf_extend(ts, qs, k0, 0);
+		if (k == tl - 1 && k == ql - 1) hit = 1, hit_noext = (k == k0), k = k0;
+		H[c0] = (wf_cell_t)k;
+	}
+	{
+		const uint32_t vb = warp_or_u32((hit? 1u : 0u) | (hit_noext? 2u : 0u));
+		hit = vb & 1, hit_noext = vb >> 1 & 1;
+	}
+	warp_sync();
+	for (;;) {
+		if (hit) {
+			if (hit_noext) { WfTbArena t; t.row = rows.a; last_state = t.get(n_rows - 1, ql - tl) & 7; }
+			break;
+		}
+		const int32_t lo = wlo > -tl? wlo - 1 : -tl;
+		const int32_t hi = whi < ql? whi + 1 : ql;
+		const int32_t width = hi - lo + 1;
+		const int32_t ns = s + 1;
+		const int nhs = hs + 1 == 17? 0 : hs + 1;
+		MGB_TRY(avec_reserve_w(A, rows, n_rows + 1, lane));
+		uint8_t *x;
+		MGB_ALLOC(A, x, uint8_t, width);
+		if (lane == 0) rows.a[n_rows].lo = lo, rows.a[n_rows].hi = hi, rows.a[n_rows].x = x;
+		rows.n = ++n_rows;
+		uint8_t *ax = x - lo;
+		const int r4 = nhs >= WF_X? nhs - WF_X : nhs - WF_X + 17, r6 = nhs >= WF_O1 + WF_E1? nhs - (WF_O1 + WF_E1) : nhs - (WF_O1 + WF_E1) + 17;
+		const int r16 = nhs >= WF_O2 + WF_E2? nhs - (WF_O2 + WF_E2) : nhs - (WF_O2 + WF_E2) + 17, r2 = nhs >= WF_E1? nhs - WF_E1 : nhs - WF_E1 + 17;
+		MGB_WF2_FILL(lo - 1, hi + 1);
+		{ // the slot of score ns held score ns-17: after a band shrink that range can reach beyond [lo,hi]; what sticks out becomes -inf again
+			const int32_t olo = (int32_t)(g16 & 0xffffu) - 0x8000, ohi = (int32_t)(g16 >> 16) - 0x8000;
+			if (olo < lo || ohi > hi) {
+				for (int a5 = 0; a5 < 5; ++a5) {
+					wf_cell_t *p = cells + ((int64_t)a5 * 17 + nhs) * W;
+					for (int32_t d = olo + lane; d <= ohi && d < lo; d += MGB_W) p[(d + (1 << 20)) & mask] = (wf_cell_t)WF_NEG_INF16;
+					for (int32_t d = (hi + 1 > olo? hi + 1 : olo) + lane; d <= ohi; d += MGB_W) p[(d + (1 << 20)) & mask] = (wf_cell_t)WF_NEG_INF16;
+				}
+			}
+		}
+		// byte offsets of the source and destination slices inside their arrays (kept in registers, see wfa_smem2)
+		int32_t bHx = r4 * W * 2, bHo1 = r6 * W * 2, bHo2 = r16 * W * 2, bE1 = r2 * W * 2, bE2 = hs * W * 2, bN = nhs * W * 2;
+		MGB_OPAQUE(bHx); MGB_OPAQUE(bHo1); MGB_OPAQUE(bHo2); MGB_OPAQUE(bE1); MGB_OPAQUE(bE2); MGB_OPAQUE(bN);
+		uint32_t vote = 0; // 1: window grows on the low side, 2: on the high side, 4: corner reached, 8: ... without extension
+		const int32_t mask2 = 2 * W - 1;
+		for (int32_t d = lo + lane; d <= hi; d += MGB_W) { // reference: miniwfa.c:281-308 wf_next_tb, then :212-226 on the new cell
+			int32_t h, f, e, e1, e2, f1, f2, a0, b0;
+			uint8_t xb = 0, ze, zf, z;
+			const int32_t c2 = ((d + (1 << 20)) & mask) * 2, cm = (c2 - 2) & mask2, cp = (c2 + 2) & mask2; // byte columns
+			a0 = wf2_ld(H, bHo1 + cm), b0 = wf2_ld(E1, bE1 + cm);
+			xb |= a0 >= b0? 0 : 0x08; e1 = MGB_WF_MAX(a0, b0);
+			a0 = wf2_ld(H, bHo2 + cm), b0 = wf2_ld(E2, bE2 + cm);
+			xb |= a0 >= b0? 0 : 0x20; e2 = MGB_WF_MAX(a0, b0);
+			ze = e1 >= e2? 1 : 3;
+			e = MGB_WF_MAX(e1, e2);
+			a0 = wf2_ld(H, bHo1 + cp), b0 = wf2_ld(F1, bE1 + cp);
+			xb |= a0 >= b0? 0 : 0x10; f1 = MGB_WF_MAX(a0, b0) + 1;
+			a0 = wf2_ld(H, bHo2 + cp), b0 = wf2_ld(F2, bE2 + cp);
+			xb |= a0 >= b0? 0 : 0x40; f2 = MGB_WF_MAX(a0, b0) + 1;
+			zf = f1 >= f2? 2 : 4;
+			f = MGB_WF_MAX(f1, f2);
+			z = e >= f? ze : zf;
+			h = MGB_WF_MAX(e, f);
+			a0 = wf2_ld(H, bHx + c2) + 1;
+			z = a0 >= h? 0 : z;
+			h = MGB_WF_MAX(a0, h);
+			ax[d] = xb | z;
+			if (d == lo || d == hi) {
+				if (h >= -1 || e1 >= -1 || f1 >= -1 || e2 >= -1 || f2 >= -1) vote |= (d == lo? 1u : 0u) | (d == hi? 2u : 0u);
+			}
+			if (!(h < -1 || d + h < -1 || h >= tl || d + h >= ql)) {
+				const int32_t k = wf_extend(ts, qs, h, d);
+				if (d == d_corner && k == tl - 1) vote |= 4u | (k == h? 8u : 0u);
+				else h = k;
+			}
+			const int32_t bo = bN + c2;
+			*(wf_cell_t*)((char*)E1 + bo) = (wf_cell_t)e1, *(wf_cell_t*)((char*)F1 + bo) = (wf_cell_t)f1, *(wf_cell_t*)((char*)E2 + bo) = (wf_cell_t)e2, *(wf_cell_t*)((char*)F2 + bo) = (wf_cell_t)f2, *(wf_cell_t*)((char*)H + bo) = (wf_cell_t)h;
+		}
+		vote = warp_or_u32(vote);
+		if (vote & 1) wlo = lo;
+		if (vote & 2) whi = hi;
+		hit = vote >> 2 & 1, hit_noext = vote >> 3 & 1;
+		g16 = g15, g15 = g14, g14 = g13, g13 = g12, g12 = g11, g11 = g10, g10 = g9, g9 = g8, g8 = g7, g7 = g6, g6 = g5, g5 = g4, g4 = g3, g3 = g2, g2 = g1, g1 = g0;
+		g0 = MGB_WF_RG(lo, hi);
+		s = ns, hs = nhs;
+		warp_sync();
+		if ((s & 0xff) == 0) { // reference: miniwfa.c:144-171 wf_stripe_shrink: keep the diagonals on which one of the 17 wavefronts still has a cell inside the matrix
+			const uint32_t gg[17] = { g0, g1, g2, g3, g4, g5, g6, g7, g8, g9, g10, g11, g12, g13, g14, g15, g16 };
+			int32_t nlo = 0, nhi = 0, found = 0;
+			for (int pass = 0; pass < 2; ++pass) {
+				found = 0;
+				for (int32_t base = pass == 0? wlo : whi; pass == 0? base <= whi : base >= wlo; base += pass == 0? MGB_W : -MGB_W) {
+					const int32_t d = pass == 0? base + lane : base - lane;
+					int good = 0;
+					if (d >= wlo && d <= whi) {
+						const int32_t c = (d + (1 << 20)) & mask;
+						for (int j = 0; j < 17 && !good; ++j) {
+							const int32_t jl = (int32_t)(gg[j] & 0xffffu) - 0x8000, jh = (int32_t)(gg[j] >> 16) - 0x8000;
+							if (d < jl || d > jh) continue;
+							const int slot = hs >= j? hs - j : hs - j + 17;
+							const int64_t o = (int64_t)slot * W + c;
+							good = wf_good_diag(d, H[o], tl, ql) || wf_good_diag(d, E1[o], tl, ql) || wf_good_diag(d, F1[o], tl, ql) || wf_good_diag(d, E2[o], tl, ql) || wf_good_diag(d, F2[o], tl, ql);
+						}
+					}
+					const uint32_t m = warp_ballot(good);
+					if (m) { found = 1; if (pass == 0) nlo = base + ctz32(m); else nhi = base - ctz32(m); break; }
+				}
+				if (!found) break;
+			}
+			if (!found) { A.top = mark; return MGB_E_INTERNAL; }
+			wlo = nlo, whi = nhi;
+		}
+		n_iter += width;
+		if (max_iter > 0 && n_iter > max_iter) { stopped = 1; break; }
+	}
+#undef MGB_WF_RG
+	r->n_iter = n_iter;
+	r->s = stopped? -1 : s;
+	if (!stopped) {
+		int rc = 0;
+		int32_t n_cig = 0;
+		int64_t first = 0;
+		if (lane == 0) {
+			WfTbArena t; t.row = rows.a;
+			rc = wf_traceback(t, n_rows, tl, ts, ql, qs, last_state, cig_store, max_cigar, &n_cig, &first);
+		}
+		rc = warp_bcast_i32(rc, 0), n_cig = warp_bcast_i32(n_cig, 0), first = (int64_t)warp_bcast_u64((uint64_t)first, 0);
+		warp_sync();
+		if (rc < 0) { A.top = mark; return rc; }
+		r->n_cigar = n_cig, r->cigar = cig_store + first;
+	}
+	A.top = mark;
+	return 0;
+}
+#undef MGB_WF2_FILL
+
 typedef WfSmemLayout<64, 256, 4096, 17> WfTier1v2; // the layouts of the first version
 typedef WfSmemLayout<256, 1024, 0, 17> WfTier2v2;
 

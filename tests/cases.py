@@ -92,23 +92,37 @@ def case_struct_random(lib, workdir, n_reads=150, seed=23):
     return st
 
 
+_mwf = None
+
+
+def _mwf_types():
+    """ctypes view of miniwfa.h:36-51 (mwf_opt_t, mwf_rst_t) and the prototypes of the reference functions used as the checker"""
+    global _mwf
+    if _mwf is None:
+        import ctypes as C
+        ref = T.load_ref()
+
+        class mwf_opt_t(C.Structure):
+            _fields_ = [("flag", C.c_int32), ("x", C.c_int32), ("o1", C.c_int32), ("e1", C.c_int32), ("o2", C.c_int32), ("e2", C.c_int32),
+                        ("step", C.c_int32), ("max_s", C.c_int32), ("max_iter", C.c_int64), ("max_occ", C.c_int32), ("kmer", C.c_int32), ("min_len", C.c_int32)]
+
+        class mwf_rst_t(C.Structure):
+            _fields_ = [("s", C.c_int32), ("n_cigar", C.c_int32), ("n_iter", C.c_int64), ("cigar", C.POINTER(C.c_uint32))]
+        for f in (ref.mwf_wfa_exact, ref.mwf_wfa_chain):
+            f.restype = None
+            f.argtypes = [C.c_void_p, C.POINTER(mwf_opt_t), C.c_int32, C.c_char_p, C.c_int32, C.c_char_p, C.POINTER(mwf_rst_t)]
+        ref.mwf_opt_init.argtypes = [C.POINTER(mwf_opt_t)]
+        _mwf = (mwf_opt_t, mwf_rst_t)
+    return _mwf
+
+
 def case_wfa_fallback(lib, n_cases=12, seed=5):
     """gaps whose exact WFA exceeds the cell cap take the reference's chaining heuristic + low-memory checkpoints
     (miniwfa.c:551-601,776-834): same CIGAR and score as mwf_wfa_exact(max_iter) -> mwf_wfa_chain(step) of the reference"""
     import ctypes as C
     import random
     ref = T.load_ref()
-
-    class mwf_opt_t(C.Structure):
-        _fields_ = [("flag", C.c_int32), ("x", C.c_int32), ("o1", C.c_int32), ("e1", C.c_int32), ("o2", C.c_int32), ("e2", C.c_int32),
-                    ("step", C.c_int32), ("max_s", C.c_int32), ("max_iter", C.c_int64), ("max_occ", C.c_int32), ("kmer", C.c_int32), ("min_len", C.c_int32)]
-
-    class mwf_rst_t(C.Structure):
-        _fields_ = [("s", C.c_int32), ("n_cigar", C.c_int32), ("n_iter", C.c_int64), ("cigar", C.POINTER(C.c_uint32))]
-    for f in (ref.mwf_wfa_exact, ref.mwf_wfa_chain):
-        f.restype = None
-        f.argtypes = [C.c_void_p, C.POINTER(mwf_opt_t), C.c_int32, C.c_char_p, C.c_int32, C.c_char_p, C.POINTER(mwf_rst_t)]
-    ref.mwf_opt_init.argtypes = [C.POINTER(mwf_opt_t)]
+    mwf_opt_t, mwf_rst_t = _mwf_types()
     rng = random.Random(seed)
 
     def mutate(s, rate):
@@ -226,6 +240,38 @@ def case_full_size(lib, workdir, n_reads=10000, n_sub=300, n_ref=100, seed=11):
             assert d is None, "read %d vs reference: %s" % (i, d)
 
 
+def case_wfa_divergent(lib, n_cases=24, seed=5):
+    """unrelated sequences of unequal length: the band reaches the matrix borders, is re-centred and shrinks
+    (miniwfa.c:144-171) -- what the tier-3 ring has to get right when slots are reused by narrower wavefronts"""
+    import ctypes as C
+    import random
+    ref = T.load_ref()
+    mwf_opt_t, mwf_rst_t = _mwf_types()
+    rng = random.Random(seed)
+    for it in range(n_cases):
+        tl = rng.choice([150, 300, 500, 800])
+        ql = max(20, int(tl * rng.choice([0.3, 0.7, 1.0, 1.5])))
+        t = "".join(rng.choice("ACGT") for _ in range(tl))
+        q = "".join(rng.choice("ACGT") for _ in range(ql))
+        if it % 3 == 0:  # a shared core between random flanks
+            core = "".join(rng.choice("ACGT") for _ in range(100))
+            t, q = t[:tl // 2] + core + t[tl // 2:], q[:ql // 3] + core + q[ql // 3:]
+        ts, qs = t.encode(), q.encode()
+        opt = mwf_opt_t()
+        ref.mwf_opt_init(C.byref(opt))
+        opt.flag |= 1
+        opt.step, opt.max_iter = 0, 10 ** 8
+        rst = mwf_rst_t()
+        ref.mwf_wfa_exact(None, C.byref(opt), len(ts), ts, len(qs), qs, C.byref(rst))
+        assert rst.s >= 0
+        want = [rst.cigar[i] for i in range(rst.n_cigar)]
+        cap = len(ts) + len(qs) + 8
+        buf = (C.c_uint32 * cap)()
+        score = C.c_int(0)
+        nc = lib.mgb_test_wfa(ts, len(ts), qs, len(qs), 10 ** 8, 5000, buf, cap, C.byref(score))
+        assert nc >= 0 and [buf[i] for i in range(nc)] == want and score.value == rst.s, (it, tl, ql, score.value, rst.s)
+
+
 def case_wfa_v2(lib, workdir, n_struct=60):
     """the second version of the on-chip gap alignment ("wfa_v2", off by default; mgb_wfa2.cuh): slices that hold -inf
     outside their range instead of bounds checks.  Same GAF for the golden cases (lr and asm presets, both on-chip tiers
@@ -241,6 +287,8 @@ def case_wfa_v2(lib, workdir, n_struct=60):
         if T.have_ref():
             case_struct_random(lib, workdir, n_reads=n_struct, seed=37)
             case_tier_routing(lib, workdir)
+            case_wfa_fallback(lib)  # tier 3 against miniwfa: scores far past 256 (band re-centring), capped runs, a gap beyond the 16-bit ring
+            case_wfa_divergent(lib)
     finally:
         lib.mgb_set_param(b"wfa_v2", 0)
 

@@ -89,3 +89,4 @@ def test_block_per_gap_tier(lib, workdir):
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not shipped")
 def test_wfa_iteration_cap_fallback(lib):
     cases.case_wfa_fallback(lib, n_cases=10)
+    cases.case_wfa_divergent(lib)

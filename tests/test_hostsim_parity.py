@@ -63,6 +63,7 @@ def test_struct_fields_vs_reference(lib, workdir):
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
 def test_wfa_iteration_cap_fallback(lib):
     cases.case_wfa_fallback(lib)
+    cases.case_wfa_divergent(lib)
 
 
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
