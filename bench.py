@@ -189,14 +189,11 @@ def main():
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib = capi.load_product()
+    lib = capi.load_product()  # applies MGB_PARAMS (engine switches for experiments)
     lib.mgb_set_param(b"device", local_rank)
     # host threads for packing, result assembly and GAF text: this rank's share of the box (two pools run at once)
     host_threads = max(4, min(48, ncores // (2 * world)))
     lib.mgb_set_param(b"host_threads", host_threads)
-    for kv in os.environ.get("MGB_PARAMS", "").split(","):
-        if "=" in kv:
-            lib.mgb_set_param(kv.split("=")[0].encode(), int(kv.split("=")[1], 0))
     gfa, fa = make_workload_c3(tmp, rank, a.reads) if a.workload == "c3" else make_workload(tmp, rank, a.reads)
     names, seqs = read_fasta(fa)
     n = len(seqs)
@@ -347,7 +344,7 @@ def main():
         "metric": "mapped Gbp/s (-cx lr)", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": t_kern / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64/u8 (fp32 chain penalties, bit-exact)", "data": "synthetic",
-        "config": {"workload": workload, "reads_per_gpu": n, "bases_per_gpu": bases, "l2": "512 MiB flush buffer written between steps",
+        "config": {"workload": workload, "reads_per_gpu": n, "bases_per_gpu": bases, "l2": "512 MiB flush buffer written between steps", "engine_params": capi.env_params(),
                    "parallelism": "reads sharded one batch per GPU, index replicated; all-gather of GAF byte counts only",
                    "gaf_offsets": offsets},
         "sub_batches": n_slots, "host_threads": host_threads, "host_cores": ncores,

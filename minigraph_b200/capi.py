@@ -121,13 +121,30 @@ def bind_mapping_api(lib):
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def env_params():
+    """engine switches from the environment: MGB_PARAMS="wfa_v2=1,cta_len=1500" (pairs for mgb_set_param)"""
+    out = {}
+    for kv in os.environ.get("MGB_PARAMS", "").split(","):
+        if "=" in kv:
+            k, v = kv.split("=", 1)
+            out[k.strip()] = int(v, 0)
+    return out
+
+
+def apply_env_params(lib):
+    for k, v in env_params().items():
+        if lib.mgb_set_param(k.encode(), v) != 0:
+            raise RuntimeError("MGB_PARAMS: unknown engine parameter %r" % k)
+    return lib
+
+
 def load_product(path=None):
     """Load libmgb200.so (the CUDA build). Fails loudly when it has not been built -- there is no fallback."""
     path = path or os.path.join(_REPO, "minigraph_b200", "libmgb200.so")
     if not os.path.exists(path):
         raise RuntimeError("libmgb200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
     lib = C.CDLL(path)
-    return bind_engine_api(bind_mapping_api(lib))
+    return apply_env_params(bind_engine_api(bind_mapping_api(lib)))
 
 
 def bind_engine_api(lib):

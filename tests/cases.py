@@ -290,7 +290,7 @@ def case_wfa_v2(lib, workdir, n_struct=60):
             case_wfa_fallback(lib)  # tier 3 against miniwfa: scores far past 256 (band re-centring), capped runs, a gap beyond the 16-bit ring
             case_wfa_divergent(lib)
     finally:
-        lib.mgb_set_param(b"wfa_v2", 0)
+        lib.mgb_set_param(b"wfa_v2", capi.env_params().get("wfa_v2", 0))
 
 
 def case_cta(lib, workdir, n_cases=12):
@@ -307,7 +307,7 @@ def case_cta(lib, workdir, n_cases=12):
         case_wfa_fallback(lib, n_cases=n_cases)
         assert lib.mgb_set_param(b"cta_taken", 0) >= 3
     finally:
-        lib.mgb_set_param(b"cta_len", 0)
+        lib.mgb_set_param(b"cta_len", capi.env_params().get("cta_len", 0))
 
 
 def case_switches(lib, workdir, device):

@@ -46,7 +46,7 @@ def load_hostsim():
     if _hostsim is None:
         subprocess.check_call(["make", "-s", "-C", os.path.join(REPO, "tests", "hostsim")])
         lib = C.CDLL(HOSTSIM_SO)
-        _hostsim = capi.bind_engine_api(capi.bind_mapping_api(lib))
+        _hostsim = capi.apply_env_params(capi.bind_engine_api(capi.bind_mapping_api(lib)))
     return _hostsim
 
 
@@ -59,7 +59,7 @@ def load_hostsim32():
     if _hostsim32 is None:
         subprocess.check_call(["make", "-s", "-C", os.path.join(REPO, "tests", "hostsim"), "libmgb_hostsim32.so"])
         lib = C.CDLL(os.path.join(REPO, "tests", "hostsim", "libmgb_hostsim32.so"))
-        _hostsim32 = capi.bind_engine_api(capi.bind_mapping_api(lib))
+        _hostsim32 = capi.apply_env_params(capi.bind_engine_api(capi.bind_mapping_api(lib)))
     return _hostsim32
 
 
