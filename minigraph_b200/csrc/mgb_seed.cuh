@@ -31,7 +31,7 @@ MG_HD inline int sketch_seq(Arena &A, const char *str, int len, int w, int k, ui
 			int z = kmer[0] < kmer[1]? 0 : 1;
 			++l;
 			if (l >= k && kmer_span < 256) {
-				info.x = hash64_mask(kmer[z], mask) << 8 | (uint64_t)kmer_span;
+				info.x = hash64_mask(z? kmer[1] : kmer[0], mask) << 8 | (uint64_t)kmer_span; // a select: indexing kmer[] by z would put it in local memory
 				info.y = (uint64_t)rid << 32 | (uint64_t)((uint32_t)i << 1) | (uint64_t)z;
 			}
 		} else l = 0, kmer_span = 0;
@@ -105,7 +105,7 @@ MG_HD inline int sketch_chunk(const char *str, int w, int k, uint32_t rid, int p
 		int z = kmer[0] < kmer[1]? 0 : 1;
 		if (l < w + k + 1) ++l;
 		if (l >= k && kmer_span < 256) {
-			info.x = hash64_mask(kmer[z], mask) << 8 | (uint64_t)kmer_span;
+			info.x = hash64_mask(z? kmer[1] : kmer[0], mask) << 8 | (uint64_t)kmer_span; // a select: indexing kmer[] by z would put it in local memory
 			info.y = (uint64_t)rid << 32 | (uint64_t)((uint32_t)i << 1) | (uint64_t)z;
 		}
 		buf[buf_pos] = info;
