@@ -287,6 +287,8 @@ def case_wfa_v2(lib, workdir, n_struct=60):
         if T.have_ref():
             case_struct_random(lib, workdir, n_reads=n_struct, seed=37)
             case_tier_routing(lib, workdir)
+            case_short_reads(lib, workdir, n_pairs=20)  # sr preset: tier 1 only, two-segment fragments
+            case_edge(lib, workdir)
             case_wfa_fallback(lib)  # tier 3 against miniwfa: scores far past 256 (band re-centring), capped runs, a gap beyond the 16-bit ring
             case_wfa_divergent(lib)
     finally:
