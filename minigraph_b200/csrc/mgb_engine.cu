@@ -48,14 +48,15 @@ static int64_t p_slot_workers = 0;
 static int64_t p_tier_learn = 1;       // 0: every gap tries every tier (no routing)
 static int64_t p_side_warps = 1;       // warps per SM of that side launch
 static int g_test_wfa_cta_taken = 0;   // gaps of mgb_test_wfa() answered by the block function so far (mgb_set_param("cta_taken", v) returns it and sets it to v)
+static int64_t p_seed_v2 = 0;          // 1: the sketch keeps its window rings in shared memory (k_seed2); not yet measured
 static int64_t p_wfa_v2 = 0;           // 1: tiers 1/2 run the padded-slice version of the on-chip alignment (mgb_wfa2.cuh); not yet measured
 static int64_t p_cta_len = 0;          // > 0: tier-3 gaps with tl + ql at or above this are first offered to a block-per-gap kernel (k_wfa_cta); not yet measured
 static int64_t p_big_len = 0;          // > 0: gaps with tl or ql at or above this go to a tier-3 launch on a second stream beside tiers 1/2
                                        // (measured on B200 with 384: tier 3 -3 ms, tier 1 +7 ms from the shared SMs -- off)
 
 // launch shape per stage: warps per block and blocks per SM wanted (tunable for experiments: "sw<stage>", "mb<stage>")
-static int STAGE_MINB[13] = { 8, 8, 8, 8, 5, 8, 7, 4, 4, 4, 5, 7, 4 };  // 10, 11, 12: second version of tiers 1, 2 and 3 ("wfa_v2")
-static int STAGE_WARPS[13] = { 4, 4, 4, 4, 4, 4, 2, 4, 4, 4, 4, 2, 4 };
+static int STAGE_MINB[14] = { 8, 8, 8, 8, 5, 8, 7, 4, 4, 4, 5, 7, 4, 8 };  // 10, 11, 12: second version of tiers 1, 2 and 3 ("wfa_v2"); 13: of the seeding stage ("seed_v2")
+static int STAGE_WARPS[14] = { 4, 4, 4, 4, 4, 4, 2, 4, 4, 4, 4, 2, 4, 4 };
 extern "C" const char *mgb_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char *mgb_version(void) { return "mgb200-r1"; }
 extern "C" int mgb_set_param(const char *key, int64_t value)
@@ -72,6 +73,7 @@ extern "C" int mgb_set_param(const char *key, int64_t value)
 	else if (!strcmp(key, "big_len")) p_big_len = value;
 	else if (!strcmp(key, "cta_len")) p_cta_len = value;
 	else if (!strcmp(key, "wfa_v2")) p_wfa_v2 = value;
+	else if (!strcmp(key, "seed_v2")) p_seed_v2 = value;
 	else if (!strcmp(key, "cta_taken")) { int n = g_test_wfa_cta_taken; g_test_wfa_cta_taken = (int)value; return n; } // test hook counter: returns it, then sets it
 	else if (!strcmp(key, "side_warps")) p_side_warps = value;
 	else if (!strcmp(key, "tier_learn")) p_tier_learn = value;
@@ -189,11 +191,12 @@ struct LaunchArgs {
 //         materialisation + alignment plan (K7b), 4/6/7 WFA jobs tier 1/2/3 (K8a), 5 finish: CIGAR stitching + ds + result
 //         blob (K8b), 3 segment sketch for the index
 #define MGB_IS_WFA(STAGE) ((STAGE) == 4 || (STAGE) == 6 || (STAGE) == 7 || (STAGE) == 10 || (STAGE) == 11 || (STAGE) == 12)
-#define MGB_IS_WARP(STAGE) (MGB_IS_WFA(STAGE) || (STAGE) == 8 || (STAGE) == 1 || (STAGE) == 0 || (STAGE) == 5) // stages entered by all lanes of the warp
+#define MGB_IS_WARP(STAGE) (MGB_IS_WFA(STAGE) || (STAGE) == 8 || (STAGE) == 1 || (STAGE) == 0 || (STAGE) == 5 || (STAGE) == 13) // stages entered by all lanes of the warp
 template<int STAGE>
 MG_HD inline int run_stage(const LaunchArgs &L, int item, Arena &A, int lane, int32_t *smem)
 {
 	if (STAGE == 0) return stage_seed(L.c, item, A, lane);
+	if (STAGE == 13) return stage_seed<1>(L.c, item, A, lane, smem);
 	if (STAGE == 1) return stage_chain(L.c, item, A, lane, smem);
 	if (STAGE == 2) return stage_gchain(L.c, L.routs, item, A);
 	if (STAGE == 5) return stage_finish(L.c, L.routs, item, A, lane);
@@ -249,7 +252,7 @@ __device__ __forceinline__ void stage_loop(const LaunchArgs &L)
 	Arena A;
 	arena_init(A, L.arena_base + (uint64_t)worker * L.arena_bytes, L.arena_bytes);
 	extern __shared__ int4 dyn_smem[];
-	const int smem_stride = STAGE == 4? WfTier1::STRIDE : STAGE == 6? WfTier2::STRIDE : STAGE == 10? WfTier1v2::STRIDE : STAGE == 11? WfTier2v2::STRIDE : STAGE == 8? GWFA_SMEM_ARENA : 0;
+	const int smem_stride = STAGE == 4? WfTier1::STRIDE : STAGE == 6? WfTier2::STRIDE : STAGE == 10? WfTier1v2::STRIDE : STAGE == 11? WfTier2v2::STRIDE : STAGE == 13? SKETCH_SMEM_BYTES : STAGE == 8? GWFA_SMEM_ARENA : 0;
 	int32_t *smem = smem_stride? (int32_t*)((char*)dyn_smem + (size_t)(threadIdx.x >> 5) * smem_stride) : 0;
 	for (;;) {
 		int item = 0;
@@ -308,6 +311,7 @@ MGB_KERNEL(k_finish, 5, 8)        // K8b: CIGAR stitching, ds strings, result bl
 MGB_KERNEL(k_wfa_small2, 10, 5)   // tier 1, second version (mgb_wfa2.cuh; parameter "wfa_v2")
 MGB_KERNEL(k_wfa_mid2, 11, 5)     // tier 2, second version
 MGB_KERNEL(k_wfa_big2, 12, 4)     // tier 3, second version
+MGB_KERNEL(k_seed2, 13, 8)        // K1-K3 with the sketch's window rings in shared memory (parameter "seed_v2")
 template<int STAGE> struct StageKernel;
 template<> struct StageKernel<0> { static void (*get())(LaunchArgs) { return k_seed; } };
 template<> struct StageKernel<1> { static void (*get())(LaunchArgs) { return k_chain; } };
@@ -322,6 +326,7 @@ template<> struct StageKernel<5> { static void (*get())(LaunchArgs) { return k_f
 template<> struct StageKernel<10> { static void (*get())(LaunchArgs) { return k_wfa_small2; } };
 template<> struct StageKernel<11> { static void (*get())(LaunchArgs) { return k_wfa_mid2; } };
 template<> struct StageKernel<12> { static void (*get())(LaunchArgs) { return k_wfa_big2; } };
+template<> struct StageKernel<13> { static void (*get())(LaunchArgs) { return k_seed2; } };
 #endif
 
 // Longest-first order of a job list (a tail of a few long jobs otherwise decides the kernel time).  Jobs are binned by
@@ -473,7 +478,7 @@ static void launch_stage(LaunchArgs &L, const Workers &W, int warps_override = 0
 #ifdef MGB_HOSTSIM
 	Arena A;
 	arena_init(A, W.arena, W.arena_bytes);
-	std::vector<int32_t> sim_smem(std::max<size_t>(std::max<size_t>(WfTier1v2::STRIDE, WfTier2v2::STRIDE), std::max<size_t>(GWFA_SMEM_ARENA, CHAIN_SMEM)) / 4);
+	std::vector<int32_t> sim_smem(std::max<size_t>(std::max<size_t>(WfTier1v2::STRIDE, WfTier2v2::STRIDE), std::max<size_t>(std::max<size_t>(GWFA_SMEM_ARENA, CHAIN_SMEM), SKETCH_SMEM_BYTES)) / 4);
 	for (int it = 0; it < L.n_work; ++it) {
 		int item = L.rid_list? L.rid_list[it] : it;
 		A.top = 0;
@@ -503,7 +508,7 @@ static void launch_stage(LaunchArgs &L, const Workers &W, int warps_override = 0
 	int want = dev_sm_count() * STAGE_MINB[STAGE] * STAGE_WARPS[STAGE]; // resident warps this stage can keep on the chip
 	int n_w = std::min(W.n_workers, want);
 	int blocks = std::max(1, n_w / warps);
-	size_t smem = STAGE == 4? (size_t)warps * WfTier1::STRIDE : STAGE == 6? (size_t)warps * WfTier2::STRIDE : STAGE == 10? (size_t)warps * WfTier1v2::STRIDE : STAGE == 11? (size_t)warps * WfTier2v2::STRIDE : STAGE == 8? (size_t)warps * GWFA_SMEM_ARENA : 0;
+	size_t smem = STAGE == 4? (size_t)warps * WfTier1::STRIDE : STAGE == 6? (size_t)warps * WfTier2::STRIDE : STAGE == 10? (size_t)warps * WfTier1v2::STRIDE : STAGE == 11? (size_t)warps * WfTier2v2::STRIDE : STAGE == 13? (size_t)warps * SKETCH_SMEM_BYTES : STAGE == 8? (size_t)warps * GWFA_SMEM_ARENA : 0;
 	void (*kern)(LaunchArgs) = StageKernel<STAGE>::get();
 	if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	L.thread_mode = (p_thread_mask >> STAGE) & 1;
@@ -1127,7 +1132,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 			if (first_kernel) { CUDA_OK(cudaEventRecord(sl.ev_first, t_stream)); first_kernel = false; }
 #endif
 			if (timed) tm_seed.start();
-			{ if (timed) tm_k[0].start(); launch_stage<0>(L, W); if (timed) tm_k[0].stop(); }
+			{ if (timed) tm_k[0].start(); if (p_seed_v2) launch_stage<13>(L, W); else launch_stage<0>(L, W); if (timed) tm_k[0].stop(); }
 			if (timed) tm_seed.stop(), tm_chain.start();
 			{ if (timed) tm_k[1].start(); launch_stage<1>(L, W); if (timed) tm_k[1].stop(); }
 			if (timed) tm_chain.stop(), tm_align.start();

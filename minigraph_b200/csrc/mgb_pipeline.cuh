@@ -71,7 +71,8 @@ MG_HD inline void prof_max(const PipeCtx &c, int slot, unsigned long long v)
 // mini_pos pool.
 // Warp-uniform: all lanes enter; the sketch is cut into chunks over the lanes, the index probes and the seed expansion
 // are spread over the lanes, the (order-sensitive, unstable) seed sort runs on lane 0.
-MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A, int lane)
+template<int V2 = 0> // V2: the window rings of the sketch live in shared memory (smem: SKETCH_SMEM_BYTES per warp), parameter "seed_v2"
+MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A, int lane, int32_t *smem = 0)
 {
 	ReadMeta &m = c.meta[rid];
 	const char *seq = c.b.seq + c.b.seq_off[rid];
@@ -94,7 +95,7 @@ MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A, int lane)
 	unsigned long long t0 = prof_clock();
 	const int32_t n_seg = batch_n_seg(c.b, rid);
 	if (n_seg == 1) {
-		MGB_TRY(sketch_seq_w(A, seq, qlen, c.ix.w, c.ix.k, 0, mv, lane));
+		MGB_TRY(sketch_seq_w(A, seq, qlen, c.ix.w, c.ix.k, 0, mv, lane, V2? (u128*)smem : 0));
 	} else { // reference: map-algo.c:34-45 collect_minimizers: every segment on its own, positions shifted by the lengths before it
 		const int32_t *sl = c.b.seg_len + c.b.seg_off[rid];
 		MGB_ALLOC(A, mv.a, u128, (int64_t)qlen + 16 * (int64_t)n_seg);
@@ -104,7 +105,7 @@ MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A, int lane)
 		for (int32_t i = 0; i < n_seg; ++i) {
 			AVec<u128> one;
 			avec_init(one);
-			if (sl[i] > 0) MGB_TRY(sketch_seq_w(A, seq + sum, sl[i], c.ix.w, c.ix.k, (uint32_t)i, one, lane));
+			if (sl[i] > 0) MGB_TRY(sketch_seq_w(A, seq + sum, sl[i], c.ix.w, c.ix.k, (uint32_t)i, one, lane, V2? (u128*)smem : 0));
 			if (mv.n + one.n > mv.m) return MGB_E_INTERNAL;
 			for (int64_t j = lane; j < one.n; j += MGB_W) { u128 e = one.a[j]; e.y += (uint64_t)sum << 1; mv.a[mv.n + j] = e; }
 			warp_sync();

@@ -75,6 +75,9 @@ MG_HD inline int sketch_seq(Arena &A, const char *str, int len, int w, int k, ui
 // sketch_seq() on the whole sequence.
 static const int SKETCH_CHUNKS = 32;
 
+// BS: distance between two slots of the window ring (1: a private ring in the arena; 32: the rings of the 32 lanes interleaved in
+// shared memory, slot j of lane l at [j * 32 + l], so that the lanes of a warp touch consecutive 16-byte words)
+template<int BS = 1>
 MG_HD inline int sketch_chunk(const char *str, int w, int k, uint32_t rid, int p, int end, int is_first, int is_last, u128 *buf, u128 *outp, int cap, int *n_out)
 {
 	const uint64_t shift1 = 2 * (k - 1), mask = (1ULL << 2 * k) - 1;
@@ -82,7 +85,7 @@ MG_HD inline int sketch_chunk(const char *str, int w, int k, uint32_t rid, int p
 	int l = 0, buf_pos = 0, min_pos = 0, kmer_span = 0, n = 0, i0 = 0;
 	const u128 none = { ~0ULL, ~0ULL };
 	u128 mn = none;
-	for (int j = 0; j < w; ++j) buf[j] = none;
+	for (int j = 0; j < w; ++j) buf[(j) * BS] = none;
 	if (!is_first) {
 		i0 = p - w;
 		for (int i = i0 - k + 1; i < i0; ++i) { // the k-1 bases in front of the first warm-up slot
@@ -108,12 +111,12 @@ MG_HD inline int sketch_chunk(const char *str, int w, int k, uint32_t rid, int p
 			info.x = hash64_mask(z? kmer[1] : kmer[0], mask) << 8 | (uint64_t)kmer_span; // a select: indexing kmer[] by z would put it in local memory
 			info.y = (uint64_t)rid << 32 | (uint64_t)((uint32_t)i << 1) | (uint64_t)z;
 		}
-		buf[buf_pos] = info;
+		buf[(buf_pos) * BS] = info;
 		if (l == w + k - 1 && mn.x != ~0ULL) {
 			for (int j = buf_pos + 1; j < w; ++j)
-				if (mn.x == buf[j].x && buf[j].y != mn.y) MGB_SK_PUSH(buf[j]);
+				if (mn.x == buf[(j) * BS].x && buf[(j) * BS].y != mn.y) MGB_SK_PUSH(buf[(j) * BS]);
 			for (int j = 0; j < buf_pos; ++j)
-				if (mn.x == buf[j].x && buf[j].y != mn.y) MGB_SK_PUSH(buf[j]);
+				if (mn.x == buf[(j) * BS].x && buf[(j) * BS].y != mn.y) MGB_SK_PUSH(buf[(j) * BS]);
 		}
 		if (info.x <= mn.x) {
 			if (l >= w + k && mn.x != ~0ULL) MGB_SK_PUSH(mn);
@@ -122,14 +125,14 @@ MG_HD inline int sketch_chunk(const char *str, int w, int k, uint32_t rid, int p
 			if (l >= w + k - 1 && mn.x != ~0ULL) MGB_SK_PUSH(mn);
 			mn.x = ~0ULL;
 			for (int j = buf_pos + 1; j < w; ++j)
-				if (mn.x >= buf[j].x) mn = buf[j], min_pos = j;
+				if (mn.x >= buf[(j) * BS].x) mn = buf[(j) * BS], min_pos = j;
 			for (int j = 0; j <= buf_pos; ++j)
-				if (mn.x >= buf[j].x) mn = buf[j], min_pos = j;
+				if (mn.x >= buf[(j) * BS].x) mn = buf[(j) * BS], min_pos = j;
 			if (l >= w + k - 1 && mn.x != ~0ULL) {
 				for (int j = buf_pos + 1; j < w; ++j)
-					if (mn.x == buf[j].x && mn.y != buf[j].y) MGB_SK_PUSH(buf[j]);
+					if (mn.x == buf[(j) * BS].x && mn.y != buf[(j) * BS].y) MGB_SK_PUSH(buf[(j) * BS]);
 				for (int j = 0; j <= buf_pos; ++j)
-					if (mn.x == buf[j].x && mn.y != buf[j].y) MGB_SK_PUSH(buf[j]);
+					if (mn.x == buf[(j) * BS].x && mn.y != buf[(j) * BS].y) MGB_SK_PUSH(buf[(j) * BS]);
 			}
 		}
 		if (++buf_pos == w) buf_pos = 0;
@@ -141,7 +144,11 @@ MG_HD inline int sketch_chunk(const char *str, int w, int k, uint32_t rid, int p
 }
 
 // sketch_seq() entered by all lanes of a warp; `out` (replicated on every lane) must be empty.
-MG_HD inline int sketch_seq_w(Arena &A, const char *str, int len, int w, int k, uint32_t rid, AVec<u128> &out, int lane)
+static const int SKETCH_SMEM_W = 12; // widest window whose rings fit the shared-memory variant ("seed_v2")
+static const int SKETCH_SMEM_BYTES = SKETCH_SMEM_W * 32 * 16; // per warp
+
+// sring: NULL, or SKETCH_SMEM_BYTES of shared memory of this warp for the window rings
+MG_HD inline int sketch_seq_w(Arena &A, const char *str, int len, int w, int k, uint32_t rid, AVec<u128> &out, int lane, u128 *sring = 0)
 {
 	if (!(len > 0 && w > 0 && w < 256 && k > 0 && k <= 28)) return MGB_E_INTERNAL;
 	const int min_chunk = w + 2 * k > 64? w + 2 * k : 64;
@@ -158,7 +165,10 @@ MG_HD inline int sketch_seq_w(Arena &A, const char *str, int len, int w, int k, 
 		for (int c = lane; c < n_ch; c += MGB_W) {
 			const int p = c * chunk, e = p + chunk < len? p + chunk : len;
 			int n = 0;
-			if (p < e) fail |= sketch_chunk(str, w, k, rid, p, e, c == 0, e == len, ring + (int64_t)c * w, tmp + (int64_t)c * cap, cap, &n);
+			if (p < e) {
+				if (sring && w <= SKETCH_SMEM_W) fail |= sketch_chunk<32>(str, w, k, rid, p, e, c == 0, e == len, sring + lane, tmp + (int64_t)c * cap, cap, &n);
+				else fail |= sketch_chunk<1>(str, w, k, rid, p, e, c == 0, e == len, ring + (int64_t)c * w, tmp + (int64_t)c * cap, cap, &n);
+			}
 			cnt[c] = n;
 		}
 		fail = warp_any(fail);

@@ -3,6 +3,7 @@ import hashlib
 import os
 
 import mgtest as T
+from minigraph_b200 import capi  # noqa: E402
 
 G = os.path.join(T.REPO, "tests", "golden")
 
@@ -293,6 +294,21 @@ def case_wfa_v2(lib, workdir, n_struct=60):
             case_wfa_divergent(lib)
     finally:
         lib.mgb_set_param(b"wfa_v2", capi.env_params().get("wfa_v2", 0))
+
+
+def case_seed_v2(lib, workdir):
+    """the sketch with its window rings in shared memory ("seed_v2", off by default): same minimizers, so the same GAF on
+    the golden cases (k=17/w=11 and k=19/w=10), on reads with N and tiny reads (which take the sequential path), on
+    multi-segment fragments and on the short-read preset"""
+    try:
+        assert lib.mgb_set_param(b"seed_v2", 1) == 0
+        for fn in (case_c1, case_c2, case_c3, case_c4, case_edge):
+            fn(lib, workdir)
+        if T.have_ref():
+            case_multi_segment(lib, workdir, n_frag=6)
+            case_short_reads(lib, workdir, n_pairs=20)
+    finally:
+        lib.mgb_set_param(b"seed_v2", capi.env_params().get("seed_v2", 0))
 
 
 def case_cta(lib, workdir, n_cases=12):
