@@ -256,6 +256,90 @@ MG_HD inline int gchain_cigar_finish(Arena &A, const PipeCtx &c, GcSet &gt, Ciga
 	return 0;
 }
 
+#if MGB_ON_DEVICE
+MG_D inline void lane_atomic_add_u64(uint64_t *p, uint64_t v) { atomicAdd((unsigned long long*)p, (unsigned long long)v); }
+#else
+inline void lane_atomic_add_u64(uint64_t *p, uint64_t v) { *p += v; } // lanes of the simulators never run concurrently
+#endif
+
+// gchain_cigar_finish() entered by all lanes of a warp (stage_finish<1>, parameter "fin_v2").  The reference appends item after
+// item and merges the first operation of an item into the last one written when they are of the same kind (galign.c:125-141 via
+// mg_cigar_push); nothing else is ever merged.  Here: (1) a prefix sum over the items gives every item its place in a flat list,
+// (2) the lanes copy the items there, the first operation of each item tagged, (3) a tagged operation that equals its left
+// neighbour continues that neighbour's run, every other operation starts a run; the runs are numbered by a ballot prefix
+// count and their lengths added up.  Same list as the sequential append, operation for operation.
+MG_HD inline int gchain_cigar_finish_w(Arena &A, const PipeCtx &c, GcSet &gt, CigarOut *out, int lane)
+{
+	const uint64_t FIRST = 1ULL << 62; // tag: first operation of an item (lengths stay far below 2^58)
+	for (int32_t i = 0; i < gt.n_gc; ++i) {
+		GChain *gc = &gt.gc[i];
+		const int32_t off_a0 = gt.lc[gc->off].off, n_plan = gc->n_plan;
+		const uint64_t *plan = c.plan + gc->plan_off;
+		int32_t *ioff;
+		MGB_ALLOC(A, ioff, int32_t, n_plan + 1);
+		int32_t tot = 0;
+		for (int32_t base = 0; base < n_plan; base += MGB_W) {
+			const int32_t t = base + lane;
+			int32_t cnt = 0;
+			if (t < n_plan) cnt = (plan[t] & PLAN_JOB)? c.jobs[plan[t] & ~PLAN_JOB].n_cigar : 1;
+			const int32_t incl = warp_incl_scan_i32(cnt, lane);
+			if (t < n_plan) ioff[t] = tot + incl - cnt;
+			tot += warp_bcast_i32(incl, MGB_W - 1);
+		}
+		uint64_t *F, *O;
+		int32_t *oidx;
+		MGB_ALLOC(A, F, uint64_t, tot + 1);
+		MGB_ALLOC(A, O, uint64_t, tot + 1);
+		MGB_ALLOC(A, oidx, int32_t, tot + 1);
+		warp_sync();
+		for (int32_t t = lane; t < n_plan; t += MGB_W) {
+			uint64_t *dst = F + ioff[t];
+			if (plan[t] & PLAN_JOB) {
+				const WfaJob *J = &c.jobs[plan[t] & ~PLAN_JOB];
+				const uint32_t *cig = (const uint32_t*)((const char*)c.cig + J->cig_off);
+				for (int32_t k = 0; k < J->n_cigar; ++k) dst[k] = (uint64_t)cig[k] | (k == 0? FIRST : 0);
+			} else dst[0] = plan[t] | FIRST;
+		}
+		warp_sync();
+		int32_t n_out = 0;
+		for (int32_t base = 0; base < tot; base += MGB_W) {
+			const int32_t j = base + lane;
+			int head = 0;
+			if (j < tot) head = j == 0 || !((F[j] & FIRST) && (F[j] & 0xf) == (F[j - 1] & 0xf));
+			const uint32_t mh = warp_ballot(head);
+			if (j < tot) {
+				const int32_t o = n_out + mask_rank(mh, lane) + head - 1;
+				oidx[j] = o;
+				if (head) O[o] = F[j] & 0xf;
+			}
+			n_out += mask_count(mh);
+		}
+		warp_sync();
+		for (int32_t j = lane; j < tot; j += MGB_W) lane_atomic_add_u64(&O[oidx[j]], (F[j] & ~FIRST) >> 4 << 4);
+		warp_sync();
+		int32_t mlen = 0, blen = 0, aplen = 0, l = 0;
+		for (int32_t j = lane; j < n_out; j += MGB_W) {
+			const int32_t op = (int32_t)(O[j] & 0xf), len = (int32_t)(O[j] >> 4);
+			if (op == 7) mlen += len;
+			blen += len;
+			if (op != 1) aplen += len;
+			if (op != 2) l += len;
+		}
+		mlen = warp_sum_i32(mlen), blen = warp_sum_i32(blen), aplen = warp_sum_i32(aplen), l = warp_sum_i32(l);
+		if (lane == 0) {
+			out[i].cigar = O, out[i].n = n_out;
+			gc->has_cigar = 1;
+			gc->n_cigar = n_out;
+			gc->c_ss = (int32_t)gt.a[off_a0].x + 1 - (int32_t)(gt.a[off_a0].y >> 32 & 0xff);
+			gc->c_ee = (int32_t)gt.a[off_a0 + gc->n_anchor - 1].x + 1;
+			gc->c_mlen = mlen, gc->c_blen = blen, gc->c_aplen = aplen;
+		}
+		if (!(l == gc->qe - gc->qs && aplen == gc->pe - gc->ps)) return MGB_E_INTERNAL;
+		warp_sync();
+	}
+	return 0;
+}
+
 // ---- ds:Z difference string ----
 
 struct DsOut { char *ds; int32_t len; int32_t *off; int32_t n_off; };
@@ -631,6 +715,7 @@ MG_HD inline int stage_gchain_gen(const PipeCtx &c, ReadOut *routs, int rid, Are
 
 // K8b for one read: stitch CIGARs, ds strings, part 2 of the result (one lane).
 // Warp-uniform: all lanes enter.  The CIGAR stitching runs on lane 0, the ds strings and the copies on all lanes.
+template<int V2 = 0> // V2: CIGAR stitching by the whole warp (gchain_cigar_finish_w), parameter "fin_v2"
 MG_HD inline int stage_finish(const PipeCtx &c, ReadOut *routs, int rid, Arena &A, int lane)
 {
 	ReadMeta &m = c.meta[rid];
@@ -650,7 +735,8 @@ MG_HD inline int stage_finish(const PipeCtx &c, ReadOut *routs, int rid, Arena &
 	MGB_ALLOC(A, cg, CigarOut, gs.n_gc);
 	MGB_ALLOC(A, ds, DsOut, gs.n_gc);
 	unsigned long long pt0 = prof_clock();
-	{
+	if (V2) MGB_TRY(gchain_cigar_finish_w(A, c, gs, cg, lane));
+	else {
 		Arena B = A;
 		int rc = 0;
 		if (lane == 0) rc = gchain_cigar_finish(B, c, gs, cg); // cg[] and the chain headers live in memory: visible to all lanes after the sync

@@ -311,6 +311,19 @@ def case_seed_v2(lib, workdir):
         lib.mgb_set_param(b"seed_v2", capi.env_params().get("seed_v2", 0))
 
 
+def case_fin_v2(lib, workdir):
+    """CIGAR stitching by the whole warp ("fin_v2", off by default): the same operations, merged at the same item boundaries,
+    so the same cg:Z/ds:Z text on the golden cases and the same mg_gchains_t fields as the reference on an SV graph"""
+    try:
+        assert lib.mgb_set_param(b"fin_v2", 1) == 0
+        for fn in (case_c1, case_c2, case_c3, case_c4, case_edge):
+            fn(lib, workdir)
+        if T.have_ref():
+            case_struct_random(lib, workdir, n_reads=60, seed=41)
+    finally:
+        lib.mgb_set_param(b"fin_v2", capi.env_params().get("fin_v2", 0))
+
+
 def case_cta(lib, workdir, n_cases=12):
     """the block-per-gap tier ("cta_len", off by default): gaps it takes come out the same -- through the job queue (golden
     GAF of c3, every tier-3 gap taken by a block) and one gap at a time against miniwfa (scores past 256, so the band of

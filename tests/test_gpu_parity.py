@@ -76,6 +76,11 @@ def test_index_matches_oracle_sketch(lib):
     test_oracle.check_index(lib, orc)
 
 
+@pytest.mark.skipif(not os.environ.get("MGB_TEST_FIN_V2"), reason="warp-wide CIGAR stitching is opt-in (MGB_TEST_FIN_V2=1): off by default in the engine")
+def test_finish_second_version(lib, workdir):
+    cases.case_fin_v2(lib, workdir)
+
+
 @pytest.mark.skipif(not os.environ.get("MGB_TEST_SEED_V2"), reason="the sketch with shared-memory rings is opt-in (MGB_TEST_SEED_V2=1): off by default in the engine")
 def test_seed_second_version(lib, workdir):
     cases.case_seed_v2(lib, workdir)

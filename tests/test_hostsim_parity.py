@@ -73,6 +73,10 @@ def test_full_size_properties_small(lib, workdir):
 
 
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
+def test_finish_second_version(lib, workdir):
+    cases.case_fin_v2(lib, workdir)
+
+
 def test_seed_second_version(lib, workdir):
     cases.case_seed_v2(lib, workdir)
 
