@@ -210,6 +210,7 @@ MG_HD inline int stage_chain_tail(const PipeCtx &c, ReadMeta &m, Arena &A, u128 
 // lower occupancy cost the rest of the kernel more (k_chain 11.0 -> 14.6 / 16.0 ms on B200), so the kernel asks for none.
 static const int CHAIN_SMEM = 7 * 1024;
 
+template<int V2 = 0> // V2: ballot replay in the RMQ walk (chain_rmq_fill_w<1>), parameter "chain_v2"
 MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A, int lane, int32_t *smem = 0)
 {
 	ReadMeta &m = c.meta[rid];
@@ -235,7 +236,7 @@ MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A, int lane, int3
 	unsigned long long t0 = prof_clock();
 	if (n_a > 0) {
 		if (o.flag & F_RMQ) {
-			MGB_TRY(chain_rmq_w(A, o.max_gap, o.max_gap_pre, o.bw, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
+			MGB_TRY(chain_rmq_w<V2>(A, o.max_gap, o.max_gap_pre, o.bw, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
 								o.chn_pen_gap, o.chn_pen_skip, n_a, a, &n_lc, &u, &n_a_new, lane));
 		} else {
 			MGB_TRY(chain_dp_w(A, max_gap_ref, max_gap_qry, o.bw, o.max_lc_skip, o.max_lc_iter, o.min_lc_cnt, o.min_lc_score,
@@ -254,7 +255,7 @@ MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A, int lane, int3
 			warp_sync(); // u[] sits at the mark: every lane must have read it before the sort below reuses that memory
 			A.top = mark;
 			MGB_TRY(radix_sort_128x_w(A, a, n2, lane));
-			MGB_TRY(chain_rmq_w(A, o.max_gap, o.max_gap_pre, o.bw_long, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
+			MGB_TRY(chain_rmq_w<V2>(A, o.max_gap, o.max_gap_pre, o.bw_long, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
 								o.chn_pen_gap, o.chn_pen_skip, n2, a, &n_lc, &u, &n_a_new, lane));
 		}
 	}

@@ -324,6 +324,41 @@ def case_fin_v2(lib, workdir):
         lib.mgb_set_param(b"fin_v2", capi.env_params().get("fin_v2", 0))
 
 
+def case_chain_skip(lib, workdir, n_reads=40):
+    """max_lc_skip far below its default (25): the early stop of the chaining DP and of the RMQ walk -- "too many candidates in
+    a row that are already on a better chain" (lchain.c:185-190, 336-343) -- fires all the time instead of almost never;
+    every field against the reference, DP chaining (lr) and RMQ chaining (asm)"""
+    pre, reads = os.path.join(workdir, "svc"), os.path.join(workdir, "svc.reads.fa")
+    T.sim_graph(pre, 300000, 3, 19)
+    T.sim_reads(pre + ".hap.fa", reads, n_reads, 12000, "ont", 47)
+    names, seqs = T.read_fasta(reads)
+    for preset in ("lr", "asm"):
+        for skip in (1, 3):
+            def tweak(mo, skip=skip):
+                mo.max_lc_skip = skip
+            want, _ = T.map_with_ref(pre + ".gfa", names, seqs, preset, tweak=tweak)
+            got, _, _ = T.map_with_engine(lib, pre + ".gfa", names, seqs, preset, tweak=tweak)
+            for i, (a, b) in enumerate(zip(want, got)):
+                d = T.diff_results(a, b)
+                assert d is None, "%s max_lc_skip=%d read %d: %s" % (preset, skip, i, d)
+
+
+def case_chain_v2(lib, workdir):
+    """ballot replay in the RMQ walk of the chaining stage ("chain_v2", off by default): the same chains -- asm preset (RMQ
+    chaining for every read), lr preset (RMQ rescue of the reads that span several segments), multi-segment fragments,
+    and the mg_gchains_t fields (anchors and linear chains included) against the reference on an SV graph"""
+    try:
+        assert lib.mgb_set_param(b"chain_v2", 1) == 0
+        for fn in (case_c1, case_c2, case_c3, case_c4):
+            fn(lib, workdir)
+        if T.have_ref():
+            case_struct_random(lib, workdir, n_reads=80, seed=43)
+            case_multi_segment(lib, workdir, n_frag=6)
+            case_chain_skip(lib, workdir)
+    finally:
+        lib.mgb_set_param(b"chain_v2", capi.env_params().get("chain_v2", 0))
+
+
 def case_cta(lib, workdir, n_cases=12):
     """the block-per-gap tier ("cta_len", off by default): gaps it takes come out the same -- through the job queue (golden
     GAF of c3, every tier-3 gap taken by a block) and one gap at a time against miniwfa (scores past 256, so the band of

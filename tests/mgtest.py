@@ -135,12 +135,14 @@ def diff_results(a, b):
     return None
 
 
-def map_with_ref(gfa_path, names, seqs, preset="lr", cigar=True):
-    """Run the reference's own mg_index/mg_map on every read (CPU)."""
+def map_with_ref(gfa_path, names, seqs, preset="lr", cigar=True, tweak=None):
+    """Run the reference's own mg_index/mg_map on every read (CPU).  tweak(mo) may change mapping options after the preset."""
     ref = load_ref()
     g = ref.gfa_read(gfa_path.encode())
     assert g, "gfa_read failed"
     io, mo = options.opt_set(preset, cigar)
+    if tweak:
+        tweak(mo)
     gi = ref.mg_index(g, C.byref(io), 1, C.byref(mo))
     assert gi
     b = ref.mg_tbuf_init()
@@ -155,12 +157,14 @@ def map_with_ref(gfa_path, names, seqs, preset="lr", cigar=True):
     return res, mo
 
 
-def map_with_engine(lib, gfa_path, names, seqs, preset="lr", cigar=True, gfa_loader=None):
+def map_with_engine(lib, gfa_path, names, seqs, preset="lr", cigar=True, gfa_loader=None, tweak=None):
     """Run an engine library (product or hostsim) through mg_index + mg_map_batch."""
     loader = gfa_loader or lib.mgb_gfa_read
     g = loader(gfa_path.encode())
     assert g, "gfa read failed"
     io, mo = options.opt_set(preset, cigar)
+    if tweak:
+        tweak(mo)
     gi = lib.mg_index(g, C.byref(io), 1, C.byref(mo))
     assert gi, lib.mgb_last_error()
     n = len(seqs)

@@ -60,6 +60,11 @@ def test_engine_switches_keep_results(lib, workdir):
 
 
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not shipped")
+def test_small_max_lc_skip(lib, workdir):
+    cases.case_chain_skip(lib, workdir)
+
+
+@pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not shipped")
 def test_struct_fields_vs_reference(lib, workdir):
     cases.case_struct_random(lib, workdir, n_reads=400)
 
@@ -74,6 +79,11 @@ def test_index_matches_oracle_sketch(lib):
     orc.orc_sketch.restype = C.c_int64
     orc.orc_sketch.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int64]
     test_oracle.check_index(lib, orc)
+
+
+@pytest.mark.skipif(not os.environ.get("MGB_TEST_CHAIN_V2"), reason="ballot replay in the RMQ walk is opt-in (MGB_TEST_CHAIN_V2=1): off by default in the engine")
+def test_chain_second_version(lib, workdir):
+    cases.case_chain_v2(lib, workdir)
 
 
 @pytest.mark.skipif(not os.environ.get("MGB_TEST_FIN_V2"), reason="warp-wide CIGAR stitching is opt-in (MGB_TEST_FIN_V2=1): off by default in the engine")

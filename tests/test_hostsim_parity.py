@@ -56,6 +56,11 @@ def test_engine_switches_keep_results(lib, workdir):
 
 
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
+def test_small_max_lc_skip(lib, workdir):
+    cases.case_chain_skip(lib, workdir)
+
+
+@pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
 def test_struct_fields_vs_reference(lib, workdir):
     cases.case_struct_random(lib, workdir, n_reads=60)
 
@@ -73,6 +78,10 @@ def test_full_size_properties_small(lib, workdir):
 
 
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
+def test_chain_second_version(lib, workdir):
+    cases.case_chain_v2(lib, workdir)
+
+
 def test_finish_second_version(lib, workdir):
     cases.case_fin_v2(lib, workdir)
 
