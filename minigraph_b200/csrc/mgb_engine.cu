@@ -48,6 +48,7 @@ static int64_t p_slot_workers = 0;
 static int64_t p_tier_learn = 1;       // 0: every gap tries every tier (no routing)
 static int64_t p_side_warps = 1;       // warps per SM of that side launch
 static int g_test_wfa_cta_taken = 0;   // gaps of mgb_test_wfa() answered by the block function so far (mgb_set_param("cta_taken", v) returns it and sets it to v)
+static int64_t p_gen_v2 = 0;           // 1: alignment plan and result copies of the materialisation stage on all lanes (k_gchain_gen2); not yet measured
 static int64_t p_chain_v2 = 0;         // 1: ballot replay in the RMQ walk of the chaining stage (k_chain2); not yet measured
 static int64_t p_fin_v2 = 0;           // 1: CIGAR stitching by the whole warp (k_finish2); not yet measured
 static int64_t p_seed_v2 = 0;          // 1: the sketch keeps its window rings in shared memory (k_seed2); not yet measured
@@ -57,8 +58,8 @@ static int64_t p_big_len = 0;          // > 0: gaps with tl or ql at or above th
                                        // (measured on B200 with 384: tier 3 -3 ms, tier 1 +7 ms from the shared SMs -- off)
 
 // launch shape per stage: warps per block and blocks per SM wanted (tunable for experiments: "sw<stage>", "mb<stage>")
-static int STAGE_MINB[16] = { 8, 8, 8, 8, 5, 8, 7, 4, 4, 4, 5, 7, 4, 8, 8, 8 };  // 10, 11, 12: second version of tiers 1, 2 and 3 ("wfa_v2"); 13: of the seeding stage ("seed_v2"); 14: of the finishing stage ("fin_v2"); 15: of the chaining stage ("chain_v2")
-static int STAGE_WARPS[16] = { 4, 4, 4, 4, 4, 4, 2, 4, 4, 4, 4, 2, 4, 4, 4, 4 };
+static int STAGE_MINB[17] = { 8, 8, 8, 8, 5, 8, 7, 4, 4, 4, 5, 7, 4, 8, 8, 8, 4 };  // 10, 11, 12: second version of tiers 1, 2 and 3 ("wfa_v2"); 13: of the seeding stage ("seed_v2"); 14: of the finishing stage ("fin_v2"); 15: of the chaining stage ("chain_v2"); 16: of the graph-chain materialisation ("gen_v2")
+static int STAGE_WARPS[17] = { 4, 4, 4, 4, 4, 4, 2, 4, 4, 4, 4, 2, 4, 4, 4, 4, 4 };
 extern "C" const char *mgb_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char *mgb_version(void) { return "mgb200-r1"; }
 extern "C" int mgb_set_param(const char *key, int64_t value)
@@ -78,6 +79,7 @@ extern "C" int mgb_set_param(const char *key, int64_t value)
 	else if (!strcmp(key, "seed_v2")) p_seed_v2 = value;
 	else if (!strcmp(key, "fin_v2")) p_fin_v2 = value;
 	else if (!strcmp(key, "chain_v2")) p_chain_v2 = value;
+	else if (!strcmp(key, "gen_v2")) p_gen_v2 = value;
 	else if (!strcmp(key, "cta_taken")) { int n = g_test_wfa_cta_taken; g_test_wfa_cta_taken = (int)value; return n; } // test hook counter: returns it, then sets it
 	else if (!strcmp(key, "side_warps")) p_side_warps = value;
 	else if (!strcmp(key, "tier_learn")) p_tier_learn = value;
@@ -195,7 +197,7 @@ struct LaunchArgs {
 //         materialisation + alignment plan (K7b), 4/6/7 WFA jobs tier 1/2/3 (K8a), 5 finish: CIGAR stitching + ds + result
 //         blob (K8b), 3 segment sketch for the index
 #define MGB_IS_WFA(STAGE) ((STAGE) == 4 || (STAGE) == 6 || (STAGE) == 7 || (STAGE) == 10 || (STAGE) == 11 || (STAGE) == 12)
-#define MGB_IS_WARP(STAGE) (MGB_IS_WFA(STAGE) || (STAGE) == 8 || (STAGE) == 1 || (STAGE) == 0 || (STAGE) == 5 || (STAGE) == 13 || (STAGE) == 14 || (STAGE) == 15) // stages entered by all lanes of the warp
+#define MGB_IS_WARP(STAGE) (MGB_IS_WFA(STAGE) || (STAGE) == 8 || (STAGE) == 1 || (STAGE) == 0 || (STAGE) == 5 || (STAGE) == 13 || (STAGE) == 14 || (STAGE) == 15 || (STAGE) == 16) // stages entered by all lanes of the warp
 template<int STAGE>
 MG_HD inline int run_stage(const LaunchArgs &L, int item, Arena &A, int lane, int32_t *smem)
 {
@@ -208,6 +210,7 @@ MG_HD inline int run_stage(const LaunchArgs &L, int item, Arena &A, int lane, in
 	if (STAGE == 14) return stage_finish<1>(L.c, L.routs, item, A, lane);
 	if (STAGE == 8) return gwfa_job_run(A, L.c, L.job_start + item, lane, smem);
 	if (STAGE == 9) return stage_gchain_gen(L.c, L.routs, item, A);
+	if (STAGE == 16) return stage_gchain_gen_w(L.c, L.routs, item, A, lane);
 	if (STAGE == 4) return wfa_job_run(A, L.c, L.job_start + item, lane, smem, 1);
 	if (STAGE == 6) return wfa_job_run(A, L.c, L.c.jobq[0][item], lane, smem, 2);
 	if (STAGE == 10) return wfa_job_run<1>(A, L.c, L.job_start + item, lane, smem, 1);
@@ -317,6 +320,7 @@ MGB_KERNEL(k_finish, 5, 8)        // K8b: CIGAR stitching, ds strings, result bl
 MGB_KERNEL(k_wfa_small2, 10, 5)   // tier 1, second version (mgb_wfa2.cuh; parameter "wfa_v2")
 MGB_KERNEL(k_wfa_mid2, 11, 5)     // tier 2, second version
 MGB_KERNEL(k_wfa_big2, 12, 4)     // tier 3, second version
+MGB_KERNEL(k_gchain_gen2, 16, 4)  // K7b with the alignment plan and the result copies on all lanes (parameter "gen_v2")
 MGB_KERNEL(k_chain2, 15, 8)       // K4/K5 with the ballot replay in the RMQ walk (parameter "chain_v2")
 MGB_KERNEL(k_finish2, 14, 8)      // K8b with the CIGAR stitching on all lanes (parameter "fin_v2")
 MGB_KERNEL(k_seed2, 13, 8)        // K1-K3 with the sketch's window rings in shared memory (parameter "seed_v2")
@@ -337,6 +341,7 @@ template<> struct StageKernel<12> { static void (*get())(LaunchArgs) { return k_
 template<> struct StageKernel<13> { static void (*get())(LaunchArgs) { return k_seed2; } };
 template<> struct StageKernel<14> { static void (*get())(LaunchArgs) { return k_finish2; } };
 template<> struct StageKernel<15> { static void (*get())(LaunchArgs) { return k_chain2; } };
+template<> struct StageKernel<16> { static void (*get())(LaunchArgs) { return k_gchain_gen2; } };
 #endif
 
 // Longest-first order of a job list (a tail of a few long jobs otherwise decides the kernel time).  Jobs are binned by
@@ -1173,7 +1178,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 				}
 				gjobs_done = n_gj;
 				L.rid_list = d_list, L.n_work = n_list;
-				{ if (timed) tm_k[9].start(); launch_stage<9>(L, W); if (timed) tm_k[9].stop(); }
+				{ if (timed) tm_k[9].start(); if (p_gen_v2) launch_stage<16>(L, W); else launch_stage<9>(L, W); if (timed) tm_k[9].stop(); }
 				S.n_launches += 1;
 			}
 			if (timed) tm_align.stop();

@@ -650,8 +650,106 @@ MG_HD inline int gwfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int l
 	return rc;
 }
 
+// What the sequential head of stage_gchain_gen<1>() hands to the warp-wide tail (stage_gchain_gen_w, parameter "gen_v2")
+struct GenHand {
+	GcSet gs;
+	int64_t boff;
+	uint64_t off_lc, off_a, sz, mark;
+	unsigned long long pt3;
+	int32_t want_plan, skip;
+};
+
+// gchain_cigar_plan() entered by all lanes of a warp.  Every kept anchor but the first yields exactly one item, which depends on
+// the anchor, on the kept anchor in front of it and on the linear chains the two sit on: the kept anchors are listed by an
+// ordered compaction, then every lane makes the item of one of them; the jobs of a chunk are allocated with one pool request.
+MG_HD inline int gchain_cigar_plan_w(Arena &A, const PipeCtx &c, int rid, const GraphDev &g, GcSet &gt, int64_t lc_off_bytes, int lane)
+{
+	for (int32_t i = 0; i < gt.n_gc; ++i) {
+		GChain *gc = &gt.gc[i];
+		const int32_t off_a0 = gt.lc[gc->off].off, n_anchor = gc->n_anchor, l_beg = gc->off, l_end = gc->off + gc->cnt;
+		uint64_t mark = A.top;
+		int32_t *kj, *kl; // kept anchors (index into the chain's anchors) and the linear chain each sits on; entry 0 is the first anchor
+		uint64_t *plan;
+		MGB_ALLOC(A, kj, int32_t, n_anchor + 1);
+		MGB_ALLOC(A, kl, int32_t, n_anchor + 1);
+		MGB_ALLOC(A, plan, uint64_t, n_anchor + 8);
+		if (lane == 0) kj[0] = 0, kl[0] = l_beg;
+		int32_t nk = 1, bad = 0;
+		for (int32_t base = 1; base < n_anchor; base += MGB_W) {
+			const int32_t j = base + lane;
+			int keep = 0, l = -1;
+			if (j < n_anchor) {
+				keep = !((gt.a[off_a0 + j].y & SEED_IGNORE) && j != n_anchor - 1);
+				if (keep) { // the linear chains of a graph chain own disjoint, ascending runs of its anchors
+					for (l = l_beg; l < l_end; ++l)
+						if (off_a0 + j >= gt.lc[l].off && off_a0 + j < gt.lc[l].off + gt.lc[l].cnt) break;
+					if (l >= l_end) bad = 1;
+				}
+			}
+			const uint32_t mk = warp_ballot(keep);
+			if (keep) { const int32_t at = nk + mask_rank(mk, lane); kj[at] = j, kl[at] = l; }
+			nk += mask_count(mk);
+		}
+		if (warp_any(bad)) return MGB_E_INTERNAL;
+		warp_sync();
+		if (lane == 0) plan[0] = (uint64_t)(gt.a[off_a0].y >> 32 & 0xff) << 4 | 7;
+		for (int32_t base = 1; base < nk; base += MGB_W) {
+			const int32_t k = base + lane;
+			uint64_t item = 0;
+			int is_job = 0;
+			int32_t l0 = 0, l = 0, l_seq = 0, qlen = 0;
+			u128 p, q;
+			p.x = p.y = q.x = q.y = 0;
+			if (k < nk) {
+				p = gt.a[off_a0 + kj[k]], q = gt.a[off_a0 + kj[k - 1]];
+				l = kl[k], l0 = kl[k - 1];
+				if (l == l0) l_seq = (int32_t)p.x - (int32_t)q.x;
+				else {
+					l_seq = g.seg_len[gt.lc[l0].v >> 1] - (int32_t)q.x - 1;
+					for (int32_t t = l0 + 1; t < l; ++t) l_seq += g_vlen(g, gt.lc[t].v);
+					l_seq += (int32_t)p.x + 1;
+				}
+				qlen = (int32_t)p.y - (int32_t)q.y;
+				if (!(l_seq > 0 || qlen > 0)) bad = 1;
+				else if (l_seq == 0) item = (uint64_t)(int64_t)qlen << 4 | 1;
+				else if (qlen == 0) item = (uint64_t)(int64_t)l_seq << 4 | 2;
+				else if (l_seq == qlen && (uint64_t)(int64_t)qlen <= (q.y >> 32 & 0xff)) item = (uint64_t)(int64_t)qlen << 4 | 7;
+				else is_job = 1;
+			}
+			if (warp_any(bad)) return MGB_E_INTERNAL;
+			const uint32_t mj = warp_ballot(is_job);
+			int64_t jbase = 0;
+			if (mj) {
+				if (lane == 0) jbase = pool_alloc(c.pool_jobs, (uint64_t)mask_count(mj) * sizeof(WfaJob));
+				jbase = (int64_t)warp_bcast_u64((uint64_t)jbase, 0);
+				if (jbase < 0) return MGB_E_POOL;
+			}
+			if (is_job) {
+				const int64_t joff = jbase + (int64_t)mask_rank(mj, lane) * (int64_t)sizeof(WfaJob);
+				WfaJob *J = (WfaJob*)((char*)c.jobs + joff);
+				J->rid = rid, J->gc = i, J->l0 = l0, J->l = l, J->t_beg = (int32_t)q.x + 1, J->t_last = (int32_t)p.x;
+				J->tl = l_seq, J->ql = qlen, J->q_off = (int32_t)q.y + 1, J->n_cigar = 0, J->status = 0, J->lc_off = lc_off_bytes, J->cig_off = 0;
+				item = PLAN_JOB | (uint64_t)(joff / (int64_t)sizeof(WfaJob));
+			}
+			if (k < nk) plan[k] = item;
+		}
+		warp_sync();
+		int64_t poff = 0;
+		if (lane == 0) poff = pool_alloc(c.pool_plan, (uint64_t)nk * 8);
+		poff = (int64_t)warp_bcast_u64((uint64_t)poff, 0);
+		if (poff < 0) return MGB_E_POOL;
+		uint64_t *dst = c.plan + poff / 8;
+		for (int32_t t = lane; t < nk; t += MGB_W) dst[t] = plan[t];
+		if (lane == 0) gc->plan_off = poff / 8, gc->n_plan = nk;
+		warp_sync();
+		A.top = mark;
+	}
+	return 0;
+}
+
 // K7b for one read: materialise graph chains from the DP and the bridging results, post filters, alignment plan.
-MG_HD inline int stage_gchain_gen(const PipeCtx &c, ReadOut *routs, int rid, Arena &A)
+template<int V2 = 0> // V2: stop after the first part of the result is allocated and hand over to the warp-wide tail (stage_gchain_gen_w)
+MG_HD inline int stage_gchain_gen(const PipeCtx &c, ReadOut *routs, int rid, Arena &A, GenHand *hand = 0)
 {
 	ReadMeta &m = c.meta[rid];
 	ReadOut &ro = routs[rid];
@@ -697,6 +795,11 @@ MG_HD inline int stage_gchain_gen(const PipeCtx &c, ReadOut *routs, int rid, Are
 		GChain *gc = &gs.gc[i];
 		gc->has_cigar = 0, gc->n_cigar = 0, gc->cigar_off = gc->ds_off = gc->dsoff_off = 0, gc->ds_len = gc->n_dsoff = 0, gc->plan_off = 0, gc->n_plan = 0;
 	}
+	if (V2) {
+		hand->gs = gs, hand->boff = boff, hand->off_lc = off_lc, hand->off_a = off_a, hand->sz = sz, hand->mark = mark, hand->pt3 = pt3;
+		hand->want_plan = (o.flag & F_CIGAR) && gs.n_gc > 0 && batch_n_seg(c.b, rid) == 1, hand->skip = 0;
+		return 0;
+	}
 	if ((o.flag & F_CIGAR) && gs.n_gc > 0 && batch_n_seg(c.b, rid) == 1) // reference: map-algo.c:475
 		MGB_TRY(gchain_cigar_plan(A, c, rid, c.g, gs, boff + (int64_t)off_lc));
 	{
@@ -710,6 +813,46 @@ MG_HD inline int stage_gchain_gen(const PipeCtx &c, ReadOut *routs, int rid, Are
 	ro.n_gc = gs.n_gc, ro.n_lc = gs.n_lc, ro.n_a = gs.n_a, ro.blob_size = (uint32_t)sz, ro.blob_off = boff;
 	prof_add(c, PROF_GC_PLAN_CYC, prof_clock() - pt3);
 	A.top = mark;
+	return 0;
+}
+
+// stage_gchain_gen() entered by all lanes of a warp (parameter "gen_v2"): lane 0 runs the sequential head, then the plan and
+// the copies of the first part of the result are shared by the lanes.
+MG_HD inline int stage_gchain_gen_w(const PipeCtx &c, ReadOut *routs, int rid, Arena &A, int lane)
+{
+	GenHand h;
+	h.gs.n_gc = h.gs.n_lc = h.gs.n_a = h.gs.rep_len = 0, h.gs.gc = 0, h.gs.lc = 0, h.gs.a = 0;
+	h.gs.cyc_gwfa = h.gs.cyc_shortk = h.gs.cyc_extra = 0;
+	h.boff = 0, h.off_lc = h.off_a = h.sz = 0, h.mark = A.top, h.pt3 = 0, h.want_plan = 0, h.skip = 1;
+	int rc = 0;
+	Arena B = A;
+	if (lane == 0) rc = stage_gchain_gen<1>(c, routs, rid, B, &h);
+	rc = warp_bcast_i32(rc, 0);
+	A.top = warp_bcast_u64(B.top, 0), A.peak = warp_bcast_u64(B.peak, 0);
+	h.skip = warp_bcast_i32(h.skip, 0);
+	warp_sync();
+	if (rc < 0 || h.skip) { A.top = h.mark; return rc; }
+	h.gs.n_gc = warp_bcast_i32(h.gs.n_gc, 0), h.gs.n_lc = warp_bcast_i32(h.gs.n_lc, 0), h.gs.n_a = warp_bcast_i32(h.gs.n_a, 0);
+	h.gs.gc = (GChain*)warp_bcast_u64((uint64_t)h.gs.gc, 0), h.gs.lc = (LLChain*)warp_bcast_u64((uint64_t)h.gs.lc, 0), h.gs.a = (u128*)warp_bcast_u64((uint64_t)h.gs.a, 0);
+	h.boff = (int64_t)warp_bcast_u64((uint64_t)h.boff, 0), h.off_lc = warp_bcast_u64(h.off_lc, 0), h.off_a = warp_bcast_u64(h.off_a, 0), h.sz = warp_bcast_u64(h.sz, 0);
+	h.want_plan = warp_bcast_i32(h.want_plan, 0);
+	if (h.want_plan) MGB_TRY(gchain_cigar_plan_w(A, c, rid, c.g, h.gs, h.boff + (int64_t)h.off_lc, lane));
+	char *blob = c.out + h.boff;
+	{
+		GChain *d = (GChain*)blob;
+		for (int32_t i = lane; i < h.gs.n_gc; i += MGB_W) d[i] = h.gs.gc[i];
+		LLChain *dl = (LLChain*)(blob + h.off_lc);
+		for (int32_t i = lane; i < h.gs.n_lc; i += MGB_W) dl[i] = h.gs.lc[i];
+		u128 *da = (u128*)(blob + h.off_a);
+		for (int32_t i = lane; i < h.gs.n_a; i += MGB_W) da[i] = h.gs.a[i];
+	}
+	if (lane == 0) {
+		ReadOut &ro = routs[rid];
+		ro.n_gc = h.gs.n_gc, ro.n_lc = h.gs.n_lc, ro.n_a = h.gs.n_a, ro.blob_size = (uint32_t)h.sz, ro.blob_off = h.boff;
+		prof_add(c, PROF_GC_PLAN_CYC, prof_clock() - h.pt3);
+	}
+	warp_sync();
+	A.top = h.mark;
 	return 0;
 }
 

@@ -359,6 +359,22 @@ def case_chain_v2(lib, workdir):
         lib.mgb_set_param(b"chain_v2", capi.env_params().get("chain_v2", 0))
 
 
+def case_gen_v2(lib, workdir):
+    """alignment plan and result copies of the materialisation stage on all lanes ("gen_v2", off by default): the same plan
+    items and gap jobs, so the same CIGARs -- golden cases, every field against the reference on an SV graph, fragments
+    without CIGAR (multi-segment), short reads, reads that do not map"""
+    try:
+        assert lib.mgb_set_param(b"gen_v2", 1) == 0
+        for fn in (case_c1, case_c2, case_c3, case_c4, case_edge):
+            fn(lib, workdir)
+        if T.have_ref():
+            case_struct_random(lib, workdir, n_reads=80, seed=53)
+            case_multi_segment(lib, workdir, n_frag=6)
+            case_short_reads(lib, workdir, n_pairs=20)
+    finally:
+        lib.mgb_set_param(b"gen_v2", capi.env_params().get("gen_v2", 0))
+
+
 def case_cta(lib, workdir, n_cases=12):
     """the block-per-gap tier ("cta_len", off by default): gaps it takes come out the same -- through the job queue (golden
     GAF of c3, every tier-3 gap taken by a block) and one gap at a time against miniwfa (scores past 256, so the band of

@@ -81,6 +81,11 @@ def test_index_matches_oracle_sketch(lib):
     test_oracle.check_index(lib, orc)
 
 
+@pytest.mark.skipif(not os.environ.get("MGB_TEST_GEN_V2"), reason="warp-wide alignment plan is opt-in (MGB_TEST_GEN_V2=1): off by default in the engine")
+def test_gchain_gen_second_version(lib, workdir):
+    cases.case_gen_v2(lib, workdir)
+
+
 @pytest.mark.skipif(not os.environ.get("MGB_TEST_CHAIN_V2"), reason="ballot replay in the RMQ walk is opt-in (MGB_TEST_CHAIN_V2=1): off by default in the engine")
 def test_chain_second_version(lib, workdir):
     cases.case_chain_v2(lib, workdir)

@@ -71,6 +71,10 @@ def test_no_diag_flag(lib, workdir):
     cases.case_no_diag(lib, workdir)
 
 
+def test_gchain_gen_second_version(lib, workdir):
+    cases.case_gen_v2(lib, workdir)
+
+
 def test_chain_second_version(lib, workdir):
     cases.case_chain_v2(lib, workdir)
 

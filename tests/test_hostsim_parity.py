@@ -78,6 +78,10 @@ def test_full_size_properties_small(lib, workdir):
 
 
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
+def test_gchain_gen_second_version(lib, workdir):
+    cases.case_gen_v2(lib, workdir)
+
+
 def test_chain_second_version(lib, workdir):
     cases.case_chain_v2(lib, workdir)
 
