@@ -343,7 +343,7 @@ def case_chain_skip(lib, workdir, n_reads=40):
                 assert d is None, "%s max_lc_skip=%d read %d: %s" % (preset, skip, i, d)
 
 
-def case_chain_v2(lib, workdir):
+def case_chain_v2(lib, workdir, n_struct=80, n_skip_reads=40):
     """ballot replay in the RMQ walk of the chaining stage ("chain_v2", off by default): the same chains -- asm preset (RMQ
     chaining for every read), lr preset (RMQ rescue of the reads that span several segments), multi-segment fragments,
     and the mg_gchains_t fields (anchors and linear chains included) against the reference on an SV graph"""
@@ -352,9 +352,9 @@ def case_chain_v2(lib, workdir):
         for fn in (case_c1, case_c2, case_c3, case_c4):
             fn(lib, workdir)
         if T.have_ref():
-            case_struct_random(lib, workdir, n_reads=80, seed=43)
+            case_struct_random(lib, workdir, n_reads=n_struct, seed=43)
             case_multi_segment(lib, workdir, n_frag=6)
-            case_chain_skip(lib, workdir)
+            case_chain_skip(lib, workdir, n_reads=n_skip_reads)
     finally:
         lib.mgb_set_param(b"chain_v2", capi.env_params().get("chain_v2", 0))
 

@@ -76,7 +76,7 @@ def test_gchain_gen_second_version(lib, workdir):
 
 
 def test_chain_second_version(lib, workdir):
-    cases.case_chain_v2(lib, workdir)
+    cases.case_chain_v2(lib, workdir, n_struct=40, n_skip_reads=12)
 
 
 def test_finish_second_version(lib, workdir):
