@@ -231,6 +231,8 @@ typedef struct {
 	uint64_t arena_peak;    /* largest per-worker arena use */
 	double t_kernel_ms[10]; /* CUDA-event time of each kernel of the first pass: k_seed, k_chain, k_gchain, (index), k_wfa_small, k_finish, k_wfa_mid, k_wfa_big, k_gwfa, k_gchain_gen */
 	uint64_t prof[32];      /* device cycle counters per phase (see mgb_pipeline.cuh PROF_*) */
+	double t_lab_ms;        /* k_gc_labels: reachability labels of source vertices seen for the first time (0 once the table is warm) */
+	int64_t n_lab_new;      /* such sources in this batch */
 } mgb_stats_t;
 
 /* test hook: align one gap through the tier-3 WFA path (exact up to max_iter cells, then the reference's chaining

@@ -20,8 +20,6 @@
 
 #include "../../include/mgb200.h"
 #include "mgb_galign.cuh"
-#include "mgb_wfa_cta.cuh"
-#include "mgb_wfa2.cuh"
 
 #ifndef MGB_HOSTSIM
 #include <cuda_runtime.h>
@@ -46,20 +44,11 @@ static int64_t p_thread_mask = 0;      // bit s set: stage s runs one item per t
 extern int p_slots; extern int64_t p_min_slot_reads;
 static int64_t p_slot_workers = 0;
 static int64_t p_tier_learn = 1;       // 0: every gap tries every tier (no routing)
-static int64_t p_side_warps = 1;       // warps per SM of that side launch
-static int g_test_wfa_cta_taken = 0;   // gaps of mgb_test_wfa() answered by the block function so far (mgb_set_param("cta_taken", v) returns it and sets it to v)
-static int64_t p_gen_v2 = 0;           // 1: alignment plan and result copies of the materialisation stage on all lanes (k_gchain_gen2); not yet measured
-static int64_t p_chain_v2 = 0;         // 1: ballot replay in the RMQ walk of the chaining stage (k_chain2); not yet measured
-static int64_t p_fin_v2 = 0;           // 1: CIGAR stitching by the whole warp (k_finish2); not yet measured
-static int64_t p_seed_v2 = 0;          // 1: the sketch keeps its window rings in shared memory (k_seed2); not yet measured
-static int64_t p_wfa_v2 = 0;           // 1: tiers 1/2 run the padded-slice version of the on-chip alignment (mgb_wfa2.cuh); not yet measured
-static int64_t p_cta_len = 0;          // > 0: tier-3 gaps with tl + ql at or above this are first offered to a block-per-gap kernel (k_wfa_cta); not yet measured
-static int64_t p_big_len = 0;          // > 0: gaps with tl or ql at or above this go to a tier-3 launch on a second stream beside tiers 1/2
-                                       // (measured on B200 with 384: tier 3 -3 ms, tier 1 +7 ms from the shared SMs -- off)
+static int64_t p_lab_cache = 1;        // 0: graph chaining searches its walks per read instead of keeping per-source labels in HBM (mgb_gclabel.cuh)
 
 // launch shape per stage: warps per block and blocks per SM wanted (tunable for experiments: "sw<stage>", "mb<stage>")
-static int STAGE_MINB[17] = { 8, 8, 8, 8, 5, 8, 7, 4, 4, 4, 5, 7, 4, 8, 8, 8, 4 };  // 10, 11, 12: second version of tiers 1, 2 and 3 ("wfa_v2"); 13: of the seeding stage ("seed_v2"); 14: of the finishing stage ("fin_v2"); 15: of the chaining stage ("chain_v2"); 16: of the graph-chain materialisation ("gen_v2")
-static int STAGE_WARPS[17] = { 4, 4, 4, 4, 4, 4, 2, 4, 4, 4, 4, 2, 4, 4, 4, 4, 4 };
+static int STAGE_MINB[18] = { 8, 8, 8, 8, 5, 8, 7, 4, 4, 4, 0, 0, 0, 0, 0, 0, 0, 8 }; // indexed by stage number (10-16 unused)
+static int STAGE_WARPS[18] = { 4, 4, 4, 4, 4, 4, 2, 4, 4, 4, 0, 0, 0, 0, 0, 0, 0, 4 };
 extern "C" const char *mgb_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char *mgb_version(void) { return "mgb200-r1"; }
 extern "C" int mgb_set_param(const char *key, int64_t value)
@@ -73,15 +62,7 @@ extern "C" int mgb_set_param(const char *key, int64_t value)
 	else if (!strcmp(key, "thread_mask")) p_thread_mask = value;
 	else if (!strcmp(key, "slots")) p_slots = (int)value;
 	else if (!strcmp(key, "slot_workers")) p_slot_workers = value;
-	else if (!strcmp(key, "big_len")) p_big_len = value;
-	else if (!strcmp(key, "cta_len")) p_cta_len = value;
-	else if (!strcmp(key, "wfa_v2")) p_wfa_v2 = value;
-	else if (!strcmp(key, "seed_v2")) p_seed_v2 = value;
-	else if (!strcmp(key, "fin_v2")) p_fin_v2 = value;
-	else if (!strcmp(key, "chain_v2")) p_chain_v2 = value;
-	else if (!strcmp(key, "gen_v2")) p_gen_v2 = value;
-	else if (!strcmp(key, "cta_taken")) { int n = g_test_wfa_cta_taken; g_test_wfa_cta_taken = (int)value; return n; } // test hook counter: returns it, then sets it
-	else if (!strcmp(key, "side_warps")) p_side_warps = value;
+	else if (!strcmp(key, "lab_cache")) p_lab_cache = value;
 	else if (!strcmp(key, "tier_learn")) p_tier_learn = value;
 	else if (!strcmp(key, "min_slot_reads")) p_min_slot_reads = value;
 	else if (!strncmp(key, "sw", 2) && key[2] >= '0' && key[2] <= '9' && !key[3] && value >= 1 && value <= 4) STAGE_WARPS[key[2] - '0'] = (int)value;
@@ -101,6 +82,7 @@ static void dfree(void *p) { free(p); }
 static void h2d(void *d, const void *h, size_t n) { if (n) memcpy(d, h, n); }
 static void d2h(void *h, const void *d, size_t n) { if (n) memcpy(h, d, n); }
 static void dzero(void *d, size_t n) { if (n) memset(d, 0, n); }
+static void d2d(void *d, const void *s, size_t n) { if (n) memcpy(d, s, n); }
 static void dfill(void *d, int v, size_t n) { if (n) memset(d, v, n); }
 static void dsync() {}
 static int dev_sm_count() { return 2; }
@@ -122,6 +104,7 @@ static void dsync() { CUDA_OK(cudaStreamSynchronize(t_stream)); }
 static void h2d(void *d, const void *h, size_t n) { if (n) { CUDA_OK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, t_stream)); dsync(); } }
 static void d2h(void *h, const void *d, size_t n) { if (n) { CUDA_OK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, t_stream)); dsync(); } }
 static void dzero(void *d, size_t n) { if (n) CUDA_OK(cudaMemsetAsync(d, 0, n, t_stream)); }
+static void d2d(void *d, const void *s, size_t n) { if (n) CUDA_OK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, t_stream)); }
 static void dfill(void *d, int v, size_t n) { if (n) CUDA_OK(cudaMemsetAsync(d, v, n, t_stream)); }
 static int dev_sm_count() { static int v = 0; if (v == 0) CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, (int)p_device)); return v; }
 static size_t dev_free_mem() { size_t f = 0, t = 0; CUDA_OK(cudaMemGetInfo(&f, &t)); return f; }
@@ -184,6 +167,7 @@ struct LaunchArgs {
 	ReadOut *routs;
 	const int32_t *rid_list; // NULL: reads 0..n-1
 	int32_t n_work;
+	const unsigned int *n_work_dev; // non-NULL: the number of items is read on the device (known only after the kernel in front)
 	char *arena_base;
 	uint64_t arena_bytes;
 	uint64_t *arena_peak;    // per worker
@@ -195,28 +179,22 @@ struct LaunchArgs {
 
 // stages: 0 seed (K1-K3), 1 chain (K4/K5), 2 graph chaining DP + bridge plan (K6), 8 bridging jobs (K7a), 9 graph-chain
 //         materialisation + alignment plan (K7b), 4/6/7 WFA jobs tier 1/2/3 (K8a), 5 finish: CIGAR stitching + ds + result
-//         blob (K8b), 3 segment sketch for the index
-#define MGB_IS_WFA(STAGE) ((STAGE) == 4 || (STAGE) == 6 || (STAGE) == 7 || (STAGE) == 10 || (STAGE) == 11 || (STAGE) == 12)
-#define MGB_IS_WARP(STAGE) (MGB_IS_WFA(STAGE) || (STAGE) == 8 || (STAGE) == 1 || (STAGE) == 0 || (STAGE) == 5 || (STAGE) == 13 || (STAGE) == 14 || (STAGE) == 15 || (STAGE) == 16) // stages entered by all lanes of the warp
+//         blob (K8b), 3 segment sketch for the index, 17 reachability labels of the sources graph chaining asks for (one per thread)
+#define MGB_IS_WFA(STAGE) ((STAGE) == 4 || (STAGE) == 6 || (STAGE) == 7)
+#define MGB_IS_WARP(STAGE) (MGB_IS_WFA(STAGE) || (STAGE) == 8 || (STAGE) == 1 || (STAGE) == 2 || (STAGE) == 0 || (STAGE) == 5 || (STAGE) == 9) // stages entered by all lanes of the warp
 template<int STAGE>
 MG_HD inline int run_stage(const LaunchArgs &L, int item, Arena &A, int lane, int32_t *smem)
 {
-	if (STAGE == 0) return stage_seed(L.c, item, A, lane);
-	if (STAGE == 13) return stage_seed<1>(L.c, item, A, lane, smem);
+	if (STAGE == 0) return stage_seed(L.c, item, A, lane, smem);
 	if (STAGE == 1) return stage_chain(L.c, item, A, lane, smem);
-	if (STAGE == 15) return stage_chain<1>(L.c, item, A, lane, smem);
-	if (STAGE == 2) return stage_gchain(L.c, L.routs, item, A);
+	if (STAGE == 2) return stage_gchain(L.c, L.routs, item, A, lane);
+	if (STAGE == 17) return label_job(A, L.c.g, L.c.lab, item);
 	if (STAGE == 5) return stage_finish(L.c, L.routs, item, A, lane);
-	if (STAGE == 14) return stage_finish<1>(L.c, L.routs, item, A, lane);
 	if (STAGE == 8) return gwfa_job_run(A, L.c, L.job_start + item, lane, smem);
-	if (STAGE == 9) return stage_gchain_gen(L.c, L.routs, item, A);
-	if (STAGE == 16) return stage_gchain_gen_w(L.c, L.routs, item, A, lane);
+	if (STAGE == 9) return stage_gchain_gen(L.c, L.routs, item, A, lane);
 	if (STAGE == 4) return wfa_job_run(A, L.c, L.job_start + item, lane, smem, 1);
 	if (STAGE == 6) return wfa_job_run(A, L.c, L.c.jobq[0][item], lane, smem, 2);
-	if (STAGE == 10) return wfa_job_run<1>(A, L.c, L.job_start + item, lane, smem, 1);
-	if (STAGE == 11) return wfa_job_run<1>(A, L.c, L.c.jobq[0][item], lane, smem, 2);
-	if (STAGE == 12) return L.c.jobq[1][item] < 0? 0 : wfa_job_run<1>(A, L.c, L.c.jobq[1][item], lane, smem, 3);
-	if (STAGE == 7) return L.c.jobq[1][item] < 0? 0 : wfa_job_run(A, L.c, L.c.jobq[1][item], lane, smem, 3); // < 0: struck by k_wfa_cta
+	if (STAGE == 7) return wfa_job_run(A, L.c, L.c.jobq[1][item], lane, smem, 3);
 	if (STAGE == 3) { // sketch one graph segment for the index (reference: index.c:200-205)
 		AVec<u128> mv;
 		avec_init(mv);
@@ -236,6 +214,7 @@ MG_HD inline int run_stage(const LaunchArgs &L, int item, Arena &A, int lane, in
 template<int STAGE>
 MG_HD inline void stage_fail(const LaunchArgs &L, int item, int rc)
 {
+	if (STAGE == 17) return; // a source that could not be finished is searched again by the read that needs it
 	if (STAGE == 3) {
 #if MGB_ON_DEVICE
 		atomicMin((int*)L.routs, rc);
@@ -244,15 +223,14 @@ MG_HD inline void stage_fail(const LaunchArgs &L, int item, int rc)
 #endif
 		return;
 	}
-	int rid = STAGE == 8? L.c.gjobs[L.job_start + item].rid : (STAGE == 4 || STAGE == 10)? L.c.jobs[L.job_start + item].rid : (STAGE == 6 || STAGE == 11)? L.c.jobs[L.c.jobq[0][item]].rid : (STAGE == 7 || STAGE == 12)? L.c.jobs[L.c.jobq[1][item]].rid : item;
+	int rid = STAGE == 8? L.c.gjobs[L.job_start + item].rid : STAGE == 4? L.c.jobs[L.job_start + item].rid : STAGE == 6? L.c.jobs[L.c.jobq[0][item]].rid : STAGE == 7? L.c.jobs[L.c.jobq[1][item]].rid : item;
 	L.c.meta[rid].status = rc; // benign race between jobs of one read: any negative code triggers the redo
 	if (STAGE == 2 || MGB_IS_WARP(STAGE) || STAGE == 5 || STAGE == 9) L.routs[rid].status = rc;
 }
 
 #ifndef MGB_HOSTSIM
 // One warp per work item; items are pulled from a global counter so that long items do not stall a wave.
-// The stages listed in MGB_IS_WARP are warp-uniform (all lanes enter the stage function, see mgb_common.cuh); the two
-// graph-chaining stages (2 and 9) run their sequential control flow on lane 0 while the other lanes wait at the barrier.
+// Every mapping stage is warp-uniform (all lanes enter the stage function, see mgb_common.cuh).
 template<int STAGE>
 __device__ __forceinline__ void stage_loop(const LaunchArgs &L)
 {
@@ -261,7 +239,7 @@ __device__ __forceinline__ void stage_loop(const LaunchArgs &L)
 	Arena A;
 	arena_init(A, L.arena_base + (uint64_t)worker * L.arena_bytes, L.arena_bytes);
 	extern __shared__ int4 dyn_smem[];
-	const int smem_stride = STAGE == 4? WfTier1::STRIDE : STAGE == 6? WfTier2::STRIDE : STAGE == 10? WfTier1v2::STRIDE : STAGE == 11? WfTier2v2::STRIDE : STAGE == 13? SKETCH_SMEM_BYTES : STAGE == 8? GWFA_SMEM_ARENA : 0;
+	const int smem_stride = STAGE == 4? WfTier1::STRIDE : STAGE == 6? WfTier2::STRIDE : STAGE == 0? SKETCH_SMEM_BYTES : STAGE == 8? GWFA_SMEM_ARENA : 0;
 	int32_t *smem = smem_stride? (int32_t*)((char*)dyn_smem + (size_t)(threadIdx.x >> 5) * smem_stride) : 0;
 	for (;;) {
 		int item = 0;
@@ -294,9 +272,10 @@ __device__ __forceinline__ void stage_loop_thread(const LaunchArgs &L)
 	const uint64_t sub = (L.arena_bytes / 32) & ~(uint64_t)15;
 	Arena A;
 	arena_init(A, L.arena_base + (uint64_t)worker * L.arena_bytes + (uint64_t)lane * sub, sub);
+	const int n_work = L.n_work_dev? (int)*L.n_work_dev : L.n_work;
 	for (;;) {
 		int item = (int)atomicAdd(L.c.next_read, 1u);
-		if (item >= L.n_work) break;
+		if (item >= n_work) break;
 		if (L.rid_list) item = L.rid_list[item];
 		A.top = 0;
 		int rc = run_stage<STAGE>(L, item, A, -1, 0);
@@ -317,13 +296,7 @@ MGB_KERNEL(k_wfa_small, 4, 5)     // K8a tier 1: small gaps, wavefronts + traceb
 MGB_KERNEL(k_wfa_mid, 6, 5)       // K8a tier 2: mid-size gaps, wavefronts in shared memory (blocks of 2 warps)
 MGB_KERNEL(k_wfa_big, 7, 4)       // K8a tier 3: anything else, wavefronts in the worker arena
 MGB_KERNEL(k_finish, 5, 8)        // K8b: CIGAR stitching, ds strings, result blobs
-MGB_KERNEL(k_wfa_small2, 10, 5)   // tier 1, second version (mgb_wfa2.cuh; parameter "wfa_v2")
-MGB_KERNEL(k_wfa_mid2, 11, 5)     // tier 2, second version
-MGB_KERNEL(k_wfa_big2, 12, 4)     // tier 3, second version
-MGB_KERNEL(k_gchain_gen2, 16, 4)  // K7b with the alignment plan and the result copies on all lanes (parameter "gen_v2")
-MGB_KERNEL(k_chain2, 15, 8)       // K4/K5 with the ballot replay in the RMQ walk (parameter "chain_v2")
-MGB_KERNEL(k_finish2, 14, 8)      // K8b with the CIGAR stitching on all lanes (parameter "fin_v2")
-MGB_KERNEL(k_seed2, 13, 8)        // K1-K3 with the sketch's window rings in shared memory (parameter "seed_v2")
+MGB_KERNEL(k_gc_labels, 17, 8)    // reachability labels of new source vertices, one search per thread (mgb_gclabel.cuh)
 template<int STAGE> struct StageKernel;
 template<> struct StageKernel<0> { static void (*get())(LaunchArgs) { return k_seed; } };
 template<> struct StageKernel<1> { static void (*get())(LaunchArgs) { return k_chain; } };
@@ -335,13 +308,7 @@ template<> struct StageKernel<7> { static void (*get())(LaunchArgs) { return k_w
 template<> struct StageKernel<8> { static void (*get())(LaunchArgs) { return k_gwfa; } };
 template<> struct StageKernel<9> { static void (*get())(LaunchArgs) { return k_gchain_gen; } };
 template<> struct StageKernel<5> { static void (*get())(LaunchArgs) { return k_finish; } };
-template<> struct StageKernel<10> { static void (*get())(LaunchArgs) { return k_wfa_small2; } };
-template<> struct StageKernel<11> { static void (*get())(LaunchArgs) { return k_wfa_mid2; } };
-template<> struct StageKernel<12> { static void (*get())(LaunchArgs) { return k_wfa_big2; } };
-template<> struct StageKernel<13> { static void (*get())(LaunchArgs) { return k_seed2; } };
-template<> struct StageKernel<14> { static void (*get())(LaunchArgs) { return k_finish2; } };
-template<> struct StageKernel<15> { static void (*get())(LaunchArgs) { return k_chain2; } };
-template<> struct StageKernel<16> { static void (*get())(LaunchArgs) { return k_gchain_gen2; } };
+template<> struct StageKernel<17> { static void (*get())(LaunchArgs) { return k_gc_labels; } };
 #endif
 
 // Longest-first order of a job list (a tail of a few long jobs otherwise decides the kernel time).  Jobs are binned by
@@ -376,29 +343,6 @@ __global__ void __launch_bounds__(1024) k_job_order(LaunchArgs L, int kind, cons
 	for (int i = tid; i < n; i += 1024) order[atomicAdd(&cnt[order_bin(order_key(L, kind, q, i))], 1u)] = i;
 }
 #endif
-// gaps that no on-chip tier can take (tl or ql >= big_len): listed up front, so that their tier-3 launch can run beside tiers 1/2
-#ifndef MGB_HOSTSIM
-__global__ void __launch_bounds__(1024) k_job_split(LaunchArgs L, int n, int32_t *bigq, unsigned int *n_big)
-{
-	for (int i = threadIdx.x; i < n; i += 1024) {
-		const WfaJob &J = L.c.jobs[L.job_start + i];
-		if (J.tl >= L.c.big_len || J.ql >= L.c.big_len) bigq[atomicAdd(n_big, 1u)] = (int32_t)(L.job_start + i);
-	}
-}
-#endif
-static void make_job_split(const LaunchArgs &L, int n, int32_t *bigq, unsigned int *n_big)
-{
-#ifndef MGB_HOSTSIM
-	k_job_split<<<1, 1024, 0, t_stream>>>(L, n, bigq, n_big);
-	CUDA_OK(cudaGetLastError());
-#else
-	for (int i = 0; i < n; ++i) {
-		const WfaJob &J = L.c.jobs[L.job_start + i];
-		if (J.tl >= L.c.big_len || J.ql >= L.c.big_len) bigq[(*n_big)++] = (int32_t)(L.job_start + i);
-	}
-#endif
-}
-
 static void make_job_order(const LaunchArgs &L, int kind, const int32_t *q, int n, int32_t *order)
 {
 #ifndef MGB_HOSTSIM
@@ -488,13 +432,13 @@ template<int STAGE>
 static void launch_stage(LaunchArgs &L, const Workers &W, int warps_override = 0)
 {
 	L.arena_base = W.arena, L.arena_bytes = W.arena_bytes, L.arena_peak = W.peak;
-	unsigned int zero = 0;
-	h2d(L.c.next_read, &zero, sizeof(zero));
+	dzero(L.c.next_read, sizeof(unsigned int)); // in stream order: no host round trip per launch
 #ifdef MGB_HOSTSIM
 	Arena A;
 	arena_init(A, W.arena, W.arena_bytes);
-	std::vector<int32_t> sim_smem(std::max<size_t>(std::max<size_t>(WfTier1v2::STRIDE, WfTier2v2::STRIDE), std::max<size_t>(std::max<size_t>(GWFA_SMEM_ARENA, CHAIN_SMEM), SKETCH_SMEM_BYTES)) / 4);
-	for (int it = 0; it < L.n_work; ++it) {
+	std::vector<int32_t> sim_smem(std::max<size_t>(std::max<size_t>(WfTier1::STRIDE, WfTier2::STRIDE), std::max<size_t>(std::max<size_t>(GWFA_SMEM_ARENA, CHAIN_SMEM), SKETCH_SMEM_BYTES)) / 4);
+	const int n_work_sim = L.n_work_dev? (int)*L.n_work_dev : L.n_work;
+	for (int it = 0; it < n_work_sim; ++it) {
 		int item = L.rid_list? L.rid_list[it] : it;
 		A.top = 0;
 		int rc;
@@ -523,78 +467,14 @@ static void launch_stage(LaunchArgs &L, const Workers &W, int warps_override = 0
 	int want = dev_sm_count() * STAGE_MINB[STAGE] * STAGE_WARPS[STAGE]; // resident warps this stage can keep on the chip
 	int n_w = std::min(W.n_workers, want);
 	int blocks = std::max(1, n_w / warps);
-	size_t smem = STAGE == 4? (size_t)warps * WfTier1::STRIDE : STAGE == 6? (size_t)warps * WfTier2::STRIDE : STAGE == 10? (size_t)warps * WfTier1v2::STRIDE : STAGE == 11? (size_t)warps * WfTier2v2::STRIDE : STAGE == 13? (size_t)warps * SKETCH_SMEM_BYTES : STAGE == 8? (size_t)warps * GWFA_SMEM_ARENA : 0;
+	size_t smem = STAGE == 4? (size_t)warps * WfTier1::STRIDE : STAGE == 6? (size_t)warps * WfTier2::STRIDE : STAGE == 0? (size_t)warps * SKETCH_SMEM_BYTES : STAGE == 8? (size_t)warps * GWFA_SMEM_ARENA : 0;
 	void (*kern)(LaunchArgs) = StageKernel<STAGE>::get();
 	if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	L.thread_mode = (p_thread_mask >> STAGE) & 1;
 	if (MGB_IS_WARP(STAGE)) L.thread_mode = 0;
+	if (STAGE == 17) L.thread_mode = 1;
 	if (L.thread_mode) smem = 0;
 	kern<<<blocks, threads, smem, t_stream>>>(L);
-	CUDA_OK(cudaGetLastError());
-#endif
-}
-
-// Block-per-gap pass over the tier-3 queue (mgb_wfa_cta.cuh): every block pulls queue entries, aligns the long ones with all
-// its threads and strikes them from the queue; the warp kernel (stage 7) that follows does the rest.
-#ifndef MGB_HOSTSIM
-__global__ void __launch_bounds__(MGB_CTA_THREADS) k_wfa_cta(LaunchArgs L)
-{
-	__shared__ CtaScratch scr;
-	__shared__ int s_item;
-	const int tid = threadIdx.x, warps = MGB_CTA_THREADS / 32;
-	Arena A;
-	arena_init(A, L.arena_base + (uint64_t)blockIdx.x * warps * L.arena_bytes, (uint64_t)warps * L.arena_bytes); // the arenas of its warps, as one
-	CtaCtx cx;
-	cta_init(cx, &scr, tid);
-	for (;;) {
-		if (tid == 0) s_item = (int)atomicAdd(L.c.next_read, 1u);
-		__syncthreads();
-		int item = s_item;
-		__syncthreads();
-		if (item >= L.n_work) break;
-		if (L.rid_list) item = L.rid_list[item];
-		A.top = 0;
-		wfa_job_cta(A, cx, L.c, item, tid);
-		__syncthreads();
-	}
-	if (tid == 0 && L.arena_peak && A.peak > L.arena_peak[blockIdx.x * warps]) L.arena_peak[blockIdx.x * warps] = A.peak;
-}
-#endif
-static void launch_wfa_cta(LaunchArgs &L, const Workers &W)
-{
-	L.arena_base = W.arena, L.arena_bytes = W.arena_bytes, L.arena_peak = W.peak;
-	unsigned int zero = 0;
-	h2d(L.c.next_read, &zero, sizeof(zero));
-#ifdef MGB_HOSTSIM
-	Arena A;
-	arena_init(A, W.arena, W.arena_bytes);
-	CtaScratch scr;
-	for (int it = 0; it < L.n_work; ++it) {
-		const int item = L.rid_list? L.rid_list[it] : it;
-		A.top = 0;
-#if MGB_W > 1
-		uint64_t peaks[MGB_CTA_T];
-		sim::tag()[0] = 10, sim::tag()[1] = item;
-		sim::run_warp(MGB_CTA_T, [&](int tid) {
-			Arena Al = A;
-			CtaCtx cx;
-			cta_init(cx, &scr, tid);
-			wfa_job_cta(Al, cx, L.c, item, tid);
-			peaks[tid] = Al.peak;
-		});
-		for (int l = 0; l < MGB_CTA_T; ++l) if (peaks[l] > A.peak) A.peak = peaks[l];
-#else
-		CtaCtx cx;
-		cta_init(cx, &scr, 0);
-		wfa_job_cta(A, cx, L.c, item, 0);
-#endif
-	}
-	if (W.peak && A.peak > W.peak[0]) W.peak[0] = A.peak;
-#else
-	const int warps = MGB_CTA_THREADS / 32;
-	if (W.n_workers < warps) return; // a block works in the arenas of its warps
-	const int blocks = std::min(W.n_workers / warps, dev_sm_count() * 4);
-	k_wfa_cta<<<blocks, MGB_CTA_THREADS, 0, t_stream>>>(L);
 	CUDA_OK(cudaGetLastError());
 #endif
 }
@@ -630,12 +510,12 @@ struct Model {
 	// the batch pipeline: a batch is cut into sub-batches, each driven by its own host thread on its own stream ("slot"),
 	// so that kernels, copies and host-side result assembly of different sub-batches overlap
 	struct Slot {
-		GrowBuf h_seq{true}, h_out{true}, h_small{true}, d_seq, d_meta, d_routs, d_small, d_jobq, d_order, d_bigq, d_packed, d_packoff, d_segs, d_pool[10];
-		Workers W, W2; // W2: the few workers of the tier-3 launch that runs beside tiers 1/2
+		GrowBuf h_seq{true}, h_out{true}, h_small{true}, d_seq, d_meta, d_routs, d_small, d_jobq, d_order, d_packed, d_packoff, d_segs, d_pool[10];
+		Workers W;
 		mgb_stats_t st;
 		double ev_first_ms, ev_last_ms; // first kernel start / last kernel end relative to the batch reference event
 #ifndef MGB_HOSTSIM
-		cudaStream_t stream, stream2;
+		cudaStream_t stream;
 		cudaEvent_t ev_first, ev_last, ev_piece[4];
 #endif
 		bool ready;
@@ -644,6 +524,9 @@ struct Model {
 	enum { MAX_SLOTS = 8 };
 	Slot slots[MAX_SLOTS];
 	std::mutex big_mutex; // the large-arena retry pass is shared by the slots
+	// reachability labels of the graph (mgb_gclabel.cuh): built on demand, kept across batches, grown between them
+	long long *d_lab_off = 0; int32_t *d_lab_new = 0; unsigned int *d_lab_n = 0; Pool *d_lab_hdr = 0; char *d_lab_pool = 0;
+	uint64_t lab_cap = 0; int32_t lab_max_dist_g = -1; int64_t lab_sources = 0;
 };
 
 static void model_free(Model *M)
@@ -654,16 +537,15 @@ static void model_free(Model *M)
 	if (M->Wbig.arena) dfree(M->Wbig.arena);
 	if (M->Wbig.peak) dfree(M->Wbig.peak);
 	if (M->d_logf) dfree(M->d_logf);
+	dfree(M->d_lab_off), dfree(M->d_lab_new), dfree(M->d_lab_n), dfree(M->d_lab_hdr), dfree(M->d_lab_pool);
 	for (int k = 0; k < Model::MAX_SLOTS; ++k) {
 		Model::Slot &sl = M->slots[k];
-		sl.h_seq.release(), sl.h_out.release(), sl.h_small.release(), sl.d_seq.release(), sl.d_meta.release(), sl.d_routs.release(), sl.d_small.release(), sl.d_jobq.release(), sl.d_order.release(), sl.d_bigq.release(), sl.d_packed.release(), sl.d_packoff.release(), sl.d_segs.release();
-		if (sl.W2.arena) dfree(sl.W2.arena);
-		if (sl.W2.peak) dfree(sl.W2.peak);
+		sl.h_seq.release(), sl.h_out.release(), sl.h_small.release(), sl.d_seq.release(), sl.d_meta.release(), sl.d_routs.release(), sl.d_small.release(), sl.d_jobq.release(), sl.d_order.release(), sl.d_packed.release(), sl.d_packoff.release(), sl.d_segs.release();
 		for (int i = 0; i < 10; ++i) sl.d_pool[i].release();
 		if (sl.W.arena) dfree(sl.W.arena);
 		if (sl.W.peak) dfree(sl.W.peak);
 #ifndef MGB_HOSTSIM
-		if (sl.ready) { cudaStreamDestroy(sl.stream); cudaEventDestroy(sl.ev_first); cudaEventDestroy(sl.ev_last); }
+		if (sl.ready) { cudaStreamDestroy(sl.stream); cudaEventDestroy(sl.ev_first); cudaEventDestroy(sl.ev_last); for (int i = 0; i < 4; ++i) cudaEventDestroy(sl.ev_piece[i]); }
 #endif
 	}
 	delete M;
@@ -999,6 +881,46 @@ static mg_gchains_t *build_result(const ReadOut &ro, const char *pool)
 int p_slots = 1;              // sub-batches in flight per batch (measured on B200: the kernels already fill the chip, overlap buys nothing)
 int64_t p_min_slot_reads = 512; // do not cut batches into pieces smaller than this
 
+// The label table of graph chaining: allocated at the first batch, emptied when a batch asks for longer walks than it was built for.
+static void lab_prepare(Model *M, int32_t max_dist_g)
+{
+	std::lock_guard<std::mutex> lock(M->big_mutex);
+	const size_t n_vtx = (size_t)M->g.n_seg * 2;
+	if (M->d_lab_off == 0) {
+		M->d_lab_off = (long long*)dmalloc(n_vtx * sizeof(long long));
+		M->d_lab_new = (int32_t*)dmalloc(n_vtx * sizeof(int32_t));
+		M->d_lab_n = (unsigned int*)dmalloc(sizeof(unsigned int));
+		M->d_lab_hdr = (Pool*)dmalloc(sizeof(Pool));
+		M->lab_cap = std::max<uint64_t>((uint64_t)64 << 20, (uint64_t)n_vtx * 4096);
+		M->d_lab_pool = (char*)dmalloc(M->lab_cap);
+		M->lab_max_dist_g = -1;
+	}
+	if (M->lab_max_dist_g < max_dist_g) { // labels are exact for every bound up to the one they were searched with
+		dfill(M->d_lab_off, 0xff, n_vtx * sizeof(long long));
+		Pool hp; hp.used = 0, hp.cap = M->lab_cap;
+		h2d(M->d_lab_hdr, &hp, sizeof(Pool));
+		M->lab_max_dist_g = max_dist_g;
+	}
+}
+// after a batch: a label pool that overflowed is enlarged for the batches to come (the sources that did not fit were searched per read)
+static void lab_after_batch(Model *M, unsigned int n_new)
+{
+	std::lock_guard<std::mutex> lock(M->big_mutex);
+	M->lab_sources += n_new;
+	Pool hp;
+	d2h(&hp, M->d_lab_hdr, sizeof(Pool));
+	if (hp.used <= hp.cap) return;
+	const uint64_t want = std::max<uint64_t>((uint64_t)hp.used * 2, M->lab_cap * 2);
+	if (want > dev_free_mem() / 2) return;
+	char *np = (char*)dmalloc(want);
+	d2d(np, M->d_lab_pool, M->lab_cap);
+	dsync();
+	dfree(M->d_lab_pool);
+	hp.used = M->lab_cap, hp.cap = want; // everything that was written lies below the old capacity
+	M->d_lab_pool = np, M->lab_cap = want;
+	h2d(M->d_lab_hdr, &hp, sizeof(Pool));
+}
+
 // Map reads [0, n_reads) of one sub-batch on the calling thread's stream (slot `sl`).
 static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads, const int *qlens, const char *const *seqs, const char *const *names,
 					 mg_gchains_t **gcs, int host_threads, const std::vector<int32_t> *seg_off = 0, const std::vector<int32_t> *seg_len = 0)
@@ -1032,7 +954,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 		g_host_pool.run(n, host_threads, fn);
 	};
 	EvTimer tm_h2d, tm_seed, tm_chain, tm_align, tm_wfa, tm_fin, tm_d2h;
-	EvTimer tm_k[10]; // one per kernel (first pass only)
+	EvTimer tm_k[10], tm_lab; // one per kernel (first pass only)
 	// ---- device buffers (all persistent: cudaMalloc/cudaFree would serialise the slots) ----
 	enum { P_ANCHOR, P_MINIPOS, P_LCHAIN, P_OUT, P_PLAN, P_JOBS, P_CIG, P_GSTATE, P_GJOBS, P_WALK, N_POOLS };
 	char *d_seq = (char*)sl.d_seq.ensure(hseq_bytes);
@@ -1066,7 +988,6 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	char *dsm = (char*)(((uintptr_t)(d_self_id + n_reads) + 255) & ~(uintptr_t)255);
 	unsigned int *d_next = (unsigned int*)dsm;
 	unsigned int *d_jobq_n = d_next + 4;
-	unsigned int *d_next2 = d_next + 8, *d_nbig = d_next + 9;
 	unsigned long long *d_prof = (unsigned long long*)(dsm + 64);
 	Pool *d_pools = (Pool*)(dsm + 64 + sizeof(unsigned long long) * PROF_N);
 	unsigned int *d_tier_hist = (unsigned int*)((char*)(d_pools + 16) + 64); // 32 x 4 counters behind the pool headers
@@ -1112,6 +1033,8 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	bool first_kernel = true;
 	(void)first_kernel;
 
+	const bool use_lab = p_lab_cache && p_slots <= 1; // one table per model: sub-batches on private streams would race on its work list
+	if (use_lab) lab_prepare(M, o.bw_long);
 	for (int attempt = 0; attempt < 8; ++attempt) {
 		void *d_buf[N_POOLS];
 		Pool hp[N_POOLS];
@@ -1135,6 +1058,12 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 		L.c.pool_gjobs = &d_pools[P_GJOBS], L.c.gjobs = (GwfaJob*)d_buf[P_GJOBS];
 		L.c.pool_walk = &d_pools[P_WALK], L.c.walk = (int32_t*)d_buf[P_WALK];
 		L.c.next_read = d_next;
+		memset(&L.c.lab, 0, sizeof(L.c.lab));
+		if (use_lab) {
+			L.c.lab.src_off = M->d_lab_off, L.c.lab.pool_hdr = M->d_lab_hdr, L.c.lab.pool = M->d_lab_pool, L.c.lab.new_src = M->d_lab_new, L.c.lab.n_new = M->d_lab_n;
+			L.c.lab.max_dist_g = M->lab_max_dist_g;
+			dzero(M->d_lab_n, sizeof(unsigned int));
+		}
 		L.c.prof = d_prof;
 		L.c.tier_hist = d_tier_hist, L.c.skip1_len = L_skip1, L.c.skip2_len = L_skip2;
 		L.c.jobq[0] = 0, L.c.jobq[1] = 0, L.c.jobq_n = d_jobq_n;
@@ -1147,10 +1076,18 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 			if (first_kernel) { CUDA_OK(cudaEventRecord(sl.ev_first, t_stream)); first_kernel = false; }
 #endif
 			if (timed) tm_seed.start();
-			{ if (timed) tm_k[0].start(); if (p_seed_v2) launch_stage<13>(L, W); else launch_stage<0>(L, W); if (timed) tm_k[0].stop(); }
+			{ if (timed) tm_k[0].start(); launch_stage<0>(L, W); if (timed) tm_k[0].stop(); }
 			if (timed) tm_seed.stop(), tm_chain.start();
-			{ if (timed) tm_k[1].start(); if (p_chain_v2) launch_stage<15>(L, W); else launch_stage<1>(L, W); if (timed) tm_k[1].stop(); }
+			{ if (timed) tm_k[1].start(); launch_stage<1>(L, W); if (timed) tm_k[1].stop(); }
 			if (timed) tm_chain.stop(), tm_align.start();
+			if (use_lab) { // labels of the sources k_chain listed (count known on the device only)
+				L.n_work_dev = M->d_lab_n, L.rid_list = 0;
+				if (timed) tm_lab.start();
+				launch_stage<17>(L, W);
+				if (timed) tm_lab.stop();
+				L.n_work_dev = 0, L.rid_list = d_list;
+				S.n_launches += 1;
+			}
 			if (d_list == 0 && n_list >= 1024) { // whole batch: reads with many linear chains first (a few of them set the time of this kernel)
 				int32_t *order = (int32_t*)sl.d_order.ensure(sizeof(int32_t) * (size_t)n_list);
 				if (timed) tm_k[2].start();
@@ -1178,7 +1115,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 				}
 				gjobs_done = n_gj;
 				L.rid_list = d_list, L.n_work = n_list;
-				{ if (timed) tm_k[9].start(); if (p_gen_v2) launch_stage<16>(L, W); else launch_stage<9>(L, W); if (timed) tm_k[9].stop(); }
+				{ if (timed) tm_k[9].start(); launch_stage<9>(L, W); if (timed) tm_k[9].stop(); }
 				S.n_launches += 1;
 			}
 			if (timed) tm_align.stop();
@@ -1193,63 +1130,27 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 				L.c.jobq[0] = q, L.c.jobq[1] = q + n_new;
 				unsigned int qn[2] = {0, 0};
 				h2d(d_jobq_n, qn, sizeof(qn));
-				// gaps too long for the on-chip tiers are known up front: their tier-3 launch goes to a second stream with its own few
-				// workers and runs beside tiers 1/2 (its time is set by the longest gap, which would otherwise be an idle tail)
-				bool side = false;
-				L.c.big_len = 0;
-				if (&W == &sl.W && p_big_len > 0) {
-					L.c.big_len = (int32_t)p_big_len;
-					int32_t *bigq = (int32_t*)sl.d_bigq.ensure(sizeof(int32_t) * 2 * (size_t)n_new);
-					unsigned int n_big = 0;
-					h2d(d_nbig, &n_big, sizeof(n_big));
-					make_job_split(L, n_new, bigq, d_nbig);
-					d2h(&n_big, d_nbig, sizeof(n_big));
-					if (n_big > 0) {
-						LaunchArgs L2 = L;
-						L2.c.jobq[1] = bigq, L2.c.next_read = d_next2, L2.n_work = (int32_t)n_big;
-						make_job_order(L2, 1, bigq, (int)n_big, bigq + n_new);
-						L2.rid_list = bigq + n_new;
-						dsync();
-#ifndef MGB_HOSTSIM
-						cudaStream_t main_stream = t_stream;
-						t_stream = sl.stream2;
-						launch_stage<7>(L2, sl.W2, 1); // one-warp blocks, one per SM: the long gaps ride along without taking much from tiers 1/2
-						t_stream = main_stream;
-#else
-						launch_stage<7>(L2, sl.W2);
-#endif
-						side = true;
-						S.n_launches += 3;
-						if (timed) S.n_jobs_side = n_big;
-					}
-				}
-				{ if (timed) tm_k[4].start(); if (p_wfa_v2) launch_stage<10>(L, W); else launch_stage<4>(L, W); if (timed) tm_k[4].stop(); }
+				{ if (timed) tm_k[4].start(); launch_stage<4>(L, W); if (timed) tm_k[4].stop(); }
 				d2h(qn, d_jobq_n, sizeof(qn));
 				S.n_launches += 1;
-				if (qn[0] > 0) { L.n_work = (int32_t)qn[0]; { if (timed) tm_k[6].start(); if (p_wfa_v2) launch_stage<11>(L, W); else launch_stage<6>(L, W); if (timed) tm_k[6].stop(); } d2h(qn, d_jobq_n, sizeof(qn)); S.n_launches += 1; }
+				if (qn[0] > 0) { L.n_work = (int32_t)qn[0]; { if (timed) tm_k[6].start(); launch_stage<6>(L, W); if (timed) tm_k[6].stop(); } d2h(qn, d_jobq_n, sizeof(qn)); S.n_launches += 1; }
 				if (qn[1] > 0) {
 					L.n_work = (int32_t)qn[1];
 					int32_t *order = (int32_t*)sl.d_order.ensure(sizeof(int32_t) * (size_t)L.n_work);
 					if (timed) tm_k[7].start();
 					make_job_order(L, 1, L.c.jobq[1], L.n_work, order);
 					L.rid_list = order;
-					if (p_cta_len > 0) { L.c.cta_len = (int32_t)p_cta_len; launch_wfa_cta(L, W); S.n_launches += 1; }
-					if (p_wfa_v2) launch_stage<12>(L, W); else launch_stage<7>(L, W);
+					launch_stage<7>(L, W);
 					L.rid_list = 0;
 					if (timed) tm_k[7].stop();
 					S.n_launches += 2;
 				}
 				if (timed) S.n_jobs_mid = qn[0], S.n_jobs_big = qn[1];
-#ifndef MGB_HOSTSIM
-				if (side) CUDA_OK(cudaStreamSynchronize(sl.stream2));
-#endif
-				(void)side;
-				L.c.big_len = 0;
 			}
 			if (timed) tm_wfa.stop(), tm_fin.start();
 			jobs_done = n_jobs;
 			L.rid_list = d_list, L.n_work = n_list;
-			{ if (timed) tm_k[5].start(); if (p_fin_v2) launch_stage<14>(L, W); else launch_stage<5>(L, W); if (timed) tm_k[5].stop(); }
+			{ if (timed) tm_k[5].start(); launch_stage<5>(L, W); if (timed) tm_k[5].stop(); }
 			if (timed) tm_fin.stop();
 			S.n_launches += 4;
 #ifndef MGB_HOSTSIM
@@ -1286,6 +1187,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 			}
 		}
 		d2h(hp, d_pools, sizeof(hp));
+		if (use_lab) { unsigned int nn = 0; d2h(&nn, M->d_lab_n, sizeof(nn)); S.n_lab_new = (int64_t)nn; lab_after_batch(M, nn); }
 		bool done = !pool_full;
 		if (done) { // blobs into read order, then to the host in pieces (the assembly below follows piece by piece)
 			tm_d2h.start();
@@ -1322,6 +1224,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	S.t_h2d_ms = tm_h2d.ms(), S.t_seed_ms = tm_seed.ms(), S.t_chain_ms = tm_chain.ms(), S.t_align_ms = tm_align.ms();
 	S.t_wfa_ms = tm_wfa.ms(), S.t_finish_ms = tm_fin.ms();
 	for (int i = 0; i < 10; ++i) S.t_kernel_ms[i] = tm_k[i].ms();
+	S.t_lab_ms = tm_lab.ms();
 	{
 		std::vector<uint64_t> peak(sl.W.n_workers);
 		d2h(peak.data(), sl.W.peak, sizeof(uint64_t) * peak.size());
@@ -1380,7 +1283,6 @@ static void slot_prepare(Model *M, Model::Slot &sl, int n_workers)
 #ifndef MGB_HOSTSIM
 	if (!sl.ready) {
 		CUDA_OK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
-		CUDA_OK(cudaStreamCreateWithFlags(&sl.stream2, cudaStreamNonBlocking));
 		CUDA_OK(cudaEventCreate(&sl.ev_first));
 		CUDA_OK(cudaEventCreate(&sl.ev_last));
 		for (int i = 0; i < 4; ++i) CUDA_OK(cudaEventCreateWithFlags(&sl.ev_piece[i], cudaEventDisableTiming));
@@ -1388,7 +1290,6 @@ static void slot_prepare(Model *M, Model::Slot &sl, int n_workers)
 #endif
 	sl.ready = true;
 	ensure_workers(sl.W, n_workers, (uint64_t)p_arena_mb << 20);
-	ensure_workers(sl.W2, dev_sm_count() * (int)p_side_warps, (uint64_t)p_arena_mb << 20);
 	(void)M;
 }
 
@@ -1481,7 +1382,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 		for (int i = 0; i < 10; ++i) S.t_kernel_ms[i] += T.t_kernel_ms[i];
 		S.n_jobs += T.n_jobs, S.n_jobs_mid += T.n_jobs_mid, S.n_jobs_big += T.n_jobs_big, S.n_jobs_side += T.n_jobs_side, S.skip1_len = T.skip1_len, S.skip2_len = T.skip2_len, S.n_reads += T.n_reads, S.n_bases += T.n_bases;
 		S.n_seeds += T.n_seeds, S.n_anchors_out += T.n_anchors_out, S.n_chains_out += T.n_chains_out, S.n_minimizers += T.n_minimizers;
-		S.out_bytes += T.out_bytes, S.n_launches += T.n_launches, S.n_retry += T.n_retry;
+		S.out_bytes += T.out_bytes, S.n_launches += T.n_launches, S.n_retry += T.n_retry, S.n_lab_new += T.n_lab_new, S.t_lab_ms += T.t_lab_ms;
 		if (T.arena_peak > S.arena_peak) S.arena_peak = T.arena_peak;
 		for (int i = 0; i < 32; ++i) { if (i == PROF_WFA_MAX_CYC || i == PROF_GWFA_MAX_CYC || i == PROF_GC_DP_MAX_CYC) { if (T.prof[i] > S.prof[i]) S.prof[i] = T.prof[i]; } else S.prof[i] += T.prof[i]; }
 #ifndef MGB_HOSTSIM
@@ -1579,48 +1480,24 @@ extern "C" mg_gchains_t *mg_map(const mg_idx_t *gi, int qlen, const char *seq, m
 // test hook: one gap alignment through the tier-3 path (exact WFA capped at max_iter cells, then the chaining
 // heuristic with low-memory checkpoints every `step` scores), reference: miniwfa.c:824-834 mwf_wfa_auto
 // ---------------------------------------------------------------------------------------------------------------
-struct TestWfaArgs { const char *ts, *qs; int32_t tl, ql, step, cap, v2; int64_t max_iter; uint32_t *cigar; int32_t *out; char *arena; uint64_t arena_bytes; };
+struct TestWfaArgs { const char *ts, *qs; int32_t tl, ql, step, cap; int64_t max_iter; uint32_t *cigar; int32_t *out; char *arena; uint64_t arena_bytes; };
 MG_HD inline void test_wfa_body(const TestWfaArgs &t, int lane)
 {
 	Arena A;
 	arena_init(A, t.arena, t.arena_bytes);
 	WfResult r;
-	int rc = t.v2? wfa_exact<1>(A, t.tl, t.ts, t.ql, t.qs, t.max_iter, &r, lane, t.step) : wfa_exact<0>(A, t.tl, t.ts, t.ql, t.qs, t.max_iter, &r, lane, t.step);
+	int rc = wfa_exact(A, t.tl, t.ts, t.ql, t.qs, t.max_iter, &r, lane, t.step);
 	if (rc == 0 && r.n_cigar <= t.cap) for (int32_t i = lane; i < r.n_cigar; i += MGB_W) t.cigar[i] = r.cigar[i];
 	if (lane == 0) t.out[0] = rc, t.out[1] = rc == 0? r.n_cigar : 0, t.out[2] = rc == 0? r.s : 0;
 }
-// the same gap offered to the block-per-gap function first (parameter "cta_len"); out[3] = 1 when it produced the result
-MG_HD inline void test_wfa_cta_body(const TestWfaArgs &t, CtaCtx &cx, int tid)
-{
-	Arena A;
-	arena_init(A, t.arena, t.arena_bytes);
-	WfResult r;
-	r.s = -1, r.n_cigar = 0, r.n_iter = 0, r.cigar = 0;
-	char *ts = (char*)arena_alloc(A, (uint64_t)(t.tl + WF_SEQ_PAD + 4)), *qs = (char*)arena_alloc(A, (uint64_t)(t.ql + WF_SEQ_PAD + 4));
-	uint32_t *cig_store = (uint32_t*)arena_alloc(A, (uint64_t)(t.tl + t.ql + 2) * 4);
-	wf_stage_seq_cta(ts, t.ts, t.tl, 0xfe, tid);
-	wf_stage_seq_cta(qs, t.qs, t.ql, 0xff, tid);
-	cta_sync();
-	int rc = wfa_ring_cta(A, cx, t.tl, ts, t.ql, qs, t.max_iter, &r, cig_store, (int64_t)t.tl + t.ql + 2, tid);
-	const int taken = rc == 0 && r.s >= 0 && r.n_cigar <= t.cap;
-	if (taken) for (int32_t i = tid; i < r.n_cigar; i += MGB_CTA_T) t.cigar[i] = r.cigar[i];
-	if (tid == 0) t.out[0] = 0, t.out[1] = taken? r.n_cigar : 0, t.out[2] = taken? r.s : 0, t.out[3] = taken;
-}
 #ifndef MGB_HOSTSIM
 __global__ void k_test_wfa(TestWfaArgs t) { test_wfa_body(t, threadIdx.x & 31); }
-__global__ void __launch_bounds__(MGB_CTA_THREADS) k_test_wfa_cta(TestWfaArgs t)
-{
-	__shared__ CtaScratch scr;
-	CtaCtx cx;
-	cta_init(cx, &scr, threadIdx.x);
-	test_wfa_cta_body(t, cx, threadIdx.x);
-}
 #endif
 extern "C" int mgb_test_wfa(const char *ts, int tl, const char *qs, int ql, int64_t max_iter, int step, uint32_t *cigar, int cap, int *score)
 {
 	if (!dev_ok()) { set_error("no CUDA device available: libmgb200 has no CPU path"); return -100; }
 	TestWfaArgs t;
-	t.tl = tl, t.ql = ql, t.step = step, t.cap = cap, t.v2 = p_wfa_v2? 1 : 0, t.max_iter = max_iter, t.arena_bytes = (uint64_t)1 << 30;
+	t.tl = tl, t.ql = ql, t.step = step, t.cap = cap, t.max_iter = max_iter, t.arena_bytes = (uint64_t)1 << 30;
 	char *d_ts = (char*)dmalloc((size_t)tl + 64), *d_qs = (char*)dmalloc((size_t)ql + 64);
 	h2d(d_ts, ts, (size_t)tl), h2d(d_qs, qs, (size_t)ql);
 	t.ts = d_ts, t.qs = d_qs;
@@ -1628,23 +1505,7 @@ extern "C" int mgb_test_wfa(const char *ts, int tl, const char *qs, int ql, int6
 	t.out = (int32_t*)dmalloc(sizeof(int32_t) * 4);
 	t.arena = (char*)dmalloc(t.arena_bytes);
 	int32_t out[4] = {0, 0, 0, 0};
-	if (p_cta_len > 0 && tl + ql >= p_cta_len && tl + ql <= 16000 && tl > 0 && ql > 0) {
-		h2d(t.out, out, sizeof(out));
-#ifdef MGB_HOSTSIM
-		CtaScratch scr;
-#if MGB_W > 1
-		sim::run_warp(MGB_CTA_T, [&](int tid) { CtaCtx cx; cta_init(cx, &scr, tid); test_wfa_cta_body(t, cx, tid); });
-#else
-		{ CtaCtx cx; cta_init(cx, &scr, 0); test_wfa_cta_body(t, cx, 0); }
-#endif
-#else
-		k_test_wfa_cta<<<1, MGB_CTA_THREADS>>>(t);
-		CUDA_OK(cudaGetLastError());
-		dsync();
-#endif
-		d2h(out, t.out, sizeof(out));
-	}
-	if (!out[3]) {
+	{
 #ifdef MGB_HOSTSIM
 #if MGB_W > 1
 	sim::run_warp(MGB_W, [&](int lane) { test_wfa_body(t, lane); });
@@ -1657,9 +1518,7 @@ extern "C" int mgb_test_wfa(const char *ts, int tl, const char *qs, int ql, int6
 	dsync();
 #endif
 	d2h(out, t.out, sizeof(out));
-	out[3] = 0;
 	}
-	g_test_wfa_cta_taken += out[3];
 	if (out[0] == 0 && out[1] <= cap) d2h(cigar, t.cigar, sizeof(uint32_t) * (size_t)out[1]);
 	*score = out[2];
 	dfree(d_ts), dfree(d_qs), dfree(t.cigar), dfree(t.out), dfree(t.arena);

@@ -5,8 +5,7 @@
 #pragma once
 #include "mgb_pipeline.cuh"
 #include "mgb_gchain.cuh"
-#include "mgb_wfa.cuh"
-#include "mgb_wfa2.cuh"
+#include "mgb_wfa_tiers.cuh"
 #if defined(MGB_HOSTSIM)
 #include <stdio.h>
 #include <stdlib.h>
@@ -53,69 +52,16 @@ static const uint64_t PLAN_JOB = 1ULL << 63;
 
 // Planning pass of mg_gchain_cigar() (reference: galign.c:39-124): walk the kept anchors of every graph chain, emit
 // literal CIGAR items for the trivial gaps (galign.c:98-100) and a WfaJob for the others.
-MG_HD inline int gchain_cigar_plan(Arena &A, const PipeCtx &c, int rid, const GraphDev &g, GcSet &gt, int64_t lc_off_bytes)
-{
-	for (int32_t i = 0; i < gt.n_gc; ++i) {
-		GChain *gc = &gt.gc[i];
-		int32_t l0 = gc->off;
-		const int32_t off_a0 = gt.lc[l0].off;
-		int32_t j, j0 = 0, k, l, l_seq;
-		uint64_t mark = A.top;
-		AVec<uint64_t> plan;
-		avec_init(plan);
-		MGB_TRY(avec_reserve(A, plan, gc->n_anchor + 8));
-		plan.a[plan.n++] = (uint64_t)(gt.a[off_a0].y >> 32 & 0xff) << 4 | 7;
-		for (j = 1; j < gc->n_anchor; ++j) {
-			const u128 *q, *p = &gt.a[off_a0 + j];
-			if ((p->y & SEED_IGNORE) && j != gc->n_anchor - 1) continue;
-			q = &gt.a[off_a0 + j0];
-			for (l = l0; l < gc->off + gc->cnt; ++l) {
-				const LLChain *r = &gt.lc[l];
-				if (off_a0 + j >= r->off && off_a0 + j < r->off + r->cnt) break;
-			}
-			if (l >= gc->off + gc->cnt) return MGB_E_INTERNAL;
-			if (l == l0) l_seq = (int32_t)p->x - (int32_t)q->x;
-			else {
-				l_seq = g.seg_len[gt.lc[l0].v >> 1] - (int32_t)q->x - 1;
-				for (k = l0 + 1; k < l; ++k) l_seq += g_vlen(g, gt.lc[k].v);
-				l_seq += (int32_t)p->x + 1;
-			}
-			int32_t qlen = (int32_t)p->y - (int32_t)q->y;
-			if (!(l_seq > 0 || qlen > 0)) return MGB_E_INTERNAL;
-			if (l_seq == 0) plan.a[plan.n++] = (uint64_t)(int64_t)qlen << 4 | 1;
-			else if (qlen == 0) plan.a[plan.n++] = (uint64_t)(int64_t)l_seq << 4 | 2;
-			else if (l_seq == qlen && (uint64_t)(int64_t)qlen <= (q->y >> 32 & 0xff)) plan.a[plan.n++] = (uint64_t)(int64_t)qlen << 4 | 7;
-			else {
-				int64_t joff = pool_alloc(c.pool_jobs, sizeof(WfaJob));
-				if (joff < 0) return MGB_E_POOL;
-				WfaJob *J = (WfaJob*)((char*)c.jobs + joff);
-				J->rid = rid, J->gc = i, J->l0 = l0, J->l = l, J->t_beg = (int32_t)q->x + 1, J->t_last = (int32_t)p->x;
-				J->tl = l_seq, J->ql = qlen, J->q_off = (int32_t)q->y + 1, J->n_cigar = 0, J->status = 0, J->lc_off = lc_off_bytes, J->cig_off = 0;
-				plan.a[plan.n++] = PLAN_JOB | (uint64_t)(joff / (int64_t)sizeof(WfaJob));
-			}
-			j0 = j, l0 = l;
-		}
-		int64_t poff = pool_alloc(c.pool_plan, (uint64_t)plan.n * 8);
-		if (poff < 0) return MGB_E_POOL;
-		uint64_t *dst = c.plan + poff / 8;
-		for (int64_t t = 0; t < plan.n; ++t) dst[t] = plan.a[t];
-		gc->plan_off = poff / 8, gc->n_plan = (int32_t)plan.n;
-		A.top = mark;
-	}
-	return 0;
-}
 
 // K8a: align one gap.  Warp-uniform (all lanes enter with identical arguments).
 // tier 1: small gaps, wavefronts + traceback bytes in shared memory; tier 2: mid-size gaps, wavefronts in shared
 // memory; tier 3: anything, wavefronts in the worker arena.  A job that does not fit a tier is appended to the queue
 // of the next one (jobq[tier-1]); the host launches the next tier over that queue.
-template<int V2 = 0> // V2: tiers 1/2 use wfa_smem2() (mgb_wfa2.cuh) instead of wfa_smem()
 MG_HD inline int wfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int lane, int32_t *smem, int tier)
 {
 	WfaJob *J = &c.jobs[job_idx];
 	const int32_t rid = J->rid, l0 = J->l0, l = J->l, tl = J->tl, ql = J->ql;
 	if (c.meta[rid].status < 0) return 0; // the read already failed elsewhere; it will be redone as a whole
-	if (tier < 3 && c.big_len > 0 && (tl >= c.big_len || ql >= c.big_len)) return 0; // taken by the concurrent tier-3 launch
 	// Routing: a gap that cannot finish in an on-chip tier costs that tier up to a full window of cells before it gives up.
 	// Which lengths fail depends on the error rate of the reads, so it is learned: one gap in 64 tries every tier and
 	// reports where it finished; the host turns the counts of one batch into the two thresholds of the next.  The
@@ -173,9 +119,9 @@ MG_HD inline int wfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int la
 	WfResult rst;
 	unsigned long long pt0 = prof_clock();
 	int rc;
-	if (tier == 1) rc = V2? wfa_smem2<WfTier1::W_, WfTier1::MAXLEN_, WfTier1::TBCAP_>(A, smem, tl, tseq, ql, qs, &rst, lane) : wfa_smem<WfTier1::W_, WfTier1::MAXLEN_, WfTier1::TBCAP_, WfTier1::HS_>(A, smem, tl, tseq, ql, qs, &rst, lane);
-	else if (tier == 2) rc = V2? wfa_smem2<WfTier2::W_, WfTier2::MAXLEN_, WfTier2::TBCAP_>(A, smem, tl, tseq, ql, qs, &rst, lane) : wfa_smem<WfTier2::W_, WfTier2::MAXLEN_, WfTier2::TBCAP_, WfTier2::HS_>(A, smem, tl, tseq, ql, qs, &rst, lane);
-	else rc = wfa_exact<V2>(A, tl, tseq, ql, qs, 100000000LL, &rst, lane);
+	if (tier == 1) rc = wfa_smem<WfTier1::W_, WfTier1::MAXLEN_, WfTier1::TBCAP_>(A, smem, tl, tseq, ql, qs, &rst, lane);
+	else if (tier == 2) rc = wfa_smem<WfTier2::W_, WfTier2::MAXLEN_, WfTier2::TBCAP_>(A, smem, tl, tseq, ql, qs, &rst, lane);
+	else rc = wfa_exact(A, tl, tseq, ql, qs, 100000000LL, &rst, lane);
 	if (rc < 0) return rc;
 	if (lane == 0) {
 		unsigned long long dt = prof_clock() - pt0;
@@ -219,42 +165,6 @@ MG_HD inline int wfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int la
 }
 
 // Finishing pass of mg_gchain_cigar() (reference: galign.c:125-141): concatenate plan items and job CIGARs.
-MG_HD inline int gchain_cigar_finish(Arena &A, const PipeCtx &c, GcSet &gt, CigarOut *out)
-{
-	for (int32_t i = 0; i < gt.n_gc; ++i) {
-		GChain *gc = &gt.gc[i];
-		const int32_t off_a0 = gt.lc[gc->off].off;
-		const uint64_t *plan = c.plan + gc->plan_off;
-		int64_t tot = 0;
-		for (int32_t t = 0; t < gc->n_plan; ++t)
-			tot += (plan[t] & PLAN_JOB)? c.jobs[plan[t] & ~PLAN_JOB].n_cigar : 1;
-		AVec<uint64_t> cigar;
-		avec_init(cigar);
-		MGB_TRY(avec_reserve(A, cigar, tot + 1));
-		for (int32_t t = 0; t < gc->n_plan; ++t) {
-			if (plan[t] & PLAN_JOB) {
-				const WfaJob *J = &c.jobs[plan[t] & ~PLAN_JOB];
-				MGB_TRY(cigar_append(A, cigar, J->n_cigar, (const uint32_t*)((const char*)c.cig + J->cig_off)));
-			} else MGB_TRY(cigar_append1(A, cigar, (int32_t)(plan[t] & 0xf), (int32_t)(plan[t] >> 4)));
-		}
-		out[i].cigar = cigar.a, out[i].n = (int32_t)cigar.n;
-		gc->has_cigar = 1;
-		gc->n_cigar = (int32_t)cigar.n;
-		gc->c_ss = (int32_t)gt.a[off_a0].x + 1 - (int32_t)(gt.a[off_a0].y >> 32 & 0xff);
-		gc->c_ee = (int32_t)gt.a[off_a0 + gc->n_anchor - 1].x + 1;
-		gc->c_mlen = gc->c_blen = gc->c_aplen = 0;
-		int32_t l = 0;
-		for (int32_t j = 0; j < gc->n_cigar; ++j) {
-			int32_t op = (int32_t)(cigar.a[j] & 0xf), len = (int32_t)(cigar.a[j] >> 4);
-			if (op == 7) gc->c_mlen += len, gc->c_blen += len;
-			else gc->c_blen += len;
-			if (op != 1) gc->c_aplen += len;
-			if (op != 2) l += len;
-		}
-		if (!(l == gc->qe - gc->qs && gc->c_aplen == gc->pe - gc->ps)) return MGB_E_INTERNAL;
-	}
-	return 0;
-}
 
 #if MGB_ON_DEVICE
 MG_D inline void lane_atomic_add_u64(uint64_t *p, uint64_t v) { atomicAdd((unsigned long long*)p, (unsigned long long)v); }
@@ -541,26 +451,11 @@ struct GState {
 };
 
 // K6 for one read: graph chaining DP, overlap resolution, bridging plan (one lane).
-MG_HD inline int stage_gchain(const PipeCtx &c, ReadOut *routs, int rid, Arena &A)
+// bridging plan of one read and the state K7 picks up again; one lane
+MG_HD inline int stage_gchain_plan(const PipeCtx &c, ReadMeta &m, int rid, Arena &A, int32_t n_lc, LChain *lc, int32_t n_u, const uint64_t *u, const u128 *a, uint32_t *gc_hash)
 {
-	ReadMeta &m = c.meta[rid];
-	ReadOut &ro = routs[rid];
 	const MapOptDev &o = c.opt;
-	ro.status = 0, ro.n_gc = ro.n_lc = ro.n_a = 0, ro.rep_len = m.rep_len, ro.n_mz = m.n_mz, ro.blob_size = ro.blob2_size = 0, ro.blob_off = ro.blob2_off = 0;
-	if (m.status != 0) { ro.status = m.status; return 0; } // status 1: read skipped (empty or too long) -> no result object
-	uint64_t mark = A.top;
-	const int32_t qlen = c.b.seq_len[rid];
-	const u128 *a = c.anchor + m.a_off;
-	int32_t n_lc = m.n_lc, n_u = 0, n_gc = 0;
-	uint64_t *u = 0;
-	LChain *lc;
-	uint32_t *gc_hash;
-	MGB_ALLOC(A, lc, LChain, n_lc);
-	MGB_ALLOC(A, gc_hash, uint32_t, n_lc);
-	for (int32_t i = 0; i < n_lc; ++i) lc[i] = c.lchain[m.lc_off + i];
-	unsigned long long pt0 = prof_clock();
-	MGB_TRY(gchain1_dp(A, c.g, &n_lc, lc, qlen, o.bw_long, o.bw_long, o.bw_long, o.max_gc_skip, o.ref_bonus, o.chn_pen_gap, o.mask_level, a, &u, &n_u));
-	{ unsigned long long dt = prof_clock() - pt0; prof_add(c, PROF_GC_DP_CYC, dt); prof_max(c, PROF_GC_DP_MAX_CYC, dt); }
+	int32_t n_gc = 0;
 	// a read's jobs must be contiguous in the pool (they are consumed in order): reserve the worst case, one job per
 	// linear chain, up front and mark the unused slots
 	int64_t job_first;
@@ -589,8 +484,43 @@ MG_HD inline int stage_gchain(const PipeCtx &c, ReadOut *routs, int rid, Arena &
 	uint32_t *dh = (uint32_t*)(du + n_u);
 	for (int32_t i = 0; i < n_gc; ++i) dh[i] = gc_hash[i];
 	m.gstate_off = goff;
-	A.top = mark;
 	return 0;
+}
+
+// K6 for one read, entered by all lanes of a warp: the graph-chaining DP is warp-wide (gchain_dp_w), the bridging plan and the
+// hand-over to K7 (a few dozen words per read) are written by lane 0.
+MG_HD inline int stage_gchain(const PipeCtx &c, ReadOut *routs, int rid, Arena &A, int lane)
+{
+	ReadMeta &m = c.meta[rid];
+	ReadOut &ro = routs[rid];
+	const MapOptDev &o = c.opt;
+	if (lane == 0) ro.status = 0, ro.n_gc = ro.n_lc = ro.n_a = 0, ro.rep_len = m.rep_len, ro.n_mz = m.n_mz, ro.blob_size = ro.blob2_size = 0, ro.blob_off = ro.blob2_off = 0;
+	if (m.status != 0) { if (lane == 0) ro.status = m.status; return 0; } // status 1: read skipped (empty or too long) -> no result object
+	const uint64_t mark = A.top;
+	const int32_t qlen = c.b.seq_len[rid];
+	const u128 *a = c.anchor + m.a_off;
+	int32_t n_lc = m.n_lc, n_u = 0;
+	uint64_t *u = 0;
+	LChain *lc;
+	uint32_t *gc_hash;
+	MGB_ALLOC(A, lc, LChain, n_lc);
+	MGB_ALLOC(A, gc_hash, uint32_t, n_lc);
+	for (int32_t i = lane; i < n_lc; i += MGB_W) lc[i] = c.lchain[m.lc_off + i];
+	warp_sync();
+	unsigned long long pt0 = prof_clock();
+	GcParam gp;
+	gp.max_dist_g = gp.max_dist_q = gp.bw = o.bw_long, gp.ref_bonus = o.ref_bonus, gp.chn_pen_gap = o.chn_pen_gap, gp.mask_level = o.mask_level; // reference: map-algo.c:461-462
+	MGB_TRY(gchain_dp_w(A, c.g, c.lab, &n_lc, lc, qlen, gp, o.max_gc_skip, a, &u, &n_u, lane));
+	if (lane == 0) { unsigned long long dt = prof_clock() - pt0; prof_add(c, PROF_GC_DP_CYC, dt); prof_max(c, PROF_GC_DP_MAX_CYC, dt); }
+	int rc = 0;
+	if (lane == 0) {
+		Arena B = A;
+		rc = stage_gchain_plan(c, m, rid, B, n_lc, lc, n_u, u, a, gc_hash);
+		if (B.peak > A.peak) A.peak = B.peak;
+	}
+	rc = warp_bcast_i32(rc, 0);
+	A.top = mark;
+	return rc;
 }
 
 // K7a: one bridging alignment (reference: gchain1.c:349-381).  The wavefront containers of a typical bridge (tens of
@@ -748,8 +678,7 @@ MG_HD inline int gchain_cigar_plan_w(Arena &A, const PipeCtx &c, int rid, const 
 }
 
 // K7b for one read: materialise graph chains from the DP and the bridging results, post filters, alignment plan.
-template<int V2 = 0> // V2: stop after the first part of the result is allocated and hand over to the warp-wide tail (stage_gchain_gen_w)
-MG_HD inline int stage_gchain_gen(const PipeCtx &c, ReadOut *routs, int rid, Arena &A, GenHand *hand = 0)
+MG_HD inline int stage_gchain_gen_head(const PipeCtx &c, ReadOut *routs, int rid, Arena &A, GenHand *hand)
 {
 	ReadMeta &m = c.meta[rid];
 	ReadOut &ro = routs[rid];
@@ -795,30 +724,14 @@ MG_HD inline int stage_gchain_gen(const PipeCtx &c, ReadOut *routs, int rid, Are
 		GChain *gc = &gs.gc[i];
 		gc->has_cigar = 0, gc->n_cigar = 0, gc->cigar_off = gc->ds_off = gc->dsoff_off = 0, gc->ds_len = gc->n_dsoff = 0, gc->plan_off = 0, gc->n_plan = 0;
 	}
-	if (V2) {
-		hand->gs = gs, hand->boff = boff, hand->off_lc = off_lc, hand->off_a = off_a, hand->sz = sz, hand->mark = mark, hand->pt3 = pt3;
-		hand->want_plan = (o.flag & F_CIGAR) && gs.n_gc > 0 && batch_n_seg(c.b, rid) == 1, hand->skip = 0;
-		return 0;
-	}
-	if ((o.flag & F_CIGAR) && gs.n_gc > 0 && batch_n_seg(c.b, rid) == 1) // reference: map-algo.c:475
-		MGB_TRY(gchain_cigar_plan(A, c, rid, c.g, gs, boff + (int64_t)off_lc));
-	{
-		GChain *d = (GChain*)blob;
-		for (int32_t i = 0; i < gs.n_gc; ++i) d[i] = gs.gc[i];
-		LLChain *dl = (LLChain*)(blob + off_lc);
-		for (int32_t i = 0; i < gs.n_lc; ++i) dl[i] = gs.lc[i];
-		u128 *da = (u128*)(blob + off_a);
-		for (int32_t i = 0; i < gs.n_a; ++i) da[i] = gs.a[i];
-	}
-	ro.n_gc = gs.n_gc, ro.n_lc = gs.n_lc, ro.n_a = gs.n_a, ro.blob_size = (uint32_t)sz, ro.blob_off = boff;
-	prof_add(c, PROF_GC_PLAN_CYC, prof_clock() - pt3);
-	A.top = mark;
+	hand->gs = gs, hand->boff = boff, hand->off_lc = off_lc, hand->off_a = off_a, hand->sz = sz, hand->mark = mark, hand->pt3 = pt3;
+	hand->want_plan = (o.flag & F_CIGAR) && gs.n_gc > 0 && batch_n_seg(c.b, rid) == 1, hand->skip = 0; // reference: map-algo.c:475
 	return 0;
 }
 
 // stage_gchain_gen() entered by all lanes of a warp (parameter "gen_v2"): lane 0 runs the sequential head, then the plan and
 // the copies of the first part of the result are shared by the lanes.
-MG_HD inline int stage_gchain_gen_w(const PipeCtx &c, ReadOut *routs, int rid, Arena &A, int lane)
+MG_HD inline int stage_gchain_gen(const PipeCtx &c, ReadOut *routs, int rid, Arena &A, int lane)
 {
 	GenHand h;
 	h.gs.n_gc = h.gs.n_lc = h.gs.n_a = h.gs.rep_len = 0, h.gs.gc = 0, h.gs.lc = 0, h.gs.a = 0;
@@ -826,7 +739,7 @@ MG_HD inline int stage_gchain_gen_w(const PipeCtx &c, ReadOut *routs, int rid, A
 	h.boff = 0, h.off_lc = h.off_a = h.sz = 0, h.mark = A.top, h.pt3 = 0, h.want_plan = 0, h.skip = 1;
 	int rc = 0;
 	Arena B = A;
-	if (lane == 0) rc = stage_gchain_gen<1>(c, routs, rid, B, &h);
+	if (lane == 0) rc = stage_gchain_gen_head(c, routs, rid, B, &h);
 	rc = warp_bcast_i32(rc, 0);
 	A.top = warp_bcast_u64(B.top, 0), A.peak = warp_bcast_u64(B.peak, 0);
 	h.skip = warp_bcast_i32(h.skip, 0);
@@ -858,7 +771,6 @@ MG_HD inline int stage_gchain_gen_w(const PipeCtx &c, ReadOut *routs, int rid, A
 
 // K8b for one read: stitch CIGARs, ds strings, part 2 of the result (one lane).
 // Warp-uniform: all lanes enter.  The CIGAR stitching runs on lane 0, the ds strings and the copies on all lanes.
-template<int V2 = 0> // V2: CIGAR stitching by the whole warp (gchain_cigar_finish_w), parameter "fin_v2"
 MG_HD inline int stage_finish(const PipeCtx &c, ReadOut *routs, int rid, Arena &A, int lane)
 {
 	ReadMeta &m = c.meta[rid];
@@ -878,17 +790,7 @@ MG_HD inline int stage_finish(const PipeCtx &c, ReadOut *routs, int rid, Arena &
 	MGB_ALLOC(A, cg, CigarOut, gs.n_gc);
 	MGB_ALLOC(A, ds, DsOut, gs.n_gc);
 	unsigned long long pt0 = prof_clock();
-	if (V2) MGB_TRY(gchain_cigar_finish_w(A, c, gs, cg, lane));
-	else {
-		Arena B = A;
-		int rc = 0;
-		if (lane == 0) rc = gchain_cigar_finish(B, c, gs, cg); // cg[] and the chain headers live in memory: visible to all lanes after the sync
-		rc = warp_bcast_i32(rc, 0);
-		A.top = warp_bcast_u64(B.top, 0);
-		A.peak = warp_bcast_u64(B.peak, 0);
-		warp_sync();
-		if (rc < 0) return rc;
-	}
+	MGB_TRY(gchain_cigar_finish_w(A, c, gs, cg, lane));
 	unsigned long long pt1 = prof_clock();
 	MGB_TRY(gchain_ds_w(A, c.g, qseq, gs, cg, ds, lane));
 	if (lane == 0) prof_add(c, PROF_FIN_CIGAR_CYC, pt1 - pt0), prof_add(c, PROF_FIN_DS_CYC, prof_clock() - pt1);

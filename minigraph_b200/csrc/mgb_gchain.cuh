@@ -7,6 +7,7 @@
 #include "mgb_model.cuh"
 #include "mgb_lchain.cuh"
 #include "mgb_shortk.cuh"
+#include "mgb_gclabel.cuh"
 #include "mgb_gwfa.cuh"
 
 namespace mgb {
@@ -42,199 +43,294 @@ struct GChain {
 struct GcFrag { uint32_t srt; int32_t i; };
 struct KeyGcFrag { MG_HD uint64_t operator()(const GcFrag &p) const { return p.srt; } };
 
-MG_HD inline int32_t gc_find_max(int32_t n, const GcFrag *gf, uint32_t x)
+// ---- graph chaining DP (reference: gchain1.c:62-240 mg_gchain1_dp, :38-60 cal_sc) ----
+// The reference walks, for every linear chain i in query-end order, back over the chains j in front of it, collects those that
+// could precede i, asks mg_shortest_k() for the graph distance to each, and scores them.  Here:
+//   * what mg_shortest_k() would answer comes from the per-source label table (mgb_gclabel.cuh) -- a binary search;
+//   * whether j can precede i, the graph distance and everything of the score but f[j] depend on the two chains alone, so that
+//     part is evaluated for ALL pairs (i, j) at once, one pair per lane;
+//   * only the order-dependent part is replayed row by row, 32 predecessors per step: the walk stops at the first pair whose
+//     query gap is too long, and after max_skip predecessors that are already the chosen predecessor of a chain visited before
+//     them in the same walk (the t[] marks of the reference; p[j] < j, so a mark only ever lands on a lane further along and one
+//     ballot per step replays the counter), then the best score in walk order wins.
+
+// a linear chain as the DP sees it, in DP order (non-isolated chains by ascending query end)
+struct GcNode {
+	int32_t qs, qe, rs, re, score, vlen;
+	uint32_t v;
+	int32_t seg_f, seg_l; // read segment of the first / last anchor (paired reads; 0 otherwise)
+	int32_t lci;          // index into lc[]
+};
+
+enum { GCP_SKIP = 0, GCP_CAND = 1, GCP_STOP = 2 };
+struct GcPair {
+	int32_t sc;     // score of chaining i after j without f[j]; SC_NONE: j is not reachable from i or out of band
+	int32_t dist;
+	uint32_t hash;
+	int32_t st;     // GCP_* | inner << 4
+};
+
+// where the walk of row i starts: the reference's find_max() (gchain1.c:16-30) over the i chains in front, with its quirk --
+// when some but not all of them end before x it returns the first one that does NOT
+MG_HD inline int32_t gc_walk_start(int32_t i, const GcNode *N, int32_t x)
 {
-	int32_t s = 0, e = n;
-	if (n == 0) return -1;
-	if (gf[n-1].srt < x) return n - 1;
-	if (gf[0].srt >= x) return -1;
-	while (e > s) {
-		int32_t m = s + (e - s) / 2;
-		if (gf[m].srt >= x) e = m;
-		else s = m + 1;
+	int32_t lo = 0, hi = i; // number of chains with qe < x (they are sorted by qe)
+	while (lo < hi) { const int32_t mid = (lo + hi) >> 1; if (N[mid].qe < x) lo = mid + 1; else hi = mid; }
+	if (lo == i) return i - 1;
+	return lo == 0? -1 : lo;
+}
+
+struct GcParam { int32_t max_dist_g, max_dist_q, bw, ref_bonus; float chn_pen_gap, mask_level; };
+
+MG_HD inline bool gc_overlap_too_big(int32_t o, int32_t len_j, int32_t len_i, float mask_level)
+{
+	return (float)o > (float)len_j * mask_level || (float)o > (float)len_i * mask_level;
+}
+
+// One pair: can chain j (ending first on the query) precede chain i, and at what score?  `rec` holds the labels of i's source.
+MG_HD inline GcPair gc_eval_pair(const GcNode &I, const GcNode &J, const GcParam &P, const char *rec)
+{
+	GcPair r;
+	r.sc = SC_NONE, r.dist = -1, r.hash = 0, r.st = GCP_SKIP;
+	if (J.qs >= I.qs) return r;                                    // j inside i on the query
+	const int32_t dq = I.qs - J.qe;
+	if (dq < 0 && gc_overlap_too_big(-dq, J.qe - J.qs, I.qe - I.qs, P.mask_level)) return r;
+	const bool same_seg = I.seg_f == J.seg_l;
+	if (same_seg? dq > P.max_dist_q : (dq > P.max_dist_g && dq > P.max_dist_q)) { r.st = GCP_STOP; return r; } // every chain further back is further away
+	const int32_t tail_j = J.vlen - J.re, head_i = I.rs;            // bases behind j / in front of i on their segments
+	const bool inner = I.v == J.v;
+	if (!inner) {
+		const int32_t min_dist = head_i + tail_j;
+		if (min_dist > P.max_dist_g) return r;
+		if (same_seg && min_dist - P.bw > dq) return r;
+	} else {
+		if (J.rs >= I.rs || J.re >= I.re) return r;                // not colinear on the segment
+		const int32_t dr = I.rs - J.re, w = dr > dq? dr - dq : dq - dr;
+		if (same_seg && w > P.bw) return r;
+		if (dr > P.max_dist_g || dr < -P.max_dist_g) return r;
+		if (dr < 0 && gc_overlap_too_big(-dr, J.re - J.rs, I.re - I.rs, P.mask_level)) return r;
 	}
-	return s;
-}
-
-MG_HD inline int32_t gc_target_dist(const GraphDev &g, const LChain *l0, const LChain *l1)
-{
-	return (l1->qs - l0->qe) - (g.seg_len[l0->v >> 1] - l0->re) + (g.seg_len[l1->v >> 1] - l1->rs);
-}
-
-MG_HD inline int32_t gc_cal_sc(const PathDst *dj, const LChain *li, const LChain *lc, const u128 *an, const GcFrag *a, const int32_t *f,
-							   int bw, int ref_bonus, float chn_pen_gap)
-{
-	const LChain *lj;
-	int32_t gap, sc, segi, segj;
-	float lin_pen, log_pen;
-	if (dj->n_path == 0) return SC_NONE;
-	segi = (int32_t)((an[li->off].y & SEED_SEG_MASK) >> SEED_SEG_SHIFT);
-	gap = dj->dist - dj->target_dist;
-	lj = &lc[a[dj->meta].i];
-	segj = (int32_t)((an[lj->off + lj->cnt - 1].y & SEED_SEG_MASK) >> SEED_SEG_SHIFT);
+	const int32_t target = dq - tail_j + (I.vlen - I.rs);          // mg_target_dist(): graph distance that would match the query gap
+	if (!inner && target < 0) return r;
+	r.st = GCP_CAND | (inner? 16 : 0);
+	int32_t dist = 0, is_0 = 0;
+	uint32_t hash = 0;
+	if (!inner && !lab_query(rec, J.v ^ 1, P.max_dist_g + (I.vlen - I.rs), target, &dist, &hash, &is_0)) return r; // not reachable
+	r.dist = dist, r.hash = hash;
+	int32_t gap = dist - target;
 	if (gap < 0) gap = -gap;
-	if (segi == segj && gap > bw) return SC_NONE;
-	if (lj->qe <= li->qs) sc = li->score;
-	else sc = (int32_t)((double)(li->qe - lj->qe) / (double)(li->qe - li->qs) * (double)li->score + .499);
-	if (dj->is_0) sc += ref_bonus;
-	lin_pen = chn_pen_gap * (float)gap;
-	log_pen = gap >= 2? fast_log2((float)gap) : 0.0f;
-	sc -= (int32_t)(lin_pen + log_pen);
-	sc += f[dj->meta];
-	return sc;
+	if (same_seg && gap > P.bw) return r;
+	int32_t sc = I.score;
+	if (J.qe > I.qs) sc = (int32_t)((double)(I.qe - J.qe) / (double)(I.qe - I.qs) * (double)I.score + .499); // i's share beyond the query overlap
+	if (is_0) sc += P.ref_bonus;
+	const float lin_pen = P.chn_pen_gap * (float)gap, log_pen = gap >= 2? fast_log2((float)gap) : 0.0f;
+	r.sc = sc - (int32_t)(lin_pen + log_pen);
+	return r;
 }
 
-// Graph chaining DP.  lc[] is permuted into chain order; u[] (score<<32|#lchains) is allocated at the caller's mark.
-MG_HD inline int gchain1_dp(Arena &A, const GraphDev &g, int32_t *n_lc_, LChain *lc, int32_t qlen, int32_t max_dist_g, int32_t max_dist_q, int32_t bw,
-							int32_t max_skip, int32_t ref_bonus, float chn_pen_gap, float mask_level, const u128 *an, uint64_t **u_, int32_t *n_u_)
+// Entered by all lanes of a warp.  lc[] (in the arena) is permuted into chain order; u[] (score<<32|#lchains) sits at the caller's mark.
+MG_HD inline int gchain_dp_w(Arena &A, const GraphDev &g, const LabTab &T, int32_t *n_lc_, LChain *lc, int32_t qlen, const GcParam &P, int32_t max_skip,
+							 const u128 *an, uint64_t **u_, int32_t *n_u_, int lane)
 {
-	int32_t i, j, k, n_dst, n_ext, n_u, n_v, n_lc = *n_lc_;
+	const int32_t n_lc = *n_lc_;
 	*u_ = 0, *n_u_ = 0;
 	if (n_lc == 0) return 0;
 	uint64_t *u_store;
 	MGB_ALLOC(A, u_store, uint64_t, n_lc);
-	uint64_t mark = A.top;
+	const uint64_t mark = A.top;
 	GcFrag *a;
 	MGB_ALLOC(A, a, GcFrag, n_lc);
-	for (i = n_ext = 0; i < n_lc; ++i) {
-		LChain *r = &lc[i];
-		int32_t is_isolated = 0, min_end_dist_g;
-		r->dist_pre = -1;
-		min_end_dist_g = g.seg_len[r->v >> 1] - r->re;
-		if (r->rs < min_end_dist_g) min_end_dist_g = r->rs;
-		if (min_end_dist_g > max_dist_g) is_isolated = 1;
-		else if (min_end_dist_g >> 3 > r->score) is_isolated = 1;
-		a[i].srt = (uint32_t)is_isolated << 31 | (uint32_t)r->qe;
-		a[i].i = i;
-		if (!is_isolated) ++n_ext;
+	int32_t n_ext = 0;
+	for (int32_t i0 = 0; i0 < n_lc; i0 += MGB_W) { // chains far from both segment ends (or small against that distance) do not take part
+		const int32_t i = i0 + lane;
+		int ext = 0;
+		if (i < n_lc) {
+			LChain *r = &lc[i];
+			const uint32_t isolated = gc_isolated(g, *r, P.max_dist_g);
+			r->dist_pre = -1;
+			a[i].srt = isolated << 31 | (uint32_t)r->qe, a[i].i = i;
+			ext = !isolated;
+		}
+		n_ext += mask_count(warp_ballot(ext));
 	}
+	warp_sync();
 	if (n_ext < 2) {
-		for (i = 0; i < n_lc; ++i) u_store[i] = (uint64_t)(int64_t)lc[i].score << 32 | 1;
+		for (int32_t i = lane; i < n_lc; i += MGB_W) u_store[i] = (uint64_t)(int64_t)lc[i].score << 32 | 1;
+		warp_sync();
 		A.top = mark;
 		*u_ = u_store, *n_u_ = n_lc;
 		return 0;
 	}
-	MGB_TRY(radix_sort_exact(A, a, n_lc, 4, KeyGcFrag()));
-	int32_t *v, *f, *p, *t;
+	MGB_TRY(radix_sort_exact_w(A, a, n_lc, 4, KeyGcFrag(), lane)); // klib's unstable sort: its tie order is the DP order
+	GcNode *N;
+	int32_t *v, *f, *p, *t, *x0, *roff;
+	const char **rec;
+	MGB_ALLOC(A, N, GcNode, n_ext);
 	MGB_ALLOC(A, v, int32_t, n_lc);
 	MGB_ALLOC(A, f, int32_t, n_ext);
 	MGB_ALLOC(A, p, int32_t, n_ext);
 	MGB_ALLOC(A, t, int32_t, n_ext);
-	for (i = 0; i < n_ext; ++i) t[i] = 0;
-	PathDst *dst;
-	MGB_ALLOC(A, dst, PathDst, n_ext); // at most i destinations for frag i
-	for (i = 0; i < n_ext; ++i) {
-		GcFrag *ai = &a[i];
-		LChain *li = &lc[ai->i];
-		int32_t segi = (int32_t)((an[li->off].y & SEED_SEG_MASK) >> SEED_SEG_SHIFT);
-		{ // candidate predecessors
-			int32_t x = li->qs + bw, n_skip = 0;
-			if (x > qlen) x = qlen;
-			x = gc_find_max(i, a, (uint32_t)x);
-			n_dst = 0;
-			for (j = x; j >= 0; --j) {
-				GcFrag *aj = &a[j];
-				LChain *lj = &lc[aj->i];
-				PathDst *q;
-				int32_t target_dist, segj, dq;
-				if (lj->qs >= li->qs) continue;
-				if (lj->qe > li->qs) {
-					int o = lj->qe - li->qs;
-					if ((float)o > (float)(lj->qe - lj->qs) * mask_level || (float)o > (float)(li->qe - li->qs) * mask_level) continue;
-				}
-				dq = li->qs - lj->qe;
-				segj = (int32_t)((an[lj->off + lj->cnt - 1].y & SEED_SEG_MASK) >> SEED_SEG_SHIFT);
-				if (segi == segj) {
-					if (dq > max_dist_q) break;
-				} else {
-					if (dq > max_dist_g && dq > max_dist_q) break;
-				}
-				if (li->v != lj->v) {
-					int32_t min_dist = li->rs + (g.seg_len[lj->v >> 1] - lj->re);
-					if (min_dist > max_dist_g) continue;
-					if (segi == segj && min_dist - bw > li->qs - lj->qe) continue;
-					target_dist = gc_target_dist(g, lj, li);
-					if (target_dist < 0) continue;
-				} else if (lj->rs >= li->rs || lj->re >= li->re) {
-					continue;
-				} else {
-					int32_t dr = li->rs - lj->re, w = dr > dq? dr - dq : dq - dr;
-					if (segi == segj && w > bw) continue;
-					if (dr > max_dist_g || dr < -max_dist_g) continue;
-					if (lj->re > li->rs) {
-						int o = lj->re - li->rs;
-						if ((float)o > (float)(lj->re - lj->rs) * mask_level || (float)o > (float)(li->re - li->rs) * mask_level) continue;
-					}
-					target_dist = gc_target_dist(g, lj, li);
-				}
-				q = &dst[n_dst++];
-				q->inner = (li->v == lj->v);
-				q->v = lj->v ^ 1;
-				q->meta = j;
-				q->qlen = li->qs - lj->qe;
-				q->target_dist = target_dist;
-				q->target_hash = 0;
-				q->check_hash = 0;
-				q->n_path = 0, q->is_0 = 0, q->path_end = 0, q->dist = 0, q->hash = 0;
-				if (t[j] == i) {
-					if (++n_skip > max_skip) break;
-				}
-				if (p[j] >= 0) t[p[j]] = i;
+	MGB_ALLOC(A, x0, int32_t, n_ext);
+	MGB_ALLOC(A, roff, int32_t, n_ext + 1);
+	MGB_ALLOC(A, rec, const char*, n_ext);
+	for (int32_t i = lane; i < n_ext; i += MGB_W) {
+		const LChain &r = lc[a[i].i];
+		GcNode n;
+		n.qs = r.qs, n.qe = r.qe, n.rs = r.rs, n.re = r.re, n.score = r.score, n.v = r.v, n.vlen = g.seg_len[r.v >> 1], n.lci = a[i].i;
+		n.seg_f = (int32_t)((an[r.off].y & SEED_SEG_MASK) >> SEED_SEG_SHIFT);
+		n.seg_l = (int32_t)((an[r.off + r.cnt - 1].y & SEED_SEG_MASK) >> SEED_SEG_SHIFT);
+		N[i] = n, t[i] = 0;
+	}
+	warp_sync();
+	for (int32_t i = lane; i < n_ext; i += MGB_W) {
+		int32_t x = N[i].qs + P.bw;
+		if (x > qlen) x = qlen;
+		x0[i] = gc_walk_start(i, N, x);
+		const long long off = T.src_off && x0[i] >= 0? T.src_off[N[i].v ^ 1] : LAB_NONE;
+		rec[i] = off >= 0? T.pool + off : 0;
+	}
+	warp_sync();
+	{ // row offsets into the pair buffer; sources the table does not have (yet) are searched here
+		Arena B = A;
+		int rc = 0;
+		if (lane == 0) {
+			roff[0] = 0;
+			for (int32_t i = 0; i < n_ext; ++i) roff[i + 1] = roff[i] + (x0[i] + 1);
+			for (int32_t i = 1; i < n_ext && rc == 0; ++i) {
+				if (rec[i] || x0[i] < 0) continue;
+				for (int32_t k = 1; k < i; ++k) if (N[k].v == N[i].v && rec[k]) { rec[i] = rec[k]; break; }
+				if (rec[i]) continue;
+				const uint64_t m2 = B.top;
+				char *r0;
+				uint64_t bytes;
+				rc = label_search(B, g, N[i].v ^ 1, P.max_dist_g + N[i].vlen, &r0, &bytes);
+				if (rc < 0) break;
+				uint64_t *d = (uint64_t*)(B.base + m2); // the record moves down over the search's scratch
+				const uint64_t *s = (const uint64_t*)r0;
+				for (uint64_t q = 0; q < bytes / 8; ++q) d[q] = s[q];
+				B.top = m2 + ((bytes + 15) & ~(uint64_t)15);
+				rec[i] = (const char*)d;
 			}
 		}
-		{ // reachability and distances
-			MGB_TRY(shortest_k(A, g, li->v ^ 1, n_dst, dst, max_dist_g + (g.seg_len[li->v >> 1] - li->rs), MAX_SHORT_K, 0, 0));
-			for (j = k = 0; j < n_dst; ++j) {
-				PathDst *dj = &dst[j];
-				int32_t sc;
-				if (dj->n_path == 0) continue;
-				sc = gc_cal_sc(dj, li, lc, an, a, f, bw, ref_bonus, chn_pen_gap);
-				if (sc == SC_NONE) continue;
-				if (sc + li->score < 0) continue;
-				dst[k++] = dst[j];
-			}
-			n_dst = k;
+		rc = warp_bcast_i32(rc, 0);
+		A.top = warp_bcast_u64(B.top, 0);
+		const uint64_t pk = warp_bcast_u64(B.peak, 0);
+		if (pk > A.peak) A.peak = pk;
+		warp_sync();
+		if (rc < 0) return rc;
+	}
+	if (lane == 0) { // row 0 has nobody in front of it
+		LChain *l0 = &lc[N[0].lci];
+		f[0] = N[0].score, p[0] = -1, v[0] = N[0].score, l0->dist_pre = -1, l0->hash_pre = 0, l0->inner_pre = 0;
+	}
+	warp_sync();
+	const int32_t n_pairs = roff[n_ext];
+	int32_t max_row = 0;
+	for (int32_t i = lane; i < n_ext; i += MGB_W) max_row = x0[i] + 1 > max_row? x0[i] + 1 : max_row;
+	max_row = warp_max_i32(max_row);
+	const int32_t budget = n_pairs < 16384? n_pairs : (max_row > 16384? max_row : 16384); // pairs evaluated per block of rows
+	GcPair *Q;
+	MGB_ALLOC(A, Q, GcPair, budget);
+	for (int32_t i0 = 1; i0 < n_ext;) {
+		int32_t i1 = i0 + 1;
+		while (i1 < n_ext && roff[i1 + 1] - roff[i0] <= budget) ++i1;
+		const int32_t base = roff[i0], n_blk = roff[i1] - base;
+		// (1) all pairs of rows [i0, i1), one per lane, stored in walk order (descending j)
+		for (int32_t q = lane; q < n_blk; q += MGB_W) {
+			int32_t lo = i0, hi = i1; // the row whose range holds q
+			while (hi - lo > 1) { const int32_t mid = (lo + hi) >> 1; if (roff[mid] - base <= q) lo = mid; else hi = mid; }
+			const int32_t i = lo, j = x0[i] - (q - (roff[i] - base));
+			Q[q] = gc_eval_pair(N[i], N[j], P, rec[i]);
 		}
-		{ // DP
-			int32_t max_f = li->score, max_j = -1, max_d = -1, max_inner = 0;
+		warp_sync();
+		// (2) the walks, row by row
+		for (int32_t i = i0; i < i1; ++i) {
+			const GcNode &I = N[i];
+			const GcPair *row = Q + (roff[i] - base);
+			const int32_t cnt = x0[i] + 1;
+			int32_t max_f = I.score, max_j = -1, max_d = -1, max_inner = 0, n_skip = 0;
 			uint32_t max_hash = 0;
-			for (j = 0; j < n_dst; ++j) {
-				PathDst *dj = &dst[j];
-				int32_t sc = gc_cal_sc(dj, li, lc, an, a, f, bw, ref_bonus, chn_pen_gap);
-				if (sc == SC_NONE) continue;
-				if (sc > max_f) max_f = sc, max_j = dj->meta, max_d = dj->dist, max_hash = dj->hash, max_inner = dj->inner;
+			for (int32_t k0 = 0; k0 < cnt; k0 += MGB_W) {
+				const int32_t k = k0 + lane, j = x0[i] - k;
+				GcPair e;
+				e.sc = SC_NONE, e.dist = -1, e.hash = 0, e.st = GCP_SKIP;
+				if (k < cnt) e = row[k];
+				const uint32_t stop_m = warp_ballot((e.st & 15) == GCP_STOP);
+				const int first_stop = stop_m? ctz32(stop_m) : MGB_W;
+				const int cand = (e.st & 15) == GCP_CAND && lane < first_stop;
+				const int32_t pj = cand? p[j] : -1;
+				if (pj >= 0) t[pj] = i; // marks of lanes past the cut below are never looked at
+				warp_sync();
+				const int marked = cand && t[j] == i;
+				const uint32_t mark_m = warp_ballot(marked);
+				const int over = marked && n_skip + mask_rank(mark_m, lane) + 1 > max_skip;
+				const uint32_t over_m = warp_ballot(over);
+				const int cut = over_m? ctz32(over_m) : MGB_W; // the walk ends with this lane's chain (it is still a candidate)
+				const int live = cand && lane <= cut;
+				int32_t sc = SC_NONE;
+				if (live && e.sc != SC_NONE) { sc = e.sc + f[j]; if (sc + I.score < 0) sc = SC_NONE; }
+				const int32_t best = warp_max_i32(sc);
+				if (best != SC_NONE && best > max_f) { // the first chain of the walk that reaches the best score
+					const int w = ctz32(warp_ballot(sc == best));
+					max_f = best, max_j = warp_bcast_i32(j, w), max_d = warp_bcast_i32(e.dist, w);
+					max_hash = (uint32_t)warp_bcast_i32((int32_t)e.hash, w), max_inner = warp_bcast_i32(e.st >> 4, w);
+				}
+				n_skip += mask_count(mark_m);
+				warp_sync();
+				if (stop_m || over_m) break;
 			}
-			f[i] = max_f, p[i] = max_j;
-			li->dist_pre = max_d;
-			li->hash_pre = max_hash;
-			li->inner_pre = max_inner;
-			v[i] = max_j >= 0 && v[max_j] > max_f? v[max_j] : max_f;
+			if (lane == 0) {
+				LChain *li = &lc[I.lci];
+				f[i] = max_f, p[i] = max_j;
+				li->dist_pre = max_d, li->hash_pre = max_hash, li->inner_pre = max_inner;
+				v[i] = max_j >= 0 && v[max_j] > max_f? v[max_j] : max_f;
+			}
+			warp_sync();
 		}
+		i0 = i1;
 	}
-	uint64_t *u;
-	MGB_TRY(chain_backtrack(A, n_ext, f, p, v, t, 0, 0, INT32_MAX, n_lc - n_ext, &u, &n_u, &n_v));
-	if (u == 0) { // cannot happen with min_sc == 0 (every f >= 0), kept for safety
-		MGB_ALLOC(A, u, uint64_t, n_lc);
-		n_u = n_v = 0;
+	// ---- peel the chains (lchain.c:27-77, shared with linear chaining), isolated chains behind them, lc[] into chain order ----
+	uint64_t *u = 0;
+	int32_t n_u = 0, n_v = 0;
+	{
+		Arena B = A;
+		int rc = 0;
+		if (lane == 0) rc = chain_backtrack(B, n_ext, f, p, v, t, 0, 0, INT32_MAX, n_lc - n_ext, &u, &n_u, &n_v);
+		rc = warp_bcast_i32(rc, 0);
+		if (rc < 0) return rc;
+		A.top = warp_bcast_u64(B.top, 0);
+		const uint64_t pk = warp_bcast_u64(B.peak, 0);
+		if (pk > A.peak) A.peak = pk;
+		u = (uint64_t*)warp_bcast_u64((uint64_t)u, 0), n_u = warp_bcast_i32(n_u, 0), n_v = warp_bcast_i32(n_v, 0);
 	}
-	for (i = 0; i < n_lc - n_ext; ++i) {
-		u[n_u++] = (uint64_t)(int64_t)lc[a[n_ext + i].i].score << 32 | 1;
-		v[n_v++] = n_ext + i;
+	if (u == 0) { MGB_ALLOC(A, u, uint64_t, n_lc); n_u = n_v = 0; } // every f >= 0 = min_sc, so this does not happen
+	LChain *ordered;
+	int32_t *first;
+	MGB_ALLOC(A, ordered, LChain, n_v + (n_lc - n_ext));
+	MGB_ALLOC(A, first, int32_t, n_u + 1);
+	if (lane == 0) { first[0] = 0; for (int32_t c = 0; c < n_u; ++c) first[c + 1] = first[c] + (int32_t)u[c]; }
+	warp_sync();
+	if (first[n_u] != n_v) return MGB_E_INTERNAL;
+	for (int32_t c = lane; c < n_u; c += MGB_W) { // v[] lists a chain from its end: turn every chain around
+		const int32_t k0 = first[c], n = (int32_t)u[c];
+		for (int32_t s = 0; s < n; ++s) ordered[k0 + s] = lc[a[v[k0 + n - 1 - s]].i];
 	}
-	LChain *swap;
-	MGB_ALLOC(A, swap, LChain, n_v);
-	for (i = 0, k = 0; i < n_u; ++i) {
-		int32_t k0 = k, ni = (int32_t)u[i];
-		for (j = 0; j < ni; ++j) swap[k++] = lc[a[v[k0 + (ni - j - 1)]].i];
+	for (int32_t s = lane; s < n_lc - n_ext; s += MGB_W) {
+		const LChain &r = lc[a[n_ext + s].i];
+		u[n_u + s] = (uint64_t)(int64_t)r.score << 32 | 1;
+		ordered[n_v + s] = r;
 	}
-	if (k != n_v) return MGB_E_INTERNAL;
-	for (i = 0; i < n_v; ++i) lc[i] = swap[i];
-	for (i = 0; i < n_u; ++i) u_store[i] = u[i];
+	n_u += n_lc - n_ext, n_v += n_lc - n_ext;
+	warp_sync();
+	for (int32_t s = lane; s < n_v; s += MGB_W) lc[s] = ordered[s];
+	for (int32_t s = lane; s < n_u; s += MGB_W) u_store[s] = u[s];
+	warp_sync();
 	*n_lc_ = n_v;
 	A.top = mark;
 	*u_ = u_store, *n_u_ = n_u;
 	return 0;
 }
+
 
 // ---- materialise graph chains ----
 

@@ -517,7 +517,6 @@ MG_HD inline double warp_min_f64(double x)
 	return x;
 }
 
-template<int V2 = 0> // V2: the walk over the inner window is replayed from ballots (as in chain_dp_w) instead of candidate by candidate
 MG_HD inline int chain_rmq_fill_w(Arena &A, int max_dist, int max_dist_inner, int bw, int max_chn_skip, float pen_gap, float pen_skip,
 								  int64_t n, const u128 *a, int32_t *f, int32_t *p, int32_t *t, int32_t *v, int lane)
 {
@@ -630,7 +629,7 @@ MG_HD inline int chain_rmq_fill_w(Arena &A, int max_dist, int max_dist_inner, in
 							c_ok = w2 <= bw;
 							c_mk = t[c_j] == (int32_t)i;
 						}
-						if (V2) { // lane c holds candidate c of this chunk; the rules below are the sequential ones, evaluated for all lanes at once
+						{ // lane c holds candidate c of this chunk; the rules below are the sequential ones, evaluated for all lanes at once
 							const int32_t sc_eff = c_ok? c_sc : SC_NONE;
 							const int32_t before = warp_excl_prefix_max_i32(sc_eff, lane);
 							const int improves = c_ok && c_sc > (before > max_f? before : max_f); // strictly above everything in front of it
@@ -655,19 +654,6 @@ MG_HD inline int chain_rmq_fill_w(Arena &A, int max_dist, int max_dist_inner, in
 								max_j = warp_max_i32(eligible && c_sc == best? c_j : -1);
 							}
 							if (brk >= 0) stop = 1;
-							continue;
-						}
-						const int32_t m = top - lb < MGB_W? top - lb : MGB_W;
-						for (int32_t c = 0; c < m; ++c) { // replay in order; all lanes keep identical state
-							const int32_t ok = warp_bcast_i32(c_ok, c);
-							if (!ok) continue;
-							const int32_t s2 = warp_bcast_i32(c_sc, c);
-							if (s2 > max_f) {
-								max_f = s2, max_j = warp_bcast_i32(c_j, c);
-								if (n_skip > 0) --n_skip;
-							} else if (warp_bcast_i32(c_mk, c)) {
-								if (++n_skip > max_chn_skip) { stop = 1; break; }
-							}
 						}
 					}
 				}
@@ -685,7 +671,6 @@ MG_HD inline int chain_rmq_fill_w(Arena &A, int max_dist, int max_dist_inner, in
 
 // Warp-uniform RMQ chaining: same contract as chain_rmq(); all lanes enter with identical arguments and leave with
 // identical results (outputs are broadcast from lane 0, which runs the sequential backtrack/compaction).
-template<int V2 = 0>
 MG_HD inline int chain_rmq_w(Arena &A, int max_dist, int max_dist_inner, int bw, int max_chn_skip, int cap_rmq_size, int min_cnt, int min_sc,
 							 float pen_gap, float pen_skip, int64_t n, u128 *a, int32_t *n_u_, uint64_t **u_, int32_t *n_a_, int lane)
 {
@@ -702,7 +687,7 @@ MG_HD inline int chain_rmq_w(Arena &A, int max_dist, int max_dist_inner, int bw,
 	MGB_ALLOC(A, f, int32_t, n);
 	MGB_ALLOC(A, t, int32_t, n);
 	MGB_ALLOC(A, v, int32_t, n);
-	int rc = n <= cap_rmq_size? chain_rmq_fill_w<V2>(A, max_dist, max_dist_inner, bw, max_chn_skip, pen_gap, pen_skip, n, a, f, p, t, v, lane) : 1;
+	int rc = n <= cap_rmq_size? chain_rmq_fill_w(A, max_dist, max_dist_inner, bw, max_chn_skip, pen_gap, pen_skip, n, a, f, p, t, v, lane) : 1;
 	if (rc < 0) return rc;
 	int32_t n_u = 0, n_v = 0;
 	if (rc == 1) { // too many anchors for the cooperative fill: sequential replay on one lane

@@ -6,6 +6,7 @@
 #include "mgb_model.cuh"
 #include "mgb_seed.cuh"
 #include "mgb_lchain.cuh"
+#include "mgb_gclabel.cuh"
 
 namespace mgb {
 
@@ -24,11 +25,10 @@ struct PipeCtx {
 	Pool *pool_jobs;       struct WfaJob *jobs;  // gap alignment jobs
 	Pool *pool_cig;        uint32_t *cig;        // per-job CIGARs
 	int32_t *jobq[2];      unsigned int *jobq_n;   // jobs handed to WFA tier 2 / tier 3
-	int32_t cta_len;       // > 0: tier-3 gaps with tl + ql >= cta_len are first offered to the block-per-gap kernel (mgb_wfa_cta.cuh)
-	int32_t big_len;       // > 0: gaps with tl or ql >= big_len are not touched by tiers 1/2 (a tier-3 launch on a second stream has them)
 	Pool *pool_gstate;     char *gstate;         // per-read state between the two graph-chaining passes
 	Pool *pool_gjobs;      struct GwfaJob *gjobs; // bridging alignment jobs (K7a)
 	Pool *pool_walk;       int32_t *walk;        // walks found by the bridging jobs
+	LabTab lab;            // reachability labels of the graph (mgb_gclabel.cuh); persistent across batches
 	// work queue
 	unsigned int *next_read;
 	// instrumentation: 32 counters, see PROF_* below
@@ -40,7 +40,7 @@ struct PipeCtx {
 
 enum { PROF_WFA_FAST_CYC = 0, PROF_WFA_FAST_N, PROF_WFA_SLOW_CYC, PROF_WFA_SLOW_N, PROF_WFA_MAX_CYC, PROF_WFA_CELLS, PROF_WFA_TB_CYC,
 	   PROF_GC_DP_CYC, PROF_GC_GEN_CYC, PROF_GC_POST_CYC, PROF_GC_PLAN_CYC, PROF_FIN_CIGAR_CYC, PROF_FIN_DS_CYC, PROF_SEED_SKETCH_CYC,
-	   PROF_SEED_MATCH_CYC, PROF_SEED_SORT_CYC, PROF_CHAIN_DP_CYC, PROF_CHAIN_BT_CYC, PROF_CHAIN_RMQ_CYC, PROF_CHAIN_POST_CYC, PROF_WFA_MID_CYC, PROF_WFA_MID_N, PROF_GC_GWFA_CYC, PROF_GC_SHORTK_CYC, PROF_GC_EXTRA_CYC, PROF_GWFA_MAX_CYC, PROF_GC_DP_MAX_CYC, PROF_WFA_CTA_CYC, PROF_WFA_CTA_N, PROF_N = 32 };
+	   PROF_SEED_MATCH_CYC, PROF_SEED_SORT_CYC, PROF_CHAIN_DP_CYC, PROF_CHAIN_BT_CYC, PROF_CHAIN_RMQ_CYC, PROF_CHAIN_POST_CYC, PROF_WFA_MID_CYC, PROF_WFA_MID_N, PROF_GC_GWFA_CYC, PROF_GC_SHORTK_CYC, PROF_GC_EXTRA_CYC, PROF_GWFA_MAX_CYC, PROF_GC_DP_MAX_CYC, PROF_WFA_CTA_CYC, PROF_WFA_CTA_N, PROF_LAB_CYC, PROF_LAB_N, PROF_N = 32 };
 
 MG_HD inline unsigned long long prof_clock()
 {
@@ -71,7 +71,6 @@ MG_HD inline void prof_max(const PipeCtx &c, int slot, unsigned long long v)
 // mini_pos pool.
 // Warp-uniform: all lanes enter; the sketch is cut into chunks over the lanes, the index probes and the seed expansion
 // are spread over the lanes, the (order-sensitive, unstable) seed sort runs on lane 0.
-template<int V2 = 0> // V2: the window rings of the sketch live in shared memory (smem: SKETCH_SMEM_BYTES per warp), parameter "seed_v2"
 MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A, int lane, int32_t *smem = 0)
 {
 	ReadMeta &m = c.meta[rid];
@@ -95,7 +94,7 @@ MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A, int lane, int32
 	unsigned long long t0 = prof_clock();
 	const int32_t n_seg = batch_n_seg(c.b, rid);
 	if (n_seg == 1) {
-		MGB_TRY(sketch_seq_w(A, seq, qlen, c.ix.w, c.ix.k, 0, mv, lane, V2? (u128*)smem : 0));
+		MGB_TRY(sketch_seq_w(A, seq, qlen, c.ix.w, c.ix.k, 0, mv, lane, (u128*)smem));
 	} else { // reference: map-algo.c:34-45 collect_minimizers: every segment on its own, positions shifted by the lengths before it
 		const int32_t *sl = c.b.seg_len + c.b.seg_off[rid];
 		MGB_ALLOC(A, mv.a, u128, (int64_t)qlen + 16 * (int64_t)n_seg);
@@ -105,7 +104,7 @@ MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A, int lane, int32
 		for (int32_t i = 0; i < n_seg; ++i) {
 			AVec<u128> one;
 			avec_init(one);
-			if (sl[i] > 0) MGB_TRY(sketch_seq_w(A, seq + sum, sl[i], c.ix.w, c.ix.k, (uint32_t)i, one, lane, V2? (u128*)smem : 0));
+			if (sl[i] > 0) MGB_TRY(sketch_seq_w(A, seq + sum, sl[i], c.ix.w, c.ix.k, (uint32_t)i, one, lane, (u128*)smem));
 			if (mv.n + one.n > mv.m) return MGB_E_INTERNAL;
 			for (int64_t j = lane; j < one.n; j += MGB_W) { u128 e = one.a[j]; e.y += (uint64_t)sum << 1; mv.a[mv.n + j] = e; }
 			warp_sync();
@@ -193,6 +192,13 @@ MG_HD inline int stage_chain_tail(const PipeCtx &c, ReadMeta &m, Arena &A, u128 
 		const int32_t *mp = c.minipos + m.mp_off;
 		for (int32_t i = 0; i < n_lc; ++i)
 			MGB_TRY(update_anchors(lc[i].cnt, &a[lc[i].off], m.n_mp, mp));
+		if (n_lc > 1 && c.lab.src_off) { // graph chaining will ask for walks out of these chains' vertices (gchain_dp_w applies the same test)
+			int32_t n_ext = 0;
+			for (int32_t i = 0; i < n_lc; ++i) n_ext += !gc_isolated(c.g, lc[i], o.bw_long);
+			if (n_ext >= 2)
+				for (int32_t i = 0; i < n_lc; ++i)
+					if (!gc_isolated(c.g, lc[i], o.bw_long)) lab_want(c.lab, lc[i].v ^ 1);
+		}
 		int64_t lc_off = pool_alloc(c.pool_lchain, (uint64_t)n_lc * sizeof(LChain));
 		if (lc_off < 0) return MGB_E_POOL;
 		m.lc_off = lc_off / (int64_t)sizeof(LChain);
@@ -210,7 +216,6 @@ MG_HD inline int stage_chain_tail(const PipeCtx &c, ReadMeta &m, Arena &A, u128 
 // lower occupancy cost the rest of the kernel more (k_chain 11.0 -> 14.6 / 16.0 ms on B200), so the kernel asks for none.
 static const int CHAIN_SMEM = 7 * 1024;
 
-template<int V2 = 0> // V2: ballot replay in the RMQ walk (chain_rmq_fill_w<1>), parameter "chain_v2"
 MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A, int lane, int32_t *smem = 0)
 {
 	ReadMeta &m = c.meta[rid];
@@ -236,7 +241,7 @@ MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A, int lane, int3
 	unsigned long long t0 = prof_clock();
 	if (n_a > 0) {
 		if (o.flag & F_RMQ) {
-			MGB_TRY(chain_rmq_w<V2>(A, o.max_gap, o.max_gap_pre, o.bw, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
+			MGB_TRY(chain_rmq_w(A, o.max_gap, o.max_gap_pre, o.bw, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
 								o.chn_pen_gap, o.chn_pen_skip, n_a, a, &n_lc, &u, &n_a_new, lane));
 		} else {
 			MGB_TRY(chain_dp_w(A, max_gap_ref, max_gap_qry, o.bw, o.max_lc_skip, o.max_lc_iter, o.min_lc_cnt, o.min_lc_score,
@@ -255,7 +260,7 @@ MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A, int lane, int3
 			warp_sync(); // u[] sits at the mark: every lane must have read it before the sort below reuses that memory
 			A.top = mark;
 			MGB_TRY(radix_sort_128x_w(A, a, n2, lane));
-			MGB_TRY(chain_rmq_w<V2>(A, o.max_gap, o.max_gap_pre, o.bw_long, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
+			MGB_TRY(chain_rmq_w(A, o.max_gap, o.max_gap_pre, o.bw_long, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
 								o.chn_pen_gap, o.chn_pen_skip, n2, a, &n_lc, &u, &n_a_new, lane));
 		}
 	}

@@ -145,13 +145,8 @@ struct WfSmemLayout {
 	static const int STRIDE = (BYTES + 127) / 128 * 128;
 };
 
-struct WfSrc { const wf_cell_t *p; int32_t lo, hi; }; // one source slice of the recurrence
-
 template<int W>
 MG_HD inline int32_t wfs_col(int32_t d) { return (d + (1 << 20)) & (W - 1); }
-
-template<int W>
-MG_HD inline int32_t wfs_at(const WfSrc &s, int32_t d) { return (d >= s.lo && d <= s.hi)? (int32_t)s.p[wfs_col<W>(d)] : WF_NEG_INF16; }
 
 struct WfTbSmem { // traceback bytes in shared memory: row table {lo, width, off} is packed as lo, off; width from the next row
 	const int32_t *row; const uint8_t *x; int32_t n_rows, used;
@@ -174,151 +169,6 @@ struct WfTbArena { // traceback rows bump-allocated in the worker arena (referen
 	}
 };
 
-template<int W, int MAXLEN, int TBCAP, int HS>
-MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g, int32_t ql, const char *qs_g, WfResult *r, int lane)
-{
-	typedef WfSmemLayout<W, MAXLEN, TBCAP, HS> LY;
-	if (tl > MAXLEN || ql > MAXLEN) return 1;
-	if (MAXLEN > 16000 || HS != 17) return 1; // cells are 16-bit; all 17 H slices are kept on chip
-	uint64_t mark = A.top;
-	wf_cell_t *H = (wf_cell_t*)smem, *E1 = H + HS * W, *F1 = E1 + 3 * W, *E2 = F1 + 3 * W, *F2 = E2 + 2 * W;
-	char *ts = (char*)(smem + LY::N_INTS), *qs = ts + LY::SEQ_BYTES;
-	int32_t *tb_row = (int32_t*)(qs + LY::SEQ_BYTES); // TBCAP > 0 only
-	uint8_t *tb_x = (uint8_t*)tb_row + LY::TB_ROW_BYTES;
-	wf_stage_seq(ts, ts_g, tl, 0xfe, lane);
-	wf_stage_seq(qs, qs_g, ql, 0xff, lane);
-	r->s = -1, r->n_cigar = 0, r->n_iter = 0, r->cigar = 0;
-	uint32_t *cig_store;
-	const int64_t max_cigar = (int64_t)tl + ql + 2;
-	MGB_ALLOC(A, cig_store, uint32_t, max_cigar);
-	uint64_t mark_keep = A.top;
-	AVec<WfTbRow> rows; // TBCAP == 0 only
-	avec_init(rows);
-	if (TBCAP == 0) MGB_TRY(avec_reserve_w(A, rows, 256, lane));
-	int32_t n_rows = 0, tb_used = 0;
-	int32_t wlo = 0, whi = 0, last_state = 0, s = 0;
-	int64_t n_iter = 0;
-	int hs = 0, m3 = 0, m2 = 0; // s % 17, s % 3, s % 2, kept incrementally
-	// [lo,hi] of the last 16 scores in registers, newest first: g0 = score s, g1 = s-1, ... (hi<<16 | lo+0x8000; 0x8001 = empty)
-#define MGB_WF_RG(lo_, hi_) ((uint32_t)((hi_) + 0x8000) << 16 | (uint32_t)((lo_) + 0x8000))
-	uint32_t g0 = MGB_WF_RG(0, 0), g1 = MGB_WF_RG(1, 0), g2 = g1, g3 = g1, g4 = g1, g5 = g1, g6 = g1, g7 = g1, g8 = g1, g9 = g1, g10 = g1, g11 = g1, g12 = g1, g13 = g1, g14 = g1, g15 = g1;
-	int hit = 0, hit_noext = 0;
-	warp_sync(); // the staged sequences are complete before lane 0 reads them
-	if (lane == 0) { // score 0: the main diagonal, extended from the corner
-		E1[wfs_col<W>(0)] = F1[wfs_col<W>(0)] = E2[wfs_col<W>(0)] = F2[wfs_col<W>(0)] = (wf_cell_t)WF_NEG_INF16;
-		int32_t k0 = -1, k = -1;
-		if (!(k0 >= tl || k0 >= ql)) {
-			k = wf_extend(ts, qs, k0, 0);
-			if (k == tl - 1 && k == ql - 1) hit = 1, hit_noext = (k == k0), k = k0;
-		}
-		H[wfs_col<W>(0)] = (wf_cell_t)k;
-	}
-	hit = warp_any(hit), hit_noext = warp_any(hit_noext);
-	warp_sync();
-	for (;;) {
-		// invariant: the wavefront of score s is computed, extended along exact matches and visible to all lanes
-		if (hit) {
-			if (hit_noext) { // no extension on the last diagonal: the state comes from the traceback byte
-				int32_t x;
-				if (TBCAP > 0) { WfTbSmem t; t.row = tb_row, t.x = tb_x, t.n_rows = n_rows, t.used = tb_used; x = t.get(n_rows - 1, ql - tl); }
-				else { WfTbArena t; t.row = rows.a; x = t.get(n_rows - 1, ql - tl); }
-				last_state = x & 7;
-			}
-			break;
-		}
-		const int32_t lo = wlo > -tl? wlo - 1 : -tl;
-		const int32_t hi = whi < ql? whi + 1 : ql;
-		const int32_t width = hi - lo + 1;
-		if (width > W || s + 1 >= 255 || (TBCAP > 0 && tb_used + width > TBCAP)) { A.top = mark; return 1; }
-		const int32_t ns = s + 1;
-		const int nhs = hs + 1 == 17? 0 : hs + 1, n3 = m3 + 1 == 3? 0 : m3 + 1, n2 = m2 ^ 1;
-		uint8_t *ax;
-		if (TBCAP > 0) {
-			if (lane == 0) tb_row[2 * n_rows] = lo, tb_row[2 * n_rows + 1] = tb_used;
-			ax = tb_x + tb_used - lo;
-			tb_used += width;
-		} else {
-			MGB_TRY(avec_reserve_w(A, rows, n_rows + 1, lane));
-			uint8_t *x;
-			MGB_ALLOC(A, x, uint8_t, width);
-			if (lane == 0) rows.a[n_rows].lo = lo, rows.a[n_rows].hi = hi, rows.a[n_rows].x = x;
-			rows.n = n_rows + 1;
-			ax = x - lo;
-		}
-		++n_rows;
-		// source slices: score ns-4 (mismatch), ns-6 and ns-16 (gap opens), ns-2 and ns-1 (gap extensions)
-		const int r4 = nhs >= WF_X? nhs - WF_X : nhs - WF_X + 17, r6 = nhs >= WF_O1 + WF_E1? nhs - (WF_O1 + WF_E1) : nhs - (WF_O1 + WF_E1) + 17;
-		const int r16 = nhs >= WF_O2 + WF_E2? nhs - (WF_O2 + WF_E2) : nhs - (WF_O2 + WF_E2) + 17;
-		const int e1slot = n3 >= 2? n3 - 2 : n3 + 1; // (ns-2) % 3
-		WfSrc sHx, sHo1, sHo2, sE1, sF1, sE2, sF2;
-#define MGB_WF_SRC(dst, arr, slot, g) (dst).p = (arr) + (slot) * W, (dst).lo = (int32_t)((g) & 0xffffu) - 0x8000, (dst).hi = (int32_t)((g) >> 16) - 0x8000
-		MGB_WF_SRC(sHx, H, r4, g3); MGB_WF_SRC(sHo1, H, r6, g5); MGB_WF_SRC(sHo2, H, r16, g15);
-		MGB_WF_SRC(sE1, E1, e1slot, g1); MGB_WF_SRC(sF1, F1, e1slot, g1); MGB_WF_SRC(sE2, E2, m2, g0); MGB_WF_SRC(sF2, F2, m2, g0);
-#undef MGB_WF_SRC
-		wf_cell_t *nH = H + nhs * W, *nE1 = E1 + n3 * W, *nF1 = F1 + n3 * W, *nE2 = E2 + n2 * W, *nF2 = F2 + n2 * W;
-		int grow_lo = 0, grow_hi = 0;
-		for (int32_t d = lo + lane; d <= hi; d += MGB_W) { // reference: miniwfa.c:281-308 wf_next_tb, then :212-226 on the new cell
-			int32_t h, f, e, e1, e2, f1, f2, a0, b0;
-			uint8_t x = 0, ze, zf, z;
-			a0 = wfs_at<W>(sHo1, d - 1), b0 = wfs_at<W>(sE1, d - 1);
-			x |= a0 >= b0? 0 : 0x08; e1 = MGB_WF_MAX(a0, b0);
-			a0 = wfs_at<W>(sHo2, d - 1), b0 = wfs_at<W>(sE2, d - 1);
-			x |= a0 >= b0? 0 : 0x20; e2 = MGB_WF_MAX(a0, b0);
-			ze = e1 >= e2? 1 : 3;
-			e = MGB_WF_MAX(e1, e2);
-			a0 = wfs_at<W>(sHo1, d + 1), b0 = wfs_at<W>(sF1, d + 1);
-			x |= a0 >= b0? 0 : 0x10; f1 = MGB_WF_MAX(a0, b0) + 1;
-			a0 = wfs_at<W>(sHo2, d + 1), b0 = wfs_at<W>(sF2, d + 1);
-			x |= a0 >= b0? 0 : 0x40; f2 = MGB_WF_MAX(a0, b0) + 1;
-			zf = f1 >= f2? 2 : 4;
-			f = MGB_WF_MAX(f1, f2);
-			z = e >= f? ze : zf;
-			h = MGB_WF_MAX(e, f);
-			a0 = wfs_at<W>(sHx, d) + 1;
-			z = a0 >= h? 0 : z;
-			h = MGB_WF_MAX(a0, h);
-			ax[d] = x | z;
-			if (h >= -1 || e1 >= -1 || f1 >= -1 || e2 >= -1 || f2 >= -1) { // does the window still grow on this side?
-				if (d == lo) grow_lo = 1;
-				if (d == hi) grow_hi = 1;
-			}
-			if (!(h < -1 || d + h < -1 || h >= tl || d + h >= ql)) { // extend the new cell right away
-				const int32_t k = wf_extend(ts, qs, h, d);
-				if (k == tl - 1 && d + k == ql - 1) hit = 1, hit_noext = (k == h);
-				else h = k;
-			}
-			const int32_t c = wfs_col<W>(d);
-			nE1[c] = (wf_cell_t)e1, nF1[c] = (wf_cell_t)f1, nE2[c] = (wf_cell_t)e2, nF2[c] = (wf_cell_t)f2, nH[c] = (wf_cell_t)h; // slots of score ns are not read in this loop
-		}
-		if (warp_any(grow_lo)) wlo = lo;
-		if (warp_any(grow_hi)) whi = hi;
-		hit = warp_any(hit);
-		hit_noext = warp_any(hit && hit_noext);
-		g15 = g14, g14 = g13, g13 = g12, g12 = g11, g11 = g10, g10 = g9, g9 = g8, g8 = g7, g7 = g6, g6 = g5, g5 = g4, g4 = g3, g3 = g2, g2 = g1, g1 = g0;
-		g0 = MGB_WF_RG(lo, hi);
-		s = ns, hs = nhs, m3 = n3, m2 = n2;
-		n_iter += width;
-		warp_sync();
-	}
-#undef MGB_WF_RG
-	r->n_iter = n_iter;
-	r->s = s;
-	{
-		int rc = 0;
-		int32_t n_cig = 0;
-		int64_t first = 0;
-		if (lane == 0) {
-			if (TBCAP > 0) { WfTbSmem t; t.row = tb_row, t.x = tb_x, t.n_rows = n_rows, t.used = tb_used; rc = wf_traceback(t, n_rows, tl, ts, ql, qs, last_state, cig_store, max_cigar, &n_cig, &first); }
-			else { WfTbArena t; t.row = rows.a; rc = wf_traceback(t, n_rows, tl, ts, ql, qs, last_state, cig_store, max_cigar, &n_cig, &first); }
-		}
-		rc = warp_bcast_i32(rc, 0), n_cig = warp_bcast_i32(n_cig, 0), first = (int64_t)warp_bcast_u64((uint64_t)first, 0);
-		warp_sync();
-		if (rc < 0) { A.top = mark; return rc; }
-		r->n_cigar = n_cig, r->cigar = cig_store + first;
-	}
-	A.top = mark_keep;
-	return 0;
-}
 
 // =================================================================================================================
 // general scheme: ring in the worker arena, mirrors the reference's memory layout
@@ -889,160 +739,11 @@ MG_HD inline int wfa_chain(Arena &A, int32_t tl, const char *ts, int32_t ql, con
 // 16 bits are enough while tl + ql <= 16000: the score never exceeds o2 + e2*tl + o2 + e2*ql <= tl + ql + 30, so an
 // invalid cell (sentinel plus at most one increment per score) stays far below -1 and orders like the 32-bit one.
 // Returns 1 when it does not apply (the caller then uses wfa_core), 0 otherwise; r->s = -1 when max_iter cells were exceeded.
-struct WfSrcG { const wf_cell_t *p; int32_t lo, hi; };
-MG_HD inline int32_t wfg_at(const WfSrcG &s, int32_t d, int32_t mask) { return (d >= s.lo && d <= s.hi)? (int32_t)s.p[(d + (1 << 20)) & mask] : WF_NEG_INF16; }
-
-MG_HD inline int wfa_ring_g(Arena &A, int32_t tl, const char *ts, int32_t ql, const char *qs, int64_t max_iter, WfResult *r,
-							uint32_t *cig_store, int64_t max_cigar, int lane)
-{
-	if (tl + ql > 16000 || tl <= 0 || ql <= 0) return 1;
-	uint64_t mark = A.top;
-	int32_t W = 64;
-	while (W < tl + ql + 2) W <<= 1;
-	const int32_t mask = W - 1;
-	wf_cell_t *cells;
-	MGB_ALLOC(A, cells, wf_cell_t, (int64_t)5 * 17 * W);
-	wf_cell_t *H = cells, *E1 = H + 17 * W, *F1 = E1 + 17 * W, *E2 = F1 + 17 * W, *F2 = E2 + 17 * W;
-	AVec<WfTbRow> rows;
-	avec_init(rows);
-	MGB_TRY(avec_reserve_w(A, rows, 1024, lane));
-	int32_t n_rows = 0;
-	int32_t wlo = 0, whi = 0, last_state = 0, s = 0, stopped = 0;
-	int64_t n_iter = 0;
-	int hs = 0;
-#define MGB_WF_RG(lo_, hi_) ((uint32_t)((hi_) + 0x8000) << 16 | (uint32_t)((lo_) + 0x8000))
-	uint32_t g0 = MGB_WF_RG(0, 0), g1 = MGB_WF_RG(1, 0), g2 = g1, g3 = g1, g4 = g1, g5 = g1, g6 = g1, g7 = g1, g8 = g1, g9 = g1, g10 = g1, g11 = g1, g12 = g1, g13 = g1, g14 = g1, g15 = g1, g16 = g1;
-	int hit = 0, hit_noext = 0;
-	if (lane == 0) { // score 0: the main diagonal, extended from the corner
-		const int32_t c0 = (1 << 20) & mask;
-		E1[c0] = F1[c0] = E2[c0] = F2[c0] = (wf_cell_t)WF_NEG_INF16;
-		int32_t k0 = -1, k = -1;
-		k = wf_extend(ts, qs, k0, 0);
-		if (k == tl - 1 && k == ql - 1) hit = 1, hit_noext = (k == k0), k = k0;
-		H[c0] = (wf_cell_t)k;
-	}
-	hit = warp_any(hit), hit_noext = warp_any(hit_noext);
-	warp_sync();
-	for (;;) {
-		if (hit) {
-			if (hit_noext) { WfTbArena t; t.row = rows.a; last_state = t.get(n_rows - 1, ql - tl) & 7; }
-			break;
-		}
-		const int32_t lo = wlo > -tl? wlo - 1 : -tl;
-		const int32_t hi = whi < ql? whi + 1 : ql;
-		const int32_t width = hi - lo + 1;
-		const int32_t ns = s + 1;
-		const int nhs = hs + 1 == 17? 0 : hs + 1;
-		MGB_TRY(avec_reserve_w(A, rows, n_rows + 1, lane));
-		uint8_t *x;
-		MGB_ALLOC(A, x, uint8_t, width);
-		if (lane == 0) rows.a[n_rows].lo = lo, rows.a[n_rows].hi = hi, rows.a[n_rows].x = x;
-		rows.n = ++n_rows;
-		uint8_t *ax = x - lo;
-		const int r4 = nhs >= WF_X? nhs - WF_X : nhs - WF_X + 17, r6 = nhs >= WF_O1 + WF_E1? nhs - (WF_O1 + WF_E1) : nhs - (WF_O1 + WF_E1) + 17;
-		const int r16 = nhs >= WF_O2 + WF_E2? nhs - (WF_O2 + WF_E2) : nhs - (WF_O2 + WF_E2) + 17, r2 = nhs >= WF_E1? nhs - WF_E1 : nhs - WF_E1 + 17;
-		WfSrcG sHx, sHo1, sHo2, sE1, sF1, sE2, sF2;
-#define MGB_WF_SRC(dst, arr, slot, g) (dst).p = (arr) + (int64_t)(slot) * W, (dst).lo = (int32_t)((g) & 0xffffu) - 0x8000, (dst).hi = (int32_t)((g) >> 16) - 0x8000
-		MGB_WF_SRC(sHx, H, r4, g3); MGB_WF_SRC(sHo1, H, r6, g5); MGB_WF_SRC(sHo2, H, r16, g15);
-		MGB_WF_SRC(sE1, E1, r2, g1); MGB_WF_SRC(sF1, F1, r2, g1); MGB_WF_SRC(sE2, E2, hs, g0); MGB_WF_SRC(sF2, F2, hs, g0);
-#undef MGB_WF_SRC
-		wf_cell_t *nH = H + (int64_t)nhs * W, *nE1 = E1 + (int64_t)nhs * W, *nF1 = F1 + (int64_t)nhs * W, *nE2 = E2 + (int64_t)nhs * W, *nF2 = F2 + (int64_t)nhs * W;
-		int grow_lo = 0, grow_hi = 0;
-		for (int32_t d = lo + lane; d <= hi; d += MGB_W) { // reference: miniwfa.c:281-308 wf_next_tb, then :212-226 on the new cell
-			int32_t h, f, e, e1, e2, f1, f2, a0, b0;
-			uint8_t xb = 0, ze, zf, z;
-			a0 = wfg_at(sHo1, d - 1, mask), b0 = wfg_at(sE1, d - 1, mask);
-			xb |= a0 >= b0? 0 : 0x08; e1 = MGB_WF_MAX(a0, b0);
-			a0 = wfg_at(sHo2, d - 1, mask), b0 = wfg_at(sE2, d - 1, mask);
-			xb |= a0 >= b0? 0 : 0x20; e2 = MGB_WF_MAX(a0, b0);
-			ze = e1 >= e2? 1 : 3;
-			e = MGB_WF_MAX(e1, e2);
-			a0 = wfg_at(sHo1, d + 1, mask), b0 = wfg_at(sF1, d + 1, mask);
-			xb |= a0 >= b0? 0 : 0x10; f1 = MGB_WF_MAX(a0, b0) + 1;
-			a0 = wfg_at(sHo2, d + 1, mask), b0 = wfg_at(sF2, d + 1, mask);
-			xb |= a0 >= b0? 0 : 0x40; f2 = MGB_WF_MAX(a0, b0) + 1;
-			zf = f1 >= f2? 2 : 4;
-			f = MGB_WF_MAX(f1, f2);
-			z = e >= f? ze : zf;
-			h = MGB_WF_MAX(e, f);
-			a0 = wfg_at(sHx, d, mask) + 1;
-			z = a0 >= h? 0 : z;
-			h = MGB_WF_MAX(a0, h);
-			ax[d] = xb | z;
-			if (h >= -1 || e1 >= -1 || f1 >= -1 || e2 >= -1 || f2 >= -1) {
-				if (d == lo) grow_lo = 1;
-				if (d == hi) grow_hi = 1;
-			}
-			if (!(h < -1 || d + h < -1 || h >= tl || d + h >= ql)) {
-				const int32_t k = wf_extend(ts, qs, h, d);
-				if (k == tl - 1 && d + k == ql - 1) hit = 1, hit_noext = (k == h);
-				else h = k;
-			}
-			const int32_t c = (d + (1 << 20)) & mask;
-			nE1[c] = (wf_cell_t)e1, nF1[c] = (wf_cell_t)f1, nE2[c] = (wf_cell_t)e2, nF2[c] = (wf_cell_t)f2, nH[c] = (wf_cell_t)h;
-		}
-		if (warp_any(grow_lo)) wlo = lo;
-		if (warp_any(grow_hi)) whi = hi;
-		hit = warp_any(hit);
-		hit_noext = warp_any(hit && hit_noext);
-		g16 = g15, g15 = g14, g14 = g13, g13 = g12, g12 = g11, g11 = g10, g10 = g9, g9 = g8, g8 = g7, g7 = g6, g6 = g5, g5 = g4, g4 = g3, g3 = g2, g2 = g1, g1 = g0;
-		g0 = MGB_WF_RG(lo, hi);
-		s = ns, hs = nhs;
-		warp_sync();
-		if ((s & 0xff) == 0) { // reference: miniwfa.c:144-171 wf_stripe_shrink: keep the diagonals on which one of the 17 wavefronts still has a cell inside the matrix
-			const uint32_t gg[17] = { g0, g1, g2, g3, g4, g5, g6, g7, g8, g9, g10, g11, g12, g13, g14, g15, g16 };
-			int32_t nlo = 0, nhi = 0, found = 0;
-			for (int pass = 0; pass < 2; ++pass) {
-				found = 0;
-				for (int32_t base = pass == 0? wlo : whi; pass == 0? base <= whi : base >= wlo; base += pass == 0? MGB_W : -MGB_W) {
-					const int32_t d = pass == 0? base + lane : base - lane;
-					int good = 0;
-					if (d >= wlo && d <= whi) {
-						const int32_t c = (d + (1 << 20)) & mask;
-						for (int j = 0; j < 17 && !good; ++j) {
-							const int32_t jl = (int32_t)(gg[j] & 0xffffu) - 0x8000, jh = (int32_t)(gg[j] >> 16) - 0x8000;
-							if (d < jl || d > jh) continue;
-							const int slot = hs >= j? hs - j : hs - j + 17;
-							const int64_t o = (int64_t)slot * W + c;
-							good = wf_good_diag(d, H[o], tl, ql) || wf_good_diag(d, E1[o], tl, ql) || wf_good_diag(d, F1[o], tl, ql) || wf_good_diag(d, E2[o], tl, ql) || wf_good_diag(d, F2[o], tl, ql);
-						}
-					}
-					const uint32_t m = warp_ballot(good);
-					if (m) { found = 1; if (pass == 0) nlo = base + ctz32(m); else nhi = base - ctz32(m); break; }
-				}
-				if (!found) break;
-			}
-			if (!found) { A.top = mark; return MGB_E_INTERNAL; }
-			wlo = nlo, whi = nhi;
-		}
-		n_iter += width;
-		if (max_iter > 0 && n_iter > max_iter) { stopped = 1; break; }
-	}
-#undef MGB_WF_RG
-	r->n_iter = n_iter;
-	r->s = stopped? -1 : s;
-	if (!stopped) {
-		int rc = 0;
-		int32_t n_cig = 0;
-		int64_t first = 0;
-		if (lane == 0) {
-			WfTbArena t; t.row = rows.a;
-			rc = wf_traceback(t, n_rows, tl, ts, ql, qs, last_state, cig_store, max_cigar, &n_cig, &first);
-		}
-		rc = warp_bcast_i32(rc, 0), n_cig = warp_bcast_i32(n_cig, 0), first = (int64_t)warp_bcast_u64((uint64_t)first, 0);
-		warp_sync();
-		if (rc < 0) { A.top = mark; return rc; }
-		r->n_cigar = n_cig, r->cigar = cig_store + first;
-	}
-	A.top = mark;
-	return 0;
-}
 
 // Tier 3 entry (reference: miniwfa.c:824-834 mwf_wfa_auto): exact alignment capped at max_iter cells by the whole warp;
 // beyond the cap the chaining heuristic takes over on lane 0.
-MG_HD inline int wfa_ring_g2(Arena &A, int32_t tl, const char *ts, int32_t ql, const char *qs, int64_t max_iter, WfResult *r,
-							 uint32_t *cig_store, int64_t max_cigar, int lane); // second version of the ring (mgb_wfa2.cuh), used when V2
-template<int V2 = 0>
+MG_HD inline int wfa_ring_g(Arena &A, int32_t tl, const char *ts, int32_t ql, const char *qs, int64_t max_iter, WfResult *r,
+							 uint32_t *cig_store, int64_t max_cigar, int lane); // mgb_wfa_tiers.cuh
 MG_HD inline int wfa_exact(Arena &A, int32_t tl, const char *ts_g, int32_t ql, const char *qs_g, int64_t max_iter, WfResult *r, int lane, int32_t step = 5000)
 {
 	uint64_t mark = A.top;
@@ -1058,7 +759,7 @@ MG_HD inline int wfa_exact(Arena &A, int32_t tl, const char *ts_g, int32_t ql, c
 	wf_stage_seq(qs, qs_g, ql, 0xff, lane);
 	warp_sync();
 	{
-		int rc = V2? wfa_ring_g2(A, tl, ts, ql, qs, max_iter, r, cig_store, max_cigar, lane) : wfa_ring_g(A, tl, ts, ql, qs, max_iter, r, cig_store, max_cigar, lane);
+		int rc = wfa_ring_g(A, tl, ts, ql, qs, max_iter, r, cig_store, max_cigar, lane);
 		if (rc < 0) return rc;
 		if (rc == 1) MGB_TRY(wfa_core(A, tl, ts, ql, qs, max_iter, 0, 0, r, cig_store, max_cigar, lane, MGB_W));
 	}

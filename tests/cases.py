@@ -273,55 +273,45 @@ def case_wfa_divergent(lib, n_cases=24, seed=5):
         assert nc >= 0 and [buf[i] for i in range(nc)] == want and score.value == rst.s, (it, tl, ql, score.value, rst.s)
 
 
-def case_wfa_v2(lib, workdir, n_struct=60):
-    """the second version of the on-chip gap alignment ("wfa_v2", off by default; mgb_wfa2.cuh): slices that hold -inf
-    outside their range instead of bounds checks.  Same GAF for the golden cases (lr and asm presets, both on-chip tiers
-    busy), same mg_gchains_t fields as the reference on an SV graph, also with the learned tier routing of a second batch"""
+def case_wfa_tiers(lib, workdir, n_struct=60):
+    """the gap alignment tiers (mgb_wfa_tiers.cuh: slices that hold -inf outside their range instead of bounds checks).  Same GAF
+    for the golden cases (lr and asm presets, both on-chip tiers busy), same mg_gchains_t fields as the reference on an SV graph,
+    also with the learned tier routing of a second batch"""
     from minigraph_b200 import capi
+    for fn in (case_c2, case_c3, case_c4):
+        st = fn(lib, workdir)
+        prof = {n: st.prof[i] for i, n in enumerate(capi.PROF_NAMES)}
+        assert prof["wfa_fast_n"] > 500, prof
+        assert fn is case_c4 or prof["wfa_mid_n"] > 500, prof
+    if T.have_ref():
+        case_struct_random(lib, workdir, n_reads=n_struct, seed=37)
+        case_tier_routing(lib, workdir)
+        case_short_reads(lib, workdir, n_pairs=20)  # sr preset: tier 1 only, two-segment fragments
+        case_wfa_fallback(lib)  # tier 3 against miniwfa: scores far past 256 (band re-centring), capped runs, a gap beyond the 16-bit ring
+        case_wfa_divergent(lib)
+
+
+def case_gchain_labels(lib, workdir, n_reads=150, graph_len=1000000):
+    """graph chaining from the per-source label table (mgb_gclabel.cuh) on a graph dense enough that every read spans a dozen
+    segments: every field against the reference with the table on (sources searched once per batch by k_gc_labels), with the
+    table off (every read searches its own sources), lr and asm presets (walk bounds of 20 kb and 150 kb)"""
+    pre, reads = os.path.join(workdir, "svl"), os.path.join(workdir, "svl.reads.fa")
+    T.sim_graph(pre, graph_len, 8, 7)
+    T.sim_reads(pre + ".hap.fa", reads, n_reads, 15000, "ont", 5)
+    names, seqs = T.read_fasta(reads)
     try:
-        assert lib.mgb_set_param(b"wfa_v2", 1) == 0
-        for fn in (case_c2, case_c3, case_c4):
-            st = fn(lib, workdir)
-            prof = {n: st.prof[i] for i, n in enumerate(capi.PROF_NAMES)}
-            assert prof["wfa_fast_n"] > 500, prof
-            assert fn is case_c4 or prof["wfa_mid_n"] > 500, prof
-        if T.have_ref():
-            case_struct_random(lib, workdir, n_reads=n_struct, seed=37)
-            case_tier_routing(lib, workdir)
-            case_short_reads(lib, workdir, n_pairs=20)  # sr preset: tier 1 only, two-segment fragments
-            case_edge(lib, workdir)
-            case_wfa_fallback(lib)  # tier 3 against miniwfa: scores far past 256 (band re-centring), capped runs, a gap beyond the 16-bit ring
-            case_wfa_divergent(lib)
+        for preset, m in (("lr", n_reads), ("asm", n_reads // 3)):
+            want, _ = T.map_with_ref(pre + ".gfa", names[:m], seqs[:m], preset)
+            for cache in (1, 0):
+                assert lib.mgb_set_param(b"lab_cache", cache) == 0
+                got, _, st = T.map_with_engine(lib, pre + ".gfa", names[:m], seqs[:m], preset)
+                assert (st.n_lab_new > 100) == bool(cache), (preset, cache, st.n_lab_new)
+                assert sum(r["n_lc"] for r in got if r) > 5 * m  # the reads do span many segments
+                for i, (a, b) in enumerate(zip(want, got)):
+                    d = T.diff_results(a, b)
+                    assert d is None, "%s lab_cache=%d read %d: %s" % (preset, cache, i, d)
     finally:
-        lib.mgb_set_param(b"wfa_v2", capi.env_params().get("wfa_v2", 0))
-
-
-def case_seed_v2(lib, workdir):
-    """the sketch with its window rings in shared memory ("seed_v2", off by default): same minimizers, so the same GAF on
-    the golden cases (k=17/w=11 and k=19/w=10), on reads with N and tiny reads (which take the sequential path), on
-    multi-segment fragments and on the short-read preset"""
-    try:
-        assert lib.mgb_set_param(b"seed_v2", 1) == 0
-        for fn in (case_c1, case_c2, case_c3, case_c4, case_edge):
-            fn(lib, workdir)
-        if T.have_ref():
-            case_multi_segment(lib, workdir, n_frag=6)
-            case_short_reads(lib, workdir, n_pairs=20)
-    finally:
-        lib.mgb_set_param(b"seed_v2", capi.env_params().get("seed_v2", 0))
-
-
-def case_fin_v2(lib, workdir):
-    """CIGAR stitching by the whole warp ("fin_v2", off by default): the same operations, merged at the same item boundaries,
-    so the same cg:Z/ds:Z text on the golden cases and the same mg_gchains_t fields as the reference on an SV graph"""
-    try:
-        assert lib.mgb_set_param(b"fin_v2", 1) == 0
-        for fn in (case_c1, case_c2, case_c3, case_c4, case_edge):
-            fn(lib, workdir)
-        if T.have_ref():
-            case_struct_random(lib, workdir, n_reads=60, seed=41)
-    finally:
-        lib.mgb_set_param(b"fin_v2", capi.env_params().get("fin_v2", 0))
+        lib.mgb_set_param(b"lab_cache", 1)
 
 
 def case_chain_skip(lib, workdir, n_reads=40):
@@ -343,63 +333,13 @@ def case_chain_skip(lib, workdir, n_reads=40):
                 assert d is None, "%s max_lc_skip=%d read %d: %s" % (preset, skip, i, d)
 
 
-def case_chain_v2(lib, workdir, n_struct=80, n_skip_reads=40):
-    """ballot replay in the RMQ walk of the chaining stage ("chain_v2", off by default): the same chains -- asm preset (RMQ
-    chaining for every read), lr preset (RMQ rescue of the reads that span several segments), multi-segment fragments,
-    and the mg_gchains_t fields (anchors and linear chains included) against the reference on an SV graph"""
-    try:
-        assert lib.mgb_set_param(b"chain_v2", 1) == 0
-        for fn in (case_c1, case_c2, case_c3, case_c4):
-            fn(lib, workdir)
-        if T.have_ref():
-            case_struct_random(lib, workdir, n_reads=n_struct, seed=43)
-            case_multi_segment(lib, workdir, n_frag=6)
-            case_chain_skip(lib, workdir, n_reads=n_skip_reads)
-    finally:
-        lib.mgb_set_param(b"chain_v2", capi.env_params().get("chain_v2", 0))
-
-
-def case_gen_v2(lib, workdir):
-    """alignment plan and result copies of the materialisation stage on all lanes ("gen_v2", off by default): the same plan
-    items and gap jobs, so the same CIGARs -- golden cases, every field against the reference on an SV graph, fragments
-    without CIGAR (multi-segment), short reads, reads that do not map"""
-    try:
-        assert lib.mgb_set_param(b"gen_v2", 1) == 0
-        for fn in (case_c1, case_c2, case_c3, case_c4, case_edge):
-            fn(lib, workdir)
-        if T.have_ref():
-            case_struct_random(lib, workdir, n_reads=80, seed=53)
-            case_multi_segment(lib, workdir, n_frag=6)
-            case_short_reads(lib, workdir, n_pairs=20)
-    finally:
-        lib.mgb_set_param(b"gen_v2", capi.env_params().get("gen_v2", 0))
-
-
-def case_cta(lib, workdir, n_cases=12):
-    """the block-per-gap tier ("cta_len", off by default): gaps it takes come out the same -- through the job queue (golden
-    GAF of c3, every tier-3 gap taken by a block) and one gap at a time against miniwfa (scores past 256, so the band of
-    the ring is re-centred by block-wide votes; capped runs fall through to the warp path)"""
-    from minigraph_b200 import capi
-    try:
-        assert lib.mgb_set_param(b"cta_len", 64) == 0
-        st = case_c3(lib, workdir)
-        prof = {n: st.prof[i] for i, n in enumerate(capi.PROF_NAMES)}
-        assert prof["wfa_cta_n"] > 50 and prof["wfa_slow_n"] == 0, prof
-        lib.mgb_set_param(b"cta_taken", 0)
-        case_wfa_fallback(lib, n_cases=n_cases)
-        assert lib.mgb_set_param(b"cta_taken", 0) >= 3
-    finally:
-        lib.mgb_set_param(b"cta_len", capi.env_params().get("cta_len", 0))
-
-
 def case_switches(lib, workdir, device):
     """the engine's experiment switches change the schedule, never the result: the same golden GAF with each of them on"""
-    settings = [{b"big_len": 384}]  # long gaps to a tier-3 launch of their own
+    settings = [{b"lab_cache": 0}]  # graph chaining without the label table
     if device:
         settings += [{b"slots": 2, b"min_slot_reads": 8},          # two sub-batches on private streams
-                     {b"thread_mask": (1 << 2) | (1 << 9)},        # graph chaining stages: one read per thread
                      {b"sw8": 1, b"mb8": 16, b"sw7": 1, b"mb7": 16}]  # one-warp blocks for the tail-bound job kernels
-    defaults = {b"big_len": 0, b"slots": 1, b"min_slot_reads": 512, b"thread_mask": 0, b"sw8": 4, b"mb8": 4, b"sw7": 4, b"mb7": 4}
+    defaults = {b"lab_cache": 1, b"slots": 1, b"min_slot_reads": 512, b"sw8": 4, b"mb8": 4, b"sw7": 4, b"mb7": 4}
     for st in settings:
         try:
             for k, v in st.items():

@@ -81,34 +81,19 @@ def test_index_matches_oracle_sketch(lib):
     test_oracle.check_index(lib, orc)
 
 
-@pytest.mark.skipif(not os.environ.get("MGB_TEST_GEN_V2"), reason="warp-wide alignment plan is opt-in (MGB_TEST_GEN_V2=1): off by default in the engine")
-def test_gchain_gen_second_version(lib, workdir):
-    cases.case_gen_v2(lib, workdir)
 
 
-@pytest.mark.skipif(not os.environ.get("MGB_TEST_CHAIN_V2"), reason="ballot replay in the RMQ walk is opt-in (MGB_TEST_CHAIN_V2=1): off by default in the engine")
-def test_chain_second_version(lib, workdir):
-    cases.case_chain_v2(lib, workdir)
 
 
-@pytest.mark.skipif(not os.environ.get("MGB_TEST_FIN_V2"), reason="warp-wide CIGAR stitching is opt-in (MGB_TEST_FIN_V2=1): off by default in the engine")
-def test_finish_second_version(lib, workdir):
-    cases.case_fin_v2(lib, workdir)
 
 
-@pytest.mark.skipif(not os.environ.get("MGB_TEST_SEED_V2"), reason="the sketch with shared-memory rings is opt-in (MGB_TEST_SEED_V2=1): off by default in the engine")
-def test_seed_second_version(lib, workdir):
-    cases.case_seed_v2(lib, workdir)
+@pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not shipped")
+def test_graph_chaining_label_table(lib, workdir):
+    cases.case_gchain_labels(lib, workdir, n_reads=600, graph_len=2000000)
 
 
-@pytest.mark.skipif(not os.environ.get("MGB_TEST_WFA_V2"), reason="second version of the on-chip alignment is opt-in (MGB_TEST_WFA_V2=1): off by default in the engine")
-def test_wfa_second_version(lib, workdir):
-    cases.case_wfa_v2(lib, workdir, n_struct=150)
-
-
-@pytest.mark.skipif(not (T.have_ref() and os.environ.get("MGB_TEST_CTA")), reason="block-per-gap tier is opt-in (MGB_TEST_CTA=1): off by default in the engine")
-def test_block_per_gap_tier(lib, workdir):
-    cases.case_cta(lib, workdir, n_cases=10)
+def test_gap_alignment_tiers(lib, workdir):
+    cases.case_wfa_tiers(lib, workdir, n_struct=150)
 
 
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not shipped")

@@ -71,29 +71,8 @@ def test_no_diag_flag(lib, workdir):
     cases.case_no_diag(lib, workdir)
 
 
-def test_gchain_gen_second_version(lib, workdir):
-    cases.case_gen_v2(lib, workdir)
-
-
-def test_chain_second_version(lib, workdir):
-    cases.case_chain_v2(lib, workdir, n_struct=40, n_skip_reads=12)
-
-
-def test_finish_second_version(lib, workdir):
-    cases.case_fin_v2(lib, workdir)
-
-
-def test_seed_second_version(lib, workdir):
-    cases.case_seed_v2(lib, workdir)
-
-
-def test_wfa_second_version(lib, workdir):
-    cases.case_wfa_v2(lib, workdir)
-
-
-def test_block_per_gap_tier(lib, workdir):
-    """the block-uniform code with 128 simulated threads: block-wide votes, barriers and broadcasts really exchanged"""
-    cases.case_cta(lib, workdir)
+def test_graph_chaining_label_table(lib, workdir):
+    cases.case_gchain_labels(lib, workdir, n_reads=45, graph_len=600000)
 
 
 def test_wfa_tiers_and_fallback(lib):

@@ -66,6 +66,15 @@ def test_struct_fields_vs_reference(lib, workdir):
 
 
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
+def test_graph_chaining_label_table(lib, workdir):
+    cases.case_gchain_labels(lib, workdir, n_reads=150)
+
+
+def test_gap_alignment_tiers(lib, workdir):
+    cases.case_wfa_tiers(lib, workdir)
+
+
+@pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
 def test_wfa_iteration_cap_fallback(lib):
     cases.case_wfa_fallback(lib)
     cases.case_wfa_divergent(lib)
@@ -77,29 +86,10 @@ def test_full_size_properties_small(lib, workdir):
     cases.case_full_size(lib, workdir, n_reads=120, n_sub=40, n_ref=20)
 
 
-@pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
-def test_gchain_gen_second_version(lib, workdir):
-    cases.case_gen_v2(lib, workdir)
 
 
-def test_chain_second_version(lib, workdir):
-    cases.case_chain_v2(lib, workdir)
 
 
-def test_finish_second_version(lib, workdir):
-    cases.case_fin_v2(lib, workdir)
-
-
-def test_seed_second_version(lib, workdir):
-    cases.case_seed_v2(lib, workdir)
-
-
-def test_wfa_second_version(lib, workdir):
-    cases.case_wfa_v2(lib, workdir)
-
-
-def test_block_per_gap_tier(lib, workdir):
-    cases.case_cta(lib, workdir)
 
 
 def test_gaf_batch_writer_reuses_buffer(lib, workdir):
