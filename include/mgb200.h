@@ -233,6 +233,7 @@ typedef struct {
 	uint64_t prof[32];      /* device cycle counters per phase (see mgb_pipeline.cuh PROF_*) */
 	double t_lab_ms;        /* k_gc_labels: reachability labels of source vertices seen for the first time (0 once the table is warm) */
 	int64_t n_lab_new;      /* such sources in this batch */
+	int64_t n_lab_big;      /* ... of which needed the second, warp-per-source pass */
 } mgb_stats_t;
 
 /* test hook: align one gap through the tier-3 WFA path (exact up to max_iter cells, then the reference's chaining

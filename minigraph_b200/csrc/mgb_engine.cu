@@ -14,6 +14,7 @@
 #include <chrono>
 #include <thread>
 #include <mutex>
+#include <condition_variable>
 #include <functional>
 #include <unordered_map>
 #include "mgb_hostpool.h"
@@ -41,14 +42,14 @@ static int64_t p_device = 0;
 static int64_t p_block_warps = 4;
 static int64_t p_host_threads = 0; // 0: min(16, hardware threads)
 static int64_t p_thread_mask = 0;      // bit s set: stage s runs one item per thread instead of one per warp (experiments)
-extern int p_slots; extern int64_t p_min_slot_reads;
+static int64_t p_slots = 3;            // mg_map_batch calls that may run at once on one index (each on its own slot: stream, buffers, arenas)
 static int64_t p_slot_workers = 0;
 static int64_t p_tier_learn = 1;       // 0: every gap tries every tier (no routing)
 static int64_t p_lab_cache = 1;        // 0: graph chaining searches its walks per read instead of keeping per-source labels in HBM (mgb_gclabel.cuh)
 
 // launch shape per stage: warps per block and blocks per SM wanted (tunable for experiments: "sw<stage>", "mb<stage>")
-static int STAGE_MINB[18] = { 8, 8, 8, 8, 5, 8, 7, 4, 4, 4, 0, 0, 0, 0, 0, 0, 0, 8 }; // indexed by stage number (10-16 unused)
-static int STAGE_WARPS[18] = { 4, 4, 4, 4, 4, 4, 2, 4, 4, 4, 0, 0, 0, 0, 0, 0, 0, 4 };
+static int STAGE_MINB[19] = { 8, 8, 8, 8, 5, 8, 7, 4, 4, 4, 0, 0, 0, 0, 0, 0, 0, 8, 8 }; // indexed by stage number (10-16 unused)
+static int STAGE_WARPS[19] = { 4, 4, 4, 4, 4, 4, 2, 4, 4, 4, 0, 0, 0, 0, 0, 0, 0, 4, 4 };
 extern "C" const char *mgb_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char *mgb_version(void) { return "mgb200-r1"; }
 extern "C" int mgb_set_param(const char *key, int64_t value)
@@ -60,11 +61,10 @@ extern "C" int mgb_set_param(const char *key, int64_t value)
 	else if (!strcmp(key, "block_warps")) p_block_warps = value;
 	else if (!strcmp(key, "host_threads")) p_host_threads = value;
 	else if (!strcmp(key, "thread_mask")) p_thread_mask = value;
-	else if (!strcmp(key, "slots")) p_slots = (int)value;
+	else if (!strcmp(key, "slots")) p_slots = value;
 	else if (!strcmp(key, "slot_workers")) p_slot_workers = value;
 	else if (!strcmp(key, "lab_cache")) p_lab_cache = value;
 	else if (!strcmp(key, "tier_learn")) p_tier_learn = value;
-	else if (!strcmp(key, "min_slot_reads")) p_min_slot_reads = value;
 	else if (!strncmp(key, "sw", 2) && key[2] >= '0' && key[2] <= '9' && !key[3] && value >= 1 && value <= 4) STAGE_WARPS[key[2] - '0'] = (int)value;
 	else if (!strncmp(key, "mb", 2) && key[2] >= '0' && key[2] <= '9' && !key[3] && value >= 1 && value <= 32) STAGE_MINB[key[2] - '0'] = (int)value;
 	else return -1;
@@ -188,7 +188,8 @@ MG_HD inline int run_stage(const LaunchArgs &L, int item, Arena &A, int lane, in
 	if (STAGE == 0) return stage_seed(L.c, item, A, lane, smem);
 	if (STAGE == 1) return stage_chain(L.c, item, A, lane, smem);
 	if (STAGE == 2) return stage_gchain(L.c, L.routs, item, A, lane);
-	if (STAGE == 17) return label_job(A, L.c.g, L.c.lab, item);
+	if (STAGE == 17) return label_job(A, L.c.g, L.c.lab, item, 0);
+	if (STAGE == 18) return label_job(A, L.c.g, L.c.lab, item, 1); // lane 0 with the whole arena of its warp
 	if (STAGE == 5) return stage_finish(L.c, L.routs, item, A, lane);
 	if (STAGE == 8) return gwfa_job_run(A, L.c, L.job_start + item, lane, smem);
 	if (STAGE == 9) return stage_gchain_gen(L.c, L.routs, item, A, lane);
@@ -214,7 +215,7 @@ MG_HD inline int run_stage(const LaunchArgs &L, int item, Arena &A, int lane, in
 template<int STAGE>
 MG_HD inline void stage_fail(const LaunchArgs &L, int item, int rc)
 {
-	if (STAGE == 17) return; // a source that could not be finished is searched again by the read that needs it
+	if (STAGE == 17 || STAGE == 18) return; // a source that could not be finished is searched again by the read that needs it
 	if (STAGE == 3) {
 #if MGB_ON_DEVICE
 		atomicMin((int*)L.routs, rc);
@@ -241,11 +242,12 @@ __device__ __forceinline__ void stage_loop(const LaunchArgs &L)
 	extern __shared__ int4 dyn_smem[];
 	const int smem_stride = STAGE == 4? WfTier1::STRIDE : STAGE == 6? WfTier2::STRIDE : STAGE == 0? SKETCH_SMEM_BYTES : STAGE == 8? GWFA_SMEM_ARENA : 0;
 	int32_t *smem = smem_stride? (int32_t*)((char*)dyn_smem + (size_t)(threadIdx.x >> 5) * smem_stride) : 0;
+	const int n_work = L.n_work_dev? (int)*L.n_work_dev : L.n_work;
 	for (;;) {
 		int item = 0;
 		if (lane == 0) item = (int)atomicAdd(L.c.next_read, 1u);
 		item = __shfl_sync(0xffffffffu, item, 0);
-		if (item >= L.n_work) break;
+		if (item >= n_work) break;
 		if (L.rid_list) item = L.rid_list[item];
 		if (MGB_IS_WARP(STAGE)) {
 			A.top = 0;
@@ -297,6 +299,7 @@ MGB_KERNEL(k_wfa_mid, 6, 5)       // K8a tier 2: mid-size gaps, wavefronts in sh
 MGB_KERNEL(k_wfa_big, 7, 4)       // K8a tier 3: anything else, wavefronts in the worker arena
 MGB_KERNEL(k_finish, 5, 8)        // K8b: CIGAR stitching, ds strings, result blobs
 MGB_KERNEL(k_gc_labels, 17, 8)    // reachability labels of new source vertices, one search per thread (mgb_gclabel.cuh)
+MGB_KERNEL(k_gc_labels_big, 18, 8) // the few sources whose search outgrew a thread's share of the arena: one per warp
 template<int STAGE> struct StageKernel;
 template<> struct StageKernel<0> { static void (*get())(LaunchArgs) { return k_seed; } };
 template<> struct StageKernel<1> { static void (*get())(LaunchArgs) { return k_chain; } };
@@ -309,6 +312,7 @@ template<> struct StageKernel<8> { static void (*get())(LaunchArgs) { return k_g
 template<> struct StageKernel<9> { static void (*get())(LaunchArgs) { return k_gchain_gen; } };
 template<> struct StageKernel<5> { static void (*get())(LaunchArgs) { return k_finish; } };
 template<> struct StageKernel<17> { static void (*get())(LaunchArgs) { return k_gc_labels; } };
+template<> struct StageKernel<18> { static void (*get())(LaunchArgs) { return k_gc_labels_big; } };
 #endif
 
 // Longest-first order of a job list (a tail of a few long jobs otherwise decides the kernel time).  Jobs are binned by
@@ -435,7 +439,7 @@ static void launch_stage(LaunchArgs &L, const Workers &W, int warps_override = 0
 	dzero(L.c.next_read, sizeof(unsigned int)); // in stream order: no host round trip per launch
 #ifdef MGB_HOSTSIM
 	Arena A;
-	arena_init(A, W.arena, W.arena_bytes);
+	arena_init(A, W.arena, STAGE == 17? (W.arena_bytes / 32) & ~(uint64_t)15 : W.arena_bytes); // one item per thread: a thread's share, as on the device
 	std::vector<int32_t> sim_smem(std::max<size_t>(std::max<size_t>(WfTier1::STRIDE, WfTier2::STRIDE), std::max<size_t>(std::max<size_t>(GWFA_SMEM_ARENA, CHAIN_SMEM), SKETCH_SMEM_BYTES)) / 4);
 	const int n_work_sim = L.n_work_dev? (int)*L.n_work_dev : L.n_work;
 	for (int it = 0; it < n_work_sim; ++it) {
@@ -510,7 +514,8 @@ struct Model {
 	// the batch pipeline: a batch is cut into sub-batches, each driven by its own host thread on its own stream ("slot"),
 	// so that kernels, copies and host-side result assembly of different sub-batches overlap
 	struct Slot {
-		GrowBuf h_seq{true}, h_out{true}, h_small{true}, d_seq, d_meta, d_routs, d_small, d_jobq, d_order, d_packed, d_packoff, d_segs, d_pool[10];
+		GrowBuf h_seq{true}, h_out{true}, h_small{true}, d_seq, d_meta, d_routs, d_small, d_jobq, d_order, d_packed, d_packoff, d_segs, d_lab_new, d_pool[10];
+		mgb::HostPool host_pool; // packing and result assembly of the batch on this slot
 		Workers W;
 		mgb_stats_t st;
 		double ev_first_ms, ev_last_ms; // first kernel start / last kernel end relative to the batch reference event
@@ -523,9 +528,12 @@ struct Model {
 	};
 	enum { MAX_SLOTS = 8 };
 	Slot slots[MAX_SLOTS];
-	std::mutex big_mutex; // the large-arena retry pass is shared by the slots
+	std::mutex big_mutex; // the large-arena retry pass, the label table and the learned routing are shared by the slots
+	std::condition_variable slot_cv;
+	bool slot_busy[MAX_SLOTS] = {};
+	int in_flight = 0;    // calls inside map_batch_impl
 	// reachability labels of the graph (mgb_gclabel.cuh): built on demand, kept across batches, grown between them
-	long long *d_lab_off = 0; int32_t *d_lab_new = 0; unsigned int *d_lab_n = 0; Pool *d_lab_hdr = 0; char *d_lab_pool = 0;
+	long long *d_lab_off = 0; Pool *d_lab_hdr = 0; char *d_lab_pool = 0;
 	uint64_t lab_cap = 0; int32_t lab_max_dist_g = -1; int64_t lab_sources = 0;
 };
 
@@ -537,10 +545,10 @@ static void model_free(Model *M)
 	if (M->Wbig.arena) dfree(M->Wbig.arena);
 	if (M->Wbig.peak) dfree(M->Wbig.peak);
 	if (M->d_logf) dfree(M->d_logf);
-	dfree(M->d_lab_off), dfree(M->d_lab_new), dfree(M->d_lab_n), dfree(M->d_lab_hdr), dfree(M->d_lab_pool);
+	dfree(M->d_lab_off), dfree(M->d_lab_hdr), dfree(M->d_lab_pool);
 	for (int k = 0; k < Model::MAX_SLOTS; ++k) {
 		Model::Slot &sl = M->slots[k];
-		sl.h_seq.release(), sl.h_out.release(), sl.h_small.release(), sl.d_seq.release(), sl.d_meta.release(), sl.d_routs.release(), sl.d_small.release(), sl.d_jobq.release(), sl.d_order.release(), sl.d_packed.release(), sl.d_packoff.release(), sl.d_segs.release();
+		sl.h_seq.release(), sl.h_out.release(), sl.h_small.release(), sl.d_seq.release(), sl.d_meta.release(), sl.d_routs.release(), sl.d_small.release(), sl.d_jobq.release(), sl.d_order.release(), sl.d_packed.release(), sl.d_packoff.release(), sl.d_segs.release(), sl.d_lab_new.release();
 		for (int i = 0; i < 10; ++i) sl.d_pool[i].release();
 		if (sl.W.arena) dfree(sl.W.arena);
 		if (sl.W.peak) dfree(sl.W.peak);
@@ -673,6 +681,9 @@ static Model *model_build(gfa_t *g, int k, int w)
 			if (!retry) break;
 		}
 	}
+	// the sketch arenas are not needed again (every mapping slot owns its arenas)
+	dfree(M->W.arena), dfree(M->W.peak);
+	memset(&M->W, 0, sizeof(Workers));
 	// group by minimizer; occurrence lists ascending (reference: index.c:115-165 mg_idx_a2h)
 	std::sort(mz.begin(), mz.end(), [](const u128 &a, const u128 &b) { return (a.x >> 8) != (b.x >> 8)? (a.x >> 8) < (b.x >> 8) : a.y < b.y; });
 	size_t n_keys = 0;
@@ -878,29 +889,28 @@ static mg_gchains_t *build_result(const ReadOut &ro, const char *pool)
 	return gs;
 }
 
-int p_slots = 1;              // sub-batches in flight per batch (measured on B200: the kernels already fill the chip, overlap buys nothing)
-int64_t p_min_slot_reads = 512; // do not cut batches into pieces smaller than this
 
 // The label table of graph chaining: allocated at the first batch, emptied when a batch asks for longer walks than it was built for.
-static void lab_prepare(Model *M, int32_t max_dist_g)
+static bool lab_prepare(Model *M, int32_t max_dist_g)
 {
 	std::lock_guard<std::mutex> lock(M->big_mutex);
 	const size_t n_vtx = (size_t)M->g.n_seg * 2;
 	if (M->d_lab_off == 0) {
 		M->d_lab_off = (long long*)dmalloc(n_vtx * sizeof(long long));
-		M->d_lab_new = (int32_t*)dmalloc(n_vtx * sizeof(int32_t));
-		M->d_lab_n = (unsigned int*)dmalloc(sizeof(unsigned int));
 		M->d_lab_hdr = (Pool*)dmalloc(sizeof(Pool));
 		M->lab_cap = std::max<uint64_t>((uint64_t)64 << 20, (uint64_t)n_vtx * 4096);
 		M->d_lab_pool = (char*)dmalloc(M->lab_cap);
 		M->lab_max_dist_g = -1;
 	}
 	if (M->lab_max_dist_g < max_dist_g) { // labels are exact for every bound up to the one they were searched with
+		if (M->in_flight > 1) return false; // another call is reading the table: this one searches per read
 		dfill(M->d_lab_off, 0xff, n_vtx * sizeof(long long));
 		Pool hp; hp.used = 0, hp.cap = M->lab_cap;
 		h2d(M->d_lab_hdr, &hp, sizeof(Pool));
 		M->lab_max_dist_g = max_dist_g;
+		dsync();
 	}
+	return true;
 }
 // after a batch: a label pool that overflowed is enlarged for the batches to come (the sources that did not fit were searched per read)
 static void lab_after_batch(Model *M, unsigned int n_new)
@@ -909,7 +919,7 @@ static void lab_after_batch(Model *M, unsigned int n_new)
 	M->lab_sources += n_new;
 	Pool hp;
 	d2h(&hp, M->d_lab_hdr, sizeof(Pool));
-	if (hp.used <= hp.cap) return;
+	if (hp.used <= hp.cap || M->in_flight > 1) return; // kernels of another call may be reading the pool: grow after a later batch
 	const uint64_t want = std::max<uint64_t>((uint64_t)hp.used * 2, M->lab_cap * 2);
 	if (want > dev_free_mem() / 2) return;
 	char *np = (char*)dmalloc(want);
@@ -950,8 +960,8 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	const size_t hseq_bytes = tot + 16;
 	char *hseq = (char*)sl.h_seq.ensure(hseq_bytes);
 	auto pfor = [&](int64_t n, const std::function<void(int64_t)> &fn) {
-		if (n < 256 || host_threads <= 1 || p_slots > 1) { for (int64_t i = 0; i < n; ++i) fn(i); return; } // sub-batch threads do not share the pool
-		g_host_pool.run(n, host_threads, fn);
+		if (n < 256 || host_threads <= 1) { for (int64_t i = 0; i < n; ++i) fn(i); return; }
+		sl.host_pool.run(n, host_threads, fn);
 	};
 	EvTimer tm_h2d, tm_seed, tm_chain, tm_align, tm_wfa, tm_fin, tm_d2h;
 	EvTimer tm_k[10], tm_lab; // one per kernel (first pass only)
@@ -1033,8 +1043,9 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	bool first_kernel = true;
 	(void)first_kernel;
 
-	const bool use_lab = p_lab_cache && p_slots <= 1; // one table per model: sub-batches on private streams would race on its work list
-	if (use_lab) lab_prepare(M, o.bw_long);
+	const bool use_lab = p_lab_cache && lab_prepare(M, o.bw_long);
+	int32_t *d_lab_new = 0; unsigned int *d_lab_n = 0; // this call's list of sources to search
+	if (use_lab) { d_lab_n = (unsigned int*)sl.d_lab_new.ensure(((size_t)M->g.n_seg * 2 + 4) * sizeof(int32_t)); d_lab_new = (int32_t*)(d_lab_n + 4); }
 	for (int attempt = 0; attempt < 8; ++attempt) {
 		void *d_buf[N_POOLS];
 		Pool hp[N_POOLS];
@@ -1060,9 +1071,9 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 		L.c.next_read = d_next;
 		memset(&L.c.lab, 0, sizeof(L.c.lab));
 		if (use_lab) {
-			L.c.lab.src_off = M->d_lab_off, L.c.lab.pool_hdr = M->d_lab_hdr, L.c.lab.pool = M->d_lab_pool, L.c.lab.new_src = M->d_lab_new, L.c.lab.n_new = M->d_lab_n;
-			L.c.lab.max_dist_g = M->lab_max_dist_g;
-			dzero(M->d_lab_n, sizeof(unsigned int));
+			L.c.lab.src_off = M->d_lab_off, L.c.lab.pool_hdr = M->d_lab_hdr, L.c.lab.pool = M->d_lab_pool, L.c.lab.new_src = d_lab_new, L.c.lab.n_new = d_lab_n;
+			L.c.lab.max_dist_g = M->lab_max_dist_g, L.c.lab.cap_new = M->g.n_seg * 2;
+			dzero(d_lab_n, 2 * sizeof(unsigned int));
 		}
 		L.c.prof = d_prof;
 		L.c.tier_hist = d_tier_hist, L.c.skip1_len = L_skip1, L.c.skip2_len = L_skip2;
@@ -1081,12 +1092,14 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 			{ if (timed) tm_k[1].start(); launch_stage<1>(L, W); if (timed) tm_k[1].stop(); }
 			if (timed) tm_chain.stop(), tm_align.start();
 			if (use_lab) { // labels of the sources k_chain listed (count known on the device only)
-				L.n_work_dev = M->d_lab_n, L.rid_list = 0;
+				L.n_work_dev = d_lab_n, L.rid_list = 0;
 				if (timed) tm_lab.start();
 				launch_stage<17>(L, W);
+				L.n_work_dev = d_lab_n + 1;
+				launch_stage<18>(L, W);
 				if (timed) tm_lab.stop();
 				L.n_work_dev = 0, L.rid_list = d_list;
-				S.n_launches += 1;
+				S.n_launches += 2;
 			}
 			if (d_list == 0 && n_list >= 1024) { // whole batch: reads with many linear chains first (a few of them set the time of this kernel)
 				int32_t *order = (int32_t*)sl.d_order.ensure(sizeof(int32_t) * (size_t)n_list);
@@ -1174,7 +1187,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 		if (!pool_full && !redo.empty()) {
 			std::lock_guard<std::mutex> lock(M->big_mutex);
 			uint64_t big = (uint64_t)p_arena_big_mb << 20;
-			int nw = (int)std::min<uint64_t>((uint64_t)sl.W.n_workers, std::max<uint64_t>(1, dev_free_mem() * 3 / 4 / big));
+			int nw = (int)std::min<uint64_t>(16, std::max<uint64_t>(1, dev_free_mem() / 2 / big)); // a handful of reads per batch at most come here
 			if (M->Wbig.arena == 0 || M->Wbig.arena_bytes != big) ensure_workers(M->Wbig, std::max(1, nw), big);
 			h2d(d_list_buf, redo.data(), redo.size() * sizeof(int32_t));
 			run_pass(d_list_buf, (int32_t)redo.size(), M->Wbig, false);
@@ -1187,7 +1200,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 			}
 		}
 		d2h(hp, d_pools, sizeof(hp));
-		if (use_lab) { unsigned int nn = 0; d2h(&nn, M->d_lab_n, sizeof(nn)); S.n_lab_new = (int64_t)nn; lab_after_batch(M, nn); }
+		if (use_lab) { unsigned int nn[2] = {0, 0}; d2h(nn, d_lab_n, sizeof(nn)); S.n_lab_new = (int64_t)nn[0], S.n_lab_big = (int64_t)nn[1]; lab_after_batch(M, nn[0]); }
 		bool done = !pool_full;
 		if (done) { // blobs into read order, then to the host in pieces (the assembly below follows piece by piece)
 			tm_d2h.start();
@@ -1293,114 +1306,79 @@ static void slot_prepare(Model *M, Model::Slot &sl, int n_workers)
 	(void)M;
 }
 
+static thread_local mgb_stats_t t_last_stats; // of the last batch mapped by the calling thread
+static thread_local bool t_has_stats = false;
+
+// One call = one slot: its own stream, staging buffers, pools and worker arenas.  Up to "slots" calls run at once on one index
+// (callers beyond that wait), so a host that maps mini-batch i+1 on a second thread overlaps its packing, copies and result
+// assembly with the kernels of mini-batch i -- what the reference's kt_pipeline does with its step threads (gmap.c:176).
 static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, const char *const *seqs, const char *const *names,
 						  mg_gchains_t **gcs, const mg_mapopt_t *opt, const std::vector<int32_t> *seg_off = 0, const std::vector<int32_t> *seg_len = 0)
 {
 	Model *M = (Model*)gi->B;
-	mgb_stats_t &S = M->stats;
-	memset(&S, 0, sizeof(S));
 	for (int i = 0; i < n_reads; ++i) gcs[i] = 0;
 	if (n_reads <= 0) return 0;
 	double t0 = now_ms();
 	int32_t max_qlen = 0;
-	int64_t tot_bases = 0;
-	for (int i = 0; i < n_reads; ++i) { if (qlens[i] > max_qlen) max_qlen = qlens[i]; tot_bases += qlens[i] > 0? qlens[i] : 0; }
-	{ // glibc logf table for mapq (reference: gcmisc.c:216-217)
-		int need = std::max(1 << 16, max_qlen + 4096);
-		if (M->n_logf < need) {
-			M->logf_tab.resize(need);
-			for (int i = 0; i < need; ++i) M->logf_tab[i] = logf((float)i);
-			if (M->d_logf) dfree(M->d_logf);
-			M->d_logf = dalloc_copy(M->logf_tab);
-			M->n_logf = need;
-		}
+	for (int i = 0; i < n_reads; ++i) if (qlens[i] > max_qlen) max_qlen = qlens[i];
+	int k = -1;
+	{ // take a slot
+		std::unique_lock<std::mutex> lk(M->big_mutex);
+		const int max_slots = (int)std::max<int64_t>(1, std::min<int64_t>(p_slots, Model::MAX_SLOTS));
+		M->slot_cv.wait(lk, [&]() { for (int i = 0; i < max_slots; ++i) if (!M->slot_busy[i]) return true; return false; });
+		for (int i = 0; i < max_slots && k < 0; ++i) if (!M->slot_busy[i]) k = i;
+		M->slot_busy[k] = true, ++M->in_flight;
 	}
-	MapOptDev o;
-	fill_opt(o, opt, M->k);
-	o.logf_tab = M->d_logf, o.n_logf_tab = M->n_logf;
-	// ---- cut the batch into sub-batches of similar size (by bases), contiguous in input order ----
-#ifdef MGB_HOSTSIM
-	int n_slots = 1;
-#else
-	int n_slots = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(p_slots, Model::MAX_SLOTS), n_reads / std::max<int64_t>(1, p_min_slot_reads)));
-	if (seg_off) n_slots = 1; // the segment table indexes the reads of the whole batch
+	Model::Slot &sl = M->slots[k];
+#ifndef MGB_HOSTSIM
+	cudaSetDevice((int)p_device);
 #endif
-	std::vector<int> bound(n_slots + 1, n_reads);
-	bound[0] = 0;
+	int rc = 0;
 	{
-		int64_t acc = 0; int k = 1;
-		for (int i = 0; i < n_reads && k < n_slots; ++i) {
-			acc += qlens[i] > 0? qlens[i] : 0;
-			if (acc >= tot_bases * k / n_slots) bound[k++] = i + 1;
+		slot_prepare(M, sl, p_slot_workers > 0? (int)p_slot_workers : default_workers());
+#ifndef MGB_HOSTSIM
+		t_stream = sl.stream;
+#endif
+		MapOptDev o;
+		fill_opt(o, opt, M->k);
+		{ // glibc logf table for mapq (reference: gcmisc.c:216-217); grown under the lock, old copies are kept until the model dies
+			std::lock_guard<std::mutex> lk(M->big_mutex);
+			int need = std::max(1 << 16, max_qlen + 4096);
+			if (M->n_logf < need) {
+				M->logf_tab.resize(need);
+				for (int i = 0; i < need; ++i) M->logf_tab[i] = logf((float)i);
+				if (M->d_logf) M->dev_ptrs.push_back(M->d_logf); // a call in flight may still read it
+				M->d_logf = dalloc_copy(M->logf_tab);
+				M->n_logf = need;
+			}
+			o.logf_tab = M->d_logf, o.n_logf_tab = M->n_logf;
 		}
-	}
-	int nt_all = (int)p_host_threads;
-	if (nt_all <= 0) { nt_all = (int)std::thread::hardware_concurrency(); if (nt_all > 16) nt_all = 16; if (nt_all < 1) nt_all = 1; }
-	const int nt_slot = std::max(1, nt_all / n_slots);
-	// a sub-batch gets enough workers to cover half the chip: two kernels of different sub-batches fill it, more queue behind
-	const int n_workers = p_slot_workers > 0? (int)p_slot_workers : std::min(default_workers(), std::max(128, default_workers() * 2 / n_slots));
-	for (int k = 0; k < n_slots; ++k) slot_prepare(M, M->slots[k], n_workers);
-	std::vector<int> rcs(n_slots, 0);
-#ifndef MGB_HOSTSIM
-	cudaEvent_t ev_ref;
-	CUDA_OK(cudaEventCreate(&ev_ref));
-	CUDA_OK(cudaEventRecord(ev_ref, M->slots[0].stream));
-#endif
-	auto work = [&](int k) {
-#ifndef MGB_HOSTSIM
-		cudaSetDevice((int)p_device);
-		t_stream = M->slots[k].stream;
-#endif
-		int b = bound[k], e = bound[k + 1];
-		rcs[k] = map_range(M, M->slots[k], o, e - b, qlens + b, seqs + b, names? names + b : 0, gcs + b, nt_slot, seg_off, seg_len);
-	};
-	if (n_slots == 1) {
-		work(0);
+		int nt = (int)p_host_threads;
+		if (nt <= 0) { nt = (int)std::thread::hardware_concurrency(); if (nt > 16) nt = 16; if (nt < 1) nt = 1; }
+		rc = map_range(M, sl, o, n_reads, qlens, seqs, names, gcs, nt, seg_off, seg_len);
 #ifndef MGB_HOSTSIM
 		t_stream = 0; // the slot's stream dies with the model; later calls on this thread (mg_index of another graph) use the default one
 #endif
 	}
-	else {
-		std::vector<std::thread> th;
-		for (int k = 0; k < n_slots; ++k) th.emplace_back(work, k);
-		for (auto &x : th) x.join();
+	mgb_stats_t S = sl.st;
+#ifndef MGB_HOSTSIM
+	if (rc == 0) { float a = 0; if (cudaEventElapsedTime(&a, sl.ev_first, sl.ev_last) == cudaSuccess) S.t_dev_span_ms = a; }
+#else
+	S.t_dev_span_ms = S.t_seed_ms + S.t_chain_ms + S.t_align_ms + S.t_wfa_ms + S.t_finish_ms;
+#endif
+	S.n_slots = k;
+	S.t_host_ms = now_ms() - t0;
+	t_last_stats = S, t_has_stats = true;
+	{
+		std::lock_guard<std::mutex> lk(M->big_mutex);
+		M->stats = S;
+		M->slot_busy[k] = false, --M->in_flight;
 	}
-	int rc = 0;
-	for (int k = 0; k < n_slots; ++k) if (rcs[k] < 0 && rc == 0) rc = rcs[k];
+	M->slot_cv.notify_one();
 	if (rc < 0) { // no partial results are left behind
 		for (int i = 0; i < n_reads; ++i) if (gcs[i]) { mg_gchain_free(gcs[i]); gcs[i] = 0; }
 		return rc;
 	}
-	// ---- merge the statistics of the slots ----
-	double first = 1e30, last = 0;
-	(void)first, (void)last;
-	for (int k = 0; k < n_slots; ++k) {
-		const mgb_stats_t &T = M->slots[k].st;
-		if (bound[k + 1] == bound[k]) continue;
-		S.t_h2d_ms += T.t_h2d_ms, S.t_seed_ms += T.t_seed_ms, S.t_chain_ms += T.t_chain_ms, S.t_align_ms += T.t_align_ms, S.t_d2h_ms += T.t_d2h_ms;
-		S.t_wfa_ms += T.t_wfa_ms, S.t_finish_ms += T.t_finish_ms, S.t_pack_ms += T.t_pack_ms, S.t_asm_ms += T.t_asm_ms;
-		for (int i = 0; i < 10; ++i) S.t_kernel_ms[i] += T.t_kernel_ms[i];
-		S.n_jobs += T.n_jobs, S.n_jobs_mid += T.n_jobs_mid, S.n_jobs_big += T.n_jobs_big, S.n_jobs_side += T.n_jobs_side, S.skip1_len = T.skip1_len, S.skip2_len = T.skip2_len, S.n_reads += T.n_reads, S.n_bases += T.n_bases;
-		S.n_seeds += T.n_seeds, S.n_anchors_out += T.n_anchors_out, S.n_chains_out += T.n_chains_out, S.n_minimizers += T.n_minimizers;
-		S.out_bytes += T.out_bytes, S.n_launches += T.n_launches, S.n_retry += T.n_retry, S.n_lab_new += T.n_lab_new, S.t_lab_ms += T.t_lab_ms;
-		if (T.arena_peak > S.arena_peak) S.arena_peak = T.arena_peak;
-		for (int i = 0; i < 32; ++i) { if (i == PROF_WFA_MAX_CYC || i == PROF_GWFA_MAX_CYC || i == PROF_GC_DP_MAX_CYC) { if (T.prof[i] > S.prof[i]) S.prof[i] = T.prof[i]; } else S.prof[i] += T.prof[i]; }
-#ifndef MGB_HOSTSIM
-		float a = 0, b = 0;
-		cudaEventElapsedTime(&a, ev_ref, M->slots[k].ev_first);
-		cudaEventElapsedTime(&b, ev_ref, M->slots[k].ev_last);
-		if (a < first) first = a;
-		if (b > last) last = b;
-#endif
-	}
-#ifndef MGB_HOSTSIM
-	cudaEventDestroy(ev_ref);
-	S.t_dev_span_ms = last > first? last - first : 0;
-#else
-	S.t_dev_span_ms = S.t_seed_ms + S.t_chain_ms + S.t_align_ms + S.t_wfa_ms + S.t_finish_ms;
-#endif
-	S.n_slots = n_slots;
-	S.t_host_ms = now_ms() - t0;
 	return 0;
 }
 
@@ -1525,4 +1503,4 @@ extern "C" int mgb_test_wfa(const char *ts, int tl, const char *qs, int ql, int6
 	return out[0] < 0? out[0] : out[1];
 }
 
-extern "C" void mgb_get_stats(const mg_idx_t *gi, mgb_stats_t *st) { *st = model_of(gi)->stats; }
+extern "C" void mgb_get_stats(const mg_idx_t *gi, mgb_stats_t *st) { *st = t_has_stats? t_last_stats : model_of(gi)->stats; } // the calling thread's last batch

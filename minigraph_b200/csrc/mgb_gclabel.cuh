@@ -30,7 +30,8 @@ struct LabTab {
 	Pool *pool_hdr;
 	char *pool;
 	int32_t *new_src;       // sources wanted for the first time by the batch in flight
-	unsigned int *n_new;
+	unsigned int *n_new;    // n_new[0]: their number; n_new[1]: how many of them outgrew a thread's share of the arena (listed from the top of new_src[])
+	int32_t cap_new;        // entries of new_src[]
 	int32_t max_dist_g;     // the bound the table was built for
 };
 
@@ -289,14 +290,25 @@ MG_HD inline int label_search(Arena &A, const GraphDev &g, uint32_t src, int32_t
 // One item of the label kernel: search a source this batch asked for and publish its record.  One lane.
 // A source that cannot be finished here (arena or label pool too small) goes back to LAB_NONE: graph chaining then searches it
 // on the spot, and the host grows the pool between batches.
-MG_HD inline int label_job(Arena &A, const GraphDev &g, const LabTab &T, int item)
+MG_HD inline int label_job(Arena &A, const GraphDev &g, const LabTab &T, int item, int second_pass)
 {
-	const uint32_t v = (uint32_t)T.new_src[item];
+	const uint32_t v = (uint32_t)T.new_src[second_pass? T.cap_new - 1 - item : item];
 	if (T.src_off[v] >= 0) return 0;
 	const uint64_t mark = A.top;
 	char *rec;
 	uint64_t bytes;
 	int rc = label_search(A, g, v, T.max_dist_g + g_vlen(g, v), &rec, &bytes);
+	if (rc == MGB_E_ARENA && !second_pass) { // a large neighbourhood: once more with a whole worker arena (k_gc_labels_big)
+		unsigned int at;
+#if MGB_ON_DEVICE
+		at = atomicAdd(&T.n_new[1], 1u);
+#else
+		at = T.n_new[1]++;
+#endif
+		T.new_src[T.cap_new - 1 - (int32_t)at] = (int32_t)v; // the two lists together hold at most one entry per vertex
+		A.top = mark;
+		return 0;
+	}
 	int64_t off = -1;
 	if (rc == 0) off = pool_alloc(T.pool_hdr, bytes);
 	if (off >= 0) {

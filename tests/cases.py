@@ -337,9 +337,8 @@ def case_switches(lib, workdir, device):
     """the engine's experiment switches change the schedule, never the result: the same golden GAF with each of them on"""
     settings = [{b"lab_cache": 0}]  # graph chaining without the label table
     if device:
-        settings += [{b"slots": 2, b"min_slot_reads": 8},          # two sub-batches on private streams
-                     {b"sw8": 1, b"mb8": 16, b"sw7": 1, b"mb7": 16}]  # one-warp blocks for the tail-bound job kernels
-    defaults = {b"lab_cache": 1, b"slots": 1, b"min_slot_reads": 512, b"sw8": 4, b"mb8": 4, b"sw7": 4, b"mb7": 4}
+        settings += [{b"sw8": 1, b"mb8": 16, b"sw7": 1, b"mb7": 16}]  # one-warp blocks for the tail-bound job kernels
+    defaults = {b"lab_cache": 1, b"sw8": 4, b"mb8": 4, b"sw7": 4, b"mb7": 4}
     for st in settings:
         try:
             for k, v in st.items():
@@ -348,6 +347,51 @@ def case_switches(lib, workdir, device):
         finally:
             for k in st:
                 lib.mgb_set_param(k, defaults[k])
+
+
+def case_concurrent_calls(lib, workdir, n_threads=3, n_reads=90):
+    """mg_map_batch() entered by several host threads at once on one index (each call takes a slot of its own; the reference's
+    mg_map is re-entrant per thread buffer, minigraph.h:167-170): every thread gets what a single caller gets"""
+    import ctypes as C
+    import threading
+    from minigraph_b200 import capi, options
+    pre, reads = os.path.join(workdir, "svt"), os.path.join(workdir, "svt.reads.fa")
+    T.sim_graph(pre, 400000, 4, 23)
+    T.sim_reads(pre + ".hap.fa", reads, n_reads, 9000, "ont", 61)
+    names, seqs = T.read_fasta(reads)
+    g = lib.mgb_gfa_read((pre + ".gfa").encode())
+    io, mo = options.opt_set("lr", True)
+    gi = lib.mg_index(g, C.byref(io), 1, C.byref(mo))
+    assert gi, lib.mgb_last_error()
+
+    def run(lo, hi, out):
+        n = hi - lo
+        qlens = (C.c_int * n)(*[len(x) for x in seqs[lo:hi]])
+        cs, cn = (C.c_char_p * n)(*seqs[lo:hi]), (C.c_char_p * n)(*names[lo:hi])
+        gcs = (C.POINTER(capi.mg_gchains_t) * n)()
+        rc = lib.mg_map_batch(gi, n, qlens, cs, cn, gcs, C.byref(mo))
+        out.append((lo, rc, [T.gchains_to_py(gcs[i]) for i in range(n)]))
+        lib.mgb_free_batch(n, gcs)
+
+    whole = []
+    run(0, n_reads, whole)
+    assert whole[0][1] == 0
+    for rnd in range(2):  # the second round finds the label table warm
+        parts, th = [], []
+        for t in range(n_threads):
+            th.append(threading.Thread(target=run, args=(n_reads * t // n_threads, n_reads * (t + 1) // n_threads, parts)))
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        assert len(parts) == n_threads
+        for lo, rc, res in parts:
+            assert rc == 0, lib.mgb_last_error()
+            for i, r in enumerate(res):
+                d = T.diff_results(whole[0][2][lo + i], r)
+                assert d is None, "round %d read %d: %s" % (rnd, lo + i, d)
+    lib.mg_idx_destroy(gi)
+    lib.mgb_gfa_destroy(g)
 
 
 def case_tier_routing(lib, workdir, n_reads=120):

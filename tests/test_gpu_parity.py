@@ -59,6 +59,10 @@ def test_engine_switches_keep_results(lib, workdir):
     cases.case_switches(lib, workdir, device=True)
 
 
+def test_concurrent_callers(lib, workdir):
+    cases.case_concurrent_calls(lib, workdir)
+
+
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not shipped")
 def test_small_max_lc_skip(lib, workdir):
     cases.case_chain_skip(lib, workdir)
