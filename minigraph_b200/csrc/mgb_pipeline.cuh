@@ -222,6 +222,9 @@ MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A, int lane, int3
 	const MapOptDev &o = c.opt;
 	if (m.status != 0) return 0;
 	uint64_t mark = A.top;
+#if !MGB_ON_DEVICE && defined(MGB_HOSTSIM)
+	if (getenv("MGB_DUMP_CHAIN")) A.peak = A.top;
+#endif
 	int32_t qlen = c.b.seq_len[rid];
 	u128 *a = c.anchor + m.a_off;
 	int64_t n_a = m.n_a;
@@ -274,6 +277,9 @@ MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A, int lane, int3
 		prof_add(c, PROF_CHAIN_POST_CYC, prof_clock() - t2);
 	}
 	rc = warp_bcast_i32(rc, 0);
+#if !MGB_ON_DEVICE && defined(MGB_HOSTSIM)
+	if (lane == 0 && getenv("MGB_DUMP_CHAIN")) fprintf(stderr, "CH\t%d\t%d\t%lu\t%d\n", (int)n_a, (int)m.n_a, (unsigned long)(A.peak - mark), m.n_lc);
+#endif
 	A.top = mark;
 	return rc;
 }
