@@ -234,6 +234,8 @@ typedef struct {
 	double t_lab_ms;        /* k_gc_labels: reachability labels of source vertices seen for the first time (0 once the table is warm) */
 	int64_t n_lab_new;      /* such sources in this batch */
 	int64_t n_lab_big;      /* ... of which needed the second, warp-per-source pass */
+	double w_slot_wait_ms, w_upload_ms, w_pass_ms, w_redo_ms, w_download_ms; /* host wall clock of the call: waiting for a slot; packing + H2D; the kernels of the first pass
+	                           with the host syncs between them; the large-arena pass over reads that outgrew their arena; result packing + D2H up to the assembly */
 } mgb_stats_t;
 
 /* test hook: align one gap through the tier-3 WFA path (exact up to max_iter cells, then the reference's chaining

@@ -349,9 +349,11 @@ MG_HD inline int radix_sort_exact(Arena &A, T *a, int64_t n, int sizeof_key, Key
 	if (n <= MIN_SIZE) { rs_insertsort(a, a + n, key); return 0; }
 	uint64_t mark = A.top;
 	RsRange *stack;
-	int64_t m_stack = n / MIN_SIZE + 272;
+	int64_t m_stack = n / MIN_SIZE + 4; // pending ranges are disjoint and each holds more than MIN_SIZE elements
 	MGB_ALLOC(A, stack, RsRange, m_stack);
-	int32_t bb[256], be[256];
+	int32_t *bb, *be; // bin tables in the arena, not on the thread's stack
+	MGB_ALLOC(A, bb, int32_t, 512);
+	be = bb + 256;
 	int64_t top = 0;
 	stack[top].beg = 0, stack[top].end = (int32_t)n, stack[top].s = (sizeof_key - 1) * 8, ++top;
 	while (top > 0) {
@@ -416,7 +418,7 @@ MG_HD inline int radix_sort_exact_w(Arena &A, T *a, int64_t n, int sizeof_key, K
 	if (n <= MIN_SIZE) { if (lane == 0) rs_insertsort(a, a + n, key); warp_sync(); return 0; }
 	uint64_t mark = A.top;
 	RsRange *stack;
-	int64_t m_stack = n / MIN_SIZE + 272;
+	int64_t m_stack = n / MIN_SIZE + 4; // pending ranges are disjoint and each holds more than MIN_SIZE elements
 	MGB_ALLOC(A, stack, RsRange, m_stack);
 	int32_t *bb, *be, *nz;
 	MGB_ALLOC(A, bb, int32_t, 256);

@@ -48,8 +48,8 @@ static int64_t p_tier_learn = 1;       // 0: every gap tries every tier (no rout
 static int64_t p_lab_cache = 1;        // 0: graph chaining searches its walks per read instead of keeping per-source labels in HBM (mgb_gclabel.cuh)
 
 // launch shape per stage: warps per block and blocks per SM wanted (tunable for experiments: "sw<stage>", "mb<stage>")
-static int STAGE_MINB[19] = { 8, 8, 8, 8, 5, 8, 7, 4, 4, 4, 0, 0, 0, 0, 0, 0, 0, 8, 8 }; // indexed by stage number (10-16 unused)
-static int STAGE_WARPS[19] = { 4, 4, 4, 4, 4, 4, 2, 4, 4, 4, 0, 0, 0, 0, 0, 0, 0, 4, 4 };
+static int STAGE_MINB[20] = { 8, 2, 8, 8, 5, 8, 7, 4, 4, 4, 0, 0, 0, 0, 0, 0, 0, 8, 8, 2 }; // indexed by stage number (10-16 unused)
+static int STAGE_WARPS[20] = { 4, 3, 4, 4, 4, 4, 2, 4, 4, 4, 0, 0, 0, 0, 0, 0, 0, 4, 4, 3 };
 extern "C" const char *mgb_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char *mgb_version(void) { return "mgb200-r1"; }
 extern "C" int mgb_set_param(const char *key, int64_t value)
@@ -181,12 +181,13 @@ struct LaunchArgs {
 //         materialisation + alignment plan (K7b), 4/6/7 WFA jobs tier 1/2/3 (K8a), 5 finish: CIGAR stitching + ds + result
 //         blob (K8b), 3 segment sketch for the index, 17 reachability labels of the sources graph chaining asks for (one per thread)
 #define MGB_IS_WFA(STAGE) ((STAGE) == 4 || (STAGE) == 6 || (STAGE) == 7)
-#define MGB_IS_WARP(STAGE) (MGB_IS_WFA(STAGE) || (STAGE) == 8 || (STAGE) == 1 || (STAGE) == 2 || (STAGE) == 0 || (STAGE) == 5 || (STAGE) == 9) // stages entered by all lanes of the warp
+#define MGB_IS_WARP(STAGE) (MGB_IS_WFA(STAGE) || (STAGE) == 8 || (STAGE) == 1 || (STAGE) == 2 || (STAGE) == 0 || (STAGE) == 5 || (STAGE) == 9 || (STAGE) == 19) // stages entered by all lanes of the warp
 template<int STAGE>
 MG_HD inline int run_stage(const LaunchArgs &L, int item, Arena &A, int lane, int32_t *smem)
 {
 	if (STAGE == 0) return stage_seed(L.c, item, A, lane, smem);
-	if (STAGE == 1) return stage_chain(L.c, item, A, lane, smem);
+	if (STAGE == 1) return stage_chain<0>(L.c, item, A, lane, smem);
+	if (STAGE == 19) return stage_chain<1>(L.c, L.c.rescue_list[item], A, lane, smem); // the reads k_chain listed
 	if (STAGE == 2) return stage_gchain(L.c, L.routs, item, A, lane);
 	if (STAGE == 17) return label_job(A, L.c.g, L.c.lab, item, 0);
 	if (STAGE == 18) return label_job(A, L.c.g, L.c.lab, item, 1); // lane 0 with the whole arena of its warp
@@ -224,7 +225,7 @@ MG_HD inline void stage_fail(const LaunchArgs &L, int item, int rc)
 #endif
 		return;
 	}
-	int rid = STAGE == 8? L.c.gjobs[L.job_start + item].rid : STAGE == 4? L.c.jobs[L.job_start + item].rid : STAGE == 6? L.c.jobs[L.c.jobq[0][item]].rid : STAGE == 7? L.c.jobs[L.c.jobq[1][item]].rid : item;
+	int rid = STAGE == 8? L.c.gjobs[L.job_start + item].rid : STAGE == 4? L.c.jobs[L.job_start + item].rid : STAGE == 6? L.c.jobs[L.c.jobq[0][item]].rid : STAGE == 7? L.c.jobs[L.c.jobq[1][item]].rid : STAGE == 19? L.c.rescue_list[item] : item;
 	L.c.meta[rid].status = rc; // benign race between jobs of one read: any negative code triggers the redo
 	if (STAGE == 2 || MGB_IS_WARP(STAGE) || STAGE == 5 || STAGE == 9) L.routs[rid].status = rc;
 }
@@ -240,8 +241,9 @@ __device__ __forceinline__ void stage_loop(const LaunchArgs &L)
 	Arena A;
 	arena_init(A, L.arena_base + (uint64_t)worker * L.arena_bytes, L.arena_bytes);
 	extern __shared__ int4 dyn_smem[];
-	const int smem_stride = STAGE == 4? WfTier1::STRIDE : STAGE == 6? WfTier2::STRIDE : STAGE == 0? SKETCH_SMEM_BYTES : STAGE == 8? GWFA_SMEM_ARENA : 0;
+	const int smem_stride = STAGE == 4? WfTier1::STRIDE : STAGE == 6? WfTier2::STRIDE : STAGE == 0? SKETCH_SMEM_BYTES : STAGE == 8? GWFA_SMEM_ARENA : (STAGE == 1 || STAGE == 19)? CHAIN_SMEM_BYTES : 0;
 	int32_t *smem = smem_stride? (int32_t*)((char*)dyn_smem + (size_t)(threadIdx.x >> 5) * smem_stride) : 0;
+	if (STAGE == 1 || STAGE == 19) chain_smem_init(smem, lane);
 	const int n_work = L.n_work_dev? (int)*L.n_work_dev : L.n_work;
 	for (;;) {
 		int item = 0;
@@ -289,7 +291,8 @@ __device__ __forceinline__ void stage_loop_thread(const LaunchArgs &L)
 // named entry points (one per stage, so that profiles read well); blocks of 4 warps, MINB blocks per SM wanted
 #define MGB_KERNEL(name, STAGE, MINB) __global__ void __launch_bounds__(128, MINB) name(LaunchArgs L) { if (L.thread_mode) stage_loop_thread<STAGE>(L); else stage_loop<STAGE>(L); }
 MGB_KERNEL(k_seed, 0, 8)          // K1-K3: sketch, index lookup, seed sort
-MGB_KERNEL(k_chain, 1, 8)         // K4/K5: linear chaining
+MGB_KERNEL(k_chain, 1, 2)         // K4/K5: linear chaining on chip (seeds bulk-loaded into shared memory)
+MGB_KERNEL(k_chain_rescue, 19, 2) // K5: long-join rescue (RMQ chaining) of the reads k_chain listed
 MGB_KERNEL(k_gchain, 2, 8)        // K6: graph chaining DP + k-shortest walks, overlap resolution, bridging plan
 MGB_KERNEL(k_gwfa, 8, 4)          // K7a: bridging alignments (graph wavefront), one warp per bridge
 MGB_KERNEL(k_gchain_gen, 9, 4)    // K7b: graph-chain materialisation, post filters, mapq, alignment plan
@@ -311,6 +314,7 @@ template<> struct StageKernel<7> { static void (*get())(LaunchArgs) { return k_w
 template<> struct StageKernel<8> { static void (*get())(LaunchArgs) { return k_gwfa; } };
 template<> struct StageKernel<9> { static void (*get())(LaunchArgs) { return k_gchain_gen; } };
 template<> struct StageKernel<5> { static void (*get())(LaunchArgs) { return k_finish; } };
+template<> struct StageKernel<19> { static void (*get())(LaunchArgs) { return k_chain_rescue; } };
 template<> struct StageKernel<17> { static void (*get())(LaunchArgs) { return k_gc_labels; } };
 template<> struct StageKernel<18> { static void (*get())(LaunchArgs) { return k_gc_labels_big; } };
 #endif
@@ -440,7 +444,8 @@ static void launch_stage(LaunchArgs &L, const Workers &W, int warps_override = 0
 #ifdef MGB_HOSTSIM
 	Arena A;
 	arena_init(A, W.arena, STAGE == 17? (W.arena_bytes / 32) & ~(uint64_t)15 : W.arena_bytes); // one item per thread: a thread's share, as on the device
-	std::vector<int32_t> sim_smem(std::max<size_t>(std::max<size_t>(WfTier1::STRIDE, WfTier2::STRIDE), std::max<size_t>(std::max<size_t>(GWFA_SMEM_ARENA, CHAIN_SMEM), SKETCH_SMEM_BYTES)) / 4);
+	std::vector<int32_t> sim_smem(std::max<size_t>(std::max<size_t>(WfTier1::STRIDE, WfTier2::STRIDE), std::max<size_t>(std::max<size_t>(GWFA_SMEM_ARENA, CHAIN_SMEM_BYTES), SKETCH_SMEM_BYTES)) / 4);
+	if (STAGE == 1 || STAGE == 19) { mbar_init((uint64_t*)sim_smem.data(), 1); sim_smem[2] = 0; }
 	const int n_work_sim = L.n_work_dev? (int)*L.n_work_dev : L.n_work;
 	for (int it = 0; it < n_work_sim; ++it) {
 		int item = L.rid_list? L.rid_list[it] : it;
@@ -471,7 +476,7 @@ static void launch_stage(LaunchArgs &L, const Workers &W, int warps_override = 0
 	int want = dev_sm_count() * STAGE_MINB[STAGE] * STAGE_WARPS[STAGE]; // resident warps this stage can keep on the chip
 	int n_w = std::min(W.n_workers, want);
 	int blocks = std::max(1, n_w / warps);
-	size_t smem = STAGE == 4? (size_t)warps * WfTier1::STRIDE : STAGE == 6? (size_t)warps * WfTier2::STRIDE : STAGE == 0? (size_t)warps * SKETCH_SMEM_BYTES : STAGE == 8? (size_t)warps * GWFA_SMEM_ARENA : 0;
+	size_t smem = STAGE == 4? (size_t)warps * WfTier1::STRIDE : STAGE == 6? (size_t)warps * WfTier2::STRIDE : STAGE == 0? (size_t)warps * SKETCH_SMEM_BYTES : STAGE == 8? (size_t)warps * GWFA_SMEM_ARENA : (STAGE == 1 || STAGE == 19)? (size_t)warps * CHAIN_SMEM_BYTES : 0;
 	void (*kern)(LaunchArgs) = StageKernel<STAGE>::get();
 	if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	L.thread_mode = (p_thread_mask >> STAGE) & 1;
@@ -988,16 +993,18 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 		dsync();
 		S.t_pack_ms = t_pack;
 	}
-	size_t small_dev = (size_t)n_reads * (8 + 4 + 4 + 4 + 4) + 4096 + 1024;
+	size_t small_dev = (size_t)n_reads * (8 + 4 + 4 + 4 + 4 + 4) + 4096 + 1024;
 	char *ds = (char*)sl.d_small.ensure(small_dev);
 	uint64_t *d_seq_off = (uint64_t*)ds;
 	int32_t *d_seq_len = (int32_t*)(d_seq_off + n_reads);
 	uint32_t *d_name_hash = (uint32_t*)(d_seq_len + n_reads);
 	int32_t *d_list_buf = (int32_t*)(d_name_hash + n_reads); // n_reads entries: read list of the retry pass
 	int32_t *d_self_id = d_list_buf + n_reads; // n_reads entries, MG_M_NO_DIAG only
-	char *dsm = (char*)(((uintptr_t)(d_self_id + n_reads) + 255) & ~(uintptr_t)255);
+	int32_t *d_rescue = d_self_id + n_reads; // n_reads entries: reads handed from k_chain to k_chain_rescue
+	char *dsm = (char*)(((uintptr_t)(d_rescue + n_reads) + 255) & ~(uintptr_t)255);
 	unsigned int *d_next = (unsigned int*)dsm;
 	unsigned int *d_jobq_n = d_next + 4;
+	unsigned int *d_rescue_n = d_next + 8;
 	unsigned long long *d_prof = (unsigned long long*)(dsm + 64);
 	Pool *d_pools = (Pool*)(dsm + 64 + sizeof(unsigned long long) * PROF_N);
 	unsigned int *d_tier_hist = (unsigned int*)((char*)(d_pools + 16) + 64); // 32 x 4 counters behind the pool headers
@@ -1069,6 +1076,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 		L.c.pool_gjobs = &d_pools[P_GJOBS], L.c.gjobs = (GwfaJob*)d_buf[P_GJOBS];
 		L.c.pool_walk = &d_pools[P_WALK], L.c.walk = (int32_t*)d_buf[P_WALK];
 		L.c.next_read = d_next;
+		L.c.rescue_list = d_rescue, L.c.rescue_n = d_rescue_n;
 		memset(&L.c.lab, 0, sizeof(L.c.lab));
 		if (use_lab) {
 			L.c.lab.src_off = M->d_lab_off, L.c.lab.pool_hdr = M->d_lab_hdr, L.c.lab.pool = M->d_lab_pool, L.c.lab.new_src = d_lab_new, L.c.lab.n_new = d_lab_n;
@@ -1089,7 +1097,16 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 			if (timed) tm_seed.start();
 			{ if (timed) tm_k[0].start(); launch_stage<0>(L, W); if (timed) tm_k[0].stop(); }
 			if (timed) tm_seed.stop(), tm_chain.start();
-			{ if (timed) tm_k[1].start(); launch_stage<1>(L, W); if (timed) tm_k[1].stop(); }
+			{
+				if (timed) tm_k[1].start();
+				dzero(d_rescue_n, sizeof(unsigned int));
+				launch_stage<1>(L, W);
+				L.n_work_dev = d_rescue_n, L.rid_list = 0; // the reads k_chain put on the rescue list (count known on the device only)
+				launch_stage<19>(L, W);
+				L.n_work_dev = 0, L.rid_list = d_list;
+				if (timed) tm_k[1].stop();
+				S.n_launches += 1;
+			}
 			if (timed) tm_chain.stop(), tm_align.start();
 			if (use_lab) { // labels of the sources k_chain listed (count known on the device only)
 				L.n_work_dev = d_lab_n, L.rid_list = 0;
@@ -1171,7 +1188,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 #endif
 			dsync();
 		};
-		run_pass(0, n_reads, sl.W, true);
+		{ const double tw = now_ms(); if (attempt == 0) S.w_upload_ms = tw - t_host0; run_pass(0, n_reads, sl.W, true); S.w_pass_ms += now_ms() - tw; }
 		S.n_jobs = jobs_done;
 		d2h(routs.data(), d_routs, sizeof(ReadOut) * (size_t)n_reads);
 		d2h(meta.data(), d_meta, sizeof(ReadMeta) * (size_t)n_reads);
@@ -1190,7 +1207,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 			int nw = (int)std::min<uint64_t>(16, std::max<uint64_t>(1, dev_free_mem() / 2 / big)); // a handful of reads per batch at most come here
 			if (M->Wbig.arena == 0 || M->Wbig.arena_bytes != big) ensure_workers(M->Wbig, std::max(1, nw), big);
 			h2d(d_list_buf, redo.data(), redo.size() * sizeof(int32_t));
-			run_pass(d_list_buf, (int32_t)redo.size(), M->Wbig, false);
+			{ const double tw = now_ms(); run_pass(d_list_buf, (int32_t)redo.size(), M->Wbig, false); S.w_redo_ms += now_ms() - tw; }
 			S.n_retry += (int64_t)redo.size();
 			d2h(routs.data(), d_routs, sizeof(ReadOut) * (size_t)n_reads);
 			d2h(meta.data(), d_meta, sizeof(ReadMeta) * (size_t)n_reads);
@@ -1259,6 +1276,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 
 	// ---- results ----
 	double t_asm0 = now_ms();
+	S.w_download_ms = t_asm0 - t_host0 - S.w_upload_ms - S.w_pass_ms - S.w_redo_ms;
 	int first_bad = -1;
 	for (int i = 0; i < n_reads; ++i) {
 		int st = meta[i].status < 0? meta[i].status : routs[i].status;
@@ -1330,6 +1348,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 		M->slot_busy[k] = true, ++M->in_flight;
 	}
 	Model::Slot &sl = M->slots[k];
+	const double t_slot = now_ms();
 #ifndef MGB_HOSTSIM
 	cudaSetDevice((int)p_device);
 #endif
@@ -1361,6 +1380,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 #endif
 	}
 	mgb_stats_t S = sl.st;
+	S.w_slot_wait_ms = t_slot - t0;
 #ifndef MGB_HOSTSIM
 	if (rc == 0) { float a = 0; if (cudaEventElapsedTime(&a, sl.ev_first, sl.ev_last) == cudaSuccess) S.t_dev_span_ms = a; }
 #else

@@ -277,7 +277,7 @@ MG_HD inline int chain_dp(Arena &A, int max_dist_x, int max_dist_y, int bw, int 
 // visited predecessors) are then replayed on the ballots of the chunk, in visiting order.
 MG_HD inline int chain_dp_w(Arena &A, int max_dist_x, int max_dist_y, int bw, int max_skip, int max_iter, int min_cnt, int min_sc,
 							float pen_gap, float pen_skip, int is_cdna, int n_seg, int64_t n, u128 *a,
-							int32_t *n_u_, uint64_t **u_, int32_t *n_a_, int lane, void *onchip = 0, int64_t onchip_bytes = 0)
+							int32_t *n_u_, uint64_t **u_, int32_t *n_a_, int lane)
 {
 	int32_t *f, *t, *v, *p, max_drop = bw;
 	int64_t i, max_ii, st = 0;
@@ -289,20 +289,10 @@ MG_HD inline int chain_dp_w(Arena &A, int max_dist_x, int max_dist_y, int bw, in
 	uint64_t *u_store;
 	MGB_ALLOC(A, u_store, uint64_t, n);
 	uint64_t mark = A.top;
-	u128 *a_out = a; // where the chained anchors go (HBM)
-	if (onchip && n * 32 + 64 <= onchip_bytes) { // the read's anchors and its DP state (f,p,v,t) fit on chip: every predecessor re-read stays there
-		u128 *as = (u128*)onchip;
-		p = (int32_t*)(as + n), f = p + n, v = f + n, t = v + n;
-		for (i = lane; i < n; i += MGB_W) as[i] = a[i];
-		a = as;
-	} else if (onchip && n * 16 + 64 <= onchip_bytes) { // the DP state alone
-		p = (int32_t*)onchip, f = p + n, v = f + n, t = v + n;
-	} else {
-		MGB_ALLOC(A, p, int32_t, n);
-		MGB_ALLOC(A, f, int32_t, n);
-		MGB_ALLOC(A, v, int32_t, n);
-		MGB_ALLOC(A, t, int32_t, n);
-	}
+	MGB_ALLOC(A, p, int32_t, n);
+	MGB_ALLOC(A, f, int32_t, n);
+	MGB_ALLOC(A, v, int32_t, n);
+	MGB_ALLOC(A, t, int32_t, n);
 	for (i = lane; i < n; i += MGB_W) t[i] = 0;
 	warp_sync();
 	for (i = 0, max_ii = -1; i < n; ++i) {
@@ -366,7 +356,7 @@ MG_HD inline int chain_dp_w(Arena &A, int max_dist_x, int max_dist_y, int bw, in
 		warp_sync();
 	}
 	int32_t n_u = 0, n_v = 0;
-	MGB_TRY(chain_finish_w(A, n, f, p, v, t, min_cnt, min_sc, max_drop, a_out, u_store, &n_u, &n_v, lane));
+	MGB_TRY(chain_finish_w(A, n, f, p, v, t, min_cnt, min_sc, max_drop, a, u_store, &n_u, &n_v, lane));
 	A.top = mark;
 	*u_ = u_store, *n_u_ = n_u, *n_a_ = n_u > 0? n_v : 0;
 	return 0;

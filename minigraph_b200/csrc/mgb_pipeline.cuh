@@ -7,6 +7,7 @@
 #include "mgb_seed.cuh"
 #include "mgb_lchain.cuh"
 #include "mgb_gclabel.cuh"
+#include "mgb_tma.cuh"
 
 namespace mgb {
 
@@ -28,6 +29,7 @@ struct PipeCtx {
 	Pool *pool_gstate;     char *gstate;         // per-read state between the two graph-chaining passes
 	Pool *pool_gjobs;      struct GwfaJob *gjobs; // bridging alignment jobs (K7a)
 	Pool *pool_walk;       int32_t *walk;        // walks found by the bridging jobs
+	int32_t *rescue_list;  unsigned int *rescue_n; // reads handed from k_chain to k_chain_rescue
 	LabTab lab;            // reachability labels of the graph (mgb_gclabel.cuh); persistent across batches
 	// work queue
 	unsigned int *next_read;
@@ -209,79 +211,139 @@ MG_HD inline int stage_chain_tail(const PipeCtx &c, ReadMeta &m, Arena &A, u128 
 	return 0;
 }
 
-// K4/K5 for one read: seeds -> linear chains.  Anchors are compacted in place; chains go to the lchain pool.
-// Warp-uniform: all lanes enter; the RMQ chaining is warp-cooperative, the rest runs on lane 0 and its few scalar
-// results are broadcast.
-// Shared memory for the DP state was tried (7 and 14 KiB per warp): the DP itself got ~25 % faster, but the smaller L1 and the
-// lower occupancy cost the rest of the kernel more (k_chain 11.0 -> 14.6 / 16.0 ms on B200), so the kernel asks for none.
-static const int CHAIN_SMEM = 7 * 1024;
+// K4/K5 for one read: seeds -> linear chains, in two kernels.
+//   k_chain         (pass 0): chaining DP (lr) or RMQ chaining (asm), backtracking, compaction; then either the chain records
+//                   (stage_chain_tail) or, for a read whose best chain leaves much of it uncovered (map-algo.c:407-417: in practice
+//                   every read that spans several segments), a place on the rescue list with its compacted anchors;
+//   k_chain_rescue  (pass 1): the listed reads: anchors sorted back into target order, RMQ chaining with the long bandwidth, tail.
+// ON CHIP: the read's seeds are bulk-copied (cp.async.bulk + mbarrier, mgb_tma.cuh) into the warp's slice of shared memory and the
+// whole pass -- DP state f/p/v/t, end-point sort, backtracking, compaction, RMQ window and tree, chain filters -- works in an
+// arena that is the rest of that slice; only the surviving anchors go back to HBM, as one bulk store.  Algorithmic traffic is then
+// the traffic: 16 B per seed in, 16 B per kept anchor out, 44 B per chain.  A read that does not fit its slice (CHAIN_SMEM_BYTES,
+// about 600 seeds) is worked in the worker's HBM arena by the same code.
+static const int CHAIN_SMEM_BYTES = 36 * 1024; // per warp; 6 warps per SM
 
-MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A, int lane, int32_t *smem = 0)
+struct ChainRun { // what one pass leaves behind
+	int32_t n_keep;   // anchors of a[] to write back
+	int32_t rescue;   // pass 0: the read goes on the rescue list
+};
+
+template<int PASS>
+MG_HD inline int chain_pass(const PipeCtx &c, int rid, Arena &A, u128 *a, int64_t n_a, int lane, ChainRun *run)
 {
 	ReadMeta &m = c.meta[rid];
 	const MapOptDev &o = c.opt;
-	if (m.status != 0) return 0;
-	uint64_t mark = A.top;
-#if !MGB_ON_DEVICE && defined(MGB_HOSTSIM)
-	if (getenv("MGB_DUMP_CHAIN")) A.peak = A.top;
-#endif
-	int32_t qlen = c.b.seq_len[rid];
-	u128 *a = c.anchor + m.a_off;
-	int64_t n_a = m.n_a;
+	const uint64_t mark = A.top;
+	const int32_t qlen = c.b.seq_len[rid];
 	int32_t n_lc = 0, n_a_new = 0;
 	uint64_t *u = 0;
-	const int is_splice = !!(o.flag & F_SPLICE), is_sr = !!(o.flag & F_SR);
-	int max_gap_qry, max_gap_ref;
-	// reference: map-algo.c:377-386
-	if (is_sr) max_gap_qry = qlen > o.max_gap? qlen : o.max_gap;
-	else max_gap_qry = o.max_gap;
-	if (o.max_gap_ref > 0) max_gap_ref = o.max_gap_ref;
-	else if (o.max_frag_len > 0) {
-		max_gap_ref = o.max_frag_len - qlen;
-		if (max_gap_ref < o.max_gap) max_gap_ref = o.max_gap;
-	} else max_gap_ref = o.max_gap;
-
+	run->n_keep = 0, run->rescue = 0;
 	unsigned long long t0 = prof_clock();
-	if (n_a > 0) {
-		if (o.flag & F_RMQ) {
-			MGB_TRY(chain_rmq_w(A, o.max_gap, o.max_gap_pre, o.bw, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
-								o.chn_pen_gap, o.chn_pen_skip, n_a, a, &n_lc, &u, &n_a_new, lane));
-		} else {
-			MGB_TRY(chain_dp_w(A, max_gap_ref, max_gap_qry, o.bw, o.max_lc_skip, o.max_lc_iter, o.min_lc_cnt, o.min_lc_score,
-							   o.chn_pen_gap, o.chn_pen_skip, is_splice, batch_n_seg(c.b, rid), n_a, a, &n_lc, &u, &n_a_new, lane, smem, smem? CHAIN_SMEM : 0));
+	if (PASS == 0) {
+		const int is_splice = !!(o.flag & F_SPLICE), is_sr = !!(o.flag & F_SR);
+		int max_gap_qry, max_gap_ref;
+		// reference: map-algo.c:377-386
+		if (is_sr) max_gap_qry = qlen > o.max_gap? qlen : o.max_gap;
+		else max_gap_qry = o.max_gap;
+		if (o.max_gap_ref > 0) max_gap_ref = o.max_gap_ref;
+		else if (o.max_frag_len > 0) {
+			max_gap_ref = o.max_frag_len - qlen;
+			if (max_gap_ref < o.max_gap) max_gap_ref = o.max_gap;
+		} else max_gap_ref = o.max_gap;
+		if (n_a > 0) {
+			if (o.flag & F_RMQ) {
+				MGB_TRY(chain_rmq_w(A, o.max_gap, o.max_gap_pre, o.bw, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
+									o.chn_pen_gap, o.chn_pen_skip, n_a, a, &n_lc, &u, &n_a_new, lane));
+			} else {
+				MGB_TRY(chain_dp_w(A, max_gap_ref, max_gap_qry, o.bw, o.max_lc_skip, o.max_lc_iter, o.min_lc_cnt, o.min_lc_score,
+								   o.chn_pen_gap, o.chn_pen_skip, is_splice, batch_n_seg(c.b, rid), n_a, a, &n_lc, &u, &n_a_new, lane));
+			}
 		}
-	}
-	if (lane == 0) m.n_u0 = n_lc;
-	unsigned long long t1 = prof_clock();
-	if (lane == 0) prof_add(c, PROF_CHAIN_DP_CYC, t1 - t0);
-	// long-join rescue (reference: map-algo.c:407-417)
-	if (o.bw_long > o.bw && (o.flag & (F_SPLICE | F_SR)) == 0 && batch_n_seg(c.b, rid) == 1 && n_lc > 1) {
-		int32_t st = (int32_t)a[0].y, en = (int32_t)a[(int32_t)u[0] - 1].y;
-		if (qlen - (en - st) > o.rmq_rescue_size || (float)(qlen - (en - st)) > (float)qlen * o.rmq_rescue_ratio) {
-			int64_t n2 = 0;
-			for (int32_t i = 0; i < n_lc; ++i) n2 += (int32_t)u[i];
-			warp_sync(); // u[] sits at the mark: every lane must have read it before the sort below reuses that memory
-			A.top = mark;
-			MGB_TRY(radix_sort_128x_w(A, a, n2, lane));
-			MGB_TRY(chain_rmq_w(A, o.max_gap, o.max_gap_pre, o.bw_long, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
-								o.chn_pen_gap, o.chn_pen_skip, n2, a, &n_lc, &u, &n_a_new, lane));
+		if (lane == 0) m.n_u0 = n_lc, prof_add(c, PROF_CHAIN_DP_CYC, prof_clock() - t0);
+		// long-join rescue (reference: map-algo.c:407-417)
+		if (o.bw_long > o.bw && (o.flag & (F_SPLICE | F_SR)) == 0 && batch_n_seg(c.b, rid) == 1 && n_lc > 1) {
+			int32_t st = (int32_t)a[0].y, en = (int32_t)a[(int32_t)u[0] - 1].y;
+			if (qlen - (en - st) > o.rmq_rescue_size || (float)(qlen - (en - st)) > (float)qlen * o.rmq_rescue_ratio) {
+				int32_t n2 = 0;
+				for (int32_t i = 0; i < n_lc; ++i) n2 += (int32_t)u[i];
+				warp_sync();
+				if (lane == 0) {
+					m.n_a = n2; // the chained anchors are what the second pass starts from
+#if MGB_ON_DEVICE
+					c.rescue_list[atomicAdd(c.rescue_n, 1u)] = rid;
+#else
+					c.rescue_list[(*c.rescue_n)++] = rid;
+#endif
+				}
+				run->n_keep = n2, run->rescue = 1;
+				A.top = mark;
+				return 0;
+			}
 		}
+	} else {
+		MGB_TRY(radix_sort_128x_w(A, a, n_a, lane));
+		MGB_TRY(chain_rmq_w(A, o.max_gap, o.max_gap_pre, o.bw_long, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
+							o.chn_pen_gap, o.chn_pen_skip, n_a, a, &n_lc, &u, &n_a_new, lane));
+		if (lane == 0) prof_add(c, PROF_CHAIN_RMQ_CYC, prof_clock() - t0);
 	}
 	unsigned long long t2 = prof_clock();
 	int rc = 0;
 	if (lane == 0) {
 		Arena B = A;
-		prof_add(c, PROF_CHAIN_RMQ_CYC, t2 - t1);
 		rc = stage_chain_tail(c, m, B, a, u, n_lc, n_a_new);
 		if (B.peak > A.peak) A.peak = B.peak;
 		prof_add(c, PROF_CHAIN_POST_CYC, prof_clock() - t2);
 	}
 	rc = warp_bcast_i32(rc, 0);
-#if !MGB_ON_DEVICE && defined(MGB_HOSTSIM)
-	if (lane == 0 && getenv("MGB_DUMP_CHAIN")) fprintf(stderr, "CH\t%d\t%d\t%lu\t%d\n", (int)n_a, (int)m.n_a, (unsigned long)(A.peak - mark), m.n_lc);
-#endif
+	warp_sync();
+	run->n_keep = n_lc > 0? n_a_new : 0;
 	A.top = mark;
 	return rc;
+}
+
+// smem: the warp's slice of CHAIN_SMEM_BYTES, or NULL.  Its first 16 bytes hold the transaction barrier of the bulk loads and the
+// parity the next wait has to use (chain_smem_init() once per kernel).
+MG_HD inline void chain_smem_init(int32_t *smem, int lane)
+{
+	if (lane == 0) { mbar_init((uint64_t*)smem, 1); smem[2] = 0; }
+	warp_sync();
+}
+
+template<int PASS>
+MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A, int lane, int32_t *smem)
+{
+	ReadMeta &m = c.meta[rid];
+	if (m.status != 0) return 0;
+#if !MGB_ON_DEVICE && defined(MGB_HOSTSIM)
+	if (getenv("MGB_DUMP_CHAIN")) A.peak = A.top;
+#endif
+	u128 *a = c.anchor + m.a_off;
+	const int64_t n_a = m.n_a;
+	ChainRun run;
+	const uint64_t a_bytes = (uint64_t)n_a * sizeof(u128);
+	if (smem && n_a > 0 && a_bytes + 4096 <= (uint64_t)CHAIN_SMEM_BYTES - 16) { // (a read with a handful of seeds still needs the sort's bin tables)
+		uint64_t *bar = (uint64_t*)smem;
+		u128 *as = (u128*)((char*)smem + 16);
+		const uint32_t parity = (uint32_t)smem[2];
+		if (lane == 0) bulk_load(as, a, (uint32_t)a_bytes, bar);
+		mbar_wait(bar, parity);
+		warp_sync();
+		if (lane == 0) smem[2] = (int32_t)(parity ^ 1);
+		Arena S;
+		arena_init(S, (char*)as + a_bytes, (uint64_t)CHAIN_SMEM_BYTES - 16 - a_bytes);
+		int rc = chain_pass<PASS>(c, rid, S, as, n_a, lane, &run);
+		if (rc != MGB_E_ARENA) {
+			if (rc == 0 && run.n_keep > 0) {
+				warp_sync();
+				if (lane == 0) { bulk_store(a, as, (uint32_t)run.n_keep * (uint32_t)sizeof(u128)); bulk_store_wait(); }
+				warp_sync();
+			}
+			if (lane == 0 && c.prof) prof_add(c, PROF_CHAIN_BT_CYC, 1); // reads chained on chip
+			return rc;
+		}
+		// outgrew the slice: a[] in HBM is untouched, start over there
+	}
+	return chain_pass<PASS>(c, rid, A, a, n_a, lane, &run);
 }
 
 } // namespace mgb
