@@ -45,6 +45,7 @@ static int64_t p_thread_mask = 0;      // bit s set: stage s runs one item per t
 static int64_t p_slots = 3;            // mg_map_batch calls that may run at once on one index (each on its own slot: stream, buffers, arenas)
 static int64_t p_slot_workers = 0;
 static int64_t p_tier_learn = 1;       // 0: every gap tries every tier (no routing)
+static int64_t p_pack2 = 1;            // 0: reads are uploaded as ASCII (1 byte per base) instead of 2 bits per base
 static int64_t p_lab_cache = 1;        // 0: graph chaining searches its walks per read instead of keeping per-source labels in HBM (mgb_gclabel.cuh)
 
 // launch shape per stage: warps per block and blocks per SM wanted (tunable for experiments: "sw<stage>", "mb<stage>")
@@ -64,6 +65,7 @@ extern "C" int mgb_set_param(const char *key, int64_t value)
 	else if (!strcmp(key, "slots")) p_slots = value;
 	else if (!strcmp(key, "slot_workers")) p_slot_workers = value;
 	else if (!strcmp(key, "lab_cache")) p_lab_cache = value;
+	else if (!strcmp(key, "pack2")) p_pack2 = value;
 	else if (!strcmp(key, "tier_learn")) p_tier_learn = value;
 	else if (!strncmp(key, "sw", 2) && key[2] >= '0' && key[2] <= '9' && !key[3] && value >= 1 && value <= 4) STAGE_WARPS[key[2] - '0'] = (int)value;
 	else if (!strncmp(key, "mb", 2) && key[2] >= '0' && key[2] <= '9' && !key[3] && value >= 1 && value <= 32) STAGE_MINB[key[2] - '0'] = (int)value;
@@ -76,7 +78,7 @@ extern "C" int mgb_set_param(const char *key, int64_t value)
 // ---------------------------------------------------------------------------------------------------------------
 
 #ifdef MGB_HOSTSIM
-static bool dev_ok() { return true; }
+static bool dev_ok(int dev = -1) { (void)dev; return true; }
 static void *dmalloc(size_t n) { void *p = malloc(n? n : 16); return p; }
 static void dfree(void *p) { free(p); }
 static void h2d(void *d, const void *h, size_t n) { if (n) memcpy(d, h, n); }
@@ -91,11 +93,11 @@ static size_t dev_free_mem() { return (size_t)8 << 30; }
 #define CUDA_OK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { set_error(std::string(#call) + ": " + cudaGetErrorString(_e)); abort(); } } while (0)
 // every host thread that drives a slot of the batch pipeline works on its own stream
 static thread_local cudaStream_t t_stream = 0;
-static bool dev_ok()
+static bool dev_ok(int dev = -1)
 {
 	int n = 0;
 	if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return false;
-	if (cudaSetDevice((int)p_device) != cudaSuccess) return false;
+	if (cudaSetDevice(dev >= 0? dev : (int)p_device) != cudaSuccess) return false;
 	return true;
 }
 static void *dmalloc(size_t n) { void *p = 0; CUDA_OK(cudaMalloc(&p, n? n : 16)); return p; }
@@ -106,7 +108,7 @@ static void d2h(void *h, const void *d, size_t n) { if (n) { CUDA_OK(cudaMemcpyA
 static void dzero(void *d, size_t n) { if (n) CUDA_OK(cudaMemsetAsync(d, 0, n, t_stream)); }
 static void d2d(void *d, const void *s, size_t n) { if (n) CUDA_OK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, t_stream)); }
 static void dfill(void *d, int v, size_t n) { if (n) CUDA_OK(cudaMemsetAsync(d, v, n, t_stream)); }
-static int dev_sm_count() { static int v = 0; if (v == 0) CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, (int)p_device)); return v; }
+static int dev_sm_count() { static int v = 0; if (v == 0) { int d = 0; CUDA_OK(cudaGetDevice(&d)); CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d)); } return v; } // (the devices of one box are alike)
 static size_t dev_free_mem() { size_t f = 0, t = 0; CUDA_OK(cudaMemGetInfo(&f, &t)); return f; }
 #endif
 
@@ -429,6 +431,91 @@ static void pack_results(const PackArgs &P)
 #endif
 }
 
+// ---- reads cross PCIe 2 bits per base ----
+// Host: A/C/G/T -> 0..3 (the order of seq_nt4_table, sketch.c:9-26), 32 bases per 64-bit word, base i in bits 2*(i%32).  Returns false
+// when the read holds any other byte (N, lower case, IUPAC): such a read travels as ASCII, because the alignment compares raw bytes.
+static bool pack_read_scalar(const char *s, int len, uint64_t *out)
+{
+	static uint8_t tab[256];
+	static bool init = false;
+	if (!init) { for (int i = 0; i < 256; ++i) tab[i] = 4; tab['A'] = 0, tab['C'] = 1, tab['G'] = 2, tab['T'] = 3; init = true; }
+	unsigned bad = 0;
+	for (int w = 0; w * 32 < len; ++w) {
+		uint64_t x = 0;
+		const int n = len - w * 32 < 32? len - w * 32 : 32;
+		for (int j = 0; j < n; ++j) { const unsigned c = tab[(uint8_t)s[w * 32 + j]]; bad |= c; x |= (uint64_t)(c & 3) << (2 * j); }
+		out[w] = x;
+	}
+	return (bad & 4) == 0;
+}
+#if defined(__x86_64__) && !defined(MGB_NO_SIMD_PACK)
+#include <immintrin.h>
+// 16 bases per step: code = (b >> 1 & 3) with G and T swapped back, checked by mapping the codes to letters again
+__attribute__((target("ssse3,sse4.1,bmi2"))) static bool pack_read_simd(const char *s, int len, uint64_t *out)
+{
+	const __m128i letters = _mm_setr_epi8('A', 'C', 'G', 'T', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0), three = _mm_set1_epi8(3), one = _mm_set1_epi8(1);
+	int i = 0;
+	unsigned ok = 0xffffu;
+	for (; i + 32 <= len; i += 32) {
+		uint64_t word = 0;
+		for (int h = 0; h < 2; ++h) {
+			const __m128i x = _mm_loadu_si128((const __m128i*)(s + i + 16 * h));
+			__m128i c = _mm_and_si128(_mm_srli_epi16(x, 1), three);              // A0 C1 T2 G3
+			c = _mm_xor_si128(c, _mm_and_si128(_mm_srli_epi16(c, 1), one));       // A0 C1 G2 T3
+			ok &= (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_shuffle_epi8(letters, c), x));
+			const uint64_t lo = _pext_u64((uint64_t)_mm_cvtsi128_si64(c), 0x0303030303030303ULL), hi = _pext_u64((uint64_t)_mm_extract_epi64(c, 1), 0x0303030303030303ULL);
+			word |= (lo | hi << 16) << (32 * h);
+		}
+		out[i >> 5] = word;
+	}
+	bool good = ok == 0xffffu;
+	if (i < len) good &= pack_read_scalar(s + i, len - i, out + (i >> 5));
+	return good;
+}
+static bool pack_read(const char *s, int len, uint64_t *out)
+{
+	static const bool simd = __builtin_cpu_supports("ssse3") && __builtin_cpu_supports("bmi2") && __builtin_cpu_supports("sse4.1");
+	return simd? pack_read_simd(s, len, out) : pack_read_scalar(s, len, out);
+}
+#else
+static bool pack_read(const char *s, int len, uint64_t *out) { return pack_read_scalar(s, len, out); }
+#endif
+
+// Device: the ASCII copy of the packed reads (alignment, ds strings and the sequential sketch read bytes): one 64-bit word = 32 bases =
+// two 16-byte stores per lane, a warp per read.
+struct UnpackArgs { const uint64_t *pk, *pk_off, *seq_off; const int32_t *seq_len; char *seq; int n_reads; };
+MG_HD inline void unpack_word(const UnpackArgs &U, int r, int64_t wd)
+{
+	const int32_t len = U.seq_len[r];
+	const uint64_t x = U.pk[U.pk_off[r] + (uint64_t)wd];
+	uint32_t q[8];
+	for (int j = 0; j < 8; ++j) { // four bases -> four letters: 'A' + {0, 2, 6, 19}
+		uint32_t o = 0;
+		for (int b = 0; b < 4; ++b) { const uint32_t c = (uint32_t)(x >> (2 * (4 * j + b))) & 3u; o |= (0x41u + ((0x13060200u >> (8 * c)) & 0xffu)) << (8 * b); }
+		q[j] = o;
+	}
+	uint32_t *dst = (uint32_t*)(U.seq + U.seq_off[r] + (uint64_t)wd * 32);
+	for (int h = 0; h < 2; ++h) // a half that starts at or behind the end of the read is not the read's to write
+		if (wd * 32 + 16 * h < (int64_t)len) {
+#if MGB_ON_DEVICE
+			*(uint4*)(dst + 4 * h) = make_uint4(q[4 * h], q[4 * h + 1], q[4 * h + 2], q[4 * h + 3]);
+#else
+			for (int j = 0; j < 4; ++j) dst[4 * h + j] = q[4 * h + j];
+#endif
+		}
+}
+#ifndef MGB_HOSTSIM
+__global__ void __launch_bounds__(256) k_unpack(UnpackArgs U)
+{
+	const int lane = threadIdx.x & 31, warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), n_warp = (int)((gridDim.x * blockDim.x) >> 5);
+	for (int r = warp; r < U.n_reads; r += n_warp) {
+		if (U.pk_off[r] == ~0ULL) continue; // uploaded as ASCII
+		const int64_t nw = ((int64_t)U.seq_len[r] + 31) >> 5;
+		for (int64_t wd = lane; wd < nw; wd += 32) unpack_word(U, r, wd);
+	}
+}
+#endif
+
 struct Workers {
 	int n_workers;
 	uint64_t arena_bytes;
@@ -519,7 +606,7 @@ struct Model {
 	// the batch pipeline: a batch is cut into sub-batches, each driven by its own host thread on its own stream ("slot"),
 	// so that kernels, copies and host-side result assembly of different sub-batches overlap
 	struct Slot {
-		GrowBuf h_seq{true}, h_out{true}, h_small{true}, d_seq, d_meta, d_routs, d_small, d_jobq, d_order, d_packed, d_packoff, d_segs, d_lab_new, d_pool[10];
+		GrowBuf h_seq{true}, h_out{true}, h_small{true}, h_pk{true}, d_pk, d_seq, d_meta, d_routs, d_small, d_jobq, d_order, d_packed, d_packoff, d_segs, d_lab_new, d_pool[10];
 		mgb::HostPool host_pool; // packing and result assembly of the batch on this slot
 		Workers W;
 		mgb_stats_t st;
@@ -535,6 +622,8 @@ struct Model {
 	Slot slots[MAX_SLOTS];
 	std::mutex big_mutex; // the large-arena retry pass, the label table and the learned routing are shared by the slots
 	std::condition_variable slot_cv;
+	int device = 0;               // the GPU this image lives on
+	std::vector<Model*> peers;    // MGB_DEVICES: the same index on further GPUs; a batch is cut into one contiguous part per device
 	bool slot_busy[MAX_SLOTS] = {};
 	int in_flight = 0;    // calls inside map_batch_impl
 	// reachability labels of the graph (mgb_gclabel.cuh): built on demand, kept across batches, grown between them
@@ -544,6 +633,11 @@ struct Model {
 
 static void model_free(Model *M)
 {
+	for (Model *P : M->peers) model_free(P);
+	M->peers.clear();
+#ifndef MGB_HOSTSIM
+	cudaSetDevice(M->device);
+#endif
 	for (void *p : M->dev_ptrs) dfree(p);
 	if (M->W.arena) dfree(M->W.arena);
 	if (M->W.peak) dfree(M->W.peak);
@@ -553,7 +647,7 @@ static void model_free(Model *M)
 	dfree(M->d_lab_off), dfree(M->d_lab_hdr), dfree(M->d_lab_pool);
 	for (int k = 0; k < Model::MAX_SLOTS; ++k) {
 		Model::Slot &sl = M->slots[k];
-		sl.h_seq.release(), sl.h_out.release(), sl.h_small.release(), sl.d_seq.release(), sl.d_meta.release(), sl.d_routs.release(), sl.d_small.release(), sl.d_jobq.release(), sl.d_order.release(), sl.d_packed.release(), sl.d_packoff.release(), sl.d_segs.release(), sl.d_lab_new.release();
+		sl.h_seq.release(), sl.h_out.release(), sl.h_small.release(), sl.h_pk.release(), sl.d_pk.release(), sl.d_seq.release(), sl.d_meta.release(), sl.d_routs.release(), sl.d_small.release(), sl.d_jobq.release(), sl.d_order.release(), sl.d_packed.release(), sl.d_packoff.release(), sl.d_segs.release(), sl.d_lab_new.release();
 		for (int i = 0; i < 10; ++i) sl.d_pool[i].release();
 		if (sl.W.arena) dfree(sl.W.arena);
 		if (sl.W.peak) dfree(sl.W.peak);
@@ -751,7 +845,23 @@ extern "C" const uint64_t *mg_idx_get(const mg_idx_t *gi, uint64_t minier, int *
 extern "C" mg_idx_t *mg_index(gfa_t *g, const mg_idxopt_t *io, int n_threads, mg_mapopt_t *mo)
 {
 	(void)n_threads;
-	if (!dev_ok()) { set_error("no CUDA device available: libmgb200 has no CPU path"); return 0; }
+	// MGB_DEVICES=0-7 | 0,2,5: the index is replicated on every listed GPU and each batch is cut into one part per GPU (the reference's
+	// "-t": gmap.c:163-211 hands its mini-batch to n_threads workers; here the workers are devices).  Unset: the "device" parameter.
+	std::vector<int> devs;
+	if (const char *e = getenv("MGB_DEVICES")) {
+		for (const char *q = e; *q;) {
+			char *end;
+			long a = strtol(q, &end, 10), b2 = a;
+			if (end == q) break;
+			if (*end == '-') { q = end + 1; b2 = strtol(q, &end, 10); }
+			for (long d = a; d <= b2 && devs.size() < 64; ++d) devs.push_back((int)d);
+			q = *end == ','? end + 1 : end;
+			if (*end && *end != ',') break;
+		}
+	}
+	if (devs.empty()) devs.push_back((int)p_device);
+	for (int d : devs) if (!dev_ok(d)) { set_error("no CUDA device " + std::to_string(d) + " available: libmgb200 has no CPU path"); return 0; }
+	dev_ok(devs[0]);
 	for (uint32_t i = 0; i < g->n_seg; ++i) { // reference: index.c:215-220
 		gfa_seg_t *s = &g->seg[i];
 		for (int32_t j = 0; j < s->len; ++j)
@@ -766,6 +876,15 @@ extern "C" mg_idx_t *mg_index(gfa_t *g, const mg_idxopt_t *io, int n_threads, mg
 	if (k * 2 < b) b = k * 2;
 	if (w < 1) w = 1;
 	Model *M = model_build(g, k, w);
+	M->device = devs[0];
+	if (devs.size() > 1) { // every further device builds its own copy (sketch on that device, table on the host), all at once
+		M->peers.resize(devs.size() - 1, (Model*)0);
+		std::vector<std::thread> th;
+		for (size_t i = 1; i < devs.size(); ++i)
+			th.emplace_back([&, i]() { if (dev_ok(devs[i])) { M->peers[i - 1] = model_build(g, k, w); M->peers[i - 1]->device = devs[i]; } });
+		for (auto &t : th) t.join();
+		dev_ok(devs[0]);
+	}
 	mg_idx_t *gi = (mg_idx_t*)calloc(1, sizeof(mg_idx_t));
 	gi->g = g, gi->b = b, gi->w = w, gi->k = k, gi->n_seg = (int32_t)g->n_seg;
 	gi->B = (struct mg_idx_bucket_s*)M;
@@ -974,7 +1093,53 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	enum { P_ANCHOR, P_MINIPOS, P_LCHAIN, P_OUT, P_PLAN, P_JOBS, P_CIG, P_GSTATE, P_GJOBS, P_WALK, N_POOLS };
 	char *d_seq = (char*)sl.d_seq.ensure(hseq_bytes);
 	tm_h2d.start();
-	{ // pack and upload in a few pieces: the copy of one piece runs while the host threads pack the next
+	// The reads go up 2 bits per base (a quarter of the bytes) and k_unpack writes their ASCII copy on the device; a read with any
+	// byte other than A/C/G/T goes up as ASCII, and so does the whole batch when such reads are many or the fragments have segments.
+	uint64_t *pk_off = 0, *d_pk = 0, *d_pk_off = 0;
+	bool packed_mode = p_pack2 && seg_off == 0;
+	if (packed_mode) {
+		pk_off = (uint64_t*)sl.h_pk.ensure((size_t)n_reads * 8 + 64 + (size_t)(S.n_bases / 4) + (size_t)n_reads * 16);
+		uint64_t wtot = 0;
+		for (int i = 0; i < n_reads; ++i) { pk_off[i] = wtot; wtot += (uint64_t)((qlens[i] > 0? qlens[i] : 0) + 31) / 32 + 1; }
+		uint64_t *hpk = pk_off + (((size_t)n_reads + 7) & ~(size_t)7);
+		d_pk_off = (uint64_t*)sl.d_pk.ensure(((((size_t)n_reads + 7) & ~(size_t)7) + wtot + 8) * 8);
+		d_pk = d_pk_off + (((size_t)n_reads + 7) & ~(size_t)7);
+		std::vector<uint8_t> raw((size_t)n_reads, 0);
+		const int n_piece = n_reads >= 2048? 4 : 1;
+		double t_pack = 0;
+		for (int pc = 0; pc < n_piece; ++pc) {
+			const int64_t r0 = (int64_t)n_reads * pc / n_piece, r1 = (int64_t)n_reads * (pc + 1) / n_piece;
+			if (r0 >= r1) continue;
+			const double tp0 = now_ms();
+			pfor(r1 - r0, [&](int64_t i) { const int64_t r = r0 + i; if (qlens[r] > 0 && !pack_read(seqs[r], qlens[r], hpk + pk_off[r])) raw[(size_t)r] = 1; });
+			t_pack += now_ms() - tp0;
+			const uint64_t w0 = pk_off[r0], w1 = r1 < n_reads? pk_off[r1] : wtot;
+#ifndef MGB_HOSTSIM
+			CUDA_OK(cudaMemcpyAsync(d_pk + w0, hpk + w0, (w1 - w0) * 8, cudaMemcpyHostToDevice, t_stream));
+#else
+			memcpy(d_pk + w0, hpk + w0, (w1 - w0) * 8);
+#endif
+		}
+		int64_t n_raw = 0;
+		for (int i = 0; i < n_reads; ++i) n_raw += raw[(size_t)i];
+		if (n_raw > 64) packed_mode = false; // not worth a copy per read
+		else {
+			S.t_pack_ms = t_pack;
+			S.h2d_bytes = (int64_t)(wtot * 8);
+			for (int i = 0; i < n_reads; ++i)
+				if (raw[(size_t)i]) {
+					memcpy(hseq + seq_off[i], seqs[i], (size_t)qlens[i]);
+#ifndef MGB_HOSTSIM
+					CUDA_OK(cudaMemcpyAsync(d_seq + seq_off[i], hseq + seq_off[i], (size_t)qlens[i], cudaMemcpyHostToDevice, t_stream));
+#else
+					memcpy(d_seq + seq_off[i], hseq + seq_off[i], (size_t)qlens[i]);
+#endif
+					pk_off[i] = ~0ULL, S.h2d_bytes += qlens[i];
+				}
+			h2d(d_pk_off, pk_off, (size_t)n_reads * 8);
+		}
+	}
+	if (!packed_mode) { // pack and upload in a few pieces: the copy of one piece runs while the host threads pack the next
 		const int n_piece = n_reads >= 2048? 4 : 1;
 		double t_pack = 0;
 		for (int pc = 0; pc < n_piece; ++pc) {
@@ -991,7 +1156,8 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 #endif
 		}
 		dsync();
-		S.t_pack_ms = t_pack;
+		S.t_pack_ms += t_pack;
+		S.h2d_bytes = (int64_t)hseq_bytes;
 	}
 	size_t small_dev = (size_t)n_reads * (8 + 4 + 4 + 4 + 4 + 4) + 4096 + 1024;
 	char *ds = (char*)sl.d_small.ensure(small_dev);
@@ -1009,6 +1175,18 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	Pool *d_pools = (Pool*)(dsm + 64 + sizeof(unsigned long long) * PROF_N);
 	unsigned int *d_tier_hist = (unsigned int*)((char*)(d_pools + 16) + 64); // 32 x 4 counters behind the pool headers
 	h2d(d_seq_off, seq_off, (size_t)n_reads * 16); // seq_off, seq_len and name_hash are contiguous on both sides
+	S.h2d_bytes += (int64_t)n_reads * 16;
+	if (packed_mode) {
+		UnpackArgs U;
+		U.pk = d_pk, U.pk_off = d_pk_off, U.seq_off = d_seq_off, U.seq_len = d_seq_len, U.seq = d_seq, U.n_reads = n_reads;
+#ifndef MGB_HOSTSIM
+		k_unpack<<<dev_sm_count() * 8, 256, 0, t_stream>>>(U);
+		CUDA_OK(cudaGetLastError());
+#else
+		for (int r = 0; r < n_reads; ++r) if (pk_off[r] != ~0ULL) for (int64_t wd = 0; wd * 32 < qlens[r]; ++wd) unpack_word(U, r, wd);
+#endif
+		S.n_launches += 1;
+	}
 	tm_h2d.stop();
 	const bool no_diag = (o.flag & F_NO_DIAG) != 0;
 	if (no_diag) { // which segment name, if any, is the read's own (exact string match on the host)
@@ -1064,6 +1242,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 		L.c.g = M->g, L.c.ix = M->ix, L.c.opt = o;
 		L.c.b.n_reads = n_reads, L.c.b.seq = d_seq, L.c.b.seq_off = d_seq_off, L.c.b.seq_len = d_seq_len, L.c.b.name_hash = d_name_hash;
 		L.c.b.seg_off = d_seg_off, L.c.b.seg_len = d_seg_len, L.c.b.self_id = no_diag? d_self_id : 0;
+		L.c.b.pk = packed_mode? d_pk : 0, L.c.b.pk_off = packed_mode? d_pk_off : 0;
 		L.c.meta = d_meta;
 		L.c.pool_anchor = &d_pools[P_ANCHOR], L.c.anchor = (u128*)d_buf[P_ANCHOR];
 		L.c.pool_minipos = &d_pools[P_MINIPOS], L.c.minipos = (int32_t*)d_buf[P_MINIPOS];
@@ -1330,10 +1509,9 @@ static thread_local bool t_has_stats = false;
 // One call = one slot: its own stream, staging buffers, pools and worker arenas.  Up to "slots" calls run at once on one index
 // (callers beyond that wait), so a host that maps mini-batch i+1 on a second thread overlaps its packing, copies and result
 // assembly with the kernels of mini-batch i -- what the reference's kt_pipeline does with its step threads (gmap.c:176).
-static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, const char *const *seqs, const char *const *names,
-						  mg_gchains_t **gcs, const mg_mapopt_t *opt, const std::vector<int32_t> *seg_off = 0, const std::vector<int32_t> *seg_len = 0)
+static int map_batch_on(Model *M, int n_reads, const int *qlens, const char *const *seqs, const char *const *names,
+						mg_gchains_t **gcs, const mg_mapopt_t *opt, const std::vector<int32_t> *seg_off = 0, const std::vector<int32_t> *seg_len = 0)
 {
-	Model *M = (Model*)gi->B;
 	for (int i = 0; i < n_reads; ++i) gcs[i] = 0;
 	if (n_reads <= 0) return 0;
 	double t0 = now_ms();
@@ -1350,7 +1528,7 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 	Model::Slot &sl = M->slots[k];
 	const double t_slot = now_ms();
 #ifndef MGB_HOSTSIM
-	cudaSetDevice((int)p_device);
+	cudaSetDevice(M->device);
 #endif
 	int rc = 0;
 	{
@@ -1400,6 +1578,42 @@ static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, con
 		return rc;
 	}
 	return 0;
+}
+
+// The batch on every device of the index: contiguous parts of about equal bases, one host thread per device, results in input order.
+static int map_batch_impl(const mg_idx_t *gi, int n_reads, const int *qlens, const char *const *seqs, const char *const *names,
+						  mg_gchains_t **gcs, const mg_mapopt_t *opt, const std::vector<int32_t> *seg_off = 0, const std::vector<int32_t> *seg_len = 0)
+{
+	Model *M = (Model*)gi->B;
+	const int n_dev = 1 + (int)M->peers.size();
+	if (n_dev == 1 || seg_off || n_reads < 2 * n_dev) return map_batch_on(M, n_reads, qlens, seqs, names, gcs, opt, seg_off, seg_len);
+	for (Model *P : M->peers) if (P == 0) { set_error("the index is missing on one of the MGB_DEVICES"); return MGB_E_INTERNAL; }
+	int64_t tot = 0;
+	for (int i = 0; i < n_reads; ++i) tot += qlens[i] > 0? qlens[i] : 0;
+	std::vector<int> bound((size_t)n_dev + 1, n_reads);
+	bound[0] = 0;
+	{
+		int64_t acc = 0; int k = 1;
+		for (int i = 0; i < n_reads && k < n_dev; ++i) {
+			acc += qlens[i] > 0? qlens[i] : 0;
+			if (acc >= tot * k / n_dev) bound[(size_t)k++] = i + 1;
+		}
+	}
+	std::vector<int> rcs((size_t)n_dev, 0);
+	std::vector<std::thread> th;
+	for (int d = 0; d < n_dev; ++d)
+		th.emplace_back([&, d]() {
+			const int b = bound[(size_t)d], e = bound[(size_t)d + 1];
+			if (e > b) rcs[(size_t)d] = map_batch_on(d == 0? M : M->peers[(size_t)d - 1], e - b, qlens + b, seqs + b, names? names + b : 0, gcs + b, opt);
+		});
+	for (auto &t : th) t.join();
+	int rc = 0;
+	for (int d = 0; d < n_dev; ++d) if (rcs[(size_t)d] < 0 && rc == 0) rc = rcs[(size_t)d];
+	if (rc < 0) for (int i = 0; i < n_reads; ++i) if (gcs[i]) { mg_gchain_free(gcs[i]); gcs[i] = 0; } // no partial results are left behind
+#ifndef MGB_HOSTSIM
+	cudaSetDevice(M->device);
+#endif
+	return rc;
 }
 
 extern "C" int mg_map_batch(const mg_idx_t *gi, int n_reads, const int *qlens, const char *const *seqs, const char *const *names,

@@ -123,6 +123,10 @@ struct BatchDev {
 	// segments, seg_len[seg_off[r] .. seg_off[r+1]) their lengths.  NULL for the usual batch of single-segment reads.
 	const int32_t *seg_off;     // [n_reads + 1]
 	const int32_t *seg_len;
+	// the reads as they cross PCIe: 2 bits per base (A/C/G/T only; k_unpack writes the ASCII copy above, the sketch reads the codes).
+	// NULL when the batch was uploaded as ASCII (reads with other letters in it)
+	const uint64_t *pk;         // 32 bases per word; a read's words start at pk_off[r]
+	const uint64_t *pk_off;     // [n_reads] word offsets
 };
 MG_HD inline int32_t batch_n_seg(const BatchDev &b, int rid) { return b.seg_off? b.seg_off[rid + 1] - b.seg_off[rid] : 1; }
 

@@ -96,7 +96,7 @@ MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A, int lane, int32
 	unsigned long long t0 = prof_clock();
 	const int32_t n_seg = batch_n_seg(c.b, rid);
 	if (n_seg == 1) {
-		MGB_TRY(sketch_seq_w(A, seq, qlen, c.ix.w, c.ix.k, 0, mv, lane, (u128*)smem));
+		MGB_TRY(sketch_seq_w(A, seq, qlen, c.ix.w, c.ix.k, 0, mv, lane, (u128*)smem, c.b.pk && c.b.pk_off[rid] != ~0ULL? c.b.pk + c.b.pk_off[rid] : 0)); // (a read with letters other than A/C/G/T came up as ASCII)
 	} else { // reference: map-algo.c:34-45 collect_minimizers: every segment on its own, positions shifted by the lengths before it
 		const int32_t *sl = c.b.seg_len + c.b.seg_off[rid];
 		MGB_ALLOC(A, mv.a, u128, (int64_t)qlen + 16 * (int64_t)n_seg);

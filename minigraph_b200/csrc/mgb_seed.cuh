@@ -77,8 +77,10 @@ static const int SKETCH_CHUNKS = 32;
 
 // BS: distance between two slots of the window ring (1: a private ring in the arena; 32: the rings of the 32 lanes interleaved in
 // shared memory, slot j of lane l at [j * 32 + l], so that the lanes of a warp touch consecutive 16-byte words)
-template<int BS = 1>
-MG_HD inline int sketch_chunk(const char *str, int w, int k, uint32_t rid, int p, int end, int is_first, int is_last, u128 *buf, u128 *outp, int cap, int *n_out)
+// PK: the bases come 2 bits each from `pk` (32 per 64-bit word, base i in bits 2*(i%32).. of word i/32; no ambiguous base by
+// construction), one 8-byte load per 32 bases, instead of one byte each from `str`
+template<int BS = 1, int PK = 0>
+MG_HD inline int sketch_chunk(const char *str, const uint64_t *pk, int w, int k, uint32_t rid, int p, int end, int is_first, int is_last, u128 *buf, u128 *outp, int cap, int *n_out)
 {
 	const uint64_t shift1 = 2 * (k - 1), mask = (1ULL << 2 * k) - 1;
 	uint64_t kmer[2] = {0, 0};
@@ -89,7 +91,7 @@ MG_HD inline int sketch_chunk(const char *str, int w, int k, uint32_t rid, int p
 	if (!is_first) {
 		i0 = p - w;
 		for (int i = i0 - k + 1; i < i0; ++i) { // the k-1 bases in front of the first warm-up slot
-			int c = nt4((uint8_t)str[i]);
+			int c = PK? (int)(pk[i >> 5] >> ((i & 31) << 1) & 3) : nt4((uint8_t)str[i]);
 			if (c >= 4) return 1;
 			kmer[0] = (kmer[0] << 2 | (uint64_t)c) & mask;
 			kmer[1] = (kmer[1] >> 2) | (3ULL ^ (uint64_t)c) << shift1;
@@ -97,8 +99,14 @@ MG_HD inline int sketch_chunk(const char *str, int w, int k, uint32_t rid, int p
 		l = w + k + 1; // any value the thresholds below cannot tell from the true one
 	}
 #define MGB_SK_PUSH(v) do { if (i >= p) { if (n >= cap) return 1; outp[n++] = (v); } } while (0)
+	uint64_t word = 0;
+	if (PK && i0 < end) word = pk[i0 >> 5] >> ((i0 & 31) << 1);
 	for (int i = i0; i < end; ++i) {
-		int c = nt4((uint8_t)str[i]);
+		int c;
+		if (PK) {
+			if ((i & 31) == 0) word = pk[i >> 5];
+			c = (int)(word & 3), word >>= 2;
+		} else c = nt4((uint8_t)str[i]);
 		u128 info = none;
 		if (c >= 4) return 1;
 		kmer_span = l + 1 < k? l + 1 : k;
@@ -148,7 +156,8 @@ static const int SKETCH_SMEM_W = 12; // widest window whose rings fit the shared
 static const int SKETCH_SMEM_BYTES = SKETCH_SMEM_W * 32 * 16; // per warp
 
 // sring: NULL, or SKETCH_SMEM_BYTES of shared memory of this warp for the window rings
-MG_HD inline int sketch_seq_w(Arena &A, const char *str, int len, int w, int k, uint32_t rid, AVec<u128> &out, int lane, u128 *sring = 0)
+// pk: NULL, or the sequence 2 bits per base (see sketch_chunk); str is always there (the sequential scan below reads it)
+MG_HD inline int sketch_seq_w(Arena &A, const char *str, int len, int w, int k, uint32_t rid, AVec<u128> &out, int lane, u128 *sring = 0, const uint64_t *pk = 0)
 {
 	if (!(len > 0 && w > 0 && w < 256 && k > 0 && k <= 28)) return MGB_E_INTERNAL;
 	const int min_chunk = w + 2 * k > 64? w + 2 * k : 64;
@@ -166,8 +175,10 @@ MG_HD inline int sketch_seq_w(Arena &A, const char *str, int len, int w, int k, 
 			const int p = c * chunk, e = p + chunk < len? p + chunk : len;
 			int n = 0;
 			if (p < e) {
-				if (sring && w <= SKETCH_SMEM_W) fail |= sketch_chunk<32>(str, w, k, rid, p, e, c == 0, e == len, sring + lane, tmp + (int64_t)c * cap, cap, &n);
-				else fail |= sketch_chunk<1>(str, w, k, rid, p, e, c == 0, e == len, ring + (int64_t)c * w, tmp + (int64_t)c * cap, cap, &n);
+				if (sring && w <= SKETCH_SMEM_W) {
+					if (pk) fail |= sketch_chunk<32, 1>(str, pk, w, k, rid, p, e, c == 0, e == len, sring + lane, tmp + (int64_t)c * cap, cap, &n);
+					else fail |= sketch_chunk<32, 0>(str, pk, w, k, rid, p, e, c == 0, e == len, sring + lane, tmp + (int64_t)c * cap, cap, &n);
+				} else fail |= sketch_chunk<1, 0>(str, pk, w, k, rid, p, e, c == 0, e == len, ring + (int64_t)c * w, tmp + (int64_t)c * cap, cap, &n);
 			}
 			cnt[c] = n;
 		}

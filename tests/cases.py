@@ -394,6 +394,36 @@ def case_concurrent_calls(lib, workdir, n_threads=3, n_reads=90):
     lib.mgb_gfa_destroy(g)
 
 
+def case_upload_modes(lib, workdir, n_reads=80):
+    """how the reads reach the device does not change what comes back: 2 bits per base (all A/C/G/T), the same with a few reads that
+    hold N or lower-case letters (those travel as ASCII beside the packed ones), the whole batch as ASCII (many such reads), and the
+    pack2=0 switch; every field against the reference, whose alignment compares raw bytes (N matches N, 'a' does not match 'A')"""
+    pre, reads = os.path.join(workdir, "svu"), os.path.join(workdir, "svu.reads.fa")
+    T.sim_graph(pre, 300000, 3, 29)
+    T.sim_reads(pre + ".hap.fa", reads, n_reads, 6000, "ont", 67)
+    names, seqs = T.read_fasta(reads)
+
+    def spoil(s, k):
+        b = bytearray(s)
+        b[1000 + k] = ord("N")
+        b[3000:3004] = b[3000:3004].lower()
+        return bytes(b)
+    few = [spoil(s, i) if i % 29 == 0 else s for i, s in enumerate(seqs)]
+    many = [spoil(s, i) for i, s in enumerate(seqs)]
+    try:
+        for tag, ss, pack in (("packed", seqs, 1), ("few", few, 1), ("many", many, 1), ("switch", seqs, 0)):
+            assert lib.mgb_set_param(b"pack2", pack) == 0
+            want, _ = T.map_with_ref(pre + ".gfa", names, ss, "lr")
+            got, _, st = T.map_with_engine(lib, pre + ".gfa", names, ss, "lr")
+            bases = sum(len(x) for x in ss)
+            assert (st.h2d_bytes < bases // 2) == (tag in ("packed", "few")), (tag, st.h2d_bytes, bases)
+            for i, (a, b) in enumerate(zip(want, got)):
+                d = T.diff_results(a, b)
+                assert d is None, "%s read %d: %s" % (tag, i, d)
+    finally:
+        lib.mgb_set_param(b"pack2", 1)
+
+
 def case_tier_routing(lib, workdir, n_reads=120):
     """the WFA tier thresholds learned from one batch route the gaps of the next: same results, and the routing did engage"""
     import ctypes as C

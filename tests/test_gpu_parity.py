@@ -59,6 +59,11 @@ def test_engine_switches_keep_results(lib, workdir):
     cases.case_switches(lib, workdir, device=True)
 
 
+@pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not there")
+def test_upload_modes(lib, workdir):
+    cases.case_upload_modes(lib, workdir)
+
+
 def test_concurrent_callers(lib, workdir):
     cases.case_concurrent_calls(lib, workdir)
 
