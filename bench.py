@@ -486,6 +486,7 @@ def main():
                                                                    "large_arena_redo": e2e_acc["w_redo"] / a.steps, "pack_results+d2h": e2e_acc["w_down"] / a.steps, "device_span": e2e_acc["span"] / a.steps},
                              "reads_redone_with_large_arena": e2e_acc["retry"] / a.steps},
         "device_cycles_last_call": {k: (int(st.prof[i]) >> 16 if k in ("wfa_max_cyc", "gwfa_max_cyc") else int(st.prof[i])) for i, k in enumerate(capi.PROF_NAMES)},
+        "arena_peak_bytes_last_call": int(st.arena_peak),
         "wfa_tier_routing": {"skip_tier1_at": int(st.skip1_len), "skip_tier2_at": int(st.skip2_len)},
         "gpu_launches": int(e2e_acc["launches"]),
         "roofline": {"kernel": "k_chain (linear chaining: mg_lchain_dp/rmq + backtrack + compaction)", "bound": "hbm", "achieved": achieved, "peak": peak,

@@ -150,7 +150,10 @@ typedef struct mg_tbuf_s mg_tbuf_t; /* minigraph.h:148, opaque */
 
 /* replaces index.c:211-230 mg_index(): upper-cases the segments of g (index.c:215-220), returns NULL when the graph
  * has overlapping links (index.c:192-196), builds the minimizer index, uploads graph+index to the GPU and updates
- * mo->occ_max1 / lc_max_occ / bw_long exactly like options.c:120-134 mg_opt_update(). n_threads is ignored. */
+ * mo->occ_max1 / lc_max_occ / bw_long exactly like options.c:120-134 mg_opt_update(). n_threads is ignored.
+ * The GPU is the engine parameter "device" (default 0); with the environment variable MGB_DEVICES ("0-7", "0,2,5") the index is
+ * replicated on every listed GPU and each mg_map_batch*() call is cut into one contiguous part per GPU (results in input order).
+ * Returns NULL on failure (no CUDA device, out of device memory, overlapping links) with the reason in mgb_last_error(). */
 mg_idx_t *mg_index(gfa_t *g, const mg_idxopt_t *io, int n_threads, mg_mapopt_t *mo);
 
 /* replaces index.c:30-46 mg_idx_destroy() */
@@ -166,10 +169,6 @@ void mg_idx_cal_quantile(const mg_idx_t *gi, int32_t m, float f[], int32_t q[]);
  * (shortk.c:191, always with a NULL handle); a no-op here */
 void mg_idx_hfree(void *h);
 
-/* replaces index.c:108-113 mg_idx_hfree(): the one other index.c symbol the remaining host files reference
- * (shortk.c:191, always with a NULL handle); a no-op here */
-void mg_idx_hfree(void *h);
-
 /* replace map-algo.c:14-27 mg_tbuf_init()/mg_tbuf_destroy(): the per-thread arena becomes a handle without state */
 mg_tbuf_t *mg_tbuf_init(void);
 void mg_tbuf_destroy(mg_tbuf_t *b);
@@ -177,7 +176,11 @@ void mg_tbuf_destroy(mg_tbuf_t *b);
 /* replaces map-algo.c:340-495 mg_map_frag(): gcs[0] receives a malloc()ed result owned by the caller (free with
  * mg_gchain_free), or NULL when the fragment is empty, has more than 255 segments or is longer than opt->max_qlen
  * (map-algo.c:359-360); gcs[i>0] = NULL. With n_segs > 1 the concatenated fragment is mapped and no CIGAR is produced
- * (map-algo.c:34-45,464,475). One fragment per launch: correct but slow -- use mg_map_batch for single-segment reads. */
+ * (map-algo.c:34-45,464,475). One fragment per launch: correct but slow -- use mg_map_batch for single-segment reads.
+ * Re-entrancy: like the reference's (which needs one mg_tbuf_t per thread, map-algo.c:9-12), any number of host threads may call
+ * mg_map_frag()/mg_map()/mg_map_batch*() on one mg_idx_t at the same time.  Every call in flight owns a "slot" (stream, staging
+ * buffers, pools, worker arenas); at most "slots" calls (engine parameter, default 3) run at once, further callers wait.
+ * This entry point has no error return (the reference's has none): an internal failure ends the process as an assert would. */
 void mg_map_frag(const mg_idx_t *gi, int n_segs, const int *qlens, const char **seqs, mg_gchains_t **gcs, mg_tbuf_t *b, const mg_mapopt_t *opt, const char *qname);
 
 /* replaces map-algo.c:497-502 mg_map() */
@@ -192,7 +195,10 @@ void mg_gchain_free(mg_gchains_t *gs);
 
 /* Map n_reads single-segment reads in one go. seqs[i] must be upper-case (gmap.c:81) and need not be 0-terminated;
  * names[i] may be NULL. gcs[i] is filled exactly as worker_for() (gmap.c:29-64) would fill s->gcs[off].
- * Returns 0, or a negative code after printing the reason (no partial results are left behind). */
+ * Returns 0, or a negative code after printing the reason (no partial results are left behind; a CUDA failure -- out of memory,
+ * a fault -- is reported this way too, the library never ends the process from here).  A host that maps mini-batch i+1 from a
+ * second thread while the first is still inside the call for mini-batch i overlaps packing, copies and result assembly of one
+ * with the kernels of the other, as the reference's kt_pipeline overlaps its steps (gmap.c:176-177). */
 int mg_map_batch(const mg_idx_t *gi, int n_reads, const int *qlens, const char *const *seqs, const char *const *names,
 				 mg_gchains_t **gcs, const mg_mapopt_t *opt);
 

@@ -56,12 +56,12 @@ MG_D inline void warp_sync() { __syncwarp(); }
 MG_D inline int warp_any(int pred) { return __any_sync(0xffffffffu, pred); }
 MG_D inline int32_t warp_bcast_i32(int32_t x, int src) { return __shfl_sync(0xffffffffu, x, src); }
 MG_D inline uint64_t warp_bcast_u64(uint64_t x, int src) { return __shfl_sync(0xffffffffu, x, src); }
-MG_D inline int32_t warp_min_i32(int32_t x) { for (int o = 16; o > 0; o >>= 1) { int32_t y = __shfl_xor_sync(0xffffffffu, x, o); x = y < x? y : x; } return x; }
-MG_D inline int32_t warp_max_i32(int32_t x) { for (int o = 16; o > 0; o >>= 1) { int32_t y = __shfl_xor_sync(0xffffffffu, x, o); x = y > x? y : x; } return x; }
-MG_D inline int32_t warp_sum_i32(int32_t x) { for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o); return x; }
+MG_D inline int32_t warp_min_i32(int32_t x) { return __reduce_min_sync(0xffffffffu, x); } // one REDUX instead of five shuffle + select steps
+MG_D inline int32_t warp_max_i32(int32_t x) { return __reduce_max_sync(0xffffffffu, x); }
+MG_D inline int32_t warp_sum_i32(int32_t x) { return __reduce_add_sync(0xffffffffu, x); }
 MG_D inline uint32_t warp_ballot(int pred) { return __ballot_sync(0xffffffffu, pred); }
-MG_D inline uint64_t warp_or_u64(uint64_t x) { for (int o = 16; o > 0; o >>= 1) x |= __shfl_xor_sync(0xffffffffu, x, o); return x; }
-MG_D inline uint64_t warp_and_u64(uint64_t x) { for (int o = 16; o > 0; o >>= 1) x &= __shfl_xor_sync(0xffffffffu, x, o); return x; }
+MG_D inline uint64_t warp_or_u64(uint64_t x) { return (uint64_t)__reduce_or_sync(0xffffffffu, (uint32_t)(x >> 32)) << 32 | __reduce_or_sync(0xffffffffu, (uint32_t)x); }
+MG_D inline uint64_t warp_and_u64(uint64_t x) { return (uint64_t)__reduce_and_sync(0xffffffffu, (uint32_t)(x >> 32)) << 32 | __reduce_and_sync(0xffffffffu, (uint32_t)x); }
 MG_D inline void lane_atomic_inc(int32_t *p) { atomicAdd(p, 1); }
 // maximum over this lane and the lanes below it
 MG_D inline uint64_t warp_incl_scan_max_u64(uint64_t x, int lane)
@@ -304,6 +304,45 @@ MG_HD inline uint32_t ld32_unaligned(const char *p)
 #else
 	return sh? (lo >> sh) | (hi << (32 - sh)) : lo;
 #endif
+}
+MG_HD inline int ctz32_nz(uint32_t x)
+{
+#if MGB_ON_DEVICE
+	return __ffs((int)x) - 1;
+#else
+	return __builtin_ctz(x);
+#endif
+}
+// position of the k-th set bit of mask (k >= 1), 32 when there are fewer
+MG_HD inline int nth_set_bit(uint32_t mask, int k)
+{
+#if MGB_ON_DEVICE
+	const unsigned r = __fns(mask, 0, k);
+	return r > 31? 32 : (int)r;
+#else
+	for (int b = 0; b < 32; ++b) if ((mask >> b & 1) && --k == 0) return b;
+	return 32;
+#endif
+}
+// Replay of the "skip" counter of the chaining loops over one chunk of candidates in visiting order (lchain.c:185-190, 336-343):
+// a candidate that improves the best score lowers the counter by one (not below zero), one that is already on a better chain
+// raises it, and the walk stops at the candidate that takes it above max_skip.  imp / mk: lanes of the two kinds.  Returns the
+// lane the walk stops at, or -1; *n_skip is the counter after the chunk (or at the stop).
+MG_HD inline int replay_skips(uint32_t imp, uint32_t mk, int max_skip, int32_t *n_skip)
+{
+	int32_t ns = *n_skip;
+	for (;;) { // one round per improving candidate: the marks in front of it in one step
+		const int nxt = imp? ctz32_nz(imp) : 32;
+		const uint32_t seg = nxt >= 32? mk : mk & ((1u << nxt) - 1u);
+		const int c = mask_count(seg);
+		if (ns + c > max_skip) { *n_skip = max_skip + 1; return nth_set_bit(seg, max_skip - ns + 1); }
+		ns += c;
+		if (nxt >= 32) break;
+		if (ns > 0) --ns;
+		imp &= imp - 1, mk &= ~((2u << nxt) - 1u);
+	}
+	*n_skip = ns;
+	return -1;
 }
 MG_HD inline int ctz32(uint32_t x)
 {

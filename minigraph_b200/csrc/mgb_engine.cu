@@ -78,6 +78,7 @@ extern "C" int mgb_set_param(const char *key, int64_t value)
 // ---------------------------------------------------------------------------------------------------------------
 
 #ifdef MGB_HOSTSIM
+struct MgbError { int code; };
 static bool dev_ok(int dev = -1) { (void)dev; return true; }
 static void *dmalloc(size_t n) { void *p = malloc(n? n : 16); return p; }
 static void dfree(void *p) { free(p); }
@@ -90,7 +91,10 @@ static void dsync() {}
 static int dev_sm_count() { return 2; }
 static size_t dev_free_mem() { return (size_t)8 << 30; }
 #else
-#define CUDA_OK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { set_error(std::string(#call) + ": " + cudaGetErrorString(_e)); abort(); } } while (0)
+// A failed CUDA call (out of memory, a fault in a kernel) unwinds to the C entry point, which returns NULL / a negative code with
+// the reason in mgb_last_error(); the library never ends the host process on its own.
+struct MgbError { int code; };
+#define CUDA_OK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { set_error(std::string(#call) + ": " + cudaGetErrorString(_e)); throw MgbError{MGB_E_INTERNAL}; } } while (0)
 // every host thread that drives a slot of the batch pipeline works on its own stream
 static thread_local cudaStream_t t_stream = 0;
 static bool dev_ok(int dev = -1)
@@ -626,6 +630,7 @@ struct Model {
 	std::vector<Model*> peers;    // MGB_DEVICES: the same index on further GPUs; a batch is cut into one contiguous part per device
 	bool slot_busy[MAX_SLOTS] = {};
 	int in_flight = 0;    // calls inside map_batch_impl
+	bool lab_growing = false; // a call is waiting to replace the label pool: new calls wait
 	// reachability labels of the graph (mgb_gclabel.cuh): built on demand, kept across batches, grown between them
 	long long *d_lab_off = 0; Pool *d_lab_hdr = 0; char *d_lab_pool = 0;
 	uint64_t lab_cap = 0; int32_t lab_max_dist_g = -1; int64_t lab_sources = 0;
@@ -771,7 +776,7 @@ static Model *model_build(gfa_t *g, int k, int w)
 			bool retry = false;
 			if (st0 == MGB_E_POOL) cap *= 2, retry = true;
 			else if (st0 == MGB_E_ARENA) arena_b *= 2, nw = std::max(1, nw / 2), retry = true;
-			else if (st0 < 0) { set_error("segment sketch failed with code " + std::to_string(st0)); abort(); }
+			else if (st0 < 0) { set_error("segment sketch failed with code " + std::to_string(st0)); throw MgbError{st0}; }
 			if (!retry) {
 				mz.resize(hp.used / sizeof(u128));
 				d2h(mz.data(), d_mz, hp.used);
@@ -875,15 +880,17 @@ extern "C" mg_idx_t *mg_index(gfa_t *g, const mg_idxopt_t *io, int n_threads, mg
 	int k = io->k, w = io->w, b = io->bucket_bits;
 	if (k * 2 < b) b = k * 2;
 	if (w < 1) w = 1;
-	Model *M = model_build(g, k, w);
+	Model *M = 0;
+	try { M = model_build(g, k, w); } catch (const MgbError &) { return 0; }
 	M->device = devs[0];
 	if (devs.size() > 1) { // every further device builds its own copy (sketch on that device, table on the host), all at once
 		M->peers.resize(devs.size() - 1, (Model*)0);
 		std::vector<std::thread> th;
 		for (size_t i = 1; i < devs.size(); ++i)
-			th.emplace_back([&, i]() { if (dev_ok(devs[i])) { M->peers[i - 1] = model_build(g, k, w); M->peers[i - 1]->device = devs[i]; } });
+			th.emplace_back([&, i]() { try { if (dev_ok(devs[i])) { M->peers[i - 1] = model_build(g, k, w); M->peers[i - 1]->device = devs[i]; } } catch (const MgbError &) {} });
 		for (auto &t : th) t.join();
 		dev_ok(devs[0]);
+		for (Model *P : M->peers) if (P == 0) { model_free(M); return 0; } // mgb_last_error() has the reason
 	}
 	mg_idx_t *gi = (mg_idx_t*)calloc(1, sizeof(mg_idx_t));
 	gi->g = g, gi->b = b, gi->w = w, gi->k = k, gi->n_seg = (int32_t)g->n_seg;
@@ -1022,7 +1029,7 @@ static bool lab_prepare(Model *M, int32_t max_dist_g)
 	if (M->d_lab_off == 0) {
 		M->d_lab_off = (long long*)dmalloc(n_vtx * sizeof(long long));
 		M->d_lab_hdr = (Pool*)dmalloc(sizeof(Pool));
-		M->lab_cap = std::max<uint64_t>((uint64_t)64 << 20, (uint64_t)n_vtx * 4096);
+		M->lab_cap = std::min<uint64_t>(std::max<uint64_t>((uint64_t)256 << 20, (uint64_t)n_vtx * 8192), std::max<uint64_t>((uint64_t)64 << 20, dev_free_mem() / 16));
 		M->d_lab_pool = (char*)dmalloc(M->lab_cap);
 		M->lab_max_dist_g = -1;
 	}
@@ -1039,11 +1046,15 @@ static bool lab_prepare(Model *M, int32_t max_dist_g)
 // after a batch: a label pool that overflowed is enlarged for the batches to come (the sources that did not fit were searched per read)
 static void lab_after_batch(Model *M, unsigned int n_new)
 {
-	std::lock_guard<std::mutex> lock(M->big_mutex);
+	std::unique_lock<std::mutex> lock(M->big_mutex);
 	M->lab_sources += n_new;
 	Pool hp;
 	d2h(&hp, M->d_lab_hdr, sizeof(Pool));
-	if (hp.used <= hp.cap || M->in_flight > 1) return; // kernels of another call may be reading the pool: grow after a later batch
+	if (hp.used <= hp.cap || M->lab_growing) return;
+	// kernels of other calls may be reading the pool: no new call starts until those in flight are done, then the pool is replaced
+	M->lab_growing = true;
+	M->slot_cv.wait(lock, [&]() { return M->in_flight <= 1; });
+	struct Done { Model *M; ~Done() { M->lab_growing = false; M->slot_cv.notify_all(); } } done{M};
 	const uint64_t want = std::max<uint64_t>((uint64_t)hp.used * 2, M->lab_cap * 2);
 	if (want > dev_free_mem() / 2) return;
 	char *np = (char*)dmalloc(want);
@@ -1521,7 +1532,7 @@ static int map_batch_on(Model *M, int n_reads, const int *qlens, const char *con
 	{ // take a slot
 		std::unique_lock<std::mutex> lk(M->big_mutex);
 		const int max_slots = (int)std::max<int64_t>(1, std::min<int64_t>(p_slots, Model::MAX_SLOTS));
-		M->slot_cv.wait(lk, [&]() { for (int i = 0; i < max_slots; ++i) if (!M->slot_busy[i]) return true; return false; });
+		M->slot_cv.wait(lk, [&]() { if (M->lab_growing) return false; for (int i = 0; i < max_slots; ++i) if (!M->slot_busy[i]) return true; return false; });
 		for (int i = 0; i < max_slots && k < 0; ++i) if (!M->slot_busy[i]) k = i;
 		M->slot_busy[k] = true, ++M->in_flight;
 	}
@@ -1531,7 +1542,7 @@ static int map_batch_on(Model *M, int n_reads, const int *qlens, const char *con
 	cudaSetDevice(M->device);
 #endif
 	int rc = 0;
-	{
+	try {
 		slot_prepare(M, sl, p_slot_workers > 0? (int)p_slot_workers : default_workers());
 #ifndef MGB_HOSTSIM
 		t_stream = sl.stream;
@@ -1556,11 +1567,16 @@ static int map_batch_on(Model *M, int n_reads, const int *qlens, const char *con
 #ifndef MGB_HOSTSIM
 		t_stream = 0; // the slot's stream dies with the model; later calls on this thread (mg_index of another graph) use the default one
 #endif
+	} catch (const MgbError &e) {
+		rc = e.code;
+#ifndef MGB_HOSTSIM
+		t_stream = 0;
+#endif
 	}
 	mgb_stats_t S = sl.st;
 	S.w_slot_wait_ms = t_slot - t0;
 #ifndef MGB_HOSTSIM
-	if (rc == 0) { float a = 0; if (cudaEventElapsedTime(&a, sl.ev_first, sl.ev_last) == cudaSuccess) S.t_dev_span_ms = a; }
+	if (rc == 0 && sl.ready) { float a = 0; if (cudaEventElapsedTime(&a, sl.ev_first, sl.ev_last) == cudaSuccess) S.t_dev_span_ms = a; }
 #else
 	S.t_dev_span_ms = S.t_seed_ms + S.t_chain_ms + S.t_align_ms + S.t_wfa_ms + S.t_finish_ms;
 #endif
@@ -1572,7 +1588,7 @@ static int map_batch_on(Model *M, int n_reads, const int *qlens, const char *con
 		M->stats = S;
 		M->slot_busy[k] = false, --M->in_flight;
 	}
-	M->slot_cv.notify_one();
+	M->slot_cv.notify_all();
 	if (rc < 0) { // no partial results are left behind
 		for (int i = 0; i < n_reads; ++i) if (gcs[i]) { mg_gchain_free(gcs[i]); gcs[i] = 0; }
 		return rc;
@@ -1705,7 +1721,7 @@ MG_HD inline void test_wfa_body(const TestWfaArgs &t, int lane)
 #ifndef MGB_HOSTSIM
 __global__ void k_test_wfa(TestWfaArgs t) { test_wfa_body(t, threadIdx.x & 31); }
 #endif
-extern "C" int mgb_test_wfa(const char *ts, int tl, const char *qs, int ql, int64_t max_iter, int step, uint32_t *cigar, int cap, int *score)
+static int test_wfa_impl(const char *ts, int tl, const char *qs, int ql, int64_t max_iter, int step, uint32_t *cigar, int cap, int *score)
 {
 	if (!dev_ok()) { set_error("no CUDA device available: libmgb200 has no CPU path"); return -100; }
 	TestWfaArgs t;
@@ -1735,6 +1751,11 @@ extern "C" int mgb_test_wfa(const char *ts, int tl, const char *qs, int ql, int6
 	*score = out[2];
 	dfree(d_ts), dfree(d_qs), dfree(t.cigar), dfree(t.out), dfree(t.arena);
 	return out[0] < 0? out[0] : out[1];
+}
+
+extern "C" int mgb_test_wfa(const char *ts, int tl, const char *qs, int ql, int64_t max_iter, int step, uint32_t *cigar, int cap, int *score)
+{
+	try { return test_wfa_impl(ts, tl, qs, ql, max_iter, step, cigar, cap, score); } catch (const MgbError &e) { return e.code; }
 }
 
 extern "C" void mgb_get_stats(const mg_idx_t *gi, mgb_stats_t *st) { *st = t_has_stats? t_last_stats : model_of(gi)->stats; } // the calling thread's last batch

@@ -316,19 +316,7 @@ MG_HD inline int chain_dp_w(Arena &A, int max_dist_x, int max_dist_y, int bw, in
 			const int32_t before = warp_excl_prefix_max_i32(sc, lane);
 			const int improves = active && sc > (before > max_f? before : max_f);
 			const uint32_t m_imp = warp_ballot(improves), m_mk = warp_ballot(marked && !improves);
-			uint32_t events = m_imp | m_mk;
-			int brk = -1;
-			if (m_mk == 0) { // only improvements in this chunk: the counter just drains
-				n_skip -= mask_count(m_imp);
-				if (n_skip < 0) n_skip = 0;
-				events = 0;
-			}
-			while (events) {
-				const int l = ctz32(events);
-				events &= events - 1;
-				if (m_imp >> l & 1) { if (n_skip > 0) --n_skip; }
-				else if (++n_skip > max_skip) { brk = l; break; }
-			}
+			const int brk = replay_skips(m_imp, m_mk, max_skip, &n_skip);
 			const int eligible = active && (brk < 0 || lane < brk);
 			const int32_t best = warp_max_i32(eligible? sc : SC_NONE);
 			if (best > max_f) {
@@ -624,19 +612,7 @@ MG_HD inline int chain_rmq_fill_w(Arena &A, int max_dist, int max_dist_inner, in
 							const int32_t before = warp_excl_prefix_max_i32(sc_eff, lane);
 							const int improves = c_ok && c_sc > (before > max_f? before : max_f); // strictly above everything in front of it
 							const uint32_t m_imp = warp_ballot(improves), m_mk = warp_ballot(c_ok && !improves && c_mk);
-							int brk = -1;
-							if (m_mk == 0) { // only improvements: the skip counter just drains
-								n_skip -= mask_count(m_imp);
-								if (n_skip < 0) n_skip = 0;
-							} else {
-								uint32_t events = m_imp | m_mk;
-								while (events) {
-									const int l = ctz32(events);
-									events &= events - 1;
-									if (m_imp >> l & 1) { if (n_skip > 0) --n_skip; }
-									else if (++n_skip > max_chn_skip) { brk = l; break; }
-								}
-							}
+							const int brk = replay_skips(m_imp, m_mk, max_chn_skip, &n_skip);
 							const int eligible = improves && (brk < 0 || lane < brk);
 							const int32_t best = warp_max_i32(eligible? c_sc : SC_NONE);
 							if (best > max_f) { // improvements rise strictly: the last one before the stop holds the maximum

@@ -394,6 +394,25 @@ def case_concurrent_calls(lib, workdir, n_threads=3, n_reads=90):
     lib.mgb_gfa_destroy(g)
 
 
+def case_multi_device(lib, workdir, devices="0,0,0", n_reads=100):
+    """MGB_DEVICES: the index replicated on several devices (here the same one three times, which runs the same code), every
+    mg_map_batch() cut into one contiguous part per device: the results, in input order, are what one device gives"""
+    pre, reads = os.path.join(workdir, "svm"), os.path.join(workdir, "svm.reads.fa")
+    T.sim_graph(pre, 300000, 3, 31)
+    T.sim_reads(pre + ".hap.fa", reads, n_reads, 7000, "ont", 71)
+    names, seqs = T.read_fasta(reads)
+    one, _, _ = T.map_with_engine(lib, pre + ".gfa", names, seqs, "lr")
+    os.environ["MGB_DEVICES"] = devices
+    try:
+        many, _, _ = T.map_with_engine(lib, pre + ".gfa", names, seqs, "lr")
+    finally:
+        del os.environ["MGB_DEVICES"]
+    assert sum(1 for r in one if r and r["n_gc"] > 0) > n_reads // 2
+    for i, (a, b) in enumerate(zip(one, many)):
+        d = T.diff_results(a, b)
+        assert d is None, "read %d: %s" % (i, d)
+
+
 def case_upload_modes(lib, workdir, n_reads=80):
     """how the reads reach the device does not change what comes back: 2 bits per base (all A/C/G/T), the same with a few reads that
     hold N or lower-case letters (those travel as ASCII beside the packed ones), the whole batch as ASCII (many such reads), and the

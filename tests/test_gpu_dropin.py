@@ -47,3 +47,34 @@ def test_dropin_binary_paired_short_reads(workdir):
     got = subprocess.run([DROPIN, "-x", "sr", "-t", "4", gfa, r1, r2], check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
     assert len(want) > 1000
     assert got == want, cases.first_diff(got, want)
+
+
+@pytest.mark.skipif(not (os.path.exists(DROPIN) and os.path.exists(REF_BIN)), reason="oracle/_ref binaries not built")
+def test_dropin_other_consumers_of_the_boundary(workdir):
+    """the reference's other users of mg_index()/mg_map() -- incremental graph generation (-cxggs: ggen.c:36 maps every sample
+    through mg_map() from kt_for threads and re-indexes the grown graph), --call (asm-call.c:21) and --cov (cal_cov.c:8) -- run
+    unchanged on the library and print the reference's bytes"""
+    hum, chimp, orang = (os.path.join(T.FIX, f) for f in ("MT-human.fa", "MT-chimp.fa", "MT-orangA.fa"))
+    gfa = os.path.join(T.FIX, "MT.gfa")
+    hap, reads = os.path.join(workdir, "mt.hap.fa"), os.path.join(workdir, "mt.cov.fa")
+    T.sim_mt_haps(hap)
+    T.sim_reads(hap, reads, 60, 8000, "ont", 73)
+    for args in (["-cxggs", "-t", "3", hum, chimp, orang], ["-cxasm", "--call", "-t", "2", gfa, chimp], ["-cxasm", "--cov", gfa, chimp],
+                 ["-cxlr", "--cov", "-t", "4", gfa, reads]):
+        want = subprocess.run([REF_BIN] + args, check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
+        got = subprocess.run([DROPIN] + args, check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
+        assert len(want) > 100, args
+        assert got == want, (args, cases.first_diff(got, want))
+
+
+@pytest.mark.skipif(not os.path.exists(DROPIN), reason="oracle/_ref/minigraph_b200 not built (make -C oracle dropin)")
+def test_dropin_binary_on_several_devices(workdir):
+    """MGB_DEVICES: the reference host drives every listed GPU through the one mg_map_batch_frag() call per mini-batch"""
+    import torch
+    hap, reads = os.path.join(workdir, "mt.hap.fa"), os.path.join(workdir, "mt.reads.fa")
+    T.sim_mt_haps(hap)
+    T.sim_reads(hap, reads, 24, 10000, "ont", 11)
+    env = dict(os.environ, MGB_DEVICES="0,1" if torch.cuda.device_count() >= 2 else "0,0")
+    got = subprocess.run([DROPIN, "-cx", "lr", "-t", "4", os.path.join(T.FIX, "MT.gfa"), reads], check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=env).stdout
+    want = cases.golden("c2_MT_24x10k_ont_s11.lr.gaf")
+    assert got == want, cases.first_diff(got, want)

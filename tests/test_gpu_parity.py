@@ -64,6 +64,12 @@ def test_upload_modes(lib, workdir):
     cases.case_upload_modes(lib, workdir)
 
 
+def test_index_on_several_devices(lib, workdir):
+    import torch
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    cases.case_multi_device(lib, workdir, devices="0,1" if n >= 2 else "0,0,0")
+
+
 def test_concurrent_callers(lib, workdir):
     cases.case_concurrent_calls(lib, workdir)
 

@@ -11,7 +11,7 @@ cubin=$(ls -t *.cubin | head -1)
 nvdisasm -g -c $cubin > gpurun_out/dis.txt 2>/dev/null
 for k in "$@"; do
 	out=gpurun_out/prof_${round}_$k
-	timeout 900 ncu --set full --clock-control none --import-source on -k $k -c 1 -f -o $out python bench.py --steps 1 --warmup 1 --no-cpu > $out.log 2>&1
+	timeout 900 ncu --set full --clock-control none --import-source on -k $k -c 1 -f -o $out python bench.py --steps 1 --warmup 1 --no-cpu --pipe 1 ${BENCH_ARGS:-} > $out.log 2>&1
 	ncu -i $out.ncu-rep --page source --csv > $out.sass.csv 2>/dev/null
 	ncu -i $out.ncu-rep --page raw --csv > $out.metrics.csv 2>/dev/null
 	mangled=$(grep -o "_Z[0-9]*${k}10LaunchArgs" gpurun_out/dis.txt | head -1)
