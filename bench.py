@@ -313,7 +313,7 @@ def main():
     gaf_cap = [C.c_size_t(0) for _ in range(M)]
     gaf_len = [C.c_size_t(0) for _ in range(M)]
     acc = {"pack": 0.0, "h2d": 0.0, "d2h": 0.0, "asm": 0.0, "call": 0.0, "gaf": 0.0, "span": 0.0, "chain": 0.0, "launches": 0, "retry": 0,
-           "w_slot": 0.0, "w_up": 0.0, "w_pass": 0.0, "w_redo": 0.0, "w_down": 0.0,
+           "w_slot": 0.0, "w_gpu": 0.0, "w_up": 0.0, "w_pass": 0.0, "w_redo": 0.0, "w_down": 0.0,
            "seeds": 0, "anchors": 0, "chains": 0, "out_bytes": 0, "lab_new": 0, "jobs": 0}
     acc_lock = threading.Lock()
     kern = [0.0] * 10
@@ -353,7 +353,7 @@ def main():
                         acc["span"] += st.t_dev_span_ms; acc["chain"] += st.t_kernel_ms[1]; acc["launches"] += st.n_launches
                         acc["seeds"] += st.n_seeds; acc["anchors"] += st.n_anchors_out; acc["chains"] += st.n_chains_out
                         acc["out_bytes"] += st.out_bytes; acc["lab_new"] += st.n_lab_new; acc["jobs"] += st.n_jobs; acc["retry"] += st.n_retry
-                        acc["w_slot"] += st.w_slot_wait_ms; acc["w_up"] += st.w_upload_ms; acc["w_pass"] += st.w_pass_ms; acc["w_redo"] += st.w_redo_ms; acc["w_down"] += st.w_download_ms
+                        acc["w_slot"] += st.w_slot_wait_ms; acc["w_gpu"] += st.w_gpu_wait_ms; acc["w_up"] += st.w_upload_ms; acc["w_pass"] += st.w_pass_ms; acc["w_redo"] += st.w_redo_ms; acc["w_down"] += st.w_download_ms
                         for i in range(10):
                             kern[i] += st.t_kernel_ms[i]
                         C.memmove(C.byref(last_st), C.byref(st), C.sizeof(st))
@@ -482,7 +482,7 @@ def main():
                             "while one thread writes the GAF text (%d bytes/step) of finished mini-batches in input order and frees the results" % (n_pipe, gaf_bytes)},
         "host_ms_per_step": {"pack": e2e_acc["pack"] / a.steps, "h2d": e2e_acc["h2d"] / a.steps, "d2h": e2e_acc["d2h"] / a.steps, "assemble": e2e_acc["asm"] / a.steps,
                              "mg_map_batch_calls(sum over threads)": e2e_acc["call"] / a.steps, "gaf_text(writer thread)": e2e_acc["gaf"] / a.steps,
-                             "call_wall_parts(sum over threads)": {"wait_for_slot": e2e_acc["w_slot"] / a.steps, "pack+h2d": e2e_acc["w_up"] / a.steps, "kernels+syncs": e2e_acc["w_pass"] / a.steps,
+                             "call_wall_parts(sum over threads)": {"wait_for_slot": e2e_acc["w_slot"] / a.steps, "pack+h2d": e2e_acc["w_up"] / a.steps, "wait_for_gpu": e2e_acc["w_gpu"] / a.steps, "kernels+syncs": e2e_acc["w_pass"] / a.steps,
                                                                    "large_arena_redo": e2e_acc["w_redo"] / a.steps, "pack_results+d2h": e2e_acc["w_down"] / a.steps, "device_span": e2e_acc["span"] / a.steps},
                              "reads_redone_with_large_arena": e2e_acc["retry"] / a.steps},
         "device_cycles_last_call": {k: (int(st.prof[i]) >> 16 if k in ("wfa_max_cyc", "gwfa_max_cyc") else int(st.prof[i])) for i, k in enumerate(capi.PROF_NAMES)},

@@ -241,6 +241,7 @@ typedef struct {
 	int64_t n_lab_new;      /* such sources in this batch */
 	int64_t n_lab_big;      /* ... of which needed the second, warp-per-source pass */
 	int64_t h2d_bytes;      /* bytes of reads and per-read tables copied to the device (reads travel 2 bits per base unless they hold letters other than A/C/G/T) */
+	double w_gpu_wait_ms;   /* host wall clock spent waiting for the kernels of another call in flight to finish */
 	double w_slot_wait_ms, w_upload_ms, w_pass_ms, w_redo_ms, w_download_ms; /* host wall clock of the call: waiting for a slot; packing + H2D; the kernels of the first pass
 	                           with the host syncs between them; the large-arena pass over reads that outgrew their arena; result packing + D2H up to the assembly */
 } mgb_stats_t;

@@ -45,12 +45,13 @@ static int64_t p_thread_mask = 0;      // bit s set: stage s runs one item per t
 static int64_t p_slots = 3;            // mg_map_batch calls that may run at once on one index (each on its own slot: stream, buffers, arenas)
 static int64_t p_slot_workers = 0;
 static int64_t p_tier_learn = 1;       // 0: every gap tries every tier (no routing)
+static int64_t p_gpu_lock = 1;         // 0: the kernels of concurrent calls may interleave on the device
 static int64_t p_pack2 = 1;            // 0: reads are uploaded as ASCII (1 byte per base) instead of 2 bits per base
 static int64_t p_lab_cache = 1;        // 0: graph chaining searches its walks per read instead of keeping per-source labels in HBM (mgb_gclabel.cuh)
 
 // launch shape per stage: warps per block and blocks per SM wanted (tunable for experiments: "sw<stage>", "mb<stage>")
 static int STAGE_MINB[20] = { 8, 2, 8, 8, 5, 8, 7, 4, 4, 4, 0, 0, 0, 0, 0, 0, 0, 8, 8, 2 }; // indexed by stage number (10-16 unused)
-static int STAGE_WARPS[20] = { 4, 3, 4, 4, 4, 4, 2, 4, 4, 4, 0, 0, 0, 0, 0, 0, 0, 4, 4, 3 };
+static int STAGE_WARPS[20] = { 4, 7, 4, 4, 4, 4, 2, 4, 4, 4, 0, 0, 0, 0, 0, 0, 0, 4, 4, 5 }; // k_chain: 2 x 7 slices of 16 KB per SM, k_chain_rescue: 2 x 5 of 20 KB
 extern "C" const char *mgb_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char *mgb_version(void) { return "mgb200-r1"; }
 extern "C" int mgb_set_param(const char *key, int64_t value)
@@ -66,6 +67,7 @@ extern "C" int mgb_set_param(const char *key, int64_t value)
 	else if (!strcmp(key, "slot_workers")) p_slot_workers = value;
 	else if (!strcmp(key, "lab_cache")) p_lab_cache = value;
 	else if (!strcmp(key, "pack2")) p_pack2 = value;
+	else if (!strcmp(key, "gpu_lock")) p_gpu_lock = value;
 	else if (!strcmp(key, "tier_learn")) p_tier_learn = value;
 	else if (!strncmp(key, "sw", 2) && key[2] >= '0' && key[2] <= '9' && !key[3] && value >= 1 && value <= 4) STAGE_WARPS[key[2] - '0'] = (int)value;
 	else if (!strncmp(key, "mb", 2) && key[2] >= '0' && key[2] <= '9' && !key[3] && value >= 1 && value <= 32) STAGE_MINB[key[2] - '0'] = (int)value;
@@ -247,7 +249,7 @@ __device__ __forceinline__ void stage_loop(const LaunchArgs &L)
 	Arena A;
 	arena_init(A, L.arena_base + (uint64_t)worker * L.arena_bytes, L.arena_bytes);
 	extern __shared__ int4 dyn_smem[];
-	const int smem_stride = STAGE == 4? WfTier1::STRIDE : STAGE == 6? WfTier2::STRIDE : STAGE == 0? SKETCH_SMEM_BYTES : STAGE == 8? GWFA_SMEM_ARENA : (STAGE == 1 || STAGE == 19)? CHAIN_SMEM_BYTES : 0;
+	const int smem_stride = STAGE == 4? WfTier1::STRIDE : STAGE == 6? WfTier2::STRIDE : STAGE == 0? SKETCH_SMEM_BYTES : STAGE == 8? GWFA_SMEM_ARENA : STAGE == 1? CHAIN_SMEM_BYTES : STAGE == 19? CHAIN_RESCUE_SMEM_BYTES : 0;
 	int32_t *smem = smem_stride? (int32_t*)((char*)dyn_smem + (size_t)(threadIdx.x >> 5) * smem_stride) : 0;
 	if (STAGE == 1 || STAGE == 19) chain_smem_init(smem, lane);
 	const int n_work = L.n_work_dev? (int)*L.n_work_dev : L.n_work;
@@ -295,10 +297,11 @@ __device__ __forceinline__ void stage_loop_thread(const LaunchArgs &L)
 }
 
 // named entry points (one per stage, so that profiles read well); blocks of 4 warps, MINB blocks per SM wanted
-#define MGB_KERNEL(name, STAGE, MINB) __global__ void __launch_bounds__(128, MINB) name(LaunchArgs L) { if (L.thread_mode) stage_loop_thread<STAGE>(L); else stage_loop<STAGE>(L); }
+#define MGB_KERNEL_T(name, STAGE, THREADS, MINB) __global__ void __launch_bounds__(THREADS, MINB) name(LaunchArgs L) { if (L.thread_mode) stage_loop_thread<STAGE>(L); else stage_loop<STAGE>(L); }
+#define MGB_KERNEL(name, STAGE, MINB) MGB_KERNEL_T(name, STAGE, 128, MINB)
 MGB_KERNEL(k_seed, 0, 8)          // K1-K3: sketch, index lookup, seed sort
-MGB_KERNEL(k_chain, 1, 2)         // K4/K5: linear chaining on chip (seeds bulk-loaded into shared memory)
-MGB_KERNEL(k_chain_rescue, 19, 2) // K5: long-join rescue (RMQ chaining) of the reads k_chain listed
+MGB_KERNEL_T(k_chain, 1, 224, 2)         // K4/K5: linear chaining on chip (seeds bulk-loaded into shared memory)
+MGB_KERNEL_T(k_chain_rescue, 19, 160, 2) // K5: long-join rescue (RMQ chaining) of the reads k_chain listed
 MGB_KERNEL(k_gchain, 2, 8)        // K6: graph chaining DP + k-shortest walks, overlap resolution, bridging plan
 MGB_KERNEL(k_gwfa, 8, 4)          // K7a: bridging alignments (graph wavefront), one warp per bridge
 MGB_KERNEL(k_gchain_gen, 9, 4)    // K7b: graph-chain materialisation, post filters, mapq, alignment plan
@@ -535,7 +538,7 @@ static void launch_stage(LaunchArgs &L, const Workers &W, int warps_override = 0
 #ifdef MGB_HOSTSIM
 	Arena A;
 	arena_init(A, W.arena, STAGE == 17? (W.arena_bytes / 32) & ~(uint64_t)15 : W.arena_bytes); // one item per thread: a thread's share, as on the device
-	std::vector<int32_t> sim_smem(std::max<size_t>(std::max<size_t>(WfTier1::STRIDE, WfTier2::STRIDE), std::max<size_t>(std::max<size_t>(GWFA_SMEM_ARENA, CHAIN_SMEM_BYTES), SKETCH_SMEM_BYTES)) / 4);
+	std::vector<int32_t> sim_smem(std::max<size_t>(std::max<size_t>(WfTier1::STRIDE, WfTier2::STRIDE), std::max<size_t>(std::max<size_t>(GWFA_SMEM_ARENA, CHAIN_RESCUE_SMEM_BYTES), SKETCH_SMEM_BYTES)) / 4);
 	if (STAGE == 1 || STAGE == 19) { mbar_init((uint64_t*)sim_smem.data(), 1); sim_smem[2] = 0; }
 	const int n_work_sim = L.n_work_dev? (int)*L.n_work_dev : L.n_work;
 	for (int it = 0; it < n_work_sim; ++it) {
@@ -567,7 +570,7 @@ static void launch_stage(LaunchArgs &L, const Workers &W, int warps_override = 0
 	int want = dev_sm_count() * STAGE_MINB[STAGE] * STAGE_WARPS[STAGE]; // resident warps this stage can keep on the chip
 	int n_w = std::min(W.n_workers, want);
 	int blocks = std::max(1, n_w / warps);
-	size_t smem = STAGE == 4? (size_t)warps * WfTier1::STRIDE : STAGE == 6? (size_t)warps * WfTier2::STRIDE : STAGE == 0? (size_t)warps * SKETCH_SMEM_BYTES : STAGE == 8? (size_t)warps * GWFA_SMEM_ARENA : (STAGE == 1 || STAGE == 19)? (size_t)warps * CHAIN_SMEM_BYTES : 0;
+	size_t smem = STAGE == 4? (size_t)warps * WfTier1::STRIDE : STAGE == 6? (size_t)warps * WfTier2::STRIDE : STAGE == 0? (size_t)warps * SKETCH_SMEM_BYTES : STAGE == 8? (size_t)warps * GWFA_SMEM_ARENA : STAGE == 1? (size_t)warps * CHAIN_SMEM_BYTES : STAGE == 19? (size_t)warps * CHAIN_RESCUE_SMEM_BYTES : 0;
 	void (*kern)(LaunchArgs) = StageKernel<STAGE>::get();
 	if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	L.thread_mode = (p_thread_mask >> STAGE) & 1;
@@ -626,6 +629,7 @@ struct Model {
 	Slot slots[MAX_SLOTS];
 	std::mutex big_mutex; // the large-arena retry pass, the label table and the learned routing are shared by the slots
 	std::condition_variable slot_cv;
+	std::mutex gpu_mutex;         // the kernels of one call at a time: calls in flight overlap their copies and host work with them, not with each other's kernels
 	int device = 0;               // the GPU this image lives on
 	std::vector<Model*> peers;    // MGB_DEVICES: the same index on further GPUs; a batch is cut into one contiguous part per device
 	bool slot_busy[MAX_SLOTS] = {};
@@ -1378,7 +1382,16 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 #endif
 			dsync();
 		};
-		{ const double tw = now_ms(); if (attempt == 0) S.w_upload_ms = tw - t_host0; run_pass(0, n_reads, sl.W, true); S.w_pass_ms += now_ms() - tw; }
+		{
+			const double tq = now_ms();
+			if (attempt == 0) S.w_upload_ms = tq - t_host0;
+			std::unique_lock<std::mutex> gpu(M->gpu_mutex, std::defer_lock);
+			if (p_gpu_lock) gpu.lock();
+			const double tw = now_ms();
+			S.w_gpu_wait_ms += tw - tq;
+			run_pass(0, n_reads, sl.W, true);
+			S.w_pass_ms += now_ms() - tw;
+		}
 		S.n_jobs = jobs_done;
 		d2h(routs.data(), d_routs, sizeof(ReadOut) * (size_t)n_reads);
 		d2h(meta.data(), d_meta, sizeof(ReadMeta) * (size_t)n_reads);
@@ -1397,7 +1410,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 			int nw = (int)std::min<uint64_t>(16, std::max<uint64_t>(1, dev_free_mem() / 2 / big)); // a handful of reads per batch at most come here
 			if (M->Wbig.arena == 0 || M->Wbig.arena_bytes != big) ensure_workers(M->Wbig, std::max(1, nw), big);
 			h2d(d_list_buf, redo.data(), redo.size() * sizeof(int32_t));
-			{ const double tw = now_ms(); run_pass(d_list_buf, (int32_t)redo.size(), M->Wbig, false); S.w_redo_ms += now_ms() - tw; }
+			{ std::unique_lock<std::mutex> gpu(M->gpu_mutex, std::defer_lock); if (p_gpu_lock) gpu.lock(); const double tw = now_ms(); run_pass(d_list_buf, (int32_t)redo.size(), M->Wbig, false); S.w_redo_ms += now_ms() - tw; }
 			S.n_retry += (int64_t)redo.size();
 			d2h(routs.data(), d_routs, sizeof(ReadOut) * (size_t)n_reads);
 			d2h(meta.data(), d_meta, sizeof(ReadMeta) * (size_t)n_reads);
@@ -1466,7 +1479,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 
 	// ---- results ----
 	double t_asm0 = now_ms();
-	S.w_download_ms = t_asm0 - t_host0 - S.w_upload_ms - S.w_pass_ms - S.w_redo_ms;
+	S.w_download_ms = t_asm0 - t_host0 - S.w_upload_ms - S.w_pass_ms - S.w_redo_ms - S.w_gpu_wait_ms;
 	int first_bad = -1;
 	for (int i = 0; i < n_reads; ++i) {
 		int st = meta[i].status < 0? meta[i].status : routs[i].status;

@@ -11,6 +11,15 @@ namespace mgb {
 
 static const int32_t SC_NONE = INT32_MIN;
 
+// The chaining loops re-read a handful of small per-anchor arrays for every anchor.  They are taken from the "hot" arena -- the
+// warp's slice of shared memory when the kernel has one -- and fall back to the worker's HBM arena (the "cold" one, which holds
+// everything that is touched once: end-point lists, sort scratch, tree nodes) when the slice is full.  Hot == cold is fine.
+#define MGB_ALLOC_HOT(H, C, ptr, type, n) do { \
+		(ptr) = (type*)mgb::arena_alloc((H), (uint64_t)sizeof(type) * (uint64_t)((n) > 0? (n) : 1)); \
+		if ((ptr) == 0) (ptr) = (type*)mgb::arena_alloc((C), (uint64_t)sizeof(type) * (uint64_t)((n) > 0? (n) : 1)); \
+		if ((ptr) == 0) return mgb::MGB_E_ARENA; \
+	} while (0)
+
 // chaining score between anchors i (later) and j (earlier)  (reference: lchain.c:114-139 comput_sc)
 MG_HD inline int32_t chain_score(const u128 &ai, const u128 &aj, int32_t max_dist_x, int32_t max_dist_y, int32_t bw,
 								 float pen_gap, float pen_skip, int is_cdna, int n_seg)
@@ -94,38 +103,6 @@ MG_HD inline int chain_backtrack(Arena &A, int64_t n, const int32_t *f, const in
 	return 0;
 }
 
-// gather chained anchors and order chains by target position (reference: lchain.c:79-112 compact_a).
-// The result (n_v anchors) is written back to a[0..n_v).
-MG_HD inline int chain_compact(Arena &A, int32_t n_u, uint64_t *u, int32_t n_v, const int32_t *v, u128 *a)
-{
-	uint64_t mark = A.top;
-	u128 *b, *w;
-	uint64_t *u2;
-	int64_t i, j, k;
-	MGB_ALLOC(A, b, u128, n_v);
-	for (i = 0, k = 0; i < n_u; ++i) {
-		int32_t k0 = (int32_t)k, ni = (int32_t)u[i];
-		for (j = 0; j < ni; ++j) b[k++] = a[v[k0 + (ni - j - 1)]];
-	}
-	MGB_ALLOC(A, w, u128, n_u);
-	for (i = k = 0; i < n_u; ++i) {
-		w[i].x = b[k].x, w[i].y = (uint64_t)k << 32 | (uint64_t)i;
-		k += (int32_t)u[i];
-	}
-	MGB_TRY(radix_sort_128x(A, w, n_u));
-	MGB_ALLOC(A, u2, uint64_t, n_u);
-	for (i = k = 0; i < n_u; ++i) {
-		int32_t j2 = (int32_t)w[i].y, n = (int32_t)u[j2];
-		const u128 *src = &b[w[i].y >> 32];
-		u2[i] = u[j2];
-		for (int32_t x = 0; x < n; ++x) a[k + x] = src[x];
-		k += n;
-	}
-	for (i = 0; i < n_u; ++i) u[i] = u2[i];
-	A.top = mark;
-	return 0;
-}
-
 // chain_backtrack() + chain_compact() entered by all lanes of a warp: the end-point list, the sorts and the copies are
 // spread over the lanes, the peeling itself (a walk over p[] with the visit marks) stays on lane 0.  u_store receives
 // the chain descriptors; a[0..n_v) the chained anchors.
@@ -204,78 +181,10 @@ MG_HD inline int chain_finish_w(Arena &A, int64_t n, const int32_t *f, const int
 	return 0;
 }
 
-// Banded chaining DP (reference: lchain.c:149-219).  On return a[0..*n_a_) holds the chained anchors
-// and u[0..n_u) = score<<32|cnt per chain (u lives in the arena above the caller's mark).
-MG_HD inline int chain_dp(Arena &A, int max_dist_x, int max_dist_y, int bw, int max_skip, int max_iter, int min_cnt, int min_sc,
-						  float pen_gap, float pen_skip, int is_cdna, int n_seg, int64_t n, u128 *a,
-						  int32_t *n_u_, uint64_t **u_, int32_t *n_a_)
-{
-	int32_t *f, *t, *v, *p, n_u, n_v, max_drop = bw;
-	int64_t i, j, max_ii, st = 0;
-	uint64_t *u;
-	*u_ = 0, *n_u_ = 0, *n_a_ = 0;
-	if (n == 0) return 0;
-	if (max_dist_x < bw) max_dist_x = bw;
-	if (max_dist_y < bw && !is_cdna) max_dist_y = bw;
-	if (is_cdna) max_drop = INT32_MAX;
-	// u is allocated by chain_backtrack below the scratch; to keep stack discipline the scratch is
-	// carved after reserving room for u at the bottom.
-	uint64_t *u_store;
-	MGB_ALLOC(A, u_store, uint64_t, n);
-	uint64_t mark = A.top;
-	MGB_ALLOC(A, p, int32_t, n);
-	MGB_ALLOC(A, f, int32_t, n);
-	MGB_ALLOC(A, v, int32_t, n);
-	MGB_ALLOC(A, t, int32_t, n);
-	for (i = 0; i < n; ++i) t[i] = 0;
-	for (i = 0, max_ii = -1; i < n; ++i) {
-		int64_t max_j = -1, end_j;
-		int32_t max_f = (int32_t)(a[i].y >> 32 & 0xff), n_skip = 0;
-		while (st < i && (a[i].x >> 32 != a[st].x >> 32 || a[i].x > a[st].x + (uint64_t)max_dist_x)) ++st;
-		if (i - st > max_iter) st = i - max_iter;
-		for (j = i - 1; j >= st; --j) {
-			int32_t sc = chain_score(a[i], a[j], max_dist_x, max_dist_y, bw, pen_gap, pen_skip, is_cdna, n_seg);
-			if (sc == SC_NONE) continue;
-			sc += f[j];
-			if (sc > max_f) {
-				max_f = sc, max_j = j;
-				if (n_skip > 0) --n_skip;
-			} else if (t[j] == (int32_t)i) {
-				if (++n_skip > max_skip) break;
-			}
-			if (p[j] >= 0) t[p[j]] = (int32_t)i;
-		}
-		end_j = j;
-		if (max_ii < 0 || (int64_t)(a[i].x - a[max_ii].x) > (int64_t)max_dist_x) {
-			int32_t mx = INT32_MIN;
-			max_ii = -1;
-			for (j = i - 1; j >= st; --j)
-				if (mx < f[j]) mx = f[j], max_ii = j;
-		}
-		if (max_ii >= 0 && max_ii < end_j) {
-			int32_t tmp = chain_score(a[i], a[max_ii], max_dist_x, max_dist_y, bw, pen_gap, pen_skip, is_cdna, n_seg);
-			if (tmp != SC_NONE && max_f < tmp + f[max_ii])
-				max_f = tmp + f[max_ii], max_j = max_ii;
-		}
-		f[i] = max_f, p[i] = (int32_t)max_j;
-		v[i] = max_j >= 0 && v[max_j] > max_f? v[max_j] : max_f;
-		if (max_ii < 0 || ((int64_t)(a[i].x - a[max_ii].x) <= (int64_t)max_dist_x && f[max_ii] < f[i]))
-			max_ii = i;
-	}
-	MGB_TRY(chain_backtrack(A, n, f, p, v, t, min_cnt, min_sc, max_drop, 0, &u, &n_u, &n_v));
-	if (n_u > 0) {
-		MGB_TRY(chain_compact(A, n_u, u, n_v, v, a));
-		for (i = 0; i < n_u; ++i) u_store[i] = u[i];
-	}
-	A.top = mark;
-	*u_ = u_store, *n_u_ = n_u, *n_a_ = n_u > 0? n_v : 0;
-	return 0;
-}
-
 // chain_dp() entered by all lanes of a warp.  The predecessors of anchor i are scored 32 at a time; the sequential
 // rules (strict improvement keeps the first maximum, the skip counter with its early exit, the t[] marks left by
 // visited predecessors) are then replayed on the ballots of the chunk, in visiting order.
-MG_HD inline int chain_dp_w(Arena &A, int max_dist_x, int max_dist_y, int bw, int max_skip, int max_iter, int min_cnt, int min_sc,
+MG_HD inline int chain_dp_w(Arena &H, Arena &A, int max_dist_x, int max_dist_y, int bw, int max_skip, int max_iter, int min_cnt, int min_sc,
 							float pen_gap, float pen_skip, int is_cdna, int n_seg, int64_t n, u128 *a,
 							int32_t *n_u_, uint64_t **u_, int32_t *n_a_, int lane)
 {
@@ -288,11 +197,11 @@ MG_HD inline int chain_dp_w(Arena &A, int max_dist_x, int max_dist_y, int bw, in
 	if (is_cdna) max_drop = INT32_MAX;
 	uint64_t *u_store;
 	MGB_ALLOC(A, u_store, uint64_t, n);
-	uint64_t mark = A.top;
-	MGB_ALLOC(A, p, int32_t, n);
-	MGB_ALLOC(A, f, int32_t, n);
-	MGB_ALLOC(A, v, int32_t, n);
-	MGB_ALLOC(A, t, int32_t, n);
+	const uint64_t mark = A.top, hmark = H.top;
+	MGB_ALLOC_HOT(H, A, p, int32_t, n);
+	MGB_ALLOC_HOT(H, A, f, int32_t, n);
+	MGB_ALLOC_HOT(H, A, v, int32_t, n);
+	MGB_ALLOC_HOT(H, A, t, int32_t, n);
 	for (i = lane; i < n; i += MGB_W) t[i] = 0;
 	warp_sync();
 	for (i = 0, max_ii = -1; i < n; ++i) {
@@ -346,6 +255,7 @@ MG_HD inline int chain_dp_w(Arena &A, int max_dist_x, int max_dist_y, int bw, in
 	int32_t n_u = 0, n_v = 0;
 	MGB_TRY(chain_finish_w(A, n, f, p, v, t, min_cnt, min_sc, max_drop, a, u_store, &n_u, &n_v, lane));
 	A.top = mark;
+	if (&H != &A) H.top = hmark;
 	*u_ = u_store, *n_u_ = n_u, *n_a_ = n_u > 0? n_v : 0;
 	return 0;
 }
@@ -444,34 +354,6 @@ MG_HD inline int chain_rmq_fill_seq(Arena &A, int max_dist, int max_dist_inner, 
 	return 0;
 }
 
-// RMQ chaining (reference: lchain.c:252-372).  Same output convention as chain_dp().  Sequential (one lane).
-MG_HD inline int chain_rmq(Arena &A, int max_dist, int max_dist_inner, int bw, int max_chn_skip, int cap_rmq_size, int min_cnt, int min_sc,
-						   float pen_gap, float pen_skip, int64_t n, u128 *a, int32_t *n_u_, uint64_t **u_, int32_t *n_a_)
-{
-	int32_t *f, *t, *v, *p, n_u, n_v, max_drop = bw;
-	uint64_t *u;
-	*u_ = 0, *n_u_ = 0, *n_a_ = 0;
-	if (n == 0) return 0;
-	if (max_dist < bw) max_dist = bw;
-	if (max_dist_inner <= 0 || max_dist_inner >= max_dist) max_dist_inner = 0;
-	uint64_t *u_store;
-	MGB_ALLOC(A, u_store, uint64_t, n);
-	uint64_t mark = A.top;
-	MGB_ALLOC(A, p, int32_t, n);
-	MGB_ALLOC(A, f, int32_t, n);
-	MGB_ALLOC(A, t, int32_t, n);
-	MGB_ALLOC(A, v, int32_t, n);
-	MGB_TRY(chain_rmq_fill_seq(A, max_dist, max_dist_inner, bw, max_chn_skip, cap_rmq_size, pen_gap, pen_skip, n, a, f, p, t, v));
-	MGB_TRY(chain_backtrack(A, n, f, p, v, t, min_cnt, min_sc, max_drop, 0, &u, &n_u, &n_v));
-	if (n_u > 0) {
-		MGB_TRY(chain_compact(A, n_u, u, n_v, v, a));
-		for (int64_t i = 0; i < n_u; ++i) u_store[i] = u[i];
-	}
-	A.top = mark;
-	*u_ = u_store, *n_u_ = n_u, *n_a_ = n_u > 0? n_v : 0;
-	return 0;
-}
-
 // ---- warp-cooperative RMQ fill ----
 // The two trees of the reference only ever hold index windows of the x-sorted anchor array: outer = [st, i0),
 // inner = [st_inner, i0).  Hence
@@ -495,14 +377,14 @@ MG_HD inline double warp_min_f64(double x)
 	return x;
 }
 
-MG_HD inline int chain_rmq_fill_w(Arena &A, int max_dist, int max_dist_inner, int bw, int max_chn_skip, float pen_gap, float pen_skip,
+MG_HD inline int chain_rmq_fill_w(Arena &H, Arena &A, int max_dist, int max_dist_inner, int bw, int max_chn_skip, float pen_gap, float pen_skip,
 								  int64_t n, const u128 *a, int32_t *f, int32_t *p, int32_t *t, int32_t *v, int lane)
 {
-	uint64_t mark = A.top;
+	const uint64_t mark = A.top, hmark = H.top;
 	double *pri;
 	uint64_t *K; // inner window, keys y<<32|idx ascending
-	MGB_ALLOC(A, pri, double, n);
-	MGB_ALLOC(A, K, uint64_t, n);
+	MGB_ALLOC_HOT(H, A, pri, double, n);
+	MGB_ALLOC_HOT(H, A, K, uint64_t, n);
 	int32_t nK = 0;
 	int64_t i, i0 = 0, st = 0, st_inner = 0;
 	for (i = lane; i < n; i += MGB_W) t[i] = 0;
@@ -575,7 +457,7 @@ MG_HD inline int chain_rmq_fill_w(Arena &A, int max_dist, int max_dist_inner, in
 			}
 			const double gbest = warp_min_f64(best);
 			const int32_t n_at_min = warp_sum_i32(best_j >= 0 && best == gbest? n_best : 0);
-			if (n_at_min > 1) { A.top = mark; return 1; } // pri tie: the winner depends on the AVL shape
+			if (n_at_min > 1) { A.top = mark; if (&H != &A) H.top = hmark; return 1; } // pri tie: the winner depends on the AVL shape
 			if (n_at_min == 1) {
 				const int32_t j = warp_max_i32(best_j >= 0 && best == gbest? best_j : -1);
 				int32_t exact, width, n_skip = 0;
@@ -632,12 +514,13 @@ MG_HD inline int chain_rmq_fill_w(Arena &A, int max_dist, int max_dist_inner, in
 		warp_sync();
 	}
 	A.top = mark;
+	if (&H != &A) H.top = hmark;
 	return 0;
 }
 
 // Warp-uniform RMQ chaining: same contract as chain_rmq(); all lanes enter with identical arguments and leave with
 // identical results (outputs are broadcast from lane 0, which runs the sequential backtrack/compaction).
-MG_HD inline int chain_rmq_w(Arena &A, int max_dist, int max_dist_inner, int bw, int max_chn_skip, int cap_rmq_size, int min_cnt, int min_sc,
+MG_HD inline int chain_rmq_w(Arena &H, Arena &A, int max_dist, int max_dist_inner, int bw, int max_chn_skip, int cap_rmq_size, int min_cnt, int min_sc,
 							 float pen_gap, float pen_skip, int64_t n, u128 *a, int32_t *n_u_, uint64_t **u_, int32_t *n_a_, int lane)
 {
 	int32_t *f, *t, *v, *p;
@@ -648,12 +531,12 @@ MG_HD inline int chain_rmq_w(Arena &A, int max_dist, int max_dist_inner, int bw,
 	if (max_dist_inner <= 0 || max_dist_inner >= max_dist) max_dist_inner = 0;
 	uint64_t *u_store;
 	MGB_ALLOC(A, u_store, uint64_t, n);
-	uint64_t mark = A.top;
-	MGB_ALLOC(A, p, int32_t, n);
-	MGB_ALLOC(A, f, int32_t, n);
-	MGB_ALLOC(A, t, int32_t, n);
-	MGB_ALLOC(A, v, int32_t, n);
-	int rc = n <= cap_rmq_size? chain_rmq_fill_w(A, max_dist, max_dist_inner, bw, max_chn_skip, pen_gap, pen_skip, n, a, f, p, t, v, lane) : 1;
+	const uint64_t mark = A.top, hmark = H.top;
+	MGB_ALLOC_HOT(H, A, p, int32_t, n);
+	MGB_ALLOC_HOT(H, A, f, int32_t, n);
+	MGB_ALLOC_HOT(H, A, t, int32_t, n);
+	MGB_ALLOC_HOT(H, A, v, int32_t, n);
+	int rc = n <= cap_rmq_size? chain_rmq_fill_w(H, A, max_dist, max_dist_inner, bw, max_chn_skip, pen_gap, pen_skip, n, a, f, p, t, v, lane) : 1;
 	if (rc < 0) return rc;
 	int32_t n_u = 0, n_v = 0;
 	if (rc == 1) { // too many anchors for the cooperative fill: sequential replay on one lane
@@ -669,6 +552,7 @@ MG_HD inline int chain_rmq_w(Arena &A, int max_dist, int max_dist_inner, int bw,
 	}
 	MGB_TRY(chain_finish_w(A, n, f, p, v, t, min_cnt, min_sc, max_drop, a, u_store, &n_u, &n_v, lane));
 	A.top = mark;
+	if (&H != &A) H.top = hmark;
 	*u_ = u_store, *n_u_ = n_u, *n_a_ = n_u > 0? n_v : 0;
 	return 0;
 }

@@ -216,12 +216,15 @@ MG_HD inline int stage_chain_tail(const PipeCtx &c, ReadMeta &m, Arena &A, u128 
 //                   (stage_chain_tail) or, for a read whose best chain leaves much of it uncovered (map-algo.c:407-417: in practice
 //                   every read that spans several segments), a place on the rescue list with its compacted anchors;
 //   k_chain_rescue  (pass 1): the listed reads: anchors sorted back into target order, RMQ chaining with the long bandwidth, tail.
-// ON CHIP: the read's seeds are bulk-copied (cp.async.bulk + mbarrier, mgb_tma.cuh) into the warp's slice of shared memory and the
-// whole pass -- DP state f/p/v/t, end-point sort, backtracking, compaction, RMQ window and tree, chain filters -- works in an
-// arena that is the rest of that slice; only the surviving anchors go back to HBM, as one bulk store.  Algorithmic traffic is then
-// the traffic: 16 B per seed in, 16 B per kept anchor out, 44 B per chain.  A read that does not fit its slice (CHAIN_SMEM_BYTES,
-// about 600 seeds) is worked in the worker's HBM arena by the same code.
-static const int CHAIN_SMEM_BYTES = 36 * 1024; // per warp; 6 warps per SM
+// ON CHIP: the read's seeds are bulk-copied (cp.async.bulk + mbarrier, mgb_tma.cuh) into the warp's slice of shared memory, and the
+// arrays the chaining loops re-read for every anchor (f/p/v/t, the RMQ priorities and window) are taken from the rest of the slice
+// (MGB_ALLOC_HOT); only the surviving anchors go back to HBM, as one bulk store.  What is touched once (end-point list, sort
+// scratch, chain records) stays in the worker's HBM arena, so that a slice is small and many warps are resident: the loops are
+// bound by the latency of their warp-wide votes, and what hides that is warps (measured on B200: everything in a 36 KB slice,
+// 6 warps per SM, was 2.2 times faster per warp and 2 times slower per kernel than 26 warps per SM working in HBM).
+// A read whose seeds do not fit the slice works on the HBM copy, with whatever fits of the hot arrays still on chip.
+static const int CHAIN_SMEM_BYTES = 16 * 1024;        // per warp, k_chain: anchors + f/p/v/t of a read of up to ~500 seeds
+static const int CHAIN_RESCUE_SMEM_BYTES = 20 * 1024; // per warp, k_chain_rescue: + priorities and window of the RMQ pass
 
 struct ChainRun { // what one pass leaves behind
 	int32_t n_keep;   // anchors of a[] to write back
@@ -229,7 +232,7 @@ struct ChainRun { // what one pass leaves behind
 };
 
 template<int PASS>
-MG_HD inline int chain_pass(const PipeCtx &c, int rid, Arena &A, u128 *a, int64_t n_a, int lane, ChainRun *run)
+MG_HD inline int chain_pass(const PipeCtx &c, int rid, Arena &H, Arena &A, u128 *a, int64_t n_a, int lane, ChainRun *run)
 {
 	ReadMeta &m = c.meta[rid];
 	const MapOptDev &o = c.opt;
@@ -252,10 +255,10 @@ MG_HD inline int chain_pass(const PipeCtx &c, int rid, Arena &A, u128 *a, int64_
 		} else max_gap_ref = o.max_gap;
 		if (n_a > 0) {
 			if (o.flag & F_RMQ) {
-				MGB_TRY(chain_rmq_w(A, o.max_gap, o.max_gap_pre, o.bw, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
+				MGB_TRY(chain_rmq_w(H, A, o.max_gap, o.max_gap_pre, o.bw, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
 									o.chn_pen_gap, o.chn_pen_skip, n_a, a, &n_lc, &u, &n_a_new, lane));
 			} else {
-				MGB_TRY(chain_dp_w(A, max_gap_ref, max_gap_qry, o.bw, o.max_lc_skip, o.max_lc_iter, o.min_lc_cnt, o.min_lc_score,
+				MGB_TRY(chain_dp_w(H, A, max_gap_ref, max_gap_qry, o.bw, o.max_lc_skip, o.max_lc_iter, o.min_lc_cnt, o.min_lc_score,
 								   o.chn_pen_gap, o.chn_pen_skip, is_splice, batch_n_seg(c.b, rid), n_a, a, &n_lc, &u, &n_a_new, lane));
 			}
 		}
@@ -282,7 +285,7 @@ MG_HD inline int chain_pass(const PipeCtx &c, int rid, Arena &A, u128 *a, int64_
 		}
 	} else {
 		MGB_TRY(radix_sort_128x_w(A, a, n_a, lane));
-		MGB_TRY(chain_rmq_w(A, o.max_gap, o.max_gap_pre, o.bw_long, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
+		MGB_TRY(chain_rmq_w(H, A, o.max_gap, o.max_gap_pre, o.bw_long, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
 							o.chn_pen_gap, o.chn_pen_skip, n_a, a, &n_lc, &u, &n_a_new, lane));
 		if (lane == 0) prof_add(c, PROF_CHAIN_RMQ_CYC, prof_clock() - t0);
 	}
@@ -320,30 +323,28 @@ MG_HD inline int stage_chain(const PipeCtx &c, int rid, Arena &A, int lane, int3
 	u128 *a = c.anchor + m.a_off;
 	const int64_t n_a = m.n_a;
 	ChainRun run;
-	const uint64_t a_bytes = (uint64_t)n_a * sizeof(u128);
-	if (smem && n_a > 0 && a_bytes + 4096 <= (uint64_t)CHAIN_SMEM_BYTES - 16) { // (a read with a handful of seeds still needs the sort's bin tables)
-		uint64_t *bar = (uint64_t*)smem;
-		u128 *as = (u128*)((char*)smem + 16);
+	if (smem == 0 || n_a == 0) return chain_pass<PASS>(c, rid, A, A, a, n_a, lane, &run);
+	const uint64_t slice = PASS == 0? CHAIN_SMEM_BYTES : CHAIN_RESCUE_SMEM_BYTES, a_bytes = (uint64_t)n_a * sizeof(u128);
+	const int staged = a_bytes + 16 <= slice;
+	uint64_t *bar = (uint64_t*)smem;
+	u128 *as = (u128*)((char*)smem + 16);
+	if (staged) { // the read's seeds: one bulk copy, completion on the slice's barrier
 		const uint32_t parity = (uint32_t)smem[2];
 		if (lane == 0) bulk_load(as, a, (uint32_t)a_bytes, bar);
 		mbar_wait(bar, parity);
 		warp_sync();
 		if (lane == 0) smem[2] = (int32_t)(parity ^ 1);
-		Arena S;
-		arena_init(S, (char*)as + a_bytes, (uint64_t)CHAIN_SMEM_BYTES - 16 - a_bytes);
-		int rc = chain_pass<PASS>(c, rid, S, as, n_a, lane, &run);
-		if (rc != MGB_E_ARENA) {
-			if (rc == 0 && run.n_keep > 0) {
-				warp_sync();
-				if (lane == 0) { bulk_store(a, as, (uint32_t)run.n_keep * (uint32_t)sizeof(u128)); bulk_store_wait(); }
-				warp_sync();
-			}
-			if (lane == 0 && c.prof) prof_add(c, PROF_CHAIN_BT_CYC, 1); // reads chained on chip
-			return rc;
-		}
-		// outgrew the slice: a[] in HBM is untouched, start over there
 	}
-	return chain_pass<PASS>(c, rid, A, a, n_a, lane, &run);
+	Arena S; // what is left of the slice
+	arena_init(S, (char*)as + (staged? a_bytes : 0), slice - 16 - (staged? a_bytes : 0));
+	const int rc = chain_pass<PASS>(c, rid, S, A, staged? as : a, n_a, lane, &run);
+	if (staged && rc == 0 && run.n_keep > 0) {
+		warp_sync();
+		if (lane == 0) { bulk_store(a, as, (uint32_t)run.n_keep * (uint32_t)sizeof(u128)); bulk_store_wait(); }
+		warp_sync();
+	}
+	if (staged && lane == 0 && c.prof) prof_add(c, PROF_CHAIN_BT_CYC, 1); // reads whose anchors were chained on chip
+	return rc;
 }
 
 } // namespace mgb

@@ -59,7 +59,12 @@ def test_dropin_other_consumers_of_the_boundary(workdir):
     hap, reads = os.path.join(workdir, "mt.hap.fa"), os.path.join(workdir, "mt.cov.fa")
     T.sim_mt_haps(hap)
     T.sim_reads(hap, reads, 60, 8000, "ont", 73)
-    for args in (["-cxggs", "-t", "3", hum, chimp, orang], ["-cxasm", "--call", "-t", "2", gfa, chimp], ["-cxasm", "--cov", gfa, chimp],
+    pre = os.path.join(workdir, "svcall")
+    T.sim_graph(pre, 200000, 3, 41)  # --call wants bubbles: an SV graph and one of its haplotypes as the assembly (a 200 kb query, -x asm)
+    hn, hs = T.read_fasta(pre + ".hap.fa")
+    sample = os.path.join(workdir, "svcall.h2.fa")
+    T.write_fasta(sample, hn[2:3], hs[2:3])
+    for args in (["-cxggs", "-t", "3", hum, chimp, orang], ["-cxasm", "--call", "-t", "2", pre + ".gfa", sample], ["-cxasm", "--cov", gfa, chimp],
                  ["-cxlr", "--cov", "-t", "4", gfa, reads]):
         want = subprocess.run([REF_BIN] + args, check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
         got = subprocess.run([DROPIN] + args, check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
