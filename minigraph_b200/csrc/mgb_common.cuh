@@ -454,7 +454,24 @@ template<typename T, typename KeyFn>
 MG_HD inline int radix_sort_exact_w(Arena &A, T *a, int64_t n, int sizeof_key, KeyFn key, int lane)
 {
 	const int MIN_SIZE = 64;
-	if (n <= MIN_SIZE) { if (lane == 0) rs_insertsort(a, a + n, key); warp_sync(); return 0; }
+	if (n <= MIN_SIZE) { // klib sorts these by insertion, i.e. stably: every element's final place is a count, two elements per lane
+		if (MGB_W < 32) { if (lane == 0) rs_insertsort(a, a + n, key); warp_sync(); return 0; }
+		T e[2];
+		int32_t r[2] = {-1, -1};
+		for (int h = 0; h < 2; ++h) {
+			const int64_t i = lane + 32 * h;
+			if (i >= n) continue;
+			e[h] = a[i];
+			const uint64_t ki = (uint64_t)key(e[h]);
+			int32_t c = 0;
+			for (int64_t j = 0; j < n; ++j) { const uint64_t kj = (uint64_t)key(a[j]); c += kj < ki || (kj == ki && j < i); }
+			r[h] = c;
+		}
+		warp_sync();
+		for (int h = 0; h < 2; ++h) if (r[h] >= 0) a[r[h]] = e[h];
+		warp_sync();
+		return 0;
+	}
 	uint64_t mark = A.top;
 	RsRange *stack;
 	int64_t m_stack = n / MIN_SIZE + 4; // pending ranges are disjoint and each holds more than MIN_SIZE elements

@@ -24,6 +24,7 @@
 
 #ifndef MGB_HOSTSIM
 #include <cuda_runtime.h>
+#include "mgb_index.cuh"
 #endif
 
 using namespace mgb;
@@ -45,6 +46,7 @@ static int64_t p_thread_mask = 0;      // bit s set: stage s runs one item per t
 static int64_t p_slots = 3;            // mg_map_batch calls that may run at once on one index (each on its own slot: stream, buffers, arenas)
 static int64_t p_slot_workers = 0;
 static int64_t p_tier_learn = 1;       // 0: every gap tries every tier (no routing)
+static int64_t p_index_dev = 1;        // 0: the minimizer table is grouped and laid out on the host (std::sort) instead of on the device
 static int64_t p_gpu_lock = 1;         // 0: the kernels of concurrent calls may interleave on the device
 static int64_t p_pack2 = 1;            // 0: reads are uploaded as ASCII (1 byte per base) instead of 2 bits per base
 static int64_t p_lab_cache = 1;        // 0: graph chaining searches its walks per read instead of keeping per-source labels in HBM (mgb_gclabel.cuh)
@@ -68,6 +70,7 @@ extern "C" int mgb_set_param(const char *key, int64_t value)
 	else if (!strcmp(key, "lab_cache")) p_lab_cache = value;
 	else if (!strcmp(key, "pack2")) p_pack2 = value;
 	else if (!strcmp(key, "gpu_lock")) p_gpu_lock = value;
+	else if (!strcmp(key, "index_dev")) p_index_dev = value;
 	else if (!strcmp(key, "tier_learn")) p_tier_learn = value;
 	else if (!strncmp(key, "sw", 2) && key[2] >= '0' && key[2] <= '9' && !key[3] && value >= 1 && value <= 4) STAGE_WARPS[key[2] - '0'] = (int)value;
 	else if (!strncmp(key, "mb", 2) && key[2] >= '0' && key[2] <= '9' && !key[3] && value >= 1 && value <= 32) STAGE_MINB[key[2] - '0'] = (int)value;
@@ -523,6 +526,32 @@ __global__ void __launch_bounds__(256) k_unpack(UnpackArgs U)
 }
 #endif
 
+// ---- the few words the host needs between two kernels (pool fill levels, queue lengths) ----
+// They do not travel by cudaMemcpy: a copy of 16 bytes queues behind whatever another call in flight has put on the copy engines
+// (a few hundred MB of results, tens of ms).  A one-warp kernel writes them into page-locked host memory the device can address.
+struct Mail { Pool pools[16]; unsigned int jobq_n[2], lab_n[2]; };
+#ifndef MGB_HOSTSIM
+__global__ void k_mail(const Pool *pools, const unsigned int *jobq_n, const unsigned int *lab_n, Mail *out)
+{
+	const int t = threadIdx.x;
+	if (t < 16) out->pools[t] = pools[t];
+	if (t < 2) out->jobq_n[t] = jobq_n[t], out->lab_n[t] = lab_n? lab_n[t] : 0;
+	__threadfence_system();
+}
+#endif
+static void fetch_mail(const Pool *d_pools, const unsigned int *d_jobq_n, const unsigned int *d_lab_n, Mail *mail)
+{
+#ifndef MGB_HOSTSIM
+	k_mail<<<1, 32, 0, t_stream>>>(d_pools, d_jobq_n, d_lab_n, mail);
+	CUDA_OK(cudaGetLastError());
+	dsync();
+#else
+	memcpy(mail->pools, d_pools, sizeof(mail->pools));
+	memcpy(mail->jobq_n, d_jobq_n, sizeof(mail->jobq_n));
+	if (d_lab_n) memcpy(mail->lab_n, d_lab_n, sizeof(mail->lab_n)); else mail->lab_n[0] = mail->lab_n[1] = 0;
+#endif
+}
+
 struct Workers {
 	int n_workers;
 	uint64_t arena_bytes;
@@ -598,6 +627,8 @@ struct Model {
 	std::vector<uint32_t> occ;      // occurrences per distinct minimizer (for the quantiles)
 	uint64_t n_slots_mask;
 	int k, w;
+	uint32_t *d_occ_sorted = 0; uint64_t n_keys = 0, n_pos = 0; // device-built index: ascending occurrence counts; host copies of slot/pos are made on demand
+	std::mutex host_ix_mutex;
 	// device image
 	GraphDev g;
 	IndexDev ix;
@@ -613,7 +644,7 @@ struct Model {
 	// the batch pipeline: a batch is cut into sub-batches, each driven by its own host thread on its own stream ("slot"),
 	// so that kernels, copies and host-side result assembly of different sub-batches overlap
 	struct Slot {
-		GrowBuf h_seq{true}, h_out{true}, h_small{true}, h_pk{true}, d_pk, d_seq, d_meta, d_routs, d_small, d_jobq, d_order, d_packed, d_packoff, d_segs, d_lab_new, d_pool[10];
+		GrowBuf h_seq{true}, h_out{true}, h_small{true}, h_pk{true}, h_mail{true}, d_pk, d_seq, d_meta, d_routs, d_small, d_jobq, d_order, d_packed, d_packoff, d_segs, d_lab_new, d_pool[10];
 		mgb::HostPool host_pool; // packing and result assembly of the batch on this slot
 		Workers W;
 		mgb_stats_t st;
@@ -653,10 +684,10 @@ static void model_free(Model *M)
 	if (M->Wbig.arena) dfree(M->Wbig.arena);
 	if (M->Wbig.peak) dfree(M->Wbig.peak);
 	if (M->d_logf) dfree(M->d_logf);
-	dfree(M->d_lab_off), dfree(M->d_lab_hdr), dfree(M->d_lab_pool);
+	dfree(M->d_lab_off), dfree(M->d_lab_hdr), dfree(M->d_lab_pool), dfree(M->d_occ_sorted);
 	for (int k = 0; k < Model::MAX_SLOTS; ++k) {
 		Model::Slot &sl = M->slots[k];
-		sl.h_seq.release(), sl.h_out.release(), sl.h_small.release(), sl.h_pk.release(), sl.d_pk.release(), sl.d_seq.release(), sl.d_meta.release(), sl.d_routs.release(), sl.d_small.release(), sl.d_jobq.release(), sl.d_order.release(), sl.d_packed.release(), sl.d_packoff.release(), sl.d_segs.release(), sl.d_lab_new.release();
+		sl.h_seq.release(), sl.h_out.release(), sl.h_small.release(), sl.h_pk.release(), sl.h_mail.release(), sl.d_pk.release(), sl.d_seq.release(), sl.d_meta.release(), sl.d_routs.release(), sl.d_small.release(), sl.d_jobq.release(), sl.d_order.release(), sl.d_packed.release(), sl.d_packoff.release(), sl.d_segs.release(), sl.d_lab_new.release();
 		for (int i = 0; i < 10; ++i) sl.d_pool[i].release();
 		if (sl.W.arena) dfree(sl.W.arena);
 		if (sl.W.peak) dfree(sl.W.peak);
@@ -781,6 +812,20 @@ static Model *model_build(gfa_t *g, int k, int w)
 			if (st0 == MGB_E_POOL) cap *= 2, retry = true;
 			else if (st0 == MGB_E_ARENA) arena_b *= 2, nw = std::max(1, nw / 2), retry = true;
 			else if (st0 < 0) { set_error("segment sketch failed with code " + std::to_string(st0)); throw MgbError{st0}; }
+#ifndef MGB_HOSTSIM
+			if (!retry && p_index_dev) { // group, lay out and insert on the device (mgb_index.cuh)
+				DevIndexOut out;
+				dfree(M->W.arena), dfree(M->W.peak); // the sketch arenas are not needed again; the sort wants the memory
+				memset(&M->W, 0, sizeof(Workers));
+				cudaError_t e = build_index_device(d_mz, hp.used / sizeof(u128), 2 * k, t_stream, &out);
+				dfree(d_pool), dfree(d_mz), dfree(d_status), dfree(d_next);
+				if (e != cudaSuccess) { set_error(std::string("index build on the device: ") + cudaGetErrorString(e)); throw MgbError{MGB_E_INTERNAL}; }
+				M->n_slots_mask = out.n_slots - 1, M->n_keys = out.n_keys, M->n_pos = out.n_pos, M->d_occ_sorted = out.occ_sorted;
+				M->ix.n_slots_mask = M->n_slots_mask, M->ix.slot = out.slot, M->ix.pos = out.pos;
+				M->dev_ptrs.push_back((void*)out.slot), M->dev_ptrs.push_back((void*)out.pos);
+				return M;
+			}
+#endif
 			if (!retry) {
 				mz.resize(hp.used / sizeof(u128));
 				d2h(mz.data(), d_mz, hp.used);
@@ -832,6 +877,21 @@ static const Model *model_of(const mg_idx_t *gi) { return (const Model*)gi->B; }
 extern "C" void mg_idx_cal_quantile(const mg_idx_t *gi, int32_t m, float f[], int32_t q[])
 {
 	const Model *M = model_of(gi);
+#ifndef MGB_HOSTSIM
+	if (M->d_occ_sorted) { // the table was built on the device: the counts are there, sorted
+		const uint64_t n = M->n_keys;
+		for (int32_t i = 0; i < m; ++i) {
+			size_t kk = (size_t)((1.0 - (double)f[i]) * (double)n);
+			if (n == 0) { q[i] = 0; continue; }
+			if (kk >= n) kk = n - 1;
+			uint32_t v = 0;
+			cudaSetDevice(M->device);
+			cudaMemcpy(&v, M->d_occ_sorted + kk, 4, cudaMemcpyDeviceToHost);
+			q[i] = (int32_t)v;
+		}
+		return;
+	}
+#endif
 	std::vector<uint32_t> a(M->occ);
 	uint64_t n = a.size();
 	for (int32_t i = 0; i < m; ++i) {
@@ -845,7 +905,20 @@ extern "C" void mg_idx_cal_quantile(const mg_idx_t *gi, int32_t m, float f[], in
 
 extern "C" const uint64_t *mg_idx_get(const mg_idx_t *gi, uint64_t minier, int *n)
 {
-	const Model *M = model_of(gi);
+	Model *M = (Model*)model_of(gi);
+#ifndef MGB_HOSTSIM
+	if (M->slot.empty() && M->ix.slot) { // device-built table: the host view is fetched the first time somebody asks for it
+		std::lock_guard<std::mutex> lk(M->host_ix_mutex);
+		if (M->slot.empty()) {
+			cudaSetDevice(M->device);
+			M->pos.resize(M->n_pos? M->n_pos : 1);
+			cudaMemcpy(M->pos.data(), M->ix.pos, M->n_pos * 8, cudaMemcpyDeviceToHost);
+			std::vector<u128> sl(M->n_slots_mask + 1);
+			cudaMemcpy(sl.data(), M->ix.slot, sl.size() * sizeof(u128), cudaMemcpyDeviceToHost);
+			M->slot.swap(sl);
+		}
+	}
+#endif
 	IndexDev ix;
 	ix.k = M->k, ix.w = M->w, ix.n_slots_mask = M->n_slots_mask, ix.slot = M->slot.data(), ix.pos = M->pos.data();
 	return idx_get(ix, minier, n);
@@ -1245,6 +1318,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 
 	const bool use_lab = p_lab_cache && lab_prepare(M, o.bw_long);
 	int32_t *d_lab_new = 0; unsigned int *d_lab_n = 0; // this call's list of sources to search
+	Mail *mail = (Mail*)sl.h_mail.ensure(sizeof(Mail));
 	if (use_lab) { d_lab_n = (unsigned int*)sl.d_lab_new.ensure(((size_t)M->g.n_seg * 2 + 4) * sizeof(int32_t)); d_lab_new = (int32_t*)(d_lab_n + 4); }
 	for (int attempt = 0; attempt < 8; ++attempt) {
 		void *d_buf[N_POOLS];
@@ -1324,7 +1398,8 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 			} else { if (timed) tm_k[2].start(); launch_stage<2>(L, W); if (timed) tm_k[2].stop(); }
 			{ // bridging jobs planned by k_gchain, then materialisation
 				Pool pg;
-				d2h(&pg, &d_pools[P_GJOBS], sizeof(Pool));
+				fetch_mail(d_pools, d_jobq_n, d_lab_n, mail);
+				pg = mail->pools[P_GJOBS];
 				int64_t n_gj = (int64_t)(std::min<uint64_t>(pg.used, pg.cap) / sizeof(GwfaJob));
 				L.rid_list = 0, L.job_start = gjobs_done, L.n_work = (int32_t)(n_gj - gjobs_done);
 				if (L.n_work > 0) {
@@ -1344,7 +1419,8 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 			}
 			if (timed) tm_align.stop();
 			Pool pj;
-			d2h(&pj, &d_pools[P_JOBS], sizeof(Pool));
+			fetch_mail(d_pools, d_jobq_n, d_lab_n, mail);
+			pj = mail->pools[P_JOBS];
 			int64_t n_jobs = (int64_t)(std::min<uint64_t>(pj.used, pj.cap) / sizeof(WfaJob));
 			L.rid_list = 0, L.job_start = jobs_done, L.n_work = (int32_t)(n_jobs - jobs_done);
 			if (timed) tm_wfa.start();
@@ -1353,11 +1429,12 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 				int32_t *q = (int32_t*)sl.d_jobq.ensure(sizeof(int32_t) * 2 * (size_t)n_new);
 				L.c.jobq[0] = q, L.c.jobq[1] = q + n_new;
 				unsigned int qn[2] = {0, 0};
-				h2d(d_jobq_n, qn, sizeof(qn));
+				dzero(d_jobq_n, sizeof(qn));
 				{ if (timed) tm_k[4].start(); launch_stage<4>(L, W); if (timed) tm_k[4].stop(); }
-				d2h(qn, d_jobq_n, sizeof(qn));
+				fetch_mail(d_pools, d_jobq_n, d_lab_n, mail);
+				qn[0] = mail->jobq_n[0], qn[1] = mail->jobq_n[1];
 				S.n_launches += 1;
-				if (qn[0] > 0) { L.n_work = (int32_t)qn[0]; { if (timed) tm_k[6].start(); launch_stage<6>(L, W); if (timed) tm_k[6].stop(); } d2h(qn, d_jobq_n, sizeof(qn)); S.n_launches += 1; }
+				if (qn[0] > 0) { L.n_work = (int32_t)qn[0]; { if (timed) tm_k[6].start(); launch_stage<6>(L, W); if (timed) tm_k[6].stop(); } fetch_mail(d_pools, d_jobq_n, d_lab_n, mail); qn[0] = mail->jobq_n[0], qn[1] = mail->jobq_n[1]; S.n_launches += 1; }
 				if (qn[1] > 0) {
 					L.n_work = (int32_t)qn[1];
 					int32_t *order = (int32_t*)sl.d_order.ensure(sizeof(int32_t) * (size_t)L.n_work);
@@ -1419,8 +1496,9 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 				if (st == MGB_E_POOL) pool_full = true;
 			}
 		}
-		d2h(hp, d_pools, sizeof(hp));
-		if (use_lab) { unsigned int nn[2] = {0, 0}; d2h(nn, d_lab_n, sizeof(nn)); S.n_lab_new = (int64_t)nn[0], S.n_lab_big = (int64_t)nn[1]; lab_after_batch(M, nn[0]); }
+		fetch_mail(d_pools, d_jobq_n, d_lab_n, mail);
+		memcpy(hp, mail->pools, sizeof(hp));
+		if (use_lab) { unsigned int nn[2] = {mail->lab_n[0], mail->lab_n[1]}; S.n_lab_new = (int64_t)nn[0], S.n_lab_big = (int64_t)nn[1]; lab_after_batch(M, nn[0]); }
 		bool done = !pool_full;
 		if (done) { // blobs into read order, then to the host in pieces (the assembly below follows piece by piece)
 			tm_d2h.start();

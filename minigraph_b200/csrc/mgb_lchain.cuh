@@ -757,4 +757,22 @@ MG_HD inline int update_anchors(int32_t n_a, u128 *a, int32_t n, const int32_t *
 	return k == n_a? 0 : MGB_E_INTERNAL;
 }
 
+// update_anchors() entered by all lanes of a warp: one anchor per lane.  mini_pos[] (query positions of the kept minimizers) is
+// strictly ascending and so are the query positions along a chain, hence the sequential merge above pairs anchor k with THE entry
+// that equals its position: a binary search per anchor finds the same index.
+MG_HD inline int update_anchors_w(int32_t n_a, u128 *a, int32_t n, const int32_t *mini_pos, int lane)
+{
+	int bad = 0;
+	for (int32_t k = lane; k < n_a; k += MGB_W) {
+		const int32_t x = (int32_t)a[k].y;
+		int32_t lo = 0, hi = n;
+		while (lo < hi) { const int32_t m = (int32_t)(((uint32_t)lo + (uint32_t)hi) >> 1); if (mini_pos[m] < x) lo = m + 1; else hi = m; }
+		if (lo < n && mini_pos[lo] == x) a[k].x = (uint64_t)lo << 32 | (a[k].x & 0xffffffffULL);
+		else bad = 1;
+	}
+	bad = warp_any(bad);
+	warp_sync();
+	return bad? MGB_E_INTERNAL : 0;
+}
+
 } // namespace mgb

@@ -161,11 +161,13 @@ MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A, int lane, int32
 }
 
 // chain records, end trimming, bad-seed filters, anchor update, pool write (reference: map-algo.c:419-449); one lane
-MG_HD inline int stage_chain_tail(const PipeCtx &c, ReadMeta &m, Arena &A, u128 *a, const uint64_t *u, int32_t n_lc, int32_t n_a_new)
+// part 1 (one lane): chain records, end trimming, bad-seed filters; leaves the kept chains in lc_[0..*n_lc_) (in the arena)
+MG_HD inline int stage_chain_tail(const PipeCtx &c, ReadMeta &m, Arena &A, u128 *a, const uint64_t *u, int32_t n_lc, int32_t n_a_new, LChain **lc_, int32_t *n_lc_)
 {
 	const MapOptDev &o = c.opt;
 	m.n_a = n_lc > 0? n_a_new : 0;
 	m.n_lc = 0;
+	*lc_ = 0, *n_lc_ = 0;
 	if (n_lc > 0) {
 		LChain *lc;
 		MGB_ALLOC(A, lc, LChain, n_lc);
@@ -191,9 +193,15 @@ MG_HD inline int stage_chain_tail(const PipeCtx &c, ReadMeta &m, Arena &A, u128 
 			}
 			n_lc = n_new;
 		}
-		const int32_t *mp = c.minipos + m.mp_off;
-		for (int32_t i = 0; i < n_lc; ++i)
-			MGB_TRY(update_anchors(lc[i].cnt, &a[lc[i].off], m.n_mp, mp));
+		*lc_ = lc, *n_lc_ = n_lc;
+	}
+	return 0;
+}
+// part 2 (one lane, after the warp-wide anchor update): sources for graph chaining, chain records into the pool
+MG_HD inline int stage_chain_tail2(const PipeCtx &c, ReadMeta &m, const LChain *lc, int32_t n_lc)
+{
+	const MapOptDev &o = c.opt;
+	{
 		if (n_lc > 1 && c.lab.src_off) { // graph chaining will ask for walks out of these chains' vertices (gchain_dp_w applies the same test)
 			int32_t n_ext = 0;
 			for (int32_t i = 0; i < n_lc; ++i) n_ext += !gc_isolated(c.g, lc[i], o.bw_long);
@@ -291,13 +299,27 @@ MG_HD inline int chain_pass(const PipeCtx &c, int rid, Arena &H, Arena &A, u128 
 	}
 	unsigned long long t2 = prof_clock();
 	int rc = 0;
-	if (lane == 0) {
+	LChain *lc = 0;
+	int32_t n_keep_lc = 0;
+	{
 		Arena B = A;
-		rc = stage_chain_tail(c, m, B, a, u, n_lc, n_a_new);
-		if (B.peak > A.peak) A.peak = B.peak;
-		prof_add(c, PROF_CHAIN_POST_CYC, prof_clock() - t2);
+		if (lane == 0) rc = stage_chain_tail(c, m, B, a, u, n_lc, n_a_new, &lc, &n_keep_lc);
+		rc = warp_bcast_i32(rc, 0);
+		lc = (LChain*)warp_bcast_u64((uint64_t)lc, 0), n_keep_lc = warp_bcast_i32(n_keep_lc, 0);
+		A.top = warp_bcast_u64(B.top, 0);
+		const uint64_t pk = warp_bcast_u64(B.peak, 0);
+		if (pk > A.peak) A.peak = pk;
+		warp_sync();
 	}
-	rc = warp_bcast_i32(rc, 0);
+	if (rc == 0) { // minimizer indices into the anchors (reference: lchain.c:424-441), one anchor per lane
+		const int32_t *mp = c.minipos + m.mp_off;
+		for (int32_t i = 0; i < n_keep_lc && rc == 0; ++i) rc = update_anchors_w(lc[i].cnt, &a[lc[i].off], m.n_mp, mp, lane);
+	}
+	if (rc == 0) {
+		if (lane == 0 && lc) rc = stage_chain_tail2(c, m, lc, n_keep_lc);
+		rc = warp_bcast_i32(rc, 0);
+	}
+	if (lane == 0) prof_add(c, PROF_CHAIN_POST_CYC, prof_clock() - t2);
 	warp_sync();
 	run->n_keep = n_lc > 0? n_a_new : 0;
 	A.top = mark;

@@ -3,6 +3,10 @@ import hashlib
 import os
 
 import mgtest as T
+
+
+class capi_u128(__import__("ctypes").Structure):
+    _fields_ = [("x", __import__("ctypes").c_uint64), ("y", __import__("ctypes").c_uint64)]
 from minigraph_b200 import capi  # noqa: E402
 
 G = os.path.join(T.REPO, "tests", "golden")
@@ -11,6 +15,31 @@ G = os.path.join(T.REPO, "tests", "golden")
 def golden(name):
     with open(os.path.join(G, name), "rb") as f:
         return f.read()
+
+
+def golden_gz(name):
+    import gzip
+    with gzip.open(os.path.join(G, name), "rb") as f:
+        return f.read()
+
+
+def case_golden_large(lib, workdir, which=("L2", "L3", "L4")):
+    """the larger golden sets (tests/golden/make_golden.sh): 240 x 10 kb reads on test/MT.gfa, 240 x 15 kb on an SV graph as dense as
+    the bench's MHC-scale one (1 Mb, 8 haplotypes), 200 x 20 kb HiFi-error reads with the asm preset; GAF text byte for byte"""
+    if "L2" in which:
+        hap, reads = os.path.join(workdir, "mt.hap.fa"), os.path.join(workdir, "mtL.reads.fa")
+        T.sim_mt_haps(hap)
+        T.sim_reads(hap, reads, 240, 10000, "ont", 111)
+        check_gaf(lib, os.path.join(T.FIX, "MT.gfa"), reads, "lr", golden_gz("L2_MT_240x10k_ont_s111.lr.gaf.gz"))
+    if "L3" in which:
+        pre, reads = os.path.join(workdir, "svL"), os.path.join(workdir, "svL.reads.fa")
+        T.sim_graph(pre, 1000000, 8, 7)
+        T.sim_reads(pre + ".hap.fa", reads, 240, 15000, "ont", 105)
+        check_gaf(lib, pre + ".gfa", reads, "lr", golden_gz("L3_sv1m_h8_s7_240x15k_ont_s105.lr.gaf.gz"))
+    if "L4" in which:
+        reads = os.path.join(workdir, "mthL.reads.fa")
+        T.sim_reads(os.path.join(T.FIX, "MT-human.fa"), reads, 200, 20000, "hifi", 113, circular=True)
+        check_gaf(lib, os.path.join(T.FIX, "MT-human.fa"), reads, "asm", golden_gz("L4_MThuman_200x20k_hifi_s113.asm.gaf.gz"))
 
 
 def first_diff(a, b):
@@ -392,6 +421,70 @@ def case_concurrent_calls(lib, workdir, n_threads=3, n_reads=90):
                 assert d is None, "round %d read %d: %s" % (rnd, lo + i, d)
     lib.mg_idx_destroy(gi)
     lib.mgb_gfa_destroy(g)
+
+
+def case_index_big(lib, workdir, graph_len=50000000, n_probe=40000):
+    """the minimizer table of a graph whose index does not fit L2 (built on the device, mgb_index.cuh) against the reference's
+    (index.c:115-165): the same occurrence list -- content and order -- for tens of thousands of probed minimizers and for keys
+    that are not there, the same quantile-derived mapping options (options.c:120-134), and the switch back to the host build"""
+    import ctypes as C
+    import random
+    from minigraph_b200 import options
+    pre = os.path.join(workdir, "big")
+    T.sim_graph(pre, graph_len, 3, 17)
+    with open(pre + ".gfa") as f:  # repeats: sixty segments once more under another name, so that many minimizers have occurrence lists
+        dup = [ln.split("\t") for ln in f if ln.startswith("S\t")][100:160]
+    with open(pre + ".gfa", "a") as f:
+        for i, t in enumerate(dup):
+            f.write("\t".join([t[0], "dup%d" % i] + t[2:]))
+    ref = T.load_ref()
+    rg = ref.gfa_read((pre + ".gfa").encode())
+    io, rmo = options.opt_set("lr")
+    rgi = ref.mg_index(rg, C.byref(io), 8, C.byref(rmo))
+    assert rgi
+    ref.mg_idx_get.restype = C.POINTER(C.c_uint64)
+    # probes: the minimizers of random stretches of the graph (through the reference's own sketch), plus random keys
+    ref.mg_sketch.restype = None
+    ref.mg_sketch.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p]
+
+    class V(C.Structure):
+        _fields_ = [("n", C.c_size_t), ("m", C.c_size_t), ("a", C.POINTER(capi_u128))]
+    rnd = random.Random(5)
+    keys = set()
+    n_seg = rg.contents.n_seg
+    while len(keys) < n_probe:
+        seg = rg.contents.seg[rnd.randrange(n_seg) if len(keys) % 4 else n_seg - 1 - rnd.randrange(60)]
+        if seg.len < 200:
+            continue
+        st = rnd.randrange(seg.len - 199)
+        v = V(0, 0, None)
+        ref.mg_sketch(None, C.string_at(C.addressof(seg.seq.contents) + st, 200) if False else C.string_at(seg.seq, seg.len)[st:st + 200], 200, io.w, io.k, 0, C.byref(v))
+        for i in range(v.n):
+            keys.add(v.a[i].x >> 8)
+        C.CDLL(None).free(v.a)
+    keys = sorted(keys) + [rnd.getrandbits(2 * io.k) for _ in range(2000)]
+    n1, n2 = C.c_int(0), C.c_int(0)
+    for index_dev in (1, 0):
+        assert lib.mgb_set_param(b"index_dev", index_dev) == 0
+        try:
+            g = lib.mgb_gfa_read((pre + ".gfa").encode())
+            io2, mo = options.opt_set("lr")
+            gi = lib.mg_index(g, C.byref(io2), 1, C.byref(mo))
+            assert gi, lib.mgb_last_error()
+            assert (mo.occ_max1, mo.lc_max_occ, mo.bw_long) == (rmo.occ_max1, rmo.lc_max_occ, rmo.bw_long)
+            n_multi = 0
+            for k in keys:
+                a, b = ref.mg_idx_get(rgi, k, C.byref(n1)), lib.mg_idx_get(gi, k, C.byref(n2))
+                assert n1.value == n2.value, (hex(k), n1.value, n2.value)
+                assert [a[i] for i in range(n1.value)] == [b[i] for i in range(n2.value)], hex(k)
+                n_multi += n1.value > 1
+            assert n_multi > 100, n_multi
+            lib.mg_idx_destroy(gi)
+            lib.mgb_gfa_destroy(g)
+        finally:
+            lib.mgb_set_param(b"index_dev", 1)
+    ref.mg_idx_destroy(rgi)
+    ref.gfa_destroy(rg)
 
 
 def case_multi_device(lib, workdir, devices="0,0,0", n_reads=100):

@@ -32,6 +32,10 @@ def test_c4_asm_preset(lib, workdir):
     cases.case_c4(lib, workdir)
 
 
+def test_larger_golden_sets(lib, workdir):
+    cases.case_golden_large(lib, workdir)
+
+
 def test_edge_reads(lib, workdir):
     cases.case_edge(lib, workdir)
 
@@ -62,6 +66,11 @@ def test_engine_switches_keep_results(lib, workdir):
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not there")
 def test_upload_modes(lib, workdir):
     cases.case_upload_modes(lib, workdir)
+
+
+@pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not shipped")
+def test_index_of_a_50mb_graph(lib, workdir):
+    cases.case_index_big(lib, workdir)
 
 
 def test_index_on_several_devices(lib, workdir):
