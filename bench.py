@@ -399,6 +399,7 @@ def main():
     if world > 1:
         dist.barrier()
     e2e_acc = dict(acc)
+    kern_e2e = list(kern)
     # ---- timed region 2: the kernels alone (CUDA events), mini-batches one after the other ----
     for k in acc:
         acc[k] = 0
@@ -474,6 +475,7 @@ def main():
         "mini_batches_per_step": M, "pipe_threads": n_pipe, "host_threads": host_threads, "gaf_threads": gaf_threads, "host_cores": ncores,
         "engine_params": capi.env_params(), "index_build_s": t_index,
         "kernel_ms_per_step": {k: round(kern[i] / a.steps, 3) for i, k in enumerate(capi.KERNEL_NAMES) if k != "k_index_sketch"},
+        "kernel_ms_per_step_in_e2e_region": {k: round(kern_e2e[i] / a.steps, 3) for i, k in enumerate(capi.KERNEL_NAMES) if k != "k_index_sketch"},
         "kernel_ms_note": "CUDA-event time of each kernel summed over the %d mini-batches of a step, second timed region (kernels of one mini-batch at a time)" % M,
         "wfa_jobs_per_step": acc["jobs"] // a.steps, "label_sources_new_in_timed_steps": acc["lab_new"],
         "e2e": {"value": e2e, "unit": "Gbp/s", "ms_per_step": t_wall / a.steps * 1e3,

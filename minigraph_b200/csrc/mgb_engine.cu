@@ -350,8 +350,9 @@ MG_HD inline uint32_t order_key(const LaunchArgs &L, int kind, const int32_t *q,
 	return (uint32_t)(J.tl + J.ql);
 }
 #ifndef MGB_HOSTSIM
-__global__ void __launch_bounds__(1024) k_job_order(LaunchArgs L, int kind, const int32_t *q, int n, int32_t *order)
+__global__ void __launch_bounds__(1024) k_job_order(LaunchArgs L, int kind, const int32_t *q, int n, const unsigned int *n_dev, int32_t *order)
 {
+	if (n_dev) n = (int)*n_dev;
 	__shared__ unsigned int cnt[64];
 	const int tid = threadIdx.x;
 	if (tid < 64) cnt[tid] = 0;
@@ -363,12 +364,13 @@ __global__ void __launch_bounds__(1024) k_job_order(LaunchArgs L, int kind, cons
 	for (int i = tid; i < n; i += 1024) order[atomicAdd(&cnt[order_bin(order_key(L, kind, q, i))], 1u)] = i;
 }
 #endif
-static void make_job_order(const LaunchArgs &L, int kind, const int32_t *q, int n, int32_t *order)
+static void make_job_order(const LaunchArgs &L, int kind, const int32_t *q, int n, int32_t *order, const unsigned int *n_dev = 0)
 {
 #ifndef MGB_HOSTSIM
-	k_job_order<<<1, 1024, 0, t_stream>>>(L, kind, q, n, order);
+	k_job_order<<<1, 1024, 0, t_stream>>>(L, kind, q, n, n_dev, order);
 	CUDA_OK(cudaGetLastError());
 #else
+	if (n_dev) n = (int)*n_dev;
 	unsigned int cnt[65] = {0};
 	for (int i = 0; i < n; ++i) ++cnt[order_bin(order_key(L, kind, q, i)) + 1];
 	for (int b = 0; b < 64; ++b) cnt[b + 1] += cnt[b];
@@ -538,6 +540,16 @@ __global__ void k_mail(const Pool *pools, const unsigned int *jobq_n, const unsi
 	if (t < 2) out->jobq_n[t] = jobq_n[t], out->lab_n[t] = lab_n? lab_n[t] : 0;
 	__threadfence_system();
 }
+#endif
+// how many bridging jobs / gap jobs the kernels in front have appended to their pools since `done`: the job kernels read it on the device
+MG_HD inline void job_counts(const Pool *pools, int i_gjobs, int i_jobs, unsigned int gjobs_done, unsigned int jobs_done, unsigned int *cnt)
+{
+	const Pool &pg = pools[i_gjobs], &pj = pools[i_jobs];
+	cnt[0] = (unsigned int)((pg.used < pg.cap? pg.used : pg.cap) / sizeof(GwfaJob)) - gjobs_done;
+	cnt[1] = (unsigned int)((pj.used < pj.cap? pj.used : pj.cap) / sizeof(WfaJob)) - jobs_done;
+}
+#ifndef MGB_HOSTSIM
+__global__ void k_job_counts(const Pool *pools, int i_gjobs, int i_jobs, unsigned int gjobs_done, unsigned int jobs_done, unsigned int *cnt) { job_counts(pools, i_gjobs, i_jobs, gjobs_done, jobs_done, cnt); }
 #endif
 static void fetch_mail(const Pool *d_pools, const unsigned int *d_jobq_n, const unsigned int *d_lab_n, Mail *mail)
 {
@@ -1259,6 +1271,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	unsigned int *d_next = (unsigned int*)dsm;
 	unsigned int *d_jobq_n = d_next + 4;
 	unsigned int *d_rescue_n = d_next + 8;
+	unsigned int *d_cnt = d_next + 10; // [0] bridging jobs, [1] gap jobs the next job kernel has to take
 	unsigned long long *d_prof = (unsigned long long*)(dsm + 64);
 	Pool *d_pools = (Pool*)(dsm + 64 + sizeof(unsigned long long) * PROF_N);
 	unsigned int *d_tier_hist = (unsigned int*)((char*)(d_pools + 16) + 64); // 32 x 4 counters behind the pool headers
@@ -1326,6 +1339,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 		for (int i = 0; i < N_POOLS; ++i) d_buf[i] = sl.d_pool[i].ensure(cap[i]), hp[i].used = 0, hp[i].cap = cap[i];
 		h2d(d_pools, hp, sizeof(hp));
 		dfill(d_buf[P_GJOBS], 0xff, cap[P_GJOBS]); // reserved-but-unused bridging job slots read as rid == -1
+		dfill(d_buf[P_JOBS], 0xff, cap[P_JOBS]);   // the same for gap jobs: slots of an allocation that overflowed the pool are never written
 		LaunchArgs L;
 		memset(&L, 0, sizeof(L));
 		L.c.g = M->g, L.c.ix = M->ix, L.c.opt = o;
@@ -1356,6 +1370,9 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 		L.c.jobq[0] = 0, L.c.jobq[1] = 0, L.c.jobq_n = d_jobq_n;
 		L.routs = d_routs;
 		int64_t jobs_done = 0, gjobs_done = 0;
+		const int64_t max_jobs = (int64_t)(cap[P_JOBS] / sizeof(WfaJob)) + 1, max_gjobs = (int64_t)(cap[P_GJOBS] / sizeof(GwfaJob)) + 1;
+		int32_t *jobq_buf = (int32_t*)sl.d_jobq.ensure(sizeof(int32_t) * 2 * (size_t)max_jobs);
+		int32_t *order_buf = (int32_t*)sl.d_order.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(std::max<int64_t>(max_jobs, max_gjobs), n_reads));
 		// one pass over a set of reads; job counts are read back between the planning and the job kernels
 		auto run_pass = [&](const int32_t *d_list, int32_t n_list, const Workers &W, bool timed) {
 			L.rid_list = d_list, L.n_work = n_list;
@@ -1387,69 +1404,56 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 				S.n_launches += 2;
 			}
 			if (d_list == 0 && n_list >= 1024) { // whole batch: reads with many linear chains first (a few of them set the time of this kernel)
-				int32_t *order = (int32_t*)sl.d_order.ensure(sizeof(int32_t) * (size_t)n_list);
 				if (timed) tm_k[2].start();
-				make_job_order(L, 2, 0, n_list, order);
-				L.rid_list = order;
+				make_job_order(L, 2, 0, n_list, order_buf);
+				L.rid_list = order_buf;
 				launch_stage<2>(L, W);
 				L.rid_list = d_list;
 				if (timed) tm_k[2].stop();
 				S.n_launches += 1;
 			} else { if (timed) tm_k[2].start(); launch_stage<2>(L, W); if (timed) tm_k[2].stop(); }
+			auto counts = [&]() {
+#ifndef MGB_HOSTSIM
+				k_job_counts<<<1, 1, 0, t_stream>>>(d_pools, (int)P_GJOBS, (int)P_JOBS, (unsigned int)gjobs_done, (unsigned int)jobs_done, d_cnt);
+				CUDA_OK(cudaGetLastError());
+#else
+				job_counts(d_pools, (int)P_GJOBS, (int)P_JOBS, (unsigned int)gjobs_done, (unsigned int)jobs_done, d_cnt);
+#endif
+			};
+			// From here on every kernel reads its number of units on the device: the whole pass is queued without a host round trip, so
+			// nothing another thread does in the driver (large copies, blocking waits) can open gaps between its kernels.
 			{ // bridging jobs planned by k_gchain, then materialisation
-				Pool pg;
-				fetch_mail(d_pools, d_jobq_n, d_lab_n, mail);
-				pg = mail->pools[P_GJOBS];
-				int64_t n_gj = (int64_t)(std::min<uint64_t>(pg.used, pg.cap) / sizeof(GwfaJob));
-				L.rid_list = 0, L.job_start = gjobs_done, L.n_work = (int32_t)(n_gj - gjobs_done);
-				if (L.n_work > 0) {
-					int32_t *order = (int32_t*)sl.d_order.ensure(sizeof(int32_t) * (size_t)L.n_work);
-					if (timed) tm_k[8].start();
-					make_job_order(L, 0, 0, L.n_work, order);
-					L.rid_list = order;
-					launch_stage<8>(L, W);
-					L.rid_list = 0;
-					if (timed) tm_k[8].stop();
-					S.n_launches += 2;
-				}
-				gjobs_done = n_gj;
-				L.rid_list = d_list, L.n_work = n_list;
+				counts();
+				L.rid_list = 0, L.job_start = gjobs_done, L.n_work = 0, L.n_work_dev = d_cnt;
+				if (timed) tm_k[8].start();
+				make_job_order(L, 0, 0, 0, order_buf, d_cnt);
+				L.rid_list = order_buf;
+				launch_stage<8>(L, W);
+				if (timed) tm_k[8].stop();
+				L.rid_list = d_list, L.n_work = n_list, L.n_work_dev = 0;
 				{ if (timed) tm_k[9].start(); launch_stage<9>(L, W); if (timed) tm_k[9].stop(); }
-				S.n_launches += 1;
+				S.n_launches += 4;
 			}
 			if (timed) tm_align.stop();
-			Pool pj;
-			fetch_mail(d_pools, d_jobq_n, d_lab_n, mail);
-			pj = mail->pools[P_JOBS];
-			int64_t n_jobs = (int64_t)(std::min<uint64_t>(pj.used, pj.cap) / sizeof(WfaJob));
-			L.rid_list = 0, L.job_start = jobs_done, L.n_work = (int32_t)(n_jobs - jobs_done);
 			if (timed) tm_wfa.start();
-			if (L.n_work > 0) { // three tiers; a job that does not fit one tier is queued for the next
-				int32_t n_new = L.n_work;
-				int32_t *q = (int32_t*)sl.d_jobq.ensure(sizeof(int32_t) * 2 * (size_t)n_new);
-				L.c.jobq[0] = q, L.c.jobq[1] = q + n_new;
-				unsigned int qn[2] = {0, 0};
-				dzero(d_jobq_n, sizeof(qn));
+			{ // three tiers; a job that does not fit one tier is queued for the next
+				counts();
+				L.c.jobq[0] = jobq_buf, L.c.jobq[1] = jobq_buf + max_jobs;
+				dzero(d_jobq_n, 2 * sizeof(unsigned int));
+				L.rid_list = 0, L.job_start = jobs_done, L.n_work = 0, L.n_work_dev = d_cnt + 1;
 				{ if (timed) tm_k[4].start(); launch_stage<4>(L, W); if (timed) tm_k[4].stop(); }
-				fetch_mail(d_pools, d_jobq_n, d_lab_n, mail);
-				qn[0] = mail->jobq_n[0], qn[1] = mail->jobq_n[1];
-				S.n_launches += 1;
-				if (qn[0] > 0) { L.n_work = (int32_t)qn[0]; { if (timed) tm_k[6].start(); launch_stage<6>(L, W); if (timed) tm_k[6].stop(); } fetch_mail(d_pools, d_jobq_n, d_lab_n, mail); qn[0] = mail->jobq_n[0], qn[1] = mail->jobq_n[1]; S.n_launches += 1; }
-				if (qn[1] > 0) {
-					L.n_work = (int32_t)qn[1];
-					int32_t *order = (int32_t*)sl.d_order.ensure(sizeof(int32_t) * (size_t)L.n_work);
-					if (timed) tm_k[7].start();
-					make_job_order(L, 1, L.c.jobq[1], L.n_work, order);
-					L.rid_list = order;
-					launch_stage<7>(L, W);
-					L.rid_list = 0;
-					if (timed) tm_k[7].stop();
-					S.n_launches += 2;
-				}
-				if (timed) S.n_jobs_mid = qn[0], S.n_jobs_big = qn[1];
+				L.n_work_dev = d_jobq_n;
+				{ if (timed) tm_k[6].start(); launch_stage<6>(L, W); if (timed) tm_k[6].stop(); }
+				L.n_work_dev = d_jobq_n + 1;
+				if (timed) tm_k[7].start();
+				make_job_order(L, 1, L.c.jobq[1], 0, order_buf, d_jobq_n + 1);
+				L.rid_list = order_buf;
+				launch_stage<7>(L, W);
+				if (timed) tm_k[7].stop();
+				L.rid_list = 0, L.n_work_dev = 0;
+				S.n_launches += 5;
 			}
 			if (timed) tm_wfa.stop(), tm_fin.start();
-			jobs_done = n_jobs;
 			L.rid_list = d_list, L.n_work = n_list;
 			{ if (timed) tm_k[5].start(); launch_stage<5>(L, W); if (timed) tm_k[5].stop(); }
 			if (timed) tm_fin.stop();
@@ -1457,7 +1461,10 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 #ifndef MGB_HOSTSIM
 			CUDA_OK(cudaEventRecord(sl.ev_last, t_stream));
 #endif
-			dsync();
+			fetch_mail(d_pools, d_jobq_n, d_lab_n, mail); // (also the one wait of the pass)
+			gjobs_done = (int64_t)(std::min<uint64_t>(mail->pools[P_GJOBS].used, mail->pools[P_GJOBS].cap) / sizeof(GwfaJob));
+			jobs_done = (int64_t)(std::min<uint64_t>(mail->pools[P_JOBS].used, mail->pools[P_JOBS].cap) / sizeof(WfaJob));
+			if (timed) S.n_jobs_mid = mail->jobq_n[0], S.n_jobs_big = mail->jobq_n[1];
 		};
 		{
 			const double tq = now_ms();

@@ -60,6 +60,7 @@ static const uint64_t PLAN_JOB = 1ULL << 63;
 MG_HD inline int wfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int lane, int32_t *smem, int tier)
 {
 	WfaJob *J = &c.jobs[job_idx];
+	if (J->rid < 0) return 0; // a slot no read wrote (its allocation ran over the end of the pool; the batch is re-run with a larger one)
 	const int32_t rid = J->rid, l0 = J->l0, l = J->l, tl = J->tl, ql = J->ql;
 	if (c.meta[rid].status < 0) return 0; // the read already failed elsewhere; it will be redone as a whole
 	// Routing: a gap that cannot finish in an on-chip tier costs that tier up to a full window of cells before it gives up.
