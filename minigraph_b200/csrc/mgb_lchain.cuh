@@ -377,6 +377,8 @@ MG_HD inline double warp_min_f64(double x)
 	return x;
 }
 
+struct RmqBlock { double best; int32_t cnt, j, ymin, ymax; };
+
 MG_HD inline int chain_rmq_fill_w(Arena &H, Arena &A, int max_dist, int max_dist_inner, int bw, int max_chn_skip, float pen_gap, float pen_skip,
 								  int64_t n, const u128 *a, int32_t *f, int32_t *p, int32_t *t, int32_t *v, int lane)
 {
@@ -385,6 +387,13 @@ MG_HD inline int chain_rmq_fill_w(Arena &H, Arena &A, int max_dist, int max_dist
 	uint64_t *K; // inner window, keys y<<32|idx ascending
 	MGB_ALLOC_HOT(H, A, pri, double, n);
 	MGB_ALLOC_HOT(H, A, K, uint64_t, n);
+	// Summaries of the available anchors in blocks of 32 consecutive indices: the smallest priority, how many hold it and one of
+	// them, and the span of query positions.  The outer query then looks at one summary per block and at the elements of the
+	// few blocks that straddle a border of the window, instead of at every anchor of the window.
+	RmqBlock *blk;
+	const int64_t n_blk = (n + 31) >> 5;
+	MGB_ALLOC_HOT(H, A, blk, RmqBlock, n_blk);
+	for (int64_t b = lane; b < n_blk; b += MGB_W) { RmqBlock e; e.best = 1e300, e.cnt = 0, e.j = -1, e.ymin = INT32_MAX, e.ymax = INT32_MIN; blk[b] = e; }
 	int32_t nK = 0;
 	int64_t i, i0 = 0, st = 0, st_inner = 0;
 	for (i = lane; i < n; i += MGB_W) t[i] = 0;
@@ -398,9 +407,23 @@ MG_HD inline int chain_rmq_fill_w(Arena &H, Arena &A, int max_dist, int max_dist
 		if (i0 < i && a[i0].x != xi) {
 			for (int64_t j = i0; j < i; ++j) {
 				const uint64_t xj = a[j].x, yj = a[j].y;
-				if (lane == 0) pri[j] = -(f[j] + 0.5 * pen_gap * ((int32_t)xj + (int32_t)yj));
+				if (lane == 0) {
+					const double pj = -(f[j] + 0.5 * pen_gap * ((int32_t)xj + (int32_t)yj));
+					RmqBlock &B = blk[j >> 5];
+					pri[j] = pj;
+					if (pj < B.best) B.best = pj, B.cnt = 1, B.j = (int32_t)j;
+					else if (pj == B.best) ++B.cnt;
+					if ((int32_t)yj < B.ymin) B.ymin = (int32_t)yj;
+					if ((int32_t)yj > B.ymax) B.ymax = (int32_t)yj;
+				}
 				if (max_dist_inner > 0) { // insert (y,idx) into the sorted inner window
 					const uint64_t key = (uint64_t)(uint32_t)(int32_t)yj << 32 | (uint64_t)(uint32_t)j;
+					if (nK == 0 || K[nK - 1] < key) { // colinear anchors arrive in ascending query order: the new key goes on top
+						if (lane == 0) K[nK] = key;
+						++nK;
+						warp_sync();
+						continue;
+					}
 					int32_t cnt = 0;
 					for (int32_t x = lane; x < nK; x += MGB_W) cnt += K[x] < key;
 					const int32_t pos = warp_sum_i32(cnt);
@@ -426,6 +449,7 @@ MG_HD inline int chain_rmq_fill_w(Arena &H, Arena &A, int max_dist, int max_dist
 			while (st_inner < i && (xi >> 32 != a[st_inner].x >> 32 || xi > a[st_inner].x + (uint64_t)max_dist_inner)) {
 				if (st_inner < i0) { // it is in the window: remove its key
 					const uint64_t key = (uint64_t)(uint32_t)(int32_t)a[st_inner].y << 32 | (uint64_t)(uint32_t)st_inner;
+					if (K[0] == key) { ++K, --nK, ++st_inner; continue; } // ... and leave from the bottom: the window is a queue, its array slides
 					int32_t cnt = 0;
 					for (int32_t x = lane; x < nK; x += MGB_W) cnt += K[x] < key;
 					const int32_t pos = warp_sum_i32(cnt);
@@ -447,13 +471,32 @@ MG_HD inline int chain_rmq_fill_w(Arena &H, Arena &A, int max_dist, int max_dist
 			const int64_t hi_j = st < i0? i0 : st; // window [st, i0)
 			double best = 1e300;
 			int32_t best_j = -1, n_best = 0;
-			for (int64_t j = st + lane; j < hi_j; j += MGB_W) {
-				const int32_t yj = (int32_t)a[j].y;
-				if (!(yj > yi - max_dist)) continue;
-				if (!(yj < yi - 1 || (yj == yi - 1 && j == 0))) continue;
-				const double pj = pri[j];
-				if (pj < best) best = pj, best_j = (int32_t)j, n_best = 1;
-				else if (pj == best) ++n_best;
+			for (int64_t b0 = st >> 5; (b0 << 5) < hi_j; b0 += MGB_W) {
+				const int64_t b = b0 + lane;
+				int kind = 0; // 0: nothing of this block qualifies, 1: all of it does (the summary answers), 2: look at its elements
+				if ((b << 5) < hi_j) {
+					const RmqBlock B = blk[b];
+					if (B.cnt > 0 && B.ymax > yi - max_dist && B.ymin <= yi - 1 && !(B.ymin == yi - 1 && b != 0))
+						kind = (b << 5) >= st && B.ymin > yi - max_dist && B.ymax < yi - 1? 1 : 2;
+					if (kind == 1) {
+						if (B.best < best) best = B.best, best_j = B.j, n_best = B.cnt;
+						else if (B.best == best) n_best += B.cnt;
+					}
+				}
+				uint32_t scan = warp_ballot(kind == 2);
+				while (scan) { // a block on a border of the window: its elements, one per lane
+					const int64_t j0 = (b0 + ctz32(scan)) << 5;
+					scan &= scan - 1;
+					for (int64_t j = j0 + lane; j < j0 + 32; j += MGB_W) {
+						if (j < st || j >= hi_j) continue;
+						const int32_t yj = (int32_t)a[j].y;
+						if (!(yj > yi - max_dist)) continue;
+						if (!(yj < yi - 1 || (yj == yi - 1 && j == 0))) continue;
+						const double pj = pri[j];
+						if (pj < best) best = pj, best_j = (int32_t)j, n_best = 1;
+						else if (pj == best) ++n_best;
+					}
+				}
 			}
 			const double gbest = warp_min_f64(best);
 			const int32_t n_at_min = warp_sum_i32(best_j >= 0 && best == gbest? n_best : 0);

@@ -7,4 +7,7 @@ timeout 600 python bench.py $B --pipe 1 > $O/p1.json 2> $O/p1.err
 timeout 600 python bench.py $B --pipe 2 > $O/p2.json 2> $O/p2.err
 timeout 600 python bench.py $B --pipe 3 > $O/p3.json 2> $O/p3.err
 timeout 600 python bench.py --workload c2 --steps 5 --warmup 3 --no-cpu > $O/c2.json 2> $O/c2.err
+timeout 600 python bench.py $B --pipe 2 --mini-batch 800000000 > $O/p2_mb800.json 2> $O/p2_mb800.err
+MGB_PARAMS=gpu_lock=0 timeout 600 python bench.py $B --pipe 2 > $O/p2_nolock.json 2> $O/p2_nolock.err
+timeout 900 python bench.py --workload c4 --reads 20000 --steps 2 --warmup 1 --no-cpu > $O/c4.json 2> $O/c4.err
 tail -5 $O/pytest.log
