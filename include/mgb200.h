@@ -261,6 +261,13 @@ const char *mgb_version(void);
 gfa_t *mgb_gfa_read(const char *fn);
 void mgb_gfa_destroy(gfa_t *g);
 
+/* Input side for hosts without the reference's bseq.c: a whole FASTA/FASTQ file (plain or gzip, "-" = stdin) parsed by kseq.h's rules
+ * (bseq.c:46-98) and upper-cased (gmap.c:81) into the arrays mg_map_batch() takes.  max_bases > 0 stops after the record that
+ * reaches it (the reference's mini-batch rule, bseq.c:70-72).  NULL if the file cannot be opened. */
+typedef struct { int64_t n_reads, n_bases; const char **name, **seq; int *len; char *block; } mgb_reads_t;
+mgb_reads_t *mgb_reads_load(const char *fn, int64_t max_bases);
+void mgb_reads_free(mgb_reads_t *r);
+
 /* Byte-exact GAF line(s) for one read, restating format.c:121-291 mg_write_gaf() for flag bits used by -c. The text is
  * appended to *buf (realloc()ed; *len and *cap updated). */
 void mgb_write_gaf(char **buf, size_t *len, size_t *cap, const gfa_t *g, const mg_gchains_t *gs, int32_t qlen, const char *qname, uint64_t flag);

@@ -95,6 +95,11 @@ class mgb_stats_t(C.Structure):
                 ("w_gpu_wait_ms", C.c_double), ("w_slot_wait_ms", C.c_double), ("w_upload_ms", C.c_double), ("w_pass_ms", C.c_double), ("w_redo_ms", C.c_double), ("w_download_ms", C.c_double)]
 
 
+class mgb_reads_t(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("n_bases", C.c_int64), ("name", C.POINTER(C.c_char_p)), ("seq", C.POINTER(C.c_char_p)),
+                ("len", C.POINTER(C.c_int)), ("block", C.c_void_p)]
+
+
 KERNEL_NAMES = ["k_seed", "k_chain", "k_gchain", "k_index_sketch", "k_wfa_small", "k_finish", "k_wfa_mid", "k_wfa_big", "k_gwfa", "k_gchain_gen"]
 PROF_NAMES = ["wfa_fast_cyc", "wfa_fast_n", "wfa_slow_cyc", "wfa_slow_n", "wfa_max_cyc", "wfa_cells", "wfa_tb_cyc", "gc_dp_cyc", "gc_gen_cyc",
               "gc_post_cyc", "gc_plan_cyc", "fin_cigar_cyc", "fin_ds_cyc", "seed_sketch_cyc", "seed_match_cyc", "seed_sort_cyc", "chain_dp_cyc",
@@ -169,6 +174,10 @@ def bind_engine_api(lib):
     lib.mg_map_batch_frag.restype = C.c_int
     lib.mg_map_batch_frag.argtypes = [C.POINTER(mg_idx_t), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_char_p), C.POINTER(C.c_char_p),
                                       C.POINTER(C.POINTER(mg_gchains_t)), C.POINTER(mg_mapopt_t)]
+    lib.mgb_reads_load.restype = C.POINTER(mgb_reads_t)
+    lib.mgb_reads_load.argtypes = [C.c_char_p, C.c_int64]
+    lib.mgb_reads_free.restype = None
+    lib.mgb_reads_free.argtypes = [C.POINTER(mgb_reads_t)]
     lib.mgb_free_batch.restype = None
     lib.mgb_free_batch.argtypes = [C.c_int, C.POINTER(C.POINTER(mg_gchains_t))]
     lib.mgb_write_gaf_batch.restype = None

@@ -665,6 +665,7 @@ struct Model {
 		cudaStream_t stream;
 		cudaEvent_t ev_first, ev_last, ev_piece[4];
 #endif
+		struct SlotTimers *timers = 0;
 		bool ready;
 		Slot() : ready(false) { memset(&W, 0, sizeof(W)); }
 	};
@@ -683,6 +684,8 @@ struct Model {
 	uint64_t lab_cap = 0; int32_t lab_max_dist_g = -1; int64_t lab_sources = 0;
 };
 
+struct SlotTimers;
+static void timers_free(SlotTimers *t);
 static void model_free(Model *M)
 {
 	for (Model *P : M->peers) model_free(P);
@@ -701,6 +704,7 @@ static void model_free(Model *M)
 		Model::Slot &sl = M->slots[k];
 		sl.h_seq.release(), sl.h_out.release(), sl.h_small.release(), sl.h_pk.release(), sl.h_mail.release(), sl.d_pk.release(), sl.d_seq.release(), sl.d_meta.release(), sl.d_routs.release(), sl.d_small.release(), sl.d_jobq.release(), sl.d_order.release(), sl.d_packed.release(), sl.d_packoff.release(), sl.d_segs.release(), sl.d_lab_new.release();
 		for (int i = 0; i < 10; ++i) sl.d_pool[i].release();
+		if (sl.timers) timers_free(sl.timers);
 		if (sl.W.arena) dfree(sl.W.arena);
 		if (sl.W.peak) dfree(sl.W.peak);
 #ifndef MGB_HOSTSIM
@@ -1049,10 +1053,18 @@ struct EvTimer {
 	void start() { cudaEventRecord(a, t_stream); used = true; }
 	void stop() { cudaEventRecord(b, t_stream); }
 	double ms() { if (!used) return 0; float t = 0; cudaEventSynchronize(b); cudaEventElapsedTime(&t, a, b); return t; }
+	void clear() { used = false; }
 };
 #else
-struct EvTimer { double t0 = 0, t1 = 0; void start() { t0 = now_ms(); } void stop() { t1 = now_ms(); } double ms() { return t1 - t0; } };
+struct EvTimer { double t0 = 0, t1 = 0; void start() { t0 = now_ms(); } void stop() { t1 = now_ms(); } double ms() { return t1 - t0; } void clear() { t0 = t1 = 0; } };
 #endif
+
+struct SlotTimers {
+	EvTimer h2d, seed, chain, align, wfa, fin, d2h, lab, k[10];
+	void reset() { EvTimer *all[] = {&h2d, &seed, &chain, &align, &wfa, &fin, &d2h, &lab}; for (EvTimer *t : all) t->clear(); for (int i = 0; i < 10; ++i) k[i].clear(); }
+};
+
+static void timers_free(SlotTimers *t) { delete t; }
 
 static void fill_opt(MapOptDev &o, const mg_mapopt_t *opt, int k)
 {
@@ -1113,23 +1125,26 @@ static mg_gchains_t *build_result(const ReadOut &ro, const char *pool)
 // The label table of graph chaining: allocated at the first batch, emptied when a batch asks for longer walks than it was built for.
 static bool lab_prepare(Model *M, int32_t max_dist_g)
 {
-	std::lock_guard<std::mutex> lock(M->big_mutex);
+	std::unique_lock<std::mutex> lock(M->big_mutex);
 	const size_t n_vtx = (size_t)M->g.n_seg * 2;
+	if (M->lab_max_dist_g >= max_dist_g && M->d_lab_off) return true; // labels are exact for every bound up to the one they were searched with
+	// (re)start the table: it must be ours alone.  No new call starts until those in flight are done; a second call that gets here
+	// meanwhile searches per read this once (it is one of those the first is waiting for).
+	if (M->lab_growing) return false;
+	M->lab_growing = true;
+	M->slot_cv.wait(lock, [&]() { return M->in_flight <= 1; });
+	struct Done { Model *M; ~Done() { M->lab_growing = false; M->slot_cv.notify_all(); } } done{M};
 	if (M->d_lab_off == 0) {
 		M->d_lab_off = (long long*)dmalloc(n_vtx * sizeof(long long));
 		M->d_lab_hdr = (Pool*)dmalloc(sizeof(Pool));
 		M->lab_cap = std::min<uint64_t>(std::max<uint64_t>((uint64_t)256 << 20, (uint64_t)n_vtx * 8192), std::max<uint64_t>((uint64_t)64 << 20, dev_free_mem() / 16));
 		M->d_lab_pool = (char*)dmalloc(M->lab_cap);
-		M->lab_max_dist_g = -1;
 	}
-	if (M->lab_max_dist_g < max_dist_g) { // labels are exact for every bound up to the one they were searched with
-		if (M->in_flight > 1) return false; // another call is reading the table: this one searches per read
-		dfill(M->d_lab_off, 0xff, n_vtx * sizeof(long long));
-		Pool hp; hp.used = 0, hp.cap = M->lab_cap;
-		h2d(M->d_lab_hdr, &hp, sizeof(Pool));
-		M->lab_max_dist_g = max_dist_g;
-		dsync();
-	}
+	dfill(M->d_lab_off, 0xff, n_vtx * sizeof(long long));
+	Pool hp; hp.used = 0, hp.cap = M->lab_cap;
+	h2d(M->d_lab_hdr, &hp, sizeof(Pool));
+	M->lab_max_dist_g = max_dist_g;
+	dsync();
 	return true;
 }
 // after a batch: a label pool that overflowed is enlarged for the batches to come (the sources that did not fit were searched per read)
@@ -1187,8 +1202,12 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 		if (n < 256 || host_threads <= 1) { for (int64_t i = 0; i < n; ++i) fn(i); return; }
 		sl.host_pool.run(n, host_threads, fn);
 	};
-	EvTimer tm_h2d, tm_seed, tm_chain, tm_align, tm_wfa, tm_fin, tm_d2h;
-	EvTimer tm_k[10], tm_lab; // one per kernel (first pass only)
+	// the event pairs live in the slot: creating and destroying three dozen events per call contends on the driver's lock with the other calls in flight
+	if (sl.timers == 0) sl.timers = new SlotTimers();
+	SlotTimers &TM = *sl.timers;
+	TM.reset();
+	EvTimer &tm_h2d = TM.h2d, &tm_seed = TM.seed, &tm_chain = TM.chain, &tm_align = TM.align, &tm_wfa = TM.wfa, &tm_fin = TM.fin, &tm_d2h = TM.d2h, &tm_lab = TM.lab;
+	EvTimer *tm_k = TM.k; // one per kernel (first pass only)
 	// ---- device buffers (all persistent: cudaMalloc/cudaFree would serialise the slots) ----
 	enum { P_ANCHOR, P_MINIPOS, P_LCHAIN, P_OUT, P_PLAN, P_JOBS, P_CIG, P_GSTATE, P_GJOBS, P_WALK, N_POOLS };
 	char *d_seq = (char*)sl.d_seq.ensure(hseq_bytes);

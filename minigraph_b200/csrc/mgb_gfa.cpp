@@ -632,3 +632,65 @@ extern "C" void mgb_write_gaf_batch(const gfa_t *g, int n_reads, mg_gchains_t *c
 	*out = o, *out_len = tot;
 	if (out_cap) *out_cap = cap;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// input side: a whole FASTA/FASTQ file (plain or gzip) as the arrays mg_map_batch() takes
+// (reference: bseq.c:46-98 mg_bseq_read + the upper-casing of gmap.c:77-84; kseq.h's rules: the name ends at the first
+// white space, sequence lines are joined, a FASTQ record's quality is skipped by length)
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" mgb_reads_t *mgb_reads_load(const char *fn, int64_t max_bases)
+{
+	gzFile fp = fn && strcmp(fn, "-")? gzopen(fn, "rb") : gzdopen(0, "rb");
+	if (fp == 0) return 0;
+	std::vector<char> raw;
+	{
+		char buf[1 << 16];
+		int n;
+		gzbuffer(fp, 1 << 20);
+		while ((n = gzread(fp, buf, sizeof(buf))) > 0) raw.insert(raw.end(), buf, buf + n);
+		gzclose(fp);
+	}
+	mgb_reads_t *r = (mgb_reads_t*)calloc(1, sizeof(mgb_reads_t));
+	// the records are compacted in place: name\0seq\0 follow each other in one block that the arrays point into
+	r->block = (char*)malloc(raw.size() + 2);
+	std::vector<size_t> name_off, seq_off;
+	std::vector<int> len;
+	size_t w = 0, i = 0;
+	const size_t n = raw.size();
+	int64_t bases = 0;
+	while (i < n && raw[i] != '>' && raw[i] != '@') ++i; // kseq skips to the first header
+	while (i < n && (max_bases <= 0 || bases < max_bases)) {
+		const char head = raw[i++];
+		name_off.push_back(w);
+		while (i < n && !isspace((unsigned char)raw[i])) r->block[w++] = raw[i++];
+		r->block[w++] = 0;
+		while (i < n && raw[i] != '\n') ++i; // comment
+		seq_off.push_back(w);
+		size_t l = 0;
+		while (i < n) { // sequence lines up to the next header ('+' ends a FASTQ sequence)
+			if (raw[i] == '\n' || raw[i] == '\r') { ++i; continue; }
+			if (raw[i - 1] == '\n' && (raw[i] == '>' || raw[i] == '+' || raw[i] == '@')) break;
+			const unsigned char c = (unsigned char)raw[i++];
+			r->block[w++] = (char)(c >= 'a' && c <= 'z'? c - 32 : c), ++l; // gmap.c:81
+		}
+		r->block[w++] = 0;
+		len.push_back((int)l), bases += (int64_t)l;
+		if (head == '@' && i < n && raw[i] == '+') { // quality: as many characters as bases
+			while (i < n && raw[i] != '\n') ++i;
+			size_t q = 0;
+			while (i < n && q < l) { if (raw[i] != '\n' && raw[i] != '\r') ++q; ++i; }
+			while (i < n && raw[i] != '\n') ++i;
+		}
+		while (i < n && raw[i] != '>' && raw[i] != '@') ++i;
+	}
+	r->n_reads = (int64_t)len.size(), r->n_bases = bases;
+	r->name = (const char**)malloc(sizeof(char*) * (len.size() + 1)), r->seq = (const char**)malloc(sizeof(char*) * (len.size() + 1)), r->len = (int*)malloc(sizeof(int) * (len.size() + 1));
+	for (size_t k = 0; k < len.size(); ++k) r->name[k] = r->block + name_off[k], r->seq[k] = r->block + seq_off[k], r->len[k] = len[k];
+	return r;
+}
+
+extern "C" void mgb_reads_free(mgb_reads_t *r)
+{
+	if (r == 0) return;
+	free(r->block); free((void*)r->name); free((void*)r->seq); free(r->len); free(r);
+}
