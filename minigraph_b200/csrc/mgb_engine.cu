@@ -531,13 +531,20 @@ __global__ void __launch_bounds__(256) k_unpack(UnpackArgs U)
 // ---- the few words the host needs between two kernels (pool fill levels, queue lengths) ----
 // They do not travel by cudaMemcpy: a copy of 16 bytes queues behind whatever another call in flight has put on the copy engines
 // (a few hundred MB of results, tens of ms).  A one-warp kernel writes them into page-locked host memory the device can address.
-struct Mail { Pool pools[16]; unsigned int jobq_n[2], lab_n[2]; };
+struct Mail { Pool pools[16]; unsigned int jobq_n[2], lab_n[2]; unsigned long long prof[32]; unsigned int tier_hist[128]; unsigned long long arena_peak; };
+struct MailSrc { const Pool *pools; const unsigned int *jobq_n, *lab_n; const unsigned long long *prof; const unsigned int *tier_hist; const uint64_t *peak; int n_workers; };
 #ifndef MGB_HOSTSIM
-__global__ void k_mail(const Pool *pools, const unsigned int *jobq_n, const unsigned int *lab_n, Mail *out)
+__global__ void k_mail(MailSrc m, Mail *out)
 {
 	const int t = threadIdx.x;
-	if (t < 16) out->pools[t] = pools[t];
-	if (t < 2) out->jobq_n[t] = jobq_n[t], out->lab_n[t] = lab_n? lab_n[t] : 0;
+	if (t < 16) out->pools[t] = m.pools[t];
+	if (t < 2) out->jobq_n[t] = m.jobq_n[t], out->lab_n[t] = m.lab_n? m.lab_n[t] : 0;
+	out->prof[t] = m.prof[t];
+	for (int i = t; i < 128; i += 32) out->tier_hist[i] = m.tier_hist[i];
+	unsigned long long pk = 0;
+	for (int i = t; i < m.n_workers; i += 32) pk = m.peak[i] > pk? m.peak[i] : pk;
+	for (int o = 16; o > 0; o >>= 1) { const unsigned long long y = __shfl_xor_sync(0xffffffffu, pk, o); pk = y > pk? y : pk; }
+	if (t == 0) out->arena_peak = pk;
 	__threadfence_system();
 }
 #endif
@@ -551,16 +558,20 @@ MG_HD inline void job_counts(const Pool *pools, int i_gjobs, int i_jobs, unsigne
 #ifndef MGB_HOSTSIM
 __global__ void k_job_counts(const Pool *pools, int i_gjobs, int i_jobs, unsigned int gjobs_done, unsigned int jobs_done, unsigned int *cnt) { job_counts(pools, i_gjobs, i_jobs, gjobs_done, jobs_done, cnt); }
 #endif
-static void fetch_mail(const Pool *d_pools, const unsigned int *d_jobq_n, const unsigned int *d_lab_n, Mail *mail)
+static void fetch_mail(const MailSrc &m, Mail *mail)
 {
 #ifndef MGB_HOSTSIM
-	k_mail<<<1, 32, 0, t_stream>>>(d_pools, d_jobq_n, d_lab_n, mail);
+	k_mail<<<1, 32, 0, t_stream>>>(m, mail);
 	CUDA_OK(cudaGetLastError());
 	dsync();
 #else
-	memcpy(mail->pools, d_pools, sizeof(mail->pools));
-	memcpy(mail->jobq_n, d_jobq_n, sizeof(mail->jobq_n));
-	if (d_lab_n) memcpy(mail->lab_n, d_lab_n, sizeof(mail->lab_n)); else mail->lab_n[0] = mail->lab_n[1] = 0;
+	memcpy(mail->pools, m.pools, sizeof(mail->pools));
+	memcpy(mail->jobq_n, m.jobq_n, sizeof(mail->jobq_n));
+	if (m.lab_n) memcpy(mail->lab_n, m.lab_n, sizeof(mail->lab_n)); else mail->lab_n[0] = mail->lab_n[1] = 0;
+	memcpy(mail->prof, m.prof, sizeof(mail->prof));
+	memcpy(mail->tier_hist, m.tier_hist, sizeof(mail->tier_hist));
+	mail->arena_peak = 0;
+	for (int i = 0; i < m.n_workers; ++i) if (m.peak[i] > mail->arena_peak) mail->arena_peak = m.peak[i];
 #endif
 }
 
@@ -656,7 +667,7 @@ struct Model {
 	// the batch pipeline: a batch is cut into sub-batches, each driven by its own host thread on its own stream ("slot"),
 	// so that kernels, copies and host-side result assembly of different sub-batches overlap
 	struct Slot {
-		GrowBuf h_seq{true}, h_out{true}, h_small{true}, h_pk{true}, h_mail{true}, d_pk, d_seq, d_meta, d_routs, d_small, d_jobq, d_order, d_packed, d_packoff, d_segs, d_lab_new, d_pool[10];
+		GrowBuf h_seq{true}, h_out{true}, h_small{true}, h_pk{true}, h_mail{true}, h_routs{true}, d_pk, d_seq, d_meta, d_routs, d_small, d_jobq, d_order, d_packed, d_packoff, d_segs, d_lab_new, d_pool[10];
 		mgb::HostPool host_pool; // packing and result assembly of the batch on this slot
 		Workers W;
 		mgb_stats_t st;
@@ -702,7 +713,7 @@ static void model_free(Model *M)
 	dfree(M->d_lab_off), dfree(M->d_lab_hdr), dfree(M->d_lab_pool), dfree(M->d_occ_sorted);
 	for (int k = 0; k < Model::MAX_SLOTS; ++k) {
 		Model::Slot &sl = M->slots[k];
-		sl.h_seq.release(), sl.h_out.release(), sl.h_small.release(), sl.h_pk.release(), sl.h_mail.release(), sl.d_pk.release(), sl.d_seq.release(), sl.d_meta.release(), sl.d_routs.release(), sl.d_small.release(), sl.d_jobq.release(), sl.d_order.release(), sl.d_packed.release(), sl.d_packoff.release(), sl.d_segs.release(), sl.d_lab_new.release();
+		sl.h_seq.release(), sl.h_out.release(), sl.h_small.release(), sl.h_pk.release(), sl.h_mail.release(), sl.h_routs.release(), sl.d_pk.release(), sl.d_seq.release(), sl.d_meta.release(), sl.d_routs.release(), sl.d_small.release(), sl.d_jobq.release(), sl.d_order.release(), sl.d_packed.release(), sl.d_packoff.release(), sl.d_segs.release(), sl.d_lab_new.release();
 		for (int i = 0; i < 10; ++i) sl.d_pool[i].release();
 		if (sl.timers) timers_free(sl.timers);
 		if (sl.W.arena) dfree(sl.W.arena);
@@ -1340,8 +1351,8 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	cap[P_GJOBS] = std::max<uint64_t>((uint64_t)n_reads * 24 * sizeof(GwfaJob), (uint64_t)1 << 20);
 	cap[P_WALK] = std::max<uint64_t>((uint64_t)n_reads * 256, (uint64_t)1 << 20);
 	for (int i = 0; i < N_POOLS; ++i) if (sl.d_pool[i].cap > cap[i]) cap[i] = sl.d_pool[i].cap & ~(size_t)4095; // keep what earlier batches needed
-	std::vector<ReadOut> routs(n_reads);
-	std::vector<ReadMeta> meta(n_reads);
+	ReadOut *routs = (ReadOut*)sl.h_routs.ensure((sizeof(ReadOut) + sizeof(ReadMeta)) * (size_t)n_reads + 64); // page-locked: a pageable destination makes the copy a blocking, staged one
+	ReadMeta *meta = (ReadMeta*)(routs + n_reads);
 	char *hout = 0;
 	int rc_final = 0, n_piece = 1;
 	std::vector<uint64_t> pack_off;
@@ -1352,6 +1363,8 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	int32_t *d_lab_new = 0; unsigned int *d_lab_n = 0; // this call's list of sources to search
 	Mail *mail = (Mail*)sl.h_mail.ensure(sizeof(Mail));
 	if (use_lab) { d_lab_n = (unsigned int*)sl.d_lab_new.ensure(((size_t)M->g.n_seg * 2 + 4) * sizeof(int32_t)); d_lab_new = (int32_t*)(d_lab_n + 4); }
+	MailSrc msrc;
+	msrc.pools = d_pools, msrc.jobq_n = d_jobq_n, msrc.lab_n = d_lab_n, msrc.prof = d_prof, msrc.tier_hist = d_tier_hist, msrc.peak = sl.W.peak, msrc.n_workers = sl.W.n_workers;
 	for (int attempt = 0; attempt < 8; ++attempt) {
 		void *d_buf[N_POOLS];
 		Pool hp[N_POOLS];
@@ -1480,7 +1493,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 #ifndef MGB_HOSTSIM
 			CUDA_OK(cudaEventRecord(sl.ev_last, t_stream));
 #endif
-			fetch_mail(d_pools, d_jobq_n, d_lab_n, mail); // (also the one wait of the pass)
+			fetch_mail(msrc, mail); // (also the one wait of the pass)
 			gjobs_done = (int64_t)(std::min<uint64_t>(mail->pools[P_GJOBS].used, mail->pools[P_GJOBS].cap) / sizeof(GwfaJob));
 			jobs_done = (int64_t)(std::min<uint64_t>(mail->pools[P_JOBS].used, mail->pools[P_JOBS].cap) / sizeof(WfaJob));
 			if (timed) S.n_jobs_mid = mail->jobq_n[0], S.n_jobs_big = mail->jobq_n[1];
@@ -1496,8 +1509,8 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 			S.w_pass_ms += now_ms() - tw;
 		}
 		S.n_jobs = jobs_done;
-		d2h(routs.data(), d_routs, sizeof(ReadOut) * (size_t)n_reads);
-		d2h(meta.data(), d_meta, sizeof(ReadMeta) * (size_t)n_reads);
+		d2h(routs, d_routs, sizeof(ReadOut) * (size_t)n_reads);
+		d2h(meta, d_meta, sizeof(ReadMeta) * (size_t)n_reads);
 
 		// reads whose worker arena overflowed: run them again with large arenas and few workers (shared by the slots)
 		std::vector<int32_t> redo;
@@ -1515,14 +1528,14 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 			h2d(d_list_buf, redo.data(), redo.size() * sizeof(int32_t));
 			{ std::unique_lock<std::mutex> gpu(M->gpu_mutex, std::defer_lock); if (p_gpu_lock) gpu.lock(); const double tw = now_ms(); run_pass(d_list_buf, (int32_t)redo.size(), M->Wbig, false); S.w_redo_ms += now_ms() - tw; }
 			S.n_retry += (int64_t)redo.size();
-			d2h(routs.data(), d_routs, sizeof(ReadOut) * (size_t)n_reads);
-			d2h(meta.data(), d_meta, sizeof(ReadMeta) * (size_t)n_reads);
+			d2h(routs, d_routs, sizeof(ReadOut) * (size_t)n_reads);
+			d2h(meta, d_meta, sizeof(ReadMeta) * (size_t)n_reads);
 			for (int i = 0; i < n_reads; ++i) {
 				int st = meta[i].status < 0? meta[i].status : routs[i].status;
 				if (st == MGB_E_POOL) pool_full = true;
 			}
 		}
-		fetch_mail(d_pools, d_jobq_n, d_lab_n, mail);
+		fetch_mail(msrc, mail);
 		memcpy(hp, mail->pools, sizeof(hp));
 		if (use_lab) { unsigned int nn[2] = {mail->lab_n[0], mail->lab_n[1]}; S.n_lab_new = (int64_t)nn[0], S.n_lab_big = (int64_t)nn[1]; lab_after_batch(M, nn[0]); }
 		bool done = !pool_full;
@@ -1534,7 +1547,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 			P.packed = (char*)sl.d_packed.ensure(pool_bytes + 64), P.off = (uint64_t*)sl.d_packoff.ensure(sizeof(uint64_t) * ((size_t)n_reads + 1));
 			pack_results(P);
 			S.n_launches += 2;
-			d2h(routs.data(), d_routs, sizeof(ReadOut) * (size_t)n_reads);
+			d2h(routs, d_routs, sizeof(ReadOut) * (size_t)n_reads);
 			pack_off.resize((size_t)n_reads + 1);
 			d2h(pack_off.data(), P.off, sizeof(uint64_t) * ((size_t)n_reads + 1));
 			const size_t out_bytes = (size_t)pack_off[n_reads];
@@ -1562,15 +1575,10 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	S.t_wfa_ms = tm_wfa.ms(), S.t_finish_ms = tm_fin.ms();
 	for (int i = 0; i < 10; ++i) S.t_kernel_ms[i] = tm_k[i].ms();
 	S.t_lab_ms = tm_lab.ms();
-	{
-		std::vector<uint64_t> peak(sl.W.n_workers);
-		d2h(peak.data(), sl.W.peak, sizeof(uint64_t) * peak.size());
-		for (uint64_t p : peak) if (p > S.arena_peak) S.arena_peak = p;
-	}
-	{ unsigned long long hp2[PROF_N]; d2h(hp2, d_prof, sizeof(hp2)); for (int i = 0; i < 32; ++i) S.prof[i] = (uint64_t)hp2[i]; }
+	S.arena_peak = mail->arena_peak; // (the mailbox was last filled after the last pass of the batch)
+	for (int i = 0; i < 32; ++i) S.prof[i] = (uint64_t)mail->prof[i];
 	{ // tier routing for the next batch: the first length bucket in which the sampled gaps mostly ended beyond a tier
-		unsigned int h[128];
-		d2h(h, d_tier_hist, sizeof(h));
+		const unsigned int *h = mail->tier_hist;
 		int32_t t1 = INT32_MAX, t2 = INT32_MAX;
 		for (int b = 0; b < 32 && t1 == INT32_MAX; ++b) { unsigned int in = h[b * 4 + 1], out = h[b * 4 + 2] + h[b * 4 + 3]; if (in + out >= 8 && in < out) t1 = b * 16; }
 		for (int b = 0; b < 32 && t2 == INT32_MAX; ++b) { unsigned int in = h[b * 4 + 1] + h[b * 4 + 2], out = h[b * 4 + 3]; if (in + out >= 8 && in < out) t2 = b * 16; }

@@ -555,7 +555,12 @@ MG_HD inline int gwfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int l
 		warp_sync();
 		if (lane == 0) sh->A = A;
 		warp_sync();
+		const uint64_t top0 = sh->A.top;
+		sh->A.peak = top0;
 		rc = gwf_align_w(sh, c.g, opt, J->ql, qseq + J->qs, J->v0, J->end0, J->v1, J->end1, J->max_ed, lane);
+#if !MGB_ON_DEVICE && defined(MGB_HOSTSIM)
+		if (getenv("MGB_DUMP_JOBS")) fprintf(stderr, "GWFAG\t%d\t%lu\n", J->ql, (unsigned long)(sh->A.peak - top0));
+#endif
 		if (sh->A.peak > A.peak) A.peak = sh->A.peak;
 	}
 	if (lane == 0) {
