@@ -141,25 +141,29 @@ class ClockSampler(threading.Thread):
 
 
 def chain_traffic(workload):
-    """DRAM bytes of one k_chain launch from the newest committed `ncu --set full` digest of this workload, or (None, None)."""
+    """DRAM bytes of the chaining kernels (k_chain + k_chain_rescue, one launch each = one mini-batch) from the newest committed
+    `ncu --set full` digests of this workload (profiles/r*<workload>_ncu_k_chain*.txt), or (None, None)."""
     import glob
-    for fn in sorted(glob.glob(os.path.join(REPO, "profiles", "r*_ncu_k_chain*%s*.txt" % workload)), reverse=True):
-        try:
-            rd = wr = None
-            with open(fn) as f:
-                for ln in f:
-                    t = ln.rstrip("\n").split("\t")
-                    if len(t) == 3 and t[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                        v = float(t[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[t[2]]
-                        if t[0].startswith("dram__bytes_read"):
-                            rd = v
-                        else:
-                            wr = v
-            if rd is not None and wr is not None:
-                return rd + wr, os.path.relpath(fn, REPO)
-        except Exception:
-            pass
-    return None, None
+    tot, srcs = 0.0, []
+    for kern in ("k_chain", "k_chain_rescue"):
+        fns = sorted(glob.glob(os.path.join(REPO, "profiles", "r*%s_ncu_%s.txt" % (workload, kern))), reverse=True)
+        if not fns:
+            return None, None
+        rd = wr = None
+        with open(fns[0]) as f:
+            for ln in f:
+                t = ln.rstrip("\n").split("\t")
+                if len(t) == 3 and t[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    v = float(t[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[t[2]]
+                    if t[0].startswith("dram__bytes_read"):
+                        rd = v
+                    else:
+                        wr = v
+        if rd is None or wr is None:
+            return None, None
+        tot += rd + wr
+        srcs.append(os.path.relpath(fns[0], REPO))
+    return tot, " + ".join(srcs)
 
 
 def hbm_peak():

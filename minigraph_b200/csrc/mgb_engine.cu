@@ -53,7 +53,7 @@ static int64_t p_lab_cache = 1;        // 0: graph chaining searches its walks p
 
 // launch shape per stage: warps per block and blocks per SM wanted (tunable for experiments: "sw<stage>", "mb<stage>")
 static int STAGE_MINB[20] = { 8, 2, 8, 8, 5, 8, 7, 4, 4, 4, 0, 0, 0, 0, 0, 0, 0, 8, 8, 2 }; // indexed by stage number (10-16 unused)
-static int STAGE_WARPS[20] = { 4, 7, 4, 4, 4, 4, 2, 4, 4, 4, 0, 0, 0, 0, 0, 0, 0, 4, 4, 5 }; // k_chain: 2 x 7 slices of 16 KB per SM, k_chain_rescue: 2 x 5 of 20 KB
+static int STAGE_WARPS[20] = { 4, 7, 4, 4, 4, 4, 2, 4, 4, 4, 0, 0, 0, 0, 0, 0, 0, 4, 4, 6 }; // k_chain: 2 x 7 slices of 16 KB per SM, k_chain_rescue: 2 x 6 of 18 KB
 extern "C" const char *mgb_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char *mgb_version(void) { return "mgb200-r1"; }
 extern "C" int mgb_set_param(const char *key, int64_t value)
@@ -304,7 +304,7 @@ __device__ __forceinline__ void stage_loop_thread(const LaunchArgs &L)
 #define MGB_KERNEL(name, STAGE, MINB) MGB_KERNEL_T(name, STAGE, 128, MINB)
 MGB_KERNEL(k_seed, 0, 8)          // K1-K3: sketch, index lookup, seed sort
 MGB_KERNEL_T(k_chain, 1, 224, 2)         // K4/K5: linear chaining on chip (seeds bulk-loaded into shared memory)
-MGB_KERNEL_T(k_chain_rescue, 19, 160, 2) // K5: long-join rescue (RMQ chaining) of the reads k_chain listed
+MGB_KERNEL_T(k_chain_rescue, 19, 192, 2) // K5: long-join rescue (RMQ chaining) of the reads k_chain listed
 MGB_KERNEL(k_gchain, 2, 8)        // K6: graph chaining DP + k-shortest walks, overlap resolution, bridging plan
 MGB_KERNEL(k_gwfa, 8, 4)          // K7a: bridging alignments (graph wavefront), one warp per bridge
 MGB_KERNEL(k_gchain_gen, 9, 4)    // K7b: graph-chain materialisation, post filters, mapq, alignment plan

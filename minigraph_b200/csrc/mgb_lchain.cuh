@@ -385,14 +385,14 @@ MG_HD inline int chain_rmq_fill_w(Arena &H, Arena &A, int max_dist, int max_dist
 	const uint64_t mark = A.top, hmark = H.top;
 	double *pri;
 	uint64_t *K; // inner window, keys y<<32|idx ascending
-	MGB_ALLOC_HOT(H, A, pri, double, n);
-	MGB_ALLOC_HOT(H, A, K, uint64_t, n);
+	MGB_ALLOC_HOT(H, A, K, uint64_t, n); // (the window is re-read for every anchor, the priorities only where a block straddles a border: hot space goes to the window first)
 	// Summaries of the available anchors in blocks of 32 consecutive indices: the smallest priority, how many hold it and one of
 	// them, and the span of query positions.  The outer query then looks at one summary per block and at the elements of the
 	// few blocks that straddle a border of the window, instead of at every anchor of the window.
 	RmqBlock *blk;
 	const int64_t n_blk = (n + 31) >> 5;
 	MGB_ALLOC_HOT(H, A, blk, RmqBlock, n_blk);
+	MGB_ALLOC_HOT(H, A, pri, double, n);
 	for (int64_t b = lane; b < n_blk; b += MGB_W) { RmqBlock e; e.best = 1e300, e.cnt = 0, e.j = -1, e.ymin = INT32_MAX, e.ymax = INT32_MIN; blk[b] = e; }
 	int32_t nK = 0;
 	int64_t i, i0 = 0, st = 0, st_inner = 0;

@@ -232,7 +232,7 @@ MG_HD inline int stage_chain_tail2(const PipeCtx &c, ReadMeta &m, const LChain *
 // 6 warps per SM, was 2.2 times faster per warp and 2 times slower per kernel than 26 warps per SM working in HBM).
 // A read whose seeds do not fit the slice works on the HBM copy, with whatever fits of the hot arrays still on chip.
 static const int CHAIN_SMEM_BYTES = 16 * 1024;        // per warp, k_chain: anchors + f/p/v/t of a read of up to ~500 seeds
-static const int CHAIN_RESCUE_SMEM_BYTES = 20 * 1024; // per warp, k_chain_rescue: + priorities and window of the RMQ pass
+static const int CHAIN_RESCUE_SMEM_BYTES = 18 * 1024; // per warp, k_chain_rescue: + window and block summaries of the RMQ pass (the priorities if they fit)
 
 struct ChainRun { // what one pass leaves behind
 	int32_t n_keep;   // anchors of a[] to write back
