@@ -103,10 +103,31 @@ MG_HD inline int chain_backtrack(Arena &A, int64_t n, const int32_t *f, const in
 	return 0;
 }
 
+// The end-point list of chain_finish_w(): score and anchor index in one word.  The sort key is the score widened exactly as the
+// reference's 128-bit records hold it ((uint64_t)(int64_t)f), so klib's radix sort makes the same moves on these 8-byte records.
+struct KeyHi32 { MG_HD uint64_t operator()(const uint64_t &p) const { return (uint64_t)(int64_t)(int32_t)(p >> 32); } };
+MG_HD inline int64_t chain_bk_end_p(int32_t max_drop, const uint64_t *z, const int32_t *f, const int32_t *p, int32_t *t, int64_t k)
+{ // chain_bk_end() on the packed list (reference: lchain.c:9-25)
+	const int32_t zf = (int32_t)(z[k] >> 32);
+	int64_t i = (int64_t)(uint32_t)z[k], end_i = -1, max_i = i;
+	int32_t max_s = 0;
+	if (t[i] != 0) return i;
+	do {
+		int32_t s;
+		t[i] = 2;
+		end_i = i = p[i];
+		s = i < 0? zf : zf - f[i];
+		if (s > max_s) max_s = s, max_i = i;
+		else if (max_s - s > max_drop) break;
+	} while (i >= 0 && t[i] == 0);
+	for (i = (int64_t)(uint32_t)z[k]; i >= 0 && i != end_i; i = p[i]) t[i] = 0;
+	return max_i;
+}
+
 // chain_backtrack() + chain_compact() entered by all lanes of a warp: the end-point list, the sorts and the copies are
 // spread over the lanes, the peeling itself (a walk over p[] with the visit marks) stays on lane 0.  u_store receives
 // the chain descriptors; a[0..n_v) the chained anchors.
-MG_HD inline int chain_finish_w(Arena &A, int64_t n, const int32_t *f, const int32_t *p, int32_t *v, int32_t *t, int32_t min_cnt, int32_t min_sc,
+MG_HD inline int chain_finish_w(Arena &H, Arena &A, int64_t n, const int32_t *f, const int32_t *p, int32_t *v, int32_t *t, int32_t min_cnt, int32_t min_sc,
 								int32_t max_drop, u128 *a, uint64_t *u_store, int32_t *n_u_, int32_t *n_v_, int lane)
 {
 	const uint64_t mark = A.top;
@@ -115,33 +136,37 @@ MG_HD inline int chain_finish_w(Arena &A, int64_t n, const int32_t *f, const int
 	for (int64_t i = lane; i < n; i += MGB_W) n_z += f[i] >= min_sc;
 	n_z = warp_sum_i32(n_z);
 	if (n_z == 0) return 0;
-	uint64_t *u;
-	u128 *z;
+	const uint64_t hmark = H.top;
+	uint64_t *u, *z;
 	MGB_ALLOC(A, u, uint64_t, n_z);
-	MGB_ALLOC(A, z, u128, n_z);
+	MGB_ALLOC_HOT(H, A, z, uint64_t, n_z); // the peeling below walks this list on one lane: it wants to be on chip, and so do the sort's bin tables
 	{
 		int32_t k = 0;
 		for (int64_t base = 0; base < n; base += MGB_W) {
 			const int64_t i = base + lane;
 			const int keep = i < n && f[i] >= min_sc;
 			const uint32_t m = warp_ballot(keep);
-			if (keep) { u128 e; e.x = (uint64_t)(int64_t)f[i], e.y = (uint64_t)i; z[k + mask_rank(m, lane)] = e; }
+			if (keep) z[k + mask_rank(m, lane)] = (uint64_t)(uint32_t)f[i] << 32 | (uint64_t)(uint32_t)i;
 			k += mask_count(m);
 		}
 	}
 	for (int64_t i = lane; i < n; i += MGB_W) t[i] = 0;
 	warp_sync();
-	MGB_TRY(radix_sort_128x_w(A, z, n_z, lane));
+	{
+		Arena &S = H.cap - H.top >= (uint64_t)n_z / 4 + 3400? H : A; // range stack + three 1 KB bin tables
+		MGB_TRY(radix_sort_exact_w(S, z, n_z, 8, KeyHi32(), lane));
+	}
 	int32_t n_u = 0, n_v = 0;
 	if (lane == 0) { // reference: lchain.c:27-77
 		for (int64_t k = n_z - 1; k >= 0; --k) {
-			if (t[z[k].y] == 0) {
+			if (t[(uint32_t)z[k]] == 0) {
 				int64_t n_v0 = n_v, end_i, i;
 				int32_t sc;
-				end_i = chain_bk_end(max_drop, z, f, p, t, k);
-				for (i = (int64_t)z[k].y; i != end_i; i = p[i])
+				const int32_t zf = (int32_t)(z[k] >> 32);
+				end_i = chain_bk_end_p(max_drop, z, f, p, t, k);
+				for (i = (int64_t)(uint32_t)z[k]; i != end_i; i = p[i])
 					v[n_v++] = (int32_t)i, t[i] = 1;
-				sc = i < 0? (int32_t)z[k].x : (int32_t)z[k].x - f[i];
+				sc = i < 0? zf : zf - f[i];
 				if (sc >= min_sc && n_v > n_v0 && n_v - n_v0 >= min_cnt)
 					u[n_u++] = (uint64_t)sc << 32 | (uint64_t)(n_v - n_v0);
 				else n_v = (int32_t)n_v0;
@@ -177,6 +202,7 @@ MG_HD inline int chain_finish_w(Arena &A, int64_t n, const int32_t *f, const int
 		warp_sync();
 	}
 	A.top = mark;
+	if (&H != &A) H.top = hmark;
 	*n_u_ = n_u, *n_v_ = n_v;
 	return 0;
 }
@@ -253,7 +279,7 @@ MG_HD inline int chain_dp_w(Arena &H, Arena &A, int max_dist_x, int max_dist_y, 
 		warp_sync();
 	}
 	int32_t n_u = 0, n_v = 0;
-	MGB_TRY(chain_finish_w(A, n, f, p, v, t, min_cnt, min_sc, max_drop, a, u_store, &n_u, &n_v, lane));
+	MGB_TRY(chain_finish_w(H, A, n, f, p, v, t, min_cnt, min_sc, max_drop, a, u_store, &n_u, &n_v, lane));
 	A.top = mark;
 	if (&H != &A) H.top = hmark;
 	*u_ = u_store, *n_u_ = n_u, *n_a_ = n_u > 0? n_v : 0;
@@ -593,7 +619,7 @@ MG_HD inline int chain_rmq_w(Arena &H, Arena &A, int max_dist, int max_dist_inne
 		warp_sync();
 		if (rc2 < 0) return rc2;
 	}
-	MGB_TRY(chain_finish_w(A, n, f, p, v, t, min_cnt, min_sc, max_drop, a, u_store, &n_u, &n_v, lane));
+	MGB_TRY(chain_finish_w(H, A, n, f, p, v, t, min_cnt, min_sc, max_drop, a, u_store, &n_u, &n_v, lane));
 	A.top = mark;
 	if (&H != &A) H.top = hmark;
 	*u_ = u_store, *n_u_ = n_u, *n_a_ = n_u > 0? n_v : 0;

@@ -153,7 +153,12 @@ MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A, int lane, int32
 		} else expand_seeds_w(c.g, n_m, sm, a_off, a, lane);
 		warp_sync();
 		t2 = prof_clock();
-		MGB_TRY(radix_sort_128x_w(A, a, n_a, lane));
+		{ // the sort's range stack and bin tables in the shared-memory slice the sketch's rings no longer need
+			Arena R;
+			arena_init(R, smem, smem? (uint64_t)SKETCH_SMEM_BYTES : 0);
+			Arena &S = smem && R.cap >= (uint64_t)n_a / 4 + 3400? R : A;
+			MGB_TRY(radix_sort_128x_w(S, a, n_a, lane));
+		}
 	}
 	if (lane == 0) prof_add(c, PROF_SEED_SKETCH_CYC, t1 - t0), prof_add(c, PROF_SEED_MATCH_CYC, t2 - t1), prof_add(c, PROF_SEED_SORT_CYC, prof_clock() - t2);
 	A.top = mark;
@@ -292,7 +297,10 @@ MG_HD inline int chain_pass(const PipeCtx &c, int rid, Arena &H, Arena &A, u128 
 			}
 		}
 	} else {
-		MGB_TRY(radix_sort_128x_w(A, a, n_a, lane));
+		{ // back into target order; the sort's range stack and bin tables on chip when the slice has the room (it is empty but for the anchors)
+			Arena &S = H.cap - H.top >= (uint64_t)n_a / 4 + 3400? H : A;
+			MGB_TRY(radix_sort_128x_w(S, a, n_a, lane));
+		}
 		MGB_TRY(chain_rmq_w(H, A, o.max_gap, o.max_gap_pre, o.bw_long, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
 							o.chn_pen_gap, o.chn_pen_skip, n_a, a, &n_lc, &u, &n_a_new, lane));
 		if (lane == 0) prof_add(c, PROF_CHAIN_RMQ_CYC, prof_clock() - t0);
