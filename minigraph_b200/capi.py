@@ -146,7 +146,7 @@ def apply_env_params(lib):
 
 def load_product(path=None):
     """Load libmgb200.so (the CUDA build). Fails loudly when it has not been built -- there is no fallback."""
-    path = path or os.path.join(_REPO, "minigraph_b200", "libmgb200.so")
+    path = path or os.environ.get("MGB_LIB") or os.path.join(_REPO, "minigraph_b200", "libmgb200.so")  # MGB_LIB: another build of the same library (A/B runs of bench.py)
     if not os.path.exists(path):
         raise RuntimeError("libmgb200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
     lib = C.CDLL(path)

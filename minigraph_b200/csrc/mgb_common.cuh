@@ -23,6 +23,16 @@
 #define MGB_ON_DEVICE 0
 #endif
 
+// a function kept out of line: rare paths (container growth, table rebuilds, large sorts) of kernels whose hot loop has to
+// stay small -- the L1.5 instruction cache holds 2048 instructions and the warps of an SM are all in different places
+#if defined(__CUDACC__)
+#define MG_NOINLINE __noinline__
+#define MGB_NO_UNROLL _Pragma("unroll 1")
+#else
+#define MG_NOINLINE __attribute__((noinline))
+#define MGB_NO_UNROLL
+#endif
+
 namespace mgb {
 
 // ---- error codes (per read) ----
@@ -215,6 +225,45 @@ template<typename T>
 MG_HD inline int avec_push(Arena &A, AVec<T> &v, const T &x)
 {
 	if (v.n == v.m) { int rc = avec_reserve(A, v, v.n + 1); if (rc < 0) return rc; }
+	v.a[v.n++] = x;
+	return 0;
+}
+
+// The same growth out of line and independent of the element type (avec_reserve_c / avec_push_c): same capacities, same arena
+// traffic, one copy of the code per kernel instead of one per call site.
+MG_HD MG_NOINLINE inline int avec_grow_cold(Arena &A, void **pa, int64_t n, int64_t *pm, uint32_t elem, int64_t want)
+{
+	int64_t m = *pm? *pm : 16;
+	while (m < want) m += (m >> 1) + 16;
+	char *a = (char*)*pa;
+	const uint64_t old_bytes = ((uint64_t)elem * (uint64_t)*pm + 15) & ~(uint64_t)15;
+	if (a && a + old_bytes == A.base + A.top) {
+		const uint64_t new_bytes = ((uint64_t)elem * (uint64_t)m + 15) & ~(uint64_t)15;
+		if ((uint64_t)(a - A.base) + new_bytes > A.cap) return MGB_E_ARENA;
+		A.top = (uint64_t)(a - A.base) + new_bytes;
+		if (A.top > A.peak) A.peak = A.top;
+		*pm = m;
+		return 0;
+	}
+	char *b = (char*)arena_alloc(A, (uint64_t)elem * (uint64_t)m);
+	if (b == 0) return MGB_E_ARENA;
+	const uint64_t n_words = (uint64_t)elem * (uint64_t)n / 4; // element sizes are multiples of four bytes, blocks 16-byte aligned
+	MGB_NO_UNROLL
+	for (uint64_t i = 0; i < n_words; ++i) ((uint32_t*)b)[i] = ((const uint32_t*)a)[i];
+	*pa = b, *pm = m;
+	return 0;
+}
+template<typename T>
+MG_HD inline int avec_reserve_c(Arena &A, AVec<T> &v, int64_t want)
+{
+	static_assert(sizeof(T) % 4 == 0, "avec_grow_cold copies words");
+	if (want <= v.m) return 0;
+	return avec_grow_cold(A, (void**)&v.a, v.n, &v.m, (uint32_t)sizeof(T), want);
+}
+template<typename T>
+MG_HD inline int avec_push_c(Arena &A, AVec<T> &v, const T &x)
+{
+	if (v.n == v.m) { int rc = avec_reserve_c(A, v, v.n + 1); if (rc < 0) return rc; }
 	v.a[v.n++] = x;
 	return 0;
 }
@@ -447,6 +496,31 @@ struct KeyU64 { MG_HD uint64_t operator()(const uint64_t &p) const { return p; }
 MG_HD inline int radix_sort_128x(Arena &A, u128 *a, int64_t n) { return radix_sort_exact(A, a, n, 8, KeyX128()); }
 MG_HD inline int radix_sort_64(Arena &A, uint64_t *a, int64_t n) { return radix_sort_exact(A, a, n, 8, KeyU64()); }
 
+// At most 64 elements, entered by all lanes: klib sorts these by insertion, i.e. stably, so every element's final place is a
+// count (keys below it, equal keys in front of it); two elements per lane.  No arena, no scratch.
+template<typename T, typename KeyFn>
+MG_HD inline void small_sort_stable_w(T *a, int64_t n, KeyFn key, int lane)
+{
+	if (MGB_W < 32) { if (lane == 0) rs_insertsort(a, a + n, key); warp_sync(); return; }
+	T e[2];
+	int32_t r[2] = {-1, -1};
+	for (int h = 0; h < 2; ++h) {
+		const int64_t i = lane + 32 * h;
+		if (i >= n) continue;
+		e[h] = a[i];
+		const uint64_t ki = (uint64_t)key(e[h]);
+		int32_t c = 0;
+#if MGB_ON_DEVICE
+#pragma unroll 2
+#endif
+		for (int64_t j = 0; j < n; ++j) { const uint64_t kj = (uint64_t)key(a[j]); c += kj < ki || (kj == ki && j < i); }
+		r[h] = c;
+	}
+	warp_sync();
+	for (int h = 0; h < 2; ++h) if (r[h] >= 0) a[r[h]] = e[h];
+	warp_sync();
+}
+
 // radix_sort_exact() entered by all lanes of a warp.  Only the cycle-leader permutation is inherently sequential (its
 // tie order is what has to be reproduced); it runs on lane 0 over the non-empty bins.  The digit census, the bin
 // offsets, the child ranges and the insertion sorts of the small bins are spread over the lanes.
@@ -454,24 +528,7 @@ template<typename T, typename KeyFn>
 MG_HD inline int radix_sort_exact_w(Arena &A, T *a, int64_t n, int sizeof_key, KeyFn key, int lane)
 {
 	const int MIN_SIZE = 64;
-	if (n <= MIN_SIZE) { // klib sorts these by insertion, i.e. stably: every element's final place is a count, two elements per lane
-		if (MGB_W < 32) { if (lane == 0) rs_insertsort(a, a + n, key); warp_sync(); return 0; }
-		T e[2];
-		int32_t r[2] = {-1, -1};
-		for (int h = 0; h < 2; ++h) {
-			const int64_t i = lane + 32 * h;
-			if (i >= n) continue;
-			e[h] = a[i];
-			const uint64_t ki = (uint64_t)key(e[h]);
-			int32_t c = 0;
-			for (int64_t j = 0; j < n; ++j) { const uint64_t kj = (uint64_t)key(a[j]); c += kj < ki || (kj == ki && j < i); }
-			r[h] = c;
-		}
-		warp_sync();
-		for (int h = 0; h < 2; ++h) if (r[h] >= 0) a[r[h]] = e[h];
-		warp_sync();
-		return 0;
-	}
+	if (n <= MIN_SIZE) { small_sort_stable_w(a, n, key, lane); return 0; }
 	uint64_t mark = A.top;
 	RsRange *stack;
 	int64_t m_stack = n / MIN_SIZE + 4; // pending ranges are disjoint and each holds more than MIN_SIZE elements

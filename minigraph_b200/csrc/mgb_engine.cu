@@ -52,7 +52,10 @@ static int64_t p_pack2 = 1;            // 0: reads are uploaded as ASCII (1 byte
 static int64_t p_lab_cache = 1;        // 0: graph chaining searches its walks per read instead of keeping per-source labels in HBM (mgb_gclabel.cuh)
 
 // launch shape per stage: warps per block and blocks per SM wanted (tunable for experiments: "sw<stage>", "mb<stage>")
-static int STAGE_MINB[20] = { 8, 2, 8, 8, 5, 8, 7, 4, 4, 4, 0, 0, 0, 0, 0, 0, 0, 8, 8, 2 }; // indexed by stage number (10-16 unused)
+#ifndef MGB_BIG_MINB
+#define MGB_BIG_MINB 6 // blocks of k_wfa_big per SM (its register budget follows: 80 at 6, 128 at 4)
+#endif
+static int STAGE_MINB[20] = { 8, 2, 8, 8, 5, 8, 7, MGB_BIG_MINB, 4, 4, 0, 0, 0, 0, 0, 0, 0, 8, 8, 2 }; // indexed by stage number (10-16 unused)
 static int STAGE_WARPS[20] = { 4, 7, 4, 4, 4, 4, 2, 4, 4, 4, 0, 0, 0, 0, 0, 0, 0, 4, 4, 6 }; // k_chain: 2 x 7 slices of 16 KB per SM, k_chain_rescue: 2 x 6 of 18 KB
 extern "C" const char *mgb_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char *mgb_version(void) { return "mgb200-r1"; }
@@ -300,7 +303,7 @@ __device__ __forceinline__ void stage_loop_thread(const LaunchArgs &L)
 }
 
 // named entry points (one per stage, so that profiles read well); blocks of 4 warps, MINB blocks per SM wanted
-#define MGB_KERNEL_T(name, STAGE, THREADS, MINB) __global__ void __launch_bounds__(THREADS, MINB) name(LaunchArgs L) { if (L.thread_mode) stage_loop_thread<STAGE>(L); else stage_loop<STAGE>(L); }
+#define MGB_KERNEL_T(name, STAGE, THREADS, MINB) __global__ void __launch_bounds__(THREADS, MINB) name(LaunchArgs L) { if (!MGB_IS_WARP(STAGE) && L.thread_mode) stage_loop_thread<STAGE>(L); else stage_loop<STAGE>(L); } // (no thread-per-item copy of the warp-wide stages in the kernel)
 #define MGB_KERNEL(name, STAGE, MINB) MGB_KERNEL_T(name, STAGE, 128, MINB)
 MGB_KERNEL(k_seed, 0, 8)          // K1-K3: sketch, index lookup, seed sort
 MGB_KERNEL_T(k_chain, 1, 224, 2)         // K4/K5: linear chaining on chip (seeds bulk-loaded into shared memory)
@@ -311,7 +314,7 @@ MGB_KERNEL(k_gchain_gen, 9, 4)    // K7b: graph-chain materialisation, post filt
 MGB_KERNEL(k_index_sketch, 3, 8)  // index build: sketch of graph segments
 MGB_KERNEL(k_wfa_small, 4, 5)     // K8a tier 1: small gaps, wavefronts + traceback bytes in shared memory
 MGB_KERNEL(k_wfa_mid, 6, 5)       // K8a tier 2: mid-size gaps, wavefronts in shared memory (blocks of 2 warps)
-MGB_KERNEL(k_wfa_big, 7, 4)       // K8a tier 3: anything else, wavefronts in the worker arena
+MGB_KERNEL(k_wfa_big, 7, MGB_BIG_MINB) // K8a tier 3: anything else, wavefronts in the worker arena (80 registers: 24 warps per SM)
 MGB_KERNEL(k_finish, 5, 8)        // K8b: CIGAR stitching, ds strings, result blobs
 MGB_KERNEL(k_gc_labels, 17, 8)    // reachability labels of new source vertices, one search per thread (mgb_gclabel.cuh)
 MGB_KERNEL(k_gc_labels_big, 18, 8) // the few sources whose search outgrew a thread's share of the arena: one per warp

@@ -542,27 +542,31 @@ MG_HD inline int gwfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int l
 	opt.i_term = 500000000LL;
 	const char *qseq = c.b.seq + c.b.seq_off[J->rid];
 	unsigned long long t0 = prof_clock();
-	int rc = MGB_E_ARENA;
-	if (J->ql < GWFA_SMEM_MAX_QL) { // longer bridges nearly always outgrow the shared-memory arena: do not try
-		if (lane == 0) arena_init(sh->A, (char*)smem + sh_bytes, GWFA_SMEM_ARENA - sh_bytes);
+	// one call site for both attempts (the kernel holds one copy of the alignment code): first in the shared-memory arena, then,
+	// if that was outgrown or not worth trying, in the worker's arena in HBM
+	int rc = MGB_E_ARENA, in_smem = 0;
+	uint64_t smem_peak = 0;
+	for (int pass = J->ql < GWFA_SMEM_MAX_QL? 0 : 1; pass < 2; ++pass) { // longer bridges nearly always outgrow the shared-memory arena: do not try
+		uint64_t top0 = 0;
+		if (lane == 0) {
+			if (pass == 0) arena_init(sh->A, (char*)smem + sh_bytes, GWFA_SMEM_ARENA - sh_bytes);
+			else sh->A = A, sh->A.peak = A.top;
+		}
 		warp_sync();
+		if (pass == 1) top0 = sh->A.top;
 		rc = gwf_align_w(sh, c.g, opt, J->ql, qseq + J->qs, J->v0, J->end0, J->v1, J->end1, J->max_ed, lane);
-	}
-	const int in_smem = rc != MGB_E_ARENA;
-	const uint64_t smem_peak = in_smem? sh->A.peak : 0;
-	(void)smem_peak, (void)in_smem;
-	if (rc == MGB_E_ARENA) { // outgrew shared memory: again in the worker's arena
-		warp_sync();
-		if (lane == 0) sh->A = A;
-		warp_sync();
-		const uint64_t top0 = sh->A.top;
-		sh->A.peak = top0;
-		rc = gwf_align_w(sh, c.g, opt, J->ql, qseq + J->qs, J->v0, J->end0, J->v1, J->end1, J->max_ed, lane);
+		if (pass == 0) {
+			if (rc != MGB_E_ARENA) { in_smem = 1, smem_peak = sh->A.peak; break; }
+			warp_sync();
+			continue;
+		}
 #if !MGB_ON_DEVICE && defined(MGB_HOSTSIM)
 		if (getenv("MGB_DUMP_JOBS")) fprintf(stderr, "GWFAG\t%d\t%lu\n", J->ql, (unsigned long)(sh->A.peak - top0));
 #endif
+		(void)top0;
 		if (sh->A.peak > A.peak) A.peak = sh->A.peak;
 	}
+	(void)smem_peak, (void)in_smem;
 	if (lane == 0) {
 		const GwfResult &r = sh->r;
 		{ unsigned long long dt = prof_clock() - t0; prof_add(c, PROF_GC_GWFA_CYC, dt); prof_max(c, PROF_GWFA_MAX_CYC, dt << 16 | (unsigned long long)(J->ql < 65535? J->ql : 65535)); }

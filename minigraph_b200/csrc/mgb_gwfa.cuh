@@ -45,11 +45,12 @@ MG_HD inline uint32_t u64tab_hash(uint64_t key)
 	return (uint32_t)key;
 }
 
-MG_HD inline int u64tab_alloc(Arena &A, U64Tab &t, int bits)
+MG_HD MG_NOINLINE inline int u64tab_alloc(Arena &A, U64Tab &t, int bits)
 {
 	MGB_ALLOC(A, t.key, uint64_t, 1LL << bits);
 	MGB_ALLOC(A, t.val, int32_t, 1LL << bits);
 	MGB_ALLOC(A, t.ep, int32_t, 1LL << bits);
+	MGB_NO_UNROLL
 	for (int64_t i = 0; i < (1LL << bits); ++i) t.ep[i] = 0;
 	t.bits = bits;
 	return 0;
@@ -58,6 +59,23 @@ MG_HD inline int u64tab_init(Arena &A, U64Tab &t, int bits) { t.epoch = 1, t.n =
 MG_HD inline void u64tab_clear(U64Tab &t) { ++t.epoch, t.n = 0; }
 
 // returns slot index; *absent tells whether the key was inserted by this call
+// twice the slots, entries re-inserted in slot order (out of line: once per doubling)
+MG_HD MG_NOINLINE inline int u64tab_grow(Arena &A, U64Tab &t)
+{
+	U64Tab o = t;
+	MGB_TRY(u64tab_alloc(A, t, o.bits + 1));
+	t.epoch = 1;
+	uint64_t nmask = (1ULL << t.bits) - 1;
+	MGB_NO_UNROLL
+	for (int64_t i = 0; i < (1LL << o.bits); ++i) {
+		if (o.ep[i] != o.epoch) continue;
+		uint64_t g = u64tab_hash(o.key[i]) & nmask;
+		while (t.ep[g] == t.epoch) g = (g + 1) & nmask;
+		t.key[g] = o.key[i], t.val[g] = o.val[i], t.ep[g] = t.epoch;
+	}
+	return 0;
+}
+
 MG_HD inline int u64tab_put(Arena &A, U64Tab &t, uint64_t key, int *absent, int64_t *slot)
 {
 	for (;;) {
@@ -65,16 +83,7 @@ MG_HD inline int u64tab_put(Arena &A, U64Tab &t, uint64_t key, int *absent, int6
 		while (t.ep[h] == t.epoch && t.key[h] != key) h = (h + 1) & mask;
 		if (t.ep[h] == t.epoch) { *absent = 0, *slot = (int64_t)h; return 0; }
 		if ((uint64_t)(t.n + 1) * 2 > (1ULL << t.bits)) { // grow
-			U64Tab o = t;
-			MGB_TRY(u64tab_alloc(A, t, o.bits + 1));
-			t.epoch = 1;
-			uint64_t nmask = (1ULL << t.bits) - 1;
-			for (int64_t i = 0; i < (1LL << o.bits); ++i) {
-				if (o.ep[i] != o.epoch) continue;
-				uint64_t g = u64tab_hash(o.key[i]) & nmask;
-				while (t.ep[g] == t.epoch) g = (g + 1) & nmask;
-				t.key[g] = o.key[i], t.val[g] = o.val[i], t.ep[g] = t.epoch;
-			}
+			MGB_TRY(u64tab_grow(A, t));
 			continue;
 		}
 		t.key[h] = key, t.val[h] = 0, t.ep[h] = t.epoch, ++t.n;
@@ -112,7 +121,7 @@ MG_HD inline int gwf_trace_push(Arena &A, GwfState &z, int32_t v, int32_t pre, i
 	MGB_TRY(u64tab_put(A, z.ht, key, &absent, &slot));
 	if (absent) {
 		GwfTrace x; x.v = v, x.pre = pre;
-		MGB_TRY(avec_push(A, z.t, x));
+		MGB_TRY(avec_push_c(A, z.t, x));
 		z.ht.val[slot] = (int32_t)z.t.n - 1;
 	}
 	*idx = z.ht.val[slot];
@@ -123,7 +132,7 @@ MG_HD inline int gwf_diag_push(Arena &A, AVec<GwfDiag> &B, uint32_t v, int32_t d
 {
 	GwfDiag p;
 	p.vd = gwf_gen_vd(v, d), p.k = k, p.len = 0, p.xo = x << 1 | ooo, p.t = t;
-	return avec_push(A, B, p);
+	return avec_push_c(A, B, p);
 }
 
 MG_HD inline int32_t gwf_diag_update(GwfDiag *p, uint32_t v, int32_t d, int32_t k, uint32_t x, uint32_t ooo, int32_t t)
@@ -152,11 +161,15 @@ MG_HD inline int32_t gwf_extend1(int32_t d, int32_t k, int32_t vl, const char *t
 	return k;
 }
 
+// the two klib sorts of this file, out of line (large inputs only in the warp-wide form below)
+MG_HD MG_NOINLINE inline int gwf_sort_diag_cold(Arena &A, GwfDiag *c, int64_t n) { return radix_sort_exact(A, c, n, 8, KeyDiagVd()); }
+MG_HD MG_NOINLINE inline int gwf_sort_intv_cold(Arena &A, GwfIntv *a, int64_t n) { return radix_sort_exact(A, a, n, 8, KeyIntvVd0()); }
+
 // split sort exploiting the out-of-order flag (reference: gfa-ed.c:162-187)
 MG_HD inline int gwf_diag_sort(Arena &A, GwfState &z, int32_t n_a, GwfDiag *a)
 {
 	int32_t i, j, k, n_b, n_c = 0;
-	MGB_TRY(avec_reserve(A, z.ooo, n_a));
+	MGB_TRY(avec_reserve_c(A, z.ooo, n_a));
 	for (i = 0; i < n_a; ++i) if (a[i].xo & 1) ++n_c;
 	n_b = n_a - n_c;
 	GwfDiag *b = z.ooo.a, *c = b + n_b;
@@ -164,7 +177,7 @@ MG_HD inline int gwf_diag_sort(Arena &A, GwfState &z, int32_t n_a, GwfDiag *a)
 		if (a[i].xo & 1) c[k++] = a[i];
 		else b[j++] = a[i];
 	}
-	MGB_TRY(radix_sort_exact(A, c, n_c, 8, KeyDiagVd()));
+	MGB_TRY(gwf_sort_diag_cold(A, c, n_c));
 	for (k = 0; k < n_c; ++k) c[k].xo &= 0xfffffffeU;
 	i = j = k = 0;
 	while (i < n_b && j < n_c) {
@@ -217,11 +230,11 @@ MG_HD inline int gwf_dedup(Arena &A, GwfState &z, int32_t n_a, GwfDiag *a, int32
 	if (z.intv.n + z.tmp.n > 0) {
 		int64_t i;
 		for (i = 1; i < z.tmp.n; ++i) if (z.tmp.a[i-1].vd0 > z.tmp.a[i].vd0) break;
-		if (i < z.tmp.n) MGB_TRY(radix_sort_exact(A, z.tmp.a, z.tmp.n, 8, KeyIntvVd0()));
-		MGB_TRY(avec_reserve(A, z.swap, z.intv.n));
+		if (i < z.tmp.n) MGB_TRY(gwf_sort_intv_cold(A, z.tmp.a, z.tmp.n));
+		MGB_TRY(avec_reserve_c(A, z.swap, z.intv.n));
 		for (i = 0; i < z.intv.n; ++i) z.swap.a[i] = z.intv.a[i];
 		z.swap.n = z.intv.n;
-		MGB_TRY(avec_reserve(A, z.intv, z.intv.n + z.tmp.n));
+		MGB_TRY(avec_reserve_c(A, z.intv, z.intv.n + z.tmp.n));
 		{ // merge two sorted lists, then fuse overlapping intervals
 			int64_t x = 0, y = 0, k = 0;
 			const GwfIntv *b = z.swap.a, *c = z.tmp.a;
@@ -257,11 +270,13 @@ MG_HD inline int32_t gwf_prune(int32_t n_a, GwfDiag *a, uint32_t max_lag, int32_
 {
 	int32_t i, j, iq, dq, max_i = 0;
 	uint32_t max_x = 0;
+	MGB_NO_UNROLL
 	for (i = 0; i < n_a; ++i)
 		if (a[i].xo >> 1 > max_x) max_x = a[i].xo >> 1, max_i = i;
 	const GwfDiag *q = &a[max_i];
 	iq = (int32_t)q->vd - GWF_DIAG_SHIFT + q->k;
 	dq = (int32_t)(q->xo >> 1) - iq - iq;
+	MGB_NO_UNROLL
 	for (i = j = 0; i < n_a; ++i) {
 		GwfDiag *p = &a[i];
 		int32_t ip = (int32_t)p->vd - GWF_DIAG_SHIFT + p->k;
@@ -288,7 +303,7 @@ MG_HD inline int gwf_extend_batch(Arena &A, GwfState &z, int32_t n, GwfDiag *a)
 		a[j].xo += (uint32_t)a[j].len << 2;
 		a[j].k = k;
 	}
-	MGB_TRY(avec_reserve(A, z.B, z.B.n + n + 2));
+	MGB_TRY(avec_reserve_c(A, z.B, z.B.n + n + 2));
 	GwfDiag *b = &z.B.a[z.B.n];
 	b[0].vd = a[0].vd - 1;
 	b[0].xo = a[0].xo + 2;
@@ -328,7 +343,7 @@ MG_HD inline int gwf_extend_batch(Arena &A, GwfState &z, int32_t n, GwfDiag *a)
 		GwfDiag *p = &a[j];
 		if (p->k == vl - 1 || (int32_t)p->vd - GWF_DIAG_SHIFT + p->k == z.ql - 1) {
 			p->xo |= 1;
-			MGB_TRY(avec_push(A, z.Q, *p));
+			MGB_TRY(avec_push_c(A, z.Q, *p));
 		}
 	}
 	for (j = 0, m = 0; j < n + 2; ++j) {
@@ -339,7 +354,7 @@ MG_HD inline int gwf_extend_batch(Arena &A, GwfState &z, int32_t n, GwfDiag *a)
 		} else if (p->k == vl) {
 			GwfIntv iv;
 			iv.vd0 = gwf_gen_vd(v, d), iv.vd1 = iv.vd0 + 1;
-			MGB_TRY(avec_push(A, z.tmp, iv));
+			MGB_TRY(avec_push_c(A, z.tmp, iv));
 		}
 	}
 	z.B.n += m;
@@ -359,7 +374,7 @@ MG_HD inline int gwf_ed_extend(Arena &A, GwfState &z, const GwfOpt &opt, uint32_
 	u64tab_clear(z.ha);
 	z.Q.n = 0, z.q_head = 0;
 	z.B.n = 0;
-	MGB_TRY(avec_reserve(A, z.B, (int64_t)n * 2));
+	MGB_TRY(avec_reserve_c(A, z.B, (int64_t)n * 2));
 	GwfDiag *a = z.a.a;
 	for (x = 0, i = 1; i <= n; ++i) {
 		if (i == n || a[i].vd != a[i-1].vd + 1) {
@@ -393,7 +408,7 @@ MG_HD inline int gwf_ed_extend(Arena &A, GwfState &z, const GwfOpt &opt, uint32_
 			const DevArc *av = g_arc_a(g, v);
 			GwfIntv iv;
 			iv.vd0 = gwf_gen_vd(v, d), iv.vd1 = iv.vd0 + 1;
-			MGB_TRY(avec_push(A, z.tmp, iv));
+			MGB_TRY(avec_push_c(A, z.tmp, iv));
 			if (opt.traceback) MGB_TRY(gwf_trace_push(A, z, (int32_t)v, t.t, &tw));
 			for (j = 0; j < nv; ++j) {
 				uint32_t w = av[j].w;
@@ -405,7 +420,7 @@ MG_HD inline int gwf_ed_extend(Arena &A, GwfState &z, const GwfOpt &opt, uint32_
 					if (absent) {
 						GwfDiag p;
 						p.vd = gwf_gen_vd(w, i + 1 - ol), p.k = ol, p.xo = (x0 + 2) << 1 | 1, p.t = tw, p.len = 0;
-						MGB_TRY(avec_push(A, z.Q, p));
+						MGB_TRY(avec_push_c(A, z.Q, p));
 					}
 				} else if (absent) {
 					MGB_TRY(gwf_diag_push(A, z.B, w, i - ol,     ol, x0 + 1, 1, tw));
@@ -449,12 +464,12 @@ MG_HD inline int gwf_align(Arena &A, const GraphDev &g, const GwfOpt &opt, int32
 	uint64_t mark_keep = mark;
 	MGB_TRY(u64tab_init(A, z.ha, 6));
 	MGB_TRY(u64tab_init(A, z.ht, 6));
-	MGB_TRY(avec_reserve(A, z.t, 16));
+	MGB_TRY(avec_reserve_c(A, z.t, 16));
 	{
 		GwfDiag d0;
 		d0.vd = gwf_gen_vd(v0, -off0), d0.k = off0 - 1, d0.xo = 0, d0.len = 0, d0.t = 0;
 		if (opt.traceback) MGB_TRY(gwf_trace_push(A, z, -1, -1, &d0.t));
-		MGB_TRY(avec_push(A, z.a, d0));
+		MGB_TRY(avec_push_c(A, z.a, d0));
 	}
 	if (s_term < 0 && opt.s_term >= 0) s_term = opt.s_term;
 	r->n_iter = 0, r->nv = 0, r->v = 0, r->end_v = (uint32_t)-1, r->end_off = -1, r->wlen = 0;
@@ -506,6 +521,7 @@ MG_HD inline int gwf_extend_batch_w(GwfShared *sh, int32_t n, GwfDiag *a, int la
 	const uint32_t v = (uint32_t)(a->vd >> 32);
 	const int32_t vl = g_vlen(g, v), ql = z.ql;
 	const char *ts = g_vseq(g, v);
+	MGB_NO_UNROLL
 	for (int32_t j = lane; j < n; j += MGB_W) {
 		GwfDiag p = a[j];
 		int32_t k = gwf_extend1((int32_t)p.vd - GWF_DIAG_SHIFT, p.k, vl, ts, ql, z.q);
@@ -516,9 +532,9 @@ MG_HD inline int gwf_extend_batch_w(GwfShared *sh, int32_t n, GwfDiag *a, int la
 	}
 	int rc = 0; // codes travel by shuffle, not through shared memory: a flag there could be rewritten before a slow lane has read it
 	if (lane == 0) {
-		rc = avec_reserve(sh->A, z.B, z.B.n + n + 2);
-		if (rc == 0) rc = avec_reserve(sh->A, z.Q, z.Q.n + n);
-		if (rc == 0) rc = avec_reserve(sh->A, z.tmp, z.tmp.n + n + 2);
+		rc = avec_reserve_c(sh->A, z.B, z.B.n + n + 2);
+		if (rc == 0) rc = avec_reserve_c(sh->A, z.Q, z.Q.n + n);
+		if (rc == 0) rc = avec_reserve_c(sh->A, z.tmp, z.tmp.n + n + 2);
 	}
 	warp_sync();
 	rc = warp_bcast_i32(rc, 0);
@@ -529,6 +545,7 @@ MG_HD inline int gwf_extend_batch_w(GwfShared *sh, int32_t n, GwfDiag *a, int la
 	int64_t qn = z.Q.n, tn = z.tmp.n;
 	int32_t m = 0;
 	// next-score candidates b[0..n+1], kept in order when still inside the vertex and the query
+	MGB_NO_UNROLL
 	for (int32_t base = 0; base < n + 2; base += MGB_W) {
 		const int32_t j = base + lane;
 		GwfDiag p;
@@ -577,6 +594,7 @@ MG_HD inline int gwf_extend_batch_w(GwfShared *sh, int32_t n, GwfDiag *a, int la
 		m += mask_count(mk), tn += mask_count(me);
 	}
 	// diagonals touching the end of the vertex or of the query go to the queue
+	MGB_NO_UNROLL
 	for (int32_t base = 0; base < n; base += MGB_W) {
 		const int32_t j = base + lane;
 		GwfDiag p;
@@ -607,6 +625,7 @@ MG_HD inline int gwf_ed_queue(Arena &A, GwfState &z, const GwfOpt &opt, uint32_t
 	const int32_t ql = z.ql;
 	const char *q = z.q;
 	int32_t i, n, do_dedup = z.Q.n != 0;
+	MGB_NO_UNROLL
 	while (z.q_head < z.Q.n) {
 		GwfDiag t = z.Q.a[z.q_head++];
 		uint32_t v, x0;
@@ -630,8 +649,9 @@ MG_HD inline int gwf_ed_queue(Arena &A, GwfState &z, const GwfOpt &opt, uint32_t
 			const DevArc *av = g_arc_a(g, v);
 			GwfIntv iv;
 			iv.vd0 = gwf_gen_vd(v, d), iv.vd1 = iv.vd0 + 1;
-			MGB_TRY(avec_push(A, z.tmp, iv));
+			MGB_TRY(avec_push_c(A, z.tmp, iv));
 			if (opt.traceback) MGB_TRY(gwf_trace_push(A, z, (int32_t)v, t.t, &tw));
+			MGB_NO_UNROLL
 			for (j = 0; j < nv; ++j) {
 				uint32_t w = av[j].w;
 				int32_t ol = av[j].ow;
@@ -642,7 +662,7 @@ MG_HD inline int gwf_ed_queue(Arena &A, GwfState &z, const GwfOpt &opt, uint32_t
 					if (absent) {
 						GwfDiag p;
 						p.vd = gwf_gen_vd(w, i + 1 - ol), p.k = ol, p.xo = (x0 + 2) << 1 | 1, p.t = tw, p.len = 0;
-						MGB_TRY(avec_push(A, z.Q, p));
+						MGB_TRY(avec_push_c(A, z.Q, p));
 					}
 				} else if (absent) {
 					MGB_TRY(gwf_diag_push(A, z.B, w, i - ol,     ol, x0 + 1, 1, tw));
@@ -662,6 +682,7 @@ MG_HD inline int gwf_ed_queue(Arena &A, GwfState &z, const GwfOpt &opt, uint32_t
 			int32_t nv = g_arc_n(g, v), j, tw = -1;
 			const DevArc *av = g_arc_a(g, v);
 			if (opt.traceback) MGB_TRY(gwf_trace_push(A, z, (int32_t)v, t.t, &tw));
+			MGB_NO_UNROLL
 			for (j = 0; j < nv; ++j)
 				MGB_TRY(gwf_diag_push(A, z.B, av[j].w, i - av[j].ow, av[j].ow, x0 + 1, 1, tw));
 		}
@@ -684,12 +705,14 @@ MG_HD inline void gwf_ed_finish(GwfState &z, const GwfOpt &opt)
 MG_HD inline int64_t gwf_lower_bound_vd(const GwfDiag *a, int64_t n, uint64_t key) // number of elements with vd < key
 {
 	int64_t lo = 0, hi = n;
+	MGB_NO_UNROLL
 	while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (a[mid].vd < key) lo = mid + 1; else hi = mid; }
 	return lo;
 }
 MG_HD inline int64_t gwf_upper_bound_vd(const GwfDiag *a, int64_t n, uint64_t key) // number of elements with vd <= key
 {
 	int64_t lo = 0, hi = n;
+	MGB_NO_UNROLL
 	while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (a[mid].vd <= key) lo = mid + 1; else hi = mid; }
 	return lo;
 }
@@ -701,17 +724,24 @@ MG_HD inline int gwf_dedup_w(GwfShared *sh, int lane)
 	Arena &A = sh->A;
 	// forbidden intervals: fold the new ones in (nothing changes when there are no new ones)
 	const int64_t n_old = z.intv.n, n_new = z.tmp.n;
-	int rc0 = 0;
+	int rc0 = 0, tmp_big_unsorted = 0;
+	if (n_new > 1) { // the new intervals in order (klib sorts up to 64 elements by insertion: a stable sort, done here by counting)
+		GwfIntv *tn = z.tmp.a;
+		int uns = 0;
+		MGB_NO_UNROLL
+		for (int64_t i = 1 + lane; i < n_new; i += MGB_W) if (tn[i-1].vd0 > tn[i].vd0) uns = 1;
+		uns = warp_any(uns);
+		if (uns && n_new <= 64) small_sort_stable_w(tn, n_new, KeyIntvVd0(), lane);
+		else tmp_big_unsorted = uns;
+	}
 	if (lane == 0) {
 		int rc = 0;
 		if (n_new > 0) {
-			int64_t i;
-			for (i = 1; i < n_new; ++i) if (z.tmp.a[i-1].vd0 > z.tmp.a[i].vd0) break;
-			if (i < n_new) rc = radix_sort_exact(A, z.tmp.a, n_new, 8, KeyIntvVd0());
-			if (rc == 0) rc = avec_reserve(A, z.swap, n_old);
-			if (rc == 0) z.swap.n = n_old, rc = avec_reserve(A, z.intv, n_old + n_new);
+			if (tmp_big_unsorted) rc = gwf_sort_intv_cold(A, z.tmp.a, n_new);
+			if (rc == 0) rc = avec_reserve_c(A, z.swap, n_old);
+			if (rc == 0) z.swap.n = n_old, rc = avec_reserve_c(A, z.intv, n_old + n_new);
 		}
-		if (rc == 0) rc = avec_reserve(A, z.ooo, z.B.n);
+		if (rc == 0) rc = avec_reserve_c(A, z.ooo, z.B.n);
 		rc0 = rc;
 	}
 	warp_sync();
@@ -719,18 +749,23 @@ MG_HD inline int gwf_dedup_w(GwfShared *sh, int lane)
 	if (rc0 < 0) return rc0;
 	if (n_new > 0) {
 		GwfIntv *b = z.swap.a, *c = z.tmp.a, *o = z.intv.a;
+		MGB_NO_UNROLL
 		for (int64_t i = lane; i < n_old; i += MGB_W) b[i] = o[i]; // o may have moved: avec_reserve copied the old content
 		warp_sync();
 		// stable merge of two sorted lists (the old one first on ties), every element finds its place by bisection
+		MGB_NO_UNROLL
 		for (int64_t x = lane; x < n_old; x += MGB_W) {
 			const uint64_t key = b[x].vd0;
 			int64_t lo = 0, hi = n_new;
+			MGB_NO_UNROLL
 			while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (c[mid].vd0 < key) lo = mid + 1; else hi = mid; }
 			o[x + lo] = b[x];
 		}
+		MGB_NO_UNROLL
 		for (int64_t y = lane; y < n_new; y += MGB_W) {
 			const uint64_t key = c[y].vd0;
 			int64_t lo = 0, hi = n_old;
+			MGB_NO_UNROLL
 			while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (b[mid].vd0 <= key) lo = mid + 1; else hi = mid; }
 			o[y + lo] = c[y];
 		}
@@ -739,6 +774,7 @@ MG_HD inline int gwf_dedup_w(GwfShared *sh, int lane)
 		const int64_t n_m = n_old + n_new;
 		int64_t k = 0;
 		uint64_t carry = 0; // running maximum of vd1 over the elements of the earlier rounds
+		MGB_NO_UNROLL
 		for (int64_t base = 0; base < n_m; base += MGB_W) {
 			const int64_t i = base + lane;
 			GwfIntv e;
@@ -766,11 +802,13 @@ MG_HD inline int gwf_dedup_w(GwfShared *sh, int lane)
 	const int32_t n_a = (int32_t)z.B.n;
 	// ---- gwf_diag_dedup: sort if needed ----
 	int unsorted = 0;
+	MGB_NO_UNROLL
 	for (int32_t i = 1 + lane; i < n_a; i += MGB_W) if (a[i-1].vd > a[i].vd) unsorted = 1;
 	unsorted = warp_any(unsorted);
 	if (unsorted) { // gwf_diag_sort: in-order part and out-of-order part, the latter sorted, then a stable merge
 		GwfDiag *b = z.ooo.a;
 		int32_t n_c = 0;
+		MGB_NO_UNROLL
 		for (int32_t base = 0; base < n_a; base += MGB_W) {
 			const int32_t i = base + lane;
 			n_c += mask_count(warp_ballot(i < n_a && (a[i].xo & 1)));
@@ -778,6 +816,7 @@ MG_HD inline int gwf_dedup_w(GwfShared *sh, int lane)
 		const int32_t n_b = n_a - n_c;
 		GwfDiag *c = b + n_b;
 		int32_t jb = 0, jc = 0;
+		MGB_NO_UNROLL
 		for (int32_t base = 0; base < n_a; base += MGB_W) {
 			const int32_t i = base + lane;
 			GwfDiag p;
@@ -791,18 +830,25 @@ MG_HD inline int gwf_dedup_w(GwfShared *sh, int lane)
 			jc += mask_count(mc), jb += mask_count(mb);
 		}
 		warp_sync();
-		if (lane == 0) rc0 = radix_sort_exact(A, c, n_c, 8, KeyDiagVd());
-		warp_sync();
-		rc0 = warp_bcast_i32(rc0, 0);
-		if (rc0 < 0) return rc0;
+		if (n_c <= 64) small_sort_stable_w(c, n_c, KeyDiagVd(), lane); // what klib's insertion sort of a short list yields
+		else {
+			if (lane == 0) rc0 = gwf_sort_diag_cold(A, c, n_c);
+			warp_sync();
+			rc0 = warp_bcast_i32(rc0, 0);
+			if (rc0 < 0) return rc0;
+		}
+		MGB_NO_UNROLL
 		for (int32_t j = lane; j < n_c; j += MGB_W) c[j].xo &= 0xfffffffeU;
 		warp_sync();
+		MGB_NO_UNROLL
 		for (int32_t i = lane; i < n_b; i += MGB_W) a[i + gwf_lower_bound_vd(c, n_c, b[i].vd)] = b[i];
+		MGB_NO_UNROLL
 		for (int32_t j = lane; j < n_c; j += MGB_W) a[j + gwf_upper_bound_vd(b, n_b, c[j].vd)] = c[j];
 		warp_sync();
 	}
 	// ---- one diagonal per (vertex,diag): the first one reaching furthest ----
 	int32_t n = 0;
+	MGB_NO_UNROLL
 	for (int32_t base = 0; base < n_a; base += MGB_W) {
 		const int32_t i = base + lane;
 		GwfDiag best;
@@ -812,6 +858,7 @@ MG_HD inline int gwf_dedup_w(GwfShared *sh, int lane)
 			best = a[i];
 			head = i == 0 || a[i-1].vd != best.vd;
 			if (head)
+				MGB_NO_UNROLL
 				for (int32_t j = i + 1; j < n_a && a[j].vd == best.vd; ++j)
 					if (best.k < a[j].k) best = a[j];
 		}
@@ -826,6 +873,7 @@ MG_HD inline int gwf_dedup_w(GwfShared *sh, int lane)
 		const GwfIntv *iv = z.intv.a;
 		const int64_t n_iv = z.intv.n;
 		int32_t k = 0;
+		MGB_NO_UNROLL
 		for (int32_t base = 0; base < n; base += MGB_W) {
 			const int32_t i = base + lane;
 			GwfDiag p;
@@ -834,6 +882,7 @@ MG_HD inline int gwf_dedup_w(GwfShared *sh, int lane)
 			if (i < n) {
 				p = a[i];
 				int64_t lo = 0, hi = n_iv; // intervals are disjoint and sorted: the last one starting at or before vd decides
+				MGB_NO_UNROLL
 				while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (iv[mid].vd0 <= p.vd) lo = mid + 1; else hi = mid; }
 				keep = !(lo > 0 && p.vd < iv[lo - 1].vd1);
 			}
@@ -868,18 +917,19 @@ MG_HD inline int gwf_align_w(GwfShared *sh, const GraphDev &g, const GwfOpt &opt
 		avec_init(z.a), avec_init(z.B), avec_init(z.ooo), avec_init(z.Q), avec_init(z.intv), avec_init(z.tmp), avec_init(z.swap), avec_init(z.t);
 		rc = u64tab_init(A, z.ha, 6);
 		if (rc == 0) rc = u64tab_init(A, z.ht, 6);
-		if (rc == 0) rc = avec_reserve(A, z.t, 16);
+		if (rc == 0) rc = avec_reserve_c(A, z.t, 16);
 		if (rc == 0) {
 			GwfDiag d0;
 			d0.vd = gwf_gen_vd(v0, -off0), d0.k = off0 - 1, d0.xo = 0, d0.len = 0, d0.t = 0;
 			if (opt.traceback) rc = gwf_trace_push(A, z, -1, -1, &d0.t);
-			if (rc == 0) rc = avec_push(A, z.a, d0);
+			if (rc == 0) rc = avec_push_c(A, z.a, d0);
 		}
 		r->n_iter = 0, r->nv = 0, r->v = 0, r->end_v = (uint32_t)-1, r->end_off = -1, r->wlen = 0;
 		code = rc, go = rc == 0 && z.a.n > 0;
 	}
 	warp_sync();
 	code = warp_bcast_i32(code, 0), go = warp_bcast_i32(go, 0);
+	MGB_NO_UNROLL
 	while (go) {
 		// ---- one edit-distance step (gwf_ed_extend) ----
 		if (lane == 0) {
@@ -889,7 +939,7 @@ MG_HD inline int gwf_align_w(GwfShared *sh, const GraphDev &g, const GwfOpt &opt
 			u64tab_clear(z.ha);
 			z.Q.n = 0, z.q_head = 0;
 			z.B.n = 0;
-			code = avec_reserve(A, z.B, z.a.n * 2);
+			code = avec_reserve_c(A, z.B, z.a.n * 2);
 		}
 		warp_sync();
 		code = warp_bcast_i32(code, 0);
@@ -898,9 +948,11 @@ MG_HD inline int gwf_align_w(GwfShared *sh, const GraphDev &g, const GwfOpt &opt
 			const int32_t n = (int32_t)z.a.n;
 			GwfDiag *a = z.a.a;
 			int32_t x = 0, rc = 0;
+			MGB_NO_UNROLL
 			for (int32_t base = 1; base <= n && rc == 0; base += MGB_W) { // runs of consecutive diagonals, in order
 				const int32_t i = base + lane;
 				uint32_t mask = warp_ballot(i <= n && (i == n || a[i].vd != a[i-1].vd + 1));
+				MGB_NO_UNROLL
 				while (mask && rc == 0) {
 					const int32_t e = base + ctz32(mask);
 					mask &= mask - 1;
@@ -935,6 +987,7 @@ MG_HD inline int gwf_align_w(GwfShared *sh, const GraphDev &g, const GwfOpt &opt
 		int rc = 0;
 		if (opt.traceback && r->end_off >= 0) { // reference: gfa-ed.c:509-522 gwf_traceback
 			int32_t i = z.end_tb, n = 1;
+			MGB_NO_UNROLL
 			while (i >= 0 && z.t.a[i].v >= 0) ++n, i = z.t.a[i].pre;
 			int32_t *walk = (int32_t*)(A.base + mark);
 			int32_t *tmpw = (int32_t*)arena_alloc(A, (uint64_t)n * sizeof(int32_t));
@@ -942,9 +995,12 @@ MG_HD inline int gwf_align_w(GwfShared *sh, const GraphDev &g, const GwfOpt &opt
 			else {
 				i = z.end_tb, n = 0;
 				tmpw[n++] = (int32_t)r->end_v;
+				MGB_NO_UNROLL
 				while (i >= 0 && z.t.a[i].v >= 0) tmpw[n++] = z.t.a[i].v, i = z.t.a[i].pre;
 				r->nv = n;
+				MGB_NO_UNROLL
 				for (i = 0; i < n >> 1; ++i) { int32_t t = tmpw[i]; tmpw[i] = tmpw[n - 1 - i], tmpw[n - 1 - i] = t; }
+				MGB_NO_UNROLL
 				for (i = 0; i < n; ++i) { int32_t t = tmpw[i]; walk[i] = t; } // forward copy: the destination lies below the source
 				r->v = walk;
 				mark_keep = mark + (((uint64_t)n * 4 + 15) & ~(uint64_t)15);

@@ -744,6 +744,16 @@ MG_HD inline int wfa_chain(Arena &A, int32_t tl, const char *ts, int32_t ql, con
 // beyond the cap the chaining heuristic takes over on lane 0.
 MG_HD inline int wfa_ring_g(Arena &A, int32_t tl, const char *ts, int32_t ql, const char *qs, int64_t max_iter, WfResult *r,
 							 uint32_t *cig_store, int64_t max_cigar, int lane); // mgb_wfa_tiers.cuh
+// the two rare continuations of tier 3, out of line: they are most of the kernel's code and would set its register count
+MG_HD MG_NOINLINE inline int wfa_core_cold(Arena &A, int32_t tl, const char *ts, int32_t ql, const char *qs, int64_t max_iter, WfResult *r, uint32_t *cig_store, int64_t max_cigar, int lane)
+{
+	return wfa_core(A, tl, ts, ql, qs, max_iter, 0, 0, r, cig_store, max_cigar, lane, MGB_W);
+}
+MG_HD MG_NOINLINE inline int wfa_chain_cold(Arena &A, int32_t tl, const char *ts_g, int32_t ql, const char *qs_g, WfResult *r, uint32_t *cig_store, int64_t max_cigar, int32_t step)
+{
+	return wfa_chain(A, tl, ts_g, ql, qs_g, r, cig_store, max_cigar, step);
+}
+
 MG_HD inline int wfa_exact(Arena &A, int32_t tl, const char *ts_g, int32_t ql, const char *qs_g, int64_t max_iter, WfResult *r, int lane, int32_t step = 5000)
 {
 	uint64_t mark = A.top;
@@ -761,14 +771,19 @@ MG_HD inline int wfa_exact(Arena &A, int32_t tl, const char *ts_g, int32_t ql, c
 	{
 		int rc = wfa_ring_g(A, tl, ts, ql, qs, max_iter, r, cig_store, max_cigar, lane);
 		if (rc < 0) return rc;
-		if (rc == 1) MGB_TRY(wfa_core(A, tl, ts, ql, qs, max_iter, 0, 0, r, cig_store, max_cigar, lane, MGB_W));
+		if (rc == 1) { // (through a copy: an arena header whose address is taken would live in local memory for the whole kernel)
+			Arena B = A;
+			rc = wfa_core_cold(B, tl, ts, ql, qs, max_iter, r, cig_store, max_cigar, lane);
+			A.top = B.top, A.peak = B.peak;
+			if (rc < 0) return rc;
+		}
 	}
 	if (r->s < 0) { // iteration cap hit
 		int rc = 0;
 		int32_t n_cig = 0, sc = 0;
 		if (lane == 0) {
 			Arena B = A;
-			rc = wfa_chain(B, tl, ts_g, ql, qs_g, r, cig_store, max_cigar, step);
+			rc = wfa_chain_cold(B, tl, ts_g, ql, qs_g, r, cig_store, max_cigar, step);
 			n_cig = r->n_cigar, sc = r->s;
 			if (B.peak > A.peak) A.peak = B.peak;
 		}

@@ -35,6 +35,58 @@ MG_HD inline int32_t wf2_ld(const void *base, int32_t off)
 	return v;
 }
 
+// ---- one cell of a wavefront, in two halves so that two cells can be in flight per lane (MGB_WF_CELLS = 2) ----
+// LOAD: the nine neighbour reads and the recurrence (reference: miniwfa.c:281-308 wf_next_tb); FINISH: traceback byte, window
+// votes, extension along exact matches (miniwfa.c:212-226) and the five stores.  The slots of score ns are not read while a
+// wavefront is computed, so the FINISH of one cell may follow the LOAD of the next.  Expected in scope: H E1 F1 E2 F2 (arrays),
+// bHx bHo1 bHo2 bE1 bE2 bnH bn3 bn2 (byte offsets of the slices), colmask2 (2W-1), ax, lo, hi, tl, ql, ts, qs, d_corner, vote.
+#ifndef MGB_WF_CELLS
+#define MGB_WF_CELLS 1
+#endif
+#define MGB_WF_CELL_LOAD(S, d_) \
+	int32_t h##S, e1##S, e2##S, f1##S, f2##S; \
+	uint8_t xz##S; \
+	const int32_t c##S = (((d_) + (1 << 20)) * 2) & colmask2; /* byte column */ \
+	{ \
+		const int32_t cm_ = (c##S - 2) & colmask2, cp_ = (c##S + 2) & colmask2; \
+		int32_t a0_, b0_, e_, f_; \
+		uint8_t x_ = 0, ze_, zf_, z_; \
+		a0_ = wf2_ld(H, bHo1 + cm_), b0_ = wf2_ld(E1, bE1 + cm_); \
+		x_ |= a0_ >= b0_? 0 : 0x08; e1##S = MGB_WF_MAX(a0_, b0_); \
+		a0_ = wf2_ld(H, bHo2 + cm_), b0_ = wf2_ld(E2, bE2 + cm_); \
+		x_ |= a0_ >= b0_? 0 : 0x20; e2##S = MGB_WF_MAX(a0_, b0_); \
+		ze_ = e1##S >= e2##S? 1 : 3; \
+		e_ = MGB_WF_MAX(e1##S, e2##S); \
+		a0_ = wf2_ld(H, bHo1 + cp_), b0_ = wf2_ld(F1, bE1 + cp_); \
+		x_ |= a0_ >= b0_? 0 : 0x10; f1##S = MGB_WF_MAX(a0_, b0_) + 1; \
+		a0_ = wf2_ld(H, bHo2 + cp_), b0_ = wf2_ld(F2, bE2 + cp_); \
+		x_ |= a0_ >= b0_? 0 : 0x40; f2##S = MGB_WF_MAX(a0_, b0_) + 1; \
+		zf_ = f1##S >= f2##S? 2 : 4; \
+		f_ = MGB_WF_MAX(f1##S, f2##S); \
+		z_ = e_ >= f_? ze_ : zf_; \
+		h##S = MGB_WF_MAX(e_, f_); \
+		a0_ = wf2_ld(H, bHx + c##S) + 1; \
+		z_ = a0_ >= h##S? 0 : z_; \
+		h##S = MGB_WF_MAX(a0_, h##S); \
+		xz##S = x_ | z_; \
+	}
+#define MGB_WF_CELL_FINISH(S, d_) \
+	{ \
+		const int32_t dd_ = (d_); \
+		ax[dd_] = xz##S; \
+		if (dd_ == lo || dd_ == hi) { /* does the window still grow on this side? */ \
+			if (h##S >= -1 || e1##S >= -1 || f1##S >= -1 || e2##S >= -1 || f2##S >= -1) vote |= (dd_ == lo? 1u : 0u) | (dd_ == hi? 2u : 0u); \
+		} \
+		if (!(h##S < -1 || dd_ + h##S < -1 || h##S >= tl || dd_ + h##S >= ql)) { /* extend the new cell right away */ \
+			const int32_t k_ = wf_extend(ts, qs, h##S, dd_); \
+			if (dd_ == d_corner && k_ == tl - 1) vote |= 4u | (k_ == h##S? 8u : 0u); \
+			else h##S = k_; \
+		} \
+		*(wf_cell_t*)((char*)E1 + bn3 + c##S) = (wf_cell_t)e1##S, *(wf_cell_t*)((char*)F1 + bn3 + c##S) = (wf_cell_t)f1##S; \
+		*(wf_cell_t*)((char*)E2 + bn2 + c##S) = (wf_cell_t)e2##S, *(wf_cell_t*)((char*)F2 + bn2 + c##S) = (wf_cell_t)f2##S; \
+		*(wf_cell_t*)((char*)H + bnH + c##S) = (wf_cell_t)h##S; \
+	}
+
 template<int W, int MAXLEN, int TBCAP>
 MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g, int32_t ql, const char *qs_g, WfResult *r, int lane)
 {
@@ -121,43 +173,22 @@ MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g,
 		// otherwise re-derive each of them from the slot numbers for every cell)
 		int32_t bHx = r4 * W * 2, bHo1 = r6 * W * 2, bHo2 = r16 * W * 2, bE1 = e1slot * W * 2, bE2 = m2 * W * 2, bnH = nhs * W * 2, bn3 = n3 * W * 2, bn2 = n2 * W * 2;
 		MGB_OPAQUE(bHx); MGB_OPAQUE(bHo1); MGB_OPAQUE(bHo2); MGB_OPAQUE(bE1); MGB_OPAQUE(bE2); MGB_OPAQUE(bnH); MGB_OPAQUE(bn3); MGB_OPAQUE(bn2);
-#define MGB_WF_LD(base, off) wf2_ld(base, off)
-#define MGB_WF_ST(base, off, v) (*(wf_cell_t*)((char*)(base) + (off)) = (wf_cell_t)(v))
+		const int32_t colmask2 = 2 * W - 1;
 		uint32_t vote = 0; // 1: window grows on the low side, 2: on the high side, 4: corner reached, 8: ... without extension
-		for (int32_t d = lo + lane; d <= hi; d += MGB_W) { // reference: miniwfa.c:281-308 wf_next_tb, then :212-226 on the new cell
-			int32_t h, f, e, e1, e2, f1, f2, a0, b0;
-			uint8_t x = 0, ze, zf, z;
-			const int32_t c = wfs_col<W>(d) * 2, cm = (c - 2) & (2 * W - 1), cp = (c + 2) & (2 * W - 1); // byte columns
-			a0 = MGB_WF_LD(H, bHo1 + cm), b0 = MGB_WF_LD(E1, bE1 + cm);
-			x |= a0 >= b0? 0 : 0x08; e1 = MGB_WF_MAX(a0, b0);
-			a0 = MGB_WF_LD(H, bHo2 + cm), b0 = MGB_WF_LD(E2, bE2 + cm);
-			x |= a0 >= b0? 0 : 0x20; e2 = MGB_WF_MAX(a0, b0);
-			ze = e1 >= e2? 1 : 3;
-			e = MGB_WF_MAX(e1, e2);
-			a0 = MGB_WF_LD(H, bHo1 + cp), b0 = MGB_WF_LD(F1, bE1 + cp);
-			x |= a0 >= b0? 0 : 0x10; f1 = MGB_WF_MAX(a0, b0) + 1;
-			a0 = MGB_WF_LD(H, bHo2 + cp), b0 = MGB_WF_LD(F2, bE2 + cp);
-			x |= a0 >= b0? 0 : 0x40; f2 = MGB_WF_MAX(a0, b0) + 1;
-			zf = f1 >= f2? 2 : 4;
-			f = MGB_WF_MAX(f1, f2);
-			z = e >= f? ze : zf;
-			h = MGB_WF_MAX(e, f);
-			a0 = MGB_WF_LD(H, bHx + c) + 1;
-			z = a0 >= h? 0 : z;
-			h = MGB_WF_MAX(a0, h);
-			ax[d] = x | z;
-			if (d == lo || d == hi) { // does the window still grow on this side?
-				if (h >= -1 || e1 >= -1 || f1 >= -1 || e2 >= -1 || f2 >= -1) vote |= (d == lo? 1u : 0u) | (d == hi? 2u : 0u);
-			}
-			if (!(h < -1 || d + h < -1 || h >= tl || d + h >= ql)) { // extend the new cell right away
-				const int32_t k = wf_extend(ts, qs, h, d);
-				if (d == d_corner && k == tl - 1) vote |= 4u | (k == h? 8u : 0u);
-				else h = k;
-			}
-			MGB_WF_ST(E1, bn3 + c, e1), MGB_WF_ST(F1, bn3 + c, f1), MGB_WF_ST(E2, bn2 + c, e2), MGB_WF_ST(F2, bn2 + c, f2), MGB_WF_ST(H, bnH + c, h); // slots of score ns are not read in this loop
+#if MGB_WF_CELLS == 2
+		for (int32_t d = lo + lane; d <= hi; d += 2 * MGB_W) { // two cells per lane in flight: eighteen loads before the first use
+			const int32_t dB = d + MGB_W <= hi? d + MGB_W : d;
+			MGB_WF_CELL_LOAD(A, d)
+			MGB_WF_CELL_LOAD(B, dB)
+			MGB_WF_CELL_FINISH(A, d)
+			if (dB != d) MGB_WF_CELL_FINISH(B, dB)
 		}
-#undef MGB_WF_LD
-#undef MGB_WF_ST
+#else
+		for (int32_t d = lo + lane; d <= hi; d += MGB_W) {
+			MGB_WF_CELL_LOAD(A, d)
+			MGB_WF_CELL_FINISH(A, d)
+		}
+#endif
 		vote = warp_or_u32(vote);
 		if (vote & 1) wlo = lo;
 		if (vote & 2) whi = hi;
@@ -188,20 +219,26 @@ MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g,
 // =================================================================================================================
 // tier 3: the same scheme with the ring in the worker arena and clean slices
 // =================================================================================================================
-// Same idea as above, with two additions the long runs need.  (1) The ring covers every diagonal of the matrix, far more
-// than a gap ever touches, so the slices are initialised lazily: [flo,fhi] is the span of columns on which all 85
-// slices hold -inf or real cells, and it is extended ahead of the window, 128 columns at a time.  (2) Every 256 scores
-// the band is re-centred and can shrink (miniwfa.c:144-171); a slot then still holds cells of the wider wavefront of 17
-// scores ago outside the new range, which the bounds checks of the first version hide.  Here the part of the old range
-// that sticks out is set back to -inf when the slot is rewritten, which keeps the invariant "a slice holds -inf outside
-// the range it was last written with" and with it every value the recurrence and the band shrink read.
+// Same idea as above, with three additions the long runs need.  (1) The ring covers every diagonal of the matrix, far more
+// than a gap ever touches, so the slices are initialised lazily: [flo,fhi] is the span of columns on which all slices hold
+// -inf or real cells, and it is extended ahead of the window, 128 columns at a time.  (2) Every 256 scores the band is
+// re-centred and can shrink (miniwfa.c:144-171); a slot then still holds cells of a wider, older wavefront outside the new
+// range, which the bounds checks of the first version hide.  Here the part of the old range that sticks out is set back to
+// -inf when the slot is rewritten, which keeps the invariant "a slice holds -inf outside the range it was last written with"
+// and with it every value the recurrence reads.  (3) The band shrink asks, per diagonal, whether one of the last 17 wavefronts
+// has a cell inside the matrix in any of its five components -- the one reader of E/F values older than two scores.  Instead of
+// keeping 17 slots of all five arrays for it (85 slices), the 17 wavefronts in front of a shrink note, per diagonal, the last
+// score with such a cell in one extra slice G; the ring is then H x 17, E1/F1 x 3, E2/F2 x 2 as in the on-chip tiers: 28 slices.
+// Measured on B200 (round 2, config 3): the 85-slice ring of the resident warps did not fit L2 -- k_wfa_big moved 67 GB through
+// DRAM per 20 000 reads (11 bytes written per cell, every wavefront evicted before its slot was reused).
+static const int WF3_NSL = 17 + 3 + 3 + 2 + 2 + 1;
 #define MGB_WF2_FILL(need_lo_, need_hi_) do { \
 		const int32_t nl_ = (need_lo_), nh_ = (need_hi_); \
 		if (fhi < flo || nl_ < flo || nh_ > fhi) { \
 			int32_t tlo_ = nl_ - 128 > -tl - 1? nl_ - 128 : -tl - 1, thi_ = nh_ + 128 < ql + 1? nh_ + 128 : ql + 1; \
 			if (fhi >= flo) { if (nl_ >= flo) tlo_ = flo; if (nh_ <= fhi) thi_ = fhi; } \
 			const int32_t a0_ = tlo_, a1_ = fhi >= flo? flo - 1 : thi_, b0_ = fhi >= flo? fhi + 1 : thi_ + 1, b1_ = thi_; \
-			for (int sl_ = 0; sl_ < 85; ++sl_) { \
+			for (int sl_ = 0; sl_ < WF3_NSL; ++sl_) { \
 				wf_cell_t *p_ = cells + (int64_t)sl_ * W; \
 				for (int32_t d_ = a0_ + lane; d_ <= a1_; d_ += MGB_W) p_[(d_ + (1 << 20)) & mask] = (wf_cell_t)WF_NEG_INF16; \
 				for (int32_t d_ = b0_ + lane; d_ <= b1_; d_ += MGB_W) p_[(d_ + (1 << 20)) & mask] = (wf_cell_t)WF_NEG_INF16; \
@@ -210,19 +247,28 @@ MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g,
 			warp_sync(); \
 		} \
 	} while (0)
+// the slot about to be rewritten held the wavefront with range g_: what of it sticks out of [lo,hi] becomes -inf again
+#define MGB_WF2_CLEAN(p_, g_) do { \
+		const int32_t olo_ = (int32_t)((g_) & 0xffffu) - 0x8000, ohi_ = (int32_t)((g_) >> 16) - 0x8000; \
+		if (olo_ < lo || ohi_ > hi) { \
+			wf_cell_t *q_ = (p_); \
+			for (int32_t d_ = olo_ + lane; d_ <= ohi_ && d_ < lo; d_ += MGB_W) q_[(d_ + (1 << 20)) & mask] = (wf_cell_t)WF_NEG_INF16; \
+			for (int32_t d_ = (hi + 1 > olo_? hi + 1 : olo_) + lane; d_ <= ohi_; d_ += MGB_W) q_[(d_ + (1 << 20)) & mask] = (wf_cell_t)WF_NEG_INF16; \
+		} \
+	} while (0)
 
 MG_HD inline int wfa_ring_g(Arena &A, int32_t tl, const char *ts, int32_t ql, const char *qs, int64_t max_iter, WfResult *r,
 							uint32_t *cig_store, int64_t max_cigar, int lane)
 {
-	if (tl + ql > 16000 || tl <= 0 || ql <= 0) return 1;
+	if (tl + ql > 16000 || tl <= 0 || ql <= 0) return 1; // (scores stay below 2^15 too: deleting one sequence and inserting the other costs tl + ql + 30)
 	uint64_t mark = A.top;
 	int32_t W = 64;
 	while (W < tl + ql + 2) W <<= 1;
 	const int32_t mask = W - 1;
 	wf_cell_t *cells;
-	MGB_ALLOC(A, cells, wf_cell_t, (int64_t)5 * 17 * W);
-	wf_cell_t *H = cells, *E1 = H + 17 * W, *F1 = E1 + 17 * W, *E2 = F1 + 17 * W, *F2 = E2 + 17 * W;
-	int32_t flo = 0, fhi = -1; // columns on which all 85 slices have been initialised with -inf (empty so far)
+	MGB_ALLOC(A, cells, wf_cell_t, (int64_t)WF3_NSL * W);
+	wf_cell_t *H = cells, *E1 = H + 17 * W, *F1 = E1 + 3 * W, *E2 = F1 + 3 * W, *F2 = E2 + 2 * W, *G = F2 + 2 * W;
+	int32_t flo = 0, fhi = -1; // columns on which all slices have been initialised with -inf (empty so far)
 	const int32_t d_corner = ql - tl;
 	AVec<WfTbRow> rows;
 	avec_init(rows);
@@ -230,9 +276,20 @@ MG_HD inline int wfa_ring_g(Arena &A, int32_t tl, const char *ts, int32_t ql, co
 	int32_t n_rows = 0;
 	int32_t wlo = 0, whi = 0, last_state = 0, s = 0, stopped = 0;
 	int64_t n_iter = 0;
-	int hs = 0;
+	int hs = 0, m3 = 0, m2 = 0; // s % 17, s % 3, s % 2, kept incrementally
 #define MGB_WF_RG(lo_, hi_) ((uint32_t)((hi_) + 0x8000) << 16 | (uint32_t)((lo_) + 0x8000))
-	uint32_t g0 = MGB_WF_RG(0, 0), g1 = MGB_WF_RG(1, 0), g2 = g1, g3 = g1, g4 = g1, g5 = g1, g6 = g1, g7 = g1, g8 = g1, g9 = g1, g10 = g1, g11 = g1, g12 = g1, g13 = g1, g14 = g1, g15 = g1, g16 = g1;
+	// [lo,hi] of the last 17 wavefronts, by score modulo 17 (empty ranges before score 0).  On the device lane j keeps entry j in a
+	// register (three shuffles per score instead of a 17-register shift chain); a simulator with fewer lanes keeps the array.
+#if MGB_W >= 32
+	uint32_t g_mine = lane == 0? MGB_WF_RG(0, 0) : MGB_WF_RG(1, 0);
+#define MGB_WF_GGET(slot_) ((uint32_t)warp_bcast_i32((int32_t)g_mine, (slot_)))
+#define MGB_WF_GSET(slot_, v_) do { if (lane == (slot_)) g_mine = (v_); } while (0)
+#else
+	uint32_t g_all[17];
+	for (int j = 0; j < 17; ++j) g_all[j] = j == 0? MGB_WF_RG(0, 0) : MGB_WF_RG(1, 0);
+#define MGB_WF_GGET(slot_) (g_all[(slot_)])
+#define MGB_WF_GSET(slot_, v_) (g_all[(slot_)] = (v_))
+#endif
 	int hit = 0, hit_noext = 0;
 	MGB_WF2_FILL(-1, 1);
 	if (lane == 0) { // score 0: the main diagonal, extended from the corner
@@ -256,7 +313,7 @@ MG_HD inline int wfa_ring_g(Arena &A, int32_t tl, const char *ts, int32_t ql, co
 		const int32_t hi = whi < ql? whi + 1 : ql;
 		const int32_t width = hi - lo + 1;
 		const int32_t ns = s + 1;
-		const int nhs = hs + 1 == 17? 0 : hs + 1;
+		const int nhs = hs + 1 == 17? 0 : hs + 1, n3 = m3 + 1 == 3? 0 : m3 + 1, n2 = m2 ^ 1;
 		MGB_TRY(avec_reserve_w(A, rows, n_rows + 1, lane));
 		uint8_t *x;
 		MGB_ALLOC(A, x, uint8_t, width);
@@ -264,82 +321,57 @@ MG_HD inline int wfa_ring_g(Arena &A, int32_t tl, const char *ts, int32_t ql, co
 		rows.n = ++n_rows;
 		uint8_t *ax = x - lo;
 		const int r4 = nhs >= WF_X? nhs - WF_X : nhs - WF_X + 17, r6 = nhs >= WF_O1 + WF_E1? nhs - (WF_O1 + WF_E1) : nhs - (WF_O1 + WF_E1) + 17;
-		const int r16 = nhs >= WF_O2 + WF_E2? nhs - (WF_O2 + WF_E2) : nhs - (WF_O2 + WF_E2) + 17, r2 = nhs >= WF_E1? nhs - WF_E1 : nhs - WF_E1 + 17;
+		const int r16 = nhs >= WF_O2 + WF_E2? nhs - (WF_O2 + WF_E2) : nhs - (WF_O2 + WF_E2) + 17;
+		const int e1slot = n3 >= 2? n3 - 2 : n3 + 1; // (ns-2) % 3
 		MGB_WF2_FILL(lo - 1, hi + 1);
-		{ // the slot of score ns held score ns-17: after a band shrink that range can reach beyond [lo,hi]; what sticks out becomes -inf again
-			const int32_t olo = (int32_t)(g16 & 0xffffu) - 0x8000, ohi = (int32_t)(g16 >> 16) - 0x8000;
-			if (olo < lo || ohi > hi) {
-				for (int a5 = 0; a5 < 5; ++a5) {
-					wf_cell_t *p = cells + ((int64_t)a5 * 17 + nhs) * W;
-					for (int32_t d = olo + lane; d <= ohi && d < lo; d += MGB_W) p[(d + (1 << 20)) & mask] = (wf_cell_t)WF_NEG_INF16;
-					for (int32_t d = (hi + 1 > olo? hi + 1 : olo) + lane; d <= ohi; d += MGB_W) p[(d + (1 << 20)) & mask] = (wf_cell_t)WF_NEG_INF16;
-				}
-			}
-		}
+		// the slots of score ns held scores ns-17 (H), ns-3 (E1/F1) and ns-2 (E2/F2): after a band shrink those ranges can reach beyond [lo,hi]
+		const uint32_t g16 = MGB_WF_GGET(nhs), g2 = MGB_WF_GGET(nhs >= 3? nhs - 3 : nhs + 14), g1 = MGB_WF_GGET(nhs >= 2? nhs - 2 : nhs + 15);
+		MGB_WF2_CLEAN(H + (int64_t)nhs * W, g16);
+		MGB_WF2_CLEAN(E1 + (int64_t)n3 * W, g2);
+		MGB_WF2_CLEAN(F1 + (int64_t)n3 * W, g2);
+		MGB_WF2_CLEAN(E2 + (int64_t)n2 * W, g1);
+		MGB_WF2_CLEAN(F2 + (int64_t)n2 * W, g1);
 		// byte offsets of the source and destination slices inside their arrays (kept in registers, see wfa_smem)
-		int32_t bHx = r4 * W * 2, bHo1 = r6 * W * 2, bHo2 = r16 * W * 2, bE1 = r2 * W * 2, bE2 = hs * W * 2, bN = nhs * W * 2;
-		MGB_OPAQUE(bHx); MGB_OPAQUE(bHo1); MGB_OPAQUE(bHo2); MGB_OPAQUE(bE1); MGB_OPAQUE(bE2); MGB_OPAQUE(bN);
+		int32_t bHx = r4 * W * 2, bHo1 = r6 * W * 2, bHo2 = r16 * W * 2, bE1 = e1slot * W * 2, bE2 = m2 * W * 2, bnH = nhs * W * 2, bn3 = n3 * W * 2, bn2 = n2 * W * 2;
+		MGB_OPAQUE(bHx); MGB_OPAQUE(bHo1); MGB_OPAQUE(bHo2); MGB_OPAQUE(bE1); MGB_OPAQUE(bE2); MGB_OPAQUE(bnH); MGB_OPAQUE(bn3); MGB_OPAQUE(bn2);
+		const int track = ((ns + 16) & 0xff) <= 16; // one of the 17 wavefronts the next band shrink (at a multiple of 256) looks at
 		uint32_t vote = 0; // 1: window grows on the low side, 2: on the high side, 4: corner reached, 8: ... without extension
-		const int32_t mask2 = 2 * W - 1;
-		for (int32_t d = lo + lane; d <= hi; d += MGB_W) { // reference: miniwfa.c:281-308 wf_next_tb, then :212-226 on the new cell
-			int32_t h, f, e, e1, e2, f1, f2, a0, b0;
-			uint8_t xb = 0, ze, zf, z;
-			const int32_t c2 = ((d + (1 << 20)) & mask) * 2, cm = (c2 - 2) & mask2, cp = (c2 + 2) & mask2; // byte columns
-			a0 = wf2_ld(H, bHo1 + cm), b0 = wf2_ld(E1, bE1 + cm);
-			xb |= a0 >= b0? 0 : 0x08; e1 = MGB_WF_MAX(a0, b0);
-			a0 = wf2_ld(H, bHo2 + cm), b0 = wf2_ld(E2, bE2 + cm);
-			xb |= a0 >= b0? 0 : 0x20; e2 = MGB_WF_MAX(a0, b0);
-			ze = e1 >= e2? 1 : 3;
-			e = MGB_WF_MAX(e1, e2);
-			a0 = wf2_ld(H, bHo1 + cp), b0 = wf2_ld(F1, bE1 + cp);
-			xb |= a0 >= b0? 0 : 0x10; f1 = MGB_WF_MAX(a0, b0) + 1;
-			a0 = wf2_ld(H, bHo2 + cp), b0 = wf2_ld(F2, bE2 + cp);
-			xb |= a0 >= b0? 0 : 0x40; f2 = MGB_WF_MAX(a0, b0) + 1;
-			zf = f1 >= f2? 2 : 4;
-			f = MGB_WF_MAX(f1, f2);
-			z = e >= f? ze : zf;
-			h = MGB_WF_MAX(e, f);
-			a0 = wf2_ld(H, bHx + c2) + 1;
-			z = a0 >= h? 0 : z;
-			h = MGB_WF_MAX(a0, h);
-			ax[d] = xb | z;
-			if (d == lo || d == hi) {
-				if (h >= -1 || e1 >= -1 || f1 >= -1 || e2 >= -1 || f2 >= -1) vote |= (d == lo? 1u : 0u) | (d == hi? 2u : 0u);
-			}
-			if (!(h < -1 || d + h < -1 || h >= tl || d + h >= ql)) {
-				const int32_t k = wf_extend(ts, qs, h, d);
-				if (d == d_corner && k == tl - 1) vote |= 4u | (k == h? 8u : 0u);
-				else h = k;
-			}
-			const int32_t bo = bN + c2;
-			*(wf_cell_t*)((char*)E1 + bo) = (wf_cell_t)e1, *(wf_cell_t*)((char*)F1 + bo) = (wf_cell_t)f1, *(wf_cell_t*)((char*)E2 + bo) = (wf_cell_t)e2, *(wf_cell_t*)((char*)F2 + bo) = (wf_cell_t)f2, *(wf_cell_t*)((char*)H + bo) = (wf_cell_t)h;
+		const int32_t colmask2 = 2 * W - 1;
+		// what wf_stripe_shrink() will ask of a cell (the values as stored)
+#define MGB_WF_TRACK(S, d_) do { if (track && (wf_good_diag((d_), h##S, tl, ql) || wf_good_diag((d_), e1##S, tl, ql) || wf_good_diag((d_), f1##S, tl, ql) || wf_good_diag((d_), e2##S, tl, ql) || wf_good_diag((d_), f2##S, tl, ql))) \
+				*(wf_cell_t*)((char*)G + c##S) = (wf_cell_t)ns; } while (0)
+#if MGB_WF_CELLS == 2
+		for (int32_t d = lo + lane; d <= hi; d += 2 * MGB_W) {
+			const int32_t dB = d + MGB_W <= hi? d + MGB_W : d;
+			MGB_WF_CELL_LOAD(A, d)
+			MGB_WF_CELL_LOAD(B, dB)
+			MGB_WF_CELL_FINISH(A, d)
+			MGB_WF_TRACK(A, d);
+			if (dB != d) { MGB_WF_CELL_FINISH(B, dB) MGB_WF_TRACK(B, dB); }
 		}
+#else
+		for (int32_t d = lo + lane; d <= hi; d += MGB_W) {
+			MGB_WF_CELL_LOAD(A, d)
+			MGB_WF_CELL_FINISH(A, d)
+			MGB_WF_TRACK(A, d);
+		}
+#endif
+#undef MGB_WF_TRACK
 		vote = warp_or_u32(vote);
 		if (vote & 1) wlo = lo;
 		if (vote & 2) whi = hi;
 		hit = vote >> 2 & 1, hit_noext = vote >> 3 & 1;
-		g16 = g15, g15 = g14, g14 = g13, g13 = g12, g12 = g11, g11 = g10, g10 = g9, g9 = g8, g8 = g7, g7 = g6, g6 = g5, g5 = g4, g4 = g3, g3 = g2, g2 = g1, g1 = g0;
-		g0 = MGB_WF_RG(lo, hi);
-		s = ns, hs = nhs;
+		MGB_WF_GSET(nhs, MGB_WF_RG(lo, hi));
+		s = ns, hs = nhs, m3 = n3, m2 = n2;
 		warp_sync();
 		if ((s & 0xff) == 0) { // reference: miniwfa.c:144-171 wf_stripe_shrink: keep the diagonals on which one of the 17 wavefronts still has a cell inside the matrix
-			const uint32_t gg[17] = { g0, g1, g2, g3, g4, g5, g6, g7, g8, g9, g10, g11, g12, g13, g14, g15, g16 };
 			int32_t nlo = 0, nhi = 0, found = 0;
 			for (int pass = 0; pass < 2; ++pass) {
 				found = 0;
 				for (int32_t base = pass == 0? wlo : whi; pass == 0? base <= whi : base >= wlo; base += pass == 0? MGB_W : -MGB_W) {
 					const int32_t d = pass == 0? base + lane : base - lane;
 					int good = 0;
-					if (d >= wlo && d <= whi) {
-						const int32_t c = (d + (1 << 20)) & mask;
-						for (int j = 0; j < 17 && !good; ++j) {
-							const int32_t jl = (int32_t)(gg[j] & 0xffffu) - 0x8000, jh = (int32_t)(gg[j] >> 16) - 0x8000;
-							if (d < jl || d > jh) continue;
-							const int slot = hs >= j? hs - j : hs - j + 17;
-							const int64_t o = (int64_t)slot * W + c;
-							good = wf_good_diag(d, H[o], tl, ql) || wf_good_diag(d, E1[o], tl, ql) || wf_good_diag(d, F1[o], tl, ql) || wf_good_diag(d, E2[o], tl, ql) || wf_good_diag(d, F2[o], tl, ql);
-						}
-					}
+					if (d >= wlo && d <= whi) good = G[(d + (1 << 20)) & mask] >= s - 16; // noted by one of the wavefronts s-16 .. s
 					const uint32_t m = warp_ballot(good);
 					if (m) { found = 1; if (pass == 0) nlo = base + ctz32(m); else nhi = base - ctz32(m); break; }
 				}
@@ -352,6 +384,8 @@ MG_HD inline int wfa_ring_g(Arena &A, int32_t tl, const char *ts, int32_t ql, co
 		if (max_iter > 0 && n_iter > max_iter) { stopped = 1; break; }
 	}
 #undef MGB_WF_RG
+#undef MGB_WF_GGET
+#undef MGB_WF_GSET
 	r->n_iter = n_iter;
 	r->s = stopped? -1 : s;
 	if (!stopped) {
@@ -370,6 +404,7 @@ MG_HD inline int wfa_ring_g(Arena &A, int32_t tl, const char *ts, int32_t ql, co
 	A.top = mark;
 	return 0;
 }
+#undef MGB_WF2_CLEAN
 #undef MGB_WF2_FILL
 
 
