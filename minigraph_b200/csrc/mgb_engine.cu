@@ -55,7 +55,10 @@ static int64_t p_lab_cache = 1;        // 0: graph chaining searches its walks p
 #ifndef MGB_BIG_MINB
 #define MGB_BIG_MINB 6 // blocks of k_wfa_big per SM (its register budget follows: 80 at 6, 128 at 4)
 #endif
-static int STAGE_MINB[20] = { 8, 2, 8, 8, 5, 8, 7, MGB_BIG_MINB, 4, 4, 0, 0, 0, 0, 0, 0, 0, 8, 8, 2 }; // indexed by stage number (10-16 unused)
+#ifndef MGB_GWFA_MINB
+#define MGB_GWFA_MINB 4
+#endif
+static int STAGE_MINB[20] = { 8, 2, 8, 8, 5, 8, 7, MGB_BIG_MINB, MGB_GWFA_MINB, 4, 0, 0, 0, 0, 0, 0, 0, 8, 8, 2 }; // indexed by stage number (10-16 unused)
 static int STAGE_WARPS[20] = { 4, 7, 4, 4, 4, 4, 2, 4, 4, 4, 0, 0, 0, 0, 0, 0, 0, 4, 4, 6 }; // k_chain: 2 x 7 slices of 16 KB per SM, k_chain_rescue: 2 x 6 of 18 KB
 extern "C" const char *mgb_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char *mgb_version(void) { return "mgb200-r1"; }
@@ -309,7 +312,10 @@ MGB_KERNEL(k_seed, 0, 8)          // K1-K3: sketch, index lookup, seed sort
 MGB_KERNEL_T(k_chain, 1, 224, 2)         // K4/K5: linear chaining on chip (seeds bulk-loaded into shared memory)
 MGB_KERNEL_T(k_chain_rescue, 19, 192, 2) // K5: long-join rescue (RMQ chaining) of the reads k_chain listed
 MGB_KERNEL(k_gchain, 2, 8)        // K6: graph chaining DP + k-shortest walks, overlap resolution, bridging plan
-MGB_KERNEL(k_gwfa, 8, 4)          // K7a: bridging alignments (graph wavefront), one warp per bridge
+#ifndef MGB_GWFA_MINB
+#define MGB_GWFA_MINB 4
+#endif
+MGB_KERNEL(k_gwfa, 8, MGB_GWFA_MINB)          // K7a: bridging alignments (graph wavefront), one warp per bridge
 MGB_KERNEL(k_gchain_gen, 9, 4)    // K7b: graph-chain materialisation, post filters, mapq, alignment plan
 MGB_KERNEL(k_index_sketch, 3, 8)  // index build: sketch of graph segments
 MGB_KERNEL(k_wfa_small, 4, 5)     // K8a tier 1: small gaps, wavefronts + traceback bytes in shared memory

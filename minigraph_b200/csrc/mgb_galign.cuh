@@ -527,8 +527,14 @@ MG_HD inline int stage_gchain(const PipeCtx &c, ReadOut *routs, int rid, Arena &
 // K7a: one bridging alignment (reference: gchain1.c:349-381).  The wavefront containers of a typical bridge (tens of
 // diagonals) fit a small per-warp arena in SHARED memory, which removes the global-memory latency from the sequential
 // control flow; a bridge that outgrows it is redone with the worker's arena in HBM.  Lane 0 runs the alignment.
-static const int GWFA_SMEM_ARENA = 12 * 1024;
-static const int GWFA_SMEM_MAX_QL = 96;
+#ifndef MGB_GWFA_SMEM_KB
+#define MGB_GWFA_SMEM_KB 12
+#endif
+#ifndef MGB_GWFA_SMEM_QL
+#define MGB_GWFA_SMEM_QL 96
+#endif
+static const int GWFA_SMEM_ARENA = MGB_GWFA_SMEM_KB * 1024;
+static const int GWFA_SMEM_MAX_QL = MGB_GWFA_SMEM_QL;
 
 MG_HD inline int gwfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int lane, int32_t *smem)
 {
@@ -536,6 +542,7 @@ MG_HD inline int gwfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int l
 	if (J->rid < 0) return 0;
 	if (c.meta[J->rid].status < 0) return 0;
 	GwfShared *sh = (GwfShared*)smem; // the one copy of the alignment state, seen by all lanes
+	static_assert(sizeof(GwfShared) + 16 <= GWFA_SMEM_ARENA, "the alignment state has to fit the warp's slice of shared memory");
 	const uint64_t sh_bytes = (sizeof(GwfShared) + 15) & ~(uint64_t)15;
 	GwfOpt opt;
 	opt.traceback = 1, opt.max_chk = 1000, opt.bw_dyn = 1000, opt.max_lag = J->max_ed / 2, opt.s_term = -1;

@@ -918,6 +918,16 @@ MG_HD inline int gwf_align_w(GwfShared *sh, const GraphDev &g, const GwfOpt &opt
 		rc = u64tab_init(A, z.ha, 6);
 		if (rc == 0) rc = u64tab_init(A, z.ht, 6);
 		if (rc == 0) rc = avec_reserve_c(A, z.t, 16);
+		if (rc == 0 && A.cap >= (1u << 16)) { // in the worker's arena: room for a typical wavefront up front (growth abandons the old block and copies on one lane)
+			rc = avec_reserve_c(A, z.a, 96);
+			if (rc == 0) rc = avec_reserve_c(A, z.B, 192);
+			if (rc == 0) rc = avec_reserve_c(A, z.ooo, 192);
+			if (rc == 0) rc = avec_reserve_c(A, z.Q, 96);
+			if (rc == 0) rc = avec_reserve_c(A, z.tmp, 64);
+			if (rc == 0) rc = avec_reserve_c(A, z.intv, 64);
+			if (rc == 0) rc = avec_reserve_c(A, z.swap, 64);
+			if (rc == 0) rc = avec_reserve_c(A, z.t, 64);
+		}
 		if (rc == 0) {
 			GwfDiag d0;
 			d0.vd = gwf_gen_vd(v0, -off0), d0.k = off0 - 1, d0.xo = 0, d0.len = 0, d0.t = 0;

@@ -41,7 +41,10 @@ MG_HD inline int32_t wf2_ld(const void *base, int32_t off)
 // wavefront is computed, so the FINISH of one cell may follow the LOAD of the next.  Expected in scope: H E1 F1 E2 F2 (arrays),
 // bHx bHo1 bHo2 bE1 bE2 bnH bn3 bn2 (byte offsets of the slices), colmask2 (2W-1), ax, lo, hi, tl, ql, ts, qs, d_corner, vote.
 #ifndef MGB_WF_CELLS
-#define MGB_WF_CELLS 1
+#define MGB_WF_CELLS 1 // tiers 1/2 (shared memory): two cells in flight measured slower (k_wfa_mid 103.9 -> 114.1 ms per 40 000 reads)
+#endif
+#ifndef MGB_WF_CELLS3
+#define MGB_WF_CELLS3 2 // tier 3 (ring in L2): faster (k_wfa_big 108.5 -> 82.2 ms at 16 warps per SM)
 #endif
 #define MGB_WF_CELL_LOAD(S, d_) \
 	int32_t h##S, e1##S, e2##S, f1##S, f2##S; \
@@ -340,7 +343,7 @@ MG_HD inline int wfa_ring_g(Arena &A, int32_t tl, const char *ts, int32_t ql, co
 		// what wf_stripe_shrink() will ask of a cell (the values as stored)
 #define MGB_WF_TRACK(S, d_) do { if (track && (wf_good_diag((d_), h##S, tl, ql) || wf_good_diag((d_), e1##S, tl, ql) || wf_good_diag((d_), f1##S, tl, ql) || wf_good_diag((d_), e2##S, tl, ql) || wf_good_diag((d_), f2##S, tl, ql))) \
 				*(wf_cell_t*)((char*)G + c##S) = (wf_cell_t)ns; } while (0)
-#if MGB_WF_CELLS == 2
+#if MGB_WF_CELLS3 == 2
 		for (int32_t d = lo + lane; d <= hi; d += 2 * MGB_W) {
 			const int32_t dB = d + MGB_W <= hi? d + MGB_W : d;
 			MGB_WF_CELL_LOAD(A, d)

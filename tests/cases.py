@@ -302,6 +302,56 @@ def case_wfa_divergent(lib, n_cases=24, seed=5):
         assert nc >= 0 and [buf[i] for i in range(nc)] == want and score.value == rst.s, (it, tl, ql, score.value, rst.s)
 
 
+def case_wfa_band_shrinks(lib, n_cases=48, seed=99):
+    """tier 3 far past score 256: unrelated pairs, noisy copies with a long indel, shared cores between random flanks, low-complexity
+    pairs.  The ring keeps 17 H slots but only 3 / 2 slots of E/F; what the band shrink (miniwfa.c:144-171) wants to know about the
+    last 17 wavefronts comes from the last-good-score slice.  Same CIGAR and score as the reference's mwf_wfa_exact()."""
+    import ctypes as C
+    import random
+    ref = T.load_ref()
+    mwf_opt_t, mwf_rst_t = _mwf_types()
+    rng = random.Random(seed)
+    n_shrunk = 0
+    for it in range(n_cases):
+        tl = rng.choice([200, 400, 700, 1200, 2000])
+        ql = max(30, int(tl * rng.choice([0.2, 0.5, 0.8, 1.0, 1.3, 2.0])))
+        t = "".join(rng.choice("ACGT") for _ in range(tl))
+        mode = it % 4
+        if mode == 0:
+            q = "".join(rng.choice("ACGT") for _ in range(ql))
+        elif mode == 1:
+            q = "".join(c if rng.random() > 0.25 else rng.choice("ACGT") for c in t)
+            cut = rng.randrange(len(q))
+            q = q[:cut] + q[cut + rng.choice([50, 150, 400]):]
+        elif mode == 2:
+            q = "".join(rng.choice("ACGT") for _ in range(ql))
+            for _ in range(3):
+                core = "".join(rng.choice("ACGT") for _ in range(rng.choice([30, 80])))
+                i, j = rng.randrange(len(t)), rng.randrange(len(q))
+                t, q = t[:i] + core + t[i:], q[:j] + core + q[j:]
+        else:
+            q = "".join(rng.choice("AC") for _ in range(ql))
+            t = "".join(rng.choice("AC") if rng.random() < 0.7 else rng.choice("GT") for _ in range(tl))
+        if not q:
+            continue
+        ts, qs = t.encode(), q.encode()
+        opt = mwf_opt_t()
+        ref.mwf_opt_init(C.byref(opt))
+        opt.flag |= 1
+        opt.step, opt.max_iter = 0, 10 ** 8
+        rst = mwf_rst_t()
+        ref.mwf_wfa_exact(None, C.byref(opt), len(ts), ts, len(qs), qs, C.byref(rst))
+        assert rst.s >= 0
+        n_shrunk += rst.s >= 256
+        want = [rst.cigar[i] for i in range(rst.n_cigar)]
+        cap = len(ts) + len(qs) + 8
+        buf = (C.c_uint32 * cap)()
+        score = C.c_int(0)
+        nc = lib.mgb_test_wfa(ts, len(ts), qs, len(qs), 10 ** 8, 5000, buf, cap, C.byref(score))
+        assert nc >= 0 and [buf[i] for i in range(nc)] == want and score.value == rst.s, (it, len(ts), len(qs), score.value, rst.s, nc)
+    assert n_shrunk >= n_cases // 2
+
+
 def case_wfa_tiers(lib, workdir, n_struct=60):
     """the gap alignment tiers (mgb_wfa_tiers.cuh: slices that hold -inf outside their range instead of bounds checks).  Same GAF
     for the golden cases (lr and asm presets, both on-chip tiers busy), same mg_gchains_t fields as the reference on an SV graph,
@@ -318,6 +368,7 @@ def case_wfa_tiers(lib, workdir, n_struct=60):
         case_short_reads(lib, workdir, n_pairs=20)  # sr preset: tier 1 only, two-segment fragments
         case_wfa_fallback(lib)  # tier 3 against miniwfa: scores far past 256 (band re-centring), capped runs, a gap beyond the 16-bit ring
         case_wfa_divergent(lib)
+        case_wfa_band_shrinks(lib)
 
 
 def case_gchain_labels(lib, workdir, n_reads=150, graph_len=1000000):

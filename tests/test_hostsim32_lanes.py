@@ -77,3 +77,4 @@ def test_graph_chaining_label_table(lib, workdir):
 
 def test_wfa_tiers_and_fallback(lib):
     cases.case_wfa_fallback(lib)
+    cases.case_wfa_band_shrinks(lib)

@@ -102,6 +102,7 @@ def test_gap_alignment_tiers(lib, workdir):
 def test_wfa_iteration_cap_fallback(lib):
     cases.case_wfa_fallback(lib)
     cases.case_wfa_divergent(lib)
+    cases.case_wfa_band_shrinks(lib)
 
 
 @pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not built")
