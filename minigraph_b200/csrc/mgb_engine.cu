@@ -53,7 +53,7 @@ static int64_t p_lab_cache = 1;        // 0: graph chaining searches its walks p
 
 // launch shape per stage: warps per block and blocks per SM wanted (tunable for experiments: "sw<stage>", "mb<stage>")
 #ifndef MGB_BIG_MINB
-#define MGB_BIG_MINB 6 // blocks of k_wfa_big per SM (its register budget follows: 80 at 6, 128 at 4)
+#define MGB_BIG_MINB 4 // blocks of k_wfa_big per SM (its register budget follows: 80 at 6, 96 at 5, 128 at 4)
 #endif
 #ifndef MGB_GWFA_MINB
 #define MGB_GWFA_MINB 4

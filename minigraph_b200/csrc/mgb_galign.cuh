@@ -528,10 +528,10 @@ MG_HD inline int stage_gchain(const PipeCtx &c, ReadOut *routs, int rid, Arena &
 // diagonals) fit a small per-warp arena in SHARED memory, which removes the global-memory latency from the sequential
 // control flow; a bridge that outgrows it is redone with the worker's arena in HBM.  Lane 0 runs the alignment.
 #ifndef MGB_GWFA_SMEM_KB
-#define MGB_GWFA_SMEM_KB 12
+#define MGB_GWFA_SMEM_KB 1
 #endif
 #ifndef MGB_GWFA_SMEM_QL
-#define MGB_GWFA_SMEM_QL 96
+#define MGB_GWFA_SMEM_QL 0
 #endif
 static const int GWFA_SMEM_ARENA = MGB_GWFA_SMEM_KB * 1024;
 static const int GWFA_SMEM_MAX_QL = MGB_GWFA_SMEM_QL;
