@@ -312,15 +312,12 @@ MGB_KERNEL(k_seed, 0, 8)          // K1-K3: sketch, index lookup, seed sort
 MGB_KERNEL_T(k_chain, 1, 224, 2)         // K4/K5: linear chaining on chip (seeds bulk-loaded into shared memory)
 MGB_KERNEL_T(k_chain_rescue, 19, 192, 2) // K5: long-join rescue (RMQ chaining) of the reads k_chain listed
 MGB_KERNEL(k_gchain, 2, 8)        // K6: graph chaining DP + k-shortest walks, overlap resolution, bridging plan
-#ifndef MGB_GWFA_MINB
-#define MGB_GWFA_MINB 4
-#endif
 MGB_KERNEL(k_gwfa, 8, MGB_GWFA_MINB)          // K7a: bridging alignments (graph wavefront), one warp per bridge
 MGB_KERNEL(k_gchain_gen, 9, 4)    // K7b: graph-chain materialisation, post filters, mapq, alignment plan
 MGB_KERNEL(k_index_sketch, 3, 8)  // index build: sketch of graph segments
 MGB_KERNEL(k_wfa_small, 4, 5)     // K8a tier 1: small gaps, wavefronts + traceback bytes in shared memory
 MGB_KERNEL(k_wfa_mid, 6, 5)       // K8a tier 2: mid-size gaps, wavefronts in shared memory (blocks of 2 warps)
-MGB_KERNEL(k_wfa_big, 7, MGB_BIG_MINB) // K8a tier 3: anything else, wavefronts in the worker arena (80 registers: 24 warps per SM)
+MGB_KERNEL(k_wfa_big, 7, MGB_BIG_MINB) // K8a tier 3: anything else, wavefronts in the worker arena
 MGB_KERNEL(k_finish, 5, 8)        // K8b: CIGAR stitching, ds strings, result blobs
 MGB_KERNEL(k_gc_labels, 17, 8)    // reachability labels of new source vertices, one search per thread (mgb_gclabel.cuh)
 MGB_KERNEL(k_gc_labels_big, 18, 8) // the few sources whose search outgrew a thread's share of the arena: one per warp

@@ -35,21 +35,16 @@ MG_HD inline int32_t wf2_ld(const void *base, int32_t off)
 	return v;
 }
 
-// ---- one cell of a wavefront, in two halves so that two cells can be in flight per lane (MGB_WF_CELLS = 2) ----
+// ---- one cell of a wavefront, in two halves so that two cells can be in flight per lane ----
 // LOAD: the nine neighbour reads and the recurrence (reference: miniwfa.c:281-308 wf_next_tb); FINISH: traceback byte, window
 // votes, extension along exact matches (miniwfa.c:212-226) and the five stores.  The slots of score ns are not read while a
 // wavefront is computed, so the FINISH of one cell may follow the LOAD of the next.  Expected in scope: H E1 F1 E2 F2 (arrays),
 // bHx bHo1 bHo2 bE1 bE2 bnH bn3 bn2 (byte offsets of the slices), colmask2 (2W-1), ax, lo, hi, tl, ql, ts, qs, d_corner, vote.
-// How a lane walks a wavefront: 1 = one cell at a time, 2 = two cells (32 diagonals apart) in flight, 3 = two adjacent cells packed.
-#ifndef MGB_WF_MODE1
-#define MGB_WF_MODE1 1 // tier 1 (shared memory, windows of at most 62 diagonals)
-#endif
-#ifndef MGB_WF_MODE2
-#define MGB_WF_MODE2 1 // tier 2 (shared memory): two cells in flight measured slower than one (k_wfa_mid 103.9 -> 114.1 ms per 40 000 reads)
-#endif
-#ifndef MGB_WF_MODE3
-#define MGB_WF_MODE3 2 // tier 3 (ring in L2): faster (k_wfa_big 108.5 -> 82.2 ms at 16 warps per SM)
-#endif
+// Measured on B200 (round 2, config 3, ms per 40 000 reads): tiers 1/2 (ring in shared memory) walk a wavefront one cell per lane at a
+// time -- two cells in flight were slower (k_wfa_mid 103.9 -> 114.1), and so was a packed walk of two adjacent diagonals per lane
+// (word loads, VIMNMX.S16x2 maxima whose predicates are the traceback bits: 103.2 -> 115.7; per pair it executes as many instructions
+// as two cells, on half the lanes); tier 3 (ring in L2) keeps two cells in flight: eighteen loads before the first use
+// (k_wfa_big 108.5 -> 82.2 at 16 warps per SM; 86.5 at 20 warps / 96 registers, 102.4 at 24 / 80 with spills).
 #define MGB_WF_CELL_LOAD(S, d_) \
 	int32_t h##S, e1##S, e2##S, f1##S, f2##S; \
 	uint8_t xz##S; \
@@ -92,103 +87,6 @@ MG_HD inline int32_t wf2_ld(const void *base, int32_t off)
 		*(wf_cell_t*)((char*)E1 + bn3 + c##S) = (wf_cell_t)e1##S, *(wf_cell_t*)((char*)F1 + bn3 + c##S) = (wf_cell_t)f1##S; \
 		*(wf_cell_t*)((char*)E2 + bn2 + c##S) = (wf_cell_t)e2##S, *(wf_cell_t*)((char*)F2 + bn2 + c##S) = (wf_cell_t)f2##S; \
 		*(wf_cell_t*)((char*)H + bnH + c##S) = (wf_cell_t)h##S; \
-	}
-
-// ---- two ADJACENT diagonals per lane, packed: the cells of diagonals 2q and 2q+1 are the halves of one 32-bit word of a slice ----
-// Fifteen word loads fetch what eighteen 16-bit loads fetch for two cells; the neighbours on the low side (2q-1, 2q) and on the high
-// side (2q+1, 2q+2) are cut out of two words with one byte permutation each; the eight maxima of the recurrence run on both cells at
-// once (VIMNMX.S16x2, which also returns the two "first operand wins" predicates the traceback bits are made of); the +1 of the F
-// and mismatch terms is one VIADD.16x2.  Per cell that is about half the instructions of the scalar form.  The half of a pair that
-// lies outside [lo,hi] is computed like the other and stored as -inf (what a slice holds outside its range), its traceback byte is
-// not stored.  Rows of traceback bytes start at an address of lo's parity, so that the two bytes of a pair are one 16-bit store.
-MG_HD inline uint32_t wf_ldw(const void *base, int32_t off) { return *(const uint32_t*)((const char*)base + off); }
-MG_HD inline uint32_t wf_cut(uint32_t lo_word, uint32_t hi_word) // halves (hi of lo_word, lo of hi_word)
-{
-#if MGB_ON_DEVICE
-	return __byte_perm(lo_word, hi_word, 0x5432);
-#else
-	return lo_word >> 16 | hi_word << 16;
-#endif
-}
-MG_HD inline uint32_t wf_max2(uint32_t a, uint32_t b, bool *a_wins_hi, bool *a_wins_lo) // per-half signed maximum and (a >= b)
-{
-#if MGB_ON_DEVICE
-	return __vibmax_s16x2(a, b, a_wins_hi, a_wins_lo);
-#else
-	const int16_t al = (int16_t)(a & 0xffffu), ah = (int16_t)(a >> 16), bl = (int16_t)(b & 0xffffu), bh = (int16_t)(b >> 16);
-	*a_wins_lo = al >= bl, *a_wins_hi = ah >= bh;
-	return (uint32_t)(uint16_t)(al >= bl? al : bl) | (uint32_t)(uint16_t)(ah >= bh? ah : bh) << 16;
-#endif
-}
-MG_HD inline uint32_t wf_inc2(uint32_t a) // +1 on both halves
-{
-#if MGB_ON_DEVICE
-	return __vadd2(a, 0x00010001u);
-#else
-	return ((a + 1u) & 0xffffu) | ((a + 0x10000u) & 0xffff0000u);
-#endif
-}
-MG_HD inline uint32_t wf_tb_byte(bool pe1, bool pe2, bool pf1, bool pf2, bool pze, bool pzf, bool pz, bool pa)
-{
-	const uint32_t x = (pe1? 0u : 0x08u) | (pe2? 0u : 0x20u) | (pf1? 0u : 0x10u) | (pf2? 0u : 0x40u);
-	const uint32_t ze = pze? 1u : 3u, zf = pzf? 2u : 4u;
-	return x | (pa? 0u : pz? ze : zf);
-}
-#define MGB_WF_PAIR_LOAD(S, q_) \
-	const int32_t d0##S = (q_) * 2; \
-	const int32_t c##S = ((d0##S + (1 << 20)) * 2) & colmask2; /* byte column of the pair, a multiple of four */ \
-	uint32_t hw##S, e1w##S, e2w##S, f1w##S, f2w##S, tb##S; \
-	{ \
-		const int32_t cm_ = (c##S - 4) & colmask2, cp_ = (c##S + 4) & colmask2; \
-		const uint32_t ho1m_ = wf_ldw(H, bHo1 + cm_), ho1c_ = wf_ldw(H, bHo1 + c##S), ho1p_ = wf_ldw(H, bHo1 + cp_); \
-		const uint32_t ho2m_ = wf_ldw(H, bHo2 + cm_), ho2c_ = wf_ldw(H, bHo2 + c##S), ho2p_ = wf_ldw(H, bHo2 + cp_); \
-		const uint32_t e1m_ = wf_ldw(E1, bE1 + cm_), e1c_ = wf_ldw(E1, bE1 + c##S), e2m_ = wf_ldw(E2, bE2 + cm_), e2c_ = wf_ldw(E2, bE2 + c##S); \
-		const uint32_t f1c_ = wf_ldw(F1, bE1 + c##S), f1p_ = wf_ldw(F1, bE1 + cp_), f2c_ = wf_ldw(F2, bE2 + c##S), f2p_ = wf_ldw(F2, bE2 + cp_); \
-		const uint32_t hx_ = wf_ldw(H, bHx + c##S); \
-		bool pe1h_, pe1l_, pe2h_, pe2l_, pf1h_, pf1l_, pf2h_, pf2l_, pzeh_, pzel_, pzfh_, pzfl_, pzh_, pzl_, pah_, pal_; \
-		e1w##S = wf_max2(wf_cut(ho1m_, ho1c_), wf_cut(e1m_, e1c_), &pe1h_, &pe1l_); \
-		e2w##S = wf_max2(wf_cut(ho2m_, ho2c_), wf_cut(e2m_, e2c_), &pe2h_, &pe2l_); \
-		f1w##S = wf_inc2(wf_max2(wf_cut(ho1c_, ho1p_), wf_cut(f1c_, f1p_), &pf1h_, &pf1l_)); \
-		f2w##S = wf_inc2(wf_max2(wf_cut(ho2c_, ho2p_), wf_cut(f2c_, f2p_), &pf2h_, &pf2l_)); \
-		const uint32_t ew_ = wf_max2(e1w##S, e2w##S, &pzeh_, &pzel_), fw_ = wf_max2(f1w##S, f2w##S, &pzfh_, &pzfl_); \
-		hw##S = wf_max2(ew_, fw_, &pzh_, &pzl_); \
-		hw##S = wf_max2(wf_inc2(hx_), hw##S, &pah_, &pal_); \
-		tb##S = wf_tb_byte(pe1l_, pe2l_, pf1l_, pf2l_, pzel_, pzfl_, pzl_, pal_) | wf_tb_byte(pe1h_, pe2h_, pf1h_, pf2h_, pzeh_, pzfh_, pzh_, pah_) << 8; \
-	}
-#define MGB_WF_HALF_LO(w_) ((int32_t)(int16_t)((w_) & 0xffffu))
-#define MGB_WF_HALF_HI(w_) ((int32_t)(w_) >> 16)
-#define MGB_WF_PAIR_FINISH(S) \
-	const int32_t dA##S = d0##S, dB##S = d0##S + 1; \
-	const bool vA##S = dA##S >= lo, vB##S = dB##S <= hi; \
-	int32_t hA##S = MGB_WF_HALF_LO(hw##S), hB##S = MGB_WF_HALF_HI(hw##S); \
-	{ \
-		if (vA##S && vB##S) *(uint16_t*)(ax + dA##S) = (uint16_t)tb##S; \
-		else if (vA##S) ax[dA##S] = (uint8_t)tb##S; \
-		else ax[dB##S] = (uint8_t)(tb##S >> 8); \
-		if (dA##S == lo || dA##S == hi || dB##S == lo || dB##S == hi) { /* does the window still grow on this side? */ \
-			if ((dA##S == lo || dA##S == hi) && (hA##S >= -1 || MGB_WF_HALF_LO(e1w##S) >= -1 || MGB_WF_HALF_LO(f1w##S) >= -1 || MGB_WF_HALF_LO(e2w##S) >= -1 || MGB_WF_HALF_LO(f2w##S) >= -1)) \
-				vote |= (dA##S == lo? 1u : 0u) | (dA##S == hi? 2u : 0u); \
-			if ((dB##S == lo || dB##S == hi) && (hB##S >= -1 || MGB_WF_HALF_HI(e1w##S) >= -1 || MGB_WF_HALF_HI(f1w##S) >= -1 || MGB_WF_HALF_HI(e2w##S) >= -1 || MGB_WF_HALF_HI(f2w##S) >= -1)) \
-				vote |= (dB##S == lo? 1u : 0u) | (dB##S == hi? 2u : 0u); \
-		} \
-		if (vA##S && !(hA##S < -1 || dA##S + hA##S < -1 || hA##S >= tl || dA##S + hA##S >= ql)) { /* extend the new cells right away */ \
-			const int32_t k_ = wf_extend(ts, qs, hA##S, dA##S); \
-			if (dA##S == d_corner && k_ == tl - 1) vote |= 4u | (k_ == hA##S? 8u : 0u); \
-			else hA##S = k_; \
-		} \
-		if (vB##S && !(hB##S < -1 || dB##S + hB##S < -1 || hB##S >= tl || dB##S + hB##S >= ql)) { \
-			const int32_t k_ = wf_extend(ts, qs, hB##S, dB##S); \
-			if (dB##S == d_corner && k_ == tl - 1) vote |= 4u | (k_ == hB##S? 8u : 0u); \
-			else hB##S = k_; \
-		} \
-		hw##S = ((uint32_t)hA##S & 0xffffu) | (uint32_t)hB##S << 16; \
-		if (!(vA##S && vB##S)) { /* the half outside [lo,hi] stays -inf */ \
-			const uint32_t keep_ = vA##S? 0x0000ffffu : 0xffff0000u, inf_ = ((uint32_t)(uint16_t)(wf_cell_t)WF_NEG_INF16 * 0x10001u) & ~keep_; \
-			hw##S = (hw##S & keep_) | inf_, e1w##S = (e1w##S & keep_) | inf_, f1w##S = (f1w##S & keep_) | inf_, e2w##S = (e2w##S & keep_) | inf_, f2w##S = (f2w##S & keep_) | inf_; \
-		} \
-		*(uint32_t*)((char*)E1 + bn3 + c##S) = e1w##S, *(uint32_t*)((char*)F1 + bn3 + c##S) = f1w##S; \
-		*(uint32_t*)((char*)E2 + bn2 + c##S) = e2w##S, *(uint32_t*)((char*)F2 + bn2 + c##S) = f2w##S; \
-		*(uint32_t*)((char*)H + bnH + c##S) = hw##S; \
 	}
 
 template<int W, int MAXLEN, int TBCAP>
@@ -253,19 +151,17 @@ MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g,
 		const int32_t lo = wlo > -tl? wlo - 1 : -tl;
 		const int32_t hi = whi < ql? whi + 1 : ql;
 		const int32_t width = hi - lo + 1;
-		if (width + 2 > W || s + 1 >= 255 || (TBCAP > 0 && tb_used + width + 1 > TBCAP)) { A.top = mark; return 1; }
+		if (width + 2 > W || s + 1 >= 255 || (TBCAP > 0 && tb_used + width > TBCAP)) { A.top = mark; return 1; }
 		const int32_t ns = s + 1;
 		const int nhs = hs + 1 == 17? 0 : hs + 1, n3 = m3 + 1 == 3? 0 : m3 + 1, n2 = m2 ^ 1;
 		uint8_t *ax;
 		if (TBCAP > 0) {
-			const int32_t off = tb_used + ((tb_used ^ lo) & 1); // an even diagonal at an even address (see MGB_WF_PAIR_FINISH)
-			if (lane == 0) tb_row[2 * n_rows] = lo, tb_row[2 * n_rows + 1] = off;
-			ax = tb_x + off - lo;
-			tb_used = off + width;
+			if (lane == 0) tb_row[2 * n_rows] = lo, tb_row[2 * n_rows + 1] = tb_used;
+			ax = tb_x + tb_used - lo;
+			tb_used += width;
 		} else {
 			uint8_t *x;
-			MGB_ALLOC(A, x, uint8_t, width + 1);
-			x += lo & 1; // an even diagonal at an even address (the two bytes of a packed pair are one store)
+			MGB_ALLOC(A, x, uint8_t, width);
 			if (lane == 0) rows.a[n_rows].lo = lo, rows.a[n_rows].hi = hi, rows.a[n_rows].x = x;
 			rows.n = n_rows + 1;
 			ax = x - lo;
@@ -281,25 +177,9 @@ MG_HD inline int wfa_smem(Arena &A, int32_t *smem, int32_t tl, const char *ts_g,
 		MGB_OPAQUE(bHx); MGB_OPAQUE(bHo1); MGB_OPAQUE(bHo2); MGB_OPAQUE(bE1); MGB_OPAQUE(bE2); MGB_OPAQUE(bnH); MGB_OPAQUE(bn3); MGB_OPAQUE(bn2);
 		const int32_t colmask2 = 2 * W - 1;
 		uint32_t vote = 0; // 1: window grows on the low side, 2: on the high side, 4: corner reached, 8: ... without extension
-		const int mode = TBCAP > 0? MGB_WF_MODE1 : MGB_WF_MODE2;
-		if (mode == 3) {
-			for (int32_t q = (lo >> 1) + lane; q <= hi >> 1; q += MGB_W) {
-				MGB_WF_PAIR_LOAD(A, q)
-				MGB_WF_PAIR_FINISH(A)
-			}
-		} else if (mode == 2) {
-			for (int32_t d = lo + lane; d <= hi; d += 2 * MGB_W) { // two cells per lane in flight: eighteen loads before the first use
-				const int32_t dB = d + MGB_W <= hi? d + MGB_W : d;
-				MGB_WF_CELL_LOAD(A, d)
-				MGB_WF_CELL_LOAD(B, dB)
-				MGB_WF_CELL_FINISH(A, d)
-				if (dB != d) MGB_WF_CELL_FINISH(B, dB)
-			}
-		} else {
-			for (int32_t d = lo + lane; d <= hi; d += MGB_W) {
-				MGB_WF_CELL_LOAD(A, d)
-				MGB_WF_CELL_FINISH(A, d)
-			}
+		for (int32_t d = lo + lane; d <= hi; d += MGB_W) {
+			MGB_WF_CELL_LOAD(A, d)
+			MGB_WF_CELL_FINISH(A, d)
 		}
 		vote = warp_or_u32(vote);
 		if (vote & 1) wlo = lo;
@@ -428,8 +308,7 @@ MG_HD inline int wfa_ring_g(Arena &A, int32_t tl, const char *ts, int32_t ql, co
 		const int nhs = hs + 1 == 17? 0 : hs + 1, n3 = m3 + 1 == 3? 0 : m3 + 1, n2 = m2 ^ 1;
 		MGB_TRY(avec_reserve_w(A, rows, n_rows + 1, lane));
 		uint8_t *x;
-		MGB_ALLOC(A, x, uint8_t, width + 1);
-		x += lo & 1; // an even diagonal at an even address (see MGB_WF_PAIR_FINISH)
+		MGB_ALLOC(A, x, uint8_t, width);
 		if (lane == 0) rows.a[n_rows].lo = lo, rows.a[n_rows].hi = hi, rows.a[n_rows].x = x;
 		rows.n = ++n_rows;
 		uint8_t *ax = x - lo;
@@ -453,21 +332,7 @@ MG_HD inline int wfa_ring_g(Arena &A, int32_t tl, const char *ts, int32_t ql, co
 		// what wf_stripe_shrink() will ask of a cell (the values as stored)
 #define MGB_WF_TRACK(S, d_) do { if (track && (wf_good_diag((d_), h##S, tl, ql) || wf_good_diag((d_), e1##S, tl, ql) || wf_good_diag((d_), f1##S, tl, ql) || wf_good_diag((d_), e2##S, tl, ql) || wf_good_diag((d_), f2##S, tl, ql))) \
 				*(wf_cell_t*)((char*)G + c##S) = (wf_cell_t)ns; } while (0)
-#if MGB_WF_MODE3 == 3
-		for (int32_t q = (lo >> 1) + lane; q <= hi >> 1; q += MGB_W) {
-			MGB_WF_PAIR_LOAD(A, q)
-			MGB_WF_PAIR_FINISH(A)
-			if (track) { // (the values as stored: after the extension, -inf outside [lo,hi])
-				const int32_t e1 = MGB_WF_HALF_LO(e1wA), f1 = MGB_WF_HALF_LO(f1wA), e2 = MGB_WF_HALF_LO(e2wA), f2 = MGB_WF_HALF_LO(f2wA), h = MGB_WF_HALF_LO(hwA);
-				if (vAA && (wf_good_diag(dAA, h, tl, ql) || wf_good_diag(dAA, e1, tl, ql) || wf_good_diag(dAA, f1, tl, ql) || wf_good_diag(dAA, e2, tl, ql) || wf_good_diag(dAA, f2, tl, ql)))
-					*(wf_cell_t*)((char*)G + cA) = (wf_cell_t)ns;
-				const int32_t e1b = MGB_WF_HALF_HI(e1wA), f1b = MGB_WF_HALF_HI(f1wA), e2b = MGB_WF_HALF_HI(e2wA), f2b = MGB_WF_HALF_HI(f2wA), hb = MGB_WF_HALF_HI(hwA);
-				if (vBA && (wf_good_diag(dBA, hb, tl, ql) || wf_good_diag(dBA, e1b, tl, ql) || wf_good_diag(dBA, f1b, tl, ql) || wf_good_diag(dBA, e2b, tl, ql) || wf_good_diag(dBA, f2b, tl, ql)))
-					*(wf_cell_t*)((char*)G + cA + 2) = (wf_cell_t)ns;
-			}
-		}
-#elif MGB_WF_MODE3 == 2
-		for (int32_t d = lo + lane; d <= hi; d += 2 * MGB_W) {
+		for (int32_t d = lo + lane; d <= hi; d += 2 * MGB_W) { // two cells per lane in flight
 			const int32_t dB = d + MGB_W <= hi? d + MGB_W : d;
 			MGB_WF_CELL_LOAD(A, d)
 			MGB_WF_CELL_LOAD(B, dB)
@@ -475,13 +340,6 @@ MG_HD inline int wfa_ring_g(Arena &A, int32_t tl, const char *ts, int32_t ql, co
 			MGB_WF_TRACK(A, d);
 			if (dB != d) { MGB_WF_CELL_FINISH(B, dB) MGB_WF_TRACK(B, dB); }
 		}
-#else
-		for (int32_t d = lo + lane; d <= hi; d += MGB_W) {
-			MGB_WF_CELL_LOAD(A, d)
-			MGB_WF_CELL_FINISH(A, d)
-			MGB_WF_TRACK(A, d);
-		}
-#endif
 #undef MGB_WF_TRACK
 		vote = warp_or_u32(vote);
 		if (vote & 1) wlo = lo;
