@@ -261,11 +261,19 @@ __device__ __forceinline__ void stage_loop(const LaunchArgs &L)
 	const int smem_stride = STAGE == 4? WfTier1::STRIDE : STAGE == 6? WfTier2::STRIDE : STAGE == 0? SKETCH_SMEM_BYTES : STAGE == 8? GWFA_SMEM_ARENA : STAGE == 1? CHAIN_SMEM_BYTES : STAGE == 19? CHAIN_RESCUE_SMEM_BYTES : 0;
 	int32_t *smem = smem_stride? (int32_t*)((char*)dyn_smem + (size_t)(threadIdx.x >> 5) * smem_stride) : 0;
 	if (STAGE == 1 || STAGE == 19) chain_smem_init(smem, lane);
+	if ((STAGE == 4 || STAGE == 6) && lane == 0) { unsigned long long *ck = wfa_cig_chunk(smem, STAGE == 4? 1 : 2); ck[0] = ck[1] = 0; } // no slice of the CIGAR pool yet
+	prof_block_begin();
 	const int n_work = L.n_work_dev? (int)*L.n_work_dev : L.n_work;
+	const int grab = STAGE == 4 || STAGE == 6? 4 : 1; // the short jobs of the on-chip WFA tiers are taken four at a time: one contended ticket per four jobs
+	int next_item = 0, have = 0;
 	for (;;) {
-		int item = 0;
-		if (lane == 0) item = (int)atomicAdd(L.c.next_read, 1u);
-		item = __shfl_sync(0xffffffffu, item, 0);
+		if (have == 0) {
+			if (lane == 0) next_item = (int)atomicAdd(L.c.next_read, (unsigned int)grab);
+			next_item = __shfl_sync(0xffffffffu, next_item, 0);
+			have = grab;
+		}
+		int item = next_item++;
+		--have;
 		if (item >= n_work) break;
 		if (L.rid_list) item = L.rid_list[item];
 		if (MGB_IS_WARP(STAGE)) {
@@ -280,6 +288,7 @@ __device__ __forceinline__ void stage_loop(const LaunchArgs &L)
 		__syncwarp();
 	}
 	if (lane == 0 && L.arena_peak) L.arena_peak[worker] = A.peak > L.arena_peak[worker]? A.peak : L.arena_peak[worker];
+	prof_block_end(L.c.prof);
 }
 
 // Thread-per-item variant for the stages whose control flow is sequential: every THREAD pulls its own item and owns
@@ -293,6 +302,7 @@ __device__ __forceinline__ void stage_loop_thread(const LaunchArgs &L)
 	const uint64_t sub = (L.arena_bytes / 32) & ~(uint64_t)15;
 	Arena A;
 	arena_init(A, L.arena_base + (uint64_t)worker * L.arena_bytes + (uint64_t)lane * sub, sub);
+	prof_block_begin();
 	const int n_work = L.n_work_dev? (int)*L.n_work_dev : L.n_work;
 	for (;;) {
 		int item = (int)atomicAdd(L.c.next_read, 1u);
@@ -303,6 +313,7 @@ __device__ __forceinline__ void stage_loop_thread(const LaunchArgs &L)
 		if (rc < 0) stage_fail<STAGE>(L, item, rc);
 	}
 	if (L.arena_peak) atomicMax((unsigned long long*)&L.arena_peak[worker], (unsigned long long)A.peak);
+	prof_block_end(L.c.prof);
 }
 
 // named entry points (one per stage, so that profiles read well); blocks of 4 warps, MINB blocks per SM wanted
@@ -1352,7 +1363,7 @@ static int map_range(Model *M, Model::Slot &sl, const MapOptDev &o, int n_reads,
 	cap[P_OUT] = std::max<uint64_t>((uint64_t)S.n_bases * 4, (uint64_t)1 << 22);
 	cap[P_PLAN] = std::max<uint64_t>((uint64_t)S.n_bases / 8 * 8, (uint64_t)1 << 20);
 	cap[P_JOBS] = std::max<uint64_t>((uint64_t)S.n_bases / 40 * sizeof(WfaJob), (uint64_t)1 << 20);
-	cap[P_CIG] = std::max<uint64_t>((uint64_t)S.n_bases, (uint64_t)1 << 20);
+	cap[P_CIG] = std::max<uint64_t>((uint64_t)S.n_bases, (uint64_t)1 << 20) + (uint64_t)sl.W.n_workers * CIG_CHUNK_BYTES * 4; // + the unused ends of the warps' slices (three tier kernels per pass)
 	cap[P_GSTATE] = std::max<uint64_t>((uint64_t)n_reads * 2048, (uint64_t)1 << 20);
 	cap[P_GJOBS] = std::max<uint64_t>((uint64_t)n_reads * 24 * sizeof(GwfaJob), (uint64_t)1 << 20);
 	cap[P_WALK] = std::max<uint64_t>((uint64_t)n_reads * 256, (uint64_t)1 << 20);

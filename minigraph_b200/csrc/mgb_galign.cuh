@@ -49,6 +49,14 @@ struct WfaJob {
 };
 
 static const uint64_t PLAN_JOB = 1ULL << 63;
+// The state of a warp's slice {next free byte, end} sits in the 96 bytes between the end of the tier's shared-memory layout and its
+// stride (a static array would cost k_wfa_mid its seventh block per SM); tier 3 has no shared memory and few jobs: it asks per gap.
+MG_HD inline unsigned long long *wfa_cig_chunk(int32_t *smem, int tier)
+{
+	static_assert(WfTier1::BYTES % 8 == 0 && WfTier1::BYTES + 16 <= WfTier1::STRIDE && WfTier2::BYTES % 8 == 0 && WfTier2::BYTES + 16 <= WfTier2::STRIDE, "no room for the slice state behind the tier layouts");
+	return smem == 0 || tier > 2? (unsigned long long*)0 : (unsigned long long*)((char*)smem + (tier == 1? WfTier1::BYTES : WfTier2::BYTES));
+}
+static const unsigned long long CIG_CHUNK_BYTES = 2048; // a warp of a WFA kernel takes the CIGAR pool in slices of this size (the host sizes the pool with one slice per worker and kernel to spare)
 
 // Planning pass of mg_gchain_cigar() (reference: galign.c:39-124): walk the kept anchors of every graph chain, emit
 // literal CIGAR items for the trivial gaps (galign.c:98-100) and a WfaJob for the others.
@@ -156,7 +164,23 @@ MG_HD inline int wfa_job_run(Arena &A, const PipeCtx &c, int64_t job_idx, int la
 #endif
 	if (rst.s < 0) return MGB_E_INTERNAL;
 	int64_t coff = 0;
-	if (lane == 0) coff = pool_alloc(c.pool_cig, (uint64_t)rst.n_cigar * 4);
+	if (lane == 0) {
+#if MGB_ON_DEVICE
+		unsigned long long *ck = wfa_cig_chunk(smem, tier); // the warp's slice of the pool
+		const unsigned long long need = ((unsigned long long)rst.n_cigar * 4 + 15) & ~15ULL;
+		if (ck == 0) coff = pool_alloc(c.pool_cig, (uint64_t)rst.n_cigar * 4);
+		else if (ck[0] + need > ck[1]) {
+			const unsigned long long get = need > CIG_CHUNK_BYTES? need : CIG_CHUNK_BYTES;
+			const int64_t off = pool_alloc(c.pool_cig, get);
+			if (off < 0) ck[0] = ck[1] = 0;
+			else ck[0] = (unsigned long long)off, ck[1] = (unsigned long long)off + get;
+			coff = off;
+		}
+		if (ck && coff >= 0) coff = (int64_t)ck[0], ck[0] += need;
+#else
+		coff = pool_alloc(c.pool_cig, (uint64_t)rst.n_cigar * 4);
+#endif
+	}
 	coff = (int64_t)warp_bcast_u64((uint64_t)coff, 0);
 	if (coff < 0) return MGB_E_POOL;
 	uint32_t *dst = (uint32_t*)((char*)c.cig + coff);

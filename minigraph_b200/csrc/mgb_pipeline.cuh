@@ -52,10 +52,26 @@ MG_HD inline unsigned long long prof_clock()
 	return 0;
 #endif
 }
+// The counters of a launch are summed per block in shared memory and reach the global ones once, when the block ends
+// (stage_loop): a gap alignment job bumps four of them, and 17 million jobs per step doing that with global atomics is
+// 70 million reductions on one 32-byte sector of L2, which serialises them.
+#if defined(__CUDACC__)
+MG_D inline unsigned long long *prof_block() { __shared__ unsigned long long s_prof[PROF_N]; return s_prof; }
+MG_D inline bool prof_is_max(int slot) { return slot == PROF_WFA_MAX_CYC || slot == PROF_GWFA_MAX_CYC || slot == PROF_GC_DP_MAX_CYC; }
+MG_D inline void prof_block_begin() { if (threadIdx.x < PROF_N) prof_block()[threadIdx.x] = 0; __syncthreads(); }
+MG_D inline void prof_block_end(unsigned long long *prof)
+{
+	__syncthreads();
+	if (prof && threadIdx.x < PROF_N) {
+		const unsigned long long v = prof_block()[threadIdx.x];
+		if (v) { if (prof_is_max((int)threadIdx.x)) atomicMax(&prof[threadIdx.x], v); else atomicAdd(&prof[threadIdx.x], v); }
+	}
+}
+#endif
 MG_HD inline void prof_add(const PipeCtx &c, int slot, unsigned long long v)
 {
 #if MGB_ON_DEVICE
-	if (c.prof) atomicAdd(&c.prof[slot], v);
+	if (c.prof) atomicAdd(&prof_block()[slot], v);
 #else
 	if (c.prof) c.prof[slot] += v;
 #endif
@@ -63,7 +79,7 @@ MG_HD inline void prof_add(const PipeCtx &c, int slot, unsigned long long v)
 MG_HD inline void prof_max(const PipeCtx &c, int slot, unsigned long long v)
 {
 #if MGB_ON_DEVICE
-	if (c.prof) atomicMax(&c.prof[slot], v);
+	if (c.prof) atomicMax(&prof_block()[slot], v);
 #else
 	if (c.prof && c.prof[slot] < v) c.prof[slot] = v;
 #endif
