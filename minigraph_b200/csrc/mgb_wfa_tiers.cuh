@@ -44,7 +44,8 @@ MG_HD inline int32_t wf2_ld(const void *base, int32_t off)
 // time -- two cells in flight were slower (k_wfa_mid 103.9 -> 114.1), and so was a packed walk of two adjacent diagonals per lane
 // (word loads, VIMNMX.S16x2 maxima whose predicates are the traceback bits: 103.2 -> 115.7; per pair it executes as many instructions
 // as two cells, on half the lanes); tier 3 (ring in L2) keeps two cells in flight: eighteen loads before the first use
-// (k_wfa_big 108.5 -> 82.2 at 16 warps per SM; 86.5 at 20 warps / 96 registers, 102.4 at 24 / 80 with spills).
+// (k_wfa_big 108.5 -> 82.2 at 16 warps per SM; 86.5 at 20 warps / 96 registers, 102.4 at 24 / 80 with spills; three cells in
+// flight 80.4, four 87.6: the kernel is bound by what L2 delivers, not by the latency one warp sees).
 #define MGB_WF_CELL_LOAD(S, d_) \
 	int32_t h##S, e1##S, e2##S, f1##S, f2##S; \
 	uint8_t xz##S; \
