@@ -415,11 +415,28 @@ MG_HD inline int chain_rmq_fill_w(Arena &H, Arena &A, int max_dist, int max_dist
 	// Summaries of the available anchors in blocks of 32 consecutive indices: the smallest priority, how many hold it and one of
 	// them, and the span of query positions.  The outer query then looks at one summary per block and at the elements of the
 	// few blocks that straddle a border of the window, instead of at every anchor of the window.
+	// Where it pays (below), a block keeps TWO summaries, one for its anchors at or below the middle of the block's span of query positions and one for those
+	// above it (blk[2b], blk[2b+1]; ysplit[b] is that middle, known up front because the positions are).  Where two diagonals
+	// interleave in target order -- a read that wraps around a circular genome, a tandem duplication -- a block spans both, would
+	// straddle the border of nearly every query and be scanned element by element; its halves are narrow and answer from the summary.
 	RmqBlock *blk;
 	const int64_t n_blk = (n + 31) >> 5;
-	MGB_ALLOC_HOT(H, A, blk, RmqBlock, n_blk);
+	MGB_ALLOC_HOT(H, A, blk, RmqBlock, 2 * n_blk);
 	MGB_ALLOC_HOT(H, A, pri, double, n);
-	for (int64_t b = lane; b < n_blk; b += MGB_W) { RmqBlock e; e.best = 1e300, e.cnt = 0, e.j = -1, e.ymin = INT32_MAX, e.ymax = INT32_MIN; blk[b] = e; }
+	int32_t *ys, *ysplit; // query positions by themselves (the border scan below reads one 128-byte line per block instead of four)
+	MGB_ALLOC(A, ys, int32_t, n);
+	MGB_ALLOC(A, ysplit, int32_t, n_blk);
+	for (int64_t j = lane; j < n; j += MGB_W) ys[j] = (int32_t)a[j].y;
+	for (int64_t b = lane; b < 2 * n_blk; b += MGB_W) { RmqBlock e; e.best = 1e300, e.cnt = 0, e.j = -1, e.ymin = INT32_MAX, e.ymax = INT32_MIN; blk[b] = e; }
+	warp_sync();
+	int wide = 0; // does any block span more query positions than 32 anchors of one diagonal do?  If none does, one summary per block is enough
+	for (int64_t b = lane; b < n_blk; b += MGB_W) {
+		int32_t mn = INT32_MAX, mx = INT32_MIN;
+		for (int64_t j = b << 5; j < n && j < (b + 1) << 5; ++j) { const int32_t y = ys[j]; mn = y < mn? y : mn, mx = y > mx? y : mx; }
+		ysplit[b] = (int32_t)(((int64_t)mn + mx) >> 1);
+		wide |= (int64_t)mx - mn > 2048;
+	}
+	const int hs = warp_any(wide)? 1 : 0; // summaries per block: 1 << hs; half-block hb belongs to block hb >> hs
 	int32_t nK = 0;
 	int64_t i, i0 = 0, st = 0, st_inner = 0;
 	for (i = lane; i < n; i += MGB_W) t[i] = 0;
@@ -435,7 +452,7 @@ MG_HD inline int chain_rmq_fill_w(Arena &H, Arena &A, int max_dist, int max_dist
 				const uint64_t xj = a[j].x, yj = a[j].y;
 				if (lane == 0) {
 					const double pj = -(f[j] + 0.5 * pen_gap * ((int32_t)xj + (int32_t)yj));
-					RmqBlock &B = blk[j >> 5];
+					RmqBlock &B = blk[((j >> 5) << hs) + (hs & (int)((int32_t)yj > ysplit[j >> 5]))];
 					pri[j] = pj;
 					if (pj < B.best) B.best = pj, B.cnt = 1, B.j = (int32_t)j;
 					else if (pj == B.best) ++B.cnt;
@@ -497,11 +514,11 @@ MG_HD inline int chain_rmq_fill_w(Arena &H, Arena &A, int max_dist, int max_dist
 			const int64_t hi_j = st < i0? i0 : st; // window [st, i0)
 			double best = 1e300;
 			int32_t best_j = -1, n_best = 0;
-			for (int64_t b0 = st >> 5; (b0 << 5) < hi_j; b0 += MGB_W) {
-				const int64_t b = b0 + lane;
-				int kind = 0; // 0: nothing of this block qualifies, 1: all of it does (the summary answers), 2: look at its elements
+			for (int64_t b0 = (st >> 5) << hs; ((b0 >> hs) << 5) < hi_j; b0 += MGB_W) { // one (half-)block per lane
+				const int64_t hb = b0 + lane, b = hb >> hs;
+				int kind = 0; // 0: nothing of this half-block qualifies, 1: all of it does (the summary answers), 2: look at its elements
 				if ((b << 5) < hi_j) {
-					const RmqBlock B = blk[b];
+					const RmqBlock B = blk[hb];
 					if (B.cnt > 0 && B.ymax > yi - max_dist && B.ymin <= yi - 1 && !(B.ymin == yi - 1 && b != 0))
 						kind = (b << 5) >= st && B.ymin > yi - max_dist && B.ymax < yi - 1? 1 : 2;
 					if (kind == 1) {
@@ -510,17 +527,37 @@ MG_HD inline int chain_rmq_fill_w(Arena &H, Arena &A, int max_dist, int max_dist
 					}
 				}
 				uint32_t scan = warp_ballot(kind == 2);
-				while (scan) { // a block on a border of the window: its elements, one per lane
-					const int64_t j0 = (b0 + ctz32(scan)) << 5;
-					scan &= scan - 1;
-					for (int64_t j = j0 + lane; j < j0 + 32; j += MGB_W) {
-						if (j < st || j >= hi_j) continue;
-						const int32_t yj = (int32_t)a[j].y;
-						if (!(yj > yi - max_dist)) continue;
-						if (!(yj < yi - 1 || (yj == yi - 1 && j == 0))) continue;
-						const double pj = pri[j];
-						if (pj < best) best = pj, best_j = (int32_t)j, n_best = 1;
-						else if (pj == best) ++n_best;
+				while (scan) { // half-blocks on a border of the window: their elements, one per lane, four at a time (eight loads in flight per lane)
+					int32_t j0s[4];
+					int nb = 0;
+					int32_t halves = 0; // bit u: the upper half of block u is the one to look at
+					while (scan && nb < 4) { const int64_t h = b0 + ctz32(scan); halves |= (int32_t)(h & hs) << nb, j0s[nb++] = (int32_t)((h >> hs) << 5); scan &= scan - 1; }
+					for (int32_t off = lane; off < 32; off += MGB_W) {
+						int32_t yv[4];
+						double pv[4];
+						uint32_t okm = 0;
+#if MGB_ON_DEVICE
+#pragma unroll
+#endif
+						for (int u = 0; u < 4; ++u) {
+							const int32_t j = (u < nb? j0s[u] : j0s[0]) + off;
+							const int ok = u < nb && j >= st && j < hi_j;
+							okm |= (uint32_t)ok << u;
+							yv[u] = ok? ys[j] : 0, pv[u] = ok? pri[j] : 1e300;
+						}
+#if MGB_ON_DEVICE
+#pragma unroll
+#endif
+						for (int u = 0; u < 4; ++u) {
+							if (!(okm >> u & 1)) continue;
+							const int32_t j = j0s[u] + off;
+							const int32_t yj = yv[u];
+							if (hs && (yj > ysplit[j >> 5]) != (halves >> u & 1)) continue; // an anchor of the block's other half
+							if (!(yj > yi - max_dist)) continue;
+							if (!(yj < yi - 1 || (yj == yi - 1 && j == 0))) continue;
+							if (pv[u] < best) best = pv[u], best_j = j, n_best = 1;
+							else if (pv[u] == best) ++n_best;
+						}
 					}
 				}
 			}
