@@ -524,11 +524,18 @@ MG_HD inline void small_sort_stable_w(T *a, int64_t n, KeyFn key, int lane)
 // radix_sort_exact() entered by all lanes of a warp.  Only the cycle-leader permutation is inherently sequential (its
 // tie order is what has to be reproduced); it runs on lane 0 over the non-empty bins.  The digit census, the bin
 // offsets, the child ranges and the insertion sorts of the small bins are spread over the lanes.
+// The permutation as a walk over DIGITS: every read of the cycle-leader loop is of an element still at its original place (a bin's
+// frontier only moves forward and the home slot of a chain is not read before the chain ends), so where each element ends up
+// follows from the digits alone.  Lane 0 walks a byte per element (kept in the hot arena A, on chip where the caller has the room)
+// and notes the destinations; all lanes then move the elements through a copy in the arena `cold`.  Same moves, same result; the
+// dependent load of the walk is a byte that stays in L1 / shared memory instead of a 16-byte element in L2.  Asked for by the caller
+// (`walk`): it pays where the elements are in global memory (the seeds of k_seed), not where the list is already on chip.
 template<typename T, typename KeyFn>
-MG_HD inline int radix_sort_exact_w(Arena &A, T *a, int64_t n, int sizeof_key, KeyFn key, int lane)
+MG_HD inline int radix_sort_exact_w(Arena &A, T *a, int64_t n, int sizeof_key, KeyFn key, int lane, Arena *cold = 0, bool walk = false)
 {
-	const int MIN_SIZE = 64;
+	const int MIN_SIZE = 64, MIN_WALK = 192; // ranges shorter than MIN_WALK are permuted in place as before
 	if (n <= MIN_SIZE) { small_sort_stable_w(a, n, key, lane); return 0; }
+	Arena &C = cold? *cold : A;
 	uint64_t mark = A.top;
 	RsRange *stack;
 	int64_t m_stack = n / MIN_SIZE + 4; // pending ranges are disjoint and each holds more than MIN_SIZE elements
@@ -553,7 +560,24 @@ MG_HD inline int radix_sort_exact_w(Arena &A, T *a, int64_t n, int sizeof_key, K
 		if (((diff >> s) & 0xff) == 0) continue;
 		for (int k = lane; k < 256; k += MGB_W) bb[k] = 0;
 		warp_sync();
-		for (int32_t i = r.beg + lane; i < r.end; i += MGB_W) lane_atomic_inc(&bb[(key(a[i]) >> s) & 0xff]);
+		// scratch of the digit walk: digits (hot if there is room), destinations and the copy of the range (cold)
+		const int32_t n_r = r.end - r.beg;
+		const uint64_t mark_hot = A.top, mark_cold = C.top;
+		uint8_t *dg = 0;
+		int32_t *dst = 0;
+		T *cp = 0;
+		if (walk && n_r >= MIN_WALK) {
+			dg = (uint8_t*)arena_alloc(A, (uint64_t)n_r);
+			if (dg == 0 && &C != &A) dg = (uint8_t*)arena_alloc(C, (uint64_t)n_r);
+			dst = (int32_t*)arena_alloc(C, (uint64_t)n_r * sizeof(int32_t));
+			cp = (T*)arena_alloc(C, (uint64_t)n_r * sizeof(T));
+			if (dg == 0 || dst == 0 || cp == 0) dg = 0; // no room: in place
+		}
+		for (int32_t i = r.beg + lane; i < r.end; i += MGB_W) {
+			const int d = (int)((key(a[i]) >> s) & 0xff);
+			lane_atomic_inc(&bb[d]);
+			if (dg) dg[i - r.beg] = (uint8_t)d, cp[i - r.beg] = a[i];
+		}
 		warp_sync();
 		int32_t acc = r.beg, n_nz = 0;
 		for (int k0 = 0; k0 < 256; k0 += MGB_W) {
@@ -568,7 +592,30 @@ MG_HD inline int radix_sort_exact_w(Arena &A, T *a, int64_t n, int sizeof_key, K
 			acc += warp_bcast_i32(incl, MGB_W - 1);
 		}
 		warp_sync();
-		if (lane == 0) {
+		if (dg) {
+			if (lane == 0) {
+				const uint8_t *dgr = dg - r.beg;
+				int32_t *dstr = dst - r.beg;
+				for (int z = 0; z < n_nz;) { // the walk of the cycle-leader permutation over the digits
+					const int k = nz[z];
+					if (bb[k] != be[k]) {
+						int32_t cur = bb[k];
+						int l = dgr[cur];
+						if (l != k) {
+							do { // the element held (cur) goes to the frontier of its bin, whose occupant is held next
+								const int32_t nxt = bb[l];
+								dstr[cur] = nxt, bb[l] = nxt + 1;
+								cur = nxt, l = dgr[cur];
+							} while (l != k);
+							dstr[cur] = bb[k]++;
+						} else dstr[cur] = cur, ++bb[k];
+					} else ++z;
+				}
+			}
+			warp_sync();
+			for (int32_t i = lane; i < n_r; i += MGB_W) a[dst[i]] = cp[i];
+			A.top = mark_hot, C.top = mark_cold;
+		} else if (lane == 0) {
 			for (int z = 0; z < n_nz;) { // cycle-leader permutation (empty bins have nothing to do)
 				const int k = nz[z];
 				if (bb[k] != be[k]) {
@@ -604,6 +651,6 @@ MG_HD inline int radix_sort_exact_w(Arena &A, T *a, int64_t n, int sizeof_key, K
 	return 0;
 }
 
-MG_HD inline int radix_sort_128x_w(Arena &A, u128 *a, int64_t n, int lane) { return radix_sort_exact_w(A, a, n, 8, KeyX128(), lane); }
+MG_HD inline int radix_sort_128x_w(Arena &A, u128 *a, int64_t n, int lane, Arena *cold = 0, bool walk = false) { return radix_sort_exact_w(A, a, n, 8, KeyX128(), lane, cold, walk); }
 
 } // namespace mgb

@@ -154,7 +154,7 @@ MG_HD inline int chain_finish_w(Arena &H, Arena &A, int64_t n, const int32_t *f,
 	warp_sync();
 	{
 		Arena &S = H.cap - H.top >= (uint64_t)n_z / 4 + 3400? H : A; // range stack + three 1 KB bin tables
-		MGB_TRY(radix_sort_exact_w(S, z, n_z, 8, KeyHi32(), lane));
+		MGB_TRY(radix_sort_exact_w(S, z, n_z, 8, KeyHi32(), lane)); // (in place: the list is on chip)
 	}
 	int32_t n_u = 0, n_v = 0;
 	if (lane == 0) { // reference: lchain.c:27-77

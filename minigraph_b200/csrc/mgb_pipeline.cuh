@@ -173,7 +173,7 @@ MG_HD inline int stage_seed(const PipeCtx &c, int rid, Arena &A, int lane, int32
 			Arena R;
 			arena_init(R, smem, smem? (uint64_t)SKETCH_SMEM_BYTES : 0);
 			Arena &S = smem && R.cap >= (uint64_t)n_a / 4 + 3400? R : A;
-			MGB_TRY(radix_sort_128x_w(S, a, n_a, lane));
+			MGB_TRY(radix_sort_128x_w(S, a, n_a, lane, &A, true)); // digit walk: k_seed 31.9 -> 24.5 ms per 40 000 reads
 		}
 	}
 	if (lane == 0) prof_add(c, PROF_SEED_SKETCH_CYC, t1 - t0), prof_add(c, PROF_SEED_MATCH_CYC, t2 - t1), prof_add(c, PROF_SEED_SORT_CYC, prof_clock() - t2);
@@ -315,7 +315,7 @@ MG_HD inline int chain_pass(const PipeCtx &c, int rid, Arena &H, Arena &A, u128 
 	} else {
 		{ // back into target order; the sort's range stack and bin tables on chip when the slice has the room (it is empty but for the anchors)
 			Arena &S = H.cap - H.top >= (uint64_t)n_a / 4 + 3400? H : A;
-			MGB_TRY(radix_sort_128x_w(S, a, n_a, lane));
+			MGB_TRY(radix_sort_128x_w(S, a, n_a, lane, 0, false)); // (in place: with the digit walk the chaining kernels measured 2 ms per 40 000 reads slower)
 		}
 		MGB_TRY(chain_rmq_w(H, A, o.max_gap, o.max_gap_pre, o.bw_long, o.max_lc_skip, o.rmq_size_cap, o.min_lc_cnt, o.min_lc_score,
 							o.chn_pen_gap, o.chn_pen_skip, n_a, a, &n_lc, &u, &n_a_new, lane));
