@@ -1900,4 +1900,30 @@ extern "C" int mgb_test_wfa(const char *ts, int tl, const char *qs, int ql, int6
 	try { return test_wfa_impl(ts, tl, qs, ql, max_iter, step, cigar, cap, score); } catch (const MgbError &e) { return e.code; }
 }
 
+#ifdef MGB_HOSTSIM
+// TEST INFRASTRUCTURE (simulator builds only): the warp-wide exact radix sort on an array of 16-byte records, in place or with the digit
+// walk, with `hot_bytes` of "on-chip" scratch (0: everything in the arena).  tests/test_hostsim32_lanes.py holds it against klib's.
+extern "C" int mgb_test_radix128(u128 *a, int64_t n, int walk, int hot_bytes)
+{
+	std::vector<char> cold((size_t)n * 64 + (1 << 20)), hot((size_t)(hot_bytes > 0? hot_bytes : 16));
+	int rc_all = 0;
+#if MGB_W > 1
+	int rcs[MGB_W];
+	sim::run_warp(MGB_W, [&](int lane) {
+		Arena A, H;
+		arena_init(A, cold.data(), cold.size());
+		arena_init(H, hot.data(), hot_bytes > 0? (uint64_t)hot_bytes : 0);
+		rcs[lane] = radix_sort_128x_w(hot_bytes > 0? H : A, a, n, lane, &A, walk != 0);
+	});
+	for (int l = 0; l < MGB_W; ++l) if (rcs[l] != rcs[0]) return -99; else rc_all = rcs[0];
+#else
+	Arena A, H;
+	arena_init(A, cold.data(), cold.size());
+	arena_init(H, hot.data(), hot_bytes > 0? (uint64_t)hot_bytes : 0);
+	rc_all = radix_sort_128x_w(hot_bytes > 0? H : A, a, n, 0, &A, walk != 0);
+#endif
+	return rc_all;
+}
+#endif
+
 extern "C" void mgb_get_stats(const mg_idx_t *gi, mgb_stats_t *st) { *st = t_has_stats? t_last_stats : model_of(gi)->stats; } // the calling thread's last batch

@@ -352,6 +352,43 @@ def case_wfa_band_shrinks(lib, n_cases=48, seed=99):
     assert n_shrunk >= n_cases // 2
 
 
+def case_radix_exact(lib, n_cases=60, seed=17):
+    """the warp-wide replay of klib's unstable radix sort (mgb_common.cuh radix_sort_exact_w), in place and as a walk over digits, with
+    scratch on "chip" and in the arena: the same order as radix_sort_128x() of the reference, ties included (ksort.h:112-162) --
+    few distinct keys (long runs of ties), keys that differ in one byte only (one level), bins above 64 elements (recursion), skewed bins"""
+    import ctypes as C
+    import random
+    from minigraph_b200 import capi
+    ref = T.load_ref()
+    ref.radix_sort_128x.restype = None
+    ref.radix_sort_128x.argtypes = [C.POINTER(capi.mg128_t), C.POINTER(capi.mg128_t)]
+    lib.mgb_test_radix128.restype = C.c_int
+    lib.mgb_test_radix128.argtypes = [C.POINTER(capi.mg128_t), C.c_int64, C.c_int, C.c_int]
+    rng = random.Random(seed)
+    for it in range(n_cases):
+        n = rng.choice([65, 191, 192, 193, 700, 1100, 3000, 9000])
+        nk = rng.choice([2, 7, 300, 5000, 2 ** 40])
+        sh = rng.choice([0, 8, 16, 33])
+        base = rng.randrange(2 ** 20) << 40
+        if it % 5 == 4:  # one heavy bin and a sprinkle of others
+            keys = [base + ((rng.randrange(nk) << sh) if rng.random() < 0.1 else (3 << sh)) for _ in range(n)]
+        else:
+            keys = [base + (rng.randrange(nk) << sh) for _ in range(n)]
+        want = (capi.mg128_t * n)()
+        for i, x in enumerate(keys):
+            want[i].x, want[i].y = x, i
+        ref.radix_sort_128x(want, C.cast(C.byref(want, C.sizeof(want)), C.POINTER(capi.mg128_t)))
+        for walk, hot in ((0, 0), (1, 0), (1, 16384), (1, n // 4 + 3400), (0, 16384)):  # (n/4 + 3400: what the callers ask of the on-chip slice; the digits then go to the arena)
+            got = (capi.mg128_t * n)()
+            for i, x in enumerate(keys):
+                got[i].x, got[i].y = x, i
+            rc = lib.mgb_test_radix128(got, n, walk, hot)
+            assert rc == 0, (it, n, walk, hot, rc)
+            bad = next((i for i in range(n) if got[i].y != want[i].y or got[i].x != want[i].x), None)
+            assert bad is None, "case %d (n=%d, %d keys << %d, walk=%d, hot=%d): position %d holds element %d, the reference has %d" % (
+                it, n, nk, sh, walk, hot, bad, got[bad].y, want[bad].y)
+
+
 def case_wfa_tiers(lib, workdir, n_struct=60):
     """the gap alignment tiers (mgb_wfa_tiers.cuh: slices that hold -inf outside their range instead of bounds checks).  Same GAF
     for the golden cases (lr and asm presets, both on-chip tiers busy), same mg_gchains_t fields as the reference on an SV graph,

@@ -78,3 +78,7 @@ def test_graph_chaining_label_table(lib, workdir):
 def test_wfa_tiers_and_fallback(lib):
     cases.case_wfa_fallback(lib)
     cases.case_wfa_band_shrinks(lib)
+
+
+def test_exact_radix_sort_in_place_and_by_digit_walk(lib):
+    cases.case_radix_exact(lib)

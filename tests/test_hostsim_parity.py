@@ -153,3 +153,7 @@ def test_gaf_batch_writer_reuses_buffer(lib, workdir):
     lib.mgb_free_batch(n, gcs)
     assert all(not gcs[i] for i in range(n))
     lib.mg_idx_destroy(gi)
+
+
+def test_exact_radix_sort_in_place_and_by_digit_walk(lib):
+    cases.case_radix_exact(lib)
