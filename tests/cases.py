@@ -431,6 +431,33 @@ def case_gchain_labels(lib, workdir, n_reads=150, graph_len=1000000):
         lib.mgb_set_param(b"lab_cache", 1)
 
 
+def case_tandem_diagonals(lib, workdir, n_reads=48, seed=29):
+    """RMQ chaining where two diagonals interleave in target order: a linear reference with tandem duplications (copies 700 bp and
+    3 kb apart: narrow and wide blocks of the outer query's summaries, mgb_lchain.cuh chain_rmq_fill_w) and a circular one whose reads
+    wrap around; asm preset (RMQ chaining of every read) and lr (the long-join rescue); every field against the reference"""
+    import random
+    rng = random.Random(seed)
+
+    def rnd(n):
+        return "".join(rng.choice("ACGT") for _ in range(n))
+    d1, d2 = rnd(700), rnd(3000)
+    ref = rnd(6000) + d1 + d1 + d1 + rnd(5000) + d2 + d2 + rnd(7000) + d1 + rnd(4000)
+    lin = os.path.join(workdir, "tandem.fa")
+    with open(lin, "w") as f:
+        f.write(">tandem\n%s\n" % ref)
+    for gfa, circular, tag in ((lin, False, "lin"), (os.path.join(T.FIX, "MT-human.fa"), True, "circ")):
+        for preset, err, rl in (("asm", "hifi", 18000), ("lr", "ont", 11000)):
+            reads = os.path.join(workdir, "tandem.%s.%s.fa" % (tag, preset))
+            T.sim_reads(gfa, reads, n_reads, rl, err, seed + len(tag) + len(preset), circular=circular)
+            names, seqs = T.read_fasta(reads)
+            want, _ = T.map_with_ref(gfa, names, seqs, preset)
+            got, _, _ = T.map_with_engine(lib, gfa, names, seqs, preset)
+            assert sum(1 for r in want if r and r["n_gc"] > 0) >= n_reads // 2, (tag, preset)
+            for i, (a, b) in enumerate(zip(want, got)):
+                d = T.diff_results(a, b)
+                assert d is None, "%s %s read %d: %s" % (tag, preset, i, d)
+
+
 def case_chain_skip(lib, workdir, n_reads=40):
     """max_lc_skip far below its default (25): the early stop of the chaining DP and of the RMQ walk -- "too many candidates in
     a row that are already on a better chain" (lchain.c:185-190, 336-343) -- fires all the time instead of almost never;

@@ -157,3 +157,7 @@ def test_gaf_batch_writer_reuses_buffer(lib, workdir):
 
 def test_exact_radix_sort_in_place_and_by_digit_walk(lib):
     cases.case_radix_exact(lib)
+
+
+def test_rmq_chaining_with_interleaved_diagonals(lib, workdir):
+    cases.case_tandem_diagonals(lib, workdir)
