@@ -760,7 +760,6 @@ MG_HD inline int stage_gchain_gen_head(const PipeCtx &c, ReadOut *routs, int rid
 	uint64_t sz = off_a + align8((uint64_t)gs.n_a * sizeof(u128));
 	int64_t boff = pool_alloc(c.pool_out, sz);
 	if (boff < 0) return MGB_E_POOL;
-	char *blob = c.out + boff;
 	for (int32_t i = 0; i < gs.n_gc; ++i) {
 		GChain *gc = &gs.gc[i];
 		gc->has_cigar = 0, gc->n_cigar = 0, gc->cigar_off = gc->ds_off = gc->dsoff_off = 0, gc->ds_len = gc->n_dsoff = 0, gc->plan_off = 0, gc->n_plan = 0;
