@@ -124,8 +124,3 @@ def test_gap_alignment_tiers(lib, workdir):
 def test_wfa_iteration_cap_fallback(lib):
     cases.case_wfa_fallback(lib, n_cases=10)
     cases.case_wfa_divergent(lib)
-
-
-@pytest.mark.skipif(not T.have_ref(), reason="oracle/_ref not shipped")
-def test_rmq_chaining_with_interleaved_diagonals(lib, workdir):
-    cases.case_tandem_diagonals(lib, workdir, n_reads=200)
